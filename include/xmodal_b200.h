@@ -1,0 +1,194 @@
+/*
+ * xmodal_b200.h -- C ABI of the B200-native hot path of bacon205/Multimodal_eeg_fmri
+ * (paired EEG/fMRI cross-modal training step).
+ *
+ * The reference has no FFI layer: its hot path is `torch.nn` calls inside the module
+ * `forward`s.  Each entry point below replaces the ATen/oneDNN/cuDNN call
+ * the cited reference line makes; the Python modules in multimodal_eeg_fmri_b200/ (same class
+ * names, forward signatures and state_dict keys as the reference) bind these with ctypes --
+ * see INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (or int64 / int32 where stated), row-major;
+ *     the caller owns and allocates every buffer, including workspaces; nothing here
+ *     allocates, frees or synchronises; all work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*, e.g. torch.cuda.current_stream().cuda_stream).
+ *   - return value: XM_OK (0) or a negative XM_ERR_* code; xm_strerror() names it.
+ *   - "ld*" arguments are leading dimensions (row pitches) in ELEMENTS.  Tensors read through
+ *     TMA need 16-byte aligned bases and row pitches that are multiples of 4 elements.
+ *   - GEMM-shaped work runs on tcgen05 tensor cores in TF32 with fp32 accumulation;
+ *     reductions, norms, activations and the spectral path are fp32 (fp64 for the final
+ *     combination of batch statistics).
+ */
+#ifndef XMODAL_B200_H_
+#define XMODAL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XM_ABI_VERSION 1
+
+#define XM_OK 0
+#define XM_ERR_INVALID -1     /* bad argument (shape, alignment, null pointer) */
+#define XM_ERR_UNSUPPORTED -2 /* shape outside what the kernels implement */
+#define XM_ERR_LAUNCH -3      /* CUDA launch / driver error; see xm_last_cuda_error() */
+#define XM_ERR_NO_DRIVER -4   /* cuTensorMapEncodeTiled could not be resolved (no GPU driver) */
+
+#define XM_ACT_NONE 0
+#define XM_ACT_RELU 1
+#define XM_ACT_GELU 2 /* exact erf GELU, as nn.GELU() */
+
+int xm_abi_version(void);
+const char* xm_strerror(int code);
+int xm_last_cuda_error(void);
+
+/* ------------------------------------------------------------------ EEG preprocessing
+ * No reference implementation exists: vocabulary from EEG_CODE/config.py:34-36,
+ * PW layout from EEG_CODE/CrossModal_EEG_scr.ipynb cell 7:45-47.  Oracle: oracle/spectral.py. */
+
+/* Window index generation for `n_rec` recordings of `n_samples` samples each:
+ * n_win = (n_samples - win)/hop + 1 per recording; window g = r*n_win + w has
+ * starts[g] = w*hop, rec_ids[g] = r, labels[g] = rec_labels[r], subjects[g] = rec_subjects[r].
+ * All arrays int64 on the device.  rec_labels / rec_subjects may be NULL (outputs skipped). */
+int xm_window_index_i64(int64_t n_rec, int64_t n_samples, int64_t win, int64_t hop, const int64_t* rec_labels,
+                        const int64_t* rec_subjects, int64_t* starts, int64_t* rec_ids, int64_t* labels,
+                        int64_t* subjects, void* stream);
+
+/* Gather windows: rec (n_rec, C, n_samples) -> out (n_rec*n_win, C, ld_out) with the first `win`
+ * elements of every row valid.  round_tf32 != 0 rounds values to tf32 (feeds the conv GEMMs). */
+int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
+                         float* out, int64_t ld_out, int round_tf32, void* stream);
+
+/* Fused window gather + taper + real FFT (nfft = power of two in [64, 2048], >= win, zero padded) +
+ * one-sided PSD + band-power reduction.  power[g, c, b] = sum_{k in [band_bins[2b], band_bins[2b+1])}
+ * |X_k|^2 * s_k / (fs * sum(taper^2)) * (fs / nfft),  s_k = 2 except k = 0 and k = nfft/2.
+ * taper: (win) fp32 window coefficients (device); band_bins: (2*n_bands) int32 (device). */
+int xm_bandpower_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
+                     int64_t nfft, float fs, const float* taper, float taper_sumsq, const int32_t* band_bins,
+                     int n_bands, float* power, void* stream);
+
+/* normalize_modality (EEG_CODE/run_training_lite.py:48-51): out = (x - mean)/(std + eps) per item,
+ * population std, over `item_len` contiguous elements. */
+int xm_zscore_f32(const float* x, int64_t n_items, int64_t item_len, float eps, float* out, void* stream);
+
+/* fMRI ROI aggregation (fMRI_CODE/fmri_utils.py:140-147, agg_method='both'): x (B, TR, ROI) ->
+ * out (B, 2*ROI) = concat(mean over TR, population std over TR); NaN inputs count as 0. */
+int xm_roi_meanstd_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, void* stream);
+
+/* ------------------------------------------------------------------ dense projections (nn.Linear)
+ * fMRI_CODE/fmri_utils.py:27,31,45,49,66 ; bridge_utils.py:35,41,61,65 ; enhanced_models_v4.py:164 */
+
+/* y (M,N) = act(x (M,K) @ w (N,K)^T + bias).  splits > 1 splits K across CTAs through
+ * `workspace` (splits*M*N floats).  round_out rounds y to tf32. */
+int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int round_out, int splits, float* workspace,
+                      void* stream);
+/* dx (M,K) = dy (M,N) @ w (N,K) */
+int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
+                        int64_t ldw, int64_t lddx, int round_out, void* stream);
+/* dw (N,K) = dy (M,N)^T @ x (M,K); db (N) = column sums of dy (db may be NULL).
+ * workspace: splits*N*K floats when splits > 1. */
+int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
+                        int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, void* stream);
+
+/* ------------------------------------------------------------------ dense Conv1d ("same" padding, stride 1)
+ * EEG_CODE/enhanced_models_v4.py:128-144 ; EEG_CODE/crossmodal_v4_enhancements.py:822-834,854-866 */
+
+/* Repack w (Cout, Cin, taps) into wk (taps, Cout, ldk) and wt (taps, Cin, ldt), tf32-rounded,
+ * zero padded; ldk >= Cin, ldt >= Cout, both multiples of 4. */
+int xm_conv1d_pack_weight_f32(const float* w, int64_t Cout, int64_t Cin, int64_t taps, float* wk, int64_t ldk,
+                              float* wt, int64_t ldt, void* stream);
+/* y (B,Cout,T) = conv1d(x (B,Cin,T), w) + bias, pad = taps/2.  ldx/ldy: row pitch of a (b,c) row. */
+int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,
+                      int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy, int round_out,
+                      void* stream);
+/* dx (B,Cin,T) from dy (B,Cout,T) */
+int xm_conv1d_dgrad_f32(const float* dy, const float* wt, float* dx, int64_t B, int64_t Cin, int64_t Cout, int64_t T,
+                        int64_t taps, int64_t lddy, int64_t ldt, int64_t lddx, int round_out, void* stream);
+/* dw (Cout,Cin,taps), db (Cout) (db may be NULL).  workspace: xm_conv1d_wgrad_workspace() floats. */
+int64_t xm_conv1d_wgrad_workspace(int64_t B, int64_t Cin, int64_t Cout, int64_t taps);
+int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout,
+                        int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, void* stream);
+
+/* ------------------------------------------------------------------ normalisation + activation (+pool, +dropout)
+ * nn.BatchNorm1d (train mode) + nn.GELU/nn.ReLU + nn.MaxPool1d(2) + nn.Dropout chains of the encoders. */
+
+/* Batch statistics of y viewed as (B, C, T) with row pitch ldy (T = 1, ldy = 1 for (B, C) inputs):
+ * stats (2*C) = {mean[C], biased var[C]}; partials: 2*C*nsplit doubles of workspace, nsplit =
+ * xm_bn_nsplit(B, C, T).  When running_mean/var are non-NULL they are updated with `momentum`
+ * and the unbiased variance, as torch does.  count_scale: multiply the element count (SyncBN hook;
+ * pass 1). */
+int xm_bn_nsplit(int64_t B, int64_t C, int64_t T);
+int xm_bn_partial_stats_f32(const float* y, int64_t B, int64_t C, int64_t T, int64_t ldy, double* partials,
+                            void* stream);
+/* partials (nsplit, C, 2) doubles {sum, sumsq}; total_count = elements per channel behind them. */
+int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double total_count, float eps, float* mean,
+                         float* invstd, float* running_mean, float* running_var, float momentum, void* stream);
+/* out = drop(pool?(act(gamma*(y-mean)*invstd + beta))) ; pool: 0 none, 2 = MaxPool1d(2) over T.
+ * drop_p in [0,1): keep with prob 1-p, scale 1/(1-p); mask from (seed, element index).
+ * drop_before_pool selects Conv-BN-GELU-Drop-Pool (Lite) vs Conv-BN-GELU-Pool-Drop (v4) ordering.
+ * out has row pitch ldo and T_out = pool ? T/2 : T. */
+int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      float* out, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo, int act, int pool,
+                      float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream);
+/* Backward, pass 1: per-channel partial sums of dz and dz*xhat (dz = grad wrt the BN output).
+ * partials: (nsplit, C, 2) doubles. */
+int xm_bn_act_bwd_reduce_f32(const float* dout, const float* y, const float* mean, const float* invstd,
+                             const float* gamma, const float* beta, int64_t B, int64_t C, int64_t T, int64_t ldy,
+                             int64_t ldo, int act, int pool, float drop_p, uint64_t seed, int drop_before_pool,
+                             double* partials, void* stream);
+/* sums (2*C) floats = {sum dz, sum dz*xhat} from partials: also dgamma = sums[C..2C), dbeta = sums[0..C) */
+int xm_bn_bwd_finalize(const double* partials, int nsplit, int64_t C, float* dbeta, float* dgamma, void* stream);
+/* Backward, pass 2: dy = gamma*invstd*(dz - dbeta/count - xhat*dgamma/count) */
+int xm_bn_act_bwd_apply_f32(const float* dout, const float* y, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, const float* dbeta, const float* dgamma,
+                            double total_count, float* dy, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo,
+                            int act, int pool, float drop_p, uint64_t seed, int drop_before_pool, int round_out,
+                            void* stream);
+
+/* LayerNorm over the last dim + activation + dropout on (M, D) rows (bridge_utils.py:36-38,42-44,62-64).
+ * Saves mean/rstd (M each) for the backward. */
+int xm_ln_act_fwd_f32(const float* x, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
+                      int64_t M, int64_t D, float eps, int act, float drop_p, uint64_t seed, void* stream);
+/* dx (M,D); dgamma/dbeta partials (nblk, D) reduced by xm_colsum_f32. nblk = xm_ln_nblk(M). */
+int xm_ln_nblk(int64_t M);
+int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, float* dx, float* dgamma_part, float* dbeta_part, int64_t M, int64_t D,
+                      int act, float drop_p, uint64_t seed, void* stream);
+
+/* out (N) = column sums of x (M, N) (bias gradients, partial reductions). */
+int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream);
+/* Mean over the last dim: x (R, T) pitch ldx -> out (R) ; and its backward (broadcast / T). */
+int xm_rowmean_f32(const float* x, int64_t R, int64_t T, int64_t ldx, float* out, void* stream);
+int xm_rowmean_bwd_f32(const float* dout, int64_t R, int64_t T, int64_t lddx, float* dx, void* stream);
+
+/* ------------------------------------------------------------------ similarity + symmetric InfoNCE
+ * No reference implementation; embeddings are the outputs of
+ * bridge_utils.py:71-72.  Oracle: oracle/infonce.py. */
+
+/* xn = x / max(||x||_2, eps) per row (F.normalize), tf32-rounded; inv_norm (M) saved. */
+int xm_l2norm_fwd_f32(const float* x, float* xn, float* inv_norm, int64_t M, int64_t D, float eps, void* stream);
+/* dx = (dxn - xn * <xn, dxn>) * inv_norm */
+int xm_l2norm_bwd_f32(const float* dxn, const float* xn, const float* inv_norm, float* dx, int64_t M, int64_t D,
+                      void* stream);
+/* S (Ml, Ng) = a (Ml, D) @ b (Ng, D)^T * inv_tau, materialised (bridge_utils.similarity_matrix). */
+int xm_similarity_f32(const float* a, const float* b, float* S, int64_t Ml, int64_t Ng, int64_t D, float inv_tau,
+                      void* stream);
+/* Row-wise logsumexp of S = a @ b^T * inv_tau without materialising S:
+ * lse (Ml) ; diag (Ml) = S[i, i + diag_off].  Rows of a and b must be unit-norm (|S| <= inv_tau).
+ * workspace: Ml * ceil(Ng/ xm_infonce_tile_n()) floats. */
+int xm_infonce_tile_n(void);
+int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D,
+                       float inv_tau, int64_t diag_off, float* workspace, void* stream);
+/* G (Ml, Ng) = coef * (exp(S - lse_row[i]) + exp(S - lse_col[j]) - 2*[j == i + diag_off]) */
+int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
+                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMODAL_B200_H_ */

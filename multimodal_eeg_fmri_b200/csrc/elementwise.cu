@@ -1,0 +1,620 @@
+// HBM-bound kernels of the paired step: fMRI ROI aggregation, z-scoring, train-mode
+// BatchNorm (+GELU/ReLU, +MaxPool1d(2), +dropout) forward/backward on (B, C, T) activations,
+// LayerNorm(+act, +dropout) on (M, D) rows, L2 row normalisation, small reductions.
+// Layouts are the reference's own (NCW / row-major fp32); every kernel is a streaming pass
+// with coalesced (128-bit where alignment allows) accesses and fp32 math; batch statistics
+// are combined in fp64.
+#include "xm_common.cuh"
+
+namespace xm {
+
+static int grid_rows(long long rows) { return (int)(rows < 1 ? 1 : (rows > 2147483647ll ? 2147483647ll : rows)); }
+
+// ------------------------------------------------------------------ block reduce helpers
+template <typename T>
+XM_DEVICE T block_sum(T v, T* sm) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  T r = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : (T)0;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) sm[0] = r;
+  __syncthreads();
+  return sm[0];
+}
+
+// ------------------------------------------------------------------ fMRI ROI mean/std over TR
+// fMRI_CODE/fmri_utils.py:140-147: nan_to_num then concat(mean(axis=0), std(axis=0)) (ddof=0).
+__global__ void roi_meanstd_kernel(const float* __restrict__ x, long long TR, long long ROI, float* __restrict__ out) {
+  const long long b = blockIdx.y;
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= ROI) return;
+  const float* col = x + b * TR * ROI + r;
+  float s = 0.f;
+  for (long long t = 0; t < TR; ++t) {
+    float v = col[t * ROI];
+    s += (v != v) ? 0.f : v;
+  }
+  const float mean = s / (float)TR;
+  float q = 0.f;
+  for (long long t = 0; t < TR; ++t) {
+    float v = col[t * ROI];
+    v = (v != v) ? 0.f : v;
+    const float d = v - mean;
+    q += d * d;
+  }
+  out[b * 2 * ROI + r] = mean;
+  out[b * 2 * ROI + ROI + r] = sqrtf(q / (float)TR);
+}
+
+// ------------------------------------------------------------------ per-item z-score
+// EEG_CODE/run_training_lite.py:48-51
+__global__ void zscore_kernel(const float* __restrict__ x, long long len, float eps, float* __restrict__ out) {
+  __shared__ double smd[32];
+  const float* xi = x + blockIdx.x * len;
+  float* oi = out + blockIdx.x * len;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) s += (double)xi[i];
+  const double mean = block_sum(s, smd) / (double)len;
+  double q = 0.0;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+    const double d = (double)xi[i] - mean;
+    q += d * d;
+  }
+  const double var = block_sum(q, smd) / (double)len;
+  const float fmean = (float)mean;
+  const float inv = 1.0f / ((float)sqrt(var) + eps);
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) oi[i] = (xi[i] - fmean) * inv;
+}
+
+// ------------------------------------------------------------------ BatchNorm statistics
+// grid (C, nsplit): block (c, s) reduces samples b = s, s+nsplit, ... of channel c.
+__global__ void bn_partial_stats_kernel(const float* __restrict__ y, long long B, int C, long long T, long long ld,
+                                        double* __restrict__ partials) {
+  __shared__ double smd[32];
+  const int c = blockIdx.x, s = blockIdx.y, ns = gridDim.y;
+  double sum = 0.0, sq = 0.0;
+  for (long long b = s; b < B; b += ns) {
+    const float* row = y + (b * C + c) * ld;
+    float ps = 0.f, pq = 0.f;
+    for (long long t = threadIdx.x; t < T; t += blockDim.x) {
+      const float v = row[t];
+      ps += v;
+      pq += v * v;
+    }
+    sum += (double)ps;
+    sq += (double)pq;
+  }
+  sum = block_sum(sum, smd);
+  sq = block_sum(sq, smd);
+  if (threadIdx.x == 0) {
+    partials[((long long)s * C + c) * 2 + 0] = sum;
+    partials[((long long)s * C + c) * 2 + 1] = sq;
+  }
+}
+
+__global__ void bn_finalize_stats_kernel(const double* __restrict__ partials, int nsplit, int C, double n, float eps,
+                                         float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
+                                         float* running_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < nsplit; ++i) {
+    s += partials[((long long)i * C + c) * 2 + 0];
+    q += partials[((long long)i * C + c) * 2 + 1];
+  }
+  const double mu = s / n;
+  double var = q / n - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mu;
+  if (running_var) {
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ------------------------------------------------------------------ BN + act (+pool, +dropout)
+struct BnActArgs {
+  const float* y;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  const float* beta;
+  long long B, T, ldy, ldo;
+  int C, act, pool, drop_before_pool, round_out;
+  float drop_scale;       // 1/(1-p), 1 when p == 0
+  uint32_t drop_thresh;   // p * 2^32, 0 when p == 0
+  uint64_t seed;
+};
+
+XM_DEVICE float drop_mul(const BnActArgs& a, long long idx) {
+  if (a.drop_thresh == 0u) return 1.0f;
+  return dropout_keep((uint64_t)idx, a.seed, a.drop_thresh) ? a.drop_scale : 0.0f;
+}
+
+// one block per (b, c) row
+__global__ void bn_act_fwd_kernel(const BnActArgs a, float* __restrict__ out) {
+  const long long row = blockIdx.x;
+  const int c = (int)(row % a.C);
+  const float mu = a.mean[c], is = a.invstd[c], g = a.gamma[c], bt = a.beta[c];
+  const float sc = g * is, sh = bt - mu * sc;
+  const float* yr = a.y + row * a.ldy;
+  float* orow = out + row * a.ldo;
+  if (a.pool == 2) {
+    const long long To = a.T / 2;
+    for (long long t = threadIdx.x; t < To; t += blockDim.x) {
+      const float2 v = *reinterpret_cast<const float2*>(yr + 2 * t);  // ldy % 2 == 0 checked on the host
+      float a0 = apply_act(v.x * sc + sh, a.act);
+      float a1 = apply_act(v.y * sc + sh, a.act);
+      float o;
+      if (a.drop_before_pool) {
+        a0 *= drop_mul(a, row * a.T + 2 * t);
+        a1 *= drop_mul(a, row * a.T + 2 * t + 1);
+        o = fmaxf(a0, a1);
+      } else {
+        o = fmaxf(a0, a1) * drop_mul(a, row * To + t);
+      }
+      orow[t] = a.round_out ? round_tf32(o) : o;
+    }
+  } else {
+    for (long long t = threadIdx.x; t < a.T; t += blockDim.x) {
+      float o = apply_act(yr[t] * sc + sh, a.act) * drop_mul(a, row * a.T + t);
+      orow[t] = a.round_out ? round_tf32(o) : o;
+    }
+  }
+}
+
+// dz (gradient wrt the BN output z = gamma*xhat + beta) for pre-pool element t of `row`.
+// Recomputes the activation / pool argmax / dropout mask instead of storing them.
+XM_DEVICE void bn_act_dz_pair(const BnActArgs& a, const float* __restrict__ dout_row, const float* __restrict__ yr,
+                              long long row, long long tp, float sc, float sh, float& dz0, float& dz1) {
+  // pool == 2: handles pre-pool elements (2tp, 2tp+1) fed by dout[tp]
+  const float2 v = *reinterpret_cast<const float2*>(yr + 2 * tp);
+  const float z0 = v.x * sc + sh, z1 = v.y * sc + sh;
+  float a0 = apply_act(z0, a.act), a1 = apply_act(z1, a.act);
+  const long long To = a.T / 2;
+  float g = dout_row[tp];
+  float m0 = 1.f, m1 = 1.f;
+  if (a.drop_before_pool) {
+    m0 = drop_mul(a, row * a.T + 2 * tp);
+    m1 = drop_mul(a, row * a.T + 2 * tp + 1);
+    a0 *= m0;
+    a1 *= m1;
+  } else {
+    g *= drop_mul(a, row * To + tp);
+  }
+  const bool first = a0 >= a1;  // ties -> first element, as torch max_pool1d
+  dz0 = first ? g * m0 * act_grad(z0, a.act) : 0.f;
+  dz1 = first ? 0.f : g * m1 * act_grad(z1, a.act);
+}
+XM_DEVICE float bn_act_dz_single(const BnActArgs& a, const float* __restrict__ dout_row, const float* __restrict__ yr,
+                                 long long row, long long t, float sc, float sh) {
+  const float z = yr[t] * sc + sh;
+  return dout_row[t] * drop_mul(a, row * a.T + t) * act_grad(z, a.act);
+}
+
+// grid (C, nsplit): per-channel partial sums of dz and dz*xhat
+__global__ void bn_act_bwd_reduce_kernel(const BnActArgs a, const float* __restrict__ dout,
+                                         double* __restrict__ partials) {
+  __shared__ double smd[32];
+  const int c = blockIdx.x, s = blockIdx.y, ns = gridDim.y;
+  const float mu = a.mean[c], is = a.invstd[c], g = a.gamma[c], bt = a.beta[c];
+  const float sc = g * is, sh = bt - mu * sc;
+  double sdz = 0.0, sdzx = 0.0;
+  for (long long b = s; b < a.B; b += ns) {
+    const long long row = b * a.C + c;
+    const float* yr = a.y + row * a.ldy;
+    const float* dr = dout + row * a.ldo;
+    float p0 = 0.f, p1 = 0.f;
+    if (a.pool == 2) {
+      const long long To = a.T / 2;
+      for (long long t = threadIdx.x; t < To; t += blockDim.x) {
+        float dz0, dz1;
+        bn_act_dz_pair(a, dr, yr, row, t, sc, sh, dz0, dz1);
+        const float2 v = *reinterpret_cast<const float2*>(yr + 2 * t);
+        p0 += dz0 + dz1;
+        p1 += dz0 * ((v.x - mu) * is) + dz1 * ((v.y - mu) * is);
+      }
+    } else {
+      for (long long t = threadIdx.x; t < a.T; t += blockDim.x) {
+        const float dz = bn_act_dz_single(a, dr, yr, row, t, sc, sh);
+        p0 += dz;
+        p1 += dz * ((yr[t] - mu) * is);
+      }
+    }
+    sdz += (double)p0;
+    sdzx += (double)p1;
+  }
+  sdz = block_sum(sdz, smd);
+  sdzx = block_sum(sdzx, smd);
+  if (threadIdx.x == 0) {
+    partials[((long long)s * a.C + c) * 2 + 0] = sdz;
+    partials[((long long)s * a.C + c) * 2 + 1] = sdzx;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int nsplit, int C, float* __restrict__ dbeta,
+                                       float* __restrict__ dgamma) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < nsplit; ++i) {
+    s += partials[((long long)i * C + c) * 2 + 0];
+    q += partials[((long long)i * C + c) * 2 + 1];
+  }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)q;
+}
+
+// one block per (b, c) row: dy = gamma*invstd*(dz - dbeta/n - xhat*dgamma/n)
+__global__ void bn_act_bwd_apply_kernel(const BnActArgs a, const float* __restrict__ dout,
+                                        const float* __restrict__ dbeta, const float* __restrict__ dgamma, float inv_n,
+                                        float* __restrict__ dy) {
+  const long long row = blockIdx.x;
+  const int c = (int)(row % a.C);
+  const float mu = a.mean[c], is = a.invstd[c], g = a.gamma[c], bt = a.beta[c];
+  const float sc = g * is, sh = bt - mu * sc;
+  const float k1 = dbeta[c] * inv_n, k2 = dgamma[c] * inv_n;
+  const float* yr = a.y + row * a.ldy;
+  const float* dr = dout + row * a.ldo;
+  float* dyr = dy + row * a.ldy;
+  if (a.pool == 2) {
+    const long long To = a.T / 2;
+    for (long long t = threadIdx.x; t < To; t += blockDim.x) {
+      float dz0, dz1;
+      bn_act_dz_pair(a, dr, yr, row, t, sc, sh, dz0, dz1);
+      const float2 v = *reinterpret_cast<const float2*>(yr + 2 * t);
+      float o0 = sc * (dz0 - k1 - (v.x - mu) * is * k2);
+      float o1 = sc * (dz1 - k1 - (v.y - mu) * is * k2);
+      if (a.round_out) { o0 = round_tf32(o0); o1 = round_tf32(o1); }
+      *reinterpret_cast<float2*>(dyr + 2 * t) = make_float2(o0, o1);
+    }
+    if ((a.T & 1) && threadIdx.x == 0) {  // odd tail element is dropped by the pool: dz = 0
+      const long long t = a.T - 1;
+      float o = sc * (0.f - k1 - (yr[t] - mu) * is * k2);
+      dyr[t] = a.round_out ? round_tf32(o) : o;
+    }
+  } else {
+    for (long long t = threadIdx.x; t < a.T; t += blockDim.x) {
+      const float dz = bn_act_dz_single(a, dr, yr, row, t, sc, sh);
+      float o = sc * (dz - k1 - (yr[t] - mu) * is * k2);
+      dyr[t] = a.round_out ? round_tf32(o) : o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm + act + dropout (warp per row)
+__global__ void ln_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ out, float* __restrict__ mean,
+                                  float* __restrict__ rstd, long long M, int D, float eps, int act, float drop_scale,
+                                  uint32_t drop_thresh, uint64_t seed) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * D;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) s += xr[d];
+  const float mu = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = xr[d] - mu;
+    q += v * v;
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)D + eps);
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+  for (int d = lane; d < D; d += 32) {
+    float o = apply_act((xr[d] - mu) * rs * gamma[d] + beta[d], act);
+    if (drop_thresh) o = dropout_keep((uint64_t)(row * D + d), seed, drop_thresh) ? o * drop_scale : 0.f;
+    out[row * D + d] = o;
+  }
+}
+
+// grid = nblk blocks of 8 warps; block accumulates dgamma/dbeta partials for its rows in smem.
+__global__ void ln_act_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
+                                  float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, long long M, int D,
+                                  int act, float drop_scale, uint32_t drop_thresh, uint64_t seed) {
+  extern __shared__ float sm[];  // 2 * D
+  float* sg = sm;
+  float* sb = sm + D;
+  for (int d = threadIdx.x; d < 2 * D; d += blockDim.x) sm[d] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* xr = x + row * D;
+    const float* dr = dout + row * D;
+    float s1 = 0.f, s2 = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float xh = (xr[d] - mu) * rs;
+      const float z = xh * gamma[d] + beta[d];
+      float g = dr[d];
+      if (drop_thresh) g = dropout_keep((uint64_t)(row * D + d), seed, drop_thresh) ? g * drop_scale : 0.f;
+      const float dz = g * act_grad(z, act);
+      atomicAdd(&sg[d], dz * xh);
+      atomicAdd(&sb[d], dz);
+      const float dzg = dz * gamma[d];
+      s1 += dzg;
+      s2 += dzg * xh;
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+    for (int d = lane; d < D; d += 32) {
+      const float xh = (xr[d] - mu) * rs;
+      const float z = xh * gamma[d] + beta[d];
+      float g = dr[d];
+      if (drop_thresh) g = dropout_keep((uint64_t)(row * D + d), seed, drop_thresh) ? g * drop_scale : 0.f;
+      const float dzg = g * act_grad(z, act) * gamma[d];
+      dx[row * D + d] = rs * (dzg - s1 - xh * s2);
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    dgamma_part[(long long)blockIdx.x * D + d] = sg[d];
+    dbeta_part[(long long)blockIdx.x * D + d] = sb[d];
+  }
+}
+
+// ------------------------------------------------------------------ small reductions
+// out[n] = sum_m x[m, n]; block = 32 columns x 8 row lanes
+__global__ void colsum_kernel(const float* __restrict__ x, long long M, long long N, long long ld,
+                              float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long n = blockIdx.x * 32ll + tx;
+  float acc = 0.f;
+  if (n < N)
+    for (long long m = ty; m < M; m += 8) acc += x[m * ld + n];
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sm[i][tx];
+    out[n] = s;
+  }
+}
+
+__global__ void rowmean_kernel(const float* __restrict__ x, long long R, long long T, long long ld,
+                               float* __restrict__ out) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (long long t = lane; t < T; t += 32) s += x[row * ld + t];
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s / (float)T;
+}
+__global__ void rowmean_bwd_kernel(const float* __restrict__ dout, long long R, long long T, long long ld,
+                                   float* __restrict__ dx) {
+  const long long row = blockIdx.x;
+  const float g = dout[row] / (float)T;
+  for (long long t = threadIdx.x; t < T; t += blockDim.x) dx[row * ld + t] = g;
+}
+
+// ------------------------------------------------------------------ L2 row normalisation (warp per row)
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ inv_norm,
+                                  long long M, int D, float eps) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  float q = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = x[row * D + d];
+    q += v * v;
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(q)), eps);
+  if (lane == 0) inv_norm[row] = inv;
+  for (int d = lane; d < D; d += 32) xn[row * D + d] = round_tf32(x[row * D + d] * inv);
+}
+__global__ void l2norm_bwd_kernel(const float* __restrict__ dxn, const float* __restrict__ xn,
+                                  const float* __restrict__ inv_norm, float* __restrict__ dx, long long M, int D) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32) dot += dxn[row * D + d] * xn[row * D + d];
+  dot = warp_sum(dot);
+  const float inv = inv_norm[row];
+  for (int d = lane; d < D; d += 32) dx[row * D + d] = (dxn[row * D + d] - xn[row * D + d] * dot) * inv;
+}
+
+static BnActArgs make_bn_args(const float* y, const float* mean, const float* invstd, const float* gamma,
+                              const float* beta, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo, int act,
+                              int pool, float drop_p, uint64_t seed, int drop_before_pool, int round_out) {
+  BnActArgs a;
+  a.y = y; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta;
+  a.B = B; a.T = T; a.ldy = ldy; a.ldo = ldo; a.C = (int)C; a.act = act; a.pool = pool;
+  a.drop_before_pool = drop_before_pool; a.round_out = round_out; a.seed = seed;
+  if (drop_p > 0.f) {
+    a.drop_scale = 1.0f / (1.0f - drop_p);
+    double th = (double)drop_p * 4294967296.0;
+    a.drop_thresh = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
+    if (a.drop_thresh == 0u) a.drop_thresh = 1u;
+  } else {
+    a.drop_scale = 1.0f;
+    a.drop_thresh = 0u;
+  }
+  return a;
+}
+
+static bool bn_args_ok(const void* y, const void* m, const void* is, const void* g, const void* b, int64_t B, int64_t C,
+                       int64_t T, int64_t ldy, int pool, float p) {
+  if (!y || !m || !is || !g || !b || B <= 0 || C <= 0 || T <= 0 || ldy < T) return false;
+  if (pool != 0 && pool != 2) return false;
+  if (pool == 2 && ((ldy & 1) || (reinterpret_cast<uintptr_t>(y) & 7))) return false;
+  if (!(p >= 0.f && p < 1.f)) return false;
+  return true;
+}
+
+}  // namespace xm
+
+using namespace xm;
+
+extern "C" {
+
+int xm_roi_meanstd_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, void* stream) {
+  if (!x || !out || B <= 0 || TR <= 0 || ROI <= 0 || B > 65535) return XM_ERR_INVALID;
+  dim3 grid(ceil_div(ROI, 128), (unsigned)B);
+  roi_meanstd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, TR, ROI, out);
+  return check_launch();
+}
+
+int xm_zscore_f32(const float* x, int64_t n_items, int64_t item_len, float eps, float* out, void* stream) {
+  if (!x || !out || n_items <= 0 || item_len <= 0) return XM_ERR_INVALID;
+  zscore_kernel<<<grid_rows(n_items), 256, 0, (cudaStream_t)stream>>>(x, item_len, eps, out);
+  return check_launch();
+}
+
+int xm_bn_nsplit(int64_t B, int64_t C, int64_t T) {
+  (void)T;
+  int64_t ns = (kNumSMs * 8 + C - 1) / C;
+  if (ns > B) ns = B;
+  if (ns < 1) ns = 1;
+  if (ns > 65535) ns = 65535;
+  return (int)ns;
+}
+
+int xm_bn_partial_stats_f32(const float* y, int64_t B, int64_t C, int64_t T, int64_t ldy, double* partials,
+                            void* stream) {
+  if (!y || !partials || B <= 0 || C <= 0 || T <= 0) return XM_ERR_INVALID;
+  dim3 grid((unsigned)C, (unsigned)xm_bn_nsplit(B, C, T));
+  bn_partial_stats_kernel<<<grid, T >= 256 ? 256 : 64, 0, (cudaStream_t)stream>>>(y, B, (int)C, T, ldy, partials);
+  return check_launch();
+}
+
+int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double total_count, float eps, float* mean,
+                         float* invstd, float* running_mean, float* running_var, float momentum, void* stream) {
+  if (!partials || !mean || !invstd || nsplit <= 0 || C <= 0 || total_count <= 0) return XM_ERR_INVALID;
+  bn_finalize_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nsplit, (int)C, total_count, eps,
+                                                                               mean, invstd, running_mean, running_var,
+                                                                               momentum);
+  return check_launch();
+}
+
+int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      float* out, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo, int act, int pool,
+                      float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream) {
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, C, T, ldy, pool, drop_p) || !out) return XM_ERR_INVALID;
+  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, C, T, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
+                             round_out);
+  bn_act_fwd_kernel<<<grid_rows(B * C), T >= 256 ? 128 : 32, 0, (cudaStream_t)stream>>>(a, out);
+  return check_launch();
+}
+
+int xm_bn_act_bwd_reduce_f32(const float* dout, const float* y, const float* mean, const float* invstd,
+                             const float* gamma, const float* beta, int64_t B, int64_t C, int64_t T, int64_t ldy,
+                             int64_t ldo, int act, int pool, float drop_p, uint64_t seed, int drop_before_pool,
+                             double* partials, void* stream) {
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, C, T, ldy, pool, drop_p) || !dout || !partials) return XM_ERR_INVALID;
+  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, C, T, ldy, ldo, act, pool, drop_p, seed, drop_before_pool, 0);
+  dim3 grid((unsigned)C, (unsigned)xm_bn_nsplit(B, C, T));
+  bn_act_bwd_reduce_kernel<<<grid, T >= 256 ? 256 : 64, 0, (cudaStream_t)stream>>>(a, dout, partials);
+  return check_launch();
+}
+
+int xm_bn_bwd_finalize(const double* partials, int nsplit, int64_t C, float* dbeta, float* dgamma, void* stream) {
+  if (!partials || !dbeta || !dgamma || nsplit <= 0 || C <= 0) return XM_ERR_INVALID;
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nsplit, (int)C, dbeta, dgamma);
+  return check_launch();
+}
+
+int xm_bn_act_bwd_apply_f32(const float* dout, const float* y, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, const float* dbeta, const float* dgamma,
+                            double total_count, float* dy, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo,
+                            int act, int pool, float drop_p, uint64_t seed, int drop_before_pool, int round_out,
+                            void* stream) {
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, C, T, ldy, pool, drop_p) || !dout || !dbeta || !dgamma || !dy ||
+      total_count <= 0)
+    return XM_ERR_INVALID;
+  if (pool == 2 && (reinterpret_cast<uintptr_t>(dy) & 7)) return XM_ERR_INVALID;
+  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, C, T, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
+                             round_out);
+  bn_act_bwd_apply_kernel<<<grid_rows(B * C), T >= 256 ? 128 : 32, 0, (cudaStream_t)stream>>>(
+      a, dout, dbeta, dgamma, (float)(1.0 / total_count), dy);
+  return check_launch();
+}
+
+static void drop_consts(float p, float& scale, uint32_t& thresh) {
+  if (p > 0.f) {
+    scale = 1.0f / (1.0f - p);
+    double th = (double)p * 4294967296.0;
+    thresh = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
+    if (thresh == 0u) thresh = 1u;
+  } else {
+    scale = 1.0f;
+    thresh = 0u;
+  }
+}
+
+int xm_ln_act_fwd_f32(const float* x, const float* gamma, const float* beta, float* out, float* mean, float* rstd,
+                      int64_t M, int64_t D, float eps, int act, float drop_p, uint64_t seed, void* stream) {
+  if (!x || !gamma || !beta || !out || !mean || !rstd || M <= 0 || D <= 0 || !(drop_p >= 0.f && drop_p < 1.f))
+    return XM_ERR_INVALID;
+  float sc;
+  uint32_t th;
+  drop_consts(drop_p, sc, th);
+  ln_act_fwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, out, mean, rstd, M, (int)D, eps, act,
+                                                                      sc, th, seed);
+  return check_launch();
+}
+
+int xm_ln_nblk(int64_t M) {
+  int64_t n = (M + 7) / 8;
+  if (n > kNumSMs * 2) n = kNumSMs * 2;
+  return (int)(n < 1 ? 1 : n);
+}
+
+int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, float* dx, float* dgamma_part, float* dbeta_part, int64_t M, int64_t D,
+                      int act, float drop_p, uint64_t seed, void* stream) {
+  if (!dout || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma_part || !dbeta_part || M <= 0 || D <= 0 ||
+      D > 4096 || !(drop_p >= 0.f && drop_p < 1.f))
+    return XM_ERR_INVALID;
+  float sc;
+  uint32_t th;
+  drop_consts(drop_p, sc, th);
+  ln_act_bwd_kernel<<<xm_ln_nblk(M), 256, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
+      dout, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, M, (int)D, act, sc, th, seed);
+  return check_launch();
+}
+
+int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream) {
+  if (!x || !out || M <= 0 || N <= 0) return XM_ERR_INVALID;
+  colsum_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(x, M, N, ldx, out);
+  return check_launch();
+}
+
+int xm_rowmean_f32(const float* x, int64_t R, int64_t T, int64_t ldx, float* out, void* stream) {
+  if (!x || !out || R <= 0 || T <= 0) return XM_ERR_INVALID;
+  rowmean_kernel<<<ceil_div(R, 8), 256, 0, (cudaStream_t)stream>>>(x, R, T, ldx, out);
+  return check_launch();
+}
+int xm_rowmean_bwd_f32(const float* dout, int64_t R, int64_t T, int64_t lddx, float* dx, void* stream) {
+  if (!dout || !dx || R <= 0 || T <= 0) return XM_ERR_INVALID;
+  rowmean_bwd_kernel<<<grid_rows(R), 128, 0, (cudaStream_t)stream>>>(dout, R, T, lddx, dx);
+  return check_launch();
+}
+
+int xm_l2norm_fwd_f32(const float* x, float* xn, float* inv_norm, int64_t M, int64_t D, float eps, void* stream) {
+  if (!x || !xn || !inv_norm || M <= 0 || D <= 0) return XM_ERR_INVALID;
+  l2norm_fwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, xn, inv_norm, M, (int)D, eps);
+  return check_launch();
+}
+int xm_l2norm_bwd_f32(const float* dxn, const float* xn, const float* inv_norm, float* dx, int64_t M, int64_t D,
+                      void* stream) {
+  if (!dxn || !xn || !inv_norm || !dx || M <= 0 || D <= 0) return XM_ERR_INVALID;
+  l2norm_bwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(dxn, xn, inv_norm, dx, M, (int)D);
+  return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+// tcgen05 TF32 GEMM engine (sm_100a).
+//
+//   D[m, n] (+)= sum over k-blocks of  A_tile[m, 32] * B_tile[n, 32]^T      (fp32 accumulate in TMEM)
+//
+// One CTA computes one 128 x BN output tile (or `taps_n` of them, one TMEM accumulator per
+// conv tap, for the conv weight gradient).  Warp roles: warp 0 = TMA producer (one lane),
+// warp 1 = TMEM allocator + tcgen05.mma issuer (one lane), warps 2..5 = epilogue
+// (TMEM -> registers -> global).  Operand tiles are fetched by TMA (cp.async.bulk.tensor.3d)
+// into 128B-swizzled shared memory and consumed directly by tcgen05.mma.kind::tf32 through
+// shared-memory descriptors; fp32 data is used as-is (the tensor core reads the tf32 bits).
+//
+// Both operands may be K-major (rows of 32 consecutive k) or MN-major (rows of 32 consecutive
+// m/n, one row per k) so that forward, data-gradient and weight-gradient contractions all read
+// the SAME row-major fp32 tensors without transposed copies.  Conv1d is the same engine with a
+// 3-D tensor map over (T, C, B): a tap is a TMA coordinate shift along T, and TMA's
+// out-of-bounds zero fill implements the conv zero padding and the ragged last tile.
+#pragma once
+#include "xm_common.cuh"
+#include "xm_ptx.cuh"
+
+namespace xm {
+
+enum : int {
+  EPI_ROWMAJOR = 0,    // C[z][tap][m][n] = act(alpha*acc + bias[n])
+  EPI_TRANSPOSED = 1,  // C[z][n][m]      = alpha*acc + bias[n]           (conv: NCW output)
+  EPI_LSE = 2,         // partial[ny][m]  = sum_n exp(alpha*acc - shift) ; diag[m] = alpha*acc[m, m+diag_off]
+  EPI_NCE_GRAD = 3,    // C[m][n] = coef*(exp(s-lse_row[m]) + exp(s-lse_col[n]) - 2*[n == m+diag_off]),  s = alpha*acc
+};
+
+struct OperandCfg {
+  int mn_major;  // 0: K-major tile, one TMA box {32 k, rows, 1}; 1: MN-major, rows/32 boxes {32 mn, 32 k, 1}
+  int rows;      // MN extent of the tile (A: 128, B: bn)
+  // TMA coordinate d = base[d] + bx*sx[d] + by*sy[d] + bz*sz[d] + kin*kin_step[d] + kout*kout_step[d] + tap*tap_step[d]
+  int base[3], sx[3], sy[3], sz[3], kin_step[3], kout_step[3], tap_step[3];
+};
+
+struct GemmParams {
+  OperandCfg a, b;
+  int bn;          // N of one MMA / one accumulator (multiple of 16, <= 256)
+  int taps_k;      // taps iterated inside the K loop (conv fwd / dgrad), >= 1
+  int taps_n;      // taps held as separate accumulators (conv wgrad), >= 1
+  int kin_count;   // inner k-blocks per (kout, tap)
+  int kout_count;  // outer k iterations per CTA (split along gridDim.z when kout_split != 0)
+  int kout_total;  // total outer k iterations (only used when kout_split != 0)
+  int kout_split;  // 1: blockIdx.z selects a kout range [bz*kout_count, ...)
+  int stages;
+  int tmem_cols;
+  // epilogue
+  int M, N;  // valid extents of the output (guards)
+  float* c;
+  long long ldc, c_z_stride, c_tap_stride;
+  const float* bias;
+  float alpha;
+  int act;
+  int round_tf32;
+  // InfoNCE epilogues
+  const float* lse_row;
+  const float* lse_col;
+  float* partial;  // (gridDim.y, M)
+  float* diag;     // (M)
+  int diag_off;
+  float coef;
+  float shift;
+};
+
+constexpr int kGemmThreads = 192;
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 32 tf32
+constexpr int kMaxStages = 8;
+
+XM_DEVICE void issue_operand_loads(const CUtensorMap* tm, uint64_t* bar, uint8_t* dst, const OperandCfg& o, int c0,
+                                   int c1, int c2) {
+  if (!o.mn_major) {
+    ptx::tma_load_3d(tm, bar, dst, c0, c1, c2);
+  } else {
+    const int nbox = o.rows >> 5;
+    for (int bx = 0; bx < nbox; ++bx) ptx::tma_load_3d(tm, bar, dst + bx * 4096, c0 + 32 * bx, c1, c2);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+
+  int kout_n = p.kout_count;
+  int kout_lo = 0;
+  if (p.kout_split) {
+    kout_lo = bz * p.kout_count;
+    kout_n = min(p.kout_count, p.kout_total - kout_lo);
+  }
+  const int total_kb = kout_n * p.taps_k * p.kin_count;
+  if (total_kb <= 0) return;  // host never launches such a CTA; uniform early-out keeps it safe
+
+  // 1024-B aligned operand ring (128B swizzle atoms are 1024 B)
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int b_tile_bytes = p.bn * 128;
+  const int stage_bytes = kATileBytes + p.taps_n * b_tile_bytes;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(&tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      int ca[3], cb[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        ca[d] = p.a.base[d] + bx * p.a.sx[d] + by * p.a.sy[d] + bz * p.a.sz[d];
+        cb[d] = p.b.base[d] + bx * p.b.sx[d] + by * p.b.sy[d] + bz * p.b.sz[d];
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ko = 0; ko < kout_n; ++ko) {
+        const int kout = kout_lo + ko;
+        for (int tk = 0; tk < p.taps_k; ++tk) {
+          for (int kin = 0; kin < p.kin_count; ++kin) {
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            issue_operand_loads(&tmA, &full_bar[s], sa, p.a,
+                                ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0] + tk * p.a.tap_step[0],
+                                ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + tk * p.a.tap_step[1],
+                                ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2] + tk * p.a.tap_step[2]);
+            for (int tn = 0; tn < p.taps_n; ++tn) {
+              const int tap = tk + tn;  // exactly one of taps_k / taps_n exceeds 1
+              issue_operand_loads(&tmB, &full_bar[s], sa + kATileBytes + tn * b_tile_bytes, p.b,
+                                  cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tap * p.b.tap_step[0],
+                                  cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tap * p.b.tap_step[1],
+                                  cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tap * p.b.tap_step[2]);
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      const uint32_t idesc = ptx::make_idesc_tf32(128, p.bn, p.a.mn_major, p.b.mn_major);
+      const uint32_t a_kstep = p.a.mn_major ? 1024u : 32u;  // bytes per K=8 slab
+      const uint32_t b_kstep = p.b.mn_major ? 1024u : 32u;
+      const uint32_t a_lbo = p.a.mn_major ? 4096u : 16u;
+      const uint32_t b_lbo = p.b.mn_major ? 4096u : 16u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+        for (int tn = 0; tn < p.taps_n; ++tn) {
+          const uint32_t sb = sa + kATileBytes + tn * b_tile_bytes;
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {
+            const uint64_t da = ptx::make_smem_desc(sa + k8 * a_kstep, a_lbo, 1024u);
+            const uint64_t db = ptx::make_smem_desc(sb + k8 * b_kstep, b_lbo, 1024u);
+            ptx::mma_tf32_ss(tmem_base + (uint32_t)(tn * p.bn), da, db, idesc, (kb > 0 || k8 > 0) ? 1u : 0u);
+          }
+        }
+        ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      ptx::mma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // -------------------------------------------------- epilogue warps 2..5
+    ptx::mbar_wait(&tmem_full_bar, 0);
+    ptx::tc_fence_after_sync();
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int m = bx * 128 + row;  // row index inside this z-slab
+    const bool row_ok = m < p.M;
+    const int n0 = by * p.bn;
+
+    float lse_r = 0.f;
+    if (EPI == EPI_NCE_GRAD && row_ok) lse_r = p.lse_row[m];
+    float rowsum = 0.f;
+
+    for (int tn = 0; tn < p.taps_n; ++tn) {
+      float* cbase = p.c ? p.c + (long long)bz * p.c_z_stride + (long long)tn * p.c_tap_stride : nullptr;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tn * p.bn + c0), r);
+        ptx::tmem_ld_wait();
+        if (EPI == EPI_ROWMAJOR) {
+          if (row_ok) {
+            float* crow = cbase + (long long)m * p.ldc + n0 + c0;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              float x = __uint_as_float(r[j]) * p.alpha;
+              if (p.bias != nullptr && n < p.N) x += p.bias[n];
+              x = apply_act(x, p.act);
+              if (p.round_tf32) x = round_tf32(x);
+              v[j] = x;
+            }
+            const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + 16 <= p.N);
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c0 + j < p.N) crow[j] = v[j];
+            }
+          }
+        } else if (EPI == EPI_TRANSPOSED) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (row_ok && n < p.N) {
+              float x = __uint_as_float(r[j]) * p.alpha;
+              if (p.bias != nullptr) x += p.bias[n];
+              if (p.round_tf32) x = round_tf32(x);
+              cbase[(long long)n * p.ldc + m] = x;  // lanes = consecutive m: coalesced
+            }
+          }
+        } else if (EPI == EPI_LSE) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (row_ok && n < p.N) {
+              const float s = __uint_as_float(r[j]) * p.alpha;
+              rowsum += __expf(s - p.shift);
+              if (n == m + p.diag_off) p.diag[m] = s;
+            }
+          }
+        } else {  // EPI_NCE_GRAD
+          if (row_ok) {
+            float* crow = cbase + (long long)m * p.ldc + n0 + c0;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              float g = 0.f;
+              if (n < p.N) {
+                const float s = __uint_as_float(r[j]) * p.alpha;
+                g = __expf(s - lse_r) + __expf(s - p.lse_col[n]);
+                if (n == m + p.diag_off) g -= 2.0f;
+                g = round_tf32(g * p.coef);
+              }
+              v[j] = g;
+            }
+            const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + 16 <= p.N);
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + c0 + j < p.N) crow[j] = v[j];
+            }
+          }
+        }
+      }
+    }
+    if (EPI == EPI_LSE && row_ok) p.partial[(long long)by * p.M + m] = rowsum;
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+struct TensorView3 {
+  const void* ptr;
+  unsigned long long dim[3];         // dim[0] innermost (contiguous)
+  unsigned long long stride_bytes[2];  // strides of dim[1], dim[2]
+};
+
+int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1);
+int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, GemmParams& p, dim3 grid, cudaStream_t stream);
+
+inline int tmem_cols_for(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+}  // namespace xm

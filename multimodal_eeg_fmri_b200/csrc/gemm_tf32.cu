@@ -1,0 +1,566 @@
+// Host side of the tcgen05 TF32 GEMM engine + the C-ABI entry points built on it:
+// nn.Linear fwd/dgrad/wgrad, dense Conv1d fwd/dgrad/wgrad (implicit GEMM over taps),
+// similarity / InfoNCE contractions.  See gemm_engine.cuh for the kernel.
+#include "gemm_engine.cuh"
+
+#include <string.h>
+
+namespace xm {
+
+int g_last_cuda_error = 0;
+
+// ---------------------------------------------------------------- TMA descriptor encode
+// cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time
+// dependency on libcuda (it must load on a CPU-only box for the ABI export test).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    else (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return XM_ERR_NO_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) return XM_ERR_INVALID;
+  if ((t.stride_bytes[0] & 15) != 0 || (t.stride_bytes[1] & 15) != 0) return XM_ERR_INVALID;
+  cuuint64_t dims[3] = {t.dim[0], t.dim[1], t.dim[2]};
+  cuuint64_t strides[2] = {t.stride_bytes[0], t.stride_bytes[1]};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(t.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = 100000 + (int)r;
+    return XM_ERR_LAUNCH;
+  }
+  return XM_OK;
+}
+
+template <int EPI>
+static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, dim3 grid, size_t smem,
+                      cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return XM_ERR_LAUNCH;
+  }
+  gemm_tf32_kernel<EPI><<<grid, kGemmThreads, smem, stream>>>(ma, mb, p);
+  return check_launch();
+}
+
+int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, GemmParams& p, dim3 grid, cudaStream_t stream) {
+  if (p.bn < 16 || p.bn > 256 || (p.bn & 15)) return XM_ERR_UNSUPPORTED;
+  if (p.b.mn_major && (p.bn & 31)) return XM_ERR_UNSUPPORTED;
+  if (p.taps_n * p.bn > 512) return XM_ERR_UNSUPPORTED;
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return XM_OK;
+  const int stage_bytes = kATileBytes + p.taps_n * p.bn * 128;
+  const int total_kb = p.kout_count * p.taps_k * p.kin_count;
+  if (total_kb <= 0) return XM_ERR_INVALID;
+  // Small stages: keep the ring <= ~100 KB so two CTAs share an SM (one's prologue/epilogue
+  // hides behind the other's main loop).  Large stages: one CTA per SM, as deep as fits.
+  int budget = (stage_bytes * 4 <= 100 * 1024) ? 100 * 1024 : 220 * 1024;
+  int stages = budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > total_kb) stages = total_kb < 2 ? 2 : total_kb;
+  if (stages < 2) return XM_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.tmem_cols = tmem_cols_for(p.taps_n * p.bn);
+  p.a.rows = 128;
+  p.b.rows = p.bn;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+
+  CUtensorMap ma, mb;
+  int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : 128);
+  if (rc != XM_OK) return rc;
+  rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? 32 : (unsigned)p.bn);
+  if (rc != XM_OK) return rc;
+
+  switch (epi) {
+    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, p, grid, smem, stream);
+    case EPI_TRANSPOSED: return launch_epi<EPI_TRANSPOSED>(ma, mb, p, grid, smem, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, p, grid, smem, stream);
+    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, p, grid, smem, stream);
+  }
+  return XM_ERR_INVALID;
+}
+
+static void zero_params(GemmParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.taps_k = 1;
+  p.taps_n = 1;
+  p.kout_count = 1;
+  p.kout_total = 1;
+  p.alpha = 1.0f;
+}
+
+// N tile: as wide as the problem allows (fewer A re-reads), narrowed while the grid
+// would leave most of the 148 SMs idle.
+static int choose_bn(int64_t N, int64_t other_tiles, int gran) {
+  int bn = (int)(((N + gran - 1) / gran) * gran);
+  if (bn > 256) bn = 256;
+  while (bn >= 2 * 32 && (bn / 2) % gran == 0 && other_tiles * ((N + bn - 1) / bn) < kNumSMs) bn /= 2;
+  return bn;
+}
+
+// ---------------------------------------------------------------- split-K / wgrad reductions
+// out[m, n] = act(sum_s ws[s, m, n] + bias[n])
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long M, long long N,
+                                     const float* __restrict__ bias, float* __restrict__ out, long long ldo, int act,
+                                     int round_out) {
+  const long long total = M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N, n = i - m * N;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];
+    if (bias) acc += bias[n];
+    acc = apply_act(acc, act);
+    if (round_out) acc = round_tf32(acc);
+    out[m * ldo + n] = acc;
+  }
+}
+
+// dw[co, ci, tap] = sum_s ws[s, tap, co, ci]   (ws slabs are (taps, Cout, bn) with pitch bn)
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int Cout, int Cin, int bn,
+                                         float* __restrict__ dw) {
+  const long long total = (long long)Cout * Cin * taps;
+  const long long slab = (long long)taps * Cout * bn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const long long r = i / taps;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    const long long src = ((long long)tap * Cout + co) * bn + ci;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * slab + src];
+    dw[i] = acc;
+  }
+}
+
+// db[c] = sum_{b,t} dy[b, c, t]   (one block per channel)
+__global__ void conv_bias_grad_kernel(const float* __restrict__ dy, long long B, int C, long long T, long long ld,
+                                      float* __restrict__ db) {
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (long long b = 0; b < B; ++b) {
+    const float* row = dy + (b * C + c) * ld;
+    float part = 0.f;
+    for (long long t = threadIdx.x; t < T; t += blockDim.x) part += row[t];
+    acc += (double)part;
+  }
+  __shared__ double sm[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) db[c] = (float)v;
+  }
+}
+
+// w (Cout, Cin, taps) -> wk (taps, Cout, ldk) and wt (taps, Cin, ldt), tf32-rounded, zero padded
+__global__ void conv_pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, float* __restrict__ wk,
+                                        int ldk, float* __restrict__ wt, int ldt) {
+  const long long nk = (long long)taps * Cout * ldk;
+  const long long nt = (long long)taps * Cin * ldt;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nk + nt; i += (long long)gridDim.x * blockDim.x) {
+    if (i < nk) {
+      const int ci = (int)(i % ldk);
+      const long long r = i / ldk;
+      const int co = (int)(r % Cout);
+      const int tap = (int)(r / Cout);
+      wk[i] = ci < Cin ? round_tf32(w[((long long)co * Cin + ci) * taps + tap]) : 0.f;
+    } else {
+      const long long j = i - nk;
+      const int co = (int)(j % ldt);
+      const long long r = j / ldt;
+      const int ci = (int)(r % Cin);
+      const int tap = (int)(r / Cin);
+      wt[j] = co < Cout ? round_tf32(w[((long long)co * Cin + ci) * taps + tap]) : 0.f;
+    }
+  }
+}
+
+// lse[m] = shift + log(sum_t partial[t, m])
+__global__ void lse_finalize_kernel(const float* __restrict__ partial, int ntiles, long long M, float shift,
+                                    float* __restrict__ lse) {
+  const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float acc = 0.f;
+  for (int t = 0; t < ntiles; ++t) acc += partial[(long long)t * M + m];
+  lse[m] = shift + logf(acc);
+}
+
+static int grid_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace xm
+
+using namespace xm;
+
+// =================================================================== C ABI
+extern "C" {
+
+int xm_abi_version(void) { return XM_ABI_VERSION; }
+int xm_last_cuda_error(void) { return xm::g_last_cuda_error; }
+const char* xm_strerror(int code) {
+  switch (code) {
+    case XM_OK: return "ok";
+    case XM_ERR_INVALID: return "invalid argument (shape / alignment / null pointer)";
+    case XM_ERR_UNSUPPORTED: return "unsupported shape";
+    case XM_ERR_LAUNCH: return "CUDA launch or driver error (see xm_last_cuda_error)";
+    case XM_ERR_NO_DRIVER: return "cuTensorMapEncodeTiled unavailable (no CUDA driver)";
+  }
+  return "unknown error";
+}
+
+int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int round_out, int splits, float* workspace,
+                      void* stream) {
+  if (!x || !w || !y || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
+  if ((ldx & 3) || (ldw & 3)) return XM_ERR_INVALID;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !workspace) return XM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m_tiles = ceil_div(M, 128);
+  GemmParams p;
+  zero_params(p);
+  p.bn = choose_bn(N, (int64_t)m_tiles * splits, 16);
+  const int kb = ceil_div(K, 32);
+  const int kb_split = ceil_div(kb, splits);
+  splits = ceil_div(kb, kb_split);
+  p.kin_count = kb_split;
+  p.a.mn_major = 0;
+  p.a.sx[1] = 128;
+  p.a.kin_step[0] = 32;
+  p.a.sz[0] = 32 * kb_split;
+  p.b.mn_major = 0;
+  p.b.sy[1] = p.bn;
+  p.b.kin_step[0] = 32;
+  p.b.sz[0] = 32 * kb_split;
+  p.M = (int)M;
+  p.N = (int)N;
+  if (splits == 1) {
+    p.c = y;
+    p.ldc = ldy;
+    p.bias = bias;
+    p.act = act;
+    p.round_tf32 = round_out;
+  } else {
+    p.c = workspace;
+    p.ldc = N;
+    p.c_z_stride = (long long)M * N;
+  }
+  TensorView3 ta{x, {(unsigned long long)K, (unsigned long long)M, 1}, {(unsigned long long)ldx * 4, (unsigned long long)M * ldx * 4}};
+  TensorView3 tb{w, {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
+  int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, ceil_div(N, p.bn), splits), st);
+  if (rc != XM_OK || splits == 1) return rc;
+  splitk_reduce_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(workspace, splits, M, N, bias, y, ldy, act, round_out);
+  return check_launch();
+}
+
+int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
+                        int64_t ldw, int64_t lddx, int round_out, void* stream) {
+  if (!dy || !w || !dx || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
+  if ((lddy & 3) || (ldw & 3)) return XM_ERR_INVALID;
+  const int m_tiles = ceil_div(M, 128);
+  GemmParams p;
+  zero_params(p);
+  p.bn = choose_bn(K, m_tiles, 32);
+  p.kin_count = ceil_div(N, 32);
+  p.a.mn_major = 0;  // dy (M, N): contraction index N is contiguous
+  p.a.sx[1] = 128;
+  p.a.kin_step[0] = 32;
+  p.b.mn_major = 1;  // w (N, K): output index K is contiguous
+  p.b.sy[0] = p.bn;
+  p.b.kin_step[1] = 32;
+  p.M = (int)M;
+  p.N = (int)K;
+  p.c = dx;
+  p.ldc = lddx;
+  p.round_tf32 = round_out;
+  TensorView3 ta{dy, {(unsigned long long)N, (unsigned long long)M, 1}, {(unsigned long long)lddy * 4, (unsigned long long)M * lddy * 4}};
+  TensorView3 tb{w, {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream);
+}
+
+int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream);
+
+int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
+                        int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, void* stream) {
+  if (!dy || !x || !dw || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
+  if ((lddy & 3) || (ldx & 3)) return XM_ERR_INVALID;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !workspace) return XM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m_tiles = ceil_div(N, 128);  // GEMM rows = output features
+  GemmParams p;
+  zero_params(p);
+  p.bn = choose_bn(K, (int64_t)m_tiles * splits, 32);
+  const int kb = ceil_div(M, 32);
+  const int kb_split = ceil_div(kb, splits);
+  splits = ceil_div(kb, kb_split);
+  p.kin_count = kb_split;
+  p.a.mn_major = 1;  // dy (M, N): GEMM row index N contiguous, contraction index M strided
+  p.a.sx[0] = 128;
+  p.a.kin_step[1] = 32;
+  p.a.sz[1] = 32 * kb_split;
+  p.b.mn_major = 1;  // x (M, K): GEMM col index K contiguous
+  p.b.sy[0] = p.bn;
+  p.b.kin_step[1] = 32;
+  p.b.sz[1] = 32 * kb_split;
+  p.M = (int)N;
+  p.N = (int)K;
+  if (splits == 1) {
+    p.c = dw;
+    p.ldc = lddw;
+  } else {
+    p.c = workspace;
+    p.ldc = K;
+    p.c_z_stride = (long long)N * K;
+  }
+  TensorView3 ta{dy, {(unsigned long long)N, (unsigned long long)M, 1}, {(unsigned long long)lddy * 4, (unsigned long long)M * lddy * 4}};
+  TensorView3 tb{x, {(unsigned long long)K, (unsigned long long)M, 1}, {(unsigned long long)ldx * 4, (unsigned long long)M * ldx * 4}};
+  int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, ceil_div(K, p.bn), splits), st);
+  if (rc != XM_OK) return rc;
+  if (splits > 1) {
+    splitk_reduce_kernel<<<grid_for(N * K, 256), 256, 0, st>>>(workspace, splits, N, K, nullptr, dw, lddw, XM_ACT_NONE, 0);
+    rc = check_launch();
+    if (rc != XM_OK) return rc;
+  }
+  if (db) return xm_colsum_f32(dy, M, N, lddy, db, stream);
+  return XM_OK;
+}
+
+// ------------------------------------------------------------------ conv1d
+int xm_conv1d_pack_weight_f32(const float* w, int64_t Cout, int64_t Cin, int64_t taps, float* wk, int64_t ldk,
+                              float* wt, int64_t ldt, void* stream) {
+  if (!w || !wk || !wt || ldk < Cin || ldt < Cout || (ldk & 3) || (ldt & 3)) return XM_ERR_INVALID;
+  const long long n = taps * Cout * ldk + taps * Cin * ldt;
+  conv_pack_weight_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (int)Cout, (int)Cin, (int)taps, wk,
+                                                                              (int)ldk, wt, (int)ldt);
+  return check_launch();
+}
+
+// Shared by fwd (direction +1) and dgrad (direction -1): out[b, n, t] = sum_tap sum_k in[b, k, t + dir*(tap - pad)] * wp[tap, n, k]
+static int conv_like(const float* in, const float* wp, const float* bias, float* out, int64_t B, int64_t Kc, int64_t Nc,
+                     int64_t T, int64_t taps, int64_t ld_in, int64_t ld_w, int64_t ld_out, int dir, int round_out,
+                     cudaStream_t st) {
+  if (!in || !wp || !out || B <= 0 || Kc <= 0 || Nc <= 0 || T <= 0 || taps <= 0 || !(taps & 1)) return XM_ERR_INVALID;
+  if ((ld_in & 3) || (ld_w & 3) || ld_in < T || ld_out < T) return XM_ERR_INVALID;
+  const int pad = (int)(taps / 2);
+  const int t_tiles = ceil_div(T, 128);
+  GemmParams p;
+  zero_params(p);
+  p.bn = choose_bn(Nc, (int64_t)t_tiles * B, 16);
+  p.taps_k = (int)taps;
+  p.kin_count = ceil_div(Kc, 32);
+  p.a.mn_major = 1;  // activations (B, C, T): GEMM row index t contiguous
+  p.a.base[0] = -dir * pad;
+  p.a.sx[0] = 128;
+  p.a.sz[2] = 1;
+  p.a.kin_step[1] = 32;
+  p.a.tap_step[0] = dir;
+  p.b.mn_major = 0;  // packed weights (taps, N, K): contraction index contiguous
+  p.b.sy[1] = p.bn;
+  p.b.kin_step[0] = 32;
+  p.b.tap_step[2] = 1;
+  p.M = (int)T;
+  p.N = (int)Nc;
+  p.c = out;
+  p.ldc = ld_out;
+  p.c_z_stride = (long long)Nc * ld_out;
+  p.bias = bias;
+  p.round_tf32 = round_out;
+  TensorView3 ta{in, {(unsigned long long)T, (unsigned long long)Kc, (unsigned long long)B},
+                 {(unsigned long long)ld_in * 4, (unsigned long long)Kc * ld_in * 4}};
+  TensorView3 tb{wp, {(unsigned long long)Kc, (unsigned long long)Nc, (unsigned long long)taps},
+                 {(unsigned long long)ld_w * 4, (unsigned long long)Nc * ld_w * 4}};
+  return launch_gemm(EPI_TRANSPOSED, ta, tb, p, dim3(t_tiles, ceil_div(Nc, p.bn), (unsigned)B), st);
+}
+
+int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,
+                      int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy, int round_out,
+                      void* stream) {
+  return conv_like(x, wk, bias, y, B, Cin, Cout, T, taps, ldx, ldk, ldy, +1, round_out, (cudaStream_t)stream);
+}
+
+int xm_conv1d_dgrad_f32(const float* dy, const float* wt, float* dx, int64_t B, int64_t Cin, int64_t Cout, int64_t T,
+                        int64_t taps, int64_t lddy, int64_t ldt, int64_t lddx, int round_out, void* stream) {
+  return conv_like(dy, wt, nullptr, dx, B, Cout, Cin, T, taps, lddy, ldt, lddx, -1, round_out, (cudaStream_t)stream);
+}
+
+// wgrad geometry: samples are the outer contraction index, split across gridDim.z; taps are
+// separate TMEM accumulators (as many as fit 512 columns), tap groups across gridDim.y.
+struct WgradPlan {
+  int bn, taps_n, tap_groups, samples_per_cta, splits;
+};
+static WgradPlan wgrad_plan(int64_t B, int64_t Cin, int64_t Cout, int64_t taps) {
+  WgradPlan pl;
+  pl.bn = (int)((Cin + 15) / 16 * 16);
+  int per = 512 / pl.bn;
+  if (per < 1) per = 1;
+  // keep >= 2 pipeline stages in shared memory: 16 KB + taps_n * bn * 128 B per stage
+  while (per > 1 && 2 * (kATileBytes + per * pl.bn * 128) > 220 * 1024) --per;
+  pl.taps_n = (int)(taps < per ? taps : per);
+  pl.tap_groups = (int)((taps + pl.taps_n - 1) / pl.taps_n);
+  const int m_tiles = (int)((Cout + 127) / 128);
+  int want = kNumSMs / (m_tiles * pl.tap_groups);
+  if (want < 1) want = 1;
+  if (want > B) want = (int)B;
+  pl.samples_per_cta = (int)((B + want - 1) / want);
+  pl.splits = (int)((B + pl.samples_per_cta - 1) / pl.samples_per_cta);
+  return pl;
+}
+
+int64_t xm_conv1d_wgrad_workspace(int64_t B, int64_t Cin, int64_t Cout, int64_t taps) {
+  WgradPlan pl = wgrad_plan(B, Cin, Cout, taps);
+  return (int64_t)pl.splits * taps * Cout * pl.bn;
+}
+
+int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout,
+                        int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, void* stream) {
+  if (!dy || !x || !dw || !workspace || B <= 0 || Cin <= 0 || Cout <= 0 || T <= 0 || taps <= 0 || !(taps & 1))
+    return XM_ERR_INVALID;
+  if ((lddy & 3) || (ldx & 3) || Cin > 256) return XM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = (int)(taps / 2);
+  WgradPlan pl = wgrad_plan(B, Cin, Cout, taps);
+  const int m_tiles = ceil_div(Cout, 128);
+  for (int g = 0; g < pl.tap_groups; ++g) {
+    const int tap0 = g * pl.taps_n;
+    const int ntap = (int)(taps - tap0 < pl.taps_n ? taps - tap0 : pl.taps_n);
+    GemmParams p;
+    zero_params(p);
+    p.bn = pl.bn;
+    p.taps_n = ntap;
+    p.kin_count = ceil_div(T, 32);
+    p.kout_count = pl.samples_per_cta;
+    p.kout_total = (int)B;
+    p.kout_split = 1;
+    p.a.mn_major = 0;  // dy (B, Cout, T): contraction index t contiguous
+    p.a.sx[1] = 128;
+    p.a.kin_step[0] = 32;
+    p.a.kout_step[2] = 1;
+    p.b.mn_major = 0;  // x (B, Cin, T)
+    p.b.base[0] = tap0 - pad;
+    p.b.kin_step[0] = 32;
+    p.b.kout_step[2] = 1;
+    p.b.tap_step[0] = 1;
+    p.M = (int)Cout;
+    p.N = (int)Cin;
+    p.c = workspace + (long long)tap0 * Cout * pl.bn;
+    p.ldc = pl.bn;
+    p.c_tap_stride = (long long)Cout * pl.bn;
+    p.c_z_stride = (long long)taps * Cout * pl.bn;
+    TensorView3 ta{dy, {(unsigned long long)T, (unsigned long long)Cout, (unsigned long long)B},
+                   {(unsigned long long)lddy * 4, (unsigned long long)Cout * lddy * 4}};
+    TensorView3 tb{x, {(unsigned long long)T, (unsigned long long)Cin, (unsigned long long)B},
+                   {(unsigned long long)ldx * 4, (unsigned long long)Cin * ldx * 4}};
+    int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, 1, pl.splits), st);
+    if (rc != XM_OK) return rc;
+  }
+  conv_wgrad_reduce_kernel<<<grid_for(Cout * Cin * taps, 256), 256, 0, st>>>(workspace, pl.splits, (int)taps, (int)Cout,
+                                                                             (int)Cin, pl.bn, dw);
+  int rc = check_launch();
+  if (rc != XM_OK) return rc;
+  if (db) {
+    conv_bias_grad_kernel<<<(unsigned)Cout, 256, 0, st>>>(dy, B, (int)Cout, T, lddy, db);
+    rc = check_launch();
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------ similarity / InfoNCE
+static void sim_operands(GemmParams& p, int bn) {
+  p.bn = bn;
+  p.a.mn_major = 0;
+  p.a.sx[1] = 128;
+  p.a.kin_step[0] = 32;
+  p.b.mn_major = 0;
+  p.b.sy[1] = bn;
+  p.b.kin_step[0] = 32;
+}
+
+int xm_similarity_f32(const float* a, const float* b, float* S, int64_t Ml, int64_t Ng, int64_t D, float inv_tau,
+                      void* stream) {
+  if (!a || !b || !S || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
+  GemmParams p;
+  zero_params(p);
+  sim_operands(p, choose_bn(Ng, ceil_div(Ml, 128), 16));
+  p.kin_count = ceil_div(D, 32);
+  p.M = (int)Ml;
+  p.N = (int)Ng;
+  p.c = S;
+  p.ldc = Ng;
+  p.alpha = inv_tau;
+  TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
+  TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, p.bn), 1), (cudaStream_t)stream);
+}
+
+int xm_infonce_tile_n(void) { return 128; }
+
+int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D,
+                       float inv_tau, int64_t diag_off, float* workspace, void* stream) {
+  if (!a || !b || !lse || !diag || !workspace || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams p;
+  zero_params(p);
+  sim_operands(p, 128);
+  p.kin_count = ceil_div(D, 32);
+  p.M = (int)Ml;
+  p.N = (int)Ng;
+  p.alpha = inv_tau;
+  p.shift = inv_tau;  // |cos| <= 1  =>  S <= inv_tau: a fixed shift replaces the running max
+  p.partial = workspace;
+  p.diag = diag;
+  p.diag_off = (int)diag_off;
+  const int ntiles = ceil_div(Ng, 128);
+  TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
+  TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
+  int rc = launch_gemm(EPI_LSE, ta, tb, p, dim3(ceil_div(Ml, 128), ntiles, 1), st);
+  if (rc != XM_OK) return rc;
+  lse_finalize_kernel<<<ceil_div(Ml, 256), 256, 0, st>>>(workspace, ntiles, Ml, inv_tau, lse);
+  return check_launch();
+}
+
+int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
+                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
+                        void* stream) {
+  if (!a || !b || !lse_row || !lse_col || !G || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
+  GemmParams p;
+  zero_params(p);
+  sim_operands(p, 128);
+  p.kin_count = ceil_div(D, 32);
+  p.M = (int)Ml;
+  p.N = (int)Ng;
+  p.alpha = inv_tau;
+  p.c = G;
+  p.ldc = Ng;
+  p.lse_row = lse_row;
+  p.lse_col = lse_col;
+  p.diag_off = (int)diag_off;
+  p.coef = coef;
+  TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
+  TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
+  return launch_gemm(EPI_NCE_GRAD, ta, tb, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, 128), 1), (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,259 @@
+// EEG preprocessing on the device: window index generation, window gather, and the fused
+// window-gather + taper + real FFT + one-sided PSD + band-power reduction.
+//
+// Band-power kernel: one warp per (window, channel) row.  The row is read straight from the
+// recording (the gather is the address computation; windows are never materialised), packed as
+// N2 = nfft/2 complex points, transformed by radix-8/4/2 Stockham passes that exchange through
+// a padded per-warp shared-memory buffer, then only the bins inside the requested bands are
+// unpacked (real-FFT post-processing), squared and reduced with warp shuffles.
+// Algorithmic traffic: C*win*4 B read + C*n_bands*4 B written per window.
+#include "spectral_core.cuh"
+#include "xm_common.cuh"
+
+namespace xm {
+
+constexpr int kBpWarps = 8;      // rows in flight per CTA
+constexpr int kMaxBands = 8;
+
+__global__ void window_index_kernel(long long n_rec, long long n_win, long long hop, const long long* __restrict__ rec_labels,
+                                    const long long* __restrict__ rec_subjects, long long* __restrict__ starts,
+                                    long long* __restrict__ rec_ids, long long* __restrict__ labels,
+                                    long long* __restrict__ subjects) {
+  const long long total = n_rec * n_win;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / n_win, w = g - r * n_win;
+    if (starts) starts[g] = w * hop;
+    if (rec_ids) rec_ids[g] = r;
+    if (labels && rec_labels) labels[g] = rec_labels[r];
+    if (subjects && rec_subjects) subjects[g] = rec_subjects[r];
+  }
+}
+
+// one block per (window, channel) row; coalesced copy
+__global__ void window_gather_kernel(const float* __restrict__ rec, long long C, long long n_samples, long long n_win,
+                                     long long win, long long hop, float* __restrict__ out, long long ld_out,
+                                     int round_out) {
+  const long long row = blockIdx.x;  // g*C + c
+  const long long g = row / C, c = row - g * C;
+  const long long r = g / n_win, w = g - r * n_win;
+  const float* src = rec + (r * C + c) * n_samples + w * hop;
+  float* dst = out + row * ld_out;
+  for (long long t = threadIdx.x; t < win; t += blockDim.x) {
+    const float v = src[t];
+    dst[t] = round_out ? round_tf32(v) : v;
+  }
+}
+
+// Ping-pong Stockham passes: pass p gathers from one per-warp buffer (pass 0: from global,
+// applying the taper and the zero padding) and scatters to the other, so a pass with more than
+// 32 butterflies never overwrites a source another lane group still has to read.
+template <int N2, int Ns>
+struct PassesPP {
+  static constexpr int rem = N2 / Ns;
+  static constexpr int R = fft::radix_for(rem);
+  static XM_DEVICE void run(const float* __restrict__ row, const float* __restrict__ taper, int win, bool aligned8,
+                            float* are, float* aim, float* bre, float* bim, const float* __restrict__ tw_re,
+                            const float* __restrict__ tw_im, int lane) {
+    // reads (are, aim) [or global when Ns == 1], writes (bre, bim)
+    constexpr int NB = N2 / R;
+#pragma unroll
+    for (int j0 = 0; j0 < NB; j0 += 32) {
+      const int j = j0 + lane;
+      if (NB >= 32 || j < NB) {
+        float re[R], im[R];
+        if (Ns == 1) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int n = j + r * NB;
+            float x0 = 0.f, x1 = 0.f;
+            if (2 * n + 1 < win) {
+              if (aligned8) {
+                const float2 v = *reinterpret_cast<const float2*>(row + 2 * n);
+                x0 = v.x; x1 = v.y;
+              } else {
+                x0 = row[2 * n]; x1 = row[2 * n + 1];
+              }
+              const float2 tp = *reinterpret_cast<const float2*>(taper + 2 * n);
+              x0 *= tp.x; x1 *= tp.y;
+            } else if (2 * n < win) {
+              x0 = row[2 * n] * taper[2 * n];
+            }
+            re[r] = x0; im[r] = x1;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int i = fft::pad_idx(j + r * NB);
+            re[r] = are[i]; im[r] = aim[i];
+          }
+        }
+        fft::twiddle_and_butterfly<R>(re, im, j % Ns, Ns, N2, tw_re, tw_im);
+        const int b = fft::scatter_base(j, Ns, R);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = fft::pad_idx(b + r * Ns);
+          bre[i] = re[r]; bim[i] = im[r];
+        }
+      }
+    }
+    __syncwarp();
+    PassesPP<N2, Ns * R>::run(row, taper, win, aligned8, bre, bim, are, aim, tw_re, tw_im, lane);
+  }
+  // number of passes from this Ns on (to know which buffer holds the result)
+  static constexpr int count = 1 + PassesPP<N2, Ns * R>::count;
+};
+template <int N2>
+struct PassesPP<N2, N2> {
+  static XM_DEVICE void run(const float*, const float*, int, bool, float*, float*, float*, float*, const float*,
+                            const float*, int) {}
+  static constexpr int count = 0;
+};
+
+template <int N2>
+__global__ void __launch_bounds__(kBpWarps * 32)
+bandpower_kernel(const float* __restrict__ rec, long long n_rows, long long C, long long n_samples, long long n_win,
+                 int win, long long hop, const float* __restrict__ taper, float scale,
+                 const int* __restrict__ band_bins, int n_bands, float* __restrict__ power) {
+  constexpr int PL = N2 + (N2 >> 5) + 1;
+  extern __shared__ float smem[];
+  float* tw_re = smem;             // N2
+  float* tw_im = smem + N2;        // N2
+  float* bufs = smem + 2 * N2;     // per warp: 4 * PL (A.re, A.im, B.re, B.im)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = threadIdx.x; m < N2; m += blockDim.x) {
+    float s, c;
+    sincospif(-2.0f * (float)m / (float)N2, &s, &c);
+    tw_re[m] = c; tw_im[m] = s;
+  }
+  __syncthreads();
+  float* are = bufs + warp * 4 * PL;
+  float* aim = are + PL;
+  float* bre = aim + PL;
+  float* bim = bre + PL;
+  // the first pass writes B, the second A, ...: result buffer by pass-count parity
+  constexpr int NP = PassesPP<N2, 1>::count;
+  float* zre = (NP & 1) ? bre : are;
+  float* zim = (NP & 1) ? bim : aim;
+
+  int lo = 1 << 30, hi = 0;
+  for (int b = 0; b < n_bands; ++b) {
+    lo = min(lo, band_bins[2 * b]);
+    hi = max(hi, band_bins[2 * b + 1]);
+  }
+  const int nfft = 2 * N2;
+
+  for (long long row = blockIdx.x * (long long)kBpWarps + warp; row < n_rows; row += (long long)gridDim.x * kBpWarps) {
+    const long long g = row / C, c = row - g * C;
+    const long long r = g / n_win, w = g - r * n_win;
+    const float* src = rec + (r * C + c) * n_samples + w * hop;
+    const bool aligned8 = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+    PassesPP<N2, 1>::run(src, taper, win, aligned8, are, aim, bre, bim, tw_re, tw_im, lane);
+
+    float acc[kMaxBands];
+#pragma unroll
+    for (int b = 0; b < kMaxBands; ++b) acc[b] = 0.f;
+    for (int k = lo + lane; k < hi; k += 32) {
+      // X[k] = 0.5*[(Z[k] + conj(Z[N2-k])) - i*e^{-2 pi i k/nfft} * (Z[k] - conj(Z[N2-k]))]
+      const int k1 = (k == N2) ? 0 : k;
+      const int k2 = (k == 0 || k == N2) ? 0 : N2 - k;
+      const float ar = zre[fft::pad_idx(k1)], ai = zim[fft::pad_idx(k1)];
+      const float br = zre[fft::pad_idx(k2)], bi = -zim[fft::pad_idx(k2)];
+      const float er = 0.5f * (ar + br), ei = 0.5f * (ai + bi);
+      const float dr = 0.5f * (ar - br), di = 0.5f * (ai - bi);
+      float s, co;
+      sincospif(-2.0f * (float)k / (float)nfft, &s, &co);
+      // -i * (co + i s) * (dr + i di) = (co*di + s*dr) + i*(s*di - co*dr)
+      const float xr = er + (co * di + s * dr);
+      const float xi = ei + (s * di - co * dr);
+      float pw = xr * xr + xi * xi;
+      if (k != 0 && k != N2) pw *= 2.0f;
+#pragma unroll
+      for (int b = 0; b < kMaxBands; ++b)
+        if (b < n_bands && k >= band_bins[2 * b] && k < band_bins[2 * b + 1]) acc[b] += pw;
+    }
+#pragma unroll
+    for (int b = 0; b < kMaxBands; ++b) {
+      if (b < n_bands) {
+        const float t = warp_sum(acc[b]);
+        if (lane == 0) power[row * n_bands + b] = t * scale;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int N2>
+static int launch_bandpower(const float* rec, long long n_rows, long long C, long long n_samples, long long n_win, int win,
+                            long long hop, const float* taper, float scale, const int* band_bins, int n_bands,
+                            float* power, cudaStream_t st) {
+  constexpr int PL = N2 + (N2 >> 5) + 1;
+  const size_t smem = (size_t)(2 * N2 + kBpWarps * 4 * PL) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(bandpower_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return XM_ERR_LAUNCH;
+  }
+  long long blocks = (n_rows + kBpWarps - 1) / kBpWarps;
+  const long long cap = (long long)kNumSMs * 8;  // persistent-ish: a few CTAs per SM, grid-stride over rows
+  if (blocks > cap) blocks = cap;
+  bandpower_kernel<N2><<<(unsigned)blocks, kBpWarps * 32, smem, st>>>(rec, n_rows, C, n_samples, n_win, win, hop, taper,
+                                                                      scale, band_bins, n_bands, power);
+  return check_launch();
+}
+
+}  // namespace xm
+
+using namespace xm;
+
+extern "C" {
+
+int xm_window_index_i64(int64_t n_rec, int64_t n_samples, int64_t win, int64_t hop, const int64_t* rec_labels,
+                        const int64_t* rec_subjects, int64_t* starts, int64_t* rec_ids, int64_t* labels,
+                        int64_t* subjects, void* stream) {
+  if (n_rec <= 0 || win <= 0 || hop <= 0 || n_samples < win) return XM_ERR_INVALID;
+  const long long n_win = (n_samples - win) / hop + 1;
+  const long long total = n_rec * n_win;
+  long long blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  window_index_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      n_rec, n_win, hop, (const long long*)rec_labels, (const long long*)rec_subjects, (long long*)starts,
+      (long long*)rec_ids, (long long*)labels, (long long*)subjects);
+  return check_launch();
+}
+
+int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
+                         float* out, int64_t ld_out, int round_tf32, void* stream) {
+  if (!rec || !out || n_rec <= 0 || C <= 0 || win <= 0 || hop <= 0 || n_samples < win || ld_out < win)
+    return XM_ERR_INVALID;
+  const long long n_win = (n_samples - win) / hop + 1;
+  const long long rows = n_rec * n_win * C;
+  if (rows > 2147483647ll) return XM_ERR_UNSUPPORTED;
+  window_gather_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(rec, C, n_samples, n_win, win, hop, out, ld_out,
+                                                                         round_tf32);
+  return check_launch();
+}
+
+int xm_bandpower_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
+                     int64_t nfft, float fs, const float* taper, float taper_sumsq, const int32_t* band_bins,
+                     int n_bands, float* power, void* stream) {
+  (void)fs;  // PSD * bin width: fs cancels; kept in the signature for the reference formula
+  if (!rec || !taper || !band_bins || !power || n_rec <= 0 || C <= 0 || win <= 0 || hop <= 0 || n_samples < win)
+    return XM_ERR_INVALID;
+  if (n_bands <= 0 || n_bands > kMaxBands || nfft < win || !(taper_sumsq > 0.f)) return XM_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(taper) & 7) return XM_ERR_INVALID;
+  const long long n_win = (n_samples - win) / hop + 1;
+  const long long rows = n_rec * n_win * C;
+  const float scale = 1.0f / ((float)nfft * taper_sumsq);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nfft) {
+    case 64: return launch_bandpower<32>(rec, rows, C, n_samples, n_win, (int)win, hop, taper, scale, band_bins, n_bands, power, st);
+    case 128: return launch_bandpower<64>(rec, rows, C, n_samples, n_win, (int)win, hop, taper, scale, band_bins, n_bands, power, st);
+    case 256: return launch_bandpower<128>(rec, rows, C, n_samples, n_win, (int)win, hop, taper, scale, band_bins, n_bands, power, st);
+    case 512: return launch_bandpower<256>(rec, rows, C, n_samples, n_win, (int)win, hop, taper, scale, band_bins, n_bands, power, st);
+    case 1024: return launch_bandpower<512>(rec, rows, C, n_samples, n_win, (int)win, hop, taper, scale, band_bins, n_bands, power, st);
+    case 2048: return launch_bandpower<1024>(rec, rows, C, n_samples, n_win, (int)win, hop, taper, scale, band_bins, n_bands, power, st);
+  }
+  return XM_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Shared helpers for the xmodal-b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/xmodal_b200.h"
+
+#ifndef XM_DEVICE
+#define XM_DEVICE __device__ __forceinline__
+#endif
+
+namespace xm {
+
+// Last CUDA runtime error seen by a launcher in this process (diagnostic only).
+extern int g_last_cuda_error;
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return XM_ERR_LAUNCH;
+  }
+  return XM_OK;
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+constexpr int kNumSMs = 148;
+
+XM_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+XM_DEVICE double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+XM_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Round-to-nearest fp32 -> tf32 (kept in an fp32 container). Tensor cores read the top 19
+// bits only; rounding at the producer removes the truncation bias from the next contraction.
+XM_DEVICE float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+XM_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+XM_DEVICE float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Counter-based dropout mask: one 32-bit hash per element (murmur3 finaliser over a
+// seed-keyed index).  keep  <=>  hash >= threshold, threshold = p * 2^32.
+XM_DEVICE uint32_t hash_u32(uint64_t idx, uint64_t seed) {
+  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+XM_DEVICE bool dropout_keep(uint64_t idx, uint64_t seed, uint32_t threshold) {
+  return hash_u32(idx, seed) >= threshold;
+}
+
+// act codes shared with the host (include/xmodal_b200.h): 0 none, 1 relu, 2 gelu(erf)
+XM_DEVICE float apply_act(float x, int act) {
+  if (act == XM_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == XM_ACT_GELU) return gelu_erf(x);
+  return x;
+}
+XM_DEVICE float act_grad(float x, int act) {
+  if (act == XM_ACT_RELU) return x > 0.0f ? 1.0f : 0.0f;
+  if (act == XM_ACT_GELU) return gelu_erf_grad(x);
+  return 1.0f;
+}
+
+}  // namespace xm

@@ -1,0 +1,432 @@
+"""Raw (non-autograd) device ops: thin tensor-level wrappers over the C ABI.
+
+Every function takes CUDA fp32 tensors, allocates its outputs/workspaces with torch (device
+memory plumbing only), enqueues the hand-written kernels on torch's current stream and returns.
+No function here has a CPU path: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU}
+
+_launches = 0  # C-ABI calls made (bench.py reports it as gpu_launches lower bound)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def act_code(act) -> int:
+    return act if isinstance(act, int) else _ACT[act]
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.XmodalError("xmodal-b200 ops need CUDA tensors (no CPU fallback on this path)")
+        if t.dtype != torch.float32:
+            raise _lib.XmodalError(f"expected float32, got {t.dtype}")
+
+
+def _call(name, *args):
+    global _launches
+    _launches += 1
+    _lib.call(name, *args)
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D tensor with unit inner stride, 16-B aligned base and row pitch % 4 == 0 (TMA-readable)."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.data_ptr() % 16 != 0 or t.stride(0) < t.size(1):
+        k = t.size(1)
+        kp = (k + 3) // 4 * 4
+        buf = torch.zeros(t.size(0), kp, device=t.device, dtype=t.dtype)
+        buf[:, :k] = t
+        return buf[:, :k]
+    return t
+
+
+def pitch4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def empty_pitched(shape: Tuple[int, ...], device) -> torch.Tensor:
+    """(..., T) fp32 tensor whose last-dim pitch is a multiple of 4 elements (a view if T % 4)."""
+    *lead, T = shape
+    Tp = pitch4(T)
+    buf = torch.empty(*lead, Tp, device=device, dtype=torch.float32)
+    return buf if Tp == T else buf[..., :T]
+
+
+def as_pitched(t: torch.Tensor) -> torch.Tensor:
+    """(B, C, T) tensor laid out as rows of pitch % 4 == 0, rows densely stacked, 16-B aligned."""
+    B, C, T = t.shape
+    ld = t.stride(2) == 1 and t.stride(1)
+    ok = ld and ld % 4 == 0 and t.stride(0) == C * ld and t.data_ptr() % 16 == 0
+    if ok:
+        return t
+    out = empty_pitched((B, C, T), t.device)
+    out.copy_(t)
+    return out
+
+
+# ------------------------------------------------------------------ linear
+def linear_fwd(x, w, bias=None, act=None, round_out=False, splits: int = 0):
+    _chk(x, w, bias)
+    x, w = _rowmajor(x), _rowmajor(w)
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    if splits <= 0:  # split K only when the output grid alone cannot fill the GPU
+        tiles = ((M + 127) // 128) * max(1, (N + 255) // 256)
+        splits = 1 if tiles >= 74 or K < 2048 else min(8, max(1, 148 // tiles), K // 512)
+    ws = torch.empty(splits * M * N, device=x.device, dtype=torch.float32) if splits > 1 else None
+    _call("xm_linear_fwd_f32", _p(x), _p(w), _p(bias), _p(y), M, N, K, x.stride(0), w.stride(0), y.stride(0),
+          act_code(act), int(round_out), splits, _p(ws), _stream())
+    return y
+
+
+def linear_dgrad(dy, w, round_out=False):
+    _chk(dy, w)
+    dy, w = _rowmajor(dy), _rowmajor(w)
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+    _call("xm_linear_dgrad_f32", _p(dy), _p(w), _p(dx), M, N, K, dy.stride(0), w.stride(0), dx.stride(0),
+          int(round_out), _stream())
+    return dx
+
+
+def linear_wgrad(dy, x, need_bias=True, splits: int = 0):
+    _chk(dy, x)
+    dy, x = _rowmajor(dy), _rowmajor(x)
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.empty(N, K, device=dy.device, dtype=torch.float32)
+    db = torch.empty(N, device=dy.device, dtype=torch.float32) if need_bias else None
+    if splits <= 0:
+        tiles = ((N + 127) // 128) * max(1, (K + 255) // 256)
+        splits = 1 if tiles >= 74 or M < 1024 else min(16, max(1, 148 // tiles), M // 256)
+    ws = torch.empty(splits * N * K, device=dy.device, dtype=torch.float32) if splits > 1 else None
+    _call("xm_linear_wgrad_f32", _p(dy), _p(x), _p(dw), _p(db), M, N, K, dy.stride(0), x.stride(0), dw.stride(0),
+          splits, _p(ws), _stream())
+    return dw, db
+
+
+# ------------------------------------------------------------------ conv1d
+def conv1d_pack_weight(w):
+    """(Cout, Cin, taps) -> tf32-rounded (taps, Cout, ldk) and (taps, Cin, ldt) operand copies."""
+    _chk(w)
+    w = w.contiguous()
+    Cout, Cin, taps = w.shape
+    ldk, ldt = pitch4(Cin), pitch4(Cout)
+    wk = torch.empty(taps, Cout, ldk, device=w.device, dtype=torch.float32)
+    wt = torch.empty(taps, Cin, ldt, device=w.device, dtype=torch.float32)
+    _call("xm_conv1d_pack_weight_f32", _p(w), Cout, Cin, taps, _p(wk), ldk, _p(wt), ldt, _stream())
+    return wk, wt
+
+
+def conv1d_fwd(x, wk, bias, Cout, round_out=False):
+    _chk(x, wk, bias)
+    x = as_pitched(x)
+    B, Cin, T = x.shape
+    taps, _, ldk = wk.shape
+    y = empty_pitched((B, Cout, T), x.device)
+    _call("xm_conv1d_fwd_f32", _p(x), _p(wk), _p(bias), _p(y), B, Cin, Cout, T, taps, x.stride(1), ldk, y.stride(1),
+          int(round_out), _stream())
+    return y
+
+
+def conv1d_dgrad(dy, wt, Cin, round_out=False):
+    _chk(dy, wt)
+    dy = as_pitched(dy)
+    B, Cout, T = dy.shape
+    taps, _, ldt = wt.shape
+    dx = empty_pitched((B, Cin, T), dy.device)
+    _call("xm_conv1d_dgrad_f32", _p(dy), _p(wt), _p(dx), B, Cin, Cout, T, taps, dy.stride(1), ldt, dx.stride(1),
+          int(round_out), _stream())
+    return dx
+
+
+def conv1d_wgrad(dy, x, taps, need_bias=True):
+    _chk(dy, x)
+    dy, x = as_pitched(dy), as_pitched(x)
+    B, Cout, T = dy.shape
+    Cin = x.shape[1]
+    n_ws = _lib.lib().xm_conv1d_wgrad_workspace(B, Cin, Cout, taps)
+    ws = torch.empty(n_ws, device=dy.device, dtype=torch.float32)
+    dw = torch.empty(Cout, Cin, taps, device=dy.device, dtype=torch.float32)
+    db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if need_bias else None
+    _call("xm_conv1d_wgrad_f32", _p(dy), _p(x), _p(dw), _p(db), B, Cin, Cout, T, taps, dy.stride(1), x.stride(1),
+          _p(ws), _stream())
+    return dw, db
+
+
+# ------------------------------------------------------------------ batch norm + act (+pool, +dropout)
+def bn_partial_stats(y):
+    """y (B, C, T) pitched or (B, C): per-split {sum, sumsq} doubles, shape (nsplit, C, 2)."""
+    _chk(y)
+    if y.dim() == 2:
+        B, C = y.shape
+        T, ld = 1, 1
+        assert y.is_contiguous()
+    else:
+        B, C, T = y.shape
+        ld = y.stride(1)
+    ns = _lib.lib().xm_bn_nsplit(B, C, T)
+    part = torch.empty(ns, C, 2, device=y.device, dtype=torch.float64)
+    _call("xm_bn_partial_stats_f32", _p(y), B, C, T, ld, _p(part), _stream())
+    return part
+
+
+def bn_finalize_stats(part, count, eps, running_mean=None, running_var=None, momentum=0.1):
+    ns, C, _ = part.shape
+    mean = torch.empty(C, device=part.device, dtype=torch.float32)
+    invstd = torch.empty(C, device=part.device, dtype=torch.float32)
+    _call("xm_bn_finalize_stats", _p(part), ns, C, float(count), float(eps), _p(mean), _p(invstd), _p(running_mean),
+          _p(running_var), float(momentum), _stream())
+    return mean, invstd
+
+
+def _bn_dims(y):
+    if y.dim() == 2:
+        B, C = y.shape
+        return B, C, 1, 1
+    B, C, T = y.shape
+    return B, C, T, y.stride(1)
+
+
+def bn_act_fwd(y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, drop_before_pool=False,
+               round_out=False):
+    _chk(y, mean, invstd, gamma, beta)
+    B, C, T, ld = _bn_dims(y)
+    if y.dim() == 2:
+        out = torch.empty_like(y)
+        ldo = 1
+    else:
+        out = empty_pitched((B, C, T // 2 if pool == 2 else T), y.device)
+        ldo = out.stride(1)
+    _call("xm_bn_act_fwd_f32", _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(out), B, C, T, ld, ldo,
+          act_code(act), pool, float(drop_p), int(seed), int(drop_before_pool), int(round_out), _stream())
+    return out
+
+
+def bn_act_bwd_reduce(dout, y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, drop_before_pool=False):
+    _chk(dout, y)
+    B, C, T, ld = _bn_dims(y)
+    ldo = 1 if y.dim() == 2 else dout.stride(1)
+    ns = _lib.lib().xm_bn_nsplit(B, C, T)
+    part = torch.empty(ns, C, 2, device=y.device, dtype=torch.float64)
+    _call("xm_bn_act_bwd_reduce_f32", _p(dout), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), B, C, T, ld, ldo,
+          act_code(act), pool, float(drop_p), int(seed), int(drop_before_pool), _p(part), _stream())
+    return part
+
+
+def bn_bwd_finalize(part):
+    ns, C, _ = part.shape
+    dbeta = torch.empty(C, device=part.device, dtype=torch.float32)
+    dgamma = torch.empty(C, device=part.device, dtype=torch.float32)
+    _call("xm_bn_bwd_finalize", _p(part), ns, C, _p(dbeta), _p(dgamma), _stream())
+    return dbeta, dgamma
+
+
+def bn_act_bwd_apply(dout, y, mean, invstd, gamma, beta, dbeta, dgamma, count, act, pool=0, drop_p=0.0, seed=0,
+                     drop_before_pool=False, round_out=False):
+    B, C, T, ld = _bn_dims(y)
+    ldo = 1 if y.dim() == 2 else dout.stride(1)
+    dy = torch.empty_like(y) if y.dim() == 2 else empty_pitched((B, C, T), y.device)
+    _call("xm_bn_act_bwd_apply_f32", _p(dout), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(dbeta),
+          _p(dgamma), float(count), _p(dy), B, C, T, ld, ldo, act_code(act), pool, float(drop_p), int(seed),
+          int(drop_before_pool), int(round_out), _stream())
+    return dy
+
+
+# ------------------------------------------------------------------ layer norm + act
+def ln_act_fwd(x, gamma, beta, eps, act, drop_p=0.0, seed=0):
+    _chk(x, gamma, beta)
+    x = x.contiguous()
+    M, D = x.shape
+    out = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    _call("xm_ln_act_fwd_f32", _p(x), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), M, D, float(eps),
+          act_code(act), float(drop_p), int(seed), _stream())
+    return out, mean, rstd
+
+
+def ln_act_bwd(dout, x, gamma, beta, mean, rstd, act, drop_p=0.0, seed=0):
+    _chk(dout, x)
+    dout, x = dout.contiguous(), x.contiguous()
+    M, D = x.shape
+    nblk = _lib.lib().xm_ln_nblk(M)
+    dx = torch.empty_like(x)
+    dgp = torch.empty(nblk, D, device=x.device, dtype=torch.float32)
+    dbp = torch.empty(nblk, D, device=x.device, dtype=torch.float32)
+    _call("xm_ln_act_bwd_f32", _p(dout), _p(x), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(dx), _p(dgp), _p(dbp), M,
+          D, act_code(act), float(drop_p), int(seed), _stream())
+    return dx, colsum(dgp), colsum(dbp)
+
+
+# ------------------------------------------------------------------ reductions
+def colsum(x):
+    _chk(x)
+    M, N = x.shape
+    assert x.stride(1) == 1
+    out = torch.empty(N, device=x.device, dtype=torch.float32)
+    _call("xm_colsum_f32", _p(x), M, N, x.stride(0), _p(out), _stream())
+    return out
+
+
+def rowmean(x):
+    """x (..., T) with unit inner stride and uniform row pitch -> (...)"""
+    _chk(x)
+    *lead, T = x.shape
+    if x.dim() == 3:
+        assert x.stride(2) == 1 and x.stride(0) == x.size(1) * x.stride(1)
+        ld = x.stride(1)
+    else:
+        assert x.is_contiguous()
+        ld = T
+    R = 1
+    for s in lead:
+        R *= s
+    out = torch.empty(*lead, device=x.device, dtype=torch.float32)
+    _call("xm_rowmean_f32", _p(x), R, T, ld, _p(out), _stream())
+    return out
+
+
+def rowmean_bwd(dout, T):
+    _chk(dout)
+    dout = dout.contiguous()
+    dx = empty_pitched((*dout.shape, T), dout.device)
+    R = dout.numel()
+    _call("xm_rowmean_bwd_f32", _p(dout), R, T, dx.stride(-2), _p(dx), _stream())
+    return dx
+
+
+# ------------------------------------------------------------------ l2norm / similarity / infonce
+def l2norm_fwd(x, eps=1e-12):
+    _chk(x)
+    x = x.contiguous()
+    M, D = x.shape
+    xn = torch.empty_like(x)
+    inv = torch.empty(M, device=x.device, dtype=torch.float32)
+    _call("xm_l2norm_fwd_f32", _p(x), _p(xn), _p(inv), M, D, float(eps), _stream())
+    return xn, inv
+
+
+def l2norm_bwd(dxn, xn, inv):
+    _chk(dxn, xn, inv)
+    dxn = dxn.contiguous()
+    M, D = xn.shape
+    dx = torch.empty_like(xn)
+    _call("xm_l2norm_bwd_f32", _p(dxn), _p(xn), _p(inv), _p(dx), M, D, _stream())
+    return dx
+
+
+def similarity(a, b, inv_tau):
+    _chk(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    Ml, D = a.shape
+    Ng = b.shape[0]
+    S = torch.empty(Ml, Ng, device=a.device, dtype=torch.float32)
+    _call("xm_similarity_f32", _p(a), _p(b), _p(S), Ml, Ng, D, float(inv_tau), _stream())
+    return S
+
+
+def infonce_lse(a, b, inv_tau, diag_off=0):
+    _chk(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    Ml, D = a.shape
+    Ng = b.shape[0]
+    tn = _lib.lib().xm_infonce_tile_n()
+    ws = torch.empty(Ml * ((Ng + tn - 1) // tn), device=a.device, dtype=torch.float32)
+    lse = torch.empty(Ml, device=a.device, dtype=torch.float32)
+    diag = torch.empty(Ml, device=a.device, dtype=torch.float32)
+    _call("xm_infonce_lse_f32", _p(a), _p(b), _p(lse), _p(diag), Ml, Ng, D, float(inv_tau), int(diag_off), _p(ws),
+          _stream())
+    return lse, diag
+
+
+def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
+    _chk(a, b, lse_row, lse_col)
+    a, b = a.contiguous(), b.contiguous()
+    Ml, D = a.shape
+    Ng = b.shape[0]
+    G = torch.empty(Ml, Ng, device=a.device, dtype=torch.float32)
+    _call("xm_infonce_grad_f32", _p(a), _p(b), _p(lse_row), _p(lse_col), _p(G), Ml, Ng, D, float(inv_tau),
+          int(diag_off), float(coef), _stream())
+    return G
+
+
+# ------------------------------------------------------------------ preprocessing
+def window_index(n_rec, n_samples, win, hop, rec_labels=None, rec_subjects=None, device="cuda"):
+    n_win = (n_samples - win) // hop + 1
+    tot = n_rec * n_win
+    mk = lambda: torch.empty(tot, device=device, dtype=torch.int64)
+    starts, rec_ids = mk(), mk()
+    labels = mk() if rec_labels is not None else None
+    subjects = mk() if rec_subjects is not None else None
+    _call("xm_window_index_i64", n_rec, n_samples, win, hop, _p(rec_labels), _p(rec_subjects), _p(starts),
+          _p(rec_ids), _p(labels), _p(subjects), _stream())
+    return starts, rec_ids, labels, subjects
+
+
+def window_gather(rec, win, hop, round_out=False):
+    _chk(rec)
+    rec = rec.contiguous()
+    R, C, n = rec.shape
+    n_win = (n - win) // hop + 1
+    out = empty_pitched((R * n_win, C, win), rec.device)
+    _call("xm_window_gather_f32", _p(rec), R, C, n, win, hop, _p(out), out.stride(1), int(round_out), _stream())
+    return out
+
+
+def bandpower(rec, win, hop, nfft, fs, taper, taper_sumsq, band_bins):
+    _chk(rec, taper)
+    rec = rec.contiguous()
+    R, C, n = rec.shape
+    n_win = (n - win) // hop + 1
+    nb = band_bins.numel() // 2
+    power = torch.empty(R * n_win, C, nb, device=rec.device, dtype=torch.float32)
+    _call("xm_bandpower_f32", _p(rec), R, C, n, win, hop, nfft, float(fs), _p(taper), float(taper_sumsq),
+          _p(band_bins), nb, _p(power), _stream())
+    return power
+
+
+def zscore(x, eps=1e-8):
+    """Per-item (dim 0) global z-score, population std."""
+    _chk(x)
+    x = x.contiguous()
+    n = x.shape[0]
+    out = torch.empty_like(x)
+    _call("xm_zscore_f32", _p(x), n, x.numel() // n, float(eps), _p(out), _stream())
+    return out
+
+
+def roi_meanstd(x):
+    _chk(x)
+    x = x.contiguous()
+    B, TR, ROI = x.shape
+    out = torch.empty(B, 2 * ROI, device=x.device, dtype=torch.float32)
+    _call("xm_roi_meanstd_f32", _p(x), B, TR, ROI, _p(out), _stream())
+    return out

@@ -1,0 +1,313 @@
+"""Kernel bring-up on a real B200: each group runs in its own subprocess (a trapped kernel leaves
+a sticky CUDA error) and prints relative errors against fp64 torch references.
+
+    python tests/gpu_bringup.py            # all groups
+    python tests/gpu_bringup.py conv_fwd   # one group, in-process
+
+Not collected by pytest (the parity tests proper are tests/test_gpu_*.py); this is the fast
+diagnostic used while developing kernels.
+"""
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def rel(a, b):
+    import torch
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def g_linear_fwd():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(0)
+    for (M, N, K, act, splits) in [(128, 64, 64, None, 1), (300, 96, 200, "gelu", 1), (4096, 128, 400, "relu", 1),
+                                   (256, 128, 4096, None, 4), (70, 2, 32, None, 1), (512, 256, 128, None, 1),
+                                   (1000, 320, 96, None, 1)]:
+        x = torch.randn(M, K, device="cuda")
+        w = torch.randn(N, K, device="cuda") / K ** 0.5
+        b = torch.randn(N, device="cuda")
+        y = ops.linear_fwd(x, w, b, act=act, splits=splits)
+        ref = x.double() @ w.double().t() + b.double()
+        if act == "gelu":
+            ref = torch.nn.functional.gelu(ref)
+        if act == "relu":
+            ref = torch.relu(ref)
+        print(f"linear_fwd M{M} N{N} K{K} act={act} splits={splits}: rel={rel(y, ref):.3e}", flush=True)
+
+
+def g_linear_dgrad():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(1)
+    for (M, N, K) in [(128, 32, 32), (300, 96, 200), (4096, 128, 400), (256, 64, 128), (512, 2, 64)]:
+        dy = torch.randn(M, N, device="cuda")
+        w = torch.randn(N, K, device="cuda")
+        dx = ops.linear_dgrad(dy, w)
+        ref = dy.double() @ w.double()
+        print(f"linear_dgrad M{M} N{N} K{K}: rel={rel(dx, ref):.3e}", flush=True)
+
+
+def g_linear_wgrad():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(2)
+    for (M, N, K, splits) in [(128, 128, 32, 1), (300, 96, 200, 1), (4096, 128, 400, 4), (256, 64, 128, 1),
+                              (2048, 128, 4000, 2), (512, 2, 64, 1)]:
+        dy = torch.randn(M, N, device="cuda")
+        x = torch.randn(M, K, device="cuda")
+        dw, db = ops.linear_wgrad(dy, x, splits=splits)
+        ref = dy.double().t() @ x.double()
+        print(f"linear_wgrad M{M} N{N} K{K} splits={splits}: rel={rel(dw, ref):.3e} db={rel(db, dy.double().sum(0)):.3e}",
+              flush=True)
+
+
+def _conv_cases():
+    return [(2, 32, 32, 128, 3), (3, 64, 64, 500, 7), (2, 64, 128, 500, 5), (2, 128, 128, 250, 3), (2, 48, 96, 250, 5),
+            (2, 18, 48, 500, 7), (1, 192, 128, 100, 1)]
+
+
+def g_conv_fwd():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(3)
+    for (B, Cin, Cout, T, k) in _conv_cases():
+        x = torch.randn(B, Cin, T, device="cuda")
+        w = torch.randn(Cout, Cin, k, device="cuda") / (Cin * k) ** 0.5
+        b = torch.randn(Cout, device="cuda")
+        wk, wt = ops.conv1d_pack_weight(w)
+        y = ops.conv1d_fwd(x, wk, b, Cout)
+        ref = torch.nn.functional.conv1d(x.double(), w.double(), b.double(), padding=k // 2)
+        print(f"conv_fwd B{B} Cin{Cin} Cout{Cout} T{T} k{k}: rel={rel(y, ref):.3e}", flush=True)
+
+
+def g_conv_dgrad():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(4)
+    for (B, Cin, Cout, T, k) in _conv_cases():
+        dy = torch.randn(B, Cout, T, device="cuda")
+        w = torch.randn(Cout, Cin, k, device="cuda") / (Cin * k) ** 0.5
+        wk, wt = ops.conv1d_pack_weight(w)
+        dx = ops.conv1d_dgrad(dy, wt, Cin)
+        ref = torch.nn.functional.conv_transpose1d(dy.double(), w.double(), padding=k // 2)
+        print(f"conv_dgrad B{B} Cin{Cin} Cout{Cout} T{T} k{k}: rel={rel(dx, ref):.3e}", flush=True)
+
+
+def g_conv_wgrad():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(5)
+    for (B, Cin, Cout, T, k) in _conv_cases() + [(300, 64, 64, 500, 7)]:
+        x = torch.randn(B, Cin, T, device="cuda")
+        dy = torch.randn(B, Cout, T, device="cuda")
+        dw, db = ops.conv1d_wgrad(dy, x, k)
+        xd = x.double().requires_grad_(False)
+        wd = torch.zeros(Cout, Cin, k, device="cuda", dtype=torch.float64, requires_grad=True)
+        out = torch.nn.functional.conv1d(xd, wd, None, padding=k // 2)
+        (gw,) = torch.autograd.grad(out, wd, dy.double())
+        print(f"conv_wgrad B{B} Cin{Cin} Cout{Cout} T{T} k{k}: rel={rel(dw, gw):.3e} db={rel(db, dy.double().sum((0, 2))):.3e}",
+              flush=True)
+
+
+def g_infonce():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(6)
+    for (Ml, Ng, D, off) in [(128, 128, 128, 0), (256, 256, 128, 0), (200, 600, 64, 200), (4096, 4096, 128, 0)]:
+        e = torch.randn(Ml, D, device="cuda")
+        f = torch.randn(Ng, D, device="cuda")
+        en, einv = ops.l2norm_fwd(e)
+        fn, finv = ops.l2norm_fwd(f)
+        ref_en = torch.nn.functional.normalize(e.double(), dim=1)
+        print(f"l2norm rel={rel(en, ref_en):.3e}")
+        it = 1 / 0.07
+        S = ops.similarity(en, fn, it)
+        Sref = en.double() @ fn.double().t() * it
+        lse, diag = ops.infonce_lse(en, fn, it, off)
+        lref = torch.logsumexp(Sref, dim=1)
+        dref = Sref[torch.arange(Ml), torch.arange(Ml) + off]
+        lse_col = torch.logsumexp(Sref, dim=0).float()
+        G = ops.infonce_grad(en, fn, lse, lse_col, it, off, 0.5 / Ml)
+        Gref = (torch.exp(Sref - lref[:, None]) + torch.exp(Sref - lse_col.double()[None, :]))
+        Gref[torch.arange(Ml), torch.arange(Ml) + off] -= 2
+        Gref *= 0.5 / Ml
+        print(f"infonce Ml{Ml} Ng{Ng} D{D}: S rel={rel(S, Sref):.3e} lse maxabs={float((lse.double()-lref).abs().max()):.3e} "
+              f"diag maxabs={float((diag.double()-dref).abs().max()):.3e} G rel={rel(G, Gref):.3e}", flush=True)
+        d = torch.randn(Ml, D, device="cuda")
+        dx = ops.l2norm_bwd(d, en, einv)
+        ed = e.double().requires_grad_(True)
+        (gx,) = torch.autograd.grad(torch.nn.functional.normalize(ed, dim=1), ed, d.double())
+        print(f"l2norm_bwd rel={rel(dx, gx):.3e}", flush=True)
+
+
+def g_bandpower():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(7)
+    for (R, C, n, win, hop, nfft, fs) in [(2, 4, 3000, 1024, 512, 1024, 1000.0), (3, 8, 2000, 500, 250, 512, 250.0),
+                                          (1, 3, 1001, 100, 37, 128, 128.0), (2, 128, 8192, 1024, 512, 1024, 1000.0),
+                                          (1, 2, 5000, 2000, 1000, 2048, 1000.0)]:
+        rec = torch.randn(R, C, n, device="cuda")
+        taper = torch.hann_window(win, periodic=True, device="cuda", dtype=torch.float64)
+        bands = [(4, 8), (8, 13), (13, 30)]
+        import math
+        bins = []
+        for lo, hi in bands:
+            bins += [math.ceil(lo * nfft / fs), math.ceil(hi * nfft / fs)]
+        bins_t = torch.tensor(bins, device="cuda", dtype=torch.int32)
+        tp32 = taper.float().contiguous()
+        sumsq = float((tp32.double() ** 2).sum())
+        p = ops.bandpower(rec, win, hop, nfft, fs, tp32, sumsq, bins_t)
+        wins = rec.double().unfold(2, win, hop)  # (R, C, n_win, win)
+        X = torch.fft.rfft(wins * tp32.double(), n=nfft)
+        P = X.abs() ** 2
+        P[..., 1:nfft // 2] *= 2
+        P = P / (nfft * sumsq)
+        ref = torch.stack([P[..., bins[2 * i]:bins[2 * i + 1]].sum(-1) for i in range(3)], -1)  # (R,C,nw,3)
+        ref = ref.permute(0, 2, 1, 3).reshape(-1, C, 3)
+        print(f"bandpower R{R} C{C} n{n} win{win} hop{hop} nfft{nfft}: rel={rel(p, ref):.3e} "
+              f"maxrel={float(((p.double()-ref).abs()/ref).max()):.3e}", flush=True)
+        st, rid, lab, sub = ops.window_index(R, n, win, hop, torch.arange(R, device='cuda') % 2,
+                                             torch.arange(R, device='cuda') + 100)
+        nw = (n - win) // hop + 1
+        ok = bool((st == (torch.arange(R * nw, device='cuda') % nw) * hop).all() and
+                  (rid == torch.arange(R * nw, device='cuda') // nw).all() and (lab == rid % 2).all() and
+                  (sub == rid + 100).all())
+        g = ops.window_gather(rec, win, hop)
+        okg = bool((g == rec.unfold(2, win, hop).permute(0, 2, 1, 3).reshape(-1, C, win)).all())
+        print(f"  window_index exact={ok} gather exact={okg}", flush=True)
+
+
+def _bn_ref(y, gamma, beta, act, pool, eps=1e-5):
+    import torch
+    F = torch.nn.functional
+    z = F.batch_norm(y, None, None, gamma, beta, True, 0.1, eps)
+    a = F.gelu(z) if act == "gelu" else torch.relu(z) if act == "relu" else z
+    if pool == 2:
+        a = F.max_pool1d(a, 2)
+    return a
+
+
+def g_bn():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(8)
+    for (shape, act, pool) in [((4, 16, 100), "gelu", 0), ((8, 64, 500), "gelu", 2), ((3, 48, 250), "gelu", 2),
+                               ((64, 128), "relu", 0), ((5, 7, 33), "gelu", 0)]:
+        y = torch.randn(*shape, device="cuda") * 2 + 0.5
+        C = shape[1]
+        gamma = torch.rand(C, device="cuda") + 0.5
+        beta = torch.randn(C, device="cuda")
+        yp = ops.as_pitched(y) if y.dim() == 3 else y
+        part = ops.bn_partial_stats(yp)
+        cnt = y.numel() // C
+        rm = torch.zeros(C, device="cuda")
+        rv = torch.ones(C, device="cuda")
+        mean, invstd = ops.bn_finalize_stats(part, cnt, 1e-5, rm, rv, 0.1)
+        out = ops.bn_act_fwd(yp, mean, invstd, gamma, beta, act, pool)
+        yd = y.double().requires_grad_(True)
+        gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+        ref = _bn_ref(yd, gd, bd, act, pool)
+        dout = torch.randn_like(out)
+        gy, gg, gb = torch.autograd.grad(ref, (yd, gd, bd), dout.double())
+        doutp = ops.as_pitched(dout) if dout.dim() == 3 else dout
+        part2 = ops.bn_act_bwd_reduce(doutp, yp, mean, invstd, gamma, beta, act, pool)
+        dbeta, dgamma = ops.bn_bwd_finalize(part2)
+        dy = ops.bn_act_bwd_apply(doutp, yp, mean, invstd, gamma, beta, dbeta, dgamma, cnt, act, pool)
+        dims = (0, 2) if y.dim() == 3 else (0,)
+        print(f"bn {shape} act={act} pool={pool}: fwd rel={rel(out, ref):.3e} dy rel={rel(dy, gy):.3e} "
+              f"dgamma rel={rel(dgamma, gg):.3e} dbeta rel={rel(dbeta, gb):.3e} "
+              f"rmean rel={rel(rm, 0.1 * y.double().mean(dims)):.3e} rvar rel={rel(rv, 0.9 + 0.1 * y.double().var(dims, unbiased=True)):.3e}",
+              flush=True)
+    # dropout statistics + fwd/bwd mask consistency
+    y = torch.randn(8, 64, 500, device="cuda")
+    C = 64
+    gamma = torch.ones(C, device="cuda"); beta = torch.zeros(C, device="cuda")
+    mean, invstd = ops.bn_finalize_stats(ops.bn_partial_stats(y), y.numel() // C, 1e-5)
+    for dbp in (False, True):
+        out = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "none", 2, 0.3, 1234, dbp)
+        out0 = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "none", 2, 0.0, 1234, dbp)
+        if not dbp:
+            keep = (out != 0).float().mean().item()
+            ok = torch.allclose(out[out != 0], (out0 / 0.7)[out != 0], rtol=1e-5)
+            print(f"dropout(after pool) keep={keep:.4f} (want 0.7) scaled_ok={ok}", flush=True)
+        dout = torch.ones_like(out)
+        part2 = ops.bn_act_bwd_reduce(dout, y, mean, invstd, gamma, beta, "none", 2, 0.3, 1234, dbp)
+        dbeta, _ = ops.bn_bwd_finalize(part2)
+        # sum of dz equals sum over kept outputs of scale
+        expect = float((out != 0).sum()) / 0.7 if not dbp else None
+        print(f"dropout dbp={dbp} sum(dz)={float(dbeta.sum()):.1f} expect={expect}", flush=True)
+
+
+def g_ln():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(9)
+    F = torch.nn.functional
+    for (M, D, act) in [(64, 128, "gelu"), (4096, 128, "gelu"), (100, 64, "relu"), (33, 96, "gelu")]:
+        x = torch.randn(M, D, device="cuda") * 1.5 + 0.3
+        g = torch.rand(D, device="cuda") + 0.5
+        b = torch.randn(D, device="cuda")
+        out, mean, rstd = ops.ln_act_fwd(x, g, b, 1e-5, act)
+        xd, gd, bd = (t.double().requires_grad_(True) for t in (x, g, b))
+        z = F.layer_norm(xd, (D,), gd, bd, 1e-5)
+        ref = F.gelu(z) if act == "gelu" else torch.relu(z)
+        dout = torch.randn_like(out)
+        gx, gg, gb = torch.autograd.grad(ref, (xd, gd, bd), dout.double())
+        dx, dg, db = ops.ln_act_bwd(dout, x, g, b, mean, rstd, act)
+        print(f"ln M{M} D{D} {act}: fwd={rel(out, ref):.3e} dx={rel(dx, gx):.3e} dg={rel(dg, gg):.3e} db={rel(db, gb):.3e}",
+              flush=True)
+
+
+def g_misc():
+    import torch
+    from multimodal_eeg_fmri_b200 import ops
+    torch.manual_seed(10)
+    x = torch.randn(64, 100, 200, device="cuda")
+    x[0, 3, 5] = float("nan")
+    out = ops.roi_meanstd(x)
+    xd = torch.nan_to_num(x.double(), nan=0.0)
+    ref = torch.cat([xd.mean(1), xd.std(1, unbiased=False)], 1)
+    print(f"roi_meanstd rel={rel(out, ref):.3e}")
+    x = torch.randn(16, 75, 40, device="cuda") * 3 + 1
+    z = ops.zscore(x)
+    xd = x.double()
+    ref = (xd - xd.mean((1, 2), keepdim=True)) / (xd.std((1, 2), unbiased=False, keepdim=True) + 1e-8)
+    print(f"zscore rel={rel(z, ref):.3e}")
+    x = torch.randn(1000, 96, device="cuda")
+    print(f"colsum rel={rel(ops.colsum(x), x.double().sum(0)):.3e}")
+    x = torch.randn(6, 96, 250, device="cuda")
+    xp = ops.as_pitched(x)
+    print(f"rowmean rel={rel(ops.rowmean(xp), x.double().mean(2)):.3e}")
+    d = torch.randn(6, 96, device="cuda")
+    print(f"rowmean_bwd rel={rel(ops.rowmean_bwd(d, 250), (d.double() / 250)[..., None].expand(6, 96, 250)):.3e}", flush=True)
+
+
+GROUPS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("g_")}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        GROUPS[sys.argv[1]]()
+        import torch
+        torch.cuda.synchronize()
+        print(f"[{sys.argv[1]}] done", flush=True)
+        sys.exit(0)
+    rc = 0
+    for name in GROUPS:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True, timeout=240)
+            print(r.stdout, end="")
+            if r.returncode != 0:
+                rc = 1
+                print(f"[{name}] FAILED rc={r.returncode}\n{r.stderr[-3000:]}")
+        except subprocess.TimeoutExpired as e:
+            rc = 1
+            print(f"[{name}] TIMEOUT\n{(e.stdout or b'')[-2000:]}")
+        print(f"[{name}] {time.time() - t0:.1f}s", flush=True)
+    sys.exit(rc)
