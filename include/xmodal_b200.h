@@ -57,10 +57,13 @@ int xm_window_index_i64(int64_t n_rec, int64_t n_samples, int64_t win, int64_t h
                         const int64_t* rec_subjects, int64_t* starts, int64_t* rec_ids, int64_t* labels,
                         int64_t* subjects, void* stream);
 
-/* Gather windows: rec (n_rec, C, n_samples) -> out (n_rec*n_win, C, ld_out) with the first `win`
- * elements of every row valid.  round_tf32 != 0 rounds values to tf32 (feeds the conv GEMMs). */
+/* Gather windows from rec (n_rec, C, n_samples):
+ *   channels_last == 0: out (n_rec*n_win, C, ld_out >= win)   -- the reference's (C, T) sample layout
+ *   channels_last != 0: out (n_rec*n_win, win, ld_out >= C)   -- the layout the conv GEMMs consume
+ * round_tf32 != 0 rounds values to tf32 (removes the truncation bias of the first conv).
+ * With n_win == 1 (win == n_samples) this is the (B, C, T) -> (B, T, C) layout change. */
 int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
-                         float* out, int64_t ld_out, int round_tf32, void* stream);
+                         float* out, int64_t ld_out, int channels_last, int round_tf32, void* stream);
 
 /* Fused window gather + taper + real FFT (nfft = power of two in [64, 2048], >= win, zero padded) +
  * one-sided PSD + band-power reduction.  power[g, c, b] = sum_{k in [band_bins[2b], band_bins[2b+1])}
@@ -95,59 +98,64 @@ int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
                         int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------ dense Conv1d ("same" padding, stride 1)
- * EEG_CODE/enhanced_models_v4.py:128-144 ; EEG_CODE/crossmodal_v4_enhancements.py:822-834,854-866 */
+ * EEG_CODE/enhanced_models_v4.py:128-144 ; EEG_CODE/crossmodal_v4_enhancements.py:822-834,854-866
+ * Activations are CHANNELS-LAST on the device: x (B, T, C) with row pitch ld (elements, % 4 == 0);
+ * one row per time step.  (TMA inner coordinates must be 16-byte aligned, so a conv tap has to
+ * be a shift of the row coordinate; this is also the (B, L, D) layout the transformer tail wants.) */
 
 /* Repack w (Cout, Cin, taps) into wk (taps, Cout, ldk) and wt (taps, Cin, ldt), tf32-rounded,
  * zero padded; ldk >= Cin, ldt >= Cout, both multiples of 4. */
 int xm_conv1d_pack_weight_f32(const float* w, int64_t Cout, int64_t Cin, int64_t taps, float* wk, int64_t ldk,
                               float* wt, int64_t ldt, void* stream);
-/* y (B,Cout,T) = conv1d(x (B,Cin,T), w) + bias, pad = taps/2.  ldx/ldy: row pitch of a (b,c) row. */
+/* y (B,T,Cout) = conv1d(x (B,T,Cin), w) + bias, pad = taps/2. */
 int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,
                       int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy, int round_out,
                       void* stream);
-/* dx (B,Cin,T) from dy (B,Cout,T) */
+/* dx (B,T,Cin) from dy (B,T,Cout) */
 int xm_conv1d_dgrad_f32(const float* dy, const float* wt, float* dx, int64_t B, int64_t Cin, int64_t Cout, int64_t T,
                         int64_t taps, int64_t lddy, int64_t ldt, int64_t lddx, int round_out, void* stream);
-/* dw (Cout,Cin,taps), db (Cout) (db may be NULL).  workspace: xm_conv1d_wgrad_workspace() floats. */
+/* dw (Cout,Cin,taps) [reference layout], db (Cout) (db may be NULL).
+ * workspace: xm_conv1d_wgrad_workspace() floats. */
 int64_t xm_conv1d_wgrad_workspace(int64_t B, int64_t Cin, int64_t Cout, int64_t taps);
 int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout,
                         int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------ normalisation + activation (+pool, +dropout)
- * nn.BatchNorm1d (train mode) + nn.GELU/nn.ReLU + nn.MaxPool1d(2) + nn.Dropout chains of the encoders. */
+ * nn.BatchNorm1d (train mode) + nn.GELU/nn.ReLU + nn.MaxPool1d(2) + nn.Dropout chains of the encoders,
+ * on channels-last activations y (B, T, C) with row pitch ldy (nn.Linear outputs: T = 1). */
 
-/* Batch statistics of y viewed as (B, C, T) with row pitch ldy (T = 1, ldy = 1 for (B, C) inputs):
- * stats (2*C) = {mean[C], biased var[C]}; partials: 2*C*nsplit doubles of workspace, nsplit =
- * xm_bn_nsplit(B, C, T).  When running_mean/var are non-NULL they are updated with `momentum`
- * and the unbiased variance, as torch does.  count_scale: multiply the element count (SyncBN hook;
- * pass 1). */
-int xm_bn_nsplit(int64_t B, int64_t C, int64_t T);
-int xm_bn_partial_stats_f32(const float* y, int64_t B, int64_t C, int64_t T, int64_t ldy, double* partials,
-                            void* stream);
-/* partials (nsplit, C, 2) doubles {sum, sumsq}; total_count = elements per channel behind them. */
+/* Per-split {sum, sumsq} of every channel over R = B*T rows: partials (nsplit, C, 2) doubles,
+ * nsplit = xm_bn_nsplit(R, C).  (Under data parallelism the partials are what gets all-reduced.) */
+int xm_bn_nsplit(int64_t R, int64_t C);
+int xm_bn_partial_stats_f32(const float* y, int64_t R, int64_t C, int64_t ldy, double* partials, void* stream);
+/* mean / invstd from partials; total_count = rows behind them.  running_mean/var (may be NULL) are
+ * updated with `momentum` and the unbiased variance, as torch does. */
 int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double total_count, float eps, float* mean,
                          float* invstd, float* running_mean, float* running_var, float momentum, void* stream);
-/* out = drop(pool?(act(gamma*(y-mean)*invstd + beta))) ; pool: 0 none, 2 = MaxPool1d(2) over T.
- * drop_p in [0,1): keep with prob 1-p, scale 1/(1-p); mask from (seed, element index).
- * drop_before_pool selects Conv-BN-GELU-Drop-Pool (Lite) vs Conv-BN-GELU-Pool-Drop (v4) ordering.
- * out has row pitch ldo and T_out = pool ? T/2 : T. */
+/* out = drop(pool?(act(gamma*(y-mean)*invstd + beta))) ; pool: 0 none, 2 = MaxPool1d(2) over T
+ * (out has B*(T/2) rows).  drop_p in [0,1): keep with prob 1-p, scale 1/(1-p); mask from
+ * (seed, element index).  drop_before_pool selects Conv-BN-GELU-Drop-Pool (Lite) vs
+ * Conv-BN-GELU-Pool-Drop (v4) ordering. */
 int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                      float* out, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo, int act, int pool,
+                      float* out, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo, int act, int pool,
                       float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream);
-/* Backward, pass 1: per-channel partial sums of dz and dz*xhat (dz = grad wrt the BN output).
- * partials: (nsplit, C, 2) doubles. */
+/* Backward, pass 1: per-channel partial sums of dz and dz*xhat (dz = grad wrt the BN output);
+ * partials (xm_bn_nsplit(B*T, C), C, 2) doubles.  Masks / argmax are recomputed, not stored. */
 int xm_bn_act_bwd_reduce_f32(const float* dout, const float* y, const float* mean, const float* invstd,
-                             const float* gamma, const float* beta, int64_t B, int64_t C, int64_t T, int64_t ldy,
+                             const float* gamma, const float* beta, int64_t B, int64_t T, int64_t C, int64_t ldy,
                              int64_t ldo, int act, int pool, float drop_p, uint64_t seed, int drop_before_pool,
                              double* partials, void* stream);
-/* sums (2*C) floats = {sum dz, sum dz*xhat} from partials: also dgamma = sums[C..2C), dbeta = sums[0..C) */
+/* dbeta (C) = sum dz, dgamma (C) = sum dz*xhat */
 int xm_bn_bwd_finalize(const double* partials, int nsplit, int64_t C, float* dbeta, float* dgamma, void* stream);
 /* Backward, pass 2: dy = gamma*invstd*(dz - dbeta/count - xhat*dgamma/count) */
 int xm_bn_act_bwd_apply_f32(const float* dout, const float* y, const float* mean, const float* invstd,
                             const float* gamma, const float* beta, const float* dbeta, const float* dgamma,
-                            double total_count, float* dy, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo,
+                            double total_count, float* dy, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo,
                             int act, int pool, float drop_p, uint64_t seed, int drop_before_pool, int round_out,
                             void* stream);
+/* AdaptiveAvgPool1d(1): x (B, T, C) pitch ldx -> out (B, C); and its backward (broadcast / T). */
+int xm_seqmean_f32(const float* x, int64_t B, int64_t T, int64_t C, int64_t ldx, float* out, void* stream);
+int xm_seqmean_bwd_f32(const float* dout, int64_t B, int64_t T, int64_t C, int64_t lddx, float* dx, void* stream);
 
 /* LayerNorm over the last dim + activation + dropout on (M, D) rows (bridge_utils.py:36-38,42-44,62-64).
  * Saves mean/rstd (M each) for the backward. */
@@ -161,10 +169,6 @@ int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, con
 
 /* out (N) = column sums of x (M, N) (bias gradients, partial reductions). */
 int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream);
-/* Mean over the last dim: x (R, T) pitch ldx -> out (R) ; and its backward (broadcast / T). */
-int xm_rowmean_f32(const float* x, int64_t R, int64_t T, int64_t ldx, float* out, void* stream);
-int xm_rowmean_bwd_f32(const float* dout, int64_t R, int64_t T, int64_t lddx, float* dx, void* stream);
-
 /* ------------------------------------------------------------------ similarity + symmetric InfoNCE
  * No reference implementation; embeddings are the outputs of
  * bridge_utils.py:71-72.  Oracle: oracle/infonce.py. */
@@ -187,6 +191,12 @@ int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, 
 int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
                         int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
                         void* stream);
+
+/* ------------------------------------------------------------------ diagnostics (not on the product path)
+ * Dump the raw shared-memory image of one TMA box {32,32} loaded at (c0, c1) from a (rows, cols)
+ * fp32 matrix; swizzle_atom32 selects SWIZZLE_128B_ATOM_32B instead of SWIZZLE_128B. */
+int xm_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int64_t ld, int c0, int c1, int swizzle_atom32,
+                       float* out, void* stream);
 
 #ifdef __cplusplus
 }

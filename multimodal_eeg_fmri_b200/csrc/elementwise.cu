@@ -1,9 +1,8 @@
 // HBM-bound kernels of the paired step: fMRI ROI aggregation, z-scoring, train-mode
-// BatchNorm (+GELU/ReLU, +MaxPool1d(2), +dropout) forward/backward on (B, C, T) activations,
-// LayerNorm(+act, +dropout) on (M, D) rows, L2 row normalisation, small reductions.
-// Layouts are the reference's own (NCW / row-major fp32); every kernel is a streaming pass
-// with coalesced (128-bit where alignment allows) accesses and fp32 math; batch statistics
-// are combined in fp64.
+// BatchNorm (+GELU/ReLU, +MaxPool1d(2), +dropout) forward/backward on channels-last (B, T, C)
+// activations (and (B, C) nn.Linear outputs, T = 1), LayerNorm(+act, +dropout) on (M, D) rows,
+// L2 row normalisation, small reductions.  Every kernel is a streaming pass with coalesced
+// accesses and fp32 math; batch statistics are combined in fp64.
 #include "xm_common.cuh"
 
 namespace xm {
@@ -69,29 +68,47 @@ __global__ void zscore_kernel(const float* __restrict__ x, long long len, float 
   for (long long i = threadIdx.x; i < len; i += blockDim.x) oi[i] = (xi[i] - fmean) * inv;
 }
 
-// ------------------------------------------------------------------ BatchNorm statistics
-// grid (C, nsplit): block (c, s) reduces samples b = s, s+nsplit, ... of channel c.
-__global__ void bn_partial_stats_kernel(const float* __restrict__ y, long long B, int C, long long T, long long ld,
-                                        double* __restrict__ partials) {
-  __shared__ double smd[32];
-  const int c = blockIdx.x, s = blockIdx.y, ns = gridDim.y;
+// ------------------------------------------------------------------ BatchNorm (channels-last)
+// Activations are (R, C) row-major with pitch ld: R = B*T rows of one time step (or one sample for
+// nn.Linear outputs, T = 1), C channels contiguous.  Per-channel statistics are column
+// reductions; MaxPool1d(2) pairs rows (b, 2t') and (b, 2t'+1).
+//
+// grid (ceil(C/32), nsplit), block 32 x 8: block (cx, s) reduces rows [s*rps, (s+1)*rps) of 32 columns.
+__global__ void bn_partial_stats_kernel(const float* __restrict__ y, long long R, int C, long long ld,
+                                        long long rows_per_split, double* __restrict__ partials) {
+  __shared__ double sm[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long r0 = blockIdx.y * rows_per_split;
+  const long long r1 = min(R, r0 + rows_per_split);
   double sum = 0.0, sq = 0.0;
-  for (long long b = s; b < B; b += ns) {
-    const float* row = y + (b * C + c) * ld;
+  if (c < C) {
     float ps = 0.f, pq = 0.f;
-    for (long long t = threadIdx.x; t < T; t += blockDim.x) {
-      const float v = row[t];
+    int n = 0;
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const float v = y[r * ld + c];
       ps += v;
       pq += v * v;
+      if (++n == 64) {
+        sum += (double)ps; sq += (double)pq;
+        ps = 0.f; pq = 0.f; n = 0;
+      }
     }
     sum += (double)ps;
     sq += (double)pq;
   }
-  sum = block_sum(sum, smd);
-  sq = block_sum(sq, smd);
-  if (threadIdx.x == 0) {
-    partials[((long long)s * C + c) * 2 + 0] = sum;
-    partials[((long long)s * C + c) * 2 + 1] = sq;
+  sm[0][ty][tx] = sum;
+  sm[1][ty][tx] = sq;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s += sm[0][i][tx];
+      q += sm[1][i][tx];
+    }
+    partials[((long long)blockIdx.y * C + c) * 2 + 0] = s;
+    partials[((long long)blockIdx.y * C + c) * 2 + 1] = q;
   }
 }
 
@@ -117,17 +134,16 @@ __global__ void bn_finalize_stats_kernel(const double* __restrict__ partials, in
   }
 }
 
-// ------------------------------------------------------------------ BN + act (+pool, +dropout)
 struct BnActArgs {
   const float* y;
   const float* mean;
   const float* invstd;
   const float* gamma;
   const float* beta;
-  long long B, T, ldy, ldo;
+  long long B, T, ldy, ldo;  // T rows per sample; R = B*T
   int C, act, pool, drop_before_pool, round_out;
-  float drop_scale;       // 1/(1-p), 1 when p == 0
-  uint32_t drop_thresh;   // p * 2^32, 0 when p == 0
+  float drop_scale;      // 1/(1-p), 1 when p == 0
+  uint32_t drop_thresh;  // p * 2^32, 0 when p == 0
   uint64_t seed;
 };
 
@@ -136,104 +152,107 @@ XM_DEVICE float drop_mul(const BnActArgs& a, long long idx) {
   return dropout_keep((uint64_t)idx, a.seed, a.drop_thresh) ? a.drop_scale : 0.0f;
 }
 
-// one block per (b, c) row
-__global__ void bn_act_fwd_kernel(const BnActArgs a, float* __restrict__ out) {
-  const long long row = blockIdx.x;
-  const int c = (int)(row % a.C);
-  const float mu = a.mean[c], is = a.invstd[c], g = a.gamma[c], bt = a.beta[c];
-  const float sc = g * is, sh = bt - mu * sc;
-  const float* yr = a.y + row * a.ldy;
-  float* orow = out + row * a.ldo;
+// forward value and dz for one channel of one output position.
+//   pool == 0: input row r  -> out row r
+//   pool == 2: input rows (b*T + 2tp, +1) -> out row b*To + tp
+XM_DEVICE float bn_act_fwd_elem(const BnActArgs& a, long long ro, int c, float sc, float sh) {
   if (a.pool == 2) {
-    const long long To = a.T / 2;
-    for (long long t = threadIdx.x; t < To; t += blockDim.x) {
-      const float2 v = *reinterpret_cast<const float2*>(yr + 2 * t);  // ldy % 2 == 0 checked on the host
-      float a0 = apply_act(v.x * sc + sh, a.act);
-      float a1 = apply_act(v.y * sc + sh, a.act);
-      float o;
-      if (a.drop_before_pool) {
-        a0 *= drop_mul(a, row * a.T + 2 * t);
-        a1 *= drop_mul(a, row * a.T + 2 * t + 1);
-        o = fmaxf(a0, a1);
-      } else {
-        o = fmaxf(a0, a1) * drop_mul(a, row * To + t);
-      }
-      orow[t] = a.round_out ? round_tf32(o) : o;
+    const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+    const long long r0 = b * a.T + 2 * tp;
+    float a0 = apply_act(a.y[r0 * a.ldy + c] * sc + sh, a.act);
+    float a1 = apply_act(a.y[(r0 + 1) * a.ldy + c] * sc + sh, a.act);
+    if (a.drop_before_pool) {
+      a0 *= drop_mul(a, r0 * a.C + c);
+      a1 *= drop_mul(a, (r0 + 1) * a.C + c);
+      return fmaxf(a0, a1);
     }
-  } else {
-    for (long long t = threadIdx.x; t < a.T; t += blockDim.x) {
-      float o = apply_act(yr[t] * sc + sh, a.act) * drop_mul(a, row * a.T + t);
-      orow[t] = a.round_out ? round_tf32(o) : o;
-    }
+    return fmaxf(a0, a1) * drop_mul(a, ro * a.C + c);
   }
+  return apply_act(a.y[ro * a.ldy + c] * sc + sh, a.act) * drop_mul(a, ro * a.C + c);
 }
 
-// dz (gradient wrt the BN output z = gamma*xhat + beta) for pre-pool element t of `row`.
-// Recomputes the activation / pool argmax / dropout mask instead of storing them.
-XM_DEVICE void bn_act_dz_pair(const BnActArgs& a, const float* __restrict__ dout_row, const float* __restrict__ yr,
-                              long long row, long long tp, float sc, float sh, float& dz0, float& dz1) {
-  // pool == 2: handles pre-pool elements (2tp, 2tp+1) fed by dout[tp]
-  const float2 v = *reinterpret_cast<const float2*>(yr + 2 * tp);
-  const float z0 = v.x * sc + sh, z1 = v.y * sc + sh;
-  float a0 = apply_act(z0, a.act), a1 = apply_act(z1, a.act);
-  const long long To = a.T / 2;
-  float g = dout_row[tp];
-  float m0 = 1.f, m1 = 1.f;
-  if (a.drop_before_pool) {
-    m0 = drop_mul(a, row * a.T + 2 * tp);
-    m1 = drop_mul(a, row * a.T + 2 * tp + 1);
-    a0 *= m0;
-    a1 *= m1;
-  } else {
-    g *= drop_mul(a, row * To + tp);
-  }
-  const bool first = a0 >= a1;  // ties -> first element, as torch max_pool1d
-  dz0 = first ? g * m0 * act_grad(z0, a.act) : 0.f;
-  dz1 = first ? 0.f : g * m1 * act_grad(z1, a.act);
-}
-XM_DEVICE float bn_act_dz_single(const BnActArgs& a, const float* __restrict__ dout_row, const float* __restrict__ yr,
-                                 long long row, long long t, float sc, float sh) {
-  const float z = yr[t] * sc + sh;
-  return dout_row[t] * drop_mul(a, row * a.T + t) * act_grad(z, a.act);
-}
-
-// grid (C, nsplit): per-channel partial sums of dz and dz*xhat
-__global__ void bn_act_bwd_reduce_kernel(const BnActArgs a, const float* __restrict__ dout,
-                                         double* __restrict__ partials) {
-  __shared__ double smd[32];
-  const int c = blockIdx.x, s = blockIdx.y, ns = gridDim.y;
-  const float mu = a.mean[c], is = a.invstd[c], g = a.gamma[c], bt = a.beta[c];
-  const float sc = g * is, sh = bt - mu * sc;
-  double sdz = 0.0, sdzx = 0.0;
-  for (long long b = s; b < a.B; b += ns) {
-    const long long row = b * a.C + c;
-    const float* yr = a.y + row * a.ldy;
-    const float* dr = dout + row * a.ldo;
-    float p0 = 0.f, p1 = 0.f;
-    if (a.pool == 2) {
-      const long long To = a.T / 2;
-      for (long long t = threadIdx.x; t < To; t += blockDim.x) {
-        float dz0, dz1;
-        bn_act_dz_pair(a, dr, yr, row, t, sc, sh, dz0, dz1);
-        const float2 v = *reinterpret_cast<const float2*>(yr + 2 * t);
-        p0 += dz0 + dz1;
-        p1 += dz0 * ((v.x - mu) * is) + dz1 * ((v.y - mu) * is);
-      }
+// dz (gradient wrt z = gamma*xhat + beta) of the (up to) two input rows behind output row ro.
+XM_DEVICE void bn_act_dz(const BnActArgs& a, const float* __restrict__ dout, long long ro, int c, float sc, float sh,
+                         float& x0, float& x1, float& dz0, float& dz1) {
+  const float g = dout[ro * a.ldo + c];
+  if (a.pool == 2) {
+    const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+    const long long r0 = b * a.T + 2 * tp;
+    x0 = a.y[r0 * a.ldy + c];
+    x1 = a.y[(r0 + 1) * a.ldy + c];
+    const float z0 = x0 * sc + sh, z1 = x1 * sc + sh;
+    float a0 = apply_act(z0, a.act), a1 = apply_act(z1, a.act);
+    float m0 = 1.f, m1 = 1.f, gg = g;
+    if (a.drop_before_pool) {
+      m0 = drop_mul(a, r0 * a.C + c);
+      m1 = drop_mul(a, (r0 + 1) * a.C + c);
+      a0 *= m0;
+      a1 *= m1;
     } else {
-      for (long long t = threadIdx.x; t < a.T; t += blockDim.x) {
-        const float dz = bn_act_dz_single(a, dr, yr, row, t, sc, sh);
-        p0 += dz;
-        p1 += dz * ((yr[t] - mu) * is);
+      gg *= drop_mul(a, ro * a.C + c);
+    }
+    const bool first = a0 >= a1;  // ties -> first element, as torch max_pool1d
+    dz0 = first ? gg * m0 * act_grad(z0, a.act) : 0.f;
+    dz1 = first ? 0.f : gg * m1 * act_grad(z1, a.act);
+  } else {
+    x0 = a.y[ro * a.ldy + c];
+    x1 = 0.f;
+    dz0 = g * drop_mul(a, ro * a.C + c) * act_grad(x0 * sc + sh, a.act);
+    dz1 = 0.f;
+  }
+}
+
+// one thread per (output row, channel); channels fastest => coalesced
+__global__ void bn_act_fwd_kernel(const BnActArgs a, long long R_out, float* __restrict__ out) {
+  const long long total = R_out * a.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long ro = i / a.C;
+    const int c = (int)(i - ro * a.C);
+    const float sc = a.gamma[c] * a.invstd[c], sh = a.beta[c] - a.mean[c] * sc;
+    const float o = bn_act_fwd_elem(a, ro, c, sc, sh);
+    out[ro * a.ldo + c] = a.round_out ? round_tf32(o) : o;
+  }
+}
+
+// grid (ceil(C/32), nsplit), block 32 x 8 over OUTPUT rows: partial sums of dz and dz*xhat
+__global__ void bn_act_bwd_reduce_kernel(const BnActArgs a, const float* __restrict__ dout, long long R_out,
+                                         long long rows_per_split, double* __restrict__ partials) {
+  __shared__ double sm[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long r0 = blockIdx.y * rows_per_split;
+  const long long r1 = min(R_out, r0 + rows_per_split);
+  double sdz = 0.0, sdzx = 0.0;
+  if (c < a.C) {
+    const float mu = a.mean[c], is = a.invstd[c];
+    const float sc = a.gamma[c] * is, sh = a.beta[c] - mu * sc;
+    float p0 = 0.f, p1 = 0.f;
+    int n = 0;
+    for (long long ro = r0 + ty; ro < r1; ro += 8) {
+      float x0, x1, dz0, dz1;
+      bn_act_dz(a, dout, ro, c, sc, sh, x0, x1, dz0, dz1);
+      p0 += dz0 + dz1;
+      p1 += dz0 * ((x0 - mu) * is) + dz1 * ((x1 - mu) * is);
+      if (++n == 64) {
+        sdz += (double)p0; sdzx += (double)p1;
+        p0 = 0.f; p1 = 0.f; n = 0;
       }
     }
     sdz += (double)p0;
     sdzx += (double)p1;
   }
-  sdz = block_sum(sdz, smd);
-  sdzx = block_sum(sdzx, smd);
-  if (threadIdx.x == 0) {
-    partials[((long long)s * a.C + c) * 2 + 0] = sdz;
-    partials[((long long)s * a.C + c) * 2 + 1] = sdzx;
+  sm[0][ty][tx] = sdz;
+  sm[1][ty][tx] = sdzx;
+  __syncthreads();
+  if (ty == 0 && c < a.C) {
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s += sm[0][i][tx];
+      q += sm[1][i][tx];
+    }
+    partials[((long long)blockIdx.y * a.C + c) * 2 + 0] = s;
+    partials[((long long)blockIdx.y * a.C + c) * 2 + 1] = q;
   }
 }
 
@@ -250,40 +269,63 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int 
   dgamma[c] = (float)q;
 }
 
-// one block per (b, c) row: dy = gamma*invstd*(dz - dbeta/n - xhat*dgamma/n)
+// dy = gamma*invstd*(dz - dbeta/n - xhat*dgamma/n); one thread per (output row, channel)
 __global__ void bn_act_bwd_apply_kernel(const BnActArgs a, const float* __restrict__ dout,
                                         const float* __restrict__ dbeta, const float* __restrict__ dgamma, float inv_n,
-                                        float* __restrict__ dy) {
-  const long long row = blockIdx.x;
-  const int c = (int)(row % a.C);
-  const float mu = a.mean[c], is = a.invstd[c], g = a.gamma[c], bt = a.beta[c];
-  const float sc = g * is, sh = bt - mu * sc;
-  const float k1 = dbeta[c] * inv_n, k2 = dgamma[c] * inv_n;
-  const float* yr = a.y + row * a.ldy;
-  const float* dr = dout + row * a.ldo;
-  float* dyr = dy + row * a.ldy;
-  if (a.pool == 2) {
-    const long long To = a.T / 2;
-    for (long long t = threadIdx.x; t < To; t += blockDim.x) {
-      float dz0, dz1;
-      bn_act_dz_pair(a, dr, yr, row, t, sc, sh, dz0, dz1);
-      const float2 v = *reinterpret_cast<const float2*>(yr + 2 * t);
-      float o0 = sc * (dz0 - k1 - (v.x - mu) * is * k2);
-      float o1 = sc * (dz1 - k1 - (v.y - mu) * is * k2);
+                                        long long R_out, float* __restrict__ dy) {
+  const long long total = R_out * a.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long ro = i / a.C;
+    const int c = (int)(i - ro * a.C);
+    const float mu = a.mean[c], is = a.invstd[c];
+    const float sc = a.gamma[c] * is, sh = a.beta[c] - mu * sc;
+    const float k1 = dbeta[c] * inv_n, k2 = dgamma[c] * inv_n;
+    float x0, x1, dz0, dz1;
+    bn_act_dz(a, dout, ro, c, sc, sh, x0, x1, dz0, dz1);
+    if (a.pool == 2) {
+      const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+      const long long r0 = b * a.T + 2 * tp;
+      float o0 = sc * (dz0 - k1 - (x0 - mu) * is * k2);
+      float o1 = sc * (dz1 - k1 - (x1 - mu) * is * k2);
       if (a.round_out) { o0 = round_tf32(o0); o1 = round_tf32(o1); }
-      *reinterpret_cast<float2*>(dyr + 2 * t) = make_float2(o0, o1);
+      dy[r0 * a.ldy + c] = o0;
+      dy[(r0 + 1) * a.ldy + c] = o1;
+      if ((a.T & 1) && tp == To - 1) {  // odd tail row is dropped by the pool: dz = 0
+        const float xt = a.y[(r0 + 2) * a.ldy + c];
+        const float ot = sc * (0.f - k1 - (xt - mu) * is * k2);
+        dy[(r0 + 2) * a.ldy + c] = a.round_out ? round_tf32(ot) : ot;
+      }
+    } else {
+      const float o = sc * (dz0 - k1 - (x0 - mu) * is * k2);
+      dy[ro * a.ldy + c] = a.round_out ? round_tf32(o) : o;
     }
-    if ((a.T & 1) && threadIdx.x == 0) {  // odd tail element is dropped by the pool: dz = 0
-      const long long t = a.T - 1;
-      float o = sc * (0.f - k1 - (yr[t] - mu) * is * k2);
-      dyr[t] = a.round_out ? round_tf32(o) : o;
-    }
-  } else {
-    for (long long t = threadIdx.x; t < a.T; t += blockDim.x) {
-      const float dz = bn_act_dz_single(a, dr, yr, row, t, sc, sh);
-      float o = sc * (dz - k1 - (yr[t] - mu) * is * k2);
-      dyr[t] = a.round_out ? round_tf32(o) : o;
-    }
+  }
+}
+
+// mean over the T rows of each sample: x (B, T, C) pitch ld -> out (B, C); grid (ceil(C/32), B), block 32 x 8
+__global__ void seqmean_kernel(const float* __restrict__ x, long long T, int C, long long ld, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long b = blockIdx.y;
+  float acc = 0.f;
+  if (c < C)
+    for (long long t = ty; t < T; t += 8) acc += x[(b * T + t) * ld + c];
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sm[i][tx];
+    out[b * C + c] = s / (float)T;
+  }
+}
+__global__ void seqmean_bwd_kernel(const float* __restrict__ dout, long long T, int C, long long ld, long long total,
+                                   float* __restrict__ dx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    dx[r * ld + c] = dout[(r / T) * C + c] / (float)T;
   }
 }
 
@@ -384,23 +426,6 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long M, long lon
   }
 }
 
-__global__ void rowmean_kernel(const float* __restrict__ x, long long R, long long T, long long ld,
-                               float* __restrict__ out) {
-  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= R) return;
-  const int lane = threadIdx.x & 31;
-  float s = 0.f;
-  for (long long t = lane; t < T; t += 32) s += x[row * ld + t];
-  s = warp_sum(s);
-  if (lane == 0) out[row] = s / (float)T;
-}
-__global__ void rowmean_bwd_kernel(const float* __restrict__ dout, long long R, long long T, long long ld,
-                                   float* __restrict__ dx) {
-  const long long row = blockIdx.x;
-  const float g = dout[row] / (float)T;
-  for (long long t = threadIdx.x; t < T; t += blockDim.x) dx[row * ld + t] = g;
-}
-
 // ------------------------------------------------------------------ L2 row normalisation (warp per row)
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ inv_norm,
                                   long long M, int D, float eps) {
@@ -429,7 +454,7 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dxn, const float* __
 }
 
 static BnActArgs make_bn_args(const float* y, const float* mean, const float* invstd, const float* gamma,
-                              const float* beta, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo, int act,
+                              const float* beta, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo, int act,
                               int pool, float drop_p, uint64_t seed, int drop_before_pool, int round_out) {
   BnActArgs a;
   a.y = y; a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta;
@@ -447,13 +472,19 @@ static BnActArgs make_bn_args(const float* y, const float* mean, const float* in
   return a;
 }
 
-static bool bn_args_ok(const void* y, const void* m, const void* is, const void* g, const void* b, int64_t B, int64_t C,
-                       int64_t T, int64_t ldy, int pool, float p) {
-  if (!y || !m || !is || !g || !b || B <= 0 || C <= 0 || T <= 0 || ldy < T) return false;
+static bool bn_args_ok(const void* y, const void* m, const void* is, const void* g, const void* b, int64_t B, int64_t T,
+                       int64_t C, int64_t ldy, int pool, float p) {
+  if (!y || !m || !is || !g || !b || B <= 0 || C <= 0 || T <= 0 || ldy < C) return false;
   if (pool != 0 && pool != 2) return false;
-  if (pool == 2 && ((ldy & 1) || (reinterpret_cast<uintptr_t>(y) & 7))) return false;
+  if (pool == 2 && T < 2) return false;
   if (!(p >= 0.f && p < 1.f)) return false;
   return true;
+}
+
+static int ew_grid(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 }  // namespace xm
@@ -475,20 +506,22 @@ int xm_zscore_f32(const float* x, int64_t n_items, int64_t item_len, float eps, 
   return check_launch();
 }
 
-int xm_bn_nsplit(int64_t B, int64_t C, int64_t T) {
-  (void)T;
-  int64_t ns = (kNumSMs * 8 + C - 1) / C;
-  if (ns > B) ns = B;
+int xm_bn_nsplit(int64_t R, int64_t C) {
+  const int64_t cblk = (C + 31) / 32;
+  int64_t ns = (kNumSMs * 4 + cblk - 1) / cblk;
+  const int64_t max_by_rows = (R + 63) / 64;  // at least 64 rows per split
+  if (ns > max_by_rows) ns = max_by_rows;
   if (ns < 1) ns = 1;
   if (ns > 65535) ns = 65535;
   return (int)ns;
 }
 
-int xm_bn_partial_stats_f32(const float* y, int64_t B, int64_t C, int64_t T, int64_t ldy, double* partials,
-                            void* stream) {
-  if (!y || !partials || B <= 0 || C <= 0 || T <= 0) return XM_ERR_INVALID;
-  dim3 grid((unsigned)C, (unsigned)xm_bn_nsplit(B, C, T));
-  bn_partial_stats_kernel<<<grid, T >= 256 ? 256 : 64, 0, (cudaStream_t)stream>>>(y, B, (int)C, T, ldy, partials);
+int xm_bn_partial_stats_f32(const float* y, int64_t R, int64_t C, int64_t ldy, double* partials, void* stream) {
+  if (!y || !partials || R <= 0 || C <= 0 || ldy < C) return XM_ERR_INVALID;
+  const int ns = xm_bn_nsplit(R, C);
+  const long long rps = (R + ns - 1) / ns;
+  dim3 grid(ceil_div(C, 32), (unsigned)ns);
+  bn_partial_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, R, (int)C, ldy, rps, partials);
   return check_launch();
 }
 
@@ -502,23 +535,27 @@ int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double t
 }
 
 int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                      float* out, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo, int act, int pool,
+                      float* out, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo, int act, int pool,
                       float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream) {
-  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, C, T, ldy, pool, drop_p) || !out) return XM_ERR_INVALID;
-  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, C, T, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, T, C, ldy, pool, drop_p) || !out || ldo < C) return XM_ERR_INVALID;
+  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);
-  bn_act_fwd_kernel<<<grid_rows(B * C), T >= 256 ? 128 : 32, 0, (cudaStream_t)stream>>>(a, out);
+  const long long R_out = B * (pool == 2 ? T / 2 : T);
+  bn_act_fwd_kernel<<<ew_grid(R_out * C), 256, 0, (cudaStream_t)stream>>>(a, R_out, out);
   return check_launch();
 }
 
 int xm_bn_act_bwd_reduce_f32(const float* dout, const float* y, const float* mean, const float* invstd,
-                             const float* gamma, const float* beta, int64_t B, int64_t C, int64_t T, int64_t ldy,
+                             const float* gamma, const float* beta, int64_t B, int64_t T, int64_t C, int64_t ldy,
                              int64_t ldo, int act, int pool, float drop_p, uint64_t seed, int drop_before_pool,
                              double* partials, void* stream) {
-  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, C, T, ldy, pool, drop_p) || !dout || !partials) return XM_ERR_INVALID;
-  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, C, T, ldy, ldo, act, pool, drop_p, seed, drop_before_pool, 0);
-  dim3 grid((unsigned)C, (unsigned)xm_bn_nsplit(B, C, T));
-  bn_act_bwd_reduce_kernel<<<grid, T >= 256 ? 256 : 64, 0, (cudaStream_t)stream>>>(a, dout, partials);
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, T, C, ldy, pool, drop_p) || !dout || !partials) return XM_ERR_INVALID;
+  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool, 0);
+  const long long R_out = B * (pool == 2 ? T / 2 : T);
+  const int ns = xm_bn_nsplit(B * T, C);  // same split count as the forward statistics
+  const long long rps = (R_out + ns - 1) / ns;
+  dim3 grid(ceil_div(C, 32), (unsigned)ns);
+  bn_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, dout, R_out, rps, partials);
   return check_launch();
 }
 
@@ -530,17 +567,29 @@ int xm_bn_bwd_finalize(const double* partials, int nsplit, int64_t C, float* dbe
 
 int xm_bn_act_bwd_apply_f32(const float* dout, const float* y, const float* mean, const float* invstd,
                             const float* gamma, const float* beta, const float* dbeta, const float* dgamma,
-                            double total_count, float* dy, int64_t B, int64_t C, int64_t T, int64_t ldy, int64_t ldo,
+                            double total_count, float* dy, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo,
                             int act, int pool, float drop_p, uint64_t seed, int drop_before_pool, int round_out,
                             void* stream) {
-  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, C, T, ldy, pool, drop_p) || !dout || !dbeta || !dgamma || !dy ||
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, T, C, ldy, pool, drop_p) || !dout || !dbeta || !dgamma || !dy ||
       total_count <= 0)
     return XM_ERR_INVALID;
-  if (pool == 2 && (reinterpret_cast<uintptr_t>(dy) & 7)) return XM_ERR_INVALID;
-  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, C, T, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
+  BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);
-  bn_act_bwd_apply_kernel<<<grid_rows(B * C), T >= 256 ? 128 : 32, 0, (cudaStream_t)stream>>>(
-      a, dout, dbeta, dgamma, (float)(1.0 / total_count), dy);
+  const long long R_out = B * (pool == 2 ? T / 2 : T);
+  bn_act_bwd_apply_kernel<<<ew_grid(R_out * C), 256, 0, (cudaStream_t)stream>>>(a, dout, dbeta, dgamma,
+                                                                              (float)(1.0 / total_count), R_out, dy);
+  return check_launch();
+}
+
+int xm_seqmean_f32(const float* x, int64_t B, int64_t T, int64_t C, int64_t ldx, float* out, void* stream) {
+  if (!x || !out || B <= 0 || T <= 0 || C <= 0 || B > 65535) return XM_ERR_INVALID;
+  dim3 grid(ceil_div(C, 32), (unsigned)B);
+  seqmean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, T, (int)C, ldx, out);
+  return check_launch();
+}
+int xm_seqmean_bwd_f32(const float* dout, int64_t B, int64_t T, int64_t C, int64_t lddx, float* dx, void* stream) {
+  if (!dout || !dx || B <= 0 || T <= 0 || C <= 0) return XM_ERR_INVALID;
+  seqmean_bwd_kernel<<<ew_grid(B * T * C), 256, 0, (cudaStream_t)stream>>>(dout, T, (int)C, lddx, B * T * C, dx);
   return check_launch();
 }
 
@@ -591,17 +640,6 @@ int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, con
 int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream) {
   if (!x || !out || M <= 0 || N <= 0) return XM_ERR_INVALID;
   colsum_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(x, M, N, ldx, out);
-  return check_launch();
-}
-
-int xm_rowmean_f32(const float* x, int64_t R, int64_t T, int64_t ldx, float* out, void* stream) {
-  if (!x || !out || R <= 0 || T <= 0) return XM_ERR_INVALID;
-  rowmean_kernel<<<ceil_div(R, 8), 256, 0, (cudaStream_t)stream>>>(x, R, T, ldx, out);
-  return check_launch();
-}
-int xm_rowmean_bwd_f32(const float* dout, int64_t R, int64_t T, int64_t lddx, float* dx, void* stream) {
-  if (!dout || !dx || R <= 0 || T <= 0) return XM_ERR_INVALID;
-  rowmean_bwd_kernel<<<grid_rows(R), 128, 0, (cudaStream_t)stream>>>(dout, R, T, lddx, dx);
   return check_launch();
 }
 

@@ -12,8 +12,10 @@
 // Both operands may be K-major (rows of 32 consecutive k) or MN-major (rows of 32 consecutive
 // m/n, one row per k) so that forward, data-gradient and weight-gradient contractions all read
 // the SAME row-major fp32 tensors without transposed copies.  Conv1d is the same engine with a
-// 3-D tensor map over (T, C, B): a tap is a TMA coordinate shift along T, and TMA's
-// out-of-bounds zero fill implements the conv zero padding and the ragged last tile.
+// 3-D tensor map over channels-last activations (C, T, B): a tap is a TMA coordinate shift along
+// the row (time) axis, and TMA's out-of-bounds zero fill implements the conv zero padding and the
+// ragged last tile.  (TMA inner coordinates must be 16-byte aligned -- measured on B200 -- which is
+// why time cannot be the contiguous axis of a conv operand.)
 #pragma once
 #include "xm_common.cuh"
 #include "xm_ptx.cuh"
@@ -22,7 +24,6 @@ namespace xm {
 
 enum : int {
   EPI_ROWMAJOR = 0,    // C[z][tap][m][n] = act(alpha*acc + bias[n])
-  EPI_TRANSPOSED = 1,  // C[z][n][m]      = alpha*acc + bias[n]           (conv: NCW output)
   EPI_LSE = 2,         // partial[ny][m]  = sum_n exp(alpha*acc - shift) ; diag[m] = alpha*acc[m, m+diag_off]
   EPI_NCE_GRAD = 3,    // C[m][n] = coef*(exp(s-lse_row[m]) + exp(s-lse_col[n]) - 2*[n == m+diag_off]),  s = alpha*acc
 };
@@ -167,6 +168,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t b_kstep = p.b.mn_major ? 1024u : 32u;
       const uint32_t a_lbo = p.a.mn_major ? 4096u : 16u;
       const uint32_t b_lbo = p.b.mn_major ? 4096u : 16u;
+      const uint32_t a_sbo = p.a.mn_major ? 512u : 1024u;
+      const uint32_t b_sbo = p.b.mn_major ? 512u : 1024u;
+      const uint32_t a_lt = p.a.mn_major ? 1u : 2u;
+      const uint32_t b_lt = p.b.mn_major ? 1u : 2u;
       int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < total_kb; ++kb) {
@@ -177,8 +182,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sb = sa + kATileBytes + tn * b_tile_bytes;
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
-            const uint64_t da = ptx::make_smem_desc(sa + k8 * a_kstep, a_lbo, 1024u);
-            const uint64_t db = ptx::make_smem_desc(sb + k8 * b_kstep, b_lbo, 1024u);
+            const uint64_t da = ptx::make_smem_desc(sa + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db = ptx::make_smem_desc(sb + k8 * b_kstep, b_lbo, b_sbo, b_lt);
             ptx::mma_tf32_ss(tmem_base + (uint32_t)(tn * p.bn), da, db, idesc, (kb > 0 || k8 > 0) ? 1u : 0u);
           }
         }
@@ -229,17 +234,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (n0 + c0 + j < p.N) crow[j] = v[j];
-            }
-          }
-        } else if (EPI == EPI_TRANSPOSED) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            if (row_ok && n < p.N) {
-              float x = __uint_as_float(r[j]) * p.alpha;
-              if (p.bias != nullptr) x += p.bias[n];
-              if (p.round_tf32) x = round_tf32(x);
-              cbase[(long long)n * p.ldc + m] = x;  // lanes = consecutive m: coalesced
             }
           }
         } else if (EPI == EPI_LSE) {
@@ -300,7 +294,7 @@ struct TensorView3 {
   unsigned long long stride_bytes[2];  // strides of dim[1], dim[2]
 };
 
-int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1);
+int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major);
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, GemmParams& p, dim3 grid, cudaStream_t stream);
 
 inline int tmem_cols_for(int n) {

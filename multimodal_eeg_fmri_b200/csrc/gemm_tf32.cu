@@ -30,7 +30,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1) {
+int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return XM_ERR_NO_DRIVER;
   if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) return XM_ERR_INVALID;
@@ -40,7 +40,9 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(t.ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     g_last_cuda_error = 100000 + (int)r;
@@ -83,14 +85,13 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, GemmParam
   const size_t smem = (size_t)stages * stage_bytes + 1024;
 
   CUtensorMap ma, mb;
-  int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : 128);
+  int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : 128, p.a.mn_major);
   if (rc != XM_OK) return rc;
-  rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? 32 : (unsigned)p.bn);
+  rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? 32 : (unsigned)p.bn, p.b.mn_major);
   if (rc != XM_OK) return rc;
 
   switch (epi) {
     case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, p, grid, smem, stream);
-    case EPI_TRANSPOSED: return launch_epi<EPI_TRANSPOSED>(ma, mb, p, grid, smem, stream);
     case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, p, grid, smem, stream);
     case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, p, grid, smem, stream);
   }
@@ -146,28 +147,6 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, int split
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += ws[(long long)s * slab + src];
     dw[i] = acc;
-  }
-}
-
-// db[c] = sum_{b,t} dy[b, c, t]   (one block per channel)
-__global__ void conv_bias_grad_kernel(const float* __restrict__ dy, long long B, int C, long long T, long long ld,
-                                      float* __restrict__ db) {
-  const int c = blockIdx.x;
-  double acc = 0.0;
-  for (long long b = 0; b < B; ++b) {
-    const float* row = dy + (b * C + c) * ld;
-    float part = 0.f;
-    for (long long t = threadIdx.x; t < T; t += blockDim.x) part += row[t];
-    acc += (double)part;
-  }
-  __shared__ double sm[32];
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) db[c] = (float)v;
   }
 }
 
@@ -300,8 +279,6 @@ int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, i
   return launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream);
 }
 
-int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream);
-
 int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
                         int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, void* stream) {
   if (!dy || !x || !dw || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
@@ -358,12 +335,18 @@ int xm_conv1d_pack_weight_f32(const float* w, int64_t Cout, int64_t Cin, int64_t
   return check_launch();
 }
 
-// Shared by fwd (direction +1) and dgrad (direction -1): out[b, n, t] = sum_tap sum_k in[b, k, t + dir*(tap - pad)] * wp[tap, n, k]
+// Channels-last activations: x (B, T, C) with row pitch ld (one row = one time step, C contiguous).
+// TMA needs 16-byte aligned INNER coordinates, so a conv tap cannot be a shift along a contiguous
+// time axis; with channels innermost the tap is a shift of the ROW coordinate, which is free, and
+// TMA zero-fills rows outside [0, T) of each sample -- that is the conv zero padding.
+//
+// Shared by fwd (dir = +1) and dgrad (dir = -1):
+//   out[b, t, n] = sum_tap sum_k in[b, t + dir*(tap - pad), k] * wp[tap, n, k]  (+ bias[n])
 static int conv_like(const float* in, const float* wp, const float* bias, float* out, int64_t B, int64_t Kc, int64_t Nc,
                      int64_t T, int64_t taps, int64_t ld_in, int64_t ld_w, int64_t ld_out, int dir, int round_out,
                      cudaStream_t st) {
   if (!in || !wp || !out || B <= 0 || Kc <= 0 || Nc <= 0 || T <= 0 || taps <= 0 || !(taps & 1)) return XM_ERR_INVALID;
-  if ((ld_in & 3) || (ld_w & 3) || ld_in < T || ld_out < T) return XM_ERR_INVALID;
+  if ((ld_in & 3) || (ld_w & 3) || ld_in < Kc || ld_out < Nc || B > 65535) return XM_ERR_INVALID;
   const int pad = (int)(taps / 2);
   const int t_tiles = ceil_div(T, 128);
   GemmParams p;
@@ -371,12 +354,12 @@ static int conv_like(const float* in, const float* wp, const float* bias, float*
   p.bn = choose_bn(Nc, (int64_t)t_tiles * B, 16);
   p.taps_k = (int)taps;
   p.kin_count = ceil_div(Kc, 32);
-  p.a.mn_major = 1;  // activations (B, C, T): GEMM row index t contiguous
-  p.a.base[0] = -dir * pad;
-  p.a.sx[0] = 128;
+  p.a.mn_major = 0;  // activations: contraction index (channel) contiguous
+  p.a.base[1] = -dir * pad;
+  p.a.sx[1] = 128;
   p.a.sz[2] = 1;
-  p.a.kin_step[1] = 32;
-  p.a.tap_step[0] = dir;
+  p.a.kin_step[0] = 32;
+  p.a.tap_step[1] = dir;
   p.b.mn_major = 0;  // packed weights (taps, N, K): contraction index contiguous
   p.b.sy[1] = p.bn;
   p.b.kin_step[0] = 32;
@@ -385,14 +368,14 @@ static int conv_like(const float* in, const float* wp, const float* bias, float*
   p.N = (int)Nc;
   p.c = out;
   p.ldc = ld_out;
-  p.c_z_stride = (long long)Nc * ld_out;
+  p.c_z_stride = (long long)T * ld_out;
   p.bias = bias;
   p.round_tf32 = round_out;
-  TensorView3 ta{in, {(unsigned long long)T, (unsigned long long)Kc, (unsigned long long)B},
-                 {(unsigned long long)ld_in * 4, (unsigned long long)Kc * ld_in * 4}};
+  TensorView3 ta{in, {(unsigned long long)Kc, (unsigned long long)T, (unsigned long long)B},
+                 {(unsigned long long)ld_in * 4, (unsigned long long)T * ld_in * 4}};
   TensorView3 tb{wp, {(unsigned long long)Kc, (unsigned long long)Nc, (unsigned long long)taps},
                  {(unsigned long long)ld_w * 4, (unsigned long long)Nc * ld_w * 4}};
-  return launch_gemm(EPI_TRANSPOSED, ta, tb, p, dim3(t_tiles, ceil_div(Nc, p.bn), (unsigned)B), st);
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(t_tiles, ceil_div(Nc, p.bn), (unsigned)B), st);
 }
 
 int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,
@@ -406,14 +389,16 @@ int xm_conv1d_dgrad_f32(const float* dy, const float* wt, float* dx, int64_t B, 
   return conv_like(dy, wt, nullptr, dx, B, Cout, Cin, T, taps, lddy, ldt, lddx, -1, round_out, (cudaStream_t)stream);
 }
 
-// wgrad geometry: samples are the outer contraction index, split across gridDim.z; taps are
-// separate TMEM accumulators (as many as fit 512 columns), tap groups across gridDim.y.
+// wgrad:  dw[tap][co][ci] = sum_b sum_t dy[b, t, co] * x[b, t + tap - pad, ci]
+// GEMM rows = co, cols = ci, contraction = (b, t): both operands are MN-major (channel contiguous,
+// one row per t).  Samples are the outer contraction index, split across gridDim.z; taps are
+// separate TMEM accumulators (as many as fit 512 columns), remaining tap groups are extra launches.
 struct WgradPlan {
   int bn, taps_n, tap_groups, samples_per_cta, splits;
 };
 static WgradPlan wgrad_plan(int64_t B, int64_t Cin, int64_t Cout, int64_t taps) {
   WgradPlan pl;
-  pl.bn = (int)((Cin + 15) / 16 * 16);
+  pl.bn = (int)((Cin + 31) / 32 * 32);
   int per = 512 / pl.bn;
   if (per < 1) per = 1;
   // keep >= 2 pipeline stages in shared memory: 16 KB + taps_n * bn * 128 B per stage
@@ -438,7 +423,7 @@ int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
                         int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, void* stream) {
   if (!dy || !x || !dw || !workspace || B <= 0 || Cin <= 0 || Cout <= 0 || T <= 0 || taps <= 0 || !(taps & 1))
     return XM_ERR_INVALID;
-  if ((lddy & 3) || (ldx & 3) || Cin > 256) return XM_ERR_INVALID;
+  if ((lddy & 3) || (ldx & 3) || Cin > 256 || lddy < Cout || ldx < Cin) return XM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int pad = (int)(taps / 2);
   WgradPlan pl = wgrad_plan(B, Cin, Cout, taps);
@@ -454,25 +439,25 @@ int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
     p.kout_count = pl.samples_per_cta;
     p.kout_total = (int)B;
     p.kout_split = 1;
-    p.a.mn_major = 0;  // dy (B, Cout, T): contraction index t contiguous
-    p.a.sx[1] = 128;
-    p.a.kin_step[0] = 32;
+    p.a.mn_major = 1;  // dy (B, T, Cout): GEMM row index co contiguous, one row per t
+    p.a.sx[0] = 128;
+    p.a.kin_step[1] = 32;
     p.a.kout_step[2] = 1;
-    p.b.mn_major = 0;  // x (B, Cin, T)
-    p.b.base[0] = tap0 - pad;
-    p.b.kin_step[0] = 32;
+    p.b.mn_major = 1;  // x (B, T, Cin): GEMM col index ci contiguous
+    p.b.base[1] = tap0 - pad;
+    p.b.kin_step[1] = 32;
     p.b.kout_step[2] = 1;
-    p.b.tap_step[0] = 1;
+    p.b.tap_step[1] = 1;
     p.M = (int)Cout;
     p.N = (int)Cin;
     p.c = workspace + (long long)tap0 * Cout * pl.bn;
     p.ldc = pl.bn;
     p.c_tap_stride = (long long)Cout * pl.bn;
     p.c_z_stride = (long long)taps * Cout * pl.bn;
-    TensorView3 ta{dy, {(unsigned long long)T, (unsigned long long)Cout, (unsigned long long)B},
-                   {(unsigned long long)lddy * 4, (unsigned long long)Cout * lddy * 4}};
-    TensorView3 tb{x, {(unsigned long long)T, (unsigned long long)Cin, (unsigned long long)B},
-                   {(unsigned long long)ldx * 4, (unsigned long long)Cin * ldx * 4}};
+    TensorView3 ta{dy, {(unsigned long long)Cout, (unsigned long long)T, (unsigned long long)B},
+                   {(unsigned long long)lddy * 4, (unsigned long long)T * lddy * 4}};
+    TensorView3 tb{x, {(unsigned long long)Cin, (unsigned long long)T, (unsigned long long)B},
+                   {(unsigned long long)ldx * 4, (unsigned long long)T * ldx * 4}};
     int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, 1, pl.splits), st);
     if (rc != XM_OK) return rc;
   }
@@ -480,10 +465,7 @@ int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
                                                                              (int)Cin, pl.bn, dw);
   int rc = check_launch();
   if (rc != XM_OK) return rc;
-  if (db) {
-    conv_bias_grad_kernel<<<(unsigned)Cout, 256, 0, st>>>(dy, B, (int)Cout, T, lddy, db);
-    rc = check_launch();
-  }
+  if (db) return xm_colsum_f32(dy, B * T, Cout, lddy, db, stream);
   return rc;
 }
 
@@ -564,3 +546,36 @@ int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, co
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ bring-up probe
+// Loads ONE TMA box {32, 32, 1} of a 2-D fp32 tensor at (c0, c1) into shared memory and dumps the
+// raw (still swizzled) 4 KB image: used by tests/gpu_bringup.py to establish which coordinates /
+// swizzle modes the TMA unit accepts on this part.  Not on any product path.
+namespace xm {
+__global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0, int c1, float* out) {
+  __shared__ __align__(1024) float tile[1024];
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(&bar, 4096);
+    ptx::tma_load_3d(&tm, &bar, tile, c0, c1, 0);
+  }
+  ptx::mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = tile[i];
+}
+}  // namespace xm
+
+extern "C" int xm_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int64_t ld, int c0, int c1,
+                                  int swizzle_atom32, float* out, void* stream) {
+  TensorView3 tv{src, {(unsigned long long)cols, (unsigned long long)rows, 1},
+                 {(unsigned long long)ld * 4, (unsigned long long)rows * ld * 4}};
+  CUtensorMap tm;
+  int rc = encode_tmap(&tm, tv, 32, 32, swizzle_atom32);
+  if (rc != XM_OK) return rc;
+  tma_probe_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(tm, c0, c1, out);
+  return check_launch();
+}

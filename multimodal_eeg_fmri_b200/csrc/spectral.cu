@@ -29,7 +29,7 @@ __global__ void window_index_kernel(long long n_rec, long long n_win, long long 
   }
 }
 
-// one block per (window, channel) row; coalesced copy
+// one block per (window, channel) row; coalesced copy.  out (G, C, ld_out >= win)
 __global__ void window_gather_kernel(const float* __restrict__ rec, long long C, long long n_samples, long long n_win,
                                      long long win, long long hop, float* __restrict__ out, long long ld_out,
                                      int round_out) {
@@ -41,6 +41,34 @@ __global__ void window_gather_kernel(const float* __restrict__ rec, long long C,
   for (long long t = threadIdx.x; t < win; t += blockDim.x) {
     const float v = src[t];
     dst[t] = round_out ? round_tf32(v) : v;
+  }
+}
+
+// Transposing gather to channels-last: out (G, win, ld_out >= C).  32x32 tiles through shared
+// memory so both the read (along time) and the write (along channels) are coalesced.
+// grid (G, ceil(win/32), ceil(C/32)), block 32 x 8.
+__global__ void window_gather_nwc_kernel(const float* __restrict__ rec, long long C, long long n_samples,
+                                         long long n_win, long long win, long long hop, float* __restrict__ out,
+                                         long long ld_out, int round_out) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long g = blockIdx.x;
+  const long long r = g / n_win, w = g - r * n_win;
+  const long long t0 = blockIdx.y * 32ll, c0 = blockIdx.z * 32ll;
+  const float* src = rec + (r * C) * n_samples + w * hop;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const long long c = c0 + j, t = t0 + tx;
+    tile[j][tx] = (c < C && t < win) ? src[c * n_samples + t] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const long long t = t0 + j, c = c0 + tx;
+    if (t < win && c < C) {
+      const float v = tile[tx][j];
+      out[(g * win + t) * ld_out + c] = round_out ? round_tf32(v) : v;
+    }
   }
 }
 
@@ -222,11 +250,20 @@ int xm_window_index_i64(int64_t n_rec, int64_t n_samples, int64_t win, int64_t h
 }
 
 int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
-                         float* out, int64_t ld_out, int round_tf32, void* stream) {
-  if (!rec || !out || n_rec <= 0 || C <= 0 || win <= 0 || hop <= 0 || n_samples < win || ld_out < win)
-    return XM_ERR_INVALID;
+                         float* out, int64_t ld_out, int channels_last, int round_tf32, void* stream) {
+  if (!rec || !out || n_rec <= 0 || C <= 0 || win <= 0 || hop <= 0 || n_samples < win) return XM_ERR_INVALID;
   const long long n_win = (n_samples - win) / hop + 1;
-  const long long rows = n_rec * n_win * C;
+  const long long G = n_rec * n_win;
+  if (channels_last) {
+    if (ld_out < C) return XM_ERR_INVALID;
+    if (G > 2147483647ll || ceil_div(win, 32) > 65535 || ceil_div(C, 32) > 65535) return XM_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)G, ceil_div(win, 32), ceil_div(C, 32));
+    window_gather_nwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rec, C, n_samples, n_win, win, hop, out, ld_out,
+                                                                     round_tf32);
+    return check_launch();
+  }
+  if (ld_out < win) return XM_ERR_INVALID;
+  const long long rows = G * C;
   if (rows > 2147483647ll) return XM_ERR_UNSUPPORTED;
   window_gather_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(rec, C, n_samples, n_win, win, hop, out, ld_out,
                                                                          round_tf32);

@@ -134,20 +134,23 @@ XM_DEVICE void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
 XM_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ descriptors
-// Shared-memory matrix descriptor (tcgen05), 128-byte swizzle, operand tile base 1024-B aligned.
+// Shared-memory matrix descriptor (tcgen05), operand tile base 1024-B aligned.
 //   bits [ 0,14) start address >> 4        bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1 (Blackwell)
-//   bits [61,64) layout type: 2 = SWIZZLE_128B
-// K-major  (rows of 128 B = 32 tf32 along K; 8-row groups 1024 B apart):  LBO unused, SBO = 1024.
+//   bits [61,64) layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+// K-major  (rows of 128 B = 32 tf32 along K; 8-row groups 1024 B apart; 16-B chunks XOR row%8;
+//           TMA CU_TENSOR_MAP_SWIZZLE_128B):           layout 2, LBO unused, SBO = 1024.
 // MN-major (rows of 128 B = 32 tf32 along M/N, one row per k; 32-wide MN blocks `mn_block_bytes`
-//           apart; 8-k groups 1024 B apart):                              LBO = mn_block_bytes, SBO = 1024.
-XM_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//           apart).  For 32-bit operands the ONLY MN-major layout the tensor core accepts is the
+//           32-byte-atom swizzle (32-B chunks XOR row%4, pattern repeats every 4 k-rows = 512 B;
+//           TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):  layout 1, LBO = mn_block_bytes, SBO = 512.
+XM_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout_type & 7u) << 61;
   return d;
 }
 

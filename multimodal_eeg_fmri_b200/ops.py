@@ -45,10 +45,18 @@ def _chk(*tensors):
             raise _lib.XmodalError(f"expected float32, got {t.dtype}")
 
 
+_SYNC_DEBUG = bool(int(__import__("os").environ.get("XM_SYNC_DEBUG", "0")))
+
+
 def _call(name, *args):
     global _launches
     _launches += 1
     _lib.call(name, *args)
+    if _SYNC_DEBUG:  # attribute asynchronous kernel faults to the entry point that caused them
+        try:
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            raise _lib.XmodalError(f"{name} faulted on the device: {exc}") from exc
 
 
 def _rowmajor(t: torch.Tensor) -> torch.Tensor:
@@ -76,16 +84,22 @@ def empty_pitched(shape: Tuple[int, ...], device) -> torch.Tensor:
     return buf if Tp == T else buf[..., :T]
 
 
-def as_pitched(t: torch.Tensor) -> torch.Tensor:
-    """(B, C, T) tensor laid out as rows of pitch % 4 == 0, rows densely stacked, 16-B aligned."""
-    B, C, T = t.shape
+def as_nwc(t: torch.Tensor) -> torch.Tensor:
+    """(B, T, C) channels-last tensor with unit channel stride, row pitch % 4 == 0, rows densely
+    stacked and a 16-B aligned base (what the TMA tensor maps need); copies only if it must."""
+    B, T, C = t.shape
     ld = t.stride(2) == 1 and t.stride(1)
-    ok = ld and ld % 4 == 0 and t.stride(0) == C * ld and t.data_ptr() % 16 == 0
+    ok = ld and ld % 4 == 0 and ld >= C and t.stride(0) == T * ld and t.data_ptr() % 16 == 0
     if ok:
         return t
-    out = empty_pitched((B, C, T), t.device)
+    out = empty_pitched((B, T, C), t.device)
     out.copy_(t)
     return out
+
+
+def to_nwc(x: torch.Tensor, round_out: bool = False) -> torch.Tensor:
+    """(B, C, T) reference layout -> channels-last (B, T, C) (pitched), one transposing pass."""
+    return window_gather(x, x.shape[2], 1, channels_last=True, round_out=round_out)
 
 
 # ------------------------------------------------------------------ linear
@@ -132,7 +146,7 @@ def linear_wgrad(dy, x, need_bias=True, splits: int = 0):
     return dw, db
 
 
-# ------------------------------------------------------------------ conv1d
+# ------------------------------------------------------------------ conv1d (channels-last activations)
 def conv1d_pack_weight(w):
     """(Cout, Cin, taps) -> tf32-rounded (taps, Cout, ldk) and (taps, Cin, ldt) operand copies."""
     _chk(w)
@@ -145,12 +159,14 @@ def conv1d_pack_weight(w):
     return wk, wt
 
 
-def conv1d_fwd(x, wk, bias, Cout, round_out=False):
+def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
+    """x (B, T, Cin) channels-last -> y (B, T, Cout).  `out` may be a channel slice of a wider
+    (B, T, Ctot) buffer (free concat of parallel branches)."""
     _chk(x, wk, bias)
-    x = as_pitched(x)
-    B, Cin, T = x.shape
+    x = as_nwc(x)
+    B, T, Cin = x.shape
     taps, _, ldk = wk.shape
-    y = empty_pitched((B, Cout, T), x.device)
+    y = empty_pitched((B, T, Cout), x.device) if out is None else out
     _call("xm_conv1d_fwd_f32", _p(x), _p(wk), _p(bias), _p(y), B, Cin, Cout, T, taps, x.stride(1), ldk, y.stride(1),
           int(round_out), _stream())
     return y
@@ -158,20 +174,21 @@ def conv1d_fwd(x, wk, bias, Cout, round_out=False):
 
 def conv1d_dgrad(dy, wt, Cin, round_out=False):
     _chk(dy, wt)
-    dy = as_pitched(dy)
-    B, Cout, T = dy.shape
+    dy = as_nwc(dy)
+    B, T, Cout = dy.shape
     taps, _, ldt = wt.shape
-    dx = empty_pitched((B, Cin, T), dy.device)
+    dx = empty_pitched((B, T, Cin), dy.device)
     _call("xm_conv1d_dgrad_f32", _p(dy), _p(wt), _p(dx), B, Cin, Cout, T, taps, dy.stride(1), ldt, dx.stride(1),
           int(round_out), _stream())
     return dx
 
 
 def conv1d_wgrad(dy, x, taps, need_bias=True):
+    """dy (B, T, Cout), x (B, T, Cin) channels-last -> dw (Cout, Cin, taps) [reference layout], db."""
     _chk(dy, x)
-    dy, x = as_pitched(dy), as_pitched(x)
-    B, Cout, T = dy.shape
-    Cin = x.shape[1]
+    dy, x = as_nwc(dy), as_nwc(x)
+    B, T, Cout = dy.shape
+    Cin = x.shape[2]
     n_ws = _lib.lib().xm_conv1d_wgrad_workspace(B, Cin, Cout, taps)
     ws = torch.empty(n_ws, device=dy.device, dtype=torch.float32)
     dw = torch.empty(Cout, Cin, taps, device=dy.device, dtype=torch.float32)
@@ -182,19 +199,23 @@ def conv1d_wgrad(dy, x, taps, need_bias=True):
 
 
 # ------------------------------------------------------------------ batch norm + act (+pool, +dropout)
-def bn_partial_stats(y):
-    """y (B, C, T) pitched or (B, C): per-split {sum, sumsq} doubles, shape (nsplit, C, 2)."""
-    _chk(y)
+def _bn_dims(y):
+    """-> (B, T, C, ld) for channels-last (B, T, C) or (B, C) inputs."""
     if y.dim() == 2:
-        B, C = y.shape
-        T, ld = 1, 1
-        assert y.is_contiguous()
-    else:
-        B, C, T = y.shape
-        ld = y.stride(1)
-    ns = _lib.lib().xm_bn_nsplit(B, C, T)
+        assert y.stride(1) == 1
+        return y.shape[0], 1, y.shape[1], y.stride(0)
+    B, T, C = y.shape
+    assert y.stride(2) == 1 and y.stride(0) == T * y.stride(1)
+    return B, T, C, y.stride(1)
+
+
+def bn_partial_stats(y):
+    """Per-split {sum, sumsq} doubles, shape (nsplit, C, 2)."""
+    _chk(y)
+    B, T, C, ld = _bn_dims(y)
+    ns = _lib.lib().xm_bn_nsplit(B * T, C)
     part = torch.empty(ns, C, 2, device=y.device, dtype=torch.float64)
-    _call("xm_bn_partial_stats_f32", _p(y), B, C, T, ld, _p(part), _stream())
+    _call("xm_bn_partial_stats_f32", _p(y), B * T, C, ld, _p(part), _stream())
     return part
 
 
@@ -207,37 +228,32 @@ def bn_finalize_stats(part, count, eps, running_mean=None, running_var=None, mom
     return mean, invstd
 
 
-def _bn_dims(y):
-    if y.dim() == 2:
-        B, C = y.shape
-        return B, C, 1, 1
-    B, C, T = y.shape
-    return B, C, T, y.stride(1)
-
-
 def bn_act_fwd(y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, drop_before_pool=False,
                round_out=False):
     _chk(y, mean, invstd, gamma, beta)
-    B, C, T, ld = _bn_dims(y)
+    B, T, C, ld = _bn_dims(y)
     if y.dim() == 2:
-        out = torch.empty_like(y)
-        ldo = 1
+        out = torch.empty(B, C, device=y.device, dtype=torch.float32)
+        ldo = C
     else:
-        out = empty_pitched((B, C, T // 2 if pool == 2 else T), y.device)
+        out = empty_pitched((B, T // 2 if pool == 2 else T, C), y.device)
         ldo = out.stride(1)
-    _call("xm_bn_act_fwd_f32", _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(out), B, C, T, ld, ldo,
+    _call("xm_bn_act_fwd_f32", _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(out), B, T, C, ld, ldo,
           act_code(act), pool, float(drop_p), int(seed), int(drop_before_pool), int(round_out), _stream())
     return out
 
 
+def _ldo(dout):
+    return dout.stride(0) if dout.dim() == 2 else dout.stride(1)
+
+
 def bn_act_bwd_reduce(dout, y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, drop_before_pool=False):
     _chk(dout, y)
-    B, C, T, ld = _bn_dims(y)
-    ldo = 1 if y.dim() == 2 else dout.stride(1)
-    ns = _lib.lib().xm_bn_nsplit(B, C, T)
+    B, T, C, ld = _bn_dims(y)
+    ns = _lib.lib().xm_bn_nsplit(B * T, C)
     part = torch.empty(ns, C, 2, device=y.device, dtype=torch.float64)
-    _call("xm_bn_act_bwd_reduce_f32", _p(dout), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), B, C, T, ld, ldo,
-          act_code(act), pool, float(drop_p), int(seed), int(drop_before_pool), _p(part), _stream())
+    _call("xm_bn_act_bwd_reduce_f32", _p(dout), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), B, T, C, ld,
+          _ldo(dout), act_code(act), pool, float(drop_p), int(seed), int(drop_before_pool), _p(part), _stream())
     return part
 
 
@@ -251,13 +267,32 @@ def bn_bwd_finalize(part):
 
 def bn_act_bwd_apply(dout, y, mean, invstd, gamma, beta, dbeta, dgamma, count, act, pool=0, drop_p=0.0, seed=0,
                      drop_before_pool=False, round_out=False):
-    B, C, T, ld = _bn_dims(y)
-    ldo = 1 if y.dim() == 2 else dout.stride(1)
-    dy = torch.empty_like(y) if y.dim() == 2 else empty_pitched((B, C, T), y.device)
+    B, T, C, ld = _bn_dims(y)
+    dy = torch.empty(B, C, device=y.device, dtype=torch.float32) if y.dim() == 2 else empty_pitched((B, T, C), y.device)
+    lddy = dy.stride(0) if y.dim() == 2 else dy.stride(1)
+    assert lddy == ld, "dy is written with y's pitch"
     _call("xm_bn_act_bwd_apply_f32", _p(dout), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(dbeta),
-          _p(dgamma), float(count), _p(dy), B, C, T, ld, ldo, act_code(act), pool, float(drop_p), int(seed),
+          _p(dgamma), float(count), _p(dy), B, T, C, ld, _ldo(dout), act_code(act), pool, float(drop_p), int(seed),
           int(drop_before_pool), int(round_out), _stream())
     return dy
+
+
+def seqmean(x):
+    """x (B, T, C) channels-last -> (B, C): AdaptiveAvgPool1d(1)."""
+    _chk(x)
+    B, T, C, ld = _bn_dims(x)
+    out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    _call("xm_seqmean_f32", _p(x), B, T, C, ld, _p(out), _stream())
+    return out
+
+
+def seqmean_bwd(dout, T):
+    _chk(dout)
+    dout = dout.contiguous()
+    B, C = dout.shape
+    dx = empty_pitched((B, T, C), dout.device)
+    _call("xm_seqmean_bwd_f32", _p(dout), B, T, C, dx.stride(1), _p(dx), _stream())
+    return dx
 
 
 # ------------------------------------------------------------------ layer norm + act
@@ -294,33 +329,6 @@ def colsum(x):
     out = torch.empty(N, device=x.device, dtype=torch.float32)
     _call("xm_colsum_f32", _p(x), M, N, x.stride(0), _p(out), _stream())
     return out
-
-
-def rowmean(x):
-    """x (..., T) with unit inner stride and uniform row pitch -> (...)"""
-    _chk(x)
-    *lead, T = x.shape
-    if x.dim() == 3:
-        assert x.stride(2) == 1 and x.stride(0) == x.size(1) * x.stride(1)
-        ld = x.stride(1)
-    else:
-        assert x.is_contiguous()
-        ld = T
-    R = 1
-    for s in lead:
-        R *= s
-    out = torch.empty(*lead, device=x.device, dtype=torch.float32)
-    _call("xm_rowmean_f32", _p(x), R, T, ld, _p(out), _stream())
-    return out
-
-
-def rowmean_bwd(dout, T):
-    _chk(dout)
-    dout = dout.contiguous()
-    dx = empty_pitched((*dout.shape, T), dout.device)
-    R = dout.numel()
-    _call("xm_rowmean_bwd_f32", _p(dout), R, T, dx.stride(-2), _p(dx), _stream())
-    return dx
 
 
 # ------------------------------------------------------------------ l2norm / similarity / infonce
@@ -391,13 +399,15 @@ def window_index(n_rec, n_samples, win, hop, rec_labels=None, rec_subjects=None,
     return starts, rec_ids, labels, subjects
 
 
-def window_gather(rec, win, hop, round_out=False):
+def window_gather(rec, win, hop, channels_last=False, round_out=False):
+    """rec (R, C, n) -> (R*n_win, C, win) [reference layout] or (R*n_win, win, C) [channels-last]."""
     _chk(rec)
     rec = rec.contiguous()
     R, C, n = rec.shape
     n_win = (n - win) // hop + 1
-    out = empty_pitched((R * n_win, C, win), rec.device)
-    _call("xm_window_gather_f32", _p(rec), R, C, n, win, hop, _p(out), out.stride(1), int(round_out), _stream())
+    out = empty_pitched((R * n_win, win, C) if channels_last else (R * n_win, C, win), rec.device)
+    _call("xm_window_gather_f32", _p(rec), R, C, n, win, hop, _p(out), out.stride(1), int(channels_last),
+          int(round_out), _stream())
     return out
 
 

@@ -67,8 +67,18 @@ def g_linear_wgrad():
 
 
 def _conv_cases():
-    return [(2, 32, 32, 128, 3), (3, 64, 64, 500, 7), (2, 64, 128, 500, 5), (2, 128, 128, 250, 3), (2, 48, 96, 250, 5),
+    sel = os.environ.get("XM_CASE")
+    cases = _conv_cases_all()
+    return cases if sel is None else [cases[int(sel)]]
+
+
+def _conv_cases_all():
+    return [(1, 32, 32, 128, 1), (2, 32, 32, 128, 1), (2, 32, 32, 128, 3), (3, 64, 64, 500, 7), (2, 64, 128, 500, 5), (2, 128, 128, 250, 3), (2, 48, 96, 250, 5),
             (2, 18, 48, 500, 7), (1, 192, 128, 100, 1)]
+
+
+def _nwc(x):
+    return x.transpose(1, 2).contiguous()
 
 
 def g_conv_fwd():
@@ -80,9 +90,11 @@ def g_conv_fwd():
         w = torch.randn(Cout, Cin, k, device="cuda") / (Cin * k) ** 0.5
         b = torch.randn(Cout, device="cuda")
         wk, wt = ops.conv1d_pack_weight(w)
-        y = ops.conv1d_fwd(x, wk, b, Cout)
+        xl = ops.to_nwc(x)
+        ok_t = bool((xl == _nwc(x)).all())
+        y = ops.conv1d_fwd(xl, wk, b, Cout)
         ref = torch.nn.functional.conv1d(x.double(), w.double(), b.double(), padding=k // 2)
-        print(f"conv_fwd B{B} Cin{Cin} Cout{Cout} T{T} k{k}: rel={rel(y, ref):.3e}", flush=True)
+        print(f"conv_fwd B{B} Cin{Cin} Cout{Cout} T{T} k{k}: rel={rel(y, _nwc(ref)):.3e} to_nwc_exact={ok_t}", flush=True)
 
 
 def g_conv_dgrad():
@@ -93,19 +105,19 @@ def g_conv_dgrad():
         dy = torch.randn(B, Cout, T, device="cuda")
         w = torch.randn(Cout, Cin, k, device="cuda") / (Cin * k) ** 0.5
         wk, wt = ops.conv1d_pack_weight(w)
-        dx = ops.conv1d_dgrad(dy, wt, Cin)
+        dx = ops.conv1d_dgrad(_nwc(dy), wt, Cin)
         ref = torch.nn.functional.conv_transpose1d(dy.double(), w.double(), padding=k // 2)
-        print(f"conv_dgrad B{B} Cin{Cin} Cout{Cout} T{T} k{k}: rel={rel(dx, ref):.3e}", flush=True)
+        print(f"conv_dgrad B{B} Cin{Cin} Cout{Cout} T{T} k{k}: rel={rel(dx, _nwc(ref)):.3e}", flush=True)
 
 
 def g_conv_wgrad():
     import torch
     from multimodal_eeg_fmri_b200 import ops
     torch.manual_seed(5)
-    for (B, Cin, Cout, T, k) in _conv_cases() + [(300, 64, 64, 500, 7)]:
+    for (B, Cin, Cout, T, k) in _conv_cases() + ([(300, 64, 64, 500, 7)] if os.environ.get("XM_CASE") is None else []):
         x = torch.randn(B, Cin, T, device="cuda")
         dy = torch.randn(B, Cout, T, device="cuda")
-        dw, db = ops.conv1d_wgrad(dy, x, k)
+        dw, db = ops.conv1d_wgrad(_nwc(dy), _nwc(x), k)
         xd = x.double().requires_grad_(False)
         wd = torch.zeros(Cout, Cin, k, device="cuda", dtype=torch.float64, requires_grad=True)
         out = torch.nn.functional.conv1d(xd, wd, None, padding=k // 2)
@@ -197,35 +209,37 @@ def g_bn():
     import torch
     from multimodal_eeg_fmri_b200 import ops
     torch.manual_seed(8)
-    for (shape, act, pool) in [((4, 16, 100), "gelu", 0), ((8, 64, 500), "gelu", 2), ((3, 48, 250), "gelu", 2),
-                               ((64, 128), "relu", 0), ((5, 7, 33), "gelu", 0)]:
-        y = torch.randn(*shape, device="cuda") * 2 + 0.5
+    for (shape, act, pool) in [((4, 16, 100), "gelu", 0), ((8, 64, 500), "gelu", 2), ((3, 48, 251), "gelu", 2),
+                               ((64, 128), "relu", 0), ((5, 7, 33), "gelu", 0), ((4096, 64), "relu", 0)]:
+        y = torch.randn(*shape, device="cuda") * 2 + 0.5   # reference layout (B, C, T) or (B, C)
         C = shape[1]
         gamma = torch.rand(C, device="cuda") + 0.5
         beta = torch.randn(C, device="cuda")
-        yp = ops.as_pitched(y) if y.dim() == 3 else y
-        part = ops.bn_partial_stats(yp)
+        three = y.dim() == 3
+        yl = ops.as_nwc(_nwc(y)) if three else y
+        part = ops.bn_partial_stats(yl)
         cnt = y.numel() // C
         rm = torch.zeros(C, device="cuda")
         rv = torch.ones(C, device="cuda")
         mean, invstd = ops.bn_finalize_stats(part, cnt, 1e-5, rm, rv, 0.1)
-        out = ops.bn_act_fwd(yp, mean, invstd, gamma, beta, act, pool)
+        out = ops.bn_act_fwd(yl, mean, invstd, gamma, beta, act, pool)
         yd = y.double().requires_grad_(True)
         gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
         ref = _bn_ref(yd, gd, bd, act, pool)
-        dout = torch.randn_like(out)
+        dout = torch.randn_like(ref).float()
         gy, gg, gb = torch.autograd.grad(ref, (yd, gd, bd), dout.double())
-        doutp = ops.as_pitched(dout) if dout.dim() == 3 else dout
-        part2 = ops.bn_act_bwd_reduce(doutp, yp, mean, invstd, gamma, beta, act, pool)
+        doutl = ops.as_nwc(_nwc(dout)) if three else dout
+        part2 = ops.bn_act_bwd_reduce(doutl, yl, mean, invstd, gamma, beta, act, pool)
         dbeta, dgamma = ops.bn_bwd_finalize(part2)
-        dy = ops.bn_act_bwd_apply(doutp, yp, mean, invstd, gamma, beta, dbeta, dgamma, cnt, act, pool)
-        dims = (0, 2) if y.dim() == 3 else (0,)
-        print(f"bn {shape} act={act} pool={pool}: fwd rel={rel(out, ref):.3e} dy rel={rel(dy, gy):.3e} "
+        dy = ops.bn_act_bwd_apply(doutl, yl, mean, invstd, gamma, beta, dbeta, dgamma, cnt, act, pool)
+        dims = (0, 2) if three else (0,)
+        t = (lambda z: _nwc(z)) if three else (lambda z: z)
+        print(f"bn {shape} act={act} pool={pool}: fwd rel={rel(out, t(ref)):.3e} dy rel={rel(dy, t(gy)):.3e} "
               f"dgamma rel={rel(dgamma, gg):.3e} dbeta rel={rel(dbeta, gb):.3e} "
               f"rmean rel={rel(rm, 0.1 * y.double().mean(dims)):.3e} rvar rel={rel(rv, 0.9 + 0.1 * y.double().var(dims, unbiased=True)):.3e}",
               flush=True)
     # dropout statistics + fwd/bwd mask consistency
-    y = torch.randn(8, 64, 500, device="cuda")
+    y = ops.as_nwc(torch.randn(8, 500, 64, device="cuda"))
     C = 64
     gamma = torch.ones(C, device="cuda"); beta = torch.zeros(C, device="cuda")
     mean, invstd = ops.bn_finalize_stats(ops.bn_partial_stats(y), y.numel() // C, 1e-5)
@@ -239,9 +253,12 @@ def g_bn():
         dout = torch.ones_like(out)
         part2 = ops.bn_act_bwd_reduce(dout, y, mean, invstd, gamma, beta, "none", 2, 0.3, 1234, dbp)
         dbeta, _ = ops.bn_bwd_finalize(part2)
-        # sum of dz equals sum over kept outputs of scale
         expect = float((out != 0).sum()) / 0.7 if not dbp else None
         print(f"dropout dbp={dbp} sum(dz)={float(dbeta.sum()):.1f} expect={expect}", flush=True)
+    x = ops.as_nwc(torch.randn(6, 250, 96, device="cuda"))
+    print(f"seqmean rel={rel(ops.seqmean(x), x.double().mean(1)):.3e}")
+    d = torch.randn(6, 96, device="cuda")
+    print(f"seqmean_bwd rel={rel(ops.seqmean_bwd(d, 250), (d.double() / 250)[:, None, :].expand(6, 250, 96)):.3e}", flush=True)
 
 
 def g_ln():
@@ -281,11 +298,37 @@ def g_misc():
     print(f"zscore rel={rel(z, ref):.3e}")
     x = torch.randn(1000, 96, device="cuda")
     print(f"colsum rel={rel(ops.colsum(x), x.double().sum(0)):.3e}")
-    x = torch.randn(6, 96, 250, device="cuda")
-    xp = ops.as_pitched(x)
-    print(f"rowmean rel={rel(ops.rowmean(xp), x.double().mean(2)):.3e}")
-    d = torch.randn(6, 96, device="cuda")
-    print(f"rowmean_bwd rel={rel(ops.rowmean_bwd(d, 250), (d.double() / 250)[..., None].expand(6, 96, 250)):.3e}", flush=True)
+
+
+def g_tma_probe():
+    """Which TMA coordinates are legal?  Each probe runs in its own subprocess via XM_CASE."""
+    import ctypes
+    import torch
+    from multimodal_eeg_fmri_b200 import _lib
+    cases = [(0, 0, 0), (4, 0, 0), (-4, 0, 0), (0, -1, 0), (0, 3, 0), (1, 0, 0), (-1, 0, 0), (2, 0, 0), (1, 0, 1), (0, 0, 1), (-4, 0, 1)]
+    c0, c1, sw = cases[int(os.environ.get("XM_CASE", "0"))]
+    rows, cols = 64, 96
+    src = torch.arange(rows * cols, device="cuda", dtype=torch.float32).reshape(rows, cols) + 1
+    out = torch.zeros(1024, device="cuda")
+    _lib.call("xm_debug_tma_probe", ctypes.c_void_p(src.data_ptr()), rows, cols, cols, c0, c1, sw,
+              ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    img = out.cpu().reshape(32, 32)
+    # un-swizzle: SWIZZLE_128B: 16-B chunk ^= row % 8 ; ATOM_32B: 32-B chunk ^= row % 4
+    exp = torch.zeros(32, 32)
+    for r in range(32):
+        for c in range(32):
+            rr, cc = c1 + r, c0 + c
+            exp[r, c] = float(src[rr, cc]) if (0 <= rr < rows and 0 <= cc < cols) else 0.0
+    un = torch.zeros(32, 32)
+    for r in range(32):
+        for c in range(32):
+            if sw == 0:
+                pc = (((c // 4) ^ (r % 8)) * 4) + (c % 4)
+            else:
+                pc = (((c // 8) ^ (r % 4)) * 8) + (c % 8)
+            un[r, c] = img[r, pc]
+    print(f"tma_probe c0={c0} c1={c1} atom32={sw}: match={bool((un == exp).all())}", flush=True)
 
 
 GROUPS = {k[2:]: v for k, v in list(globals().items()) if k.startswith("g_")}
@@ -298,14 +341,29 @@ if __name__ == "__main__":
         print(f"[{sys.argv[1]}] done", flush=True)
         sys.exit(0)
     rc = 0
+    runs = []
+    only = os.environ.get("XM_GROUPS")
     for name in GROUPS:
+        if only and name not in only.split(","):
+            continue
+        if name == "tma_probe":
+            runs += [(name, str(i)) for i in range(11)]
+        elif name.startswith("conv_") and os.environ.get("XM_SPLIT_CONV"):
+            runs += [(name, str(i)) for i in range(len(_conv_cases_all()))]
+        else:
+            runs.append((name, None))
+    for name, case in runs:
         t0 = time.time()
+        env = dict(os.environ)
+        if case is not None:
+            env["XM_CASE"] = case
+            env["XM_SYNC_DEBUG"] = "1"
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True, timeout=240)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True, timeout=240, env=env)
             print(r.stdout, end="")
             if r.returncode != 0:
                 rc = 1
-                print(f"[{name}] FAILED rc={r.returncode}\n{r.stderr[-3000:]}")
+                print(f"[{name} case={case}] FAILED rc={r.returncode}\n{r.stderr[-1500:]}")
         except subprocess.TimeoutExpired as e:
             rc = 1
             print(f"[{name}] TIMEOUT\n{(e.stdout or b'')[-2000:]}")
