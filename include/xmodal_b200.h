@@ -40,6 +40,8 @@ extern "C" {
 #define XM_ACT_NONE 0
 #define XM_ACT_RELU 1
 #define XM_ACT_GELU 2 /* exact erf GELU, as nn.GELU() */
+#define XM_ACT_TANH 3
+#define XM_ACT_SIGMOID 4
 
 int xm_abi_version(void);
 const char* xm_strerror(int code);
@@ -166,6 +168,12 @@ int xm_ln_nblk(int64_t M);
 int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, const float* beta, const float* mean,
                       const float* rstd, float* dx, float* dgamma_part, float* dbeta_part, int64_t M, int64_t D,
                       int act, float drop_p, uint64_t seed, void* stream);
+
+/* out = drop(act(x)) over n contiguous elements, and its backward dx = dout * mask * act'(x)
+ * (nn.GELU/ReLU/Tanh/Sigmoid + nn.Dropout after a projection). */
+int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p, uint64_t seed, void* stream);
+int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
+                   void* stream);
 
 /* out (N) = column sums of x (M, N) (bias gradients, partial reductions). */
 int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream);

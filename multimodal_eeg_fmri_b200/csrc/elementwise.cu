@@ -406,6 +406,24 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ dout, const float* _
   }
 }
 
+// ------------------------------------------------------------------ activation + dropout
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int act,
+                               float drop_scale, uint32_t drop_thresh, uint64_t seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float o = apply_act(x[i], act);
+    if (drop_thresh) o = dropout_keep((uint64_t)i, seed, drop_thresh) ? o * drop_scale : 0.f;
+    out[i] = o;
+  }
+}
+__global__ void act_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, float* __restrict__ dx,
+                               long long n, int act, float drop_scale, uint32_t drop_thresh, uint64_t seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = dout[i];
+    if (drop_thresh) g = dropout_keep((uint64_t)i, seed, drop_thresh) ? g * drop_scale : 0.f;
+    dx[i] = g * act_grad(x[i], act);
+  }
+}
+
 // ------------------------------------------------------------------ small reductions
 // out[n] = sum_m x[m, n]; block = 32 columns x 8 row lanes
 __global__ void colsum_kernel(const float* __restrict__ x, long long M, long long N, long long ld,
@@ -634,6 +652,24 @@ int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, con
   drop_consts(drop_p, sc, th);
   ln_act_bwd_kernel<<<xm_ln_nblk(M), 256, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
       dout, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, M, (int)D, act, sc, th, seed);
+  return check_launch();
+}
+
+int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p, uint64_t seed, void* stream) {
+  if (!x || !out || n <= 0 || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
+  float sc;
+  uint32_t th;
+  drop_consts(drop_p, sc, th);
+  act_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, out, n, act, sc, th, seed);
+  return check_launch();
+}
+int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
+                   void* stream) {
+  if (!dout || !x || !dx || n <= 0 || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
+  float sc;
+  uint32_t th;
+  drop_consts(drop_p, sc, th);
+  act_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dout, x, dx, n, act, sc, th, seed);
   return check_launch();
 }
 

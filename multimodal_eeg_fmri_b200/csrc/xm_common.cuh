@@ -72,15 +72,25 @@ XM_DEVICE bool dropout_keep(uint64_t idx, uint64_t seed, uint32_t threshold) {
   return hash_u32(idx, seed) >= threshold;
 }
 
-// act codes shared with the host (include/xmodal_b200.h): 0 none, 1 relu, 2 gelu(erf)
+// act codes shared with the host (include/xmodal_b200.h)
 XM_DEVICE float apply_act(float x, int act) {
   if (act == XM_ACT_RELU) return fmaxf(x, 0.0f);
   if (act == XM_ACT_GELU) return gelu_erf(x);
+  if (act == XM_ACT_TANH) return tanhf(x);
+  if (act == XM_ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
   return x;
 }
 XM_DEVICE float act_grad(float x, int act) {
   if (act == XM_ACT_RELU) return x > 0.0f ? 1.0f : 0.0f;
   if (act == XM_ACT_GELU) return gelu_erf_grad(x);
+  if (act == XM_ACT_TANH) {
+    const float t = tanhf(x);
+    return 1.0f - t * t;
+  }
+  if (act == XM_ACT_SIGMOID) {
+    const float s = 1.0f / (1.0f + expf(-x));
+    return s * (1.0f - s);
+  }
   return 1.0f;
 }
 

@@ -1,0 +1,359 @@
+"""Autograd layer over the C-ABI kernels: each class fuses one chain of reference layers
+(Conv1d-BatchNorm-GELU-MaxPool-Dropout, Linear-BatchNorm-ReLU-Dropout, Linear-LayerNorm-GELU-Dropout,
+similarity + symmetric InfoNCE, ...) into a handful of hand-written kernels, forward and backward.
+
+Conventions: activations between conv blocks are channels-last `(B, T, C)` (see csrc/gemm_engine.cuh);
+dropout masks and max-pool argmaxes are recomputed in the backward from a saved 64-bit seed, never
+stored; values that feed the next tensor-core contraction are rounded to tf32 when written.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+# ----------------------------------------------------------------------------- context
+
+
+@dataclass
+class ParallelContext:
+    """Data-parallel context consulted by the fused blocks.
+
+    group: torch.distributed process group (None = single process).  With `sync_bn` the per-channel
+    BatchNorm partial sums are all-reduced so a sharded run reproduces the single-process global
+    batch statistics."""
+
+    group: Optional[object] = None
+    sync_bn: bool = True
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if self.active else 1
+
+    @property
+    def rank(self) -> int:
+        return dist.get_rank(self.group) if self.active else 0
+
+    @property
+    def active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and (self.group is not None or dist.get_world_size() > 1)
+
+
+_CTX = ParallelContext()
+
+
+def parallel_context() -> ParallelContext:
+    return _CTX
+
+
+def set_parallel_context(ctx: ParallelContext) -> None:
+    global _CTX
+    _CTX = ctx
+
+
+_seed_counter = itertools.count(1)
+_base_seed = 0x5EED
+
+
+def manual_seed(seed: int) -> None:
+    """Re-seed the dropout mask stream (counter-based: mask = hash(seed, element index))."""
+    global _seed_counter, _base_seed
+    _base_seed = int(seed) & 0xFFFFFFFF
+    _seed_counter = itertools.count(1)
+
+
+def next_seed() -> int:
+    return ((_base_seed << 32) ^ (next(_seed_counter) * 0x9E3779B1) ^ (_CTX.rank << 20)) & 0x7FFFFFFFFFFFFFFF
+
+
+def _allreduce_sum(t: torch.Tensor) -> torch.Tensor:
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_CTX.group)
+    return t
+
+
+def _bn_stats(y, eps, running_mean, running_var, momentum, training):
+    """mean / invstd / count for a (B,T,C) or (B,C) tensor: batch statistics (optionally synchronised
+    across ranks) in training, running statistics in eval."""
+    rows = y.shape[0] * (y.shape[1] if y.dim() == 3 else 1)
+    if not training:
+        invstd = torch.rsqrt(running_var + eps)
+        return running_mean, invstd, float(rows)
+    part = ops.bn_partial_stats(y)
+    count = float(rows)
+    if _CTX.active and _CTX.sync_bn:
+        part = _allreduce_sum(part.sum(0, keepdim=True))
+        count *= _CTX.world
+    mean, invstd = ops.bn_finalize_stats(part, count, eps, running_mean, running_var, momentum)
+    return mean, invstd, count
+
+
+def _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, pool, p, seed, dbp, training, round_out):
+    part = ops.bn_act_bwd_reduce(dout, y, mean, invstd, gamma, beta, act, pool, p, seed, dbp)
+    if training and _CTX.active and _CTX.sync_bn:
+        part_g = _allreduce_sum(part.sum(0, keepdim=True).clone())
+        dbeta_g, dgamma_g = ops.bn_bwd_finalize(part_g)  # global sums drive dy
+        dbeta, dgamma = ops.bn_bwd_finalize(part)        # local sums are this rank's parameter gradients
+    else:
+        dbeta, dgamma = ops.bn_bwd_finalize(part)
+        dbeta_g, dgamma_g = dbeta, dgamma
+    if not training:  # eval-mode BN is an affine map: no statistic terms in dy
+        dbeta_g, dgamma_g = torch.zeros_like(dbeta), torch.zeros_like(dgamma)
+    dy = ops.bn_act_bwd_apply(dout, y, mean, invstd, gamma, beta, dbeta_g, dgamma_g, count, act, pool, p, seed, dbp,
+                              round_out)
+    return dy, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------- layout
+class ToChannelsLast(torch.autograd.Function):
+    """(B, C, T) reference layout -> (B, T, C) device layout, rounding to tf32 for the first conv."""
+
+    @staticmethod
+    def forward(ctx, x, round_out):
+        return ops.to_nwc(x, round_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        # the same transposing kernel maps a dense (B, T, C) gradient back to (B, C, T)
+        return ops.to_nwc(g.contiguous()), None
+
+
+def to_channels_last(x, round_out=True):
+    return ToChannelsLast.apply(x, round_out)
+
+
+# ----------------------------------------------------------------------------- conv block
+class ConvBnAct(torch.autograd.Function):
+    """Conv1d("same") -> BatchNorm1d -> act -> [MaxPool1d(2)] -> Dropout on channels-last input.
+
+    enhanced_models_v4.py:128-144, 199-221 ; crossmodal_v4_enhancements.py:822-834, 854-866."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, cfg):
+        eps, momentum, act, pool, p, dbp, training, round_out = cfg
+        Cout, Cin, taps = w.shape
+        x = ops.as_nwc(x)
+        wk, wt = ops.conv1d_pack_weight(w)
+        y = ops.conv1d_fwd(x, wk, b, Cout)
+        mean, invstd, count = _bn_stats(y, eps, running_mean, running_var, momentum, training)
+        seed = next_seed() if (training and p > 0) else 0
+        pd = p if training else 0.0
+        out = ops.bn_act_fwd(y, mean, invstd, gamma, beta, act, pool, pd, seed, dbp, round_out)
+        ctx.save_for_backward(x, y, wt, mean, invstd, gamma, beta)
+        ctx.meta = (Cin, taps, count, act, pool, pd, seed, dbp, training)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, wt, mean, invstd, gamma, beta = ctx.saved_tensors
+        Cin, taps, count, act, pool, pd, seed, dbp, training = ctx.meta
+        dout = ops.as_nwc(dout)
+        dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, pool, pd, seed, dbp, training, True)
+        dx = ops.conv1d_dgrad(dy, wt, Cin, round_out=True) if ctx.needs_input_grad[0] else None
+        dw, db = ops.conv1d_wgrad(dy, x, taps, need_bias=True)
+        return dx, dw, db, dgamma, dbeta, None, None, None
+
+
+def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=False, training=True, round_out=True):
+    """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d)."""
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    cfg = (bn.eps, bn.momentum if bn.momentum is not None else 0.1, act, pool, float(drop_p), bool(drop_before_pool),
+           bool(training), bool(round_out))
+    return ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
+
+
+# ----------------------------------------------------------------------------- linear blocks
+class Linear(torch.autograd.Function):
+    """y = x @ w^T + b on the tcgen05 GEMM (nn.Linear)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return ops.linear_fwd(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+        dw, db = ops.linear_wgrad(dy, x, need_bias=ctx.has_bias)
+        return dx, dw, db
+
+
+def linear(x, lin):
+    return Linear.apply(x, lin.weight, lin.bias)
+
+
+class ActDropout(torch.autograd.Function):
+    """act -> Dropout (nn.GELU / nn.ReLU / nn.Tanh / nn.Sigmoid followed by nn.Dropout)."""
+
+    @staticmethod
+    def forward(ctx, x, act, p, seed):
+        ctx.save_for_backward(x)
+        ctx.meta = (act, p, seed)
+        return ops.act_fwd(x, act, p, seed)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        act, p, seed = ctx.meta
+        return ops.act_bwd(g, x, act, p, seed), None, None, None
+
+
+def act_dropout(x, act, drop_p=0.0, training=True):
+    p = float(drop_p) if training else 0.0
+    return ActDropout.apply(x, act, p, next_seed() if p > 0 else 0)
+
+
+class LinearBnAct(torch.autograd.Function):
+    """Linear -> BatchNorm1d -> act -> Dropout on (B, F) rows (fMRI_CODE/fmri_utils.py:26-35, 66-71;
+    crossmodal_v4_enhancements.py:696-723, 768-773, 909-914)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, cfg):
+        eps, momentum, act, p, training = cfg
+        y = ops.linear_fwd(x, w, b)
+        mean, invstd, count = _bn_stats(y, eps, running_mean, running_var, momentum, training)
+        seed = next_seed() if (training and p > 0) else 0
+        pd = p if training else 0.0
+        out = ops.bn_act_fwd(y, mean, invstd, gamma, beta, act, 0, pd, seed, False, False)
+        ctx.save_for_backward(x, w, y, mean, invstd, gamma, beta)
+        ctx.meta = (count, act, pd, seed, training)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, y, mean, invstd, gamma, beta = ctx.saved_tensors
+        count, act, pd, seed, training = ctx.meta
+        dout = dout.contiguous()
+        dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, 0, pd, seed, False, training, False)
+        dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+        dw, db = ops.linear_wgrad(dy, x, need_bias=True)
+        return dx, dw, db, dgamma, dbeta, None, None, None
+
+
+def linear_bn_act(x, lin, bn, act="relu", drop_p=0.0, training=True):
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    cfg = (bn.eps, bn.momentum if bn.momentum is not None else 0.1, act, float(drop_p), bool(training))
+    return LinearBnAct.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
+
+
+class LinearLnAct(torch.autograd.Function):
+    """Linear -> LayerNorm -> act -> Dropout (bridge_utils.py:34-45, 60-66)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, cfg):
+        eps, act, p, training = cfg
+        y = ops.linear_fwd(x, w, b)
+        seed = next_seed() if (training and p > 0) else 0
+        pd = p if training else 0.0
+        out, mean, rstd = ops.ln_act_fwd(y, gamma, beta, eps, act, pd, seed)
+        ctx.save_for_backward(x, w, y, mean, rstd, gamma, beta)
+        ctx.meta = (act, pd, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, y, mean, rstd, gamma, beta = ctx.saved_tensors
+        act, pd, seed = ctx.meta
+        dy, dgamma, dbeta = ops.ln_act_bwd(dout.contiguous(), y, gamma, beta, mean, rstd, act, pd, seed)
+        dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+        dw, db = ops.linear_wgrad(dy, x, need_bias=True)
+        return dx, dw, db, dgamma, dbeta, None
+
+
+def linear_ln_act(x, lin, ln, act="gelu", drop_p=0.0, training=True):
+    return LinearLnAct.apply(x, lin.weight, lin.bias, ln.weight, ln.bias, (ln.eps, act, float(drop_p), bool(training)))
+
+
+# ----------------------------------------------------------------------------- pooling
+class SeqMean(torch.autograd.Function):
+    """AdaptiveAvgPool1d(1) + Flatten on channels-last input: (B, T, C) -> (B, C)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.T = x.shape[1]
+        return ops.seqmean(ops.as_nwc(x))
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.seqmean_bwd(g, ctx.T)
+
+
+def seq_mean(x):
+    return SeqMean.apply(x)
+
+
+# ----------------------------------------------------------------------------- fMRI ROI aggregation
+def roi_meanstd(x):
+    """fMRI_CODE/fmri_utils.py:140-147 on the device; inputs are data (no gradient)."""
+    return ops.roi_meanstd(x)
+
+
+# ----------------------------------------------------------------------------- similarity + InfoNCE
+class _AllGatherRows(object):
+    @staticmethod
+    def gather(t: torch.Tensor) -> torch.Tensor:
+        if not _CTX.active:
+            return t
+        out = torch.empty(_CTX.world * t.shape[0], *t.shape[1:], device=t.device, dtype=t.dtype)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=_CTX.group)
+        return out
+
+
+class SymmetricInfoNCE(torch.autograd.Function):
+    """L = 1/(2B) sum_i [lse_j S_ij - S_ii] + [lse_j S_ji - S_ii],  S = norm(e) norm(f)^T / tau, over the
+    GLOBAL batch: each rank holds B/G rows of e and f, all-gathers the normalised embeddings and the
+    two logsumexp vectors, and produces the exact gradient of the global loss for its own rows -- no
+    reduce-scatter in the backward.  S is never materialised in the forward; the
+    backward materialises the (B/G x B) softmax-gradient blocks that feed the two dgrad GEMMs.
+    Returns this rank's share of the loss (sum over ranks = global loss)."""
+
+    @staticmethod
+    def forward(ctx, e, f, temperature):
+        inv_tau = 1.0 / float(temperature)
+        en, einv = ops.l2norm_fwd(e)
+        fn, finv = ops.l2norm_fwd(f)
+        e_all = _AllGatherRows.gather(en)
+        f_all = _AllGatherRows.gather(fn)
+        Bl, Bg = en.shape[0], e_all.shape[0]
+        off = _CTX.rank * Bl if _CTX.active else 0
+        lse_ef, diag = ops.infonce_lse(en, f_all, inv_tau, off)
+        lse_fe, _ = ops.infonce_lse(fn, e_all, inv_tau, off)
+        loss = (0.5 / Bg) * ((lse_ef - diag).sum() + (lse_fe - diag).sum())
+        ctx.save_for_backward(en, fn, einv, finv, e_all, f_all, lse_ef, lse_fe)
+        ctx.meta = (inv_tau, off, Bg)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        en, fn, einv, finv, e_all, f_all, lse_ef, lse_fe = ctx.saved_tensors
+        inv_tau, off, Bg = ctx.meta
+        lse_ef_all = _AllGatherRows.gather(lse_ef)
+        lse_fe_all = _AllGatherRows.gather(lse_fe)
+        coef = 0.5 * inv_tau / Bg
+        G1 = ops.infonce_grad(en, f_all, lse_ef, lse_fe_all, inv_tau, off, coef)  # rows: my e, cols: all f
+        den = ops.linear_dgrad(G1, f_all)
+        G2 = ops.infonce_grad(fn, e_all, lse_fe, lse_ef_all, inv_tau, off, coef)  # rows: my f, cols: all e
+        dfn = ops.linear_dgrad(G2, e_all)
+        de = ops.l2norm_bwd(den, en, einv) * g
+        df = ops.l2norm_bwd(dfn, fn, finv) * g
+        return de, df, None
+
+
+def symmetric_infonce(e, f, temperature=0.07):
+    return SymmetricInfoNCE.apply(e.contiguous(), f.contiguous(), temperature)
+
+
+def similarity_matrix(e, f, temperature=0.07):
+    """Materialised S = normalize(e) @ normalize(f)^T / temperature (no gradient; inspection / retrieval)."""
+    en, _ = ops.l2norm_fwd(e.detach().contiguous())
+    fn, _ = ops.l2norm_fwd(f.detach().contiguous())
+    return ops.similarity(en, fn, 1.0 / float(temperature))

@@ -1,0 +1,430 @@
+"""Drop-in modules for the reference's classes on the paired-step hot path.
+
+Same class names, constructor / forward signatures and `state_dict` keys as the reference
+(SURVEY.md section 8b), so reference checkpoints load with strict=True.  torch.nn layer objects are used
+ONLY as parameter containers (identical initialisation and key names); their forwards are never
+called on the conv / projection / loss path -- that runs through multimodal_eeg_fmri_b200.functional
+(hand-written sm_100a kernels).  The transformer tail of the v4 encoders stays on PyTorch ops in this
+round.  CUDA tensors only: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as XF
+
+
+class Slots(nn.Module):
+    """Numbered parameter slots: reproduces nn.Sequential's `<name>.<index>.<param>` state_dict keys
+    for the layers that own parameters, without being a callable pipeline."""
+
+    def __init__(self, items: Dict[int, nn.Module]):
+        super().__init__()
+        for i, m in items.items():
+            self.add_module(str(i), m)
+
+    def __getitem__(self, i: int) -> nn.Module:
+        return self._modules[str(i)]
+
+    def forward(self, *a, **k):  # pragma: no cover - containers are not callable
+        raise RuntimeError("Slots is a parameter container; the owning module implements forward")
+
+
+# ------------------------------------------------------------------------- transformer tail (PyTorch)
+class PositionalEncoding(nn.Module):
+    """EEG_CODE/enhanced_models_v4.py:30-55 -- sinusoidal table `pe` (max_len, 1, d) + dropout."""
+
+    def __init__(self, d_model: int, max_len: int = 5000, dropout: float = 0.1):
+        super().__init__()
+        self.p = dropout
+        pos = torch.arange(max_len, dtype=torch.float32).unsqueeze(1)
+        freq = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * (-math.log(10000.0) / d_model))
+        table = torch.zeros(max_len, 1, d_model)
+        table[:, 0, 0::2] = torch.sin(pos * freq)
+        table[:, 0, 1::2] = torch.cos(pos * freq)
+        self.register_buffer("pe", table)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() == 3 and x.size(1) != 1:  # batch-first (B, L, d)
+            x = x + self.pe[: x.size(1), 0, :].unsqueeze(0)
+        else:
+            x = x + self.pe[: x.size(0)]
+        return F.dropout(x, self.p, self.training)
+
+
+class TemporalTransformerBlock(nn.Module):
+    """EEG_CODE/enhanced_models_v4.py:58-107 -- pre-norm MHA + GELU FFN residual block.  Attention
+    runs through scaled_dot_product_attention (the reference's need_weights=True path materialises
+    (B, L, L) weights it then discards)."""
+
+    def __init__(self, d_model: int, nhead: int = 4, dim_feedforward: int = 512, dropout: float = 0.1,
+                 activation: str = "gelu"):
+        super().__init__()
+        self.nhead, self.p, self.act = nhead, dropout, activation
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=True)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, L, d = x.shape
+        h = F.layer_norm(x, (d,), self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        qkv = F.linear(h, self.self_attn.in_proj_weight, self.self_attn.in_proj_bias)
+        q, k, v = (t.view(B, L, self.nhead, d // self.nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+        a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.p if self.training else 0.0)
+        a = a.transpose(1, 2).reshape(B, L, d)
+        a = F.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
+        x = x + F.dropout(a, self.p, self.training)
+        h = F.layer_norm(x, (d,), self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        h = F.linear(h, self.linear1.weight, self.linear1.bias)
+        h = F.gelu(h) if self.act == "gelu" else F.relu(h)
+        h = F.linear(F.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
+        return x + F.dropout(h, self.p, self.training)
+
+
+class _TransformerTail(nn.Module):
+    """pos_encoder / transformer_layers / output_proj members shared by the two v4 encoders."""
+
+    def _init_tail(self, hidden_dim, num_layers, num_heads, dropout):
+        self.pos_encoder = PositionalEncoding(hidden_dim, dropout=dropout)
+        self.transformer_layers = nn.ModuleList(
+            [TemporalTransformerBlock(hidden_dim, num_heads, hidden_dim * 4, dropout) for _ in range(num_layers)])
+        self.output_proj = Slots({2: nn.Linear(hidden_dim, hidden_dim)})
+
+    def _tail(self, h: torch.Tensor) -> torch.Tensor:
+        # h: (B, L, D) channels-last conv output == the transformer's batch-first sequence layout
+        h = self.pos_encoder(h)
+        for blk in self.transformer_layers:
+            h = blk(h)
+        h = XF.seq_mean(h)  # AdaptiveAvgPool1d(1) + Flatten
+        h = XF.linear(h, self.output_proj[2])
+        return XF.act_dropout(h, "gelu", self.dropout_p, self.training)
+
+
+# ------------------------------------------------------------------------- EEG encoders
+class EnhancedERPEncoder(_TransformerTail):
+    """EEG_CODE/enhanced_models_v4.py:114-193 == EEG_CODE/crossmodal_v4_enhancements.py:93-143."""
+
+    def __init__(self, in_channels: int, hidden_dim: int = 128, num_transformer_layers: int = 2, num_heads: int = 4,
+                 dropout: float = 0.3):
+        super().__init__()
+        self.dropout_p = dropout
+        self.conv_layers = Slots({
+            0: nn.Conv1d(in_channels, 64, kernel_size=7, padding=3), 1: nn.BatchNorm1d(64),
+            4: nn.Conv1d(64, 128, kernel_size=5, padding=2), 5: nn.BatchNorm1d(128),
+            9: nn.Conv1d(128, hidden_dim, kernel_size=3, padding=1), 10: nn.BatchNorm1d(hidden_dim),
+        })
+        self._init_tail(hidden_dim, num_transformer_layers, num_heads, dropout)
+
+    def conv_stack(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
+        """(B, C, T) [or (B, T, C) with channels_last=True, e.g. straight from the window gather] ->
+        channels-last (B, T/2, hidden) output of the `conv_layers` Sequential."""
+        c, p, tr = self.conv_layers, self.dropout_p, self.training
+        h = x if channels_last else XF.to_channels_last(x)
+        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 0, p, False, tr)
+        h = XF.conv_bn_act(h, c[4], c[5], "gelu", 2, p, False, tr)           # GELU -> MaxPool -> Dropout
+        return XF.conv_bn_act(h, c[9], c[10], "gelu", 0, p, False, tr, round_out=False)
+
+    def forward(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
+        return self._tail(self.conv_stack(x, channels_last))
+
+
+class EnhancedPowerEncoder(_TransformerTail):
+    """EEG_CODE/enhanced_models_v4.py:196-285 == EEG_CODE/crossmodal_v4_enhancements.py:146-213."""
+
+    def __init__(self, in_channels: int, hidden_dim: int = 128, num_transformer_layers: int = 2, num_heads: int = 4,
+                 dropout: float = 0.3):
+        super().__init__()
+        self.dropout_p = dropout
+        self.conv_scale1 = Slots({0: nn.Conv1d(in_channels, 64, kernel_size=3, padding=1), 1: nn.BatchNorm1d(64)})
+        self.conv_scale2 = Slots({0: nn.Conv1d(in_channels, 64, kernel_size=5, padding=2), 1: nn.BatchNorm1d(64)})
+        self.conv_scale3 = Slots({0: nn.Conv1d(in_channels, 64, kernel_size=7, padding=3), 1: nn.BatchNorm1d(64)})
+        self.fusion = Slots({0: nn.Conv1d(192, hidden_dim, kernel_size=1), 1: nn.BatchNorm1d(hidden_dim)})
+        self._init_tail(hidden_dim, num_transformer_layers, num_heads, dropout)
+
+    def conv_stack(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
+        tr = self.training
+        h = x if channels_last else XF.to_channels_last(x)
+        s = [XF.conv_bn_act(h, m[0], m[1], "gelu", 0, 0.0, False, tr) for m in (self.conv_scale1, self.conv_scale2, self.conv_scale3)]
+        h = torch.cat(s, dim=2)  # channel concat in the channels-last layout
+        return XF.conv_bn_act(h, self.fusion[0], self.fusion[1], "gelu", 0, self.dropout_p, False, tr, round_out=False)
+
+    def forward(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
+        return self._tail(self.conv_stack(x, channels_last))
+
+
+class _LiteEncoder(nn.Module):
+    """crossmodal_v4_enhancements.py:817-877 -- Conv-BN-GELU-Drop-MaxPool2, Conv-BN-GELU-Drop-AvgPool(1),
+    Flatten-Linear-GELU-Drop."""
+
+    def __init__(self, in_channels, mid, k1, k2, hidden_dim, dropout):
+        super().__init__()
+        self.dropout_p = dropout
+        self.conv_layers = Slots({
+            0: nn.Conv1d(in_channels, mid, kernel_size=k1, padding=k1 // 2), 1: nn.BatchNorm1d(mid),
+            5: nn.Conv1d(mid, hidden_dim, kernel_size=k2, padding=k2 // 2), 6: nn.BatchNorm1d(hidden_dim),
+        })
+        self.output = Slots({1: nn.Linear(hidden_dim, hidden_dim)})
+
+    def forward(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
+        c, p, tr = self.conv_layers, self.dropout_p, self.training
+        h = x if channels_last else XF.to_channels_last(x)
+        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 2, p, True, tr)            # Dropout BEFORE MaxPool here
+        h = XF.conv_bn_act(h, c[5], c[6], "gelu", 0, p, False, tr, round_out=False)
+        h = XF.seq_mean(h)
+        return XF.act_dropout(XF.linear(h, self.output[1]), "gelu", p, tr)
+
+
+class LiteERPEncoder(_LiteEncoder):
+    def __init__(self, in_channels: int, hidden_dim: int = 96, dropout: float = 0.4):
+        super().__init__(in_channels, 48, 7, 5, hidden_dim, dropout)
+
+
+class LitePowerEncoder(_LiteEncoder):
+    def __init__(self, in_channels: int, hidden_dim: int = 96, dropout: float = 0.4):
+        super().__init__(in_channels, 64, 5, 3, hidden_dim, dropout)
+
+
+class EnhancedConnEncoder(nn.Module):
+    """crossmodal_v4_enhancements.py:684-739."""
+
+    def __init__(self, conn_features: int, hidden_dim: int = 96, dropout: float = 0.4):
+        super().__init__()
+        self.dropout_p = dropout
+        self.proj1 = Slots({0: nn.Linear(conn_features, 256), 1: nn.BatchNorm1d(256)})
+        self.proj2 = Slots({0: nn.Linear(256, 128), 1: nn.BatchNorm1d(128)})
+        self.attention = Slots({0: nn.Linear(128, 64), 2: nn.Linear(64, 128)})
+        self.output = Slots({0: nn.Linear(128, hidden_dim), 1: nn.BatchNorm1d(hidden_dim)})
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        p, tr = self.dropout_p, self.training
+        if x.dim() > 2:
+            x = x.reshape(x.size(0), -1)
+        x = XF.linear_bn_act(x, self.proj1[0], self.proj1[1], "gelu", p, tr)
+        x = XF.linear_bn_act(x, self.proj2[0], self.proj2[1], "gelu", p, tr)
+        a = XF.act_dropout(XF.linear(x, self.attention[0]), "tanh", 0.0, tr)
+        a = XF.act_dropout(XF.linear(a, self.attention[2]), "sigmoid", 0.0, tr)
+        return XF.linear_bn_act(x * a, self.output[0], self.output[1], "gelu", p, tr)
+
+
+class HybridFusionModule(nn.Module):
+    """crossmodal_v4_enhancements.py:746-810 -- early ERP/PW gate, late fusion with boosted CONN."""
+
+    def __init__(self, hidden_dim: int, dropout: float = 0.3, conn_boost: float = 1.2):
+        super().__init__()
+        self.conn_boost, self.dropout_p = conn_boost, dropout
+        self.erp_pw_gate = Slots({0: nn.Linear(hidden_dim * 2, hidden_dim), 3: nn.Linear(hidden_dim, 2)})
+        self.late_fusion = Slots({0: nn.Linear(hidden_dim * 2, hidden_dim), 1: nn.BatchNorm1d(hidden_dim)})
+        self.final_gate = nn.Parameter(torch.tensor([0.6, 0.4]))
+
+    def forward(self, erp_feat, pw_feat, conn_feat, return_weights: bool = False):
+        p, tr = self.dropout_p, self.training
+        g = XF.act_dropout(XF.linear(torch.cat([erp_feat, pw_feat], dim=1), self.erp_pw_gate[0]), "gelu", p, tr)
+        g = torch.softmax(XF.linear(g, self.erp_pw_gate[3]), dim=-1)
+        early = g[:, 0:1] * erp_feat + g[:, 1:2] * pw_feat
+        comb = torch.cat([early, conn_feat * self.conn_boost], dim=1)
+        fused = XF.linear_bn_act(comb, self.late_fusion[0], self.late_fusion[1], "gelu", p, tr)
+        if return_weights:
+            fw = torch.softmax(self.final_gate, dim=0)
+            # one device->host transfer instead of the reference's five .item() syncs (:803-806)
+            v = torch.stack([g[:, 0].mean() * fw[0], g[:, 1].mean() * fw[0], fw[1] * self.conn_boost]).tolist()
+            return fused, {"erp_weight": v[0], "pw_weight": v[1], "conn_weight": v[2]}
+        return fused
+
+
+class EnhancedTriModalFusionNetV4Lite(nn.Module):
+    """crossmodal_v4_enhancements.py:880-948."""
+
+    def __init__(self, erp_channels: int, pw_channels: int, conn_features: int, hidden_dim: int = 96,
+                 num_classes: int = 2, dropout: float = 0.4, conn_boost: float = 1.3):
+        super().__init__()
+        self.hidden_dim, self.dropout_p = hidden_dim, dropout
+        self.erp_encoder = LiteERPEncoder(erp_channels, hidden_dim, dropout)
+        self.pw_encoder = LitePowerEncoder(pw_channels, hidden_dim, dropout)
+        self.conn_encoder = EnhancedConnEncoder(conn_features, hidden_dim, dropout)
+        self.fusion = HybridFusionModule(hidden_dim, dropout, conn_boost)
+        self.classifier = Slots({0: nn.Linear(hidden_dim, hidden_dim // 2), 1: nn.BatchNorm1d(hidden_dim // 2),
+                                 4: nn.Linear(hidden_dim // 2, num_classes)})
+        self._fusion_weights = None
+
+    def forward(self, erp, pw, conn, return_fusion_weights: bool = False, return_fused_feats: bool = False):
+        e, p, c = self.erp_encoder(erp), self.pw_encoder(pw), self.conn_encoder(conn)
+        if return_fusion_weights:
+            fused, weights = self.fusion(e, p, c, return_weights=True)
+            self._fusion_weights = weights
+        else:
+            fused, weights = self.fusion(e, p, c), None
+        h = XF.linear_bn_act(fused, self.classifier[0], self.classifier[1], "gelu", self.dropout_p, self.training)
+        logits = XF.linear(h, self.classifier[4])
+        if return_fusion_weights and return_fused_feats:
+            return logits, weights, fused
+        if return_fusion_weights:
+            return logits, weights
+        if return_fused_feats:
+            return logits, fused
+        return logits
+
+    def get_fusion_weights(self):
+        return self._fusion_weights
+
+
+class LabelSmoothingCrossEntropy(nn.Module):
+    """crossmodal_v4_enhancements.py:665-677 (B x num_classes logits: tiny, torch ops)."""
+
+    def __init__(self, smoothing: float = 0.1):
+        super().__init__()
+        self.smoothing, self.confidence = smoothing, 1.0 - smoothing
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        logp = F.log_softmax(pred, dim=-1)
+        nll = -logp.gather(-1, target.unsqueeze(1)).squeeze(1)
+        return (self.confidence * nll + self.smoothing * (-logp.mean(-1))).mean()
+
+
+# ------------------------------------------------------------------------- fusion with temperature
+class LearnedFusionModule(nn.Module):
+    """crossmodal_v4_enhancements.py:216-271 (== enhanced_models_v4.py:420-...): static softmax(logits/T)
+    mixed 50/50 with a gate-net softmax; gate_net keeps its hard-coded Dropout(0.2) (:236)."""
+
+    def __init__(self, num_modalities: int, hidden_dim: int, use_temperature: bool = True, init_temperature: float = 1.0):
+        super().__init__()
+        self.num_modalities, self.use_temperature = num_modalities, use_temperature
+        self.fusion_logits = nn.Parameter(torch.ones(num_modalities))
+        if use_temperature:
+            self.temperature = nn.Parameter(torch.tensor(init_temperature))
+        else:
+            self.register_buffer("temperature", torch.tensor(1.0))
+        self.gate_net = Slots({0: nn.Linear(hidden_dim * num_modalities, hidden_dim), 3: nn.Linear(hidden_dim, num_modalities)})
+
+    def forward(self, modality_features: List[torch.Tensor], return_weights: bool = False):
+        static = torch.softmax(self.fusion_logits / self.temperature, dim=0)
+        h = XF.act_dropout(XF.linear(torch.cat(modality_features, dim=1), self.gate_net[0]), "gelu", 0.2, self.training)
+        dyn = torch.softmax(XF.linear(h, self.gate_net[3]) / self.temperature, dim=1)
+        w = 0.5 * static.unsqueeze(0) + 0.5 * dyn
+        fused = (torch.stack(modality_features, dim=1) * w.unsqueeze(2)).sum(dim=1)
+        return (fused, w) if return_weights else fused
+
+
+# ------------------------------------------------------------------------- fMRI
+class _FmriEncoder(nn.Module):
+    """fMRI_CODE/fmri_utils.py:23-56 -- (Linear-BN-ReLU-Dropout) x 2."""
+
+    def __init__(self, in_dim: int, hidden_dim: int = 64, dropout: float = 0.3):
+        super().__init__()
+        self.dropout_p = dropout
+        self.encoder = Slots({0: nn.Linear(in_dim, hidden_dim * 2), 1: nn.BatchNorm1d(hidden_dim * 2),
+                              4: nn.Linear(hidden_dim * 2, hidden_dim), 5: nn.BatchNorm1d(hidden_dim)})
+
+    def forward(self, x):
+        e, p, tr = self.encoder, self.dropout_p, self.training
+        return XF.linear_bn_act(XF.linear_bn_act(x, e[0], e[1], "relu", p, tr), e[4], e[5], "relu", p, tr)
+
+
+class ActivationEncoder(_FmriEncoder):
+    pass
+
+
+class ConnectivityEncoder(_FmriEncoder):
+    pass
+
+
+class fMRIFusionNet(nn.Module):  # noqa: N801 - reference spelling
+    """fMRI_CODE/fmri_utils.py:59-108."""
+
+    def __init__(self, activation_dim: int, connectivity_dim: int, hidden_dim: int = 64, num_classes: int = 2,
+                 dropout: float = 0.4, task: str = "classification"):
+        super().__init__()
+        self.task, self.dropout_p = task, dropout
+        self.activation_encoder = ActivationEncoder(activation_dim, hidden_dim, dropout)
+        self.connectivity_encoder = ConnectivityEncoder(connectivity_dim, hidden_dim, dropout)
+        self.fusion = Slots({0: nn.Linear(hidden_dim * 2, hidden_dim), 1: nn.BatchNorm1d(hidden_dim)})
+        self.activation_weight = nn.Parameter(torch.ones(1) * 0.5)
+        self.connectivity_weight = nn.Parameter(torch.ones(1) * 0.5)
+        out_dim = num_classes if task == "classification" else 1
+        self.head = Slots({0: nn.Linear(hidden_dim, hidden_dim // 2), 3: nn.Linear(hidden_dim // 2, out_dim)})
+
+    def features(self, activation, connectivity):
+        """The fused (B, hidden) feature of forward(..., return_features=True) without the head."""
+        a = self.activation_encoder(activation)
+        c = self.connectivity_encoder(connectivity)
+        w = torch.softmax(torch.stack([self.activation_weight, self.connectivity_weight]), dim=0)
+        return XF.linear_bn_act(torch.cat([a * w[0], c * w[1]], dim=1), self.fusion[0], self.fusion[1], "relu",
+                                self.dropout_p, self.training)
+
+    def forward(self, activation, connectivity, return_features: bool = False):
+        p, tr = self.dropout_p, self.training
+        fused = self.features(activation, connectivity)
+        out = XF.linear(XF.act_dropout(XF.linear(fused, self.head[0]), "relu", p, tr), self.head[3])
+        if self.task == "regression":
+            out = out.squeeze(-1)
+        return (out, fused) if return_features else out
+
+    def get_fusion_weights(self):
+        with torch.no_grad():
+            w = torch.softmax(torch.stack([self.activation_weight, self.connectivity_weight]), dim=0).flatten().tolist()
+        return {"activation": w[0], "connectivity": w[1]}
+
+
+# ------------------------------------------------------------------------- bridge
+class EEGfMRIBridgeFusionNet(nn.Module):
+    """bridge_utils.py:22-114.  `project()` exposes the two shared-space embeddings the InfoNCE loss uses."""
+
+    def __init__(self, eeg_dim=128, fmri_dim=64, bridge_dim=128, num_classes=2, num_heads=4, dropout=0.3):
+        super().__init__()
+        self.bridge_dim, self.num_heads, self.dropout_p = bridge_dim, num_heads, dropout
+        self.eeg_proj = Slots({0: nn.Linear(eeg_dim, bridge_dim), 1: nn.LayerNorm(bridge_dim)})
+        self.fmri_proj = Slots({0: nn.Linear(fmri_dim, bridge_dim), 1: nn.LayerNorm(bridge_dim)})
+        self.cross_attn = nn.MultiheadAttention(bridge_dim, num_heads=num_heads, dropout=dropout, batch_first=True)
+        self.fusion = LearnedFusionModule(num_modalities=2, hidden_dim=bridge_dim, use_temperature=True)
+        self.classifier = Slots({0: nn.Linear(bridge_dim, bridge_dim // 2), 1: nn.LayerNorm(bridge_dim // 2),
+                                 4: nn.Linear(bridge_dim // 2, num_classes)})
+
+    def project(self, eeg_feats, fmri_feats):
+        p, tr = self.dropout_p, self.training
+        e = XF.linear_ln_act(eeg_feats, self.eeg_proj[0], self.eeg_proj[1], "gelu", p, tr)
+        f = XF.linear_ln_act(fmri_feats, self.fmri_proj[0], self.fmri_proj[1], "gelu", p, tr)
+        return e, f
+
+    def _cross_attention(self, e, f):
+        """One EEG query over the two-token sequence [eeg, fmri] (bridge_utils.py:74-83)."""
+        B, d = e.shape
+        H, dh = self.num_heads, d // self.num_heads
+        W, b = self.cross_attn.in_proj_weight, self.cross_attn.in_proj_bias
+        q = XF.Linear.apply(e, W[:d], b[:d]).view(B, H, dh)
+        kv = XF.Linear.apply(torch.cat([e, f], dim=0), W[d:], b[d:])  # keys and values of both tokens
+        k = kv[:, :d].reshape(2, B, H, dh)
+        v = kv[:, d:].reshape(2, B, H, dh)
+        att = torch.softmax((q.unsqueeze(0) * k).sum(-1) / math.sqrt(dh), dim=0)  # (2, B, H)
+        att_d = F.dropout(att, self.dropout_p, self.training)
+        o = (att_d.unsqueeze(-1) * v).sum(0).reshape(B, d)
+        o = XF.linear(o, self.cross_attn.out_proj)
+        return o, att_d.mean(-1).t().unsqueeze(1)  # weights averaged over heads: (B, 1, 2)
+
+    def forward(self, eeg_feats, fmri_feats, return_features=False, return_weights=False):
+        e, f = self.project(eeg_feats, fmri_feats)
+        enhanced, attn_w = self._cross_attention(e, f)
+        if return_weights:
+            fused, fusion_w = self.fusion([enhanced, f], return_weights=True)
+        else:
+            fused, fusion_w = self.fusion([enhanced, f]), None
+        h = XF.linear_ln_act(fused, self.classifier[0], self.classifier[1], "relu", self.dropout_p, self.training)
+        logits = XF.linear(h, self.classifier[4])
+        results = [logits]
+        if return_features:
+            results.append(fused)
+        if return_weights:
+            results += [fusion_w, attn_w]
+        return results[0] if len(results) == 1 else tuple(results)
+
+    def get_fusion_weights(self):
+        with torch.no_grad():
+            t = self.fusion.temperature
+            w = torch.softmax(self.fusion.fusion_logits / t, dim=0)
+            v = torch.cat([w, t.reshape(1)]).tolist()
+        return {"eeg_weight": v[0], "fmri_weight": v[1], "temperature": v[2]}

@@ -13,8 +13,8 @@ import torch
 
 from . import _lib
 
-ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-_ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU}
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "tanh": ACT_TANH, "sigmoid": ACT_SIGMOID}
 
 _launches = 0  # C-ABI calls made (bench.py reports it as gpu_launches lower bound)
 
@@ -319,6 +319,23 @@ def ln_act_bwd(dout, x, gamma, beta, mean, rstd, act, drop_p=0.0, seed=0):
     _call("xm_ln_act_bwd_f32", _p(dout), _p(x), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(dx), _p(dgp), _p(dbp), M,
           D, act_code(act), float(drop_p), int(seed), _stream())
     return dx, colsum(dgp), colsum(dbp)
+
+
+# ------------------------------------------------------------------ activation + dropout
+def act_fwd(x, act, drop_p=0.0, seed=0):
+    _chk(x)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _call("xm_act_fwd_f32", _p(x), _p(out), x.numel(), act_code(act), float(drop_p), int(seed), _stream())
+    return out
+
+
+def act_bwd(dout, x, act, drop_p=0.0, seed=0):
+    _chk(dout, x)
+    dout, x = dout.contiguous(), x.contiguous()
+    dx = torch.empty_like(x)
+    _call("xm_act_bwd_f32", _p(dout), _p(x), _p(dx), x.numel(), act_code(act), float(drop_p), int(seed), _stream())
+    return dx
 
 
 # ------------------------------------------------------------------ reductions

@@ -1,0 +1,149 @@
+"""The paired EEG/fMRI cross-modal training step and its data-parallel driver.
+
+    raw EEG recordings (R, C, n) --window gather--> (B, T, C) --EnhancedERPEncoder--> (B, 128) --eeg_proj--+
+    ROI series (B, TR, ROI) --mean/std--> (B, 2*ROI) --+                                                   |--> symmetric
+    connectivity (B, ROI*ROI) -------------------------+--> fMRIFusionNet features (B, 64) --fmri_proj----+    InfoNCE
+
+followed by the reference's step recipe (zero_grad -> backward -> clip_grad_norm_(1.0) -> AdamW,
+_test_bridge.py:775-788, lr / weight decay of :63-64,869).
+
+Data parallel: one process per GPU, batch sharded; the InfoNCE function all-gathers the normalised
+embeddings (global negatives) and returns exact local gradients of the global loss; BatchNorm
+partial sums are all-reduced (SyncBN) so a sharded run equals the single-process global-batch run;
+parameter gradients live in ONE flat bucket that is all-reduced (SUM) once per step.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import fmri_utils, ops
+from . import functional as XF
+from .modules import EEGfMRIBridgeFusionNet, EnhancedERPEncoder, LiteERPEncoder, fMRIFusionNet
+
+
+class PairedBridgeModel(nn.Module):
+    """EEG encoder + fMRI net + bridge projections trained with the symmetric InfoNCE loss."""
+
+    def __init__(self, eeg_channels: int = 64, n_roi: int = 200, conn_dim: Optional[int] = None, eeg_hidden: int = 128,
+                 fmri_hidden: int = 64, bridge_dim: int = 128, dropout: float = 0.3, fmri_dropout: float = 0.4,
+                 encoder: str = "v4", temperature: float = 0.07):
+        super().__init__()
+        conn_dim = n_roi * n_roi if conn_dim is None else conn_dim
+        if encoder == "v4":
+            self.eeg_encoder = EnhancedERPEncoder(eeg_channels, eeg_hidden, 2, 4, dropout)
+        elif encoder == "lite":
+            self.eeg_encoder = LiteERPEncoder(eeg_channels, eeg_hidden, dropout)
+        else:
+            raise ValueError(f"unknown encoder {encoder!r}")
+        self.fmri_net = fMRIFusionNet(2 * n_roi, conn_dim, fmri_hidden, 2, fmri_dropout)
+        self.bridge = EEGfMRIBridgeFusionNet(eeg_hidden, fmri_hidden, bridge_dim, 2, 4, dropout)
+        self.temperature = temperature
+
+    def contrastive_parameters(self) -> List[nn.Parameter]:
+        """Parameters the InfoNCE step reaches (the supervised heads get no gradient, exactly as
+        parameters with grad=None are skipped by the reference's optimizer)."""
+        mods: Iterable[nn.Module] = (self.eeg_encoder, self.fmri_net.activation_encoder,
+                                     self.fmri_net.connectivity_encoder, self.fmri_net.fusion,
+                                     self.bridge.eeg_proj, self.bridge.fmri_proj)
+        ps = [p for m in mods for p in m.parameters()]
+        return ps + [self.fmri_net.activation_weight, self.fmri_net.connectivity_weight]
+
+    def embed(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: torch.Tensor, eeg_channels_last: bool = False):
+        eeg_feat = self.eeg_encoder(eeg, channels_last=eeg_channels_last)
+        act = fmri_utils.aggregate_roi_timeseries(roi_series, "both")
+        fmri_feat = self.fmri_net.features(act, conn)
+        return self.bridge.project(eeg_feat, fmri_feat)
+
+    def forward(self, eeg, roi_series, conn, eeg_channels_last: bool = False) -> torch.Tensor:
+        e, f = self.embed(eeg, roi_series, conn, eeg_channels_last)
+        return XF.symmetric_infonce(e, f, self.temperature)
+
+
+def init_distributed(backend: str = "nccl") -> XF.ParallelContext:
+    """One process per GPU (torchrun env).  Returns the active context (a no-op context when WORLD_SIZE=1)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend)
+    ctx = XF.ParallelContext(group=None, sync_bn=True)
+    XF.set_parallel_context(ctx)
+    return ctx
+
+
+class PairedTrainer:
+    """zero_grad -> forward -> backward -> [all-reduce] -> clip_grad_norm_ -> AdamW, on one flat gradient bucket."""
+
+    def __init__(self, model: PairedBridgeModel, lr: float = 1e-4, weight_decay: float = 1e-4, grad_clip: float = 1.0,
+                 window: Optional[int] = None, hop: Optional[int] = None):
+        self.model = model
+        self.grad_clip = grad_clip
+        self.window, self.hop = window, hop
+        self.params = model.contrastive_parameters()
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        o = 0
+        for p in self.params:  # gradients are views into one bucket: one collective, one norm
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=dev.type == "cuda")
+        self.ctx = XF.parallel_context()
+        self._stage = {}
+
+    # -- device-resident step ---------------------------------------------------------------
+    def step(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: torch.Tensor) -> torch.Tensor:
+        """eeg: raw recordings (R, C, n) when a window spec was given (gathered on the device into
+        B = R*n_win channels-last windows), else windows (B, C, T).  Returns the loss (device scalar,
+        this rank's share of the global loss)."""
+        self.flat_grad.zero_()
+        if self.window is not None:
+            x = ops.window_gather(eeg, self.window, self.hop or self.window, channels_last=True,
+                                                 round_out=True)
+            loss = self.model(x, roi_series, conn, eeg_channels_last=True)
+        else:
+            loss = self.model(eeg, roi_series, conn)
+        loss.backward()
+        if self.ctx.active:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.ctx.group)
+        if self.grad_clip and self.grad_clip > 0:
+            total = torch.linalg.vector_norm(self.flat_grad)
+            self.flat_grad.mul_(torch.clamp(self.grad_clip / (total + 1e-6), max=1.0))
+        self.opt.step()
+        return loss.detach()
+
+    # -- end-to-end step from pinned host buffers --------------------------------------------
+    def step_from_host(self, eeg_h: torch.Tensor, roi_h: torch.Tensor, conn_h: torch.Tensor) -> float:
+        """Host -> device copies of this step's inputs, the step, and the loss read back."""
+        dev = self.flat_grad.device
+        bufs = []
+        for name, h in (("eeg", eeg_h), ("roi", roi_h), ("conn", conn_h)):
+            d = self._stage.get(name)
+            if d is None or d.shape != h.shape:
+                d = torch.empty(h.shape, device=dev, dtype=h.dtype)
+                self._stage[name] = d
+            d.copy_(h, non_blocking=True)
+            bufs.append(d)
+        return float(self.step(*bufs).item())
+
+
+def train_bridge_epoch(model, loader, optimizer, criterion, device, grad_clip: float = 1.0) -> float:
+    """_test_bridge.py:775-788 -- supervised bridge epoch (CE on logits), same recipe and return value."""
+    model.train()
+    total = 0.0
+    for eeg, fmri, labels, _ in loader:
+        eeg, fmri, labels = eeg.to(device), fmri.to(device), labels.to(device)
+        optimizer.zero_grad()
+        loss = criterion(model(eeg, fmri), labels)
+        loss.backward()
+        if grad_clip > 0:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), grad_clip)
+        optimizer.step()
+        total += loss.item()
+    return total / max(len(loader), 1)
