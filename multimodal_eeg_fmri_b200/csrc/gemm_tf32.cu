@@ -33,6 +33,14 @@ static EncodeTiledFn get_encode_fn() {
 int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return XM_ERR_NO_DRIVER;
+  // The driver entry point needs a current context on THIS thread.  The runtime binds the primary
+  // context lazily, and a fresh thread (e.g. PyTorch's autograd worker, whose first op may be one of
+  // ours) has none yet: a no-op runtime call binds it (CUDA_ERROR_INVALID_CONTEXT otherwise).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    (void)cudaFree(nullptr);
+    ctx_bound = true;
+  }
   if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) return XM_ERR_INVALID;
   if ((t.stride_bytes[0] & 15) != 0 || (t.stride_bytes[1] & 15) != 0) return XM_ERR_INVALID;
   cuuint64_t dims[3] = {t.dim[0], t.dim[1], t.dim[2]};

@@ -74,17 +74,18 @@ class TemporalTransformerBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, L, d = x.shape
+        lin = XF.Linear.apply  # the four projections run on the tcgen05 TF32 GEMM over (B*L, d) rows
         h = F.layer_norm(x, (d,), self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        qkv = F.linear(h, self.self_attn.in_proj_weight, self.self_attn.in_proj_bias)
+        qkv = lin(h.reshape(B * L, d), self.self_attn.in_proj_weight, self.self_attn.in_proj_bias).view(B, L, 3 * d)
         q, k, v = (t.view(B, L, self.nhead, d // self.nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
         a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.p if self.training else 0.0)
-        a = a.transpose(1, 2).reshape(B, L, d)
-        a = F.linear(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias)
+        a = a.transpose(1, 2).reshape(B * L, d)
+        a = lin(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias).view(B, L, d)
         x = x + F.dropout(a, self.p, self.training)
         h = F.layer_norm(x, (d,), self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        h = F.linear(h, self.linear1.weight, self.linear1.bias)
-        h = F.gelu(h) if self.act == "gelu" else F.relu(h)
-        h = F.linear(F.dropout(h, self.p, self.training), self.linear2.weight, self.linear2.bias)
+        h = lin(h.reshape(B * L, d), self.linear1.weight, self.linear1.bias)
+        h = XF.act_dropout(h, self.act, self.p, self.training)  # GELU + Dropout in one pass
+        h = lin(h, self.linear2.weight, self.linear2.bias).view(B, L, d)
         return x + F.dropout(h, self.p, self.training)
 
 

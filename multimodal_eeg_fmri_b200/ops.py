@@ -48,10 +48,49 @@ def _chk(*tensors):
 _SYNC_DEBUG = bool(int(__import__("os").environ.get("XM_SYNC_DEBUG", "0")))
 
 
+_timeline = None  # when a list: (entry point, start event, end event) per C-ABI call (bench.py's per-kernel timing)
+
+
+def start_timeline() -> None:
+    global _timeline
+    _timeline = []
+
+
+def stop_timeline():
+    """-> {entry point: (calls, total ms, algorithmic flops, algorithmic bytes)}; times are CUDA events on the
+    launching stream around each C-ABI call."""
+    global _timeline
+    tl, _timeline = _timeline or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b, (fl, by) in tl:
+        n, ms, f0, b0 = out.get(name, (0, 0.0, 0.0, 0.0))
+        out[name] = (n + 1, ms + a.elapsed_time(b), f0 + fl, b0 + by)
+    return out
+
+
+_work = (0.0, 0.0)
+
+
+def _w(flops: float, nbytes: float) -> None:
+    """Algorithmic (flops, bytes) of the NEXT C-ABI call -- minimal operand traffic, every tensor read
+    or written once; only consumed while a timeline is being recorded."""
+    global _work
+    _work = (float(flops), float(nbytes))
+
+
 def _call(name, *args):
-    global _launches
+    global _launches, _work
     _launches += 1
-    _lib.call(name, *args)
+    if _timeline is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.call(name, *args)
+        b.record()
+        _timeline.append((name, a, b, _work))
+    else:
+        _lib.call(name, *args)
+    _work = (0.0, 0.0)
     if _SYNC_DEBUG:  # attribute asynchronous kernel faults to the entry point that caused them
         try:
             torch.cuda.synchronize()
@@ -114,6 +153,7 @@ def linear_fwd(x, w, bias=None, act=None, round_out=False, splits: int = 0):
         tiles = ((M + 127) // 128) * max(1, (N + 255) // 256)
         splits = 1 if tiles >= 74 or K < 2048 else min(8, max(1, 148 // tiles), K // 512)
     ws = torch.empty(splits * M * N, device=x.device, dtype=torch.float32) if splits > 1 else None
+    _w(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
     _call("xm_linear_fwd_f32", _p(x), _p(w), _p(bias), _p(y), M, N, K, x.stride(0), w.stride(0), y.stride(0),
           act_code(act), int(round_out), splits, _p(ws), _stream())
     return y
@@ -125,6 +165,7 @@ def linear_dgrad(dy, w, round_out=False):
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+    _w(2.0 * M * N * K, 4.0 * (M * N + N * K + M * K))
     _call("xm_linear_dgrad_f32", _p(dy), _p(w), _p(dx), M, N, K, dy.stride(0), w.stride(0), dx.stride(0),
           int(round_out), _stream())
     return dx
@@ -139,8 +180,9 @@ def linear_wgrad(dy, x, need_bias=True, splits: int = 0):
     db = torch.empty(N, device=dy.device, dtype=torch.float32) if need_bias else None
     if splits <= 0:
         tiles = ((N + 127) // 128) * max(1, (K + 255) // 256)
-        splits = 1 if tiles >= 74 or M < 1024 else min(16, max(1, 148 // tiles), M // 256)
+        splits = 1 if tiles >= 74 or M < 1024 else min(max(1, 148 // tiles), M // 256)
     ws = torch.empty(splits * N * K, device=dy.device, dtype=torch.float32) if splits > 1 else None
+    _w(2.0 * M * N * K, 4.0 * (M * N + M * K + N * K))
     _call("xm_linear_wgrad_f32", _p(dy), _p(x), _p(dw), _p(db), M, N, K, dy.stride(0), x.stride(0), dw.stride(0),
           splits, _p(ws), _stream())
     return dw, db
@@ -167,6 +209,7 @@ def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
     B, T, Cin = x.shape
     taps, _, ldk = wk.shape
     y = empty_pitched((B, T, Cout), x.device) if out is None else out
+    _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cin + Cout) + taps * Cin * Cout))
     _call("xm_conv1d_fwd_f32", _p(x), _p(wk), _p(bias), _p(y), B, Cin, Cout, T, taps, x.stride(1), ldk, y.stride(1),
           int(round_out), _stream())
     return y
@@ -178,6 +221,7 @@ def conv1d_dgrad(dy, wt, Cin, round_out=False):
     B, T, Cout = dy.shape
     taps, _, ldt = wt.shape
     dx = empty_pitched((B, T, Cin), dy.device)
+    _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cin + Cout) + taps * Cin * Cout))
     _call("xm_conv1d_dgrad_f32", _p(dy), _p(wt), _p(dx), B, Cin, Cout, T, taps, dy.stride(1), ldt, dx.stride(1),
           int(round_out), _stream())
     return dx
@@ -193,6 +237,7 @@ def conv1d_wgrad(dy, x, taps, need_bias=True):
     ws = torch.empty(n_ws, device=dy.device, dtype=torch.float32)
     dw = torch.empty(Cout, Cin, taps, device=dy.device, dtype=torch.float32)
     db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if need_bias else None
+    _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cin + Cout) + taps * Cin * Cout))
     _call("xm_conv1d_wgrad_f32", _p(dy), _p(x), _p(dw), _p(db), B, Cin, Cout, T, taps, dy.stride(1), x.stride(1),
           _p(ws), _stream())
     return dw, db
@@ -215,6 +260,7 @@ def bn_partial_stats(y):
     B, T, C, ld = _bn_dims(y)
     ns = _lib.lib().xm_bn_nsplit(B * T, C)
     part = torch.empty(ns, C, 2, device=y.device, dtype=torch.float64)
+    _w(3.0 * B * T * C, 4.0 * B * T * C)
     _call("xm_bn_partial_stats_f32", _p(y), B * T, C, ld, _p(part), _stream())
     return part
 
@@ -238,6 +284,7 @@ def bn_act_fwd(y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, dr
     else:
         out = empty_pitched((B, T // 2 if pool == 2 else T, C), y.device)
         ldo = out.stride(1)
+    _w(20.0 * B * T * C, 4.0 * (B * T * C + out.numel()))
     _call("xm_bn_act_fwd_f32", _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(out), B, T, C, ld, ldo,
           act_code(act), pool, float(drop_p), int(seed), int(drop_before_pool), int(round_out), _stream())
     return out
@@ -252,6 +299,7 @@ def bn_act_bwd_reduce(dout, y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.
     B, T, C, ld = _bn_dims(y)
     ns = _lib.lib().xm_bn_nsplit(B * T, C)
     part = torch.empty(ns, C, 2, device=y.device, dtype=torch.float64)
+    _w(30.0 * B * T * C, 4.0 * (B * T * C + dout.numel()))
     _call("xm_bn_act_bwd_reduce_f32", _p(dout), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), B, T, C, ld,
           _ldo(dout), act_code(act), pool, float(drop_p), int(seed), int(drop_before_pool), _p(part), _stream())
     return part
@@ -271,6 +319,7 @@ def bn_act_bwd_apply(dout, y, mean, invstd, gamma, beta, dbeta, dgamma, count, a
     dy = torch.empty(B, C, device=y.device, dtype=torch.float32) if y.dim() == 2 else empty_pitched((B, T, C), y.device)
     lddy = dy.stride(0) if y.dim() == 2 else dy.stride(1)
     assert lddy == ld, "dy is written with y's pitch"
+    _w(30.0 * B * T * C, 4.0 * (2 * B * T * C + dout.numel()))
     _call("xm_bn_act_bwd_apply_f32", _p(dout), _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(dbeta),
           _p(dgamma), float(count), _p(dy), B, T, C, ld, _ldo(dout), act_code(act), pool, float(drop_p), int(seed),
           int(drop_before_pool), int(round_out), _stream())
@@ -282,6 +331,7 @@ def seqmean(x):
     _chk(x)
     B, T, C, ld = _bn_dims(x)
     out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    _w(B * T * C, 4.0 * (B * T * C + B * C))
     _call("xm_seqmean_f32", _p(x), B, T, C, ld, _p(out), _stream())
     return out
 
@@ -291,6 +341,7 @@ def seqmean_bwd(dout, T):
     dout = dout.contiguous()
     B, C = dout.shape
     dx = empty_pitched((B, T, C), dout.device)
+    _w(B * T * C, 4.0 * (B * T * C + B * C))
     _call("xm_seqmean_bwd_f32", _p(dout), B, T, C, dx.stride(1), _p(dx), _stream())
     return dx
 
@@ -303,6 +354,7 @@ def ln_act_fwd(x, gamma, beta, eps, act, drop_p=0.0, seed=0):
     out = torch.empty_like(x)
     mean = torch.empty(M, device=x.device, dtype=torch.float32)
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    _w(20.0 * M * D, 8.0 * M * D)
     _call("xm_ln_act_fwd_f32", _p(x), _p(gamma), _p(beta), _p(out), _p(mean), _p(rstd), M, D, float(eps),
           act_code(act), float(drop_p), int(seed), _stream())
     return out, mean, rstd
@@ -316,6 +368,7 @@ def ln_act_bwd(dout, x, gamma, beta, mean, rstd, act, drop_p=0.0, seed=0):
     dx = torch.empty_like(x)
     dgp = torch.empty(nblk, D, device=x.device, dtype=torch.float32)
     dbp = torch.empty(nblk, D, device=x.device, dtype=torch.float32)
+    _w(30.0 * M * D, 12.0 * M * D)
     _call("xm_ln_act_bwd_f32", _p(dout), _p(x), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(dx), _p(dgp), _p(dbp), M,
           D, act_code(act), float(drop_p), int(seed), _stream())
     return dx, colsum(dgp), colsum(dbp)
@@ -326,6 +379,7 @@ def act_fwd(x, act, drop_p=0.0, seed=0):
     _chk(x)
     x = x.contiguous()
     out = torch.empty_like(x)
+    _w(10.0 * x.numel(), 8.0 * x.numel())
     _call("xm_act_fwd_f32", _p(x), _p(out), x.numel(), act_code(act), float(drop_p), int(seed), _stream())
     return out
 
@@ -334,6 +388,7 @@ def act_bwd(dout, x, act, drop_p=0.0, seed=0):
     _chk(dout, x)
     dout, x = dout.contiguous(), x.contiguous()
     dx = torch.empty_like(x)
+    _w(10.0 * x.numel(), 12.0 * x.numel())
     _call("xm_act_bwd_f32", _p(dout), _p(x), _p(dx), x.numel(), act_code(act), float(drop_p), int(seed), _stream())
     return dx
 
@@ -344,6 +399,7 @@ def colsum(x):
     M, N = x.shape
     assert x.stride(1) == 1
     out = torch.empty(N, device=x.device, dtype=torch.float32)
+    _w(M * N, 4.0 * (M * N + N))
     _call("xm_colsum_f32", _p(x), M, N, x.stride(0), _p(out), _stream())
     return out
 
@@ -355,6 +411,7 @@ def l2norm_fwd(x, eps=1e-12):
     M, D = x.shape
     xn = torch.empty_like(x)
     inv = torch.empty(M, device=x.device, dtype=torch.float32)
+    _w(3.0 * M * D, 8.0 * M * D)
     _call("xm_l2norm_fwd_f32", _p(x), _p(xn), _p(inv), M, D, float(eps), _stream())
     return xn, inv
 
@@ -364,6 +421,7 @@ def l2norm_bwd(dxn, xn, inv):
     dxn = dxn.contiguous()
     M, D = xn.shape
     dx = torch.empty_like(xn)
+    _w(4.0 * M * D, 12.0 * M * D)
     _call("xm_l2norm_bwd_f32", _p(dxn), _p(xn), _p(inv), _p(dx), M, D, _stream())
     return dx
 
@@ -374,6 +432,7 @@ def similarity(a, b, inv_tau):
     Ml, D = a.shape
     Ng = b.shape[0]
     S = torch.empty(Ml, Ng, device=a.device, dtype=torch.float32)
+    _w(2.0 * Ml * Ng * D, 4.0 * (Ml * D + Ng * D + Ml * Ng))
     _call("xm_similarity_f32", _p(a), _p(b), _p(S), Ml, Ng, D, float(inv_tau), _stream())
     return S
 
@@ -387,6 +446,7 @@ def infonce_lse(a, b, inv_tau, diag_off=0):
     ws = torch.empty(Ml * ((Ng + tn - 1) // tn), device=a.device, dtype=torch.float32)
     lse = torch.empty(Ml, device=a.device, dtype=torch.float32)
     diag = torch.empty(Ml, device=a.device, dtype=torch.float32)
+    _w(2.0 * Ml * Ng * D, 4.0 * (Ml * D + Ng * D + 2 * Ml))
     _call("xm_infonce_lse_f32", _p(a), _p(b), _p(lse), _p(diag), Ml, Ng, D, float(inv_tau), int(diag_off), _p(ws),
           _stream())
     return lse, diag
@@ -398,6 +458,7 @@ def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
     Ml, D = a.shape
     Ng = b.shape[0]
     G = torch.empty(Ml, Ng, device=a.device, dtype=torch.float32)
+    _w(2.0 * Ml * Ng * D, 4.0 * (Ml * D + Ng * D + Ml * Ng))
     _call("xm_infonce_grad_f32", _p(a), _p(b), _p(lse_row), _p(lse_col), _p(G), Ml, Ng, D, float(inv_tau),
           int(diag_off), float(coef), _stream())
     return G
@@ -423,6 +484,7 @@ def window_gather(rec, win, hop, channels_last=False, round_out=False):
     R, C, n = rec.shape
     n_win = (n - win) // hop + 1
     out = empty_pitched((R * n_win, win, C) if channels_last else (R * n_win, C, win), rec.device)
+    _w(0.0, 8.0 * out.shape[0] * C * win)
     _call("xm_window_gather_f32", _p(rec), R, C, n, win, hop, _p(out), out.stride(1), int(channels_last),
           int(round_out), _stream())
     return out
@@ -435,6 +497,7 @@ def bandpower(rec, win, hop, nfft, fs, taper, taper_sumsq, band_bins):
     n_win = (n - win) // hop + 1
     nb = band_bins.numel() // 2
     power = torch.empty(R * n_win, C, nb, device=rec.device, dtype=torch.float32)
+    _w(R * n_win * C * 2.5 * nfft * max(1, nfft.bit_length() - 1), 4.0 * (R * n_win * C * win + power.numel()))
     _call("xm_bandpower_f32", _p(rec), R, C, n, win, hop, nfft, float(fs), _p(taper), float(taper_sumsq),
           _p(band_bins), nb, _p(power), _stream())
     return power
@@ -446,6 +509,7 @@ def zscore(x, eps=1e-8):
     x = x.contiguous()
     n = x.shape[0]
     out = torch.empty_like(x)
+    _w(4.0 * x.numel(), 8.0 * x.numel())
     _call("xm_zscore_f32", _p(x), n, x.numel() // n, float(eps), _p(out), _stream())
     return out
 
@@ -455,5 +519,6 @@ def roi_meanstd(x):
     x = x.contiguous()
     B, TR, ROI = x.shape
     out = torch.empty(B, 2 * ROI, device=x.device, dtype=torch.float32)
+    _w(3.0 * x.numel(), 4.0 * (x.numel() + out.numel()))
     _call("xm_roi_meanstd_f32", _p(x), B, TR, ROI, _p(out), _stream())
     return out

@@ -1,0 +1,252 @@
+"""TEST-ONLY fake backend: torch-CPU stand-ins for the raw device ops of multimodal_eeg_fmri_b200.ops, so
+the host-side logic above the C ABI (autograd functions, drop-in modules, SyncBN / all-gather /
+gradient-bucket plumbing of the data-parallel step) can be exercised without a GPU, including
+world_size-2 `gloo` runs.  Installed by monkeypatching attributes of the real `ops` module inside a
+test; never imported by the product package (whose ops raise on non-CUDA tensors).
+
+Each fake follows the contract documented in include/xmodal_b200.h for the entry point it replaces
+(fp64 internally, fp32 out; dropout supported only with p = 0)."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+_ACT = {None: "none", 0: "none", 1: "relu", 2: "gelu", 3: "tanh", 4: "sigmoid"}
+
+
+def _act(z, act):
+    act = _ACT.get(act, act)
+    return {"none": lambda t: t, "relu": torch.relu, "gelu": F.gelu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[act](z)
+
+
+def _nodrop(p):
+    assert float(p) == 0.0, "the fake backend has no dropout mask generator (parity runs use dropout = 0)"
+
+
+def as_nwc(t):
+    return t.contiguous()
+
+
+def empty_pitched(shape, device):
+    return torch.empty(*shape, device=device, dtype=torch.float32)
+
+
+def window_gather(rec, win, hop, channels_last=False, round_out=False):
+    R, C, n = rec.shape
+    w = rec.unfold(2, win, hop).permute(0, 2, 1, 3).reshape(-1, C, win)  # (R*n_win, C, win)
+    return (w.transpose(1, 2) if channels_last else w).contiguous()
+
+
+def to_nwc(x, round_out=False):
+    return x.transpose(1, 2).contiguous()
+
+
+# ---------------------------------------------------------------- linear
+def linear_fwd(x, w, bias=None, act=None, round_out=False, splits=0):
+    return _act(F.linear(x.double(), w.double(), None if bias is None else bias.double()), act).float()
+
+
+def linear_dgrad(dy, w, round_out=False):
+    return (dy.double() @ w.double()).float()
+
+
+def linear_wgrad(dy, x, need_bias=True, splits=0):
+    return (dy.double().t() @ x.double()).float(), (dy.double().sum(0).float() if need_bias else None)
+
+
+# ---------------------------------------------------------------- conv1d on channels-last activations
+def conv1d_pack_weight(w):
+    return w.detach().clone(), w.detach().clone()  # both "packed" forms are just the weight here
+
+
+def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
+    y = F.conv1d(x.double().transpose(1, 2), wk.double(), None if bias is None else bias.double(), padding=wk.shape[-1] // 2)
+    y = y.transpose(1, 2).float().contiguous()
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def conv1d_dgrad(dy, wt, Cin, round_out=False):
+    dx = F.conv_transpose1d(dy.double().transpose(1, 2), wt.double(), padding=wt.shape[-1] // 2)
+    return dx.transpose(1, 2).float().contiguous()
+
+
+@torch.enable_grad()
+def conv1d_wgrad(dy, x, taps, need_bias=True):
+    Cout, Cin = dy.shape[2], x.shape[2]
+    w = torch.zeros(Cout, Cin, taps, dtype=torch.float64, requires_grad=True)
+    y = F.conv1d(x.double().transpose(1, 2), w, None, padding=taps // 2)
+    (gw,) = torch.autograd.grad(y, w, dy.double().transpose(1, 2))
+    return gw.float(), (dy.double().sum((0, 1)).float() if need_bias else None)
+
+
+# ---------------------------------------------------------------- batch norm + act (+pool)
+def _rows(y):
+    return y.reshape(-1, y.shape[-1])
+
+
+def bn_partial_stats(y):
+    r = _rows(y).double()
+    return torch.stack([r.sum(0), (r * r).sum(0)], dim=1).unsqueeze(0)  # (1, C, 2)
+
+
+def bn_finalize_stats(part, count, eps, running_mean=None, running_var=None, momentum=0.1):
+    s = part.sum(0)
+    mean = s[:, 0] / count
+    var = (s[:, 1] / count - mean * mean).clamp_min(0)
+    if running_mean is not None:
+        running_mean.mul_(1 - momentum).add_(momentum * mean.float())
+        running_var.mul_(1 - momentum).add_(momentum * (var * count / max(count - 1, 1)).float())
+    return mean.float(), torch.rsqrt(var + eps).float()
+
+
+def _bn_formula(y, mean, invstd, gamma, beta, act, pool):
+    z = (y - mean) * invstd * gamma + beta
+    a = _act(z, act)
+    if pool == 2:
+        B, T, C = a.shape
+        a = a[:, : T // 2 * 2].reshape(B, T // 2, 2, C).amax(2)
+    return z, a
+
+
+def bn_act_fwd(y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, drop_before_pool=False, round_out=False):
+    _nodrop(drop_p)
+    _, a = _bn_formula(y.double(), mean.double(), invstd.double(), gamma.double(), beta.double(), act, pool)
+    return a.float().contiguous()
+
+
+@torch.enable_grad()
+def _dz(dout, y, mean, invstd, gamma, beta, act, pool):
+    z0 = ((y.double() - mean.double()) * invstd.double() * gamma.double() + beta.double()).requires_grad_(True)
+    a = _act(z0, act)
+    if pool == 2:
+        B, T, C = a.shape
+        a = a[:, : T // 2 * 2].reshape(B, T // 2, 2, C).amax(2)
+    (dz,) = torch.autograd.grad(a, z0, dout.double())
+    xhat = (y.double() - mean.double()) * invstd.double()
+    return dz, xhat
+
+
+def bn_act_bwd_reduce(dout, y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, drop_before_pool=False):
+    _nodrop(drop_p)
+    dz, xhat = _dz(dout, y, mean, invstd, gamma, beta, act, pool)
+    return torch.stack([_rows(dz).sum(0), _rows(dz * xhat).sum(0)], dim=1).unsqueeze(0)
+
+
+def bn_bwd_finalize(part):
+    s = part.sum(0)
+    return s[:, 0].float(), s[:, 1].float()
+
+
+def bn_act_bwd_apply(dout, y, mean, invstd, gamma, beta, dbeta, dgamma, count, act, pool=0, drop_p=0.0, seed=0,
+                     drop_before_pool=False, round_out=False):
+    dz, xhat = _dz(dout, y, mean, invstd, gamma, beta, act, pool)
+    dy = gamma.double() * invstd.double() * (dz - dbeta.double() / count - xhat * dgamma.double() / count)
+    return dy.float().contiguous()
+
+
+def seqmean(x):
+    return x.double().mean(1).float()
+
+
+def seqmean_bwd(dout, T):
+    return (dout.double() / T).unsqueeze(1).expand(dout.shape[0], T, dout.shape[1]).float().contiguous()
+
+
+# ---------------------------------------------------------------- layer norm + act, act, reductions
+def ln_act_fwd(x, gamma, beta, eps, act, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    xd = x.double()
+    mean = xd.mean(1)
+    rstd = torch.rsqrt(xd.var(1, unbiased=False) + eps)
+    z = (xd - mean[:, None]) * rstd[:, None] * gamma.double() + beta.double()
+    return _act(z, act).float(), mean.float(), rstd.float()
+
+
+@torch.enable_grad()
+def ln_act_bwd(dout, x, gamma, beta, mean, rstd, act, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    xd, gd, bd = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    eps = 0.0  # rebuild from the saved statistics: identical to layer_norm's own backward
+    m = xd.mean(1, keepdim=True)
+    v = xd.var(1, unbiased=False, keepdim=True)
+    saved_eps = (1.0 / rstd.double() ** 2 - v.detach().squeeze(1)).clamp_min(0).mean()
+    z = (xd - m) * torch.rsqrt(v + saved_eps + eps) * gd + bd
+    gx, gg, gb = torch.autograd.grad(_act(z, act), (xd, gd, bd), dout.double())
+    return gx.float(), gg.float(), gb.float()
+
+
+def act_fwd(x, act, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    return _act(x.double(), act).float()
+
+
+@torch.enable_grad()
+def act_bwd(dout, x, act, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    xd = x.double().requires_grad_(True)
+    (g,) = torch.autograd.grad(_act(xd, act), xd, dout.double())
+    return g.float()
+
+
+def colsum(x):
+    return x.double().sum(0).float()
+
+
+# ---------------------------------------------------------------- l2norm / similarity / InfoNCE
+def l2norm_fwd(x, eps=1e-12):
+    n = x.double().norm(dim=1).clamp_min(eps)
+    return (x.double() / n[:, None]).float(), (1.0 / n).float()
+
+
+def l2norm_bwd(dxn, xn, inv):
+    d, x = dxn.double(), xn.double()
+    return ((d - x * (x * d).sum(1, keepdim=True)) * inv.double()[:, None]).float()
+
+
+def similarity(a, b, inv_tau):
+    return (a.double() @ b.double().t() * inv_tau).float()
+
+
+def infonce_lse(a, b, inv_tau, diag_off=0):
+    S = a.double() @ b.double().t() * inv_tau
+    i = torch.arange(a.shape[0])
+    return torch.logsumexp(S, 1).float(), S[i, i + diag_off].float()
+
+
+def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
+    S = a.double() @ b.double().t() * inv_tau
+    G = torch.exp(S - lse_row.double()[:, None]) + torch.exp(S - lse_col.double()[None, :])
+    i = torch.arange(a.shape[0])
+    G[i, i + diag_off] -= 2.0
+    return (G * coef).float()
+
+
+# ---------------------------------------------------------------- preprocessing
+def roi_meanstd(x):
+    xd = torch.nan_to_num(x.double(), nan=0.0)
+    return torch.cat([xd.mean(1), xd.std(1, unbiased=False)], dim=1).float()
+
+
+def zscore(x, eps=1e-8):
+    xd = x.double().reshape(x.shape[0], -1)
+    out = (xd - xd.mean(1, keepdim=True)) / (xd.std(1, unbiased=False, keepdim=True) + eps)
+    return out.reshape(x.shape).float()
+
+
+FAKES = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F", "torch", "annotations")]
+
+
+def install(monkeypatch=None):
+    """Replace the raw device ops with the fakes above (attributes of the real module)."""
+    from multimodal_eeg_fmri_b200 import ops
+
+    for name in FAKES:
+        if name == "install":
+            continue
+        if monkeypatch is not None:
+            monkeypatch.setattr(ops, name, globals()[name])
+        else:
+            setattr(ops, name, globals()[name])

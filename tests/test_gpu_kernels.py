@@ -1,0 +1,291 @@
+"""Per-kernel parity on a B200, called through the C ABI (multimodal_eeg_fmri_b200.ops binds
+include/xmodal_b200.h with ctypes).  References are fp64 torch restatements of the same op.
+
+Tolerances (BASELINE.json north_star): tf32 tensor-core contractions 1e-3 relative; fp32
+reductions / norms / spectral 1e-5 relative; integer index work bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import assert_close_rel, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TF32 = 1e-3
+FP32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multimodal_eeg_fmri_b200 import _lib, ops as _ops
+    assert _lib.LIB_PATH.exists(), "CUDA library missing on the GPU box"
+    return _ops
+
+
+def _nwc(x):
+    return x.transpose(1, 2).contiguous()
+
+
+# ------------------------------------------------------------------ linear
+@pytest.mark.parametrize("M,N,K,act,splits", [
+    (128, 64, 64, None, 1), (300, 96, 200, "gelu", 1), (4096, 128, 400, "relu", 1), (256, 128, 4096, None, 4),
+    (70, 2, 32, None, 1), (512, 256, 128, None, 1), (1000, 320, 96, None, 1), (64, 128, 40000, None, 0),
+    (1, 16, 8, None, 1),
+])
+def test_linear_fwd(ops, M, N, K, act, splits):
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    y = ops.linear_fwd(x, w, b, act=act, splits=splits)
+    ref = x.double() @ w.double().t() + b.double()
+    ref = F.gelu(ref) if act == "gelu" else torch.relu(ref) if act == "relu" else ref
+    assert_close_rel(y, ref, TF32, "linear_fwd")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 32), (300, 96, 200), (4096, 128, 400), (256, 64, 128), (512, 2, 64),
+                                   (64, 128, 40000)])
+def test_linear_dgrad(ops, M, N, K):
+    torch.manual_seed(1)
+    dy = torch.randn(M, N, device="cuda")
+    w = torch.randn(N, K, device="cuda")
+    assert_close_rel(ops.linear_dgrad(dy, w), dy.double() @ w.double(), TF32, "linear_dgrad")
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(128, 128, 32, 1), (300, 96, 200, 1), (4096, 128, 400, 4), (256, 64, 128, 1),
+                                          (2048, 128, 4000, 2), (512, 2, 64, 1), (64, 128, 40000, 0)])
+def test_linear_wgrad(ops, M, N, K, splits):
+    torch.manual_seed(2)
+    dy = torch.randn(M, N, device="cuda")
+    x = torch.randn(M, K, device="cuda")
+    dw, db = ops.linear_wgrad(dy, x, splits=splits)
+    assert_close_rel(dw, dy.double().t() @ x.double(), TF32, "linear_wgrad")
+    assert_close_rel(db, dy.double().sum(0), FP32, "bias grad")
+
+
+# ------------------------------------------------------------------ conv1d
+CONV_CASES = [(1, 32, 32, 128, 1), (2, 32, 32, 128, 3), (3, 64, 64, 500, 7), (2, 64, 128, 500, 5), (2, 128, 128, 250, 3),
+              (2, 48, 96, 250, 5), (2, 18, 48, 500, 7), (1, 192, 128, 100, 1), (2, 8, 16, 64, 7), (5, 64, 64, 37, 5)]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,k", CONV_CASES)
+def test_conv1d_fwd_dgrad_wgrad(ops, B, Cin, Cout, T, k):
+    torch.manual_seed(3)
+    x = torch.randn(B, Cin, T, device="cuda")
+    w = torch.randn(Cout, Cin, k, device="cuda") / (Cin * k) ** 0.5
+    b = torch.randn(Cout, device="cuda")
+    dy = torch.randn(B, Cout, T, device="cuda")
+    wk, wt = ops.conv1d_pack_weight(w)
+    xl = ops.to_nwc(x)
+    assert torch.equal(xl, _nwc(x)), "layout change must be exact"
+    y = ops.conv1d_fwd(xl, wk, b, Cout)
+    assert_close_rel(y, _nwc(F.conv1d(x.double(), w.double(), b.double(), padding=k // 2)), TF32, "conv fwd")
+    dx = ops.conv1d_dgrad(_nwc(dy), wt, Cin)
+    assert_close_rel(dx, _nwc(F.conv_transpose1d(dy.double(), w.double(), padding=k // 2)), TF32, "conv dgrad")
+    dw, db = ops.conv1d_wgrad(_nwc(dy), xl, k)
+    wd = torch.zeros(Cout, Cin, k, device="cuda", dtype=torch.float64, requires_grad=True)
+    (gw,) = torch.autograd.grad(F.conv1d(x.double(), wd, None, padding=k // 2), wd, dy.double())
+    assert_close_rel(dw, gw, TF32, "conv wgrad")
+    assert_close_rel(db, dy.double().sum((0, 2)), FP32, "conv bias grad", atol=1e-5)
+
+
+def test_conv1d_wgrad_many_samples(ops):
+    torch.manual_seed(5)
+    B, Cin, Cout, T, k = 300, 64, 64, 500, 7
+    x = torch.randn(B, Cin, T, device="cuda")
+    dy = torch.randn(B, Cout, T, device="cuda")
+    dw, _ = ops.conv1d_wgrad(_nwc(dy), _nwc(x), k)
+    wd = torch.zeros(Cout, Cin, k, device="cuda", dtype=torch.float64, requires_grad=True)
+    (gw,) = torch.autograd.grad(F.conv1d(x.double(), wd, None, padding=k // 2), wd, dy.double())
+    assert_close_rel(dw, gw, TF32, "conv wgrad B=300")
+
+
+# ------------------------------------------------------------------ similarity / InfoNCE
+@pytest.mark.parametrize("Ml,Ng,D,off", [(128, 128, 128, 0), (256, 256, 128, 0), (200, 600, 64, 200), (4096, 4096, 128, 0),
+                                         (5, 5, 32, 0), (1, 1, 16, 0)])
+def test_infonce_kernels(ops, Ml, Ng, D, off):
+    torch.manual_seed(6)
+    e = torch.randn(Ml, D, device="cuda")
+    f = torch.randn(Ng, D, device="cuda")
+    en, einv = ops.l2norm_fwd(e)
+    fn, _ = ops.l2norm_fwd(f)
+    # l2norm output is tf32-rounded for the contraction that follows: 2^-11 relative
+    assert_close_rel(en, F.normalize(e.double(), dim=1), 5e-4, "l2norm")
+    it = 1 / 0.07
+    Sref = en.double() @ fn.double().t() * it
+    assert_close_rel(ops.similarity(en, fn, it), Sref, TF32, "similarity")
+    lse, diag = ops.infonce_lse(en, fn, it, off)
+    lref = torch.logsumexp(Sref, dim=1)
+    idx = torch.arange(Ml, device="cuda")
+    assert float((lse.double() - lref).abs().max()) < 1e-4, "row lse (fp32, |S| <= 14.3)"
+    assert float((diag.double() - Sref[idx, idx + off]).abs().max()) < 1e-4
+    lse_col = torch.logsumexp(Sref, dim=0).float()
+    G = ops.infonce_grad(en, fn, lse, lse_col, it, off, 0.5 / Ml)
+    Gref = torch.exp(Sref - lref[:, None]) + torch.exp(Sref - lse_col.double()[None, :])
+    Gref[idx, idx + off] -= 2
+    assert_close_rel(G, Gref * (0.5 / Ml), TF32, "infonce grad tile", atol=1e-6 / Ml)
+    d = torch.randn(Ml, D, device="cuda")
+    ed = e.double().requires_grad_(True)
+    (gx,) = torch.autograd.grad(F.normalize(ed, dim=1), ed, d.double())
+    assert_close_rel(ops.l2norm_bwd(d, en, einv), gx, 5e-4, "l2norm bwd")
+
+
+# ------------------------------------------------------------------ windowing + band power
+@pytest.mark.parametrize("R,C,n,win,hop,nfft,fs", [
+    (2, 4, 3000, 1024, 512, 1024, 1000.0), (3, 8, 2000, 500, 250, 512, 250.0), (1, 3, 1001, 100, 37, 128, 128.0),
+    (2, 128, 8192, 1024, 512, 1024, 1000.0), (1, 2, 5000, 2000, 1000, 2048, 1000.0), (1, 1, 64, 64, 64, 64, 64.0),
+])
+def test_window_index_gather_bandpower(ops, R, C, n, win, hop, nfft, fs):
+    from multimodal_eeg_fmri_b200 import eeg_data_utils as edu
+    from oracle import spectral as osp
+    torch.manual_seed(7)
+    rec = torch.randn(R, C, n, device="cuda")
+    labels = torch.arange(R) % 2
+    subj = torch.arange(R) + 100
+    st, rid, lab, sub = edu.window_indices(R, n, win, hop, labels, subj)
+    o_st, o_rid, o_lab, o_sub = osp.window_indices(R, n, win, hop, labels.numpy(), subj.numpy())
+    for got, want in ((st, o_st), (rid, o_rid), (lab, o_lab), (sub, o_sub)):  # bit-exact integer work
+        assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), want)
+    g = edu.gather_windows(rec, win, hop)
+    want = osp.gather_windows(rec.cpu().numpy(), win, hop)
+    assert np.array_equal(g.cpu().numpy(), want), "gather must be bit-exact"
+    gl = edu.gather_windows(rec, win, hop, channels_last=True)
+    assert np.array_equal(gl.cpu().numpy(), want.transpose(0, 2, 1))
+    p = edu.band_power(rec, fs, win, hop, nfft=nfft)
+    ref = osp.band_power(want, fs, nfft=nfft, taper=torch.hann_window(win, periodic=True, dtype=torch.float64).float().double().numpy())
+    assert p.shape == ref.shape
+    # fp32 FFT vs fp64 oracle: 1e-5 relative per element where the band holds energy
+    err = np.abs(p.cpu().numpy().astype(np.float64) - ref) / np.maximum(ref, 1e-30)
+    assert err.max() < FP32, f"band power max rel err {err.max():.3e}"
+
+
+def test_bandpower_pure_tone(ops):
+    """Known answer: a 10 Hz sinusoid of amplitude A puts A^2/2 in alpha and ~nothing elsewhere."""
+    from multimodal_eeg_fmri_b200 import eeg_data_utils as edu
+    fs, n = 1000.0, 4096
+    t = torch.arange(n, dtype=torch.float64) / fs
+    rec = (3.0 * torch.sin(2 * math.pi * 10.0 * t)).float().reshape(1, 1, n).cuda()
+    p = edu.band_power(rec, fs, 1000, 1000).cpu()  # nfft 1024, 4 windows
+    assert p.shape == (4, 1, 3)
+    alpha = p[:, 0, 1]
+    assert torch.allclose(alpha, torch.full_like(alpha, 4.5), rtol=2e-2)
+    assert float(p[:, 0, 0].max()) < 1e-2 * 4.5 and float(p[:, 0, 2].max()) < 1e-2 * 4.5
+
+
+def test_window_indices_short_recording(ops):
+    from multimodal_eeg_fmri_b200 import eeg_data_utils as edu
+    st, rid, lab, sub = edu.window_indices(3, 10, 64, 32)
+    assert st.numel() == 0 and rid.numel() == 0 and lab is None and sub is None
+
+
+# ------------------------------------------------------------------ BN + act (+pool, dropout)
+def _bn_ref(y, gamma, beta, act, pool):
+    z = F.batch_norm(y, None, None, gamma, beta, True, 0.1, 1e-5)
+    a = F.gelu(z) if act == "gelu" else torch.relu(z) if act == "relu" else z
+    return F.max_pool1d(a, 2) if pool == 2 else a
+
+
+@pytest.mark.parametrize("shape,act,pool", [((4, 16, 100), "gelu", 0), ((8, 64, 500), "gelu", 2), ((3, 48, 251), "gelu", 2),
+                                            ((64, 128), "relu", 0), ((5, 7, 33), "gelu", 0), ((4096, 64), "relu", 0),
+                                            ((2, 128, 250), "none", 0)])
+def test_bn_act_fwd_bwd(ops, shape, act, pool):
+    torch.manual_seed(8)
+    y = torch.randn(*shape, device="cuda") * 2 + 0.5
+    C = shape[1]
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda")
+    three = y.dim() == 3
+    yl = ops.as_nwc(_nwc(y)) if three else y
+    cnt = y.numel() // C
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    mean, invstd = ops.bn_finalize_stats(ops.bn_partial_stats(yl), cnt, 1e-5, rm, rv, 0.1)
+    out = ops.bn_act_fwd(yl, mean, invstd, gamma, beta, act, pool)
+    yd, gd, bd = y.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    ref = _bn_ref(yd, gd, bd, act, pool)
+    dout = torch.randn_like(ref).float()
+    gy, gg, gb = torch.autograd.grad(ref, (yd, gd, bd), dout.double())
+    doutl = ops.as_nwc(_nwc(dout)) if three else dout
+    dbeta, dgamma = ops.bn_bwd_finalize(ops.bn_act_bwd_reduce(doutl, yl, mean, invstd, gamma, beta, act, pool))
+    dy = ops.bn_act_bwd_apply(doutl, yl, mean, invstd, gamma, beta, dbeta, dgamma, cnt, act, pool)
+    t = _nwc if three else (lambda z: z)
+    dims = (0, 2) if three else (0,)
+    assert_close_rel(out, t(ref), FP32, "bn fwd")
+    assert_close_rel(dy, t(gy), FP32, "bn dy")
+    assert_close_rel(dgamma, gg, FP32, "bn dgamma")
+    assert_close_rel(dbeta, gb, FP32, "bn dbeta")
+    assert_close_rel(rm, 0.1 * y.double().mean(dims), FP32, "running mean")
+    assert_close_rel(rv, 0.9 + 0.1 * y.double().var(dims, unbiased=True), FP32, "running var")
+
+
+def test_dropout_mask_statistics_and_consistency(ops):
+    torch.manual_seed(9)
+    y = ops.as_nwc(torch.randn(8, 500, 64, device="cuda"))
+    C = 64
+    gamma, beta = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    mean, invstd = ops.bn_finalize_stats(ops.bn_partial_stats(y), y.numel() // C, 1e-5)
+    out = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "none", 2, 0.3, 1234, False)
+    out0 = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "none", 2, 0.0, 1234, False)
+    keep = out != 0
+    assert abs(float(keep.float().mean()) - 0.7) < 5e-3
+    assert torch.allclose(out[keep], (out0 / 0.7)[keep], rtol=1e-5)
+    # the backward regenerates the same mask from the seed: sum(dz) for dout = 1 counts kept elements / 0.7
+    part = ops.bn_act_bwd_reduce(torch.ones_like(out), y, mean, invstd, gamma, beta, "none", 2, 0.3, 1234, False)
+    dbeta, _ = ops.bn_bwd_finalize(part)
+    assert abs(float(dbeta.sum()) - float(keep.sum()) / 0.7) < 1.0
+    a = ops.act_fwd(torch.ones(1 << 16, device="cuda"), "none", 0.4, 77)
+    assert abs(float((a != 0).float().mean()) - 0.6) < 1e-2
+    da = ops.act_bwd(torch.ones(1 << 16, device="cuda"), torch.ones(1 << 16, device="cuda"), "none", 0.4, 77)
+    assert torch.equal(a != 0, da != 0)
+
+
+def test_seqmean(ops):
+    x = ops.as_nwc(torch.randn(6, 250, 96, device="cuda"))
+    assert_close_rel(ops.seqmean(x), x.double().mean(1), FP32, "seqmean")
+    d = torch.randn(6, 96, device="cuda")
+    assert_close_rel(ops.seqmean_bwd(d, 250), (d.double() / 250)[:, None, :].expand(6, 250, 96), FP32, "seqmean bwd")
+
+
+@pytest.mark.parametrize("M,D,act", [(64, 128, "gelu"), (4096, 128, "gelu"), (100, 64, "relu"), (33, 96, "gelu")])
+def test_ln_act(ops, M, D, act):
+    torch.manual_seed(10)
+    x = torch.randn(M, D, device="cuda") * 1.5 + 0.3
+    g = torch.rand(D, device="cuda") + 0.5
+    b = torch.randn(D, device="cuda")
+    out, mean, rstd = ops.ln_act_fwd(x, g, b, 1e-5, act)
+    xd, gd, bd = (t.double().requires_grad_(True) for t in (x, g, b))
+    z = F.layer_norm(xd, (D,), gd, bd, 1e-5)
+    ref = F.gelu(z) if act == "gelu" else torch.relu(z)
+    dout = torch.randn_like(out)
+    gx, gg, gb = torch.autograd.grad(ref, (xd, gd, bd), dout.double())
+    dx, dg, db = ops.ln_act_bwd(dout, x, g, b, mean, rstd, act)
+    assert_close_rel(out, ref, FP32, "ln fwd")
+    assert_close_rel(dx, gx, FP32, "ln dx")
+    assert_close_rel(dg, gg, FP32, "ln dgamma")
+    assert_close_rel(db, gb, FP32, "ln dbeta")
+
+
+def test_roi_meanstd_zscore_colsum(ops):
+    from oracle import models as om
+    from oracle import spectral as osp
+    torch.manual_seed(11)
+    x = torch.randn(64, 100, 200, device="cuda")
+    x[0, 3, 5] = float("nan")
+    assert_close_rel(ops.roi_meanstd(x), om.roi_meanstd(x.cpu().double()), FP32, "roi mean/std")
+    x = torch.randn(16, 75, 40, device="cuda") * 3 + 1
+    z = ops.zscore(x).cpu()
+    for i in range(16):
+        assert_close_rel(z[i], osp.normalize_modality(x[i].cpu().double().numpy()), FP32, "normalize_modality")
+    x = torch.randn(1000, 96, device="cuda")
+    assert_close_rel(ops.colsum(x), x.double().sum(0), FP32, "colsum")
+
+
+def test_error_codes_surface_as_exceptions(ops):
+    from multimodal_eeg_fmri_b200 import _lib
+    with pytest.raises(_lib.XmodalError):
+        ops.bandpower(torch.randn(1, 1, 100, device="cuda"), 100, 50, 96, 100.0, torch.ones(100, device="cuda"), 100.0,
+                      torch.tensor([1, 2], dtype=torch.int32, device="cuda"))  # nfft not a supported power of two
+    assert rel_err(torch.ones(2), torch.ones(2)) == 0.0

@@ -1,0 +1,153 @@
+"""The composite paired EEG/fMRI training step on a B200 against the CPU oracle
+(oracle/paired_step.py: pinned reference modules + authored InfoNCE), plus size-independent
+properties at the BASELINE batch sizes.  Tolerances: losses / features 1e-3 relative, gradients 3e-3
+(chains of tf32 contractions), InfoNCE reductions 1e-5 where stated."""
+import math
+
+import pytest
+import torch
+
+from conftest import assert_close_rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_model(encoder="v4", seed=7):
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel
+    torch.manual_seed(seed)
+    return PairedBridgeModel(eeg_channels=8, n_roi=12, eeg_hidden=32, fmri_hidden=16, bridge_dim=32, dropout=0.0,
+                             fmri_dropout=0.0, encoder=encoder)
+
+
+def _sd_cpu(m):
+    return {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("encoder", ["v4", "lite"])
+def test_paired_loss_and_grads_small(encoder):
+    from multimodal_eeg_fmri_b200 import synthetic
+    from oracle import paired_step as ops_
+    m = _small_model(encoder)
+    P = _sd_cpu(m)
+    eeg, roi, conn = synthetic.paired_batch(16, 8, 64, 12, 20, seed=3)
+    m = m.cuda().train()
+    loss = m(eeg.cuda(), roi.cuda(), conn.cuda())
+    loss.backward()
+    oloss, ograds = ops_.paired_loss_and_grads(P, eeg, roi, conn, 0.07, encoder)
+    assert_close_rel(loss, oloss, 1e-3, "InfoNCE loss")
+    named = dict(m.named_parameters())
+    for k, g in ograds.items():
+        assert named[k].grad is not None, k
+        assert_close_rel(named[k].grad, g, 5e-3, f"grad {k}", atol=3e-5)
+    for k in set(named) - set(ograds):  # supervised heads are not reached by the contrastive loss
+        assert named[k].grad is None, k
+
+
+def test_paired_trainer_three_steps_match_oracle():
+    from multimodal_eeg_fmri_b200 import synthetic
+    from multimodal_eeg_fmri_b200.training import PairedTrainer
+    from oracle import paired_step as ops_
+    m = _small_model("v4")
+    P = _sd_cpu(m)
+    eeg, roi, conn = synthetic.paired_batch(16, 8, 64, 12, 20, seed=5)
+    m = m.cuda().train()
+    tr = PairedTrainer(m, lr=1e-4, weight_decay=1e-4, grad_clip=1.0)
+    state, ol, dl = {}, [], []
+    for _ in range(3):
+        dl.append(float(tr.step(eeg.cuda(), roi.cuda(), conn.cuda())))
+        ol.append(float(ops_.paired_train_step(P, state, eeg, roi, conn, 0.07, "v4")[0]))
+    assert_close_rel(torch.tensor(dl), torch.tensor(ol), 1e-3, "losses over 3 steps")
+    assert dl[2] < dl[0], "loss must go down on a fixed batch"
+    sd = m.state_dict()
+    for k in set(ops_.trainable_keys(P)) - set(ops_.bias_before_batchnorm_keys(P)):
+        assert_close_rel(sd[k], P[k], 1e-3, f"param {k}", atol=1e-4)
+    # end-to-end entry from pinned host buffers gives the same kind of number
+    l4 = tr.step_from_host(eeg.pin_memory(), roi.pin_memory(), conn.pin_memory())
+    assert math.isfinite(l4) and l4 < dl[0]
+
+
+def test_windowed_raw_recordings_feed_the_encoder():
+    """Raw recordings -> on-device window gather (channels-last, tf32-rounded) -> step, equals the step
+    on pre-cut windows."""
+    from multimodal_eeg_fmri_b200 import eeg_data_utils as edu, synthetic
+    from multimodal_eeg_fmri_b200.training import PairedTrainer
+    m1, m2 = _small_model("lite", 11).cuda(), _small_model("lite", 11).cuda()
+    rec = torch.randn(4, 8, 64 * 4, device="cuda")  # 4 recordings x 4 non-overlapping windows of 64 = 16 samples
+    _, roi, conn = synthetic.paired_batch(16, 8, 64, 12, 20, seed=9)
+    t1 = PairedTrainer(m1, window=64, hop=64)
+    t2 = PairedTrainer(m2)
+    l1 = float(t1.step(rec, roi.cuda(), conn.cuda()))
+    l2 = float(t2.step(edu.gather_windows(rec, 64, 64), roi.cuda(), conn.cuda()))
+    assert abs(l1 - l2) <= 1e-5 * abs(l2)
+
+
+@pytest.mark.parametrize("B", [256, 4096])
+def test_infonce_known_answers_at_baseline_batch(B):
+    from multimodal_eeg_fmri_b200.bridge_utils import symmetric_infonce, similarity_matrix
+    D = 128
+    v = torch.randn(1, D, device="cuda").expand(B, D).contiguous()
+    assert abs(float(symmetric_infonce(v, v)) - math.log(B)) < 1e-4 * math.log(B)  # all-equal rows: L = log B
+    q, _ = torch.linalg.qr(torch.randn(D, D, device="cuda", dtype=torch.float64))
+    e = q[:, :128].t().float().contiguous()  # 128 orthonormal rows
+    want = math.log(1 + 127 * math.exp(-1 / 0.07))
+    assert abs(float(symmetric_infonce(e, e * 3.0)) - want) < 1e-5 + 1e-3 * want
+    S = similarity_matrix(e, e)
+    assert_close_rel(S, torch.eye(128, dtype=torch.float64) / 0.07, 1e-3, "similarity of orthonormal rows")
+
+
+def test_infonce_gradient_matches_oracle_closed_form():
+    from multimodal_eeg_fmri_b200.bridge_utils import symmetric_infonce
+    from oracle import infonce as oi
+    torch.manual_seed(3)
+    for B, D in ((256, 128), (1000, 64), (4096, 128)):
+        e = torch.randn(B, D)
+        f = (e + 0.5 * torch.randn(B, D)).contiguous()
+        eg, fg = e.cuda().requires_grad_(True), f.cuda().requires_grad_(True)
+        loss = symmetric_infonce(eg, fg, 0.07)
+        loss.backward()
+        eo, fo = e.double().requires_grad_(True), f.double().requires_grad_(True)
+        lo = oi.symmetric_infonce(eo, fo, 0.07)
+        lo.backward()
+        assert_close_rel(loss, lo, 1e-3, f"loss B={B}")
+        assert_close_rel(eg.grad, eo.grad, 3e-3, f"de B={B}")
+        assert_close_rel(fg.grad, fo.grad, 3e-3, f"df B={B}")
+
+
+def test_paired_step_config3_shape_vs_oracle():
+    """BASELINE config 3 sample shapes (64 ch x 500 samples, 200 ROI x 100 TR) at batch 64, Lite encoder
+    (the v4 transformer tail makes the CPU oracle slow): loss and the encoder's first-layer gradient."""
+    from multimodal_eeg_fmri_b200 import synthetic
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel
+    from oracle import paired_step as ops_
+    torch.manual_seed(1)
+    m = PairedBridgeModel(64, 200, None, 96, 64, 128, 0.0, 0.0, "lite")
+    P = _sd_cpu(m)
+    eeg, roi, conn = synthetic.paired_batch(64, 64, 500, 200, 100, seed=2)
+    m = m.cuda().train()
+    loss = m(eeg.cuda(), roi.cuda(), conn.cuda())
+    loss.backward()
+    oloss, ograds = ops_.paired_loss_and_grads(P, eeg, roi, conn, 0.07, "lite")
+    assert_close_rel(loss, oloss, 1e-3, "loss")
+    named = dict(m.named_parameters())
+    for k in ("eeg_encoder.conv_layers.0.weight", "eeg_encoder.conv_layers.5.weight", "bridge.eeg_proj.0.weight",
+              "fmri_net.connectivity_encoder.encoder.0.weight", "fmri_net.activation_encoder.encoder.0.weight"):
+        assert_close_rel(named[k].grad, ograds[k], 5e-3, f"grad {k}", atol=1e-6)
+
+
+def test_full_batch_4096_step_properties():
+    """BASELINE config 4 per-GPU shape (B = 4096, v4 encoder): the step runs, the loss starts near
+    log(B) for random init, is finite, and decreases over a few steps on a fixed batch."""
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel, PairedTrainer
+    torch.manual_seed(0)
+    B = 4096
+    m = PairedBridgeModel(64, 200, None, 128, 64, 128, 0.3, 0.4, "v4").cuda().train()
+    tr = PairedTrainer(m)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    z = torch.randn(B, 16, device="cuda", generator=g)
+    eeg = torch.randn(B, 64, 500, device="cuda", generator=g) + (z @ torch.randn(16, 64, device="cuda", generator=g))[:, :, None]
+    roi = torch.randn(B, 100, 200, device="cuda", generator=g) + (z @ torch.randn(16, 200, device="cuda", generator=g))[:, None, :]
+    conn = torch.randn(B, 40000, device="cuda", generator=g) + z @ torch.randn(16, 40000, device="cuda", generator=g)
+    losses = [float(tr.step(eeg, roi, conn)) for _ in range(4)]
+    assert all(math.isfinite(x) for x in losses)
+    assert abs(losses[0] - math.log(B)) < 1.5
+    assert losses[-1] < losses[0]

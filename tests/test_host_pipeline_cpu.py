@@ -1,0 +1,94 @@
+"""Host-side logic above the C ABI, on the CPU with the TEST-ONLY fake device ops (tests/fake_ops.py):
+autograd functions + drop-in modules against the oracle, and the data-parallel step (SyncBN partial
+sums, embedding all-gather with exact local gradients, one flat gradient bucket) under a
+world_size-2 gloo group against the single-process global-batch run."""
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import dp_worker
+import fake_ops
+from conftest import assert_close_rel
+from multimodal_eeg_fmri_b200 import synthetic
+from oracle import paired_step as ps
+
+
+@pytest.fixture()
+def fakes(monkeypatch):
+    fake_ops.install(monkeypatch)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("encoder", ["v4", "lite"])
+def test_paired_model_autograd_plumbing_vs_oracle(fakes, encoder):
+    m = dp_worker.make_model(encoder).train()
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    eeg, roi, conn = synthetic.paired_batch(16, 8, 64, 12, 20, seed=3)
+    loss = m(eeg, roi, conn)
+    loss.backward()
+    oloss, ograds = ps.paired_loss_and_grads(P, eeg, roi, conn, 0.07, encoder)
+    assert_close_rel(loss, oloss, 1e-5, "loss")
+    named = dict(m.named_parameters())
+    for k, g in ograds.items():
+        assert_close_rel(named[k].grad, g, 2e-4, f"grad {k}", atol=1e-6)
+
+
+def test_trimodal_lite_and_fmri_modules_vs_golden(fakes):
+    from conftest import load_golden
+    from multimodal_eeg_fmri_b200 import modules
+    g = load_golden("trimodal_lite_small")
+    m = modules.EnhancedTriModalFusionNetV4Lite(8, 8, 30, hidden_dim=24, num_classes=2, dropout=0.0, conn_boost=1.3)
+    m.load_state_dict(g["sd"], strict=True)
+    m.train()
+    logits, w, fused = m(g["inputs"][0], g["inputs"][1], g["inputs"][2], return_fusion_weights=True, return_fused_feats=True)
+    assert_close_rel(logits, g["outputs"][0], 1e-5, "logits")
+    assert_close_rel(fused, g["raw"]["fused"], 1e-5, "fused")
+    assert_close_rel(torch.tensor([w["erp_weight"], w["pw_weight"], w["conn_weight"]]), g["raw"]["weights"], 1e-5, "weights")
+    g = load_golden("bridge_small")
+    b = modules.EEGfMRIBridgeFusionNet(32, 16, 32, 2, 4, 0.0)
+    b.load_state_dict(g["sd"], strict=True)
+    b.eval()
+    logits, fused, fw, aw = b(g["inputs"][0], g["inputs"][1], return_features=True, return_weights=True)
+    assert_close_rel(logits, g["outputs"][0], 1e-5, "bridge logits")
+    assert_close_rel(aw, g["raw"]["attn_weights"], 1e-5, "attention weights")
+    assert_close_rel(fw, g["raw"]["fusion_weights"], 1e-5, "fusion weights")
+
+
+def test_trainer_matches_oracle_recipe(fakes):
+    from multimodal_eeg_fmri_b200.training import PairedTrainer
+    m = dp_worker.make_model("lite").train()
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    eeg, roi, conn = synthetic.paired_batch(16, 8, 64, 12, 20, seed=5)
+    tr = PairedTrainer(m)
+    state = {}
+    for _ in range(3):
+        a = float(tr.step(eeg, roi, conn))
+        b = float(ps.paired_train_step(P, state, eeg, roi, conn, 0.07, "lite")[0])
+        assert abs(a - b) < 1e-5 * abs(b)
+    for k in set(ps.trainable_keys(P)) - set(ps.bias_before_batchnorm_keys(P)):
+        assert_close_rel(m.state_dict()[k], P[k], 1e-5, k, atol=2e-5)
+
+
+@pytest.mark.parametrize("encoder", ["lite", "v4"])
+def test_two_rank_gloo_step_equals_global_batch_step(tmp_path, encoder):
+    """Rank r trains on rows [8r, 8r+8) of a 16-sample batch; the run must reproduce the
+    single-process 16-sample run: same global loss (sum of shares) and same parameters."""
+    steps = 2
+    mp.spawn(dp_worker.run, args=(2, _free_port(), encoder, steps, str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(tmp_path / "dp.pt")
+    m = dp_worker.make_model(encoder)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    eeg, roi, conn = synthetic.paired_batch(16, 8, 64, 12, 20, seed=5)
+    state, want = {}, []
+    for _ in range(steps):
+        want.append(float(ps.paired_train_step(P, state, eeg, roi, conn, 0.07, encoder)[0]))
+    assert_close_rel(torch.tensor(got["losses"]), torch.tensor(want), 1e-5, "global loss per step")
+    for k in set(ps.trainable_keys(P)) - set(ps.bias_before_batchnorm_keys(P)):
+        assert_close_rel(got["sd"][k], P[k], 1e-5, f"param {k}", atol=2e-5)
