@@ -95,9 +95,10 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
 int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
                         int64_t ldw, int64_t lddx, int round_out, void* stream);
 /* dw (N,K) = dy (M,N)^T @ x (M,K); db (N) = column sums of dy (db may be NULL).
- * workspace: splits*N*K floats when splits > 1. */
+ * workspace: splits*N*K floats when splits > 1; db_workspace: xm_colsum_nsplit(M, N)*N floats when db != NULL. */
 int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
-                        int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, void* stream);
+                        int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, float* db_workspace,
+                        void* stream);
 
 /* ------------------------------------------------------------------ dense Conv1d ("same" padding, stride 1)
  * EEG_CODE/enhanced_models_v4.py:128-144 ; EEG_CODE/crossmodal_v4_enhancements.py:822-834,854-866
@@ -117,10 +118,11 @@ int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float*
 int xm_conv1d_dgrad_f32(const float* dy, const float* wt, float* dx, int64_t B, int64_t Cin, int64_t Cout, int64_t T,
                         int64_t taps, int64_t lddy, int64_t ldt, int64_t lddx, int round_out, void* stream);
 /* dw (Cout,Cin,taps) [reference layout], db (Cout) (db may be NULL).
- * workspace: xm_conv1d_wgrad_workspace() floats. */
+ * workspace: xm_conv1d_wgrad_workspace() floats; db_workspace: xm_colsum_nsplit(B*T, Cout)*Cout floats when db != NULL. */
 int64_t xm_conv1d_wgrad_workspace(int64_t B, int64_t Cin, int64_t Cout, int64_t taps);
 int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout,
-                        int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, void* stream);
+                        int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, float* db_workspace,
+                        void* stream);
 
 /* ------------------------------------------------------------------ normalisation + activation (+pool, +dropout)
  * nn.BatchNorm1d (train mode) + nn.GELU/nn.ReLU + nn.MaxPool1d(2) + nn.Dropout chains of the encoders,
@@ -175,8 +177,10 @@ int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p,
 int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
                    void* stream);
 
-/* out (N) = column sums of x (M, N) (bias gradients, partial reductions). */
-int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream);
+/* out (N) = column sums of x (M, N) (bias gradients, partial reductions), deterministic two-stage
+ * reduction; workspace: xm_colsum_nsplit(M, N) * N floats (may be NULL when nsplit == 1). */
+int xm_colsum_nsplit(int64_t M, int64_t N);
+int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, float* workspace, void* stream);
 /* ------------------------------------------------------------------ similarity + symmetric InfoNCE
  * No reference implementation; embeddings are the outputs of
  * bridge_utils.py:71-72.  Oracle: oracle/infonce.py. */

@@ -425,22 +425,34 @@ __global__ void act_bwd_kernel(const float* __restrict__ dout, const float* __re
 }
 
 // ------------------------------------------------------------------ small reductions
-// out[n] = sum_m x[m, n]; block = 32 columns x 8 row lanes
-__global__ void colsum_kernel(const float* __restrict__ x, long long M, long long N, long long ld,
+// out[n] = sum_m x[m, n] in two deterministic stages: block (bx, by) sums rows [by*chunk, (by+1)*chunk)
+// of columns [32 bx, 32 bx + 32) into part[by][n] (or straight into out when gridDim.y == 1); a second
+// launch of the same kernel reduces the gridDim.y partial rows.  block = 32 columns x 8 row lanes.
+__global__ void colsum_kernel(const float* __restrict__ x, long long M, long long N, long long ld, long long chunk,
                               float* __restrict__ out) {
   __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long n = blockIdx.x * 32ll + tx;
-  float acc = 0.f;
-  if (n < N)
-    for (long long m = ty; m < M; m += 8) acc += x[m * ld + n];
-  sm[ty][tx] = acc;
+  const long long m0 = blockIdx.y * chunk;
+  const long long m1 = min(M, m0 + chunk);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (n < N) {
+    long long m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {  // 4 independent loads in flight per thread
+      a0 += x[m * ld + n];
+      a1 += x[(m + 8) * ld + n];
+      a2 += x[(m + 16) * ld + n];
+      a3 += x[(m + 24) * ld + n];
+    }
+    for (; m < m1; m += 8) a0 += x[m * ld + n];
+  }
+  sm[ty][tx] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (ty == 0 && n < N) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += sm[i][tx];
-    out[n] = s;
+    out[blockIdx.y * N + n] = s;
   }
 }
 
@@ -673,9 +685,27 @@ int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int 
   return check_launch();
 }
 
-int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, void* stream) {
+int xm_colsum_nsplit(int64_t M, int64_t N) {
+  const long long col_blocks = (N + 31) / 32;
+  long long want = (4ll * kNumSMs + col_blocks - 1) / col_blocks;  // ~4 CTAs per SM in total
+  const long long max_by_rows = (M + 255) / 256;                   // >= 256 rows per block
+  if (want > max_by_rows) want = max_by_rows;
+  if (want < 1) want = 1;
+  if (want > 65535) want = 65535;
+  return (int)want;
+}
+
+int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out, float* workspace, void* stream) {
   if (!x || !out || M <= 0 || N <= 0) return XM_ERR_INVALID;
-  colsum_kernel<<<ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(x, M, N, ldx, out);
+  const int ns = xm_colsum_nsplit(M, N);
+  if (ns > 1 && !workspace) return XM_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long chunk = (M + ns - 1) / ns;
+  dim3 grid(ceil_div(N, 32), ns);
+  colsum_kernel<<<grid, 256, 0, st>>>(x, M, N, ldx, chunk, ns > 1 ? workspace : out);
+  int rc = check_launch();
+  if (rc != XM_OK || ns == 1) return rc;
+  colsum_kernel<<<dim3(ceil_div(N, 32), 1), 256, 0, st>>>(workspace, ns, N, N, ns, out);
   return check_launch();
 }
 

@@ -288,7 +288,8 @@ int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, i
 }
 
 int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
-                        int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, void* stream) {
+                        int64_t lddy, int64_t ldx, int64_t lddw, int splits, float* workspace, float* db_workspace,
+                        void* stream) {
   if (!dy || !x || !dw || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
   if ((lddy & 3) || (ldx & 3)) return XM_ERR_INVALID;
   if (splits < 1) splits = 1;
@@ -329,7 +330,7 @@ int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
     rc = check_launch();
     if (rc != XM_OK) return rc;
   }
-  if (db) return xm_colsum_f32(dy, M, N, lddy, db, stream);
+  if (db) return xm_colsum_f32(dy, M, N, lddy, db, db_workspace, stream);
   return XM_OK;
 }
 
@@ -428,7 +429,8 @@ int64_t xm_conv1d_wgrad_workspace(int64_t B, int64_t Cin, int64_t Cout, int64_t 
 }
 
 int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout,
-                        int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, void* stream) {
+                        int64_t T, int64_t taps, int64_t lddy, int64_t ldx, float* workspace, float* db_workspace,
+                        void* stream) {
   if (!dy || !x || !dw || !workspace || B <= 0 || Cin <= 0 || Cout <= 0 || T <= 0 || taps <= 0 || !(taps & 1))
     return XM_ERR_INVALID;
   if ((lddy & 3) || (ldx & 3) || Cin > 256 || lddy < Cout || ldx < Cin) return XM_ERR_INVALID;
@@ -473,7 +475,7 @@ int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
                                                                              (int)Cin, pl.bn, dw);
   int rc = check_launch();
   if (rc != XM_OK) return rc;
-  if (db) return xm_colsum_f32(dy, B * T, Cout, lddy, db, stream);
+  if (db) return xm_colsum_f32(dy, B * T, Cout, lddy, db, db_workspace, stream);
   return rc;
 }
 

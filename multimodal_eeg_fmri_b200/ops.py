@@ -182,9 +182,10 @@ def linear_wgrad(dy, x, need_bias=True, splits: int = 0):
         tiles = ((N + 127) // 128) * max(1, (K + 255) // 256)
         splits = 1 if tiles >= 74 or M < 1024 else min(max(1, 148 // tiles), M // 256)
     ws = torch.empty(splits * N * K, device=dy.device, dtype=torch.float32) if splits > 1 else None
+    dbws = _colsum_ws(M, N, dy.device) if need_bias else None
     _w(2.0 * M * N * K, 4.0 * (M * N + M * K + N * K))
     _call("xm_linear_wgrad_f32", _p(dy), _p(x), _p(dw), _p(db), M, N, K, dy.stride(0), x.stride(0), dw.stride(0),
-          splits, _p(ws), _stream())
+          splits, _p(ws), _p(dbws), _stream())
     return dw, db
 
 
@@ -238,8 +239,9 @@ def conv1d_wgrad(dy, x, taps, need_bias=True):
     dw = torch.empty(Cout, Cin, taps, device=dy.device, dtype=torch.float32)
     db = torch.empty(Cout, device=dy.device, dtype=torch.float32) if need_bias else None
     _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cin + Cout) + taps * Cin * Cout))
+    dbws = _colsum_ws(B * T, Cout, dy.device) if need_bias else None
     _call("xm_conv1d_wgrad_f32", _p(dy), _p(x), _p(dw), _p(db), B, Cin, Cout, T, taps, dy.stride(1), x.stride(1),
-          _p(ws), _stream())
+          _p(ws), _p(dbws), _stream())
     return dw, db
 
 
@@ -394,13 +396,19 @@ def act_bwd(dout, x, act, drop_p=0.0, seed=0):
 
 
 # ------------------------------------------------------------------ reductions
+def _colsum_ws(M, N, device):
+    ns = _lib.lib().xm_colsum_nsplit(M, N)
+    return torch.empty(ns * N, device=device, dtype=torch.float32) if ns > 1 else None
+
+
 def colsum(x):
     _chk(x)
     M, N = x.shape
     assert x.stride(1) == 1
     out = torch.empty(N, device=x.device, dtype=torch.float32)
+    ws = _colsum_ws(M, N, x.device)
     _w(M * N, 4.0 * (M * N + N))
-    _call("xm_colsum_f32", _p(x), M, N, x.stride(0), _p(out), _stream())
+    _call("xm_colsum_f32", _p(x), M, N, x.stride(0), _p(out), _p(ws), _stream())
     return out
 
 
