@@ -2,10 +2,11 @@
 //
 //   D[m, n] (+)= sum over k-blocks of  A_tile[m, 32] * B_tile[n, 32]^T      (fp32 accumulate in TMEM)
 //
-// One CTA computes one 128 x BN output tile (or `taps_n` of them, one TMEM accumulator per
-// conv tap, for the conv weight gradient).  Warp roles: warp 0 = TMA producer (one lane),
-// warp 1 = TMEM allocator + tcgen05.mma issuer (one lane), warps 2..5 = epilogue
-// (TMEM -> registers -> global).  Operand tiles are fetched by TMA (cp.async.bulk.tensor.3d)
+// Persistent kernel: one CTA per SM walks 128 x BN output tiles (or `taps_n` of them, one TMEM
+// accumulator per conv tap, for the conv weight gradient).  Warp roles: warp 0 = TMA producer (one
+// lane), warp 1 = TMEM allocator + tcgen05.mma issuer (one lane), warps 2..5 = epilogue
+// (TMEM -> registers -> 128B-swizzled smem -> TMA store).  Two accumulator sets in TMEM let the
+// epilogue of tile i overlap the loads and MMAs of tile i+1.  Operand tiles are fetched by TMA (cp.async.bulk.tensor.3d)
 // into 128B-swizzled shared memory and consumed directly by tcgen05.mma.kind::tf32 through
 // shared-memory descriptors; fp32 data is used as-is (the tensor core reads the tf32 bits).
 //
@@ -41,14 +42,18 @@ struct GemmParams {
   int taps_k;      // taps iterated inside the K loop (conv fwd / dgrad), >= 1
   int taps_n;      // taps held as separate accumulators (conv wgrad), >= 1
   int kin_count;   // inner k-blocks per (kout, tap)
-  int kout_count;  // outer k iterations per CTA (split along gridDim.z when kout_split != 0)
+  int kout_count;  // outer k iterations per tile (split along the z tile index when kout_split != 0)
   int kout_total;  // total outer k iterations (only used when kout_split != 0)
-  int kout_split;  // 1: blockIdx.z selects a kout range [bz*kout_count, ...)
+  int kout_split;  // 1: the z tile index selects a kout range [bz*kout_count, ...)
   int stages;
-  int tmem_cols;
+  int tmem_cols;   // allocated TMEM columns (power of two)
+  int acc_bufs;    // 1 or 2 accumulator sets of taps_n*bn columns (2: epilogue of tile i overlaps MMA of tile i+1)
+  int nx, ny, nz;  // tile grid (persistent CTAs walk tile = by + ny*(bx + nx*bz))
   // epilogue
-  int M, N;  // valid extents of the output (guards)
-  float* c;
+  int M, N;        // valid extents of the output (guards)
+  int tma_store;   // 1: tile staged in swizzled smem and written by TMA through tmC (clips ragged edges)
+  int c_z_mul, c_tap_mul;  // tmC z coordinate = bz*c_z_mul + tn*c_tap_mul
+  float* c;        // direct-store path (outputs TMA cannot address: pitch or base not 16-B aligned)
   long long ldc, c_z_stride, c_tap_stride;
   const float* bias;
   float alpha;
@@ -57,7 +62,7 @@ struct GemmParams {
   // InfoNCE epilogues
   const float* lse_row;
   const float* lse_col;
-  float* partial;  // (gridDim.y, M)
+  float* partial;  // (ny, M)
   float* diag;     // (M)
   int diag_off;
   float coef;
@@ -67,6 +72,7 @@ struct GemmParams {
 constexpr int kGemmThreads = 192;
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 32 tf32
 constexpr int kMaxStages = 8;
+constexpr int kStagingBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 32 fp32)
 
 XM_DEVICE void issue_operand_loads(const CUtensorMap* tm, uint64_t* bar, uint8_t* dst, const OperandCfg& o, int c0,
                                    int c1, int c2) {
@@ -78,43 +84,59 @@ XM_DEVICE void issue_operand_loads(const CUtensorMap* tm, uint64_t* bar, uint8_t
   }
 }
 
+struct TileCoord {
+  int bx, by, bz, kout_lo, kout_n;
+};
+XM_DEVICE TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  t.by = tile % p.ny;
+  const int r = tile / p.ny;
+  t.bx = r % p.nx;
+  t.bz = r / p.nx;
+  t.kout_lo = 0;
+  t.kout_n = p.kout_count;
+  if (p.kout_split) {
+    t.kout_lo = t.bz * p.kout_count;
+    t.kout_n = min(p.kout_count, p.kout_total - t.kout_lo);
+  }
+  return t;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+  const int ntiles = p.nx * p.ny * p.nz;
 
-  int kout_n = p.kout_count;
-  int kout_lo = 0;
-  if (p.kout_split) {
-    kout_lo = bz * p.kout_count;
-    kout_n = min(p.kout_count, p.kout_total - kout_lo);
-  }
-  const int total_kb = kout_n * p.taps_k * p.kin_count;
-  if (total_kb <= 0) return;  // host never launches such a CTA; uniform early-out keeps it safe
-
-  // 1024-B aligned operand ring (128B swizzle atoms are 1024 B)
+  // 1024-B aligned operand ring (128B swizzle atoms are 1024 B), then the epilogue staging buffers
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int b_tile_bytes = p.bn * 128;
   const int stage_bytes = kATileBytes + p.taps_n * b_tile_bytes;
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
+  const int acc_cols = p.taps_n * p.bn;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (p.tma_store) ptx::prefetch_tensormap(&tmC);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(&tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full_bar[b], 1);
+      ptx::mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -129,33 +151,36 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA producer
-      int ca[3], cb[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        ca[d] = p.a.base[d] + bx * p.a.sx[d] + by * p.a.sy[d] + bz * p.a.sz[d];
-        cb[d] = p.b.base[d] + bx * p.b.sx[d] + by * p.b.sy[d] + bz * p.b.sz[d];
-      }
       int s = 0;
       uint32_t ph = 0;
-      for (int ko = 0; ko < kout_n; ++ko) {
-        const int kout = kout_lo + ko;
-        for (int tk = 0; tk < p.taps_k; ++tk) {
-          for (int kin = 0; kin < p.kin_count; ++kin) {
-            ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-            uint8_t* sa = smem + (size_t)s * stage_bytes;
-            issue_operand_loads(&tmA, &full_bar[s], sa, p.a,
-                                ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0] + tk * p.a.tap_step[0],
-                                ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + tk * p.a.tap_step[1],
-                                ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2] + tk * p.a.tap_step[2]);
-            for (int tn = 0; tn < p.taps_n; ++tn) {
-              const int tap = tk + tn;  // exactly one of taps_k / taps_n exceeds 1
-              issue_operand_loads(&tmB, &full_bar[s], sa + kATileBytes + tn * b_tile_bytes, p.b,
-                                  cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tap * p.b.tap_step[0],
-                                  cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tap * p.b.tap_step[1],
-                                  cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tap * p.b.tap_step[2]);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        int ca[3], cb[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          ca[d] = p.a.base[d] + t.bx * p.a.sx[d] + t.by * p.a.sy[d] + t.bz * p.a.sz[d];
+          cb[d] = p.b.base[d] + t.bx * p.b.sx[d] + t.by * p.b.sy[d] + t.bz * p.b.sz[d];
+        }
+        for (int ko = 0; ko < t.kout_n; ++ko) {
+          const int kout = t.kout_lo + ko;
+          for (int tk = 0; tk < p.taps_k; ++tk) {
+            for (int kin = 0; kin < p.kin_count; ++kin) {
+              ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+              ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+              uint8_t* sa = smem + (size_t)s * stage_bytes;
+              issue_operand_loads(&tmA, &full_bar[s], sa, p.a,
+                                  ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0] + tk * p.a.tap_step[0],
+                                  ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + tk * p.a.tap_step[1],
+                                  ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2] + tk * p.a.tap_step[2]);
+              for (int tn = 0; tn < p.taps_n; ++tn) {
+                const int tap = tk + tn;  // exactly one of taps_k / taps_n exceeds 1
+                issue_operand_loads(&tmB, &full_bar[s], sa + kATileBytes + tn * b_tile_bytes, p.b,
+                                    cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tap * p.b.tap_step[0],
+                                    cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tap * p.b.tap_step[1],
+                                    cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tap * p.b.tap_step[2]);
+              }
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
       }
@@ -174,109 +199,178 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t b_lt = p.b.mn_major ? 1u : 2u;
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < total_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[s], ph);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const TileCoord t = decode_tile(p, tile);
+        const int total_kb = t.kout_n * p.taps_k * p.kin_count;
+        const int buf = (p.acc_bufs == 2) ? (it & 1) : 0;
+        const uint32_t use = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it);
+        ptx::mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator set
         ptx::tc_fence_after_sync();
-        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-        for (int tn = 0; tn < p.taps_n; ++tn) {
-          const uint32_t sb = sa + kATileBytes + tn * b_tile_bytes;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+          for (int tn = 0; tn < p.taps_n; ++tn) {
+            const uint32_t sb = sa + kATileBytes + tn * b_tile_bytes;
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) {
-            const uint64_t da = ptx::make_smem_desc(sa + k8 * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t db = ptx::make_smem_desc(sb + k8 * b_kstep, b_lbo, b_sbo, b_lt);
-            ptx::mma_tf32_ss(tmem_base + (uint32_t)(tn * p.bn), da, db, idesc, (kb > 0 || k8 > 0) ? 1u : 0u);
+            for (int k8 = 0; k8 < 4; ++k8) {
+              const uint64_t da = ptx::make_smem_desc(sa + k8 * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t db = ptx::make_smem_desc(sb + k8 * b_kstep, b_lbo, b_sbo, b_lt);
+              ptx::mma_tf32_ss(acc + (uint32_t)(tn * p.bn), da, db, idesc, (kb > 0 || k8 > 0) ? 1u : 0u);
+            }
           }
+          ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        ptx::mma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      ptx::mma_commit(&tmem_full_bar);  // accumulator complete
     }
   } else {
     // -------------------------------------------------- epilogue warps 2..5
-    ptx::mbar_wait(&tmem_full_bar, 0);
-    ptx::tc_fence_after_sync();
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
-    const int m = bx * 128 + row;  // row index inside this z-slab
-    const bool row_ok = m < p.M;
-    const int n0 = by * p.bn;
+    uint8_t* stg = staging + q * 8192;  // this warp's two 4-KB staging buffers
+    int chunk_ctr = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile);
+      const int buf = (p.acc_bufs == 2) ? (it & 1) : 0;
+      const uint32_t use = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it);
+      ptx::mbar_wait(&tmem_full_bar[buf], use & 1u);
+      ptx::tc_fence_after_sync();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols) + ((uint32_t)(q * 32) << 16);
+      const int m = t.bx * 128 + row;  // row index inside this z-slab
+      const bool row_ok = m < p.M;
+      const int n0 = t.by * p.bn;
 
-    float lse_r = 0.f;
-    if (EPI == EPI_NCE_GRAD && row_ok) lse_r = p.lse_row[m];
-    float rowsum = 0.f;
+      float lse_r = 0.f;
+      if (EPI == EPI_NCE_GRAD && row_ok) lse_r = p.lse_row[m];
+      float rowsum = 0.f;
 
-    for (int tn = 0; tn < p.taps_n; ++tn) {
-      float* cbase = p.c ? p.c + (long long)bz * p.c_z_stride + (long long)tn * p.c_tap_stride : nullptr;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tn * p.bn + c0), r);
-        ptx::tmem_ld_wait();
-        if (EPI == EPI_ROWMAJOR) {
-          if (row_ok) {
-            float* crow = cbase + (long long)m * p.ldc + n0 + c0;
-            float v[16];
+      for (int tn = 0; tn < p.taps_n; ++tn) {
+        if (EPI != EPI_LSE && p.tma_store) {
+          // ---- 32-column chunks: TMEM -> registers -> swizzled smem -> TMA store (edges clipped by TMA)
+          const int zc = t.bz * p.c_z_mul + tn * p.c_tap_mul;
+          for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            if (n0 + c0 >= p.N) break;  // warp-uniform: chunk entirely outside the output
+            uint32_t r[32];
+            if (c0 + 32 <= p.bn) {
+              ptx::tmem_ld_32x32(acc + (uint32_t)(tn * p.bn + c0), r);
+            } else {  // bn % 32 == 16 tail
+              uint32_t h[16];
+              ptx::tmem_ld_32x16(acc + (uint32_t)(tn * p.bn + c0), h);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = n0 + c0 + j;
-              float x = __uint_as_float(r[j]) * p.alpha;
-              if (p.bias != nullptr && n < p.N) x += p.bias[n];
-              x = apply_act(x, p.act);
-              if (p.round_tf32) x = round_tf32(x);
-              v[j] = x;
+              for (int j = 0; j < 16; ++j) { r[j] = h[j]; r[16 + j] = 0u; }
             }
-            const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + 16 <= p.N);
-            if (vec) {
+            ptx::tmem_ld_wait();
+            // Straight-line code here is executed once per chunk by a single warp per scheduler, so its
+            // SIZE matters (instruction fetch): every runtime switch is hoisted out of the element loop.
+            float v[32];
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+            const int nb = n0 + c0;
+            if (EPI == EPI_ROWMAJOR) {
+              if (p.bias != nullptr) {
+                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0)) {
+                  const float4* b4 = reinterpret_cast<const float4*>(p.bias + nb);
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c0 + j < p.N) crow[j] = v[j];
-            }
-          }
-        } else if (EPI == EPI_LSE) {
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(b4 + j);
+                    v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                  }
+                } else {
+                  const float bl = (nb + lane < p.N) ? __ldg(p.bias + nb + lane) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            if (row_ok && n < p.N) {
-              const float s = __uint_as_float(r[j]) * p.alpha;
-              rowsum += __expf(s - p.shift);
-              if (n == m + p.diag_off) p.diag[m] = s;
-            }
-          }
-        } else {  // EPI_NCE_GRAD
-          if (row_ok) {
-            float* crow = cbase + (long long)m * p.ldc + n0 + c0;
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = n0 + c0 + j;
-              float g = 0.f;
-              if (n < p.N) {
-                const float s = __uint_as_float(r[j]) * p.alpha;
-                g = __expf(s - lse_r) + __expf(s - p.lse_col[n]);
-                if (n == m + p.diag_off) g -= 2.0f;
-                g = round_tf32(g * p.coef);
+                  for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+                }
               }
-              v[j] = g;
+              if (p.act == XM_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+              } else if (p.act == XM_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              } else if (p.act != XM_ACT_NONE) {
+#pragma unroll 1
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+              }
+              if (p.round_tf32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+              }
+            } else {  // EPI_NCE_GRAD
+              const float lc = (nb + lane < p.N) ? __ldg(p.lse_col + nb + lane) : 0.f;
+              const int dj = m + p.diag_off - nb;  // column of this row's positive inside the chunk (if in [0, 32))
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float lcj = __shfl_sync(0xffffffffu, lc, j);
+                float g = __expf(v[j] - lse_r) + __expf(v[j] - lcj);
+                if (j == dj) g -= 2.0f;
+                v[j] = round_tf32(g * p.coef);  // rows / columns outside the matrix are clipped by the TMA store
+              }
             }
-            const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + 16 <= p.N);
-            if (vec) {
+            uint8_t* sb = stg + (chunk_ctr & 1) * 4096;
+            if (lane == 0) ptx::bulk_wait_read<1>();  // the store that last read this buffer has drained it
+            __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+            for (int j = 0; j < 8; ++j)  // 16-B chunk j of row `lane` lives at chunk j ^ (lane & 7) (SWIZZLE_128B)
+              *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_3d(&tmC, sb, n0 + c0, t.bx * 128 + q * 32, zc);
+              ptx::bulk_commit();
+            }
+            ++chunk_ctr;
+          }
+        } else {
+          float* cbase = p.c ? p.c + (long long)t.bz * p.c_z_stride + (long long)tn * p.c_tap_stride : nullptr;
+          for (int c0 = 0; c0 < p.bn; c0 += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x16(acc + (uint32_t)(tn * p.bn + c0), r);
+            ptx::tmem_ld_wait();
+            if (EPI == EPI_LSE) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + c0 + j < p.N) crow[j] = v[j];
+              for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                if (row_ok && n < p.N) {
+                  const float sv = __uint_as_float(r[j]) * p.alpha;
+                  rowsum += __expf(sv - p.shift);
+                  if (n == m + p.diag_off) p.diag[m] = sv;
+                }
+              }
+            } else if (row_ok) {
+              float* crow = cbase + (long long)m * p.ldc + n0 + c0;
+#pragma unroll 1
+              for (int j = 0; j < 16; ++j) {  // small / unaligned outputs only: compact code over speed
+                const int n = n0 + c0 + j;
+                if (n >= p.N) break;
+                float x = __uint_as_float(r[j]) * p.alpha;
+                if (EPI == EPI_ROWMAJOR) {
+                  if (p.bias != nullptr) x += __ldg(p.bias + n);
+                  x = apply_act(x, p.act);
+                  if (p.round_tf32) x = round_tf32(x);
+                } else {
+                  float g = __expf(x - lse_r) + __expf(x - __ldg(p.lse_col + n));
+                  if (n == m + p.diag_off) g -= 2.0f;
+                  x = round_tf32(g * p.coef);
+                }
+                crow[j] = x;
+              }
             }
           }
         }
       }
+      if (EPI == EPI_LSE && row_ok) p.partial[(long long)t.by * p.M + m] = rowsum;
+      // hand the accumulator set back to the MMA warp
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
     }
-    if (EPI == EPI_LSE && row_ok) p.partial[(long long)by * p.M + m] = rowsum;
+    if (lane == 0) ptx::bulk_wait_all();  // staged tiles fully written before the CTA (and its smem) retires
   }
 
   ptx::tc_fence_before_sync();
@@ -295,7 +389,10 @@ struct TensorView3 {
 };
 
 int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major);
-int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, GemmParams& p, dim3 grid, cudaStream_t stream);
+// `tc` describes the output for the TMA-store epilogue (dims {N, M, Z}); pass ptr == nullptr to use
+// the direct-store path (p.c / p.ldc).  `grid` is the TILE grid; the launch is persistent.
+int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
+                cudaStream_t stream);
 
 inline int tmem_cols_for(int n) {
   int c = 32;

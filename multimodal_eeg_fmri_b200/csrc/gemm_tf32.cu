@@ -60,48 +60,64 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
 }
 
 template <int EPI>
-static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, dim3 grid, size_t smem,
-                      cudaStream_t stream) {
+static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p, int ctas,
+                      size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
-  gemm_tf32_kernel<EPI><<<grid, kGemmThreads, smem, stream>>>(ma, mb, p);
+  gemm_tf32_kernel<EPI><<<ctas, kGemmThreads, smem, stream>>>(ma, mb, mc, p);
   return check_launch();
 }
 
-int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, GemmParams& p, dim3 grid, cudaStream_t stream) {
+int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
+                cudaStream_t stream) {
   if (p.bn < 16 || p.bn > 256 || (p.bn & 15)) return XM_ERR_UNSUPPORTED;
   if (p.b.mn_major && (p.bn & 31)) return XM_ERR_UNSUPPORTED;
   if (p.taps_n * p.bn > 512) return XM_ERR_UNSUPPORTED;
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return XM_OK;
+  const long long ntiles = (long long)grid.x * grid.y * grid.z;
+  if (ntiles > 2000000000ll) return XM_ERR_UNSUPPORTED;
+  p.nx = (int)grid.x;
+  p.ny = (int)grid.y;
+  p.nz = (int)grid.z;
+  // TMA-store epilogue whenever the output is addressable by a tensor map (16-B aligned base and pitches)
+  p.tma_store = 0;
+  if (epi != EPI_LSE && tc.ptr != nullptr && (reinterpret_cast<uintptr_t>(tc.ptr) & 15) == 0 &&
+      (tc.stride_bytes[0] & 15) == 0 && (tc.stride_bytes[1] & 15) == 0 && !((p.bn & 31) && grid.y > 1))
+    p.tma_store = 1;
+  if (!p.tma_store && epi != EPI_LSE && p.c == nullptr) return XM_ERR_INVALID;
   const int stage_bytes = kATileBytes + p.taps_n * p.bn * 128;
   const int total_kb = p.kout_count * p.taps_k * p.kin_count;
   if (total_kb <= 0) return XM_ERR_INVALID;
-  // Small stages: keep the ring <= ~100 KB so two CTAs share an SM (one's prologue/epilogue
-  // hides behind the other's main loop).  Large stages: one CTA per SM, as deep as fits.
-  int budget = (stage_bytes * 4 <= 100 * 1024) ? 100 * 1024 : 220 * 1024;
-  int stages = budget / stage_bytes;
+  const int staging = p.tma_store ? kStagingBytes : 0;
+  int stages = (225 * 1024 - 1024 - staging) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > total_kb) stages = total_kb < 2 ? 2 : total_kb;
   if (stages < 2) return XM_ERR_UNSUPPORTED;
   p.stages = stages;
-  p.tmem_cols = tmem_cols_for(p.taps_n * p.bn);
+  const int acc_cols = p.taps_n * p.bn;
+  p.acc_bufs = (2 * acc_cols <= 512 && ntiles > 1) ? 2 : 1;
+  p.tmem_cols = tmem_cols_for(p.acc_bufs * acc_cols);
   p.a.rows = 128;
   p.b.rows = p.bn;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + staging + 1024;
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
+  memset(&mc, 0, sizeof(mc));
   int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : 128, p.a.mn_major);
   if (rc != XM_OK) return rc;
   rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? 32 : (unsigned)p.bn, p.b.mn_major);
   if (rc != XM_OK) return rc;
-
+  if (p.tma_store) {
+    rc = encode_tmap(&mc, tc, 32, 32, 0);
+    if (rc != XM_OK) return rc;
+  }
+  const int ctas = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   switch (epi) {
-    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, p, grid, smem, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, p, grid, smem, stream);
-    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, p, grid, smem, stream);
+    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, mc, p, ctas, smem, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, mc, p, ctas, smem, stream);
+    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, mc, p, ctas, smem, stream);
   }
   return XM_ERR_INVALID;
 }
@@ -256,7 +272,10 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
   }
   TensorView3 ta{x, {(unsigned long long)K, (unsigned long long)M, 1}, {(unsigned long long)ldx * 4, (unsigned long long)M * ldx * 4}};
   TensorView3 tb{w, {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
-  int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, ceil_div(N, p.bn), splits), st);
+  p.c_z_mul = 1;
+  const TensorView3 tc = splits == 1 ? TensorView3{y, {(unsigned long long)(N), (unsigned long long)(M), (unsigned long long)(1)}, {(unsigned long long)(ldy) * 4, (unsigned long long)(M * ldy) * 4}}
+                                     : TensorView3{workspace, {(unsigned long long)(N), (unsigned long long)(M), (unsigned long long)(splits)}, {(unsigned long long)(N) * 4, (unsigned long long)(M * N) * 4}};
+  int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(N, p.bn), splits), st);
   if (rc != XM_OK || splits == 1) return rc;
   splitk_reduce_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(workspace, splits, M, N, bias, y, ldy, act, round_out);
   return check_launch();
@@ -284,7 +303,8 @@ int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, i
   p.round_tf32 = round_out;
   TensorView3 ta{dy, {(unsigned long long)N, (unsigned long long)M, 1}, {(unsigned long long)lddy * 4, (unsigned long long)M * lddy * 4}};
   TensorView3 tb{w, {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
-  return launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream);
+  const TensorView3 tc = TensorView3{dx, {(unsigned long long)(K), (unsigned long long)(M), (unsigned long long)(1)}, {(unsigned long long)(lddx) * 4, (unsigned long long)(M * lddx) * 4}};
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream);
 }
 
 int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
@@ -323,7 +343,10 @@ int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
   }
   TensorView3 ta{dy, {(unsigned long long)N, (unsigned long long)M, 1}, {(unsigned long long)lddy * 4, (unsigned long long)M * lddy * 4}};
   TensorView3 tb{x, {(unsigned long long)K, (unsigned long long)M, 1}, {(unsigned long long)ldx * 4, (unsigned long long)M * ldx * 4}};
-  int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, ceil_div(K, p.bn), splits), st);
+  p.c_z_mul = 1;
+  const TensorView3 tc = splits == 1 ? TensorView3{dw, {(unsigned long long)(K), (unsigned long long)(N), (unsigned long long)(1)}, {(unsigned long long)(lddw) * 4, (unsigned long long)(N * lddw) * 4}}
+                                     : TensorView3{workspace, {(unsigned long long)(K), (unsigned long long)(N), (unsigned long long)(splits)}, {(unsigned long long)(K) * 4, (unsigned long long)(N * K) * 4}};
+  int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(K, p.bn), splits), st);
   if (rc != XM_OK) return rc;
   if (splits > 1) {
     splitk_reduce_kernel<<<grid_for(N * K, 256), 256, 0, st>>>(workspace, splits, N, K, nullptr, dw, lddw, XM_ACT_NONE, 0);
@@ -384,7 +407,9 @@ static int conv_like(const float* in, const float* wp, const float* bias, float*
                  {(unsigned long long)ld_in * 4, (unsigned long long)T * ld_in * 4}};
   TensorView3 tb{wp, {(unsigned long long)Kc, (unsigned long long)Nc, (unsigned long long)taps},
                  {(unsigned long long)ld_w * 4, (unsigned long long)Nc * ld_w * 4}};
-  return launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(t_tiles, ceil_div(Nc, p.bn), (unsigned)B), st);
+  p.c_z_mul = 1;
+  const TensorView3 tc = TensorView3{out, {(unsigned long long)(Nc), (unsigned long long)(T), (unsigned long long)(B)}, {(unsigned long long)(ld_out) * 4, (unsigned long long)(T * ld_out) * 4}};
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(t_tiles, ceil_div(Nc, p.bn), (unsigned)B), st);
 }
 
 int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,
@@ -468,7 +493,8 @@ int xm_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, i
                    {(unsigned long long)lddy * 4, (unsigned long long)T * lddy * 4}};
     TensorView3 tb{x, {(unsigned long long)Cin, (unsigned long long)T, (unsigned long long)B},
                    {(unsigned long long)ldx * 4, (unsigned long long)T * ldx * 4}};
-    int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(m_tiles, 1, pl.splits), st);
+    const TensorView3 tc{nullptr, {0, 0, 0}, {0, 0}};  // direct-store epilogue: one tile per CTA, all smem for the ring
+    int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, 1, pl.splits), st);
     if (rc != XM_OK) return rc;
   }
   conv_wgrad_reduce_kernel<<<grid_for(Cout * Cin * taps, 256), 256, 0, st>>>(workspace, pl.splits, (int)taps, (int)Cout,
@@ -504,7 +530,8 @@ int xm_similarity_f32(const float* a, const float* b, float* S, int64_t Ml, int6
   p.alpha = inv_tau;
   TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
   TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
-  return launch_gemm(EPI_ROWMAJOR, ta, tb, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, p.bn), 1), (cudaStream_t)stream);
+  const TensorView3 tc = TensorView3{S, {(unsigned long long)(Ng), (unsigned long long)(Ml), (unsigned long long)(1)}, {(unsigned long long)(Ng) * 4, (unsigned long long)(Ml * Ng) * 4}};
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, p.bn), 1), (cudaStream_t)stream);
 }
 
 int xm_infonce_tile_n(void) { return 128; }
@@ -527,7 +554,8 @@ int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, 
   const int ntiles = ceil_div(Ng, 128);
   TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
   TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
-  int rc = launch_gemm(EPI_LSE, ta, tb, p, dim3(ceil_div(Ml, 128), ntiles, 1), st);
+  const TensorView3 tc{nullptr, {0, 0, 0}, {0, 0}};
+  int rc = launch_gemm(EPI_LSE, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ntiles, 1), st);
   if (rc != XM_OK) return rc;
   lse_finalize_kernel<<<ceil_div(Ml, 256), 256, 0, st>>>(workspace, ntiles, Ml, inv_tau, lse);
   return check_launch();
@@ -552,7 +580,8 @@ int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, co
   p.coef = coef;
   TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
   TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
-  return launch_gemm(EPI_NCE_GRAD, ta, tb, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, 128), 1), (cudaStream_t)stream);
+  const TensorView3 tc = TensorView3{G, {(unsigned long long)(Ng), (unsigned long long)(Ml), (unsigned long long)(1)}, {(unsigned long long)(Ng) * 4, (unsigned long long)(Ml * Ng) * 4}};
+  return launch_gemm(EPI_NCE_GRAD, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, 128), 1), (cudaStream_t)stream);
 }
 
 }  // extern "C"
