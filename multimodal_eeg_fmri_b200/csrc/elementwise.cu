@@ -424,6 +424,57 @@ __global__ void act_bwd_kernel(const float* __restrict__ dout, const float* __re
   }
 }
 
+// float4 variants (n % 4 == 0, 16-B aligned)
+__global__ void act_fwd_v4_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4, int act,
+                                  float drop_scale, uint32_t drop_thresh, uint64_t seed, int round_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (act == XM_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = gelu_erf(o[j]);
+    } else if (act != XM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = apply_act(o[j], act);
+    }
+    if (drop_thresh) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = dropout_keep((uint64_t)(4 * i + j), seed, drop_thresh) ? o[j] * drop_scale : 0.f;
+    }
+    if (round_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = round_tf32(o[j]);
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+__global__ void act_bwd_v4_kernel(const float* __restrict__ dout, const float* __restrict__ x, float* __restrict__ dx,
+                                  long long n4, int act, float drop_scale, uint32_t drop_thresh, uint64_t seed,
+                                  int round_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 gv = reinterpret_cast<const float4*>(dout)[i];
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    float g[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (drop_thresh) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = dropout_keep((uint64_t)(4 * i + j), seed, drop_thresh) ? g[j] * drop_scale : 0.f;
+    }
+    if (act == XM_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] *= gelu_erf_grad(xs[j]);
+    } else if (act != XM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] *= act_grad(xs[j], act);
+    }
+    if (round_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = round_tf32(g[j]);
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(g[0], g[1], g[2], g[3]);
+  }
+}
+
 // ------------------------------------------------------------------ small reductions
 // out[n] = sum_m x[m, n] in two deterministic stages: block (bx, by) sums rows [by*chunk, (by+1)*chunk)
 // of columns [32 bx, 32 bx + 32) into part[by][n] (or straight into out when gridDim.y == 1); a second
@@ -453,6 +504,46 @@ __global__ void colsum_kernel(const float* __restrict__ x, long long M, long lon
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += sm[i][tx];
     out[blockIdx.y * N + n] = s;
+  }
+}
+
+// float4 variant (N % 4 == 0, 16-B aligned rows): block = 32 column quads x 8 row lanes = 128 columns
+__global__ void colsum_v4_kernel(const float* __restrict__ x, long long M, long long N, long long ld, long long chunk,
+                                 float* __restrict__ out) {
+  __shared__ float4 sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long n = blockIdx.x * 128ll + 4 * tx;
+  const long long m0 = blockIdx.y * chunk;
+  const long long m1 = min(M, m0 + chunk);
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) {
+    const float* base = x + n;
+    long long m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 v = *reinterpret_cast<const float4*>(base + (m + 8 * u) * ld);
+        acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+      }
+    }
+    for (; m < m1; m += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(base + m * ld);
+      acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+    }
+  }
+  sm[ty][tx] = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                           (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 v = sm[i][tx];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + blockIdx.y * N + n) = t;
   }
 }
 
@@ -511,6 +602,320 @@ static bool bn_args_ok(const void* y, const void* m, const void* is, const void*
   return true;
 }
 
+// ------------------------------------------------------------------ vectorised BatchNorm path (C % 4 == 0)
+// Thread (tx, ty): tx owns 4 consecutive channels (one float4) of every row it visits, ty strides over
+// rows, so the per-channel constants live in registers and there is no index division per element.
+// A warp covers whole 16-B aligned row segments: 128-bit coalesced loads/stores.  Rows are unrolled
+// x4 for memory-level parallelism (HBM latency x bandwidth needs ~32 KB in flight per SM).
+struct F4 {
+  float v[4];
+};
+XM_DEVICE F4 ld4(const float* p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  return F4{{t.x, t.y, t.z, t.w}};
+}
+XM_DEVICE void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+
+template <int ACT>
+XM_DEVICE float act_c(float x, int act) {
+  if (ACT == XM_ACT_NONE) return x;
+  if (ACT == XM_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == XM_ACT_GELU) return gelu_erf(x);
+  return apply_act(x, act);
+}
+template <int ACT>
+XM_DEVICE float actg_c(float x, int act) {
+  if (ACT == XM_ACT_NONE) return 1.f;
+  if (ACT == XM_ACT_RELU) return x > 0.f ? 1.f : 0.f;
+  if (ACT == XM_ACT_GELU) return gelu_erf_grad(x);
+  return act_grad(x, act);
+}
+
+// grid (nsplit), block (C/4, RY)
+__global__ void bn_partial_stats_v4_kernel(const float* __restrict__ y, long long R, int C, long long ld,
+                                           long long rows_per_split, double* __restrict__ partials) {
+  extern __shared__ double smd[];  // [RY][C][2]
+  const int tx = threadIdx.x, ty = threadIdx.y, RY = blockDim.y;
+  const long long r0 = blockIdx.x * rows_per_split;
+  const long long r1 = min(R, r0 + rows_per_split);
+  double sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+  float ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0};
+  int n = 0;
+  const float* base = y + 4 * tx;
+  long long r = r0 + ty;
+  for (; r + 3ll * RY < r1; r += 4ll * RY) {
+    F4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = ld4(base + (r + (long long)u * RY) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ps[j] += a[u].v[j];
+        pq[j] += a[u].v[j] * a[u].v[j];
+      }
+    if (++n == 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sum[j] += (double)ps[j]; sq[j] += (double)pq[j];
+        ps[j] = 0.f; pq[j] = 0.f;
+      }
+      n = 0;
+    }
+  }
+  for (; r < r1; r += RY) {
+    const F4 a = ld4(base + r * ld);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ps[j] += a.v[j];
+      pq[j] += a.v[j] * a.v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sum[j] += (double)ps[j];
+    sq[j] += (double)pq[j];
+    smd[((long long)ty * C + 4 * tx + j) * 2 + 0] = sum[j];
+    smd[((long long)ty * C + 4 * tx + j) * 2 + 1] = sq[j];
+  }
+  __syncthreads();
+  const int tid = ty * blockDim.x + tx;
+  for (int c = tid; c < C; c += blockDim.x * RY) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < RY; ++i) {
+      s += smd[((long long)i * C + c) * 2 + 0];
+      q += smd[((long long)i * C + c) * 2 + 1];
+    }
+    partials[((long long)blockIdx.x * C + c) * 2 + 0] = s;
+    partials[((long long)blockIdx.x * C + c) * 2 + 1] = q;
+  }
+}
+
+struct ChanConst {
+  float sc[4], sh[4], mu[4], is[4];
+};
+XM_DEVICE ChanConst chan_consts(const BnActArgs& a, int c0) {
+  ChanConst k;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k.mu[j] = a.mean[c0 + j];
+    k.is[j] = a.invstd[c0 + j];
+    k.sc[j] = a.gamma[c0 + j] * k.is[j];
+    k.sh[j] = a.beta[c0 + j] - k.mu[j] * k.sc[j];
+  }
+  return k;
+}
+
+// forward: grid-stride over OUTPUT rows; block (C/4, RY)
+template <int ACT, int POOL>
+__global__ void bn_act_fwd_v4_kernel(const BnActArgs a, long long R_out, float* __restrict__ out) {
+  const int tx = threadIdx.x, c0 = 4 * tx;
+  const ChanConst k = chan_consts(a, c0);
+  const long long To = a.T / 2;
+  const long long stride = (long long)gridDim.x * blockDim.y;
+  for (long long ro = blockIdx.x * (long long)blockDim.y + threadIdx.y; ro < R_out; ro += stride) {
+    F4 o;
+    if (POOL == 2) {
+      const long long b = ro / To, tp = ro - b * To;
+      const long long r0 = b * a.T + 2 * tp;
+      const F4 x0 = ld4(a.y + r0 * a.ldy + c0), x1 = ld4(a.y + (r0 + 1) * a.ldy + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a0 = act_c<ACT>(x0.v[j] * k.sc[j] + k.sh[j], a.act);
+        float a1 = act_c<ACT>(x1.v[j] * k.sc[j] + k.sh[j], a.act);
+        if (a.drop_thresh) {
+          if (a.drop_before_pool) {
+            a0 *= drop_mul(a, r0 * a.C + c0 + j);
+            a1 *= drop_mul(a, (r0 + 1) * a.C + c0 + j);
+            o.v[j] = fmaxf(a0, a1);
+          } else {
+            o.v[j] = fmaxf(a0, a1) * drop_mul(a, ro * a.C + c0 + j);
+          }
+        } else {
+          o.v[j] = fmaxf(a0, a1);
+        }
+      }
+    } else {
+      const F4 x0 = ld4(a.y + ro * a.ldy + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = act_c<ACT>(x0.v[j] * k.sc[j] + k.sh[j], a.act);
+        if (a.drop_thresh) v *= drop_mul(a, ro * a.C + c0 + j);
+        o.v[j] = v;
+      }
+    }
+    if (a.round_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o.v[j] = round_tf32(o.v[j]);
+    }
+    st4(out + ro * a.ldo + c0, o);
+  }
+}
+
+// dz of the (up to) two input rows behind output row ro, 4 channels at once
+template <int ACT, int POOL>
+XM_DEVICE void bn_dz4(const BnActArgs& a, const ChanConst& k, const float* __restrict__ dout, long long ro, int c0,
+                      long long& r0, F4& x0, F4& x1, F4& dz0, F4& dz1) {
+  const F4 g = ld4(dout + ro * a.ldo + c0);
+  if (POOL == 2) {
+    const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+    r0 = b * a.T + 2 * tp;
+    x0 = ld4(a.y + r0 * a.ldy + c0);
+    x1 = ld4(a.y + (r0 + 1) * a.ldy + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float z0 = x0.v[j] * k.sc[j] + k.sh[j], z1 = x1.v[j] * k.sc[j] + k.sh[j];
+      float a0 = act_c<ACT>(z0, a.act), a1 = act_c<ACT>(z1, a.act);
+      float m0 = 1.f, m1 = 1.f, gg = g.v[j];
+      if (a.drop_thresh) {
+        if (a.drop_before_pool) {
+          m0 = drop_mul(a, r0 * a.C + c0 + j);
+          m1 = drop_mul(a, (r0 + 1) * a.C + c0 + j);
+          a0 *= m0;
+          a1 *= m1;
+        } else {
+          gg *= drop_mul(a, ro * a.C + c0 + j);
+        }
+      }
+      const bool first = a0 >= a1;  // ties -> first element, as torch max_pool1d
+      dz0.v[j] = first ? gg * m0 * actg_c<ACT>(z0, a.act) : 0.f;
+      dz1.v[j] = first ? 0.f : gg * m1 * actg_c<ACT>(z1, a.act);
+    }
+  } else {
+    r0 = ro;
+    x0 = ld4(a.y + ro * a.ldy + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gg = g.v[j];
+      if (a.drop_thresh) gg *= drop_mul(a, ro * a.C + c0 + j);
+      dz0.v[j] = gg * actg_c<ACT>(x0.v[j] * k.sc[j] + k.sh[j], a.act);
+      dz1.v[j] = 0.f;
+      x1.v[j] = 0.f;
+    }
+  }
+}
+
+// grid (nsplit), block (C/4, RY) over OUTPUT rows: partial sums of dz and dz*xhat
+template <int ACT, int POOL>
+__global__ void bn_act_bwd_reduce_v4_kernel(const BnActArgs a, const float* __restrict__ dout, long long R_out,
+                                            long long rows_per_split, double* __restrict__ partials) {
+  extern __shared__ double smd[];  // [RY][C][2]
+  const int tx = threadIdx.x, ty = threadIdx.y, RY = blockDim.y, c0 = 4 * tx;
+  const ChanConst k = chan_consts(a, c0);
+  const long long r_lo = blockIdx.x * rows_per_split;
+  const long long r_hi = min(R_out, r_lo + rows_per_split);
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  float p0[4] = {0, 0, 0, 0}, p1[4] = {0, 0, 0, 0};
+  int n = 0;
+  for (long long ro = r_lo + ty; ro < r_hi; ro += RY) {
+    long long r0;
+    F4 x0, x1, dz0, dz1;
+    bn_dz4<ACT, POOL>(a, k, dout, ro, c0, r0, x0, x1, dz0, dz1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p0[j] += dz0.v[j] + dz1.v[j];
+      p1[j] += dz0.v[j] * ((x0.v[j] - k.mu[j]) * k.is[j]) + dz1.v[j] * ((x1.v[j] - k.mu[j]) * k.is[j]);
+    }
+    if (++n == 64) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s0[j] += (double)p0[j]; s1[j] += (double)p1[j];
+        p0[j] = 0.f; p1[j] = 0.f;
+      }
+      n = 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    smd[((long long)ty * a.C + c0 + j) * 2 + 0] = s0[j] + (double)p0[j];
+    smd[((long long)ty * a.C + c0 + j) * 2 + 1] = s1[j] + (double)p1[j];
+  }
+  __syncthreads();
+  const int tid = ty * blockDim.x + tx;
+  for (int c = tid; c < a.C; c += blockDim.x * RY) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < RY; ++i) {
+      s += smd[((long long)i * a.C + c) * 2 + 0];
+      q += smd[((long long)i * a.C + c) * 2 + 1];
+    }
+    partials[((long long)blockIdx.x * a.C + c) * 2 + 0] = s;
+    partials[((long long)blockIdx.x * a.C + c) * 2 + 1] = q;
+  }
+}
+
+template <int ACT, int POOL>
+__global__ void bn_act_bwd_apply_v4_kernel(const BnActArgs a, const float* __restrict__ dout,
+                                           const float* __restrict__ dbeta, const float* __restrict__ dgamma, float inv_n,
+                                           long long R_out, float* __restrict__ dy) {
+  const int tx = threadIdx.x, c0 = 4 * tx;
+  const ChanConst k = chan_consts(a, c0);
+  float k1[4], k2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k1[j] = dbeta[c0 + j] * inv_n;
+    k2[j] = dgamma[c0 + j] * inv_n;
+  }
+  const long long To = a.T / 2;
+  const long long stride = (long long)gridDim.x * blockDim.y;
+  for (long long ro = blockIdx.x * (long long)blockDim.y + threadIdx.y; ro < R_out; ro += stride) {
+    long long r0;
+    F4 x0, x1, dz0, dz1, o0, o1;
+    bn_dz4<ACT, POOL>(a, k, dout, ro, c0, r0, x0, x1, dz0, dz1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o0.v[j] = k.sc[j] * (dz0.v[j] - k1[j] - (x0.v[j] - k.mu[j]) * k.is[j] * k2[j]);
+      o1.v[j] = k.sc[j] * (dz1.v[j] - k1[j] - (x1.v[j] - k.mu[j]) * k.is[j] * k2[j]);
+      if (a.round_out) { o0.v[j] = round_tf32(o0.v[j]); o1.v[j] = round_tf32(o1.v[j]); }
+    }
+    st4(dy + r0 * a.ldy + c0, o0);
+    if (POOL == 2) {
+      st4(dy + (r0 + 1) * a.ldy + c0, o1);
+      const long long b = ro / To, tp = ro - b * To;
+      if ((a.T & 1) && tp == To - 1) {  // odd tail row is dropped by the pool: dz = 0
+        const F4 xt = ld4(a.y + (r0 + 2) * a.ldy + c0);
+        F4 ot;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ot.v[j] = k.sc[j] * (0.f - k1[j] - (xt.v[j] - k.mu[j]) * k.is[j] * k2[j]);
+          if (a.round_out) ot.v[j] = round_tf32(ot.v[j]);
+        }
+        st4(dy + (r0 + 2) * a.ldy + c0, ot);
+      }
+    }
+  }
+}
+
+static bool v4_ok(const void* p0, const void* p1, const void* p2, int64_t C, int64_t ld0, int64_t ld1) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (C % 4 == 0) && C <= 1024 && (ld0 % 4 == 0) && (ld1 % 4 == 0) && al(p0) && al(p1) && al(p2);
+}
+static dim3 v4_block(int64_t C) {
+  const int tx = (int)(C / 4);
+  int ry = 256 / tx;
+  if (ry < 1) ry = 1;
+  return dim3(tx, ry);
+}
+static int v4_grid(long long rows, int ry) {
+  long long b = (rows + ry - 1) / ry;
+  const long long cap = (long long)kNumSMs * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+#define XM_BN_DISPATCH(KERNEL, act, pool, ...)                                                              \
+  do {                                                                                                      \
+    if (pool == 2) {                                                                                        \
+      if (act == XM_ACT_GELU) KERNEL<XM_ACT_GELU, 2> __VA_ARGS__;                                           \
+      else if (act == XM_ACT_RELU) KERNEL<XM_ACT_RELU, 2> __VA_ARGS__;                                      \
+      else if (act == XM_ACT_NONE) KERNEL<XM_ACT_NONE, 2> __VA_ARGS__;                                      \
+      else KERNEL<99, 2> __VA_ARGS__;                                                                       \
+    } else {                                                                                                \
+      if (act == XM_ACT_GELU) KERNEL<XM_ACT_GELU, 0> __VA_ARGS__;                                           \
+      else if (act == XM_ACT_RELU) KERNEL<XM_ACT_RELU, 0> __VA_ARGS__;                                      \
+      else if (act == XM_ACT_NONE) KERNEL<XM_ACT_NONE, 0> __VA_ARGS__;                                      \
+      else KERNEL<99, 0> __VA_ARGS__;                                                                       \
+    }                                                                                                       \
+  } while (0)
+
 static int ew_grid(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = (long long)kNumSMs * 16;
@@ -550,6 +955,12 @@ int xm_bn_partial_stats_f32(const float* y, int64_t R, int64_t C, int64_t ldy, d
   if (!y || !partials || R <= 0 || C <= 0 || ldy < C) return XM_ERR_INVALID;
   const int ns = xm_bn_nsplit(R, C);
   const long long rps = (R + ns - 1) / ns;
+  if (v4_ok(y, nullptr, nullptr, C, ldy, 4)) {
+    const dim3 blk = v4_block(C);
+    bn_partial_stats_v4_kernel<<<ns, blk, blk.y * C * 2 * sizeof(double), (cudaStream_t)stream>>>(y, R, (int)C, ldy, rps,
+                                                                                                partials);
+    return check_launch();
+  }
   dim3 grid(ceil_div(C, 32), (unsigned)ns);
   bn_partial_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, R, (int)C, ldy, rps, partials);
   return check_launch();
@@ -571,6 +982,11 @@ int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, co
   BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);
   const long long R_out = B * (pool == 2 ? T / 2 : T);
+  if (v4_ok(y, out, nullptr, C, ldy, ldo)) {
+    const dim3 blk = v4_block(C);
+    XM_BN_DISPATCH(bn_act_fwd_v4_kernel, act, pool, <<<v4_grid(R_out, blk.y), blk, 0, (cudaStream_t)stream>>>(a, R_out, out));
+    return check_launch();
+  }
   bn_act_fwd_kernel<<<ew_grid(R_out * C), 256, 0, (cudaStream_t)stream>>>(a, R_out, out);
   return check_launch();
 }
@@ -584,6 +1000,12 @@ int xm_bn_act_bwd_reduce_f32(const float* dout, const float* y, const float* mea
   const long long R_out = B * (pool == 2 ? T / 2 : T);
   const int ns = xm_bn_nsplit(B * T, C);  // same split count as the forward statistics
   const long long rps = (R_out + ns - 1) / ns;
+  if (v4_ok(y, dout, nullptr, C, ldy, ldo)) {
+    const dim3 blk = v4_block(C);
+    XM_BN_DISPATCH(bn_act_bwd_reduce_v4_kernel, act, pool,
+                   <<<ns, blk, blk.y * C * 2 * sizeof(double), (cudaStream_t)stream>>>(a, dout, R_out, rps, partials));
+    return check_launch();
+  }
   dim3 grid(ceil_div(C, 32), (unsigned)ns);
   bn_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, dout, R_out, rps, partials);
   return check_launch();
@@ -606,6 +1028,13 @@ int xm_bn_act_bwd_apply_f32(const float* dout, const float* y, const float* mean
   BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);
   const long long R_out = B * (pool == 2 ? T / 2 : T);
+  if (v4_ok(y, dout, dy, C, ldy, ldo)) {
+    const dim3 blk = v4_block(C);
+    XM_BN_DISPATCH(bn_act_bwd_apply_v4_kernel, act, pool,
+                   <<<v4_grid(R_out, blk.y), blk, 0, (cudaStream_t)stream>>>(a, dout, dbeta, dgamma,
+                                                                             (float)(1.0 / total_count), R_out, dy));
+    return check_launch();
+  }
   bn_act_bwd_apply_kernel<<<ew_grid(R_out * C), 256, 0, (cudaStream_t)stream>>>(a, dout, dbeta, dgamma,
                                                                               (float)(1.0 / total_count), R_out, dy);
   return check_launch();
@@ -672,6 +1101,10 @@ int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p,
   float sc;
   uint32_t th;
   drop_consts(drop_p, sc, th);
+  if ((n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    act_fwd_v4_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, out, n / 4, act, sc, th, seed, 0);
+    return check_launch();
+  }
   act_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, out, n, act, sc, th, seed);
   return check_launch();
 }
@@ -681,13 +1114,18 @@ int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int 
   float sc;
   uint32_t th;
   drop_consts(drop_p, sc, th);
+  if ((n % 4 == 0) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+    act_bwd_v4_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(dout, x, dx, n / 4, act, sc, th, seed, 0);
+    return check_launch();
+  }
   act_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dout, x, dx, n, act, sc, th, seed);
   return check_launch();
 }
 
 int xm_colsum_nsplit(int64_t M, int64_t N) {
-  const long long col_blocks = (N + 31) / 32;
-  long long want = (4ll * kNumSMs + col_blocks - 1) / col_blocks;  // ~4 CTAs per SM in total
+  const long long col_blocks = (N + 127) / 128;
+  long long want = (8ll * kNumSMs + col_blocks - 1) / col_blocks;  // ~8 CTAs per SM in total
   const long long max_by_rows = (M + 255) / 256;                   // >= 256 rows per block
   if (want > max_by_rows) want = max_by_rows;
   if (want < 1) want = 1;
@@ -701,8 +1139,12 @@ int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out,
   if (ns > 1 && !workspace) return XM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const long long chunk = (M + ns - 1) / ns;
-  dim3 grid(ceil_div(N, 32), ns);
-  colsum_kernel<<<grid, 256, 0, st>>>(x, M, N, ldx, chunk, ns > 1 ? workspace : out);
+  float* dst = ns > 1 ? workspace : out;
+  if ((N % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    colsum_v4_kernel<<<dim3(ceil_div(N, 128), ns), 256, 0, st>>>(x, M, N, ldx, chunk, dst);
+  } else {
+    colsum_kernel<<<dim3(ceil_div(N, 32), ns), 256, 0, st>>>(x, M, N, ldx, chunk, dst);
+  }
   int rc = check_launch();
   if (rc != XM_OK || ns == 1) return rc;
   colsum_kernel<<<dim3(ceil_div(N, 32), 1), 256, 0, st>>>(workspace, ns, N, N, ns, out);
