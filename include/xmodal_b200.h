@@ -177,6 +177,10 @@ int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p,
 int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
                    void* stream);
 
+/* out = x rounded to nearest tf32 (10-bit mantissa) in an fp32 container: operands handed to the tensor
+ * cores are rounded at their producer so the contraction sees no truncation bias (may run in place). */
+int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream);
+
 /* out (N) = column sums of x (M, N) (bias gradients, partial reductions), deterministic two-stage
  * reduction; workspace: xm_colsum_nsplit(M, N) * N floats (may be NULL when nsplit == 1). */
 int xm_colsum_nsplit(int64_t M, int64_t N);
@@ -203,6 +207,19 @@ int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, 
 int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
                         int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
                         void* stream);
+
+/* ------------------------------------------------------------------ multi-head self-attention core
+ * nn.MultiheadAttention inside TemporalTransformerBlock (EEG_CODE/enhanced_models_v4.py:71-73,98; torch computes
+ * softmax(q k^T / sqrt(dh)), dropout on the weights, times v).  qkv (B, L, 3*H*dh) is the packed in_proj output
+ * [q | k | v], head h at columns h*dh inside each third; out (B, L, H*dh).  Supported: dh == 32, L <= 256.
+ * probs (B*H, L, NP) with NP = xm_attn_keys_padded(L): the dropped, normalised weights (tf32), saved for the
+ * backward; lse (B*H, L).  The dropout mask is a pure function of (seed, slab, query, key). */
+int xm_attn_keys_padded(int64_t L);
+int xm_attn_fwd_f32(const float* qkv, float* out, float* probs, float* lse, int64_t B, int64_t L, int64_t H, int64_t dh,
+                    float scale, float drop_p, uint64_t seed, int round_out, void* stream);
+/* dqkv (B, L, 3*H*dh) from dout (B, L, H*dh); ds: (B*H, L, NP) workspace for the score gradients. */
+int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, const float* lse, float* dqkv, float* ds,
+                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, void* stream);
 
 /* ------------------------------------------------------------------ diagnostics (not on the product path)
  * Dump the raw shared-memory image of one TMA box {32,32} loaded at (c0, c1) from a (rows, cols)

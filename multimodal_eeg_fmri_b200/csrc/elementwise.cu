@@ -424,6 +424,11 @@ __global__ void act_bwd_kernel(const float* __restrict__ dout, const float* __re
   }
 }
 
+__global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = round_tf32(x[i]);
+}
+
 // float4 variants (n % 4 == 0, 16-B aligned)
 __global__ void act_fwd_v4_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4, int act,
                                   float drop_scale, uint32_t drop_thresh, uint64_t seed, int round_out) {
@@ -1120,6 +1125,16 @@ int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int 
     return check_launch();
   }
   act_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dout, x, dx, n, act, sc, th, seed);
+  return check_launch();
+}
+
+int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream) {
+  if (!x || !out || n <= 0) return XM_ERR_INVALID;
+  if ((n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    act_fwd_v4_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, out, n / 4, XM_ACT_NONE, 1.f, 0u, 0ull, 1);
+    return check_launch();
+  }
+  round_tf32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, out, n);
   return check_launch();
 }
 

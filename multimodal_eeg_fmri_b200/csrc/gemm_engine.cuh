@@ -27,6 +27,8 @@ enum : int {
   EPI_ROWMAJOR = 0,    // C[z][tap][m][n] = act(alpha*acc + bias[n])
   EPI_LSE = 2,         // partial[ny][m]  = sum_n exp(alpha*acc - shift) ; diag[m] = alpha*acc[m, m+diag_off]
   EPI_NCE_GRAD = 3,    // C[m][n] = coef*(exp(s-lse_row[m]) + exp(s-lse_col[n]) - 2*[n == m+diag_off]),  s = alpha*acc
+  EPI_SOFTMAX = 4,     // attention probabilities: C[m][n] = drop(softmax_n(alpha*acc[m][:n_valid])), lse_out[z][m]
+  EPI_ATTN_DS = 5,     // attention score gradient from two accumulators (S = Q K^T, dP~ = dO V^T), see below
 };
 
 struct OperandCfg {
@@ -49,10 +51,14 @@ struct GemmParams {
   int tmem_cols;   // allocated TMEM columns (power of two)
   int acc_bufs;    // 1 or 2 accumulator sets of taps_n*bn columns (2: epilogue of tile i overlaps MMA of tile i+1)
   int nx, ny, nz;  // tile grid (persistent CTAs walk tile = by + ny*(bx + nx*bz))
+  int dual;        // 1: two k-blocks per tile, (A, B) -> accumulator 0 and (A2, B2) -> accumulator 1 (EPI_ATTN_DS)
+  OperandCfg a2, b2;
   // epilogue
   int M, N;        // valid extents of the output (guards)
   int tma_store;   // 1: tile staged in swizzled smem and written by TMA through tmC (clips ragged edges)
-  int c_z_mul, c_tap_mul;  // tmC z coordinate = bz*c_z_mul + tn*c_tap_mul
+  int n_stride;    // logical column of a tile's first column = by*n_stride (launch_gemm default: bn)
+  int c_col_base, c_col_mul;        // tmC column coordinate = c_col_base + by*c_col_mul + c0 (default 0, bn)
+  int c_z_mul, c_y_mul, c_tap_mul;  // tmC z coordinate = bz*c_z_mul + by*c_y_mul + tn*c_tap_mul
   float* c;        // direct-store path (outputs TMA cannot address: pitch or base not 16-B aligned)
   long long ldc, c_z_stride, c_tap_stride;
   const float* bias;
@@ -67,6 +73,14 @@ struct GemmParams {
   int diag_off;
   float coef;
   float shift;
+  // attention epilogues (rows = queries of one (sample, head) slab z = bz*c_z_mul + by*c_y_mul)
+  float* lse_out;       // (Z, rows_valid) logsumexp of the scaled scores (EPI_SOFTMAX)
+  const float* lse_in;  // same, read by EPI_ATTN_DS
+  int n_valid;          // keys per row (columns >= n_valid are written as 0)
+  int rows_valid;       // queries per slab (L)
+  uint32_t drop_thresh16;  // keep <=> 16-bit hash lane >= thresh (0: no dropout)
+  float drop_scale;
+  unsigned long long seed;
 };
 
 constexpr int kGemmThreads = 192;
@@ -102,10 +116,142 @@ XM_DEVICE TileCoord decode_tile(const GemmParams& p, int tile) {
   return t;
 }
 
+XM_DEVICE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 16-bit dropout lanes: one 64-bit hash per 4 consecutive columns of a row
+XM_DEVICE uint64_t hash_u64(uint64_t idx, uint64_t seed) {
+  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// Stage 32 fp32 values of this lane's row into the warp's swizzled buffer and TMA-store the 32x32 box.
+XM_DEVICE void stage_and_store(const CUtensorMap* tmC, uint8_t* stg, int& chunk_ctr, int lane, const float (&v)[32], int col,
+                               int row0, int z) {
+  uint8_t* sb = stg + (chunk_ctr & 1) * 4096;
+  if (lane == 0) ptx::bulk_wait_read<1>();
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_3d(tmC, sb, col, row0, z);
+    ptx::bulk_commit();
+  }
+  ++chunk_ctr;
+}
+
+// Attention epilogues.  Thread = one query row m of slab z; the accumulator holds the raw scores
+// Q K^T of that row against all bn (<= 256) keys, so the row softmax needs no cross-thread exchange.
+//   EPI_SOFTMAX:  P~[m][n] = keep(m, n) * softmax_n(alpha * S[m][:n_valid]) / (1 - p_drop)   (tf32-rounded), lse_out
+//   EPI_ATTN_DS:  accumulator 1 holds dP~ = dO V^T;  with P = exp(alpha*S - lse), P~ as above:
+//                 delta = sum_n P~ * dP~ ;  dS[m][n] = alpha * (P~ * dP~ - P * delta)       (tf32-rounded)
+template <int EPI>
+XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, uint32_t acc, const TileCoord& t, int m,
+                                  bool row_ok, int q, int lane, uint8_t* stg, int& chunk_ctr) {
+  const float kLog2e = 1.4426950408889634f;
+  const float c = p.alpha * kLog2e;
+  const int z = t.bz * p.c_z_mul + t.by * p.c_y_mul;
+  const bool live = row_ok && m < p.rows_valid;
+  const unsigned long long row_id = (unsigned long long)z * (unsigned long long)p.rows_valid + (unsigned long long)m;
+  const int nchunks = p.bn >> 5;
+  float off;  // log2-domain offset: P = exp2(acc*c - off)
+  if (EPI == EPI_SOFTMAX) {
+    float mx = -3.0e38f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ch * 32 + j < p.n_valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+    const float mc = mx * c;
+    float sum = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (ch * 32 + j < p.n_valid) sum += fast_exp2(__uint_as_float(r[j]) * c - mc);
+    }
+    off = mc + log2f(sum);
+    if (live) p.lse_out[row_id] = off * 0.6931471805599453f;  // natural-log logsumexp of the scaled scores
+  } else {
+    off = live ? __ldg(p.lse_in + row_id) * kLog2e : 0.f;
+  }
+
+  float delta = 0.f;
+  if (EPI == EPI_ATTN_DS) {
+    for (int ch = 0; ch < nchunks; ++ch) {
+      uint32_t r[32], g[32];
+      ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
+      ptx::tmem_ld_32x32(acc + (uint32_t)(p.bn + ch * 32), g);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        uint64_t h = 0;
+        if (p.drop_thresh16) h = hash_u64(row_id * 64ull + (unsigned long long)(ch * 8 + j4), p.seed);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * j4 + jj;
+          if (ch * 32 + j < p.n_valid) {
+            float pr = fast_exp2(__uint_as_float(r[j]) * c - off);
+            if (p.drop_thresh16) pr = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
+            delta += pr * __uint_as_float(g[j]);
+          }
+        }
+      }
+    }
+  }
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    uint32_t r[32];
+    float v[32];
+    ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
+    if (EPI == EPI_ATTN_DS) {
+      uint32_t g[32];
+      ptx::tmem_ld_32x32(acc + (uint32_t)(p.bn + ch * 32), g);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(g[j]);
+    } else {
+      ptx::tmem_ld_wait();
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      uint64_t h = 0;
+      if (p.drop_thresh16) h = hash_u64(row_id * 64ull + (unsigned long long)(ch * 8 + j4), p.seed);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * j4 + jj;
+        float o = 0.f;
+        if (ch * 32 + j < p.n_valid) {
+          const float pr = fast_exp2(__uint_as_float(r[j]) * c - off);
+          float pd = pr;
+          if (p.drop_thresh16) pd = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
+          o = (EPI == EPI_ATTN_DS) ? p.alpha * (pd * v[j] - pr * delta) : pd;
+        }
+        v[j] = round_tf32(o);
+      }
+    }
+    stage_and_store(&tmC, stg, chunk_ctr, lane, v, p.c_col_base + ch * 32, t.bx * 128 + q * 32, z);
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
@@ -129,6 +275,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     if (p.tma_store) ptx::prefetch_tensormap(&tmC);
+    if (p.dual) {
+      ptx::prefetch_tensormap(&tmA2);
+      ptx::prefetch_tensormap(&tmB2);
+    }
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -183,6 +333,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        if (p.dual) {  // second operand pair of the tile: one k-block into accumulator 1
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          issue_operand_loads(&tmA2, &full_bar[s], sa, p.a2,
+                              p.a2.base[0] + t.bx * p.a2.sx[0] + t.by * p.a2.sy[0] + t.bz * p.a2.sz[0],
+                              p.a2.base[1] + t.bx * p.a2.sx[1] + t.by * p.a2.sy[1] + t.bz * p.a2.sz[1],
+                              p.a2.base[2] + t.bx * p.a2.sx[2] + t.by * p.a2.sy[2] + t.bz * p.a2.sz[2]);
+          issue_operand_loads(&tmB2, &full_bar[s], sa + kATileBytes, p.b2,
+                              p.b2.base[0] + t.bx * p.b2.sx[0] + t.by * p.b2.sy[0] + t.bz * p.b2.sz[0],
+                              p.b2.base[1] + t.bx * p.b2.sx[1] + t.by * p.b2.sy[1] + t.bz * p.b2.sz[1],
+                              p.b2.base[2] + t.bx * p.b2.sx[2] + t.by * p.b2.sy[2] + t.bz * p.b2.sz[2]);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -224,6 +388,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
+        if (p.dual) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t idesc2 = ptx::make_idesc_tf32(128, p.bn, p.a2.mn_major, p.b2.mn_major);
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {
+            const uint64_t da = ptx::make_smem_desc(sa + k8 * (p.a2.mn_major ? 1024u : 32u), p.a2.mn_major ? 4096u : 16u,
+                                                    p.a2.mn_major ? 512u : 1024u, p.a2.mn_major ? 1u : 2u);
+            const uint64_t db = ptx::make_smem_desc(sa + kATileBytes + k8 * (p.b2.mn_major ? 1024u : 32u),
+                                                    p.b2.mn_major ? 4096u : 16u, p.b2.mn_major ? 512u : 1024u,
+                                                    p.b2.mn_major ? 1u : 2u);
+            ptx::mma_tf32_ss(acc + (uint32_t)p.bn, da, db, idesc2, k8 > 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
         ptx::mma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
     }
@@ -243,7 +424,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols) + ((uint32_t)(q * 32) << 16);
       const int m = t.bx * 128 + row;  // row index inside this z-slab
       const bool row_ok = m < p.M;
-      const int n0 = t.by * p.bn;
+      const int n0 = t.by * p.n_stride;
+      const int col0 = p.c_col_base + t.by * p.c_col_mul;  // tmC column of this tile's first column
+
+      if (EPI == EPI_SOFTMAX || EPI == EPI_ATTN_DS) {
+        attention_epilogue<EPI>(p, tmC, acc, t, m, row_ok, q, lane, stg, chunk_ctr);
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+        continue;
+      }
 
       float lse_r = 0.f;
       if (EPI == EPI_NCE_GRAD && row_ok) lse_r = p.lse_row[m];
@@ -252,7 +442,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tn = 0; tn < p.taps_n; ++tn) {
         if (EPI != EPI_LSE && p.tma_store) {
           // ---- 32-column chunks: TMEM -> registers -> swizzled smem -> TMA store (edges clipped by TMA)
-          const int zc = t.bz * p.c_z_mul + tn * p.c_tap_mul;
+          const int zc = t.bz * p.c_z_mul + t.by * p.c_y_mul + tn * p.c_tap_mul;
           for (int c0 = 0; c0 < p.bn; c0 += 32) {
             if (n0 + c0 >= p.N) break;  // warp-uniform: chunk entirely outside the output
             uint32_t r[32];
@@ -321,7 +511,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              ptx::tma_store_3d(&tmC, sb, n0 + c0, t.bx * 128 + q * 32, zc);
+              ptx::tma_store_3d(&tmC, sb, col0 + c0, t.bx * 128 + q * 32, zc);
               ptx::bulk_commit();
             }
             ++chunk_ctr;
@@ -392,7 +582,7 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
 // `tc` describes the output for the TMA-store epilogue (dims {N, M, Z}); pass ptr == nullptr to use
 // the direct-store path (p.c / p.ldc).  `grid` is the TILE grid; the launch is persistent.
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
-                cudaStream_t stream);
+                cudaStream_t stream, const TensorView3* ta2 = nullptr, const TensorView3* tb2 = nullptr);
 
 inline int tmem_cols_for(int n) {
   int c = 32;

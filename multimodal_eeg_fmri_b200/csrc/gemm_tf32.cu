@@ -60,19 +60,23 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
 }
 
 template <int EPI>
-static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p, int ctas,
-                      size_t smem, cudaStream_t stream) {
+static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& ma2,
+                      const CUtensorMap& mb2, const GemmParams& p, int ctas, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
-  gemm_tf32_kernel<EPI><<<ctas, kGemmThreads, smem, stream>>>(ma, mb, mc, p);
+  gemm_tf32_kernel<EPI><<<ctas, kGemmThreads, smem, stream>>>(ma, mb, mc, ma2, mb2, p);
   return check_launch();
 }
 
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
-                cudaStream_t stream) {
+                cudaStream_t stream, const TensorView3* ta2, const TensorView3* tb2) {
+  if (p.n_stride < 0) p.n_stride = p.bn;
+  if (p.c_col_mul < 0) p.c_col_mul = p.bn;
+  p.dual = (ta2 != nullptr && tb2 != nullptr) ? 1 : 0;
+  if (p.dual && (p.taps_n != 1 || 2 * p.bn > 512)) return XM_ERR_UNSUPPORTED;
   if (p.bn < 16 || p.bn > 256 || (p.bn & 15)) return XM_ERR_UNSUPPORTED;
   if (p.b.mn_major && (p.bn & 31)) return XM_ERR_UNSUPPORTED;
   if (p.taps_n * p.bn > 512) return XM_ERR_UNSUPPORTED;
@@ -97,14 +101,25 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   if (stages < 2) return XM_ERR_UNSUPPORTED;
   p.stages = stages;
   const int acc_cols = p.taps_n * p.bn;
-  p.acc_bufs = (2 * acc_cols <= 512 && ntiles > 1) ? 2 : 1;
-  p.tmem_cols = tmem_cols_for(p.acc_bufs * acc_cols);
+  p.acc_bufs = (2 * acc_cols <= 512 && ntiles > 1 && !p.dual) ? 2 : 1;
+  p.tmem_cols = tmem_cols_for(p.dual ? 2 * acc_cols : p.acc_bufs * acc_cols);
+  if ((epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) && (!p.tma_store || (p.bn & 31))) return XM_ERR_UNSUPPORTED;
   p.a.rows = 128;
   p.b.rows = p.bn;
   const size_t smem = (size_t)stages * stage_bytes + staging + 1024;
 
-  CUtensorMap ma, mb, mc;
+  CUtensorMap ma, mb, mc, ma2, mb2;
   memset(&mc, 0, sizeof(mc));
+  memset(&ma2, 0, sizeof(ma2));
+  memset(&mb2, 0, sizeof(mb2));
+  if (p.dual) {
+    p.a2.rows = 128;
+    p.b2.rows = p.bn;
+    int rc2 = encode_tmap(&ma2, *ta2, 32, p.a2.mn_major ? 32 : 128, p.a2.mn_major);
+    if (rc2 != XM_OK) return rc2;
+    rc2 = encode_tmap(&mb2, *tb2, 32, p.b2.mn_major ? 32 : (unsigned)p.bn, p.b2.mn_major);
+    if (rc2 != XM_OK) return rc2;
+  }
   int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : 128, p.a.mn_major);
   if (rc != XM_OK) return rc;
   rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? 32 : (unsigned)p.bn, p.b.mn_major);
@@ -115,9 +130,11 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   }
   const int ctas = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   switch (epi) {
-    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, mc, p, ctas, smem, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, mc, p, ctas, smem, stream);
-    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, mc, p, ctas, smem, stream);
+    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
+    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
+    case EPI_SOFTMAX: return launch_epi<EPI_SOFTMAX>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
+    case EPI_ATTN_DS: return launch_epi<EPI_ATTN_DS>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
   }
   return XM_ERR_INVALID;
 }
@@ -129,6 +146,8 @@ static void zero_params(GemmParams& p) {
   p.kout_count = 1;
   p.kout_total = 1;
   p.alpha = 1.0f;
+  p.n_stride = -1;   // launch_gemm: bn
+  p.c_col_mul = -1;  // launch_gemm: bn
 }
 
 // N tile: as wide as the problem allows (fewer A re-reads), narrowed while the grid
@@ -212,6 +231,203 @@ static int grid_for(long long n, int threads) {
   const long long cap = (long long)kNumSMs * 16;
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
+
+
+// ------------------------------------------------------------------ multi-head self-attention
+// nn.MultiheadAttention core as called by TemporalTransformerBlock (EEG_CODE/enhanced_models_v4.py:71-73,98):
+// softmax(q k^T / sqrt(dh)) with dropout on the weights, times v -- per (sample, head) slab, L <= 256 keys.
+// Everything is the GEMM engine: the row softmax (and, in the backward, the whole dS formula) runs in the
+// epilogue of the score GEMM because one 128 x NP accumulator tile holds complete rows.
+struct AttnDims {
+  long long B, L, H, dh, NP, E;  // E = 3*H*dh (row pitch of qkv), NP = padded key count (128 or 256)
+};
+static int attn_dims(AttnDims& d, int64_t B, int64_t L, int64_t H, int64_t dh) {
+  if (B <= 0 || L <= 0 || H <= 0 || dh <= 0) return XM_ERR_INVALID;
+  if (dh != 32 || L > 256 || B > 2000000 || H > 64) return XM_ERR_UNSUPPORTED;
+  d.B = B; d.L = L; d.H = H; d.dh = dh;
+  d.NP = L <= 128 ? 128 : 256;
+  d.E = 3 * H * dh;
+  return XM_OK;
+}
+static TensorView3 view3(const void* ptr, long long d0, long long d1, long long d2, long long ld1, long long ld2) {
+  return TensorView3{ptr, {(unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2},
+                     {(unsigned long long)ld1 * 4, (unsigned long long)ld2 * 4}};
+}
+static void drop16(GemmParams& p, float drop_p, uint64_t seed) {
+  p.seed = seed;
+  if (drop_p > 0.f) {
+    double th = (double)drop_p * 65536.0 + 0.5;
+    p.drop_thresh16 = th >= 65535.0 ? 65535u : (uint32_t)th;
+    if (p.drop_thresh16 == 0u) p.drop_thresh16 = 1u;
+    p.drop_scale = 1.0f / (1.0f - drop_p);
+  } else {
+    p.drop_thresh16 = 0u;
+    p.drop_scale = 1.0f;
+  }
+}
+// operand = a (rows, dh) block of qkv: column offset col0 + head*dh, K-major (dh contiguous)
+static void qkv_kmajor(OperandCfg& o, const AttnDims& d, long long col0, bool tile_rows) {
+  o.mn_major = 0;
+  o.base[0] = (int)col0;
+  o.sy[0] = (int)d.dh;
+  if (tile_rows) o.sx[1] = 128;
+  o.sz[2] = 1;
+  o.kin_step[0] = 32;
+}
+// operand = the same block read MN-major (dh = GEMM N or M index contiguous, one row per contraction step)
+static void qkv_mnmajor(OperandCfg& o, const AttnDims& d, long long col0) {
+  o.mn_major = 1;
+  o.base[0] = (int)col0;
+  o.sy[0] = (int)d.dh;
+  o.sz[2] = 1;
+  o.kin_step[1] = 32;
+}
+// score-shaped operand (NP, L, B*H), slab z = bz*H + by
+static void slab_kmajor(OperandCfg& o, const AttnDims& d) {
+  o.mn_major = 0;
+  o.sx[1] = 128;
+  o.sy[2] = 1;
+  o.sz[2] = (int)d.H;
+  o.kin_step[0] = 32;
+}
+static void slab_mnmajor(OperandCfg& o, const AttnDims& d) {
+  o.mn_major = 1;
+  o.sx[0] = 128;
+  o.sy[2] = 1;
+  o.sz[2] = (int)d.H;
+  o.kin_step[1] = 32;
+}
+static void score_epilogue(GemmParams& p, const AttnDims& d, float scale) {
+  p.bn = (int)d.NP;
+  p.kin_count = (int)(d.dh / 32);
+  p.M = (int)d.L;
+  p.N = (int)d.NP;
+  p.n_valid = (int)d.L;
+  p.rows_valid = (int)d.L;
+  p.n_stride = 0;
+  p.c_col_base = 0;
+  p.c_col_mul = 0;
+  p.c_z_mul = (int)d.H;
+  p.c_y_mul = 1;
+  p.alpha = scale;
+}
+// out (B, L, out_pitch) columns [col_base + h*dh, +dh) = slab GEMM result
+static void head_output(GemmParams& p, const AttnDims& d, long long col_base) {
+  p.bn = (int)d.dh;
+  p.M = (int)d.L;
+  p.N = (int)(d.H * d.dh);
+  p.n_stride = (int)d.dh;
+  p.c_col_base = (int)col_base;
+  p.c_col_mul = (int)d.dh;
+  p.c_z_mul = 1;
+  p.c_y_mul = 0;
+}
+
+}  // namespace xm
+
+using namespace xm;
+
+extern "C" {
+
+int xm_attn_keys_padded(int64_t L) { return L <= 128 ? 128 : 256; }
+
+int xm_attn_fwd_f32(const float* qkv, float* out, float* probs, float* lse, int64_t B, int64_t L, int64_t H, int64_t dh,
+                    float scale, float drop_p, uint64_t seed, int round_out, void* stream) {
+  if (!qkv || !out || !probs || !lse || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
+  AttnDims d;
+  int rc = attn_dims(d, B, L, H, dh);
+  if (rc != XM_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const TensorView3 tq = view3(qkv, d.E, L, B, d.E, L * d.E);
+  const TensorView3 tp = view3(probs, d.NP, L, B * H, d.NP, L * d.NP);
+  const dim3 grid(ceil_div(L, 128), (unsigned)H, (unsigned)B);
+  {  // P~ = dropout(softmax(scale * q k^T))
+    GemmParams p;
+    zero_params(p);
+    qkv_kmajor(p.a, d, 0, true);
+    qkv_kmajor(p.b, d, H * dh, false);
+    score_epilogue(p, d, scale);
+    drop16(p, drop_p, seed);
+    p.lse_out = lse;
+    rc = launch_gemm(EPI_SOFTMAX, tq, tq, tp, p, grid, st);
+    if (rc != XM_OK) return rc;
+  }
+  {  // out[:, :, h*dh:(h+1)*dh] = P~ v
+    GemmParams p;
+    zero_params(p);
+    slab_kmajor(p.a, d);
+    qkv_mnmajor(p.b, d, 2 * H * dh);
+    head_output(p, d, 0);
+    p.kin_count = (int)(d.NP / 32);
+    p.round_tf32 = round_out;
+    const TensorView3 to = view3(out, H * dh, L, B, H * dh, L * H * dh);
+    rc = launch_gemm(EPI_ROWMAJOR, tp, tq, to, p, grid, st);
+  }
+  return rc;
+}
+
+int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, const float* lse, float* dqkv, float* ds,
+                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, void* stream) {
+  if (!dout || !qkv || !probs || !lse || !dqkv || !ds || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
+  AttnDims d;
+  int rc = attn_dims(d, B, L, H, dh);
+  if (rc != XM_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const TensorView3 tq = view3(qkv, d.E, L, B, d.E, L * d.E);
+  const TensorView3 tp = view3(probs, d.NP, L, B * H, d.NP, L * d.NP);
+  const TensorView3 ts = view3(ds, d.NP, L, B * H, d.NP, L * d.NP);
+  const TensorView3 tdo = view3(dout, H * dh, L, B, H * dh, L * H * dh);
+  const TensorView3 tdq = view3(dqkv, d.E, L, B, d.E, L * d.E);
+  const dim3 grid(ceil_div(L, 128), (unsigned)H, (unsigned)B);
+  const int kq = ceil_div(L, 32);  // contraction over queries (rows >= L are zero-filled by TMA)
+  {  // dS = scale * (P~ o dP~ - P * rowsum(P~ o dP~)),  S = q k^T and dP~ = dO v^T recomputed side by side in TMEM
+    GemmParams p;
+    zero_params(p);
+    qkv_kmajor(p.a, d, 0, true);
+    qkv_kmajor(p.b, d, H * dh, false);
+    qkv_kmajor(p.a2, d, 0, true);  // dO (B, L, H*dh): head h at column h*dh
+    qkv_kmajor(p.b2, d, 2 * H * dh, false);
+    score_epilogue(p, d, scale);
+    drop16(p, drop_p, seed);
+    p.lse_in = lse;
+    rc = launch_gemm(EPI_ATTN_DS, tq, tq, ts, p, grid, st, &tdo, &tq);
+    if (rc != XM_OK) return rc;
+  }
+  {  // dv = P~^T dO
+    GemmParams p;
+    zero_params(p);
+    slab_mnmajor(p.a, d);
+    qkv_mnmajor(p.b, d, 0);
+    head_output(p, d, 2 * H * dh);
+    p.kin_count = kq;
+    rc = launch_gemm(EPI_ROWMAJOR, tp, tdo, tdq, p, grid, st);
+    if (rc != XM_OK) return rc;
+  }
+  {  // dk = dS^T q
+    GemmParams p;
+    zero_params(p);
+    slab_mnmajor(p.a, d);
+    qkv_mnmajor(p.b, d, 0);
+    head_output(p, d, H * dh);
+    p.kin_count = kq;
+    rc = launch_gemm(EPI_ROWMAJOR, ts, tq, tdq, p, grid, st);
+    if (rc != XM_OK) return rc;
+  }
+  {  // dq = dS k
+    GemmParams p;
+    zero_params(p);
+    slab_kmajor(p.a, d);
+    qkv_mnmajor(p.b, d, H * dh);
+    head_output(p, d, 0);
+    p.kin_count = (int)(d.NP / 32);
+    rc = launch_gemm(EPI_ROWMAJOR, ts, tq, tdq, p, grid, st);
+  }
+  return rc;
+}
+
+}  // extern "C"
+
+namespace xm {
 
 }  // namespace xm
 

@@ -169,13 +169,14 @@ def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=Fa
 
 # ----------------------------------------------------------------------------- linear blocks
 class Linear(torch.autograd.Function):
-    """y = x @ w^T + b on the tcgen05 GEMM (nn.Linear)."""
+    """y = x @ w^T + b on the tcgen05 GEMM (nn.Linear).  `round_out` rounds y to tf32 (set when y feeds
+    another tensor-core contraction directly, e.g. the packed q/k/v projections)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, round_out=False):
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
-        return ops.linear_fwd(x, w, b)
+        return ops.linear_fwd(x, w, b, round_out=round_out)
 
     @staticmethod
     def backward(ctx, dy):
@@ -183,7 +184,7 @@ class Linear(torch.autograd.Function):
         dy = dy.contiguous()
         dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
         dw, db = ops.linear_wgrad(dy, x, need_bias=ctx.has_bias)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 def linear(x, lin):
@@ -271,6 +272,38 @@ class LinearLnAct(torch.autograd.Function):
 
 def linear_ln_act(x, lin, ln, act="gelu", drop_p=0.0, training=True):
     return LinearLnAct.apply(x, lin.weight, lin.bias, ln.weight, ln.bias, (ln.eps, act, float(drop_p), bool(training)))
+
+
+# ----------------------------------------------------------------------------- attention core
+class SelfAttentionCore(torch.autograd.Function):
+    """softmax(q k^T / sqrt(dh)) -> Dropout -> @ v per (sample, head), on the packed in_proj output
+    qkv (B, L, 3d) (nn.MultiheadAttention inside TemporalTransformerBlock, enhanced_models_v4.py:71-73,98).
+    Scores never reach HBM: the softmax (and the whole dS formula in the backward) runs in the epilogue of
+    the score GEMM; the dropped probabilities are the only saved (B*H, L, L) tensor."""
+
+    @staticmethod
+    def forward(ctx, qkv, nhead, p, seed):
+        dh = qkv.shape[2] // 3 // nhead
+        scale = 1.0 / (dh ** 0.5)
+        out, probs, lse = ops.attn_fwd(qkv, nhead, scale, p, seed)
+        ctx.save_for_backward(qkv, probs, lse)
+        ctx.meta = (nhead, scale, p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, probs, lse = ctx.saved_tensors
+        nhead, scale, p, seed = ctx.meta
+        return ops.attn_bwd(dout, qkv, probs, lse, nhead, scale, p, seed), None, None, None
+
+
+def self_attention_core(qkv, nhead, drop_p=0.0, training=True):
+    p = float(drop_p) if training else 0.0
+    return SelfAttentionCore.apply(qkv, nhead, p, next_seed() if p > 0 else 0)
+
+
+def attention_core_supported(L: int, dh: int) -> bool:
+    return ops.attn_supported(L, dh)
 
 
 # ----------------------------------------------------------------------------- pooling

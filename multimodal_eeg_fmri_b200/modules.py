@@ -76,10 +76,13 @@ class TemporalTransformerBlock(nn.Module):
         B, L, d = x.shape
         lin = XF.Linear.apply  # the four projections run on the tcgen05 TF32 GEMM over (B*L, d) rows
         h = F.layer_norm(x, (d,), self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        qkv = lin(h.reshape(B * L, d), self.self_attn.in_proj_weight, self.self_attn.in_proj_bias).view(B, L, 3 * d)
-        q, k, v = (t.view(B, L, self.nhead, d // self.nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
-        a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.p if self.training else 0.0)
-        a = a.transpose(1, 2).reshape(B * L, d)
+        qkv = lin(h.reshape(B * L, d), self.self_attn.in_proj_weight, self.self_attn.in_proj_bias, True).view(B, L, 3 * d)
+        if mask is None and XF.attention_core_supported(L, d // self.nhead):
+            a = XF.self_attention_core(qkv, self.nhead, self.p, self.training).reshape(B * L, d)
+        else:  # shapes outside the fused kernel (head dim != 32, L > 256, explicit mask): library attention
+            q, k, v = (t.view(B, L, self.nhead, d // self.nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+            a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.p if self.training else 0.0)
+            a = a.transpose(1, 2).reshape(B * L, d)
         a = lin(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias).view(B, L, d)
         x = x + F.dropout(a, self.p, self.training)
         h = F.layer_norm(x, (d,), self.norm2.weight, self.norm2.bias, self.norm2.eps)

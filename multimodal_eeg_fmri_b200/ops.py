@@ -395,6 +395,16 @@ def act_bwd(dout, x, act, drop_p=0.0, seed=0):
     return dx
 
 
+def round_tf32(x, inplace=False):
+    """Round to nearest tf32 (what the tensor cores would otherwise truncate to)."""
+    _chk(x)
+    x = x.contiguous()
+    out = x if inplace else torch.empty_like(x)
+    _w(x.numel(), 8.0 * x.numel())
+    _call("xm_round_tf32_f32", _p(x), _p(out), x.numel(), _stream())
+    return out
+
+
 # ------------------------------------------------------------------ reductions
 def _colsum_ws(M, N, device):
     ns = _lib.lib().xm_colsum_nsplit(M, N)
@@ -470,6 +480,41 @@ def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
     _call("xm_infonce_grad_f32", _p(a), _p(b), _p(lse_row), _p(lse_col), _p(G), Ml, Ng, D, float(inv_tau),
           int(diag_off), float(coef), _stream())
     return G
+
+
+# ------------------------------------------------------------------ multi-head self-attention core
+def attn_supported(L: int, dh: int) -> bool:
+    return dh == 32 and 0 < L <= 256
+
+
+def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
+    """qkv (B, L, 3*H*dh) packed in_proj output -> (out (B, L, H*dh), probs (B*H, L, NP), lse (B*H, L))."""
+    _chk(qkv)
+    qkv = qkv.contiguous()
+    B, L, E = qkv.shape
+    d = E // 3
+    dh = d // nhead
+    NP = _lib.lib().xm_attn_keys_padded(L)
+    out = torch.empty(B, L, d, device=qkv.device, dtype=torch.float32)
+    probs = torch.empty(B * nhead, L, NP, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * nhead, L, device=qkv.device, dtype=torch.float32)
+    _w(4.0 * B * nhead * L * L * dh, 4.0 * (qkv.numel() + out.numel() + 2 * probs.numel()))
+    _call("xm_attn_fwd_f32", _p(qkv), _p(out), _p(probs), _p(lse), B, L, nhead, dh, float(scale), float(drop_p), int(seed),
+          int(round_out), _stream())
+    return out, probs, lse
+
+
+def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0):
+    _chk(dout, qkv, probs, lse)
+    dout = dout.contiguous()
+    B, L, E = qkv.shape
+    dh = E // 3 // nhead
+    dqkv = torch.empty_like(qkv)
+    ds = torch.empty_like(probs)
+    _w(10.0 * B * nhead * L * L * dh, 4.0 * (2 * qkv.numel() + dout.numel() + 4 * probs.numel()))
+    _call("xm_attn_bwd_f32", _p(dout), _p(qkv), _p(probs), _p(lse), _p(dqkv), _p(ds), B, L, nhead, dh, float(scale),
+          float(drop_p), int(seed), _stream())
+    return dqkv
 
 
 # ------------------------------------------------------------------ preprocessing

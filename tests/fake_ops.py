@@ -191,6 +191,10 @@ def act_bwd(dout, x, act, drop_p=0.0, seed=0):
     return g.float()
 
 
+def round_tf32(x, inplace=False):
+    return x
+
+
 def colsum(x):
     return x.double().sum(0).float()
 
@@ -222,6 +226,43 @@ def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
     i = torch.arange(a.shape[0])
     G[i, i + diag_off] -= 2.0
     return (G * coef).float()
+
+
+# ---------------------------------------------------------------- attention core
+def attn_supported(L, dh):
+    return dh == 32 and 0 < L <= 256
+
+
+def _attn_parts(qkv, nhead):
+    B, L, E = qkv.shape
+    d = E // 3
+    q, k, v = (t.reshape(B, L, nhead, d // nhead).transpose(1, 2).double() for t in qkv.chunk(3, dim=-1))
+    return q, k, v
+
+
+def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
+    _nodrop(drop_p)
+    B, L, E = qkv.shape
+    q, k, v = _attn_parts(qkv, nhead)
+    s = q @ k.transpose(-1, -2) * scale
+    p = torch.softmax(s, dim=-1)
+    out = (p @ v).transpose(1, 2).reshape(B, L, E // 3)
+    return out.float(), p.reshape(B * nhead, L, L).float(), torch.logsumexp(s, -1).reshape(B * nhead, L).float()
+
+
+def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    B, L, E = qkv.shape
+    d = E // 3
+    q, k, v = _attn_parts(qkv, nhead)
+    p = probs.reshape(B, nhead, L, L).double()
+    do = dout.reshape(B, L, nhead, d // nhead).transpose(1, 2).double()
+    dv = p.transpose(-1, -2) @ do
+    dp = do @ v.transpose(-1, -2)
+    ds = p * (dp - (p * dp).sum(-1, keepdim=True)) * scale
+    dq, dk = ds @ k, ds.transpose(-1, -2) @ q
+    back = lambda t: t.transpose(1, 2).reshape(B, L, d)
+    return torch.cat([back(dq), back(dk), back(dv)], dim=-1).float()
 
 
 # ---------------------------------------------------------------- preprocessing
