@@ -83,10 +83,19 @@ struct GemmParams {
   unsigned long long seed;
 };
 
-constexpr int kGemmThreads = 192;
+// Epilogue warps per kernel flavour: 4 per TMEM lane quadrant "part"; the parts split a tile's columns.
+// A single warp per scheduler runs a dependent TMEM-load -> ALU -> store chain at low IPC, so the
+// epilogue-heavy flavours (row softmax, dS) use 16 warps and the plain stores 8.
+template <int EPI>
+struct EpiWarps {
+  static constexpr int value = (EPI == 4 || EPI == 5) ? 16 : (EPI == 2 ? 4 : 8);
+};
+constexpr int gemm_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 32 tf32
 constexpr int kMaxStages = 8;
-constexpr int kStagingBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 32 fp32)
+// staging: one 32 x 32 fp32 box (4 KB) per buffer; 2 buffers per warp up to 8 warps, 1 beyond
+constexpr int staging_bufs(int epi_warps) { return epi_warps <= 8 ? 2 : 1; }
+constexpr int staging_bytes(int epi_warps) { return epi_warps * staging_bufs(epi_warps) * 4096; }
 
 XM_DEVICE void issue_operand_loads(const CUtensorMap* tm, uint64_t* bar, uint8_t* dst, const OperandCfg& o, int c0,
                                    int c1, int c2) {
@@ -130,10 +139,11 @@ XM_DEVICE uint64_t hash_u64(uint64_t idx, uint64_t seed) {
 }
 
 // Stage 32 fp32 values of this lane's row into the warp's swizzled buffer and TMA-store the 32x32 box.
+template <int NBUF>
 XM_DEVICE void stage_and_store(const CUtensorMap* tmC, uint8_t* stg, int& chunk_ctr, int lane, const float (&v)[32], int col,
                                int row0, int z) {
-  uint8_t* sb = stg + (chunk_ctr & 1) * 4096;
-  if (lane == 0) ptx::bulk_wait_read<1>();
+  uint8_t* sb = stg + (NBUF == 2 ? (chunk_ctr & 1) * 4096 : 0);
+  if (lane == 0) ptx::bulk_wait_read<NBUF - 1>();  // the store that last read this buffer has drained it
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -148,50 +158,73 @@ XM_DEVICE void stage_and_store(const CUtensorMap* tmC, uint8_t* stg, int& chunk_
   ++chunk_ctr;
 }
 
-// Attention epilogues.  Thread = one query row m of slab z; the accumulator holds the raw scores
-// Q K^T of that row against all bn (<= 256) keys, so the row softmax needs no cross-thread exchange.
+// Attention epilogues.  A quadrant's 4 warps ("parts") share 32 query rows of slab z: lane = row, part
+// = a quarter of the bn (<= 256) key columns.  The accumulator holds the raw scores Q K^T of complete
+// rows, so the row softmax only needs one max and one sum exchanged between the 4 parts (shared memory +
+// a 128-thread named barrier per quadrant).
 //   EPI_SOFTMAX:  P~[m][n] = keep(m, n) * softmax_n(alpha * S[m][:n_valid]) / (1 - p_drop)   (tf32-rounded), lse_out
 //   EPI_ATTN_DS:  accumulator 1 holds dP~ = dO V^T;  with P = exp(alpha*S - lse), P~ as above:
 //                 delta = sum_n P~ * dP~ ;  dS[m][n] = alpha * (P~ * dP~ - P * delta)       (tf32-rounded)
+XM_DEVICE void quad_barrier(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
+
 template <int EPI>
 XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, uint32_t acc, const TileCoord& t, int m,
-                                  bool row_ok, int q, int lane, uint8_t* stg, int& chunk_ctr) {
+                                  bool row_ok, int q, int part, int lane, uint8_t* stg, int& chunk_ctr,
+                                  float (*red)[4][32]) {
   const float kLog2e = 1.4426950408889634f;
   const float c = p.alpha * kLog2e;
   const int z = t.bz * p.c_z_mul + t.by * p.c_y_mul;
   const bool live = row_ok && m < p.rows_valid;
   const unsigned long long row_id = (unsigned long long)z * (unsigned long long)p.rows_valid + (unsigned long long)m;
-  const int nchunks = p.bn >> 5;
-  float off;  // log2-domain offset: P = exp2(acc*c - off)
+  const int nch = p.bn >> 7;       // 32-column chunks per part (bn is 128 or 256)
+  const int ch0 = part * nch;      // first chunk of this part
+  float off;                       // log2-domain offset: P = exp2(acc*c - off)
   if (EPI == EPI_SOFTMAX) {
     float mx = -3.0e38f;
-    for (int ch = 0; ch < nchunks; ++ch) {
+    for (int ch = ch0; ch < ch0 + nch; ++ch) {
       uint32_t r[32];
       ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
       ptx::tmem_ld_wait();
+      if (ch * 32 + 32 <= p.n_valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (ch * 32 + j < p.n_valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ch * 32 + j < p.n_valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
     }
+    red[q][part][lane] = mx;
+    quad_barrier(q);
+    mx = fmaxf(fmaxf(red[q][0][lane], red[q][1][lane]), fmaxf(red[q][2][lane], red[q][3][lane]));
     const float mc = mx * c;
     float sum = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch) {
+    for (int ch = ch0; ch < ch0 + nch; ++ch) {
       uint32_t r[32];
       ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
       ptx::tmem_ld_wait();
+      if (ch * 32 + 32 <= p.n_valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (ch * 32 + j < p.n_valid) sum += fast_exp2(__uint_as_float(r[j]) * c - mc);
+        for (int j = 0; j < 32; ++j) sum += fast_exp2(__uint_as_float(r[j]) * c - mc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ch * 32 + j < p.n_valid) sum += fast_exp2(__uint_as_float(r[j]) * c - mc);
+      }
     }
+    quad_barrier(q);  // every part has read the maxima: the exchange buffer can be reused
+    red[q][part][lane] = sum;
+    quad_barrier(q);
+    sum = (red[q][0][lane] + red[q][1][lane]) + (red[q][2][lane] + red[q][3][lane]);
     off = mc + log2f(sum);
-    if (live) p.lse_out[row_id] = off * 0.6931471805599453f;  // natural-log logsumexp of the scaled scores
+    if (live && part == 0) p.lse_out[row_id] = off * 0.6931471805599453f;  // natural-log logsumexp of the scaled scores
   } else {
     off = live ? __ldg(p.lse_in + row_id) * kLog2e : 0.f;
   }
 
   float delta = 0.f;
   if (EPI == EPI_ATTN_DS) {
-    for (int ch = 0; ch < nchunks; ++ch) {
+    for (int ch = ch0; ch < ch0 + nch; ++ch) {
       uint32_t r[32], g[32];
       ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
       ptx::tmem_ld_32x32(acc + (uint32_t)(p.bn + ch * 32), g);
@@ -203,17 +236,18 @@ XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, u
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = 4 * j4 + jj;
-          if (ch * 32 + j < p.n_valid) {
-            float pr = fast_exp2(__uint_as_float(r[j]) * c - off);
-            if (p.drop_thresh16) pr = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
-            delta += pr * __uint_as_float(g[j]);
-          }
+          float pr = (ch * 32 + j < p.n_valid) ? fast_exp2(__uint_as_float(r[j]) * c - off) : 0.f;
+          if (p.drop_thresh16) pr = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
+          delta += pr * __uint_as_float(g[j]);
         }
       }
     }
+    red[q][part][lane] = delta;
+    quad_barrier(q);
+    delta = (red[q][0][lane] + red[q][1][lane]) + (red[q][2][lane] + red[q][3][lane]);
   }
 
-  for (int ch = 0; ch < nchunks; ++ch) {
+  for (int ch = ch0; ch < ch0 + nch; ++ch) {
     uint32_t r[32];
     float v[32];
     ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
@@ -233,22 +267,20 @@ XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, u
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int j = 4 * j4 + jj;
-        float o = 0.f;
-        if (ch * 32 + j < p.n_valid) {
-          const float pr = fast_exp2(__uint_as_float(r[j]) * c - off);
-          float pd = pr;
-          if (p.drop_thresh16) pd = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
-          o = (EPI == EPI_ATTN_DS) ? p.alpha * (pd * v[j] - pr * delta) : pd;
-        }
+        const float pr = (ch * 32 + j < p.n_valid) ? fast_exp2(__uint_as_float(r[j]) * c - off) : 0.f;
+        float pd = pr;
+        if (p.drop_thresh16) pd = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
+        const float o = (EPI == EPI_ATTN_DS) ? p.alpha * (pd * v[j] - pr * delta) : pd;
         v[j] = round_tf32(o);
       }
     }
-    stage_and_store(&tmC, stg, chunk_ctr, lane, v, p.c_col_base + ch * 32, t.bx * 128 + q * 32, z);
+    stage_and_store<1>(&tmC, stg, chunk_ctr, lane, v, p.c_col_base + ch * 32, t.bx * 128 + q * 32, z);
   }
+  if (EPI == EPI_ATTN_DS) quad_barrier(q);  // delta exchange buffer is free again for the next tile
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(EpiWarps<EPI>::value), 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
@@ -258,6 +290,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float red[4][4][32];  // per-quadrant exchange between the column parts (attention epilogues)
+  constexpr int EW = EpiWarps<EPI>::value;
+  constexpr int NPARTS = EW / 4;
+  constexpr int NBUF = staging_bufs(EW);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -285,7 +321,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full_bar[b], 1);
-      ptx::mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[b], EW);  // one arrival per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -410,9 +446,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // -------------------------------------------------- epilogue warps 2..5
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read (hardware: warp id % 4)
+    const int part = (warp - 2) >> 2;  // which share of the tile's columns
     const int row = q * 32 + lane;
-    uint8_t* stg = staging + q * 8192;  // this warp's two 4-KB staging buffers
+    uint8_t* stg = staging + (warp - 2) * (NBUF * 4096);  // this warp's staging buffer(s)
     int chunk_ctr = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -428,7 +465,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int col0 = p.c_col_base + t.by * p.c_col_mul;  // tmC column of this tile's first column
 
       if (EPI == EPI_SOFTMAX || EPI == EPI_ATTN_DS) {
-        attention_epilogue<EPI>(p, tmC, acc, t, m, row_ok, q, lane, stg, chunk_ctr);
+        attention_epilogue<EPI>(p, tmC, acc, t, m, row_ok, q, part, lane, stg, chunk_ctr, red);
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
@@ -443,7 +480,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI != EPI_LSE && p.tma_store) {
           // ---- 32-column chunks: TMEM -> registers -> swizzled smem -> TMA store (edges clipped by TMA)
           const int zc = t.bz * p.c_z_mul + t.by * p.c_y_mul + tn * p.c_tap_mul;
-          for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          for (int c0 = part * 32; c0 < p.bn; c0 += 32 * NPARTS) {
             if (n0 + c0 >= p.N) break;  // warp-uniform: chunk entirely outside the output
             uint32_t r[32];
             if (c0 + 32 <= p.bn) {
@@ -482,10 +519,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               } else if (p.act == XM_ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              } else if (p.act != XM_ACT_NONE) {
-#pragma unroll 1
-                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-              }
+              }  // tanh / sigmoid are applied by a separate pass (host side): keeps this code compact and in registers
               if (p.round_tf32) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
@@ -501,8 +535,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[j] = round_tf32(g * p.coef);  // rows / columns outside the matrix are clipped by the TMA store
               }
             }
-            uint8_t* sb = stg + (chunk_ctr & 1) * 4096;
-            if (lane == 0) ptx::bulk_wait_read<1>();  // the store that last read this buffer has drained it
+            uint8_t* sb = stg + (NBUF == 2 ? (chunk_ctr & 1) * 4096 : 0);
+            if (lane == 0) ptx::bulk_wait_read<NBUF - 1>();  // the store that last read this buffer has drained it
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)  // 16-B chunk j of row `lane` lives at chunk j ^ (lane & 7) (SWIZZLE_128B)
@@ -518,7 +552,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         } else {
           float* cbase = p.c ? p.c + (long long)t.bz * p.c_z_stride + (long long)tn * p.c_tap_stride : nullptr;
-          for (int c0 = 0; c0 < p.bn; c0 += 16) {
+          for (int c0 = part * 16; c0 < p.bn; c0 += 16 * NPARTS) {
             uint32_t r[16];
             ptx::tmem_ld_32x16(acc + (uint32_t)(tn * p.bn + c0), r);
             ptx::tmem_ld_wait();

@@ -67,7 +67,7 @@ static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
-  gemm_tf32_kernel<EPI><<<ctas, kGemmThreads, smem, stream>>>(ma, mb, mc, ma2, mb2, p);
+  gemm_tf32_kernel<EPI><<<ctas, gemm_threads(EpiWarps<EPI>::value), smem, stream>>>(ma, mb, mc, ma2, mb2, p);
   return check_launch();
 }
 
@@ -95,15 +95,16 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   const int stage_bytes = kATileBytes + p.taps_n * p.bn * 128;
   const int total_kb = p.kout_count * p.taps_k * p.kin_count;
   if (total_kb <= 0) return XM_ERR_INVALID;
-  const int staging = p.tma_store ? kStagingBytes : 0;
-  int stages = (225 * 1024 - 1024 - staging) / stage_bytes;
+  const int epi_warps = (epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) ? 16 : (epi == EPI_LSE ? 4 : 8);
+  const int staging = p.tma_store ? staging_bytes(epi_warps) : 0;
+  int stages = (222 * 1024 - 1024 - staging) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return XM_ERR_UNSUPPORTED;
   p.stages = stages;
   const int acc_cols = p.taps_n * p.bn;
   p.acc_bufs = (2 * acc_cols <= 512 && ntiles > 1 && !p.dual) ? 2 : 1;
   p.tmem_cols = tmem_cols_for(p.dual ? 2 * acc_cols : p.acc_bufs * acc_cols);
-  if ((epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) && (!p.tma_store || (p.bn & 31))) return XM_ERR_UNSUPPORTED;
+  if ((epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) && (!p.tma_store || (p.bn & 127))) return XM_ERR_UNSUPPORTED;
   p.a.rows = 128;
   p.b.rows = p.bn;
   const size_t smem = (size_t)stages * stage_bytes + staging + 1024;
@@ -475,12 +476,15 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
   p.b.sz[0] = 32 * kb_split;
   p.M = (int)M;
   p.N = (int)N;
+  // the GEMM epilogue fuses bias + {none, relu, gelu}; tanh / sigmoid run as a second (in-place) pass
+  const bool late_act = (act == XM_ACT_TANH || act == XM_ACT_SIGMOID);
+  if (late_act && ldy != N) return XM_ERR_UNSUPPORTED;
   if (splits == 1) {
     p.c = y;
     p.ldc = ldy;
     p.bias = bias;
-    p.act = act;
-    p.round_tf32 = round_out;
+    p.act = late_act ? XM_ACT_NONE : act;
+    p.round_tf32 = late_act ? 0 : round_out;
   } else {
     p.c = workspace;
     p.ldc = N;
@@ -492,9 +496,16 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
   const TensorView3 tc = splits == 1 ? TensorView3{y, {(unsigned long long)(N), (unsigned long long)(M), (unsigned long long)(1)}, {(unsigned long long)(ldy) * 4, (unsigned long long)(M * ldy) * 4}}
                                      : TensorView3{workspace, {(unsigned long long)(N), (unsigned long long)(M), (unsigned long long)(splits)}, {(unsigned long long)(N) * 4, (unsigned long long)(M * N) * 4}};
   int rc = launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(N, p.bn), splits), st);
-  if (rc != XM_OK || splits == 1) return rc;
-  splitk_reduce_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(workspace, splits, M, N, bias, y, ldy, act, round_out);
-  return check_launch();
+  if (rc != XM_OK) return rc;
+  if (splits > 1) {
+    splitk_reduce_kernel<<<grid_for(M * N, 256), 256, 0, st>>>(workspace, splits, M, N, bias, y, ldy, act, round_out);
+    return check_launch();
+  }
+  if (late_act) {
+    rc = xm_act_fwd_f32(y, y, M * N, act, 0.f, 0, stream);
+    if (rc == XM_OK && round_out) rc = xm_round_tf32_f32(y, y, M * N, stream);
+  }
+  return rc;
 }
 
 int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,

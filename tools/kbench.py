@@ -57,6 +57,13 @@ def cases(B):
         lse, _ = ops.infonce_lse(e, f, 1 / 0.07)
         return {"lse": lambda: ops.infonce_lse(e, f, 1 / 0.07), "grad": lambda: ops.infonce_grad(e, f, lse, lse, 1 / 0.07, 0, 1e-4)}
     c["infonce"] = nce
+    def attn():
+        qkv = ops.round_tf32(r(B, L, 384))
+        dout = ops.round_tf32(r(B, L, 128))
+        out, probs, lse = ops.attn_fwd(qkv, 4, 32 ** -0.5, 0.3, 77)
+        return {"fwd": lambda: ops.attn_fwd(qkv, 4, 32 ** -0.5, 0.3, 77),
+                "bwd": lambda: ops.attn_bwd(dout, qkv, probs, lse, 4, 32 ** -0.5, 0.3, 77)}
+    c["attn"] = attn
     def pre():
         rec = r(max(B // 64, 1), 128, 512 * 65)
         from multimodal_eeg_fmri_b200 import eeg_data_utils as edu
