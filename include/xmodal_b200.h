@@ -181,6 +181,12 @@ int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int 
  * cores are rounded at their producer so the contraction sees no truncation bias (may run in place). */
 int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream);
 
+/* 3-way tf32 split of x (rows, cols) concatenated along `axis` (0: out (3*rows, cols), 1: out (rows, 3*cols)):
+ * which == 0 -> [hi | lo | hi], which == 1 -> [hi | hi | lo], hi = tf32(x), lo = tf32(x - hi).  A which-0
+ * operand contracted with a which-1 operand over the tripled axis yields an fp32-accurate product from
+ * three tf32 tensor-core passes ("precise" mode of the small projections: fMRI MLPs, bridge, heads). */
+int xm_split3_f32(const float* x, float* out, int64_t rows, int64_t cols, int which, int axis, void* stream);
+
 /* out (N) = column sums of x (M, N) (bias gradients, partial reductions), deterministic two-stage
  * reduction; workspace: xm_colsum_nsplit(M, N) * N floats (may be NULL when nsplit == 1). */
 int xm_colsum_nsplit(int64_t M, int64_t N);
@@ -191,6 +197,13 @@ int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out,
 
 /* xn = x / max(||x||_2, eps) per row (F.normalize), tf32-rounded; inv_norm (M) saved. */
 int xm_l2norm_fwd_f32(const float* x, float* xn, float* inv_norm, int64_t M, int64_t D, float eps, void* stream);
+/* Same normalisation kept in full fp32 (xn) plus xs (M, 3D), the 3-way tf32 split of xn laid out along the
+ * contraction axis: which == 0 -> [hi | lo | hi], which == 1 -> [hi | hi | lo].  The dot product of a
+ * which-0 row with a which-1 row is hi*hi + lo*hi + hi*lo: an fp32-accurate similarity on the tf32
+ * tensor cores (S is divided by the temperature 0.07 before the softmax, which would otherwise
+ * amplify tf32 rounding into ~4e-3 relative error of every probability and gradient). */
+int xm_l2norm_split_fwd_f32(const float* x, float* xn, float* xs, float* inv_norm, int64_t M, int64_t D, float eps,
+                            int which, void* stream);
 /* dx = (dxn - xn * <xn, dxn>) * inv_norm */
 int xm_l2norm_bwd_f32(const float* dxn, const float* xn, const float* inv_norm, float* dx, int64_t M, int64_t D,
                       void* stream);

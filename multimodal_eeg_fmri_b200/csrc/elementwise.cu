@@ -429,6 +429,28 @@ __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict
     out[i] = round_tf32(x[i]);
 }
 
+// 3-way tf32 split of a (rows, cols) matrix, concatenated along `axis`:
+//   which == 0: [hi | lo | hi]     which == 1: [hi | hi | lo]     hi = tf32(x), lo = tf32(x - hi)
+// Contracting a which-0 operand with a which-1 operand over the tripled axis gives hi*hi + lo*hi + hi*lo,
+// an fp32-accurate product on the tf32 tensor cores (used for the small, error-sensitive projections).
+__global__ void split3_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, long long cols,
+                              int which, int axis) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float hi = round_tf32(v);
+    const float lo = round_tf32(v - hi);
+    const float p1 = which == 0 ? lo : hi, p2 = which == 0 ? hi : lo;
+    if (axis == 1) {
+      const long long r = i / cols, c = i - r * cols;
+      float* o = out + r * 3 * cols + c;
+      o[0] = hi; o[cols] = p1; o[2 * cols] = p2;
+    } else {
+      out[i] = hi; out[n + i] = p1; out[2 * n + i] = p2;
+    }
+  }
+}
+
 // float4 variants (n % 4 == 0, 16-B aligned)
 __global__ void act_fwd_v4_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4, int act,
                                   float drop_scale, uint32_t drop_thresh, uint64_t seed, int round_out) {
@@ -566,6 +588,34 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
   const float inv = 1.0f / fmaxf(sqrtf(warp_sum(q)), eps);
   if (lane == 0) inv_norm[row] = inv;
   for (int d = lane; d < D; d += 32) xn[row * D + d] = round_tf32(x[row * D + d] * inv);
+}
+// xn = x / max(||x||, eps) in full fp32 plus the 3-way tf32 split xs (M, 3D) of xn:
+//   which == 0: [hi | lo | hi]      which == 1: [hi | hi | lo]      hi = tf32(xn), lo = tf32(xn - hi)
+// so that  xs_a . xs_b = hi_a hi_b + lo_a hi_b + hi_a lo_b  ~ fp32-accurate dot product on the tf32 tensor cores
+// (the similarity is divided by tau = 0.07 before the softmax: a plain tf32 product would put ~4e-3 of
+// relative noise into every softmax probability and hence into every contrastive gradient).
+__global__ void l2norm_split_fwd_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ xs,
+                                        float* __restrict__ inv_norm, long long M, int D, float eps, int which) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  float q = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = x[row * D + d];
+    q += v * v;
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(q)), eps);
+  if (lane == 0) inv_norm[row] = inv;
+  for (int d = lane; d < D; d += 32) {
+    const float v = x[row * D + d] * inv;
+    const float hi = round_tf32(v);
+    const float lo = round_tf32(v - hi);
+    xn[row * D + d] = v;
+    float* o = xs + row * 3ll * D;
+    o[d] = hi;
+    o[D + d] = which == 0 ? lo : hi;
+    o[2 * D + d] = which == 0 ? hi : lo;
+  }
 }
 __global__ void l2norm_bwd_kernel(const float* __restrict__ dxn, const float* __restrict__ xn,
                                   const float* __restrict__ inv_norm, float* __restrict__ dx, long long M, int D) {
@@ -1138,6 +1188,12 @@ int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream) {
   return check_launch();
 }
 
+int xm_split3_f32(const float* x, float* out, int64_t rows, int64_t cols, int which, int axis, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0 || (which != 0 && which != 1) || (axis != 0 && axis != 1)) return XM_ERR_INVALID;
+  split3_kernel<<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>(x, out, rows, cols, which, axis);
+  return check_launch();
+}
+
 int xm_colsum_nsplit(int64_t M, int64_t N) {
   const long long col_blocks = (N + 127) / 128;
   long long want = (8ll * kNumSMs + col_blocks - 1) / col_blocks;  // ~8 CTAs per SM in total
@@ -1169,6 +1225,12 @@ int xm_colsum_f32(const float* x, int64_t M, int64_t N, int64_t ldx, float* out,
 int xm_l2norm_fwd_f32(const float* x, float* xn, float* inv_norm, int64_t M, int64_t D, float eps, void* stream) {
   if (!x || !xn || !inv_norm || M <= 0 || D <= 0) return XM_ERR_INVALID;
   l2norm_fwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, xn, inv_norm, M, (int)D, eps);
+  return check_launch();
+}
+int xm_l2norm_split_fwd_f32(const float* x, float* xn, float* xs, float* inv_norm, int64_t M, int64_t D, float eps,
+                            int which, void* stream) {
+  if (!x || !xn || !xs || !inv_norm || M <= 0 || D <= 0) return XM_ERR_INVALID;
+  l2norm_split_fwd_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>(x, xn, xs, inv_norm, M, (int)D, eps, which);
   return check_launch();
 }
 int xm_l2norm_bwd_f32(const float* dxn, const float* xn, const float* inv_norm, float* dx, int64_t M, int64_t D,

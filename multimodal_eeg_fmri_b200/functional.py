@@ -168,27 +168,48 @@ def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=Fa
 
 
 # ----------------------------------------------------------------------------- linear blocks
+def _tf32(t, already=False):
+    """Operand for a tensor-core contraction: rounded to nearest tf32 unless its producer already did.
+    (The tensor core would otherwise TRUNCATE the low 13 mantissa bits, a systematic -2^-11 relative bias
+    per operand that accumulates across layers; round-to-nearest leaves only zero-mean noise.)"""
+    return t if already else ops.round_tf32(t)
+
+
 class Linear(torch.autograd.Function):
-    """y = x @ w^T + b on the tcgen05 GEMM (nn.Linear).  `round_out` rounds y to tf32 (set when y feeds
-    another tensor-core contraction directly, e.g. the packed q/k/v projections)."""
+    """y = x @ w^T + b on the tcgen05 GEMM (nn.Linear).
+
+    precise=True  : three tf32 passes over a tripled contraction axis (fp32-accurate; the small,
+                    error-sensitive projections: fMRI MLPs, bridge, gates, heads).
+    precise=False : one tf32 pass with operands rounded to nearest at their producers (the large
+                    transformer projections).  `round_out` rounds y to tf32 (y feeds another contraction
+                    directly); `x_rounded` says the producer of x already rounded it."""
 
     @staticmethod
-    def forward(ctx, x, w, b, round_out=False):
-        ctx.save_for_backward(x, w)
-        ctx.has_bias = b is not None
-        return ops.linear_fwd(x, w, b, round_out=round_out)
+    def forward(ctx, x, w, b, round_out=False, x_rounded=False, precise=False):
+        ctx.has_bias, ctx.precise = b is not None, precise
+        if precise:
+            ctx.save_for_backward(x, w)
+            return ops.linear_fwd_precise(x, w, b)
+        xr, wr = _tf32(x, x_rounded), _tf32(w)
+        ctx.save_for_backward(xr, wr)
+        return ops.linear_fwd(xr, wr, b, round_out=round_out)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.linear_wgrad(dy, x, need_bias=ctx.has_bias)
-        return dx, dw, db, None
+        if ctx.precise:
+            dx = ops.linear_dgrad_precise(dy, w) if ctx.needs_input_grad[0] else None
+            dw, db = ops.linear_wgrad_precise(dy, x, need_bias=ctx.has_bias)
+        else:
+            dyr = _tf32(dy)
+            dx = ops.linear_dgrad(dyr, w) if ctx.needs_input_grad[0] else None
+            dw, db = ops.linear_wgrad(dyr, x, need_bias=ctx.has_bias)
+        return dx, dw, db, None, None, None
 
 
-def linear(x, lin):
-    return Linear.apply(x, lin.weight, lin.bias)
+def linear(x, lin, precise=True):
+    return Linear.apply(x, lin.weight, lin.bias, False, False, precise)
 
 
 class ActDropout(torch.autograd.Function):
@@ -214,12 +235,14 @@ def act_dropout(x, act, drop_p=0.0, training=True):
 
 class LinearBnAct(torch.autograd.Function):
     """Linear -> BatchNorm1d -> act -> Dropout on (B, F) rows (fMRI_CODE/fmri_utils.py:26-35, 66-71;
-    crossmodal_v4_enhancements.py:696-723, 768-773, 909-914)."""
+    crossmodal_v4_enhancements.py:696-723, 768-773, 909-914).  The projection runs in the fp32-accurate
+    3-pass mode: BatchNorm's backward subtracts batch means (a cancellation that would amplify
+    single-pass tf32 noise of these small layers into percent-level gradient errors)."""
 
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, cfg):
         eps, momentum, act, p, training = cfg
-        y = ops.linear_fwd(x, w, b)
+        y = ops.linear_fwd_precise(x, w, b)
         mean, invstd, count = _bn_stats(y, eps, running_mean, running_var, momentum, training)
         seed = next_seed() if (training and p > 0) else 0
         pd = p if training else 0.0
@@ -234,8 +257,8 @@ class LinearBnAct(torch.autograd.Function):
         count, act, pd, seed, training = ctx.meta
         dout = dout.contiguous()
         dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, 0, pd, seed, False, training, False)
-        dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.linear_wgrad(dy, x, need_bias=True)
+        dx = ops.linear_dgrad_precise(dy, w) if ctx.needs_input_grad[0] else None
+        dw, db = ops.linear_wgrad_precise(dy, x, need_bias=True)
         return dx, dw, db, dgamma, dbeta, None, None, None
 
 
@@ -252,7 +275,7 @@ class LinearLnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, cfg):
         eps, act, p, training = cfg
-        y = ops.linear_fwd(x, w, b)
+        y = ops.linear_fwd_precise(x, w, b)
         seed = next_seed() if (training and p > 0) else 0
         pd = p if training else 0.0
         out, mean, rstd = ops.ln_act_fwd(y, gamma, beta, eps, act, pd, seed)
@@ -265,8 +288,8 @@ class LinearLnAct(torch.autograd.Function):
         x, w, y, mean, rstd, gamma, beta = ctx.saved_tensors
         act, pd, seed = ctx.meta
         dy, dgamma, dbeta = ops.ln_act_bwd(dout.contiguous(), y, gamma, beta, mean, rstd, act, pd, seed)
-        dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.linear_wgrad(dy, x, need_bias=True)
+        dx = ops.linear_dgrad_precise(dy, w) if ctx.needs_input_grad[0] else None
+        dw, db = ops.linear_wgrad_precise(dy, x, need_bias=True)
         return dx, dw, db, dgamma, dbeta, None
 
 
@@ -294,7 +317,7 @@ class SelfAttentionCore(torch.autograd.Function):
     def backward(ctx, dout):
         qkv, probs, lse = ctx.saved_tensors
         nhead, scale, p, seed = ctx.meta
-        return ops.attn_bwd(dout, qkv, probs, lse, nhead, scale, p, seed), None, None, None
+        return ops.attn_bwd(_tf32(dout.contiguous()), qkv, probs, lse, nhead, scale, p, seed), None, None, None
 
 
 def self_attention_core(qkv, nhead, drop_p=0.0, training=True):
@@ -352,30 +375,32 @@ class SymmetricInfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, e, f, temperature):
         inv_tau = 1.0 / float(temperature)
-        en, einv = ops.l2norm_fwd(e)
-        fn, finv = ops.l2norm_fwd(f)
-        e_all = _AllGatherRows.gather(en)
-        f_all = _AllGatherRows.gather(fn)
-        Bl, Bg = en.shape[0], e_all.shape[0]
+        # fp32 unit vectors + their 3-way tf32 splits: the similarity contraction is fp32-accurate
+        en, e3, einv = ops.l2norm_split_fwd(e, 0)
+        fn, f3, finv = ops.l2norm_split_fwd(f, 1)
+        e3_all = _AllGatherRows.gather(e3)
+        f3_all = _AllGatherRows.gather(f3)
+        Bl, Bg = en.shape[0], e3_all.shape[0]
         off = _CTX.rank * Bl if _CTX.active else 0
-        lse_ef, diag = ops.infonce_lse(en, f_all, inv_tau, off)
-        lse_fe, _ = ops.infonce_lse(fn, e_all, inv_tau, off)
+        lse_ef, diag = ops.infonce_lse(e3, f3_all, inv_tau, off)
+        lse_fe, _ = ops.infonce_lse(f3, e3_all, inv_tau, off)
         loss = (0.5 / Bg) * ((lse_ef - diag).sum() + (lse_fe - diag).sum())
-        ctx.save_for_backward(en, fn, einv, finv, e_all, f_all, lse_ef, lse_fe)
+        ctx.save_for_backward(en, fn, einv, finv, e3, f3, e3_all, f3_all, lse_ef, lse_fe)
         ctx.meta = (inv_tau, off, Bg)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        en, fn, einv, finv, e_all, f_all, lse_ef, lse_fe = ctx.saved_tensors
+        en, fn, einv, finv, e3, f3, e3_all, f3_all, lse_ef, lse_fe = ctx.saved_tensors
         inv_tau, off, Bg = ctx.meta
+        D = en.shape[1]
         lse_ef_all = _AllGatherRows.gather(lse_ef)
         lse_fe_all = _AllGatherRows.gather(lse_fe)
         coef = 0.5 * inv_tau / Bg
-        G1 = ops.infonce_grad(en, f_all, lse_ef, lse_fe_all, inv_tau, off, coef)  # rows: my e, cols: all f
-        den = ops.linear_dgrad(G1, f_all)
-        G2 = ops.infonce_grad(fn, e_all, lse_fe, lse_ef_all, inv_tau, off, coef)  # rows: my f, cols: all e
-        dfn = ops.linear_dgrad(G2, e_all)
+        G1 = ops.infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, off, coef)  # rows: my e, cols: all f
+        den = ops.linear_dgrad(G1, f3_all[:, :D])                                   # hi part = tf32(f_n)
+        G2 = ops.infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, off, coef)  # rows: my f, cols: all e
+        dfn = ops.linear_dgrad(G2, e3_all[:, :D])
         de = ops.l2norm_bwd(den, en, einv) * g
         df = ops.l2norm_bwd(dfn, fn, finv) * g
         return de, df, None
@@ -387,6 +412,6 @@ def symmetric_infonce(e, f, temperature=0.07):
 
 def similarity_matrix(e, f, temperature=0.07):
     """Materialised S = normalize(e) @ normalize(f)^T / temperature (no gradient; inspection / retrieval)."""
-    en, _ = ops.l2norm_fwd(e.detach().contiguous())
-    fn, _ = ops.l2norm_fwd(f.detach().contiguous())
-    return ops.similarity(en, fn, 1.0 / float(temperature))
+    _, e3, _ = ops.l2norm_split_fwd(e.detach().contiguous(), 0)
+    _, f3, _ = ops.l2norm_split_fwd(f.detach().contiguous(), 1)
+    return ops.similarity(e3, f3, 1.0 / float(temperature))

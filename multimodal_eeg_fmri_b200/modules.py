@@ -74,16 +74,17 @@ class TemporalTransformerBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, L, d = x.shape
-        lin = XF.Linear.apply  # the four projections run on the tcgen05 TF32 GEMM over (B*L, d) rows
+        lin = XF.Linear.apply  # the four projections: single-pass tf32 tcgen05 GEMMs over (B*L, d) rows
         h = F.layer_norm(x, (d,), self.norm1.weight, self.norm1.bias, self.norm1.eps)
         qkv = lin(h.reshape(B * L, d), self.self_attn.in_proj_weight, self.self_attn.in_proj_bias, True).view(B, L, 3 * d)
-        if mask is None and XF.attention_core_supported(L, d // self.nhead):
+        fused = mask is None and XF.attention_core_supported(L, d // self.nhead)
+        if fused:  # the fused core writes tf32-rounded head outputs (operand of out_proj)
             a = XF.self_attention_core(qkv, self.nhead, self.p, self.training).reshape(B * L, d)
         else:  # shapes outside the fused kernel (head dim != 32, L > 256, explicit mask): library attention
             q, k, v = (t.view(B, L, self.nhead, d // self.nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
             a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.p if self.training else 0.0)
             a = a.transpose(1, 2).reshape(B * L, d)
-        a = lin(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias).view(B, L, d)
+        a = lin(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, False, fused).view(B, L, d)
         x = x + F.dropout(a, self.p, self.training)
         h = F.layer_norm(x, (d,), self.norm2.weight, self.norm2.bias, self.norm2.eps)
         h = lin(h.reshape(B * L, d), self.linear1.weight, self.linear1.bias)
@@ -400,8 +401,8 @@ class EEGfMRIBridgeFusionNet(nn.Module):
         B, d = e.shape
         H, dh = self.num_heads, d // self.num_heads
         W, b = self.cross_attn.in_proj_weight, self.cross_attn.in_proj_bias
-        q = XF.Linear.apply(e, W[:d], b[:d]).view(B, H, dh)
-        kv = XF.Linear.apply(torch.cat([e, f], dim=0), W[d:], b[d:])  # keys and values of both tokens
+        q = XF.Linear.apply(e, W[:d], b[:d], False, False, True).view(B, H, dh)
+        kv = XF.Linear.apply(torch.cat([e, f], dim=0), W[d:], b[d:], False, False, True)  # keys and values of both tokens
         k = kv[:, :d].reshape(2, B, H, dh)
         v = kv[:, d:].reshape(2, B, H, dh)
         att = torch.softmax((q.unsqueeze(0) * k).sum(-1) / math.sqrt(dh), dim=0)  # (2, B, H)

@@ -395,6 +395,31 @@ def act_bwd(dout, x, act, drop_p=0.0, seed=0):
     return dx
 
 
+def split3(x, which, axis):
+    """3-way tf32 split of a 2-D tensor along `axis` ([hi|lo|hi] for which=0, [hi|hi|lo] for which=1)."""
+    _chk(x)
+    x = x.contiguous()
+    R, C = x.shape
+    out = torch.empty((3 * R, C) if axis == 0 else (R, 3 * C), device=x.device, dtype=torch.float32)
+    _w(3.0 * R * C, 16.0 * R * C)
+    _call("xm_split3_f32", _p(x), _p(out), R, C, int(which), int(axis), _stream())
+    return out
+
+
+def linear_fwd_precise(x, w, bias=None, act=None):
+    """fp32-accurate y = x @ w^T + b: three tf32 passes fused into one GEMM over a tripled K."""
+    return linear_fwd(split3(x, 0, 1), split3(w, 1, 1), bias, act=act)
+
+
+def linear_dgrad_precise(dy, w):
+    return linear_dgrad(split3(dy, 0, 1), split3(w, 1, 0))
+
+
+def linear_wgrad_precise(dy, x, need_bias=True):
+    dw, _ = linear_wgrad(split3(dy, 0, 0), split3(x, 1, 0), need_bias=False)
+    return dw, (colsum(dy) if need_bias else None)
+
+
 def round_tf32(x, inplace=False):
     """Round to nearest tf32 (what the tensor cores would otherwise truncate to)."""
     _chk(x)
@@ -432,6 +457,19 @@ def l2norm_fwd(x, eps=1e-12):
     _w(3.0 * M * D, 8.0 * M * D)
     _call("xm_l2norm_fwd_f32", _p(x), _p(xn), _p(inv), M, D, float(eps), _stream())
     return xn, inv
+
+
+def l2norm_split_fwd(x, which, eps=1e-12):
+    """-> (xn fp32 (M, D), xs (M, 3D) tf32 split [hi|lo|hi] (which=0) or [hi|hi|lo] (which=1), inv_norm)."""
+    _chk(x)
+    x = x.contiguous()
+    M, D = x.shape
+    xn = torch.empty_like(x)
+    xs = torch.empty(M, 3 * D, device=x.device, dtype=torch.float32)
+    inv = torch.empty(M, device=x.device, dtype=torch.float32)
+    _w(6.0 * M * D, 20.0 * M * D)
+    _call("xm_l2norm_split_fwd_f32", _p(x), _p(xn), _p(xs), _p(inv), M, D, float(eps), int(which), _stream())
+    return xn, xs, inv
 
 
 def l2norm_bwd(dxn, xn, inv):

@@ -67,3 +67,25 @@ def assert_close_rel(a, b, tol, what="", atol=0.0):
     err = float((a - b).norm())
     bound = tol * float(b.norm()) + atol * (b.numel() ** 0.5)
     assert err <= bound, f"{what}: ||a-b|| = {err:.3e} > {bound:.3e} (rel {err / (float(b.norm()) + 1e-30):.3e}, tol {tol:.1e})"
+
+
+def bias_before_batchnorm(keys):
+    """Keys `<head>.<i>.bias` of a Conv1d/Linear directly followed by a BatchNorm (`<head>.<i+1>.running_mean`
+    exists): their gradient is mathematically zero in train mode (BN subtracts the batch mean), so only an
+    absolute noise bound is meaningful for them."""
+    keys = set(keys)
+    out = set()
+    for k in keys:
+        if not k.endswith(".bias"):
+            continue
+        head, _, idx = k[: -len(".bias")].rpartition(".")
+        if idx.isdigit() and f"{head}.{int(idx) + 1}.running_mean" in keys:
+            out.add(k)
+    return out
+
+
+def assert_zero_grad_noise(g_bias, g_weight, what="", frac=2e-3):
+    """|g_bias| must be rounding noise: far below the scale of the layer's weight gradient."""
+    gb, gw = _t(g_bias), _t(g_weight)
+    scale = float(gw.abs().sum()) / max(gb.numel(), 1)  # mean absolute row sum of the weight gradient
+    assert float(gb.abs().max()) <= frac * scale + 1e-7, f"{what}: |grad| {float(gb.abs().max()):.3e} vs scale {scale:.3e}"

@@ -195,6 +195,18 @@ def round_tf32(x, inplace=False):
     return x
 
 
+def linear_fwd_precise(x, w, bias=None, act=None):
+    return linear_fwd(x, w, bias, act)
+
+
+def linear_dgrad_precise(dy, w):
+    return linear_dgrad(dy, w)
+
+
+def linear_wgrad_precise(dy, x, need_bias=True):
+    return linear_wgrad(dy, x, need_bias)
+
+
 def colsum(x):
     return x.double().sum(0).float()
 
@@ -203,6 +215,12 @@ def colsum(x):
 def l2norm_fwd(x, eps=1e-12):
     n = x.double().norm(dim=1).clamp_min(eps)
     return (x.double() / n[:, None]).float(), (1.0 / n).float()
+
+
+def l2norm_split_fwd(x, which, eps=1e-12):
+    xn, inv = l2norm_fwd(x, eps)
+    z = torch.zeros_like(xn)
+    return xn, torch.cat([xn, z, z], 1), inv
 
 
 def l2norm_bwd(dxn, xn, inv):

