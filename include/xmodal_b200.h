@@ -173,9 +173,10 @@ int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, con
 
 /* out = drop(act(x)) over n contiguous elements, and its backward dx = dout * mask * act'(x)
  * (nn.GELU/ReLU/Tanh/Sigmoid + nn.Dropout after a projection). */
-int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p, uint64_t seed, void* stream);
-int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
+int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p, uint64_t seed, int round_out,
                    void* stream);
+int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
+                   int round_out, void* stream);
 
 /* out = x rounded to nearest tf32 (10-bit mantissa) in an fp32 container: operands handed to the tensor
  * cores are rounded at their producer so the contraction sees no truncation bias (may run in place). */
@@ -232,7 +233,30 @@ int xm_attn_fwd_f32(const float* qkv, float* out, float* probs, float* lse, int6
                     float scale, float drop_p, uint64_t seed, int round_out, void* stream);
 /* dqkv (B, L, 3*H*dh) from dout (B, L, H*dh); ds: (B*H, L, NP) workspace for the score gradients. */
 int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, const float* lse, float* dqkv, float* ds,
-                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, void* stream);
+                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, int round_out,
+                    void* stream);
+
+/* ------------------------------------------------------------------ residual stream of the pre-norm transformer block
+ * EEG_CODE/enhanced_models_v4.py:89-107 (x + Dropout(branch), LayerNorm) and :44-55 (x + pe, Dropout), fused:
+ *   s = x + Dropout(a)            [a may be NULL]      or      s = Dropout(x + pe[row % L])   [pe may be NULL]
+ *   h = tf32(LayerNorm(s) * gamma + beta);   mean / rstd (M) saved.
+ * s_out may be NULL when a == pe == NULL (s == x).  D % 128 == 0, 128 <= D <= 512 (xm_resid_ln_supported). */
+int xm_resid_ln_supported(int64_t D);
+int xm_resid_ln_fwd_f32(const float* x, const float* a, const float* pe, int64_t L, const float* gamma, const float* beta,
+                        float* s_out, float* h, float* mean, float* rstd, int64_t M, int64_t D, float eps, float drop_p,
+                        uint64_t seed, void* stream);
+/* ds = dres + LayerNormBackward(dh) [dres may be NULL];  dx = ds;  da = tf32(mask * ds / (1-p)) [da may be NULL];
+ * dgamma_part / dbeta_part: (xm_resid_ln_nblk(M), D) per-block partial sums (reduce with xm_colsum_f32). */
+int xm_resid_ln_nblk(int64_t M);
+int xm_resid_ln_bwd_f32(const float* dh, const float* dres, const float* s, const float* gamma, const float* mean,
+                        const float* rstd, float* dx, float* da, float* dgamma_part, float* dbeta_part, int64_t M, int64_t D,
+                        float drop_p, uint64_t seed, void* stream);
+/* out (B, D) = mean over T of x + Dropout(a)  (last residual add + AdaptiveAvgPool1d(1), :161-163), and its
+ * backward: dx = dout / T broadcast, da = tf32(mask * dx / (1-p)); either output may be NULL. */
+int xm_resid_seqmean_fwd_f32(const float* x, const float* a, int64_t B, int64_t T, int64_t D, float* out, float drop_p,
+                             uint64_t seed, void* stream);
+int xm_resid_seqmean_bwd_f32(const float* dout, int64_t B, int64_t T, int64_t D, float* dx, float* da, float drop_p,
+                             uint64_t seed, void* stream);
 
 /* ------------------------------------------------------------------ diagnostics (not on the product path)
  * Dump the raw shared-memory image of one TMA box {32,32} loaded at (c0, c1) from a (rows, cols)

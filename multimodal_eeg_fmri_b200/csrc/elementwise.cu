@@ -1151,31 +1151,36 @@ int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, con
   return check_launch();
 }
 
-int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p, uint64_t seed, void* stream) {
+int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p, uint64_t seed, int round_out,
+                   void* stream) {
   if (!x || !out || n <= 0 || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
   float sc;
   uint32_t th;
   drop_consts(drop_p, sc, th);
   if ((n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    act_fwd_v4_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, out, n / 4, act, sc, th, seed, 0);
+    act_fwd_v4_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(x, out, n / 4, act, sc, th, seed, round_out);
     return check_launch();
   }
   act_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, out, n, act, sc, th, seed);
-  return check_launch();
+  int rc = check_launch();
+  if (rc == XM_OK && round_out) rc = xm_round_tf32_f32(out, out, n, stream);
+  return rc;
 }
 int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
-                   void* stream) {
+                   int round_out, void* stream) {
   if (!dout || !x || !dx || n <= 0 || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
   float sc;
   uint32_t th;
   drop_consts(drop_p, sc, th);
   if ((n % 4 == 0) &&
       ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
-    act_bwd_v4_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(dout, x, dx, n / 4, act, sc, th, seed, 0);
+    act_bwd_v4_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(dout, x, dx, n / 4, act, sc, th, seed, round_out);
     return check_launch();
   }
   act_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dout, x, dx, n, act, sc, th, seed);
-  return check_launch();
+  int rc = check_launch();
+  if (rc == XM_OK && round_out) rc = xm_round_tf32_f32(dx, dx, n, stream);
+  return rc;
 }
 
 int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream) {

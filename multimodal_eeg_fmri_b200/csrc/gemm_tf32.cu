@@ -368,7 +368,8 @@ int xm_attn_fwd_f32(const float* qkv, float* out, float* probs, float* lse, int6
 }
 
 int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, const float* lse, float* dqkv, float* ds,
-                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, void* stream) {
+                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, int round_out,
+                    void* stream) {
   if (!dout || !qkv || !probs || !lse || !dqkv || !ds || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
   AttnDims d;
   int rc = attn_dims(d, B, L, H, dh);
@@ -401,6 +402,7 @@ int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, con
     qkv_mnmajor(p.b, d, 0);
     head_output(p, d, 2 * H * dh);
     p.kin_count = kq;
+    p.round_tf32 = round_out;
     rc = launch_gemm(EPI_ROWMAJOR, tp, tdo, tdq, p, grid, st);
     if (rc != XM_OK) return rc;
   }
@@ -411,6 +413,7 @@ int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, con
     qkv_mnmajor(p.b, d, 0);
     head_output(p, d, H * dh);
     p.kin_count = kq;
+    p.round_tf32 = round_out;
     rc = launch_gemm(EPI_ROWMAJOR, ts, tq, tdq, p, grid, st);
     if (rc != XM_OK) return rc;
   }
@@ -421,6 +424,7 @@ int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, con
     qkv_mnmajor(p.b, d, H * dh);
     head_output(p, d, 0);
     p.kin_count = (int)(d.NP / 32);
+    p.round_tf32 = round_out;
     rc = launch_gemm(EPI_ROWMAJOR, ts, tq, tdq, p, grid, st);
   }
   return rc;
@@ -502,8 +506,7 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
     return check_launch();
   }
   if (late_act) {
-    rc = xm_act_fwd_f32(y, y, M * N, act, 0.f, 0, stream);
-    if (rc == XM_OK && round_out) rc = xm_round_tf32_f32(y, y, M * N, stream);
+    rc = xm_act_fwd_f32(y, y, M * N, act, 0.f, 0, round_out, stream);
   }
   return rc;
 }

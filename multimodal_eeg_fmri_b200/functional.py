@@ -329,6 +329,101 @@ def attention_core_supported(L: int, dh: int) -> bool:
     return ops.attn_supported(L, dh)
 
 
+# ----------------------------------------------------------------------------- transformer tail
+class TransformerTail(torch.autograd.Function):
+    """PositionalEncoding -> N x TemporalTransformerBlock -> mean over time, as ONE function over the token
+    matrix (EEG_CODE/enhanced_models_v4.py:44-55, 89-107, 161-163), forward and hand-written backward.
+
+    Per block: [residual add + Dropout + LayerNorm] fused kernel -> in_proj GEMM -> attention core ->
+    out_proj GEMM -> [residual add + Dropout + LayerNorm] -> linear1 GEMM -> GELU+Dropout -> linear2 GEMM;
+    the add of a block's FFN output is fused into the NEXT block's LayerNorm kernel (or into the final mean).
+    Every GEMM operand is rounded to tf32 by the kernel that produces it; dropout masks are regenerated from
+    seeds in the backward.  params: 12 tensors per block in the order
+    (norm1.w, norm1.b, in_proj_weight, in_proj_bias, out_proj.w, out_proj.b, norm2.w, norm2.b, linear1.w,
+    linear1.b, linear2.w, linear2.b)."""
+
+    NP = 12
+
+    @staticmethod
+    def forward(ctx, h0, pe, cfg, *params):
+        nhead, p, eps, act, training = cfg
+        p = float(p) if training else 0.0
+        B, L, D = h0.shape
+        M = B * L
+        nl = len(params) // TransformerTail.NP
+        scale = 1.0 / ((D // nhead) ** 0.5)
+        seed = (lambda: next_seed()) if p > 0 else (lambda: 0)
+        x = h0.reshape(M, D)
+        saved, meta = [], []
+        pend, pend_seed = None, 0
+        seed_pe = seed()
+        for l in range(nl):
+            n1w, n1b, wqkv, bqkv, wo, bo, n2w, n2b, w1, b1, w2, b2 = params[l * 12:(l + 1) * 12]
+            if l == 0:
+                x1, h1, m1, r1 = ops.resid_ln_fwd(x, None, n1w, n1b, eps, p, seed_pe, pe=pe, L=L)
+            else:
+                x1, h1, m1, r1 = ops.resid_ln_fwd(x, pend, n1w, n1b, eps, p, pend_seed)
+            wqkv_r, wo_r, w1_r, w2_r = (ops.round_tf32(w) for w in (wqkv, wo, w1, w2))
+            qkv = ops.linear_fwd(h1, wqkv_r, bqkv, round_out=True)
+            s_attn = seed()
+            att, probs, lse = ops.attn_fwd(qkv.view(B, L, 3 * D), nhead, scale, p, s_attn, round_out=True)
+            ao = ops.linear_fwd(att.view(M, D), wo_r, bo)
+            s_ao = seed()
+            x2, h2, m2, r2 = ops.resid_ln_fwd(x1, ao, n2w, n2b, eps, p, s_ao)
+            del ao
+            f1 = ops.linear_fwd(h2, w1_r, b1)
+            s_g = seed()
+            g = ops.act_fwd(f1, act, p, s_g, round_out=True)
+            f2 = ops.linear_fwd(g, w2_r, b2)
+            saved += [x1, h1, m1, r1, qkv, probs, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w]
+            meta.append((s_attn, s_ao, s_g, pend_seed if l > 0 else seed_pe))
+            x, pend, pend_seed = x2, f2, seed()
+        out = ops.resid_seqmean_fwd(x.view(B, L, D), pend.view(B, L, D), p, pend_seed)
+        ctx.save_for_backward(*saved)
+        ctx.meta = (B, L, D, nl, nhead, p, act, scale, meta, pend_seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, L, D, nl, nhead, p, act, scale, meta, last_seed = ctx.meta
+        M = B * L
+        sv = ctx.saved_tensors
+        dxs, df2 = ops.resid_seqmean_bwd(dout.contiguous(), L, p, last_seed)
+        dxs, df2 = dxs.view(M, D), df2.view(M, D)
+        grads = [None] * (nl * 12)
+        dh0 = None
+        for l in reversed(range(nl)):
+            (x1, h1, m1, r1, qkv, probs, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w) = sv[l * 20:(l + 1) * 20]
+            s_attn, s_ao, s_g, s_in = meta[l]
+            dg = ops.linear_dgrad(df2, w2_r)
+            dw2, db2 = ops.linear_wgrad(df2, g)
+            df1 = ops.act_bwd(dg, f1, act, p, s_g, round_out=True)
+            del dg
+            dh2 = ops.linear_dgrad(df1, w1_r)
+            dw1, db1 = ops.linear_wgrad(df1, h2)
+            del df1
+            dx1, dao, dn2w, dn2b = ops.resid_ln_bwd(dh2, dxs, x2, n2w, m2, r2, p, s_ao)
+            datt = ops.linear_dgrad(dao, wo_r, round_out=True)
+            dwo, dbo = ops.linear_wgrad(dao, att.view(M, D))
+            dqkv = ops.attn_bwd(datt.view(B, L, D), qkv.view(B, L, 3 * D), probs, lse, nhead, scale, p, s_attn, round_out=True)
+            dqkv = dqkv.view(M, 3 * D)
+            dh1 = ops.linear_dgrad(dqkv, wqkv_r)
+            dwqkv, dbqkv = ops.linear_wgrad(dqkv, h1)
+            need_in = l > 0 or ctx.needs_input_grad[0]
+            dxs, dprev, dn1w, dn1b = ops.resid_ln_bwd(dh1, dx1, x1, n1w, m1, r1, p, s_in, need_da=need_in)
+            grads[l * 12:(l + 1) * 12] = [dn1w, dn1b, dwqkv, dbqkv, dwo, dbo, dn2w, dn2b, dw1, db1, dw2, db2]
+            if l > 0:
+                df2 = dprev  # gradient of the previous block's FFN branch (its dropout mask applied)
+            else:
+                dh0 = None if dprev is None else dprev.view(B, L, D)  # d/d(conv output): Dropout(x + pe) backward
+        return (dh0, None, None, *grads)
+
+
+def transformer_tail_supported(L: int, D: int, nhead: int, act: str) -> bool:
+    return (D % nhead == 0 and ops.attn_supported(L, D // nhead) and ops.resid_ln_supported(D)
+            and act in ("gelu", "relu"))
+
+
 # ----------------------------------------------------------------------------- pooling
 class SeqMean(torch.autograd.Function):
     """AdaptiveAvgPool1d(1) + Flatten on channels-last input: (B, T, C) -> (B, C)."""

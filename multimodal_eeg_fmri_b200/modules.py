@@ -104,10 +104,23 @@ class _TransformerTail(nn.Module):
 
     def _tail(self, h: torch.Tensor) -> torch.Tensor:
         # h: (B, L, D) channels-last conv output == the transformer's batch-first sequence layout
-        h = self.pos_encoder(h)
-        for blk in self.transformer_layers:
-            h = blk(h)
-        h = XF.seq_mean(h)  # AdaptiveAvgPool1d(1) + Flatten
+        B, L, D = h.shape
+        blocks = list(self.transformer_layers)
+        b0 = blocks[0] if blocks else None
+        if b0 is not None and XF.transformer_tail_supported(L, D, b0.nhead, b0.act) and L <= self.pos_encoder.pe.shape[0]:
+            # fused tail: PE + blocks + mean-pool as one function over the token matrix
+            params = []
+            for blk in blocks:
+                params += [blk.norm1.weight, blk.norm1.bias, blk.self_attn.in_proj_weight, blk.self_attn.in_proj_bias,
+                           blk.self_attn.out_proj.weight, blk.self_attn.out_proj.bias, blk.norm2.weight, blk.norm2.bias,
+                           blk.linear1.weight, blk.linear1.bias, blk.linear2.weight, blk.linear2.bias]
+            cfg = (b0.nhead, self.dropout_p, b0.norm1.eps, b0.act, self.training)
+            h = XF.TransformerTail.apply(h.contiguous(), self.pos_encoder.pe[:L, 0, :].contiguous(), cfg, *params)
+        else:  # shapes outside the fused kernels (head dim != 32, L > 256, d_model % 128 != 0)
+            h = self.pos_encoder(h)
+            for blk in blocks:
+                h = blk(h)
+            h = XF.seq_mean(h)  # AdaptiveAvgPool1d(1) + Flatten
         h = XF.linear(h, self.output_proj[2])
         return XF.act_dropout(h, "gelu", self.dropout_p, self.training)
 

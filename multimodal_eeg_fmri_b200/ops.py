@@ -377,21 +377,22 @@ def ln_act_bwd(dout, x, gamma, beta, mean, rstd, act, drop_p=0.0, seed=0):
 
 
 # ------------------------------------------------------------------ activation + dropout
-def act_fwd(x, act, drop_p=0.0, seed=0):
+def act_fwd(x, act, drop_p=0.0, seed=0, round_out=False):
     _chk(x)
     x = x.contiguous()
     out = torch.empty_like(x)
     _w(10.0 * x.numel(), 8.0 * x.numel())
-    _call("xm_act_fwd_f32", _p(x), _p(out), x.numel(), act_code(act), float(drop_p), int(seed), _stream())
+    _call("xm_act_fwd_f32", _p(x), _p(out), x.numel(), act_code(act), float(drop_p), int(seed), int(round_out), _stream())
     return out
 
 
-def act_bwd(dout, x, act, drop_p=0.0, seed=0):
+def act_bwd(dout, x, act, drop_p=0.0, seed=0, round_out=False):
     _chk(dout, x)
     dout, x = dout.contiguous(), x.contiguous()
     dx = torch.empty_like(x)
     _w(10.0 * x.numel(), 12.0 * x.numel())
-    _call("xm_act_bwd_f32", _p(dout), _p(x), _p(dx), x.numel(), act_code(act), float(drop_p), int(seed), _stream())
+    _call("xm_act_bwd_f32", _p(dout), _p(x), _p(dx), x.numel(), act_code(act), float(drop_p), int(seed), int(round_out),
+          _stream())
     return dx
 
 
@@ -542,7 +543,7 @@ def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
     return out, probs, lse
 
 
-def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0):
+def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
     _chk(dout, qkv, probs, lse)
     dout = dout.contiguous()
     B, L, E = qkv.shape
@@ -551,8 +552,70 @@ def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0):
     ds = torch.empty_like(probs)
     _w(10.0 * B * nhead * L * L * dh, 4.0 * (2 * qkv.numel() + dout.numel() + 4 * probs.numel()))
     _call("xm_attn_bwd_f32", _p(dout), _p(qkv), _p(probs), _p(lse), _p(dqkv), _p(ds), B, L, nhead, dh, float(scale),
-          float(drop_p), int(seed), _stream())
+          float(drop_p), int(seed), int(round_out), _stream())
     return dqkv
+
+
+# ------------------------------------------------------------------ residual stream (transformer block)
+def resid_ln_supported(D: int) -> bool:
+    return D % 128 == 0 and 128 <= D <= 512
+
+
+def resid_ln_fwd(x, a, gamma, beta, eps, drop_p=0.0, seed=0, pe=None, L=0):
+    """s = x + Dropout(a)  |  Dropout(x + pe[row % L]);  h = tf32(LayerNorm(s)).  -> (s, h, mean, rstd); s is x
+    itself when there is neither a branch nor a positional table."""
+    _chk(x, a, gamma, beta, pe)
+    x = x.contiguous()
+    M, D = x.shape
+    a = None if a is None else a.contiguous()
+    s = torch.empty_like(x) if (a is not None or pe is not None) else None
+    h = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    _w(12.0 * M * D, 4.0 * M * D * (2 + (a is not None) + (s is not None)))
+    _call("xm_resid_ln_fwd_f32", _p(x), _p(a), _p(pe), int(L), _p(gamma), _p(beta), _p(s), _p(h), _p(mean), _p(rstd), M, D,
+          float(eps), float(drop_p), int(seed), _stream())
+    return (x if s is None else s), h, mean, rstd
+
+
+def resid_ln_bwd(dh, dres, s, gamma, mean, rstd, drop_p=0.0, seed=0, need_da=True):
+    """-> (dx, da | None, dgamma, dbeta)."""
+    _chk(dh, dres, s)
+    dh, s = dh.contiguous(), s.contiguous()
+    dres = None if dres is None else dres.contiguous()
+    M, D = s.shape
+    nblk = _lib.lib().xm_resid_ln_nblk(M)
+    dx = torch.empty_like(s)
+    da = torch.empty_like(s) if need_da else None
+    gp = torch.empty(nblk, D, device=s.device, dtype=torch.float32)
+    bp = torch.empty(nblk, D, device=s.device, dtype=torch.float32)
+    _w(20.0 * M * D, 4.0 * M * D * (3 + (dres is not None) + need_da))
+    _call("xm_resid_ln_bwd_f32", _p(dh), _p(dres), _p(s), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(da), _p(gp), _p(bp), M, D,
+          float(drop_p), int(seed), _stream())
+    return dx, da, colsum(gp), colsum(bp)
+
+
+def resid_seqmean_fwd(x, a, drop_p=0.0, seed=0):
+    """x, a (B, T, D) -> (B, D) = mean_t (x + Dropout(a))."""
+    _chk(x, a)
+    x = x.contiguous()
+    a = None if a is None else a.contiguous()
+    B, T, D = x.shape
+    out = torch.empty(B, D, device=x.device, dtype=torch.float32)
+    _w(2.0 * x.numel(), 4.0 * x.numel() * (1 + (a is not None)))
+    _call("xm_resid_seqmean_fwd_f32", _p(x), _p(a), B, T, D, _p(out), float(drop_p), int(seed), _stream())
+    return out
+
+
+def resid_seqmean_bwd(dout, T, drop_p=0.0, seed=0, need_dx=True, need_da=True):
+    _chk(dout)
+    dout = dout.contiguous()
+    B, D = dout.shape
+    dx = torch.empty(B, T, D, device=dout.device, dtype=torch.float32) if need_dx else None
+    da = torch.empty(B, T, D, device=dout.device, dtype=torch.float32) if need_da else None
+    _w(2.0 * B * T * D, 4.0 * B * T * D * (need_dx + need_da))
+    _call("xm_resid_seqmean_bwd_f32", _p(dout), B, T, D, _p(dx), _p(da), float(drop_p), int(seed), _stream())
+    return dx, da
 
 
 # ------------------------------------------------------------------ preprocessing

@@ -178,13 +178,13 @@ def ln_act_bwd(dout, x, gamma, beta, mean, rstd, act, drop_p=0.0, seed=0):
     return gx.float(), gg.float(), gb.float()
 
 
-def act_fwd(x, act, drop_p=0.0, seed=0):
+def act_fwd(x, act, drop_p=0.0, seed=0, round_out=False):
     _nodrop(drop_p)
     return _act(x.double(), act).float()
 
 
 @torch.enable_grad()
-def act_bwd(dout, x, act, drop_p=0.0, seed=0):
+def act_bwd(dout, x, act, drop_p=0.0, seed=0, round_out=False):
     _nodrop(drop_p)
     xd = x.double().requires_grad_(True)
     (g,) = torch.autograd.grad(_act(xd, act), xd, dout.double())
@@ -268,7 +268,7 @@ def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
     return out.float(), p.reshape(B * nhead, L, L).float(), torch.logsumexp(s, -1).reshape(B * nhead, L).float()
 
 
-def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0):
+def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
     _nodrop(drop_p)
     B, L, E = qkv.shape
     d = E // 3
@@ -281,6 +281,46 @@ def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0):
     dq, dk = ds @ k, ds.transpose(-1, -2) @ q
     back = lambda t: t.transpose(1, 2).reshape(B, L, d)
     return torch.cat([back(dq), back(dk), back(dv)], dim=-1).float()
+
+
+# ---------------------------------------------------------------- residual stream (transformer block)
+def resid_ln_supported(D):
+    return D % 128 == 0 and 128 <= D <= 512
+
+
+def resid_ln_fwd(x, a, gamma, beta, eps, drop_p=0.0, seed=0, pe=None, L=0):
+    _nodrop(drop_p)
+    s = x.double()
+    if pe is not None:
+        s = s + pe.double().repeat(x.shape[0] // L, 1)
+    if a is not None:
+        s = s + a.double()
+    mean = s.mean(1)
+    rstd = torch.rsqrt(s.var(1, unbiased=False) + eps)
+    h = (s - mean[:, None]) * rstd[:, None] * gamma.double() + beta.double()
+    return (x if (a is None and pe is None) else s.float()), h.float(), mean.float(), rstd.float()
+
+
+def resid_ln_bwd(dh, dres, s, gamma, mean, rstd, drop_p=0.0, seed=0, need_da=True):
+    _nodrop(drop_p)
+    xh = (s.double() - mean.double()[:, None]) * rstd.double()[:, None]
+    dz = dh.double() * gamma.double()
+    ds = rstd.double()[:, None] * (dz - dz.mean(1, keepdim=True) - xh * (dz * xh).mean(1, keepdim=True))
+    if dres is not None:
+        ds = ds + dres.double()
+    return ds.float(), (ds.float() if need_da else None), (dh.double() * xh).sum(0).float(), dh.double().sum(0).float()
+
+
+def resid_seqmean_fwd(x, a, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    s = x.double() + (0 if a is None else a.double())
+    return s.mean(1).float()
+
+
+def resid_seqmean_bwd(dout, T, drop_p=0.0, seed=0, need_dx=True, need_da=True):
+    _nodrop(drop_p)
+    g = (dout.double() / T).unsqueeze(1).expand(dout.shape[0], T, dout.shape[1]).float().contiguous()
+    return (g if need_dx else None), (g.clone() if need_da else None)
 
 
 # ---------------------------------------------------------------- preprocessing

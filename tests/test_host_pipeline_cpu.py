@@ -92,3 +92,26 @@ def test_two_rank_gloo_step_equals_global_batch_step(tmp_path, encoder):
     assert_close_rel(torch.tensor(got["losses"]), torch.tensor(want), 1e-5, "global loss per step")
     for k in set(ps.trainable_keys(P)) - set(ps.bias_before_batchnorm_keys(P)):
         assert_close_rel(got["sd"][k], P[k], 1e-5, f"param {k}", atol=2e-5)
+
+
+def test_fused_transformer_tail_autograd_vs_oracle(fakes):
+    """The hand-written backward of the fused PE + blocks + mean-pool tail (XF.TransformerTail) at a shape the
+    fused kernels support (d_model 128, 4 heads of 32, L = 25): outputs and every gradient vs the oracle."""
+    from multimodal_eeg_fmri_b200 import modules
+    from oracle import models as om
+    torch.manual_seed(3)
+    m = modules.EnhancedERPEncoder(8, 128, 2, 4, 0.0).train()
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(6, 8, 50)
+    cot = torch.randn(6, 128)
+    xg = x.clone().requires_grad_(True)
+    y = m(xg)
+    y.backward(cot)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")}
+    xo = x.clone().requires_grad_(True)
+    yo = om.enhanced_erp_encoder({**P, **leaves}, "", xo, nhead=4)
+    yo.backward(cot)
+    assert_close_rel(y, yo, 1e-5, "encoder output")
+    assert_close_rel(xg.grad, xo.grad, 2e-4, "dx")
+    for k, p in m.named_parameters():
+        assert_close_rel(p.grad, leaves[k].grad, 2e-4, f"grad {k}", atol=1e-6)
