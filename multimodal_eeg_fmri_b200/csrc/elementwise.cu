@@ -862,7 +862,28 @@ __global__ void bn_act_bwd_reduce_v4_kernel(const BnActArgs a, const float* __re
   double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   float p0[4] = {0, 0, 0, 0}, p1[4] = {0, 0, 0, 0};
   int n = 0;
-  for (long long ro = r_lo + ty; ro < r_hi; ro += RY) {
+  long long ro = r_lo + ty;
+  for (; ro + RY < r_hi; ro += 2ll * RY) {  // two output rows per iteration: twice the loads in flight
+    long long r0a, r0b;
+    F4 xa0, xa1, da0, da1, xb0, xb1, db0, db1;
+    bn_dz4<ACT, POOL>(a, k, dout, ro, c0, r0a, xa0, xa1, da0, da1);
+    bn_dz4<ACT, POOL>(a, k, dout, ro + RY, c0, r0b, xb0, xb1, db0, db1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p0[j] += (da0.v[j] + da1.v[j]) + (db0.v[j] + db1.v[j]);
+      p1[j] += da0.v[j] * ((xa0.v[j] - k.mu[j]) * k.is[j]) + da1.v[j] * ((xa1.v[j] - k.mu[j]) * k.is[j]) +
+               db0.v[j] * ((xb0.v[j] - k.mu[j]) * k.is[j]) + db1.v[j] * ((xb1.v[j] - k.mu[j]) * k.is[j]);
+    }
+    if (++n == 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s0[j] += (double)p0[j]; s1[j] += (double)p1[j];
+        p0[j] = 0.f; p1[j] = 0.f;
+      }
+      n = 0;
+    }
+  }
+  for (; ro < r_hi; ro += RY) {
     long long r0;
     F4 x0, x1, dz0, dz1;
     bn_dz4<ACT, POOL>(a, k, dout, ro, c0, r0, x0, x1, dz0, dz1);
@@ -870,14 +891,6 @@ __global__ void bn_act_bwd_reduce_v4_kernel(const BnActArgs a, const float* __re
     for (int j = 0; j < 4; ++j) {
       p0[j] += dz0.v[j] + dz1.v[j];
       p1[j] += dz0.v[j] * ((x0.v[j] - k.mu[j]) * k.is[j]) + dz1.v[j] * ((x1.v[j] - k.mu[j]) * k.is[j]);
-    }
-    if (++n == 64) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s0[j] += (double)p0[j]; s1[j] += (double)p1[j];
-        p0[j] = 0.f; p1[j] = 0.f;
-      }
-      n = 0;
     }
   }
 #pragma unroll
@@ -998,7 +1011,7 @@ int xm_zscore_f32(const float* x, int64_t n_items, int64_t item_len, float eps, 
 
 int xm_bn_nsplit(int64_t R, int64_t C) {
   const int64_t cblk = (C + 31) / 32;
-  int64_t ns = (kNumSMs * 4 + cblk - 1) / cblk;
+  int64_t ns = (kNumSMs * 16 + cblk - 1) / cblk;  // the float4 kernels use ONE block per split (all channels)
   const int64_t max_by_rows = (R + 63) / 64;  // at least 64 rows per split
   if (ns > max_by_rows) ns = max_by_rows;
   if (ns < 1) ns = 1;

@@ -133,6 +133,43 @@ class PairedTrainer:
         return float(self.step(*bufs).item())
 
 
+    def steps_from_host(self, host_batches) -> List[float]:
+        """End-to-end epoch over pinned host batches [(eeg, roi, conn), ...]: the host->device copy of batch
+        k+1 runs on a copy stream while batch k trains (two device buffer sets, event hand-off), and every
+        step's loss is read back.  Returns the per-step losses."""
+        dev = self.flat_grad.device
+        main = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None) or torch.cuda.Stream(dev)
+        self._copy_stream = copy
+        sets = [dict(bufs=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        for st in sets:
+            st["free"].record(main)
+
+        def stage(st, batch):
+            with torch.cuda.stream(copy):
+                copy.wait_event(st["free"])  # the step that last read this buffer set has finished
+                if st["bufs"] is None or any(d.shape != h.shape for d, h in zip(st["bufs"], batch)):
+                    st["bufs"] = [torch.empty(h.shape, device=dev, dtype=h.dtype) for h in batch]
+                for d, h in zip(st["bufs"], batch):
+                    d.copy_(h, non_blocking=True)
+                st["ready"].record(copy)
+
+        batches = list(host_batches)
+        losses: List[float] = []
+        if not batches:
+            return losses
+        stage(sets[0], batches[0])
+        for k, _ in enumerate(batches):
+            cur = sets[k % 2]
+            if k + 1 < len(batches):
+                stage(sets[(k + 1) % 2], batches[k + 1])
+            main.wait_event(cur["ready"])
+            loss = self.step(*cur["bufs"])
+            cur["free"].record(main)
+            losses.append(float(loss.item()))
+        return losses
+
+
 def train_bridge_epoch(model, loader, optimizer, criterion, device, grad_clip: float = 1.0) -> float:
     """_test_bridge.py:775-788 -- supervised bridge epoch (CE on logits), same recipe and return value."""
     model.train()
