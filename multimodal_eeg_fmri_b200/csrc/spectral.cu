@@ -75,14 +75,52 @@ __global__ void window_gather_nwc_kernel(const float* __restrict__ rec, long lon
 // Ping-pong Stockham passes: pass p gathers from one per-warp buffer (pass 0: from global,
 // applying the taper and the zero padding) and scatters to the other, so a pass with more than
 // 32 butterflies never overwrites a source another lane group still has to read.
+// Raw samples of one row held in registers: lane j keeps, for butterfly j0 + j of pass 0 (radix R0),
+// the R0 packed complex inputs n = j + r*NB, i.e. samples (2n, 2n+1).  Loaded one row AHEAD of the row
+// being transformed, so the HBM latency of row i+1 hides behind the butterflies of row i.
+template <int N2>
+struct RowRegs {
+  static constexpr int R0 = fft::radix_for(N2);
+  static constexpr int NB = N2 / R0;
+  static constexpr int NJ = (NB + 31) / 32;
+  float2 v[NJ][R0];
+};
+
+template <int N2>
+XM_DEVICE void load_row(RowRegs<N2>& rr, const float* __restrict__ row, int win, int lane) {
+  constexpr int R0 = RowRegs<N2>::R0, NB = RowRegs<N2>::NB, NJ = RowRegs<N2>::NJ;
+  const bool aligned8 = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const int j = jj * 32 + lane;
+#pragma unroll
+    for (int r = 0; r < R0; ++r) {
+      const int n = j + r * NB;
+      float2 x = make_float2(0.f, 0.f);
+      if ((NB >= 32 || j < NB) && 2 * n < win) {
+        if (2 * n + 1 < win) {
+          if (aligned8) x = __ldg(reinterpret_cast<const float2*>(row + 2 * n));
+          else { x.x = __ldg(row + 2 * n); x.y = __ldg(row + 2 * n + 1); }
+        } else {
+          x.x = __ldg(row + 2 * n);
+        }
+      }
+      rr.v[jj][r] = x;
+    }
+  }
+}
+
+// Ping-pong Stockham passes: pass p gathers from one per-warp buffer (pass 0: from the row registers,
+// applying the taper; samples beyond `win` are the zero padding) and scatters to the other, so a pass
+// with more than 32 butterflies never overwrites a source another lane group still has to read.
 template <int N2, int Ns>
 struct PassesPP {
   static constexpr int rem = N2 / Ns;
   static constexpr int R = fft::radix_for(rem);
-  static XM_DEVICE void run(const float* __restrict__ row, const float* __restrict__ taper, int win, bool aligned8,
+  static XM_DEVICE void run(const RowRegs<N2>& rr, const float* __restrict__ taper, int win,
                             float* are, float* aim, float* bre, float* bim, const float* __restrict__ tw_re,
                             const float* __restrict__ tw_im, int lane) {
-    // reads (are, aim) [or global when Ns == 1], writes (bre, bim)
+    // reads (are, aim) [or the row registers when Ns == 1], writes (bre, bim)
     constexpr int NB = N2 / R;
 #pragma unroll
     for (int j0 = 0; j0 < NB; j0 += 32) {
@@ -93,20 +131,11 @@ struct PassesPP {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int n = j + r * NB;
-            float x0 = 0.f, x1 = 0.f;
-            if (2 * n + 1 < win) {
-              if (aligned8) {
-                const float2 v = *reinterpret_cast<const float2*>(row + 2 * n);
-                x0 = v.x; x1 = v.y;
-              } else {
-                x0 = row[2 * n]; x1 = row[2 * n + 1];
-              }
-              const float2 tp = *reinterpret_cast<const float2*>(taper + 2 * n);
-              x0 *= tp.x; x1 *= tp.y;
-            } else if (2 * n < win) {
-              x0 = row[2 * n] * taper[2 * n];
-            }
-            re[r] = x0; im[r] = x1;
+            float2 tp = make_float2(0.f, 0.f);
+            if (2 * n + 1 < win) tp = *reinterpret_cast<const float2*>(taper + 2 * n);
+            else if (2 * n < win) tp.x = taper[2 * n];
+            const float2 x = rr.v[j0 / 32][r];
+            re[r] = x.x * tp.x; im[r] = x.y * tp.y;
           }
         } else {
 #pragma unroll
@@ -125,14 +154,14 @@ struct PassesPP {
       }
     }
     __syncwarp();
-    PassesPP<N2, Ns * R>::run(row, taper, win, aligned8, bre, bim, are, aim, tw_re, tw_im, lane);
+    PassesPP<N2, Ns * R>::run(rr, taper, win, bre, bim, are, aim, tw_re, tw_im, lane);
   }
   // number of passes from this Ns on (to know which buffer holds the result)
   static constexpr int count = 1 + PassesPP<N2, Ns * R>::count;
 };
 template <int N2>
 struct PassesPP<N2, N2> {
-  static XM_DEVICE void run(const float*, const float*, int, bool, float*, float*, float*, float*, const float*,
+  static XM_DEVICE void run(const RowRegs<N2>&, const float*, int, float*, float*, float*, float*, const float*,
                             const float*, int) {}
   static constexpr int count = 0;
 };
@@ -170,12 +199,20 @@ bandpower_kernel(const float* __restrict__ rec, long long n_rows, long long C, l
   }
   const int nfft = 2 * N2;
 
-  for (long long row = blockIdx.x * (long long)kBpWarps + warp; row < n_rows; row += (long long)gridDim.x * kBpWarps) {
+  const long long row_stride = (long long)gridDim.x * kBpWarps;
+  auto row_ptr = [&](long long row) {
     const long long g = row / C, c = row - g * C;
     const long long r = g / n_win, w = g - r * n_win;
-    const float* src = rec + (r * C + c) * n_samples + w * hop;
-    const bool aligned8 = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
-    PassesPP<N2, 1>::run(src, taper, win, aligned8, are, aim, bre, bim, tw_re, tw_im, lane);
+    return rec + (r * C + c) * n_samples + w * hop;
+  };
+  long long row = blockIdx.x * (long long)kBpWarps + warp;
+  RowRegs<N2> cur;
+  if (row < n_rows) load_row<N2>(cur, row_ptr(row), win, lane);
+  for (; row < n_rows; row += row_stride) {
+    RowRegs<N2> nxt;
+    const bool has_next = row + row_stride < n_rows;
+    if (has_next) load_row<N2>(nxt, row_ptr(row + row_stride), win, lane);  // in flight during this row's FFT
+    PassesPP<N2, 1>::run(cur, taper, win, are, aim, bre, bim, tw_re, tw_im, lane);
 
     float acc[kMaxBands];
 #pragma unroll
@@ -207,6 +244,7 @@ bandpower_kernel(const float* __restrict__ rec, long long n_rows, long long C, l
       }
     }
     __syncwarp();
+    if (has_next) cur = nxt;
   }
 }
 
