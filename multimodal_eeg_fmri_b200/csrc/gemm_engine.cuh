@@ -78,7 +78,7 @@ struct GemmParams {
   const float* lse_in;  // same, read by EPI_ATTN_DS
   int n_valid;          // keys per row (columns >= n_valid are written as 0)
   int rows_valid;       // queries per slab (L)
-  uint32_t drop_thresh16;  // keep <=> 16-bit hash lane >= thresh (0: no dropout)
+  uint32_t drop_thresh32;  // keep <=> 32-bit mask-stream state >= thresh (0: no dropout)
   float drop_scale;
   unsigned long long seed;
 };
@@ -167,6 +167,15 @@ XM_DEVICE void stage_and_store(const CUtensorMap* tmC, uint8_t* stg, int& chunk_
 //                 delta = sum_n P~ * dP~ ;  dS[m][n] = alpha * (P~ * dP~ - P * delta)       (tf32-rounded)
 XM_DEVICE void quad_barrier(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
+// Dropout mask stream of one (row, 32-column chunk): a well-mixed 32-bit seed, then one LCG step per
+// column; keep <=> state >= threshold (an unsigned compare is decided by the high bits, the good bits of a
+// power-of-two LCG).  3 integer instructions per element -- the epilogue below is issue-bound, and a full
+// hash per element group tripled its instruction count.
+XM_DEVICE uint32_t drop_stream_seed(unsigned long long row_id, int chunk, unsigned long long seed) {
+  return (uint32_t)(hash_u64(row_id * 8ull + (unsigned long long)chunk, seed) >> 32);
+}
+XM_DEVICE uint32_t lcg_next(uint32_t h) { return h * 747796405u + 2891336453u; }
+
 template <int EPI>
 XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, uint32_t acc, const TileCoord& t, int m,
                                   bool row_ok, int q, int part, int lane, uint8_t* stg, int& chunk_ctr,
@@ -178,6 +187,8 @@ XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, u
   const unsigned long long row_id = (unsigned long long)z * (unsigned long long)p.rows_valid + (unsigned long long)m;
   const int nch = p.bn >> 7;       // 32-column chunks per part (bn is 128 or 256)
   const int ch0 = part * nch;      // first chunk of this part
+  const uint32_t thr = p.drop_thresh32;
+  const float dscale = p.drop_scale;
   float off;                       // log2-domain offset: P = exp2(acc*c - off)
   if (EPI == EPI_SOFTMAX) {
     float mx = -3.0e38f;
@@ -185,13 +196,14 @@ XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, u
       uint32_t r[32];
       ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
       ptx::tmem_ld_wait();
-      if (ch * 32 + 32 <= p.n_valid) {
+      const int nv = p.n_valid - ch * 32;
+      if (nv >= 32) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (ch * 32 + j < p.n_valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+          if (j < nv) mx = fmaxf(mx, __uint_as_float(r[j]));
       }
     }
     red[q][part][lane] = mx;
@@ -203,13 +215,14 @@ XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, u
       uint32_t r[32];
       ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
       ptx::tmem_ld_wait();
-      if (ch * 32 + 32 <= p.n_valid) {
+      const int nv = p.n_valid - ch * 32;
+      if (nv >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += fast_exp2(__uint_as_float(r[j]) * c - mc);
+        for (int j = 0; j < 32; ++j) sum += fast_exp2(fmaf(__uint_as_float(r[j]), c, -mc));
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (ch * 32 + j < p.n_valid) sum += fast_exp2(__uint_as_float(r[j]) * c - mc);
+          if (j < nv) sum += fast_exp2(fmaf(__uint_as_float(r[j]), c, -mc));
       }
     }
     quad_barrier(q);  // every part has read the maxima: the exchange buffer can be reused
@@ -229,18 +242,18 @@ XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, u
       ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
       ptx::tmem_ld_32x32(acc + (uint32_t)(p.bn + ch * 32), g);
       ptx::tmem_ld_wait();
+      const int nv = p.n_valid - ch * 32;
+      uint32_t h = drop_stream_seed(row_id, ch, p.seed);
+      float dk = 0.f, da = 0.f;  // kept / all
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        uint64_t h = 0;
-        if (p.drop_thresh16) h = hash_u64(row_id * 64ull + (unsigned long long)(ch * 8 + j4), p.seed);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = 4 * j4 + jj;
-          float pr = (ch * 32 + j < p.n_valid) ? fast_exp2(__uint_as_float(r[j]) * c - off) : 0.f;
-          if (p.drop_thresh16) pr = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
-          delta += pr * __uint_as_float(g[j]);
-        }
+      for (int j = 0; j < 32; ++j) {
+        h = lcg_next(h);
+        float t2 = fast_exp2(fmaf(__uint_as_float(r[j]), c, -off)) * __uint_as_float(g[j]);
+        if (nv < 32 && j >= nv) t2 = 0.f;
+        if (h >= thr) dk += t2;
+        da += t2;
       }
+      delta += thr ? dk * dscale : da;
     }
     red[q][part][lane] = delta;
     quad_barrier(q);
@@ -260,19 +273,16 @@ XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, u
     } else {
       ptx::tmem_ld_wait();
     }
+    const int nv = p.n_valid - ch * 32;
+    uint32_t h = drop_stream_seed(row_id, ch, p.seed);
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      uint64_t h = 0;
-      if (p.drop_thresh16) h = hash_u64(row_id * 64ull + (unsigned long long)(ch * 8 + j4), p.seed);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = 4 * j4 + jj;
-        const float pr = (ch * 32 + j < p.n_valid) ? fast_exp2(__uint_as_float(r[j]) * c - off) : 0.f;
-        float pd = pr;
-        if (p.drop_thresh16) pd = ((uint32_t)(h >> (16 * jj)) & 0xFFFFu) >= p.drop_thresh16 ? pr * p.drop_scale : 0.f;
-        const float o = (EPI == EPI_ATTN_DS) ? p.alpha * (pd * v[j] - pr * delta) : pd;
-        v[j] = round_tf32(o);
-      }
+    for (int j = 0; j < 32; ++j) {
+      h = lcg_next(h);
+      const float pr = fast_exp2(fmaf(__uint_as_float(r[j]), c, -off));
+      const float mk = (h >= thr) ? dscale : 0.f;  // thr == 0 (no dropout): always kept, dscale == 1
+      float o = (EPI == EPI_ATTN_DS) ? p.alpha * pr * fmaf(mk, v[j], -delta) : pr * mk;
+      if (nv < 32 && j >= nv) o = 0.f;
+      v[j] = round_tf32(o);
     }
     stage_and_store<1>(&tmC, stg, chunk_ctr, lane, v, p.c_col_base + ch * 32, t.bx * 128 + q * 32, z);
   }

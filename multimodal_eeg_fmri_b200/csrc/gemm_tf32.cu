@@ -257,12 +257,12 @@ static TensorView3 view3(const void* ptr, long long d0, long long d1, long long 
 static void drop16(GemmParams& p, float drop_p, uint64_t seed) {
   p.seed = seed;
   if (drop_p > 0.f) {
-    double th = (double)drop_p * 65536.0 + 0.5;
-    p.drop_thresh16 = th >= 65535.0 ? 65535u : (uint32_t)th;
-    if (p.drop_thresh16 == 0u) p.drop_thresh16 = 1u;
+    double th = (double)drop_p * 4294967296.0;
+    p.drop_thresh32 = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
+    if (p.drop_thresh32 == 0u) p.drop_thresh32 = 1u;
     p.drop_scale = 1.0f / (1.0f - drop_p);
   } else {
-    p.drop_thresh16 = 0u;
+    p.drop_thresh32 = 0u;
     p.drop_scale = 1.0f;
   }
 }
