@@ -222,6 +222,22 @@ int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, co
                         int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
                         void* stream);
 
+/* Fused all-gather + contraction over NVLink peer memory (data-parallel global negatives).  The second
+ * operand is ROW-SHARDED: rank r holds rows [r*rows_per_peer, (r+1)*rows_per_peer) in its own buffer and
+ * b_peers[r] (a HOST array of n_peers <= 8 device pointers) is that buffer mapped into this process
+ * (torch symmetric memory / cudaIpc / cuMem peer mapping).  The TMA producer of the GEMM reads every tile
+ * straight from the owner's HBM through NVLink / NVSwitch: no gathered copy is ever materialised.
+ * rows_per_peer % 128 == 0.  The caller orders the kernels after the peers' writes (device barrier). */
+int xm_infonce_lse_peers_f32(const float* a, const void* const* b_peers, int n_peers, int64_t rows_per_peer, float* lse,
+                             float* diag, int64_t Ml, int64_t D, float inv_tau, int64_t diag_off, float* workspace,
+                             void* stream);
+int xm_infonce_grad_peers_f32(const float* a, const void* const* b_peers, int n_peers, int64_t rows_per_peer,
+                              const float* lse_row, const float* lse_col, float* G, int64_t Ml, int64_t D, float inv_tau,
+                              int64_t diag_off, float coef, void* stream);
+/* dx (M, K) = dy (M, n_peers*rows_per_peer) @ w, w row-sharded across peers (pitch ldw). */
+int xm_linear_dgrad_peers_f32(const float* dy, const void* const* w_peers, int n_peers, int64_t rows_per_peer, float* dx,
+                              int64_t M, int64_t K, int64_t lddy, int64_t ldw, int64_t lddx, int round_out, void* stream);
+
 /* ------------------------------------------------------------------ multi-head self-attention core
  * nn.MultiheadAttention inside TemporalTransformerBlock (EEG_CODE/enhanced_models_v4.py:71-73,98; torch computes
  * softmax(q k^T / sqrt(dh)), dropout on the weights, times v).  qkv (B, L, 3*H*dh) is the packed in_proj output

@@ -112,16 +112,21 @@ __global__ void bn_partial_stats_kernel(const float* __restrict__ y, long long R
   }
 }
 
+// one warp per channel: lanes stride over the splits, fp64 shuffle reduction
 __global__ void bn_finalize_stats_kernel(const double* __restrict__ partials, int nsplit, int C, double n, float eps,
                                          float* __restrict__ mean, float* __restrict__ invstd, float* running_mean,
                                          float* running_var, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
+  const int lane = threadIdx.x & 31;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < nsplit; ++i) {
+  for (int i = lane; i < nsplit; i += 32) {
     s += partials[((long long)i * C + c) * 2 + 0];
     q += partials[((long long)i * C + c) * 2 + 1];
   }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane != 0) return;
   const double mu = s / n;
   double var = q / n - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -258,15 +263,20 @@ __global__ void bn_act_bwd_reduce_kernel(const BnActArgs a, const float* __restr
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int nsplit, int C, float* __restrict__ dbeta,
                                        float* __restrict__ dgamma) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
+  const int lane = threadIdx.x & 31;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < nsplit; ++i) {
+  for (int i = lane; i < nsplit; i += 32) {
     s += partials[((long long)i * C + c) * 2 + 0];
     q += partials[((long long)i * C + c) * 2 + 1];
   }
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)q;
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)q;
+  }
 }
 
 // dy = gamma*invstd*(dz - dbeta/n - xhat*dgamma/n); one thread per (output row, channel)
@@ -1037,7 +1047,7 @@ int xm_bn_partial_stats_f32(const float* y, int64_t R, int64_t C, int64_t ldy, d
 int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double total_count, float eps, float* mean,
                          float* invstd, float* running_mean, float* running_var, float momentum, void* stream) {
   if (!partials || !mean || !invstd || nsplit <= 0 || C <= 0 || total_count <= 0) return XM_ERR_INVALID;
-  bn_finalize_stats_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nsplit, (int)C, total_count, eps,
+  bn_finalize_stats_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nsplit, (int)C, total_count, eps,
                                                                                mean, invstd, running_mean, running_var,
                                                                                momentum);
   return check_launch();
@@ -1081,7 +1091,7 @@ int xm_bn_act_bwd_reduce_f32(const float* dout, const float* y, const float* mea
 
 int xm_bn_bwd_finalize(const double* partials, int nsplit, int64_t C, float* dbeta, float* dgamma, void* stream) {
   if (!partials || !dbeta || !dgamma || nsplit <= 0 || C <= 0) return XM_ERR_INVALID;
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partials, nsplit, (int)C, dbeta, dgamma);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nsplit, (int)C, dbeta, dgamma);
   return check_launch();
 }
 

@@ -38,8 +38,18 @@ struct OperandCfg {
   int base[3], sx[3], sy[3], sz[3], kin_step[3], kout_step[3], tap_step[3];
 };
 
+constexpr int kMaxPeers = 8;
+// One tensor map per rank for an operand that is ROW-SHARDED across the GPUs of a node (peer memory mapped
+// into this process through NVLink / NVSwitch): the TMA producer reads each tile from the shard of the rank
+// that owns it, so "all-gather, then GEMM" becomes ONE kernel whose loads cross NVLink tile by tile.
+struct PeerMaps {
+  CUtensorMap m[kMaxPeers];
+};
+
 struct GemmParams {
   OperandCfg a, b;
+  int n_peers;     // > 0: operand B lives in n_peers shards of peer_rows rows each (row coordinate = dim 1)
+  int peer_rows;
   int bn;          // N of one MMA / one accumulator (multiple of 16, <= 256)
   int taps_k;      // taps iterated inside the K loop (conv fwd / dgrad), >= 1
   int taps_n;      // taps held as separate accumulators (conv wgrad), >= 1
@@ -293,7 +303,8 @@ template <int EPI>
 __global__ void __launch_bounds__(gemm_threads(EpiWarps<EPI>::value), 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ PeerMaps peers,
+                 const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
@@ -370,9 +381,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                   ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2] + tk * p.a.tap_step[2]);
               for (int tn = 0; tn < p.taps_n; ++tn) {
                 const int tap = tk + tn;  // exactly one of taps_k / taps_n exceeds 1
-                issue_operand_loads(&tmB, &full_bar[s], sa + kATileBytes + tn * b_tile_bytes, p.b,
-                                    cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tap * p.b.tap_step[0],
-                                    cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tap * p.b.tap_step[1],
+                int b1 = cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tap * p.b.tap_step[1];
+                const CUtensorMap* tb = &tmB;
+                if (p.n_peers > 0) {  // row-sharded operand: this tile's rows live on rank b1 / peer_rows
+                  const int owner = b1 / p.peer_rows;
+                  b1 -= owner * p.peer_rows;
+                  tb = &peers.m[owner];
+                }
+                issue_operand_loads(tb, &full_bar[s], sa + kATileBytes + tn * b_tile_bytes, p.b,
+                                    cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tap * p.b.tap_step[0], b1,
                                     cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tap * p.b.tap_step[2]);
               }
               if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -626,7 +643,8 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
 // `tc` describes the output for the TMA-store epilogue (dims {N, M, Z}); pass ptr == nullptr to use
 // the direct-store path (p.c / p.ldc).  `grid` is the TILE grid; the launch is persistent.
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
-                cudaStream_t stream, const TensorView3* ta2 = nullptr, const TensorView3* tb2 = nullptr);
+                cudaStream_t stream, const TensorView3* ta2 = nullptr, const TensorView3* tb2 = nullptr,
+                const void* const* b_peers = nullptr);
 
 inline int tmem_cols_for(int n) {
   int c = 32;

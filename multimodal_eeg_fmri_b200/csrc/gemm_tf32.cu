@@ -61,19 +61,24 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
 
 template <int EPI>
 static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& ma2,
-                      const CUtensorMap& mb2, const GemmParams& p, int ctas, size_t smem, cudaStream_t stream) {
+                      const CUtensorMap& mb2, const PeerMaps& pm, const GemmParams& p, int ctas, size_t smem,
+                      cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
-  gemm_tf32_kernel<EPI><<<ctas, gemm_threads(EpiWarps<EPI>::value), smem, stream>>>(ma, mb, mc, ma2, mb2, p);
+  gemm_tf32_kernel<EPI><<<ctas, gemm_threads(EpiWarps<EPI>::value), smem, stream>>>(ma, mb, mc, ma2, mb2, pm, p);
   return check_launch();
 }
 
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
-                cudaStream_t stream, const TensorView3* ta2, const TensorView3* tb2) {
+                cudaStream_t stream, const TensorView3* ta2, const TensorView3* tb2, const void* const* b_peers) {
   if (p.n_stride < 0) p.n_stride = p.bn;
+  if (p.n_peers < 0 || p.n_peers > kMaxPeers || (p.n_peers > 0 && (!b_peers || p.peer_rows <= 0 || p.taps_n != 1)))
+    return XM_ERR_INVALID;
+  // a tile's row range must not straddle two shards
+  if (p.n_peers > 0 && (p.peer_rows % (p.b.mn_major ? 32 : p.bn))) return XM_ERR_UNSUPPORTED;
   if (p.c_col_mul < 0) p.c_col_mul = p.bn;
   p.dual = (ta2 != nullptr && tb2 != nullptr) ? 1 : 0;
   if (p.dual && (p.taps_n != 1 || 2 * p.bn > 512)) return XM_ERR_UNSUPPORTED;
@@ -129,13 +134,22 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
     rc = encode_tmap(&mc, tc, 32, 32, 0);
     if (rc != XM_OK) return rc;
   }
+  static PeerMaps pm_zero;  // zero-initialised
+  PeerMaps pm = pm_zero;
+  for (int r = 0; r < p.n_peers; ++r) {  // same geometry as tb, one base pointer per rank
+    TensorView3 tv = tb;
+    tv.ptr = b_peers[r];
+    tv.dim[1] = (unsigned long long)p.peer_rows;
+    rc = encode_tmap(&pm.m[r], tv, 32, p.b.mn_major ? 32 : (unsigned)p.bn, p.b.mn_major);
+    if (rc != XM_OK) return rc;
+  }
   const int ctas = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   switch (epi) {
-    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
-    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
-    case EPI_SOFTMAX: return launch_epi<EPI_SOFTMAX>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
-    case EPI_ATTN_DS: return launch_epi<EPI_ATTN_DS>(ma, mb, mc, ma2, mb2, p, ctas, smem, stream);
+    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
+    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
+    case EPI_SOFTMAX: return launch_epi<EPI_SOFTMAX>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
+    case EPI_ATTN_DS: return launch_epi<EPI_ATTN_DS>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
   }
   return XM_ERR_INVALID;
 }
@@ -511,9 +525,10 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
   return rc;
 }
 
-int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
-                        int64_t ldw, int64_t lddx, int round_out, void* stream) {
-  if (!dy || !w || !dx || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
+static int linear_dgrad_impl(const float* dy, const float* w, const void* const* w_peers, int n_peers, int64_t peer_rows,
+                             float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy, int64_t ldw, int64_t lddx,
+                             int round_out, void* stream) {
+  if (!dy || (!w && !w_peers) || !dx || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
   if ((lddy & 3) || (ldw & 3)) return XM_ERR_INVALID;
   const int m_tiles = ceil_div(M, 128);
   GemmParams p;
@@ -531,10 +546,25 @@ int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, i
   p.c = dx;
   p.ldc = lddx;
   p.round_tf32 = round_out;
+  p.n_peers = n_peers;
+  p.peer_rows = (int)peer_rows;
   TensorView3 ta{dy, {(unsigned long long)N, (unsigned long long)M, 1}, {(unsigned long long)lddy * 4, (unsigned long long)M * lddy * 4}};
-  TensorView3 tb{w, {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
+  TensorView3 tb{w ? (const void*)w : w_peers[0], {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
   const TensorView3 tc = TensorView3{dx, {(unsigned long long)(K), (unsigned long long)(M), (unsigned long long)(1)}, {(unsigned long long)(lddx) * 4, (unsigned long long)(M * lddx) * 4}};
-  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream);
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream, nullptr, nullptr,
+                     w_peers);
+}
+
+int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
+                        int64_t ldw, int64_t lddx, int round_out, void* stream) {
+  return linear_dgrad_impl(dy, w, nullptr, 0, 0, dx, M, N, K, lddy, ldw, lddx, round_out, stream);
+}
+
+int xm_linear_dgrad_peers_f32(const float* dy, const void* const* w_peers, int n_peers, int64_t rows_per_peer, float* dx,
+                              int64_t M, int64_t K, int64_t lddy, int64_t ldw, int64_t lddx, int round_out, void* stream) {
+  if (n_peers <= 0 || rows_per_peer <= 0) return XM_ERR_INVALID;
+  return linear_dgrad_impl(dy, nullptr, w_peers, n_peers, rows_per_peer, dx, M, n_peers * rows_per_peer, K, lddy, ldw, lddx,
+                           round_out, stream);
 }
 
 int xm_linear_wgrad_f32(const float* dy, const float* x, float* dw, float* db, int64_t M, int64_t N, int64_t K,
@@ -766,9 +796,10 @@ int xm_similarity_f32(const float* a, const float* b, float* S, int64_t Ml, int6
 
 int xm_infonce_tile_n(void) { return 128; }
 
-int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D,
-                       float inv_tau, int64_t diag_off, float* workspace, void* stream) {
-  if (!a || !b || !lse || !diag || !workspace || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
+static int infonce_lse_impl(const float* a, const float* b, const void* const* b_peers, int n_peers, int64_t peer_rows,
+                            float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off,
+                            float* workspace, void* stream) {
+  if (!a || (!b && !b_peers) || !lse || !diag || !workspace || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   GemmParams p;
   zero_params(p);
@@ -781,20 +812,35 @@ int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, 
   p.partial = workspace;
   p.diag = diag;
   p.diag_off = (int)diag_off;
+  p.n_peers = n_peers;
+  p.peer_rows = (int)peer_rows;
   const int ntiles = ceil_div(Ng, 128);
   TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
-  TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
+  TensorView3 tb{b ? (const void*)b : b_peers[0], {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
   const TensorView3 tc{nullptr, {0, 0, 0}, {0, 0}};
-  int rc = launch_gemm(EPI_LSE, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ntiles, 1), st);
+  int rc = launch_gemm(EPI_LSE, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ntiles, 1), st, nullptr, nullptr, b_peers);
   if (rc != XM_OK) return rc;
   lse_finalize_kernel<<<ceil_div(Ml, 256), 256, 0, st>>>(workspace, ntiles, Ml, inv_tau, lse);
   return check_launch();
 }
 
-int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
-                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
-                        void* stream) {
-  if (!a || !b || !lse_row || !lse_col || !G || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
+int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D,
+                       float inv_tau, int64_t diag_off, float* workspace, void* stream) {
+  return infonce_lse_impl(a, b, nullptr, 0, 0, lse, diag, Ml, Ng, D, inv_tau, diag_off, workspace, stream);
+}
+
+int xm_infonce_lse_peers_f32(const float* a, const void* const* b_peers, int n_peers, int64_t rows_per_peer, float* lse,
+                             float* diag, int64_t Ml, int64_t D, float inv_tau, int64_t diag_off, float* workspace,
+                             void* stream) {
+  if (n_peers <= 0 || rows_per_peer <= 0) return XM_ERR_INVALID;
+  return infonce_lse_impl(a, nullptr, b_peers, n_peers, rows_per_peer, lse, diag, Ml, n_peers * rows_per_peer, D, inv_tau,
+                          diag_off, workspace, stream);
+}
+
+static int infonce_grad_impl(const float* a, const float* b, const void* const* b_peers, int n_peers, int64_t peer_rows,
+                             const float* lse_row, const float* lse_col, float* G, int64_t Ml, int64_t Ng, int64_t D,
+                             float inv_tau, int64_t diag_off, float coef, void* stream) {
+  if (!a || (!b && !b_peers) || !lse_row || !lse_col || !G || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
   GemmParams p;
   zero_params(p);
   sim_operands(p, 128);
@@ -808,10 +854,27 @@ int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, co
   p.lse_col = lse_col;
   p.diag_off = (int)diag_off;
   p.coef = coef;
+  p.n_peers = n_peers;
+  p.peer_rows = (int)peer_rows;
   TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
-  TensorView3 tb{b, {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
+  TensorView3 tb{b ? (const void*)b : b_peers[0], {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
   const TensorView3 tc = TensorView3{G, {(unsigned long long)(Ng), (unsigned long long)(Ml), (unsigned long long)(1)}, {(unsigned long long)(Ng) * 4, (unsigned long long)(Ml * Ng) * 4}};
-  return launch_gemm(EPI_NCE_GRAD, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, 128), 1), (cudaStream_t)stream);
+  return launch_gemm(EPI_NCE_GRAD, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, 128), 1), (cudaStream_t)stream, nullptr,
+                     nullptr, b_peers);
+}
+
+int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
+                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
+                        void* stream) {
+  return infonce_grad_impl(a, b, nullptr, 0, 0, lse_row, lse_col, G, Ml, Ng, D, inv_tau, diag_off, coef, stream);
+}
+
+int xm_infonce_grad_peers_f32(const float* a, const void* const* b_peers, int n_peers, int64_t rows_per_peer,
+                              const float* lse_row, const float* lse_col, float* G, int64_t Ml, int64_t D, float inv_tau,
+                              int64_t diag_off, float coef, void* stream) {
+  if (n_peers <= 0 || rows_per_peer <= 0) return XM_ERR_INVALID;
+  return infonce_grad_impl(a, nullptr, b_peers, n_peers, rows_per_peer, lse_row, lse_col, G, Ml, n_peers * rows_per_peer, D,
+                           inv_tau, diag_off, coef, stream);
 }
 
 }  // extern "C"

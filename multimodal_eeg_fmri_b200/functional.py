@@ -30,6 +30,7 @@ class ParallelContext:
 
     group: Optional[object] = None
     sync_bn: bool = True
+    peer_memory: bool = True  # read the other ranks' embeddings in place over NVLink (symmetric memory)
 
     @property
     def world(self) -> int:
@@ -459,43 +460,104 @@ class _AllGatherRows(object):
         return out
 
 
+class _PeerShards:
+    """Symmetric-memory buffers for the tf32-split unit embeddings: every rank writes its (Bl, 3D) shard into
+    its own buffer, which all ranks of the node can read through NVLink; the InfoNCE kernels then take the
+    list of per-rank base pointers instead of an all-gathered copy (fused all-gather + GEMM).  Two buffer
+    sets alternate so a forward may run before the previous backward has been consumed."""
+
+    _cache = {}
+    _failed = False
+
+    @classmethod
+    def get(cls, rows: int, cols: int, device):
+        if cls._failed or not (_CTX.active and _CTX.peer_memory) or device.type != "cuda" or rows % 128 != 0:
+            return None
+        key = (rows, cols, device.index)
+        ent = cls._cache.get(key)
+        if ent is None:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                group = _CTX.group if _CTX.group is not None else dist.group.WORLD
+                sets = []
+                for _ in range(2):
+                    bufs = [symm.empty(rows, cols, dtype=torch.float32, device=device) for _ in range(2)]
+                    hdls = [symm.rendezvous(b, group) for b in bufs]
+                    sets.append((bufs, hdls))
+                ent = {"sets": sets, "turn": 0}
+                cls._cache[key] = ent
+            except Exception as exc:  # noqa: BLE001 - no P2P mapping on this system: keep the NCCL all-gather path
+                cls._failed = True
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({exc}); InfoNCE falls back to NCCL all-gather")
+                return None
+        ent["turn"] ^= 1
+        return ent["sets"][ent["turn"]]
+
+
 class SymmetricInfoNCE(torch.autograd.Function):
     """L = 1/(2B) sum_i [lse_j S_ij - S_ii] + [lse_j S_ji - S_ii],  S = norm(e) norm(f)^T / tau, over the
-    GLOBAL batch: each rank holds B/G rows of e and f, all-gathers the normalised embeddings and the
-    two logsumexp vectors, and produces the exact gradient of the global loss for its own rows -- no
-    reduce-scatter in the backward.  S is never materialised in the forward; the
-    backward materialises the (B/G x B) softmax-gradient blocks that feed the two dgrad GEMMs.
-    Returns this rank's share of the loss (sum over ranks = global loss)."""
+    GLOBAL batch: each rank holds B/G rows of e and f; the similarity kernels read the other ranks' unit
+    embeddings tile by tile straight from peer HBM over NVLink (or from an NCCL all-gathered copy when peer
+    mapping is unavailable), the two logsumexp vectors are all-gathered, and every rank produces the exact
+    gradient of the global loss for its own rows -- no reduce-scatter in the backward.
+    S is never materialised in the forward; the backward materialises the (B/G x B) softmax-gradient blocks
+    that feed the two dgrad GEMMs.  Returns this rank's share of the loss (sum over ranks = global loss)."""
 
     @staticmethod
     def forward(ctx, e, f, temperature):
         inv_tau = 1.0 / float(temperature)
+        Bl, D = e.shape
+        peers = _PeerShards.get(Bl, 3 * D, e.device)
         # fp32 unit vectors + their 3-way tf32 splits: the similarity contraction is fp32-accurate
-        en, e3, einv = ops.l2norm_split_fwd(e, 0)
-        fn, f3, finv = ops.l2norm_split_fwd(f, 1)
-        e3_all = _AllGatherRows.gather(e3)
-        f3_all = _AllGatherRows.gather(f3)
-        Bl, Bg = en.shape[0], e3_all.shape[0]
-        off = _CTX.rank * Bl if _CTX.active else 0
-        lse_ef, diag = ops.infonce_lse(e3, f3_all, inv_tau, off)
-        lse_fe, _ = ops.infonce_lse(f3, e3_all, inv_tau, off)
+        if peers is not None:
+            (e3, f3), (he, hf) = peers
+            en, _, einv = ops.l2norm_split_fwd(e, 0, xs_out=e3)
+            fn, _, finv = ops.l2norm_split_fwd(f, 1, xs_out=f3)
+            hf.barrier(channel=0)  # every rank's shards are written before anyone reads them
+            e_ptrs, f_ptrs = list(he.buffer_ptrs), list(hf.buffer_ptrs)
+            world, off = _CTX.world, _CTX.rank * Bl
+            lse_ef, diag = ops.infonce_lse_peers(e3, f_ptrs, Bl, inv_tau, off)
+            lse_fe, _ = ops.infonce_lse_peers(f3, e_ptrs, Bl, inv_tau, off)
+            Bg = world * Bl
+            ctx.peers = (e_ptrs, f_ptrs, Bl)
+            ctx.save_for_backward(en, fn, einv, finv, e3, f3, lse_ef, lse_fe)
+        else:
+            en, e3, einv = ops.l2norm_split_fwd(e, 0)
+            fn, f3, finv = ops.l2norm_split_fwd(f, 1)
+            e3_all = _AllGatherRows.gather(e3)
+            f3_all = _AllGatherRows.gather(f3)
+            Bg = e3_all.shape[0]
+            off = _CTX.rank * Bl if _CTX.active else 0
+            lse_ef, diag = ops.infonce_lse(e3, f3_all, inv_tau, off)
+            lse_fe, _ = ops.infonce_lse(f3, e3_all, inv_tau, off)
+            ctx.peers = None
+            ctx.save_for_backward(en, fn, einv, finv, e3, f3, lse_ef, lse_fe, e3_all, f3_all)
         loss = (0.5 / Bg) * ((lse_ef - diag).sum() + (lse_fe - diag).sum())
-        ctx.save_for_backward(en, fn, einv, finv, e3, f3, e3_all, f3_all, lse_ef, lse_fe)
         ctx.meta = (inv_tau, off, Bg)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        en, fn, einv, finv, e3, f3, e3_all, f3_all, lse_ef, lse_fe = ctx.saved_tensors
         inv_tau, off, Bg = ctx.meta
+        sv = ctx.saved_tensors
+        en, fn, einv, finv, e3, f3, lse_ef, lse_fe = sv[:8]
         D = en.shape[1]
         lse_ef_all = _AllGatherRows.gather(lse_ef)
         lse_fe_all = _AllGatherRows.gather(lse_fe)
         coef = 0.5 * inv_tau / Bg
-        G1 = ops.infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, off, coef)  # rows: my e, cols: all f
-        den = ops.linear_dgrad(G1, f3_all[:, :D])                                   # hi part = tf32(f_n)
-        G2 = ops.infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, off, coef)  # rows: my f, cols: all e
-        dfn = ops.linear_dgrad(G2, e3_all[:, :D])
+        if ctx.peers is not None:
+            e_ptrs, f_ptrs, Bl = ctx.peers
+            G1 = ops.infonce_grad_peers(e3, f_ptrs, Bl, lse_ef, lse_fe_all, inv_tau, off, coef)  # rows: my e, cols: all f
+            den = ops.linear_dgrad_peers(G1, f_ptrs, Bl, D, 3 * D)                                  # hi part = tf32(f_n)
+            G2 = ops.infonce_grad_peers(f3, e_ptrs, Bl, lse_fe, lse_ef_all, inv_tau, off, coef)  # rows: my f, cols: all e
+            dfn = ops.linear_dgrad_peers(G2, e_ptrs, Bl, D, 3 * D)
+        else:
+            e3_all, f3_all = sv[8], sv[9]
+            G1 = ops.infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, off, coef)
+            den = ops.linear_dgrad(G1, f3_all[:, :D])
+            G2 = ops.infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, off, coef)
+            dfn = ops.linear_dgrad(G2, e3_all[:, :D])
         de = ops.l2norm_bwd(den, en, einv) * g
         df = ops.l2norm_bwd(dfn, fn, finv) * g
         return de, df, None

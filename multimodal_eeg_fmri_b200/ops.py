@@ -460,13 +460,14 @@ def l2norm_fwd(x, eps=1e-12):
     return xn, inv
 
 
-def l2norm_split_fwd(x, which, eps=1e-12):
-    """-> (xn fp32 (M, D), xs (M, 3D) tf32 split [hi|lo|hi] (which=0) or [hi|hi|lo] (which=1), inv_norm)."""
+def l2norm_split_fwd(x, which, eps=1e-12, xs_out=None):
+    """-> (xn fp32 (M, D), xs (M, 3D) tf32 split [hi|lo|hi] (which=0) or [hi|hi|lo] (which=1), inv_norm).
+    `xs_out`: write the split into this (M, 3D) buffer (e.g. NVLink-mapped symmetric memory)."""
     _chk(x)
     x = x.contiguous()
     M, D = x.shape
     xn = torch.empty_like(x)
-    xs = torch.empty(M, 3 * D, device=x.device, dtype=torch.float32)
+    xs = torch.empty(M, 3 * D, device=x.device, dtype=torch.float32) if xs_out is None else xs_out
     inv = torch.empty(M, device=x.device, dtype=torch.float32)
     _w(6.0 * M * D, 20.0 * M * D)
     _call("xm_l2norm_split_fwd_f32", _p(x), _p(xn), _p(xs), _p(inv), M, D, float(eps), int(which), _stream())
@@ -519,6 +520,54 @@ def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
     _call("xm_infonce_grad_f32", _p(a), _p(b), _p(lse_row), _p(lse_col), _p(G), Ml, Ng, D, float(inv_tau),
           int(diag_off), float(coef), _stream())
     return G
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def infonce_lse_peers(a, peer_ptrs, rows_per_peer, inv_tau, diag_off=0):
+    """Row logsumexp of a @ [b_0; b_1; ...]^T * inv_tau where shard r of the second operand is read IN PLACE
+    from rank r's memory (peer_ptrs[r], NVLink-mapped): all-gather fused into the GEMM's TMA loads."""
+    _chk(a)
+    a = a.contiguous()
+    Ml, D = a.shape
+    G = len(peer_ptrs)
+    Ng = G * rows_per_peer
+    tn = _lib.lib().xm_infonce_tile_n()
+    ws = torch.empty(Ml * ((Ng + tn - 1) // tn), device=a.device, dtype=torch.float32)
+    lse = torch.empty(Ml, device=a.device, dtype=torch.float32)
+    diag = torch.empty(Ml, device=a.device, dtype=torch.float32)
+    _w(2.0 * Ml * Ng * D, 4.0 * (Ml * D + Ng * D + 2 * Ml))
+    _call("xm_infonce_lse_peers_f32", _p(a), _ptr_array(peer_ptrs), G, rows_per_peer, _p(lse), _p(diag), Ml, D,
+          float(inv_tau), int(diag_off), _p(ws), _stream())
+    return lse, diag
+
+
+def infonce_grad_peers(a, peer_ptrs, rows_per_peer, lse_row, lse_col, inv_tau, diag_off, coef):
+    _chk(a, lse_row, lse_col)
+    a = a.contiguous()
+    Ml, D = a.shape
+    G_ = len(peer_ptrs)
+    Ng = G_ * rows_per_peer
+    G = torch.empty(Ml, Ng, device=a.device, dtype=torch.float32)
+    _w(2.0 * Ml * Ng * D, 4.0 * (Ml * D + Ng * D + Ml * Ng))
+    _call("xm_infonce_grad_peers_f32", _p(a), _ptr_array(peer_ptrs), G_, rows_per_peer, _p(lse_row), _p(lse_col), _p(G), Ml,
+          D, float(inv_tau), int(diag_off), float(coef), _stream())
+    return G
+
+
+def linear_dgrad_peers(dy, peer_ptrs, rows_per_peer, K, ldw):
+    """dx (M, K) = dy (M, G*rows_per_peer) @ w, w row-sharded across the peers (first K columns of pitch-ldw rows)."""
+    _chk(dy)
+    dy = _rowmajor(dy)
+    M, N = dy.shape
+    assert N == len(peer_ptrs) * rows_per_peer
+    dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+    _w(2.0 * M * N * K, 4.0 * (M * N + N * K + M * K))
+    _call("xm_linear_dgrad_peers_f32", _p(dy), _ptr_array(peer_ptrs), len(peer_ptrs), rows_per_peer, _p(dx), M, K,
+          dy.stride(0), ldw, dx.stride(0), 0, _stream())
+    return dx
 
 
 # ------------------------------------------------------------------ multi-head self-attention core

@@ -1,0 +1,65 @@
+"""Multi-GPU check of the data-parallel paired step (run under torchrun on >= 2 B200s of one node):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dp_gpu_check.py
+
+Rank r trains on rows [r*Bl, (r+1)*Bl) of a global batch; the sharded run (SyncBN partial sums, peer-memory
+fused all-gather + InfoNCE, flat gradient all-reduce) must reproduce the single-process global-batch oracle:
+same global loss and same parameters after the steps.  Runs both the NVLink peer-memory path and the NCCL
+all-gather path and prints one line per path."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+for p in (HERE, os.path.dirname(HERE)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def main():
+    from multimodal_eeg_fmri_b200 import functional as XF
+    from multimodal_eeg_fmri_b200 import synthetic
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel, PairedTrainer, init_distributed
+    from oracle import paired_step as ps
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    init_distributed("nccl")
+    Bl, steps = 128, 2
+    eeg, roi, conn = synthetic.paired_batch(Bl * world, 8, 64, 12, 20, seed=5)
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    ok = True
+    for peer in (True, False):
+        XF.set_parallel_context(XF.ParallelContext(group=None, sync_bn=True, peer_memory=peer))
+        torch.manual_seed(7)
+        model = PairedBridgeModel(eeg_channels=8, n_roi=12, eeg_hidden=32, fmri_hidden=16, bridge_dim=32, dropout=0.0,
+                                  fmri_dropout=0.0, encoder="lite")
+        P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        trainer = PairedTrainer(model.cuda().train())
+        losses = []
+        for _ in range(steps):
+            loss = trainer.step(eeg[sl].cuda(), roi[sl].cuda(), conn[sl].cuda()).clone()
+            dist.all_reduce(loss)
+            losses.append(float(loss))
+        used_peer = peer and not XF._PeerShards._failed
+        if rank == 0:
+            state, want = {}, []
+            for _ in range(steps):
+                want.append(float(ps.paired_train_step(P, state, eeg, roi, conn, 0.07, "lite")[0]))
+            lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, want))
+            keys = set(ps.trainable_keys(P)) - set(ps.bias_before_batchnorm_keys(P))
+            sd = model.state_dict()
+            perr = max(float((sd[k].cpu() - P[k]).abs().max()) for k in keys)
+            good = lerr < 1e-3 and perr < 3e-4
+            ok = ok and good
+            print(f"dp_gpu_check world={world} path={'peer-memory' if used_peer else 'nccl-all-gather'} "
+                  f"loss_rel_err={lerr:.2e} param_max_abs_err={perr:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
