@@ -52,7 +52,7 @@ def main():
             keys = set(ps.trainable_keys(P)) - set(ps.bias_before_batchnorm_keys(P))
             sd = model.state_dict()
             perr = max(float((sd[k].cpu() - P[k]).abs().max()) for k in keys)
-            good = lerr < 1e-3 and perr < 3e-4
+            good = lerr < 1e-3 and perr < 4.5e-4  # 2 AdamW steps of lr 1e-4: a sign flip of a ~zero gradient moves a weight by 2*lr per step
             ok = ok and good
             print(f"dp_gpu_check world={world} path={'peer-memory' if used_peer else 'nccl-all-gather'} "
                   f"loss_rel_err={lerr:.2e} param_max_abs_err={perr:.2e} {'OK' if good else 'FAIL'}", flush=True)
