@@ -234,6 +234,10 @@ int xm_infonce_lse_peers_f32(const float* a, const void* const* b_peers, int n_p
 int xm_infonce_grad_peers_f32(const float* a, const void* const* b_peers, int n_peers, int64_t rows_per_peer,
                               const float* lse_row, const float* lse_col, float* G, int64_t Ml, int64_t D, float inv_tau,
                               int64_t diag_off, float coef, void* stream);
+/* All-gather through the same peer mappings: dst (n_peers * elems_per_peer) <- concatenation of the ranks'
+ * shards, one launch of 128-bit peer loads.  Used instead of the in-GEMM peer reads when a rank has many
+ * row tiles (every row tile would otherwise re-fetch every remote tile across NVLink). */
+int xm_peer_gather_f32(const void* const* src_peers, int n_peers, int64_t elems_per_peer, float* dst, void* stream);
 /* dx (M, K) = dy (M, n_peers*rows_per_peer) @ w, w row-sharded across peers (pitch ldw). */
 int xm_linear_dgrad_peers_f32(const float* dy, const void* const* w_peers, int n_peers, int64_t rows_per_peer, float* dx,
                               int64_t M, int64_t K, int64_t lddy, int64_t ldw, int64_t lddx, int round_out, void* stream);

@@ -434,6 +434,18 @@ __global__ void act_bwd_kernel(const float* __restrict__ dout, const float* __re
   }
 }
 
+// All-gather over NVLink peer mappings: block row r copies rank r's shard (read through its mapped pointer,
+// 128-bit loads) into slot r of the local buffer.  One launch, no NCCL.
+struct PeerPtrs {
+  const float* p[8];
+};
+__global__ void peer_gather_kernel(const PeerPtrs pp, long long n4, float* __restrict__ dst) {
+  const float4* src = reinterpret_cast<const float4*>(pp.p[blockIdx.y]);
+  float4* out = reinterpret_cast<float4*>(dst) + (long long)blockIdx.y * n4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    out[i] = src[i];
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = round_tf32(x[i]);
@@ -1219,6 +1231,18 @@ int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream) {
 int xm_split3_f32(const float* x, float* out, int64_t rows, int64_t cols, int which, int axis, void* stream) {
   if (!x || !out || rows <= 0 || cols <= 0 || (which != 0 && which != 1) || (axis != 0 && axis != 1)) return XM_ERR_INVALID;
   split3_kernel<<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>(x, out, rows, cols, which, axis);
+  return check_launch();
+}
+
+int xm_peer_gather_f32(const void* const* src_peers, int n_peers, int64_t elems_per_peer, float* dst, void* stream) {
+  if (!src_peers || !dst || n_peers <= 0 || n_peers > 8 || elems_per_peer <= 0 || (elems_per_peer & 3)) return XM_ERR_INVALID;
+  PeerPtrs pp;
+  for (int r = 0; r < 8; ++r) pp.p[r] = r < n_peers ? (const float*)src_peers[r] : nullptr;
+  for (int r = 0; r < n_peers; ++r)
+    if (!pp.p[r] || (reinterpret_cast<uintptr_t>(pp.p[r]) & 15)) return XM_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(dst) & 15) return XM_ERR_INVALID;
+  const long long n4 = elems_per_peer / 4;
+  peer_gather_kernel<<<dim3((unsigned)ew_grid(n4), (unsigned)n_peers), 256, 0, (cudaStream_t)stream>>>(pp, n4, dst);
   return check_launch();
 }
 

@@ -517,11 +517,22 @@ class SymmetricInfoNCE(torch.autograd.Function):
             hf.barrier(channel=0)  # every rank's shards are written before anyone reads them
             e_ptrs, f_ptrs = list(he.buffer_ptrs), list(hf.buffer_ptrs)
             world, off = _CTX.world, _CTX.rank * Bl
-            lse_ef, diag = ops.infonce_lse_peers(e3, f_ptrs, Bl, inv_tau, off)
-            lse_fe, _ = ops.infonce_lse_peers(f3, e_ptrs, Bl, inv_tau, off)
             Bg = world * Bl
-            ctx.peers = (e_ptrs, f_ptrs, Bl)
-            ctx.save_for_backward(en, fn, einv, finv, e3, f3, lse_ef, lse_fe)
+            if Bl <= 4 * 128:
+                # few row tiles: read the remote tiles inside the GEMMs (fused all-gather + contraction)
+                lse_ef, diag = ops.infonce_lse_peers(e3, f_ptrs, Bl, inv_tau, off)
+                lse_fe, _ = ops.infonce_lse_peers(f3, e_ptrs, Bl, inv_tau, off)
+                ctx.peers = (e_ptrs, f_ptrs, Bl)
+                ctx.save_for_backward(en, fn, einv, finv, e3, f3, lse_ef, lse_fe)
+            else:
+                # many row tiles: each would re-fetch every remote tile over NVLink (remote memory is not cached
+                # in the local L2), so gather once through the peer mappings and contract against the local copy
+                e3_all = ops.peer_gather(e_ptrs, Bl, 3 * D, e.device)
+                f3_all = ops.peer_gather(f_ptrs, Bl, 3 * D, e.device)
+                lse_ef, diag = ops.infonce_lse(e3, f3_all, inv_tau, off)
+                lse_fe, _ = ops.infonce_lse(f3, e3_all, inv_tau, off)
+                ctx.peers = None
+                ctx.save_for_backward(en, fn, einv, finv, e3, f3, lse_ef, lse_fe, e3_all, f3_all)
         else:
             en, e3, einv = ops.l2norm_split_fwd(e, 0)
             fn, f3, finv = ops.l2norm_split_fwd(f, 1)

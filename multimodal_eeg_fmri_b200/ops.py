@@ -526,6 +526,15 @@ def _ptr_array(ptrs):
     return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
 
 
+def peer_gather(peer_ptrs, rows_per_peer, cols, device):
+    """(G*rows_per_peer, cols) local copy of the ranks' shards, read through their NVLink mappings."""
+    G = len(peer_ptrs)
+    out = torch.empty(G * rows_per_peer, cols, device=device, dtype=torch.float32)
+    _w(0.0, 8.0 * out.numel())
+    _call("xm_peer_gather_f32", _ptr_array(peer_ptrs), G, rows_per_peer * cols, _p(out), _stream())
+    return out
+
+
 def infonce_lse_peers(a, peer_ptrs, rows_per_peer, inv_tau, diag_off=0):
     """Row logsumexp of a @ [b_0; b_1; ...]^T * inv_tau where shard r of the second operand is read IN PLACE
     from rank r's memory (peer_ptrs[r], NVLink-mapped): all-gather fused into the GEMM's TMA loads."""
