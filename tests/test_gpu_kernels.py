@@ -343,3 +343,41 @@ def test_attention_core_dropout_consistency(ops):
     (gx,) = torch.autograd.grad(ref, x, dout.double())
     dqkv = ops.attn_bwd(dout, qkv, probs, lse, H, scale, pdrop, seed)
     assert_close_rel(dqkv, gx, 3e-3, "dqkv with dropout")
+
+
+# ------------------------------------------------------------------ out-of-bounds canaries
+def test_ragged_outputs_do_not_write_past_their_extent(ops):
+    """compute-sanitizer is closed on this pool, so ragged shapes are checked with canaries: outputs are
+    carved out of a larger sentinel-filled buffer and the guard bands must stay untouched (the TMA-store
+    epilogue has to clip rows/columns that fall outside the tensor; the direct-store path has to guard them)."""
+    import ctypes
+    from multimodal_eeg_fmri_b200 import _lib
+    torch.manual_seed(21)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    SENT = 12345.0
+    for (M, N, K) in [(130, 36, 40), (257, 100, 96), (5, 2, 8), (1000, 132, 64)]:
+        x = torch.randn(M, K, device="cuda")
+        w = torch.randn(N, K, device="cuda")
+        guard = 64
+        buf = torch.full((guard + M * N + guard,), SENT, device="cuda")
+        y = buf[guard:guard + M * N].view(M, N)
+        _lib.call("xm_linear_fwd_f32", P(x), P(w), None, P(y), M, N, K, K, K, N, 0, 0, 1, None, st)
+        torch.cuda.synchronize()
+        assert bool((buf[:guard] == SENT).all()) and bool((buf[guard + M * N:] == SENT).all()), (M, N, K)
+        assert_close_rel(y, x.double() @ w.double().t(), TF32, f"linear {M}x{N}x{K}")
+    # attention: L not a multiple of 128, outputs embedded in guarded buffers
+    B, L, H, dh = 3, 77, 2, 32
+    d = H * dh
+    qkv = ops.round_tf32(torch.randn(B, L, 3 * d, device="cuda"))
+    NP = _lib.lib().xm_attn_keys_padded(L)
+    g = 256
+    obuf = torch.full((g + B * L * d + g,), SENT, device="cuda")
+    pbuf = torch.full((g + B * H * L * NP + g,), SENT, device="cuda")
+    lbuf = torch.full((g + B * H * L + g,), SENT, device="cuda")
+    out, probs, lse = obuf[g:-g].view(B, L, d), pbuf[g:-g].view(B * H, L, NP), lbuf[g:-g].view(B * H, L)
+    _lib.call("xm_attn_fwd_f32", P(qkv), P(out), P(probs), P(lse), B, L, H, dh, ctypes.c_float(dh ** -0.5), ctypes.c_float(0.0), 0, 0, st)
+    torch.cuda.synchronize()
+    for b_ in (obuf, pbuf, lbuf):
+        assert bool((b_[:g] == SENT).all()) and bool((b_[-g:] == SENT).all())
+    assert not bool((out == SENT).any()) and not bool((lse == SENT).any()) and not bool((probs == SENT).any())
