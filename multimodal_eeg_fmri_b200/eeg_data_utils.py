@@ -43,7 +43,7 @@ def window_indices(n_rec: int, n_samples: int, win: int, hop: int, rec_labels: O
                    rec_subjects: Optional[torch.Tensor] = None, device="cuda"):
     """int64 device tensors (starts, rec_ids, labels, subjects) of the n_rec * ((n-win)//hop + 1) windows;
     windows never cross recordings."""
-    if n_samples < win:
+    if n_samples < win or n_rec == 0:
         z = torch.empty(0, dtype=torch.int64, device=device)
         return z, z.clone(), (None if rec_labels is None else z.clone()), (None if rec_subjects is None else z.clone())
     as64 = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.int64, device=device).contiguous()
@@ -52,6 +52,9 @@ def window_indices(n_rec: int, n_samples: int, win: int, hop: int, rec_labels: O
 
 def gather_windows(rec: torch.Tensor, win: int, hop: int, channels_last: bool = False) -> torch.Tensor:
     """rec (R, C, n) -> (R*n_win, C, win), or (R*n_win, win, C) with channels_last=True."""
+    if rec.shape[0] == 0 or rec.shape[1] == 0 or rec.shape[2] < win:  # no complete window
+        shape = (0, win, rec.shape[1]) if channels_last else (0, rec.shape[1], win)
+        return torch.empty(shape, device=rec.device, dtype=torch.float32)
     return ops.window_gather(rec, win, hop, channels_last=channels_last)
 
 
@@ -82,6 +85,10 @@ def band_power(rec: torch.Tensor, fs: float, win: int, hop: int, bands=None, nff
     two >= win by default), one-sided PSD, sum over [lo, hi) bins times the bin width.
     Returns (R*n_win, C, n_bands) fp32; windows are read in place (never materialised)."""
     bands = list((bands or DEFAULT_BANDS).values()) if isinstance(bands or DEFAULT_BANDS, dict) else list(bands)
+    if rec.dim() != 3:
+        raise ValueError("rec must be (recordings, channels, samples)")
+    if rec.shape[0] == 0 or rec.shape[1] == 0 or rec.shape[2] < win:  # no complete window: empty result
+        return torch.empty(0, rec.shape[1], len(bands), device=rec.device, dtype=torch.float32)
     if nfft is None:
         nfft = 1 << max(6, (win - 1).bit_length())
     taper, sumsq = _hann(win, rec.device)

@@ -13,8 +13,13 @@ def aggregate_roi_timeseries(x: torch.Tensor, agg_method: str = "both") -> torch
     population std -- the `agg_method` switch of fMRI_CODE/fmri_utils.py:140-149 (same ValueError)."""
     if agg_method not in ("mean", "std", "both"):
         raise ValueError(f"Unknown agg method: {agg_method}")
-    both = XF.roi_meanstd(x)
+    if x.dim() != 3:
+        raise ValueError("expected (subjects, TR, ROI)")
     roi = x.shape[2]
+    if x.shape[0] == 0 or roi == 0:
+        both = torch.empty(x.shape[0], 2 * roi, device=x.device, dtype=torch.float32)
+    else:
+        both = XF.roi_meanstd(x)
     if agg_method == "mean":
         return both[:, :roi]
     if agg_method == "std":

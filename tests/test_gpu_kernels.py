@@ -381,3 +381,26 @@ def test_ragged_outputs_do_not_write_past_their_extent(ops):
     for b_ in (obuf, pbuf, lbuf):
         assert bool((b_[:g] == SENT).all()) and bool((b_[-g:] == SENT).all())
     assert not bool((out == SENT).any()) and not bool((lse == SENT).any()) and not bool((probs == SENT).any())
+
+
+def test_empty_and_degenerate_inputs(ops):
+    """Edge cases of the preprocessing API: recordings shorter than a window, zero recordings, a single
+    window, one-sample batches through the BatchNorm-free paths."""
+    from multimodal_eeg_fmri_b200 import eeg_data_utils as edu, fmri_utils
+    short = torch.randn(2, 4, 100, device="cuda")
+    assert edu.band_power(short, 1000.0, 256, 128).shape == (0, 4, 3)
+    assert edu.gather_windows(short, 256, 128).shape == (0, 4, 256)
+    assert edu.gather_windows(short, 256, 128, channels_last=True).shape == (0, 256, 4)
+    st, rid, lab, sub = edu.window_indices(0, 1000, 256, 128)
+    assert st.numel() == 0 and rid.numel() == 0
+    one = torch.randn(1, 1, 256, device="cuda")
+    assert edu.band_power(one, 256.0, 256, 256).shape == (1, 1, 3)  # exactly one window
+    assert fmri_utils.aggregate_roi_timeseries(torch.empty(0, 10, 5, device="cuda")).shape == (0, 10)
+    x = torch.randn(1, 1, 7, device="cuda")  # a single TR: std = 0
+    out = fmri_utils.aggregate_roi_timeseries(x)
+    assert torch.equal(out[:, :7], x[:, 0]) and float(out[:, 7:].abs().max()) == 0.0
+    e = torch.randn(1, 128, device="cuda", requires_grad=True)
+    from multimodal_eeg_fmri_b200.bridge_utils import symmetric_infonce
+    loss = symmetric_infonce(e, e.detach().clone())  # batch of one: L = log 1 = 0
+    loss.backward()
+    assert abs(float(loss)) < 1e-5 and float(e.grad.abs().max()) < 1e-5
