@@ -266,11 +266,13 @@ int xm_resid_ln_fwd_f32(const float* x, const float* a, const float* pe, int64_t
                         float* s_out, float* h, float* mean, float* rstd, int64_t M, int64_t D, float eps, float drop_p,
                         uint64_t seed, void* stream);
 /* ds = dres + LayerNormBackward(dh) [dres may be NULL];  dx = ds;  da = tf32(mask * ds / (1-p)) [da may be NULL];
- * dgamma_part / dbeta_part: (xm_resid_ln_nblk(M), D) per-block partial sums (reduce with xm_colsum_f32). */
+ * dgamma_part / dbeta_part / dabias_part: (xm_resid_ln_nblk(M), D) per-block partial sums (reduce with
+ * xm_colsum_f32); dabias_part (may be NULL) = column sums of da, i.e. the bias gradient of the Linear that
+ * produced the branch a -- accumulated here so that no separate pass over da is needed. */
 int xm_resid_ln_nblk(int64_t M);
 int xm_resid_ln_bwd_f32(const float* dh, const float* dres, const float* s, const float* gamma, const float* mean,
-                        const float* rstd, float* dx, float* da, float* dgamma_part, float* dbeta_part, int64_t M, int64_t D,
-                        float drop_p, uint64_t seed, void* stream);
+                        const float* rstd, float* dx, float* da, float* dgamma_part, float* dbeta_part, float* dabias_part,
+                        int64_t M, int64_t D, float drop_p, uint64_t seed, void* stream);
 /* out (B, D) = mean over T of x + Dropout(a)  (last residual add + AdaptiveAvgPool1d(1), :161-163), and its
  * backward: dx = dout / T broadcast, da = tf32(mask * dx / (1-p)); either output may be NULL. */
 int xm_resid_seqmean_fwd_f32(const float* x, const float* a, int64_t B, int64_t T, int64_t D, float* out, float drop_p,

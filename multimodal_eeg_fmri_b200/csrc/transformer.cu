@@ -91,15 +91,16 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 resid_ln_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dres, const float* __restrict__ s,
                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                     float* __restrict__ dx, float* __restrict__ da, float* __restrict__ dgamma_part,
-                    float* __restrict__ dbeta_part, long long M, float drop_scale, uint32_t drop_thresh, uint64_t seed) {
+                    float* __restrict__ dbeta_part, float* __restrict__ dabias_part, long long M, float drop_scale,
+                    uint32_t drop_thresh, uint64_t seed) {
   constexpr int D = NV * 128;
-  __shared__ float red[2][kLnWarps][D];
+  __shared__ float red[3][kLnWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[NV][4], ab[NV][4];
+  float ag[NV][4], ab[NV][4], ac[NV][4];  // dgamma, dbeta, column sums of da (bias gradient of the branch's Linear)
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ag[i][j] = ab[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) ag[i][j] = ab[i][j] = ac[i][j] = 0.f;
   float4 g4[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) g4[i] = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
@@ -144,6 +145,7 @@ resid_ln_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dres
         for (int j = 0; j < 4; ++j) {
           t[j] = o[j];
           if (drop_thresh) t[j] = dropout_keep((uint64_t)(row * D + c + j), seed, drop_thresh) ? t[j] * drop_scale : 0.f;
+          ac[i][j] += t[j];
           t[j] = round_tf32(t[j]);
         }
         *reinterpret_cast<float4*>(da + row * D + c) = make_float4(t[0], t[1], t[2], t[3]);
@@ -156,17 +158,20 @@ resid_ln_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dres
     for (int j = 0; j < 4; ++j) {
       red[0][warp][i * 128 + lane * 4 + j] = ag[i][j];
       red[1][warp][i * 128 + lane * 4 + j] = ab[i][j];
+      red[2][warp][i * 128 + lane * 4 + j] = ac[i][j];
     }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float sg = 0.f, sb = 0.f;
+    float sg = 0.f, sb = 0.f, sc = 0.f;
 #pragma unroll
     for (int w = 0; w < kLnWarps; ++w) {
       sg += red[0][w][c];
       sb += red[1][w][c];
+      sc += red[2][w][c];
     }
     dgamma_part[(long long)blockIdx.x * D + c] = sg;
     dbeta_part[(long long)blockIdx.x * D + c] = sb;
+    if (dabias_part != nullptr) dabias_part[(long long)blockIdx.x * D + c] = sc;
   }
 }
 
@@ -290,8 +295,8 @@ int xm_resid_ln_fwd_f32(const float* x, const float* a, const float* pe, int64_t
 }
 
 int xm_resid_ln_bwd_f32(const float* dh, const float* dres, const float* s, const float* gamma, const float* mean,
-                        const float* rstd, float* dx, float* da, float* dgamma_part, float* dbeta_part, int64_t M, int64_t D,
-                        float drop_p, uint64_t seed, void* stream) {
+                        const float* rstd, float* dx, float* da, float* dgamma_part, float* dbeta_part, float* dabias_part,
+                        int64_t M, int64_t D, float drop_p, uint64_t seed, void* stream) {
   if (!dh || !s || !gamma || !mean || !rstd || !dx || !dgamma_part || !dbeta_part || M <= 0 ||
       !(drop_p >= 0.f && drop_p < 1.f))
     return XM_ERR_INVALID;
@@ -304,10 +309,10 @@ int xm_resid_ln_bwd_f32(const float* dh, const float* dres, const float* s, cons
   const int blocks = xm_resid_ln_nblk(M);
   cudaStream_t st = (cudaStream_t)stream;
   switch (D / 128) {
-    case 1: resid_ln_bwd_kernel<1><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, M, sc, th, seed); break;
-    case 2: resid_ln_bwd_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, M, sc, th, seed); break;
-    case 3: resid_ln_bwd_kernel<3><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, M, sc, th, seed); break;
-    default: resid_ln_bwd_kernel<4><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, M, sc, th, seed); break;
+    case 1: resid_ln_bwd_kernel<1><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, dabias_part, M, sc, th, seed); break;
+    case 2: resid_ln_bwd_kernel<2><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, dabias_part, M, sc, th, seed); break;
+    case 3: resid_ln_bwd_kernel<3><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, dabias_part, M, sc, th, seed); break;
+    default: resid_ln_bwd_kernel<4><<<blocks, kLnWarps * 32, 0, st>>>(dh, dres, s, gamma, mean, rstd, dx, da, dgamma_part, dbeta_part, dabias_part, M, sc, th, seed); break;
   }
   return check_launch();
 }

@@ -391,30 +391,32 @@ class TransformerTail(torch.autograd.Function):
         sv = ctx.saved_tensors
         dxs, df2 = ops.resid_seqmean_bwd(dout.contiguous(), L, p, last_seed)
         dxs, df2 = dxs.view(M, D), df2.view(M, D)
+        db2 = ops.colsum(df2)  # bias gradient of the last block's linear2
         grads = [None] * (nl * 12)
         dh0 = None
         for l in reversed(range(nl)):
             (x1, h1, m1, r1, qkv, probs, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w) = sv[l * 20:(l + 1) * 20]
             s_attn, s_ao, s_g, s_in = meta[l]
             dg = ops.linear_dgrad(df2, w2_r)
-            dw2, db2 = ops.linear_wgrad(df2, g)
+            dw2, _ = ops.linear_wgrad(df2, g, need_bias=False)
             df1 = ops.act_bwd(dg, f1, act, p, s_g, round_out=True)
             del dg
             dh2 = ops.linear_dgrad(df1, w1_r)
             dw1, db1 = ops.linear_wgrad(df1, h2)
             del df1
-            dx1, dao, dn2w, dn2b = ops.resid_ln_bwd(dh2, dxs, x2, n2w, m2, r2, p, s_ao)
+            # bias gradients of out_proj / the previous linear2 come out of the fused LayerNorm-backward pass
+            dx1, dao, dn2w, dn2b, dbo = ops.resid_ln_bwd(dh2, dxs, x2, n2w, m2, r2, p, s_ao)
             datt = ops.linear_dgrad(dao, wo_r, round_out=True)
-            dwo, dbo = ops.linear_wgrad(dao, att.view(M, D))
+            dwo, _ = ops.linear_wgrad(dao, att.view(M, D), need_bias=False)
             dqkv = ops.attn_bwd(datt.view(B, L, D), qkv.view(B, L, 3 * D), probs, lse, nhead, scale, p, s_attn, round_out=True)
             dqkv = dqkv.view(M, 3 * D)
             dh1 = ops.linear_dgrad(dqkv, wqkv_r)
             dwqkv, dbqkv = ops.linear_wgrad(dqkv, h1)
             need_in = l > 0 or ctx.needs_input_grad[0]
-            dxs, dprev, dn1w, dn1b = ops.resid_ln_bwd(dh1, dx1, x1, n1w, m1, r1, p, s_in, need_da=need_in)
+            dxs, dprev, dn1w, dn1b, dbprev = ops.resid_ln_bwd(dh1, dx1, x1, n1w, m1, r1, p, s_in, need_da=need_in)
             grads[l * 12:(l + 1) * 12] = [dn1w, dn1b, dwqkv, dbqkv, dwo, dbo, dn2w, dn2b, dw1, db1, dw2, db2]
             if l > 0:
-                df2 = dprev  # gradient of the previous block's FFN branch (its dropout mask applied)
+                df2, db2 = dprev, dbprev  # gradient (and bias gradient) of the previous block's FFN branch
             else:
                 dh0 = None if dprev is None else dprev.view(B, L, D)  # d/d(conv output): Dropout(x + pe) backward
         return (dh0, None, None, *grads)

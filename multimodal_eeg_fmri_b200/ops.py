@@ -637,7 +637,8 @@ def resid_ln_fwd(x, a, gamma, beta, eps, drop_p=0.0, seed=0, pe=None, L=0):
 
 
 def resid_ln_bwd(dh, dres, s, gamma, mean, rstd, drop_p=0.0, seed=0, need_da=True):
-    """-> (dx, da | None, dgamma, dbeta)."""
+    """-> (dx, da | None, dgamma, dbeta, dabias | None); dabias = column sums of da (the bias gradient of the
+    Linear that produced the branch), accumulated in the same pass."""
     _chk(dh, dres, s)
     dh, s = dh.contiguous(), s.contiguous()
     dres = None if dres is None else dres.contiguous()
@@ -645,12 +646,12 @@ def resid_ln_bwd(dh, dres, s, gamma, mean, rstd, drop_p=0.0, seed=0, need_da=Tru
     nblk = _lib.lib().xm_resid_ln_nblk(M)
     dx = torch.empty_like(s)
     da = torch.empty_like(s) if need_da else None
-    gp = torch.empty(nblk, D, device=s.device, dtype=torch.float32)
-    bp = torch.empty(nblk, D, device=s.device, dtype=torch.float32)
+    parts = torch.empty(3 if need_da else 2, nblk, D, device=s.device, dtype=torch.float32)
     _w(20.0 * M * D, 4.0 * M * D * (3 + (dres is not None) + need_da))
-    _call("xm_resid_ln_bwd_f32", _p(dh), _p(dres), _p(s), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(da), _p(gp), _p(bp), M, D,
-          float(drop_p), int(seed), _stream())
-    return dx, da, colsum(gp), colsum(bp)
+    _call("xm_resid_ln_bwd_f32", _p(dh), _p(dres), _p(s), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(da), _p(parts[0]),
+          _p(parts[1]), _p(parts[2]) if need_da else None, M, D, float(drop_p), int(seed), _stream())
+    sums = colsum(parts.transpose(0, 1).reshape(nblk, -1))  # one reduction for all partial vectors
+    return dx, da, sums[:D], sums[D:2 * D], (sums[2 * D:] if need_da else None)
 
 
 def resid_seqmean_fwd(x, a, drop_p=0.0, seed=0):

@@ -158,6 +158,14 @@ class PairedTrainer:
         losses: List[float] = []
         if not batches:
             return losses
+        # every step's loss goes device -> pinned host asynchronously and is consumed one step later, so the
+        # host keeps enqueueing step k+1 while step k runs (a blocking .item() per step would expose the
+        # launch latency of ~300 kernels as GPU idle time)
+        pinned = getattr(self, "_loss_pinned", None)
+        if pinned is None or pinned.numel() < len(batches):
+            pinned = torch.empty(max(len(batches), 16), dtype=torch.float32).pin_memory()
+            self._loss_pinned = pinned
+        done = [torch.cuda.Event() for _ in batches]
         stage(sets[0], batches[0])
         for k, _ in enumerate(batches):
             cur = sets[k % 2]
@@ -166,7 +174,13 @@ class PairedTrainer:
             main.wait_event(cur["ready"])
             loss = self.step(*cur["bufs"])
             cur["free"].record(main)
-            losses.append(float(loss.item()))
+            pinned[k:k + 1].copy_(loss.reshape(1), non_blocking=True)
+            done[k].record(main)
+            if k > 0:
+                done[k - 1].synchronize()
+                losses.append(float(pinned[k - 1]))
+        done[-1].synchronize()
+        losses.append(float(pinned[len(batches) - 1]))
         return losses
 
 

@@ -308,7 +308,8 @@ def resid_ln_bwd(dh, dres, s, gamma, mean, rstd, drop_p=0.0, seed=0, need_da=Tru
     ds = rstd.double()[:, None] * (dz - dz.mean(1, keepdim=True) - xh * (dz * xh).mean(1, keepdim=True))
     if dres is not None:
         ds = ds + dres.double()
-    return ds.float(), (ds.float() if need_da else None), (dh.double() * xh).sum(0).float(), dh.double().sum(0).float()
+    return (ds.float(), (ds.float() if need_da else None), (dh.double() * xh).sum(0).float(), dh.double().sum(0).float(),
+            (ds.sum(0).float() if need_da else None))
 
 
 def resid_seqmean_fwd(x, a, drop_p=0.0, seed=0):
