@@ -272,7 +272,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (paired samples)")
     ap.add_argument("--encoder", default="v4", choices=["v4", "lite"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-batch", type=int, default=64, help="paired samples per CPU-baseline step (bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")

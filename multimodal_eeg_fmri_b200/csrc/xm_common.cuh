@@ -59,14 +59,20 @@ XM_DEVICE float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Counter-based dropout mask: one 32-bit hash per element (murmur3 finaliser over a
-// seed-keyed index).  keep  <=>  hash >= threshold, threshold = p * 2^32.
+// Counter-based dropout mask: one 32-bit hash per element (three multiply / xor-shift rounds over a
+// seed-keyed index; ~10 integer instructions -- the streaming kernels that apply dropout next to an erf
+// GELU are instruction-bound, a 64-bit mixer doubled their integer work).
+// keep  <=>  hash >= threshold, threshold = p * 2^32.
 XM_DEVICE uint32_t hash_u32(uint64_t idx, uint64_t seed) {
-  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+  uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x9E3779B1u) ^ (uint32_t)seed;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x += (uint32_t)(seed >> 32);
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  x *= 0x27D4EB2Fu;
+  x ^= x >> 15;
+  return x;
 }
 XM_DEVICE bool dropout_keep(uint64_t idx, uint64_t seed, uint32_t threshold) {
   return hash_u32(idx, seed) >= threshold;
