@@ -283,6 +283,9 @@ int xm_resid_seqmean_bwd_f32(const float* dout, int64_t B, int64_t T, int64_t D,
 /* ------------------------------------------------------------------ diagnostics (not on the product path)
  * Dump the raw shared-memory image of one TMA box {32,32} loaded at (c0, c1) from a (rows, cols)
  * fp32 matrix; swizzle_atom32 selects SWIZZLE_128B_ATOM_32B instead of SWIZZLE_128B. */
+/* A/B switch for the conv-wgrad operand staging (1: one halo tile per k-block serves every tap through
+ * descriptor start-address shifts; 0: one shifted TMA copy per tap).  Returns the previous setting. */
+int xm_debug_set_conv_halo(int on);
 int xm_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int64_t ld, int c0, int c1, int swizzle_atom32,
                        float* out, void* stream);
 

@@ -162,7 +162,7 @@ XM_DEVICE float drop_mul(const BnActArgs& a, long long idx) {
 //   pool == 2: input rows (b*T + 2tp, +1) -> out row b*To + tp
 XM_DEVICE float bn_act_fwd_elem(const BnActArgs& a, long long ro, int c, float sc, float sh) {
   if (a.pool == 2) {
-    const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+    const long long To = a.T / 2, b = (long long)((unsigned)ro / (unsigned)To), tp = ro - b * To;
     const long long r0 = b * a.T + 2 * tp;
     float a0 = apply_act(a.y[r0 * a.ldy + c] * sc + sh, a.act);
     float a1 = apply_act(a.y[(r0 + 1) * a.ldy + c] * sc + sh, a.act);
@@ -181,7 +181,7 @@ XM_DEVICE void bn_act_dz(const BnActArgs& a, const float* __restrict__ dout, lon
                          float& x0, float& x1, float& dz0, float& dz1) {
   const float g = dout[ro * a.ldo + c];
   if (a.pool == 2) {
-    const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+    const long long To = a.T / 2, b = (long long)((unsigned)ro / (unsigned)To), tp = ro - b * To;
     const long long r0 = b * a.T + 2 * tp;
     x0 = a.y[r0 * a.ldy + c];
     x1 = a.y[(r0 + 1) * a.ldy + c];
@@ -293,7 +293,7 @@ __global__ void bn_act_bwd_apply_kernel(const BnActArgs a, const float* __restri
     float x0, x1, dz0, dz1;
     bn_act_dz(a, dout, ro, c, sc, sh, x0, x1, dz0, dz1);
     if (a.pool == 2) {
-      const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+      const long long To = a.T / 2, b = (long long)((unsigned)ro / (unsigned)To), tp = ro - b * To;
       const long long r0 = b * a.T + 2 * tp;
       float o0 = sc * (dz0 - k1 - (x0 - mu) * is * k2);
       float o1 = sc * (dz1 - k1 - (x1 - mu) * is * k2);
@@ -673,6 +673,7 @@ static BnActArgs make_bn_args(const float* y, const float* mean, const float* in
 static bool bn_args_ok(const void* y, const void* m, const void* is, const void* g, const void* b, int64_t B, int64_t T,
                        int64_t C, int64_t ldy, int pool, float p) {
   if (!y || !m || !is || !g || !b || B <= 0 || C <= 0 || T <= 0 || ldy < C) return false;
+  if (B * T >= 2147483647ll) return false;  // 32-bit row arithmetic in the pooled paths
   if (pool != 0 && pool != 2) return false;
   if (pool == 2 && T < 2) return false;
   if (!(p >= 0.f && p < 1.f)) return false;
@@ -793,7 +794,7 @@ __global__ void bn_act_fwd_v4_kernel(const BnActArgs a, long long R_out, float* 
   for (long long ro = blockIdx.x * (long long)blockDim.y + threadIdx.y; ro < R_out; ro += stride) {
     F4 o;
     if (POOL == 2) {
-      const long long b = ro / To, tp = ro - b * To;
+      const long long b = (long long)((unsigned)ro / (unsigned)To), tp = ro - b * To;  // rows < 2^31 (host-checked)
       const long long r0 = b * a.T + 2 * tp;
       const F4 x0 = ld4(a.y + r0 * a.ldy + c0), x1 = ld4(a.y + (r0 + 1) * a.ldy + c0);
 #pragma unroll
@@ -835,7 +836,7 @@ XM_DEVICE void bn_dz4(const BnActArgs& a, const ChanConst& k, const float* __res
                       long long& r0, F4& x0, F4& x1, F4& dz0, F4& dz1) {
   const F4 g = ld4(dout + ro * a.ldo + c0);
   if (POOL == 2) {
-    const long long To = a.T / 2, b = ro / To, tp = ro - b * To;
+    const long long To = a.T / 2, b = (long long)((unsigned)ro / (unsigned)To), tp = ro - b * To;
     r0 = b * a.T + 2 * tp;
     x0 = ld4(a.y + r0 * a.ldy + c0);
     x1 = ld4(a.y + (r0 + 1) * a.ldy + c0);
@@ -960,7 +961,7 @@ __global__ void bn_act_bwd_apply_v4_kernel(const BnActArgs a, const float* __res
     st4(dy + r0 * a.ldy + c0, o0);
     if (POOL == 2) {
       st4(dy + (r0 + 1) * a.ldy + c0, o1);
-      const long long b = ro / To, tp = ro - b * To;
+      const long long b = (long long)((unsigned)ro / (unsigned)To), tp = ro - b * To;  // rows < 2^31 (host-checked)
       if ((a.T & 1) && tp == To - 1) {  // odd tail row is dropped by the pool: dz = 0
         const F4 xt = ld4(a.y + (r0 + 2) * a.ldy + c0);
         F4 ot;
@@ -975,7 +976,9 @@ __global__ void bn_act_bwd_apply_v4_kernel(const BnActArgs a, const float* __res
   }
 }
 
-static bool v4_ok(const void* p0, const void* p1, const void* p2, int64_t C, int64_t ld0, int64_t ld1) {
+static bool v4_ok(const void* p0, const void* p1, const void* p2, int64_t C, int64_t ld0, int64_t ld1,
+                  int64_t rows = 0) {
+  if (rows >= 2147483647ll) return false;  // the float4 kernels use 32-bit row arithmetic
   auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   return (C % 4 == 0) && C <= 1024 && (ld0 % 4 == 0) && (ld1 % 4 == 0) && al(p0) && al(p1) && al(p2);
 }
@@ -1072,7 +1075,7 @@ int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, co
   BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);
   const long long R_out = B * (pool == 2 ? T / 2 : T);
-  if (v4_ok(y, out, nullptr, C, ldy, ldo)) {
+  if (v4_ok(y, out, nullptr, C, ldy, ldo, B * T)) {
     const dim3 blk = v4_block(C);
     XM_BN_DISPATCH(bn_act_fwd_v4_kernel, act, pool, <<<v4_grid(R_out, blk.y), blk, 0, (cudaStream_t)stream>>>(a, R_out, out));
     return check_launch();
@@ -1090,7 +1093,7 @@ int xm_bn_act_bwd_reduce_f32(const float* dout, const float* y, const float* mea
   const long long R_out = B * (pool == 2 ? T / 2 : T);
   const int ns = xm_bn_nsplit(B * T, C);  // same split count as the forward statistics
   const long long rps = (R_out + ns - 1) / ns;
-  if (v4_ok(y, dout, nullptr, C, ldy, ldo)) {
+  if (v4_ok(y, dout, nullptr, C, ldy, ldo, B * T)) {
     const dim3 blk = v4_block(C);
     XM_BN_DISPATCH(bn_act_bwd_reduce_v4_kernel, act, pool,
                    <<<ns, blk, blk.y * C * 2 * sizeof(double), (cudaStream_t)stream>>>(a, dout, R_out, rps, partials));
@@ -1118,7 +1121,7 @@ int xm_bn_act_bwd_apply_f32(const float* dout, const float* y, const float* mean
   BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);
   const long long R_out = B * (pool == 2 ? T / 2 : T);
-  if (v4_ok(y, dout, dy, C, ldy, ldo)) {
+  if (v4_ok(y, dout, dy, C, ldy, ldo, B * T)) {
     const dim3 blk = v4_block(C);
     XM_BN_DISPATCH(bn_act_bwd_apply_v4_kernel, act, pool,
                    <<<v4_grid(R_out, blk.y), blk, 0, (cudaStream_t)stream>>>(a, dout, dbeta, dgamma,

@@ -53,6 +53,14 @@ struct GemmParams {
   int bn;          // N of one MMA / one accumulator (multiple of 16, <= 256)
   int taps_k;      // taps iterated inside the K loop (conv fwd / dgrad), >= 1
   int taps_n;      // taps held as separate accumulators (conv wgrad), >= 1
+  int b_halo;      // MN-major B with taps_n > 1: ONE halo tile of 32 + b_halo k-rows per 32-wide MN block serves
+                   // every tap (tap t = the same tile read from row t: a +128 B start-address shift of the
+                   // shared-memory descriptor) instead of taps_n shifted copies
+  int b_blk_bytes; // bytes per 32-wide MN block of the halo tile (1024-B multiple)
+  int a_halo;      // K-major A with taps_k > 1 (conv fwd / dgrad): ONE halo slab of 128 + a_halo rows per k-block
+                   // serves every tap (tap t = the slab read from row a_tap_row0 + t*a_tap_dir) and the stage
+                   // carries the taps_k weight tiles: the activations cross L2 -> smem once, not taps_k times
+  int a_slab_bytes, a_tap_row0, a_tap_dir, a_halo_row_shift;  // slab starts a_halo_row_shift rows from a.base[1]
   int kin_count;   // inner k-blocks per (kout, tap)
   int kout_count;  // outer k iterations per tile (split along the z tile index when kout_split != 0)
   int kout_total;  // total outer k iterations (only used when kout_split != 0)
@@ -323,8 +331,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // 1024-B aligned operand ring (128B swizzle atoms are 1024 B), then the epilogue staging buffers
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  const int b_tile_bytes = p.bn * 128;
-  const int stage_bytes = kATileBytes + p.taps_n * b_tile_bytes;
+  const int b_tile_bytes = p.b_halo ? (p.bn >> 5) * p.b_blk_bytes : p.bn * 128;
+  const int a_bytes = p.a_halo ? p.a_slab_bytes : kATileBytes;
+  const int stage_bytes = a_bytes + (p.b_halo ? 1 : (p.a_halo ? p.taps_k : p.taps_n)) * b_tile_bytes;
+  const int stage_tx_bytes = p.b_halo   ? kATileBytes + (p.bn >> 5) * (32 + p.b_halo) * 128
+                             : p.a_halo ? (128 + p.a_halo) * 128 + p.taps_k * b_tile_bytes
+                                        : stage_bytes;
+  const int taps_k_loop = p.a_halo ? 1 : p.taps_k;  // with a halo slab the taps live inside one stage
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
   const int acc_cols = p.taps_n * p.bn;
 
@@ -370,15 +383,36 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int ko = 0; ko < t.kout_n; ++ko) {
           const int kout = t.kout_lo + ko;
-          for (int tk = 0; tk < p.taps_k; ++tk) {
+          for (int tk = 0; tk < taps_k_loop; ++tk) {
             for (int kin = 0; kin < p.kin_count; ++kin) {
               ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-              ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+              ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_tx_bytes);
               uint8_t* sa = smem + (size_t)s * stage_bytes;
+              if (p.a_halo) {
+                // halo slab (rows of every tap) + the taps_k weight tiles of this k-block
+                ptx::tma_load_3d(&tmA, &full_bar[s], sa, ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0],
+                                 ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + p.a_halo_row_shift,
+                                 ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2]);
+                for (int tp = 0; tp < p.taps_k; ++tp)
+                  issue_operand_loads(&tmB, &full_bar[s], sa + a_bytes + tp * b_tile_bytes, p.b,
+                                      cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tp * p.b.tap_step[0],
+                                      cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tp * p.b.tap_step[1],
+                                      cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tp * p.b.tap_step[2]);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+                continue;
+              }
               issue_operand_loads(&tmA, &full_bar[s], sa, p.a,
                                   ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0] + tk * p.a.tap_step[0],
                                   ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + tk * p.a.tap_step[1],
                                   ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2] + tk * p.a.tap_step[2]);
+              if (p.b_halo) {  // one halo box per MN block (rows of tap 0 ... tap taps_n-1 overlap)
+                const int nbox = p.bn >> 5;
+                for (int bxi = 0; bxi < nbox; ++bxi)
+                  ptx::tma_load_3d(&tmB, &full_bar[s], sa + a_bytes + bxi * p.b_blk_bytes,
+                                   cb[0] + 32 * bxi + kin * p.b.kin_step[0] + kout * p.b.kout_step[0],
+                                   cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1],
+                                   cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2]);
+              } else
               for (int tn = 0; tn < p.taps_n; ++tn) {
                 const int tap = tk + tn;  // exactly one of taps_k / taps_n exceeds 1
                 int b1 = cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tap * p.b.tap_step[1];
@@ -388,7 +422,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   b1 -= owner * p.peer_rows;
                   tb = &peers.m[owner];
                 }
-                issue_operand_loads(tb, &full_bar[s], sa + kATileBytes + tn * b_tile_bytes, p.b,
+                issue_operand_loads(tb, &full_bar[s], sa + a_bytes + tn * b_tile_bytes, p.b,
                                     cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tap * p.b.tap_step[0], b1,
                                     cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tap * p.b.tap_step[2]);
               }
@@ -419,17 +453,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t a_kstep = p.a.mn_major ? 1024u : 32u;  // bytes per K=8 slab
       const uint32_t b_kstep = p.b.mn_major ? 1024u : 32u;
       const uint32_t a_lbo = p.a.mn_major ? 4096u : 16u;
-      const uint32_t b_lbo = p.b.mn_major ? 4096u : 16u;
+      const uint32_t b_lbo = p.b_halo ? (uint32_t)p.b_blk_bytes : (p.b.mn_major ? 4096u : 16u);
       const uint32_t a_sbo = p.a.mn_major ? 512u : 1024u;
       const uint32_t b_sbo = p.b.mn_major ? 512u : 1024u;
       const uint32_t a_lt = p.a.mn_major ? 1u : 2u;
       const uint32_t b_lt = p.b.mn_major ? 1u : 2u;
+      // Descriptors are built ONCE (for stage 0, K-slab 0, tap 0); every other operand view is the same
+      // descriptor with its 14-bit start-address field advanced by (byte offset >> 4).  The single issuing
+      // thread then spends ~4 integer instructions per MMA instead of ~30 -- with N = 64 tiles an MMA lasts
+      // only 32 cycles, so descriptor arithmetic was what paced the conv kernels.
+      const uint32_t smem0 = ptx::smem_u32(smem);
+      const uint64_t da0 = ptx::make_smem_desc(smem0, a_lbo, a_sbo, a_lt);
+      const uint64_t db0 = ptx::make_smem_desc(smem0 + a_bytes, b_lbo, b_sbo, b_lt);
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t a_k16 = a_kstep >> 4, b_k16 = b_kstep >> 4;
+      const uint32_t b_tap16 = (uint32_t)(p.b_halo ? 128 : b_tile_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const TileCoord t = decode_tile(p, tile);
-        const int total_kb = t.kout_n * p.taps_k * p.kin_count;
+        const int total_kb = t.kout_n * taps_k_loop * p.kin_count;
         const int buf = (p.acc_bufs == 2) ? (it & 1) : 0;
         const uint32_t use = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it);
         ptx::mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator set
@@ -438,15 +482,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < total_kb; ++kb) {
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after_sync();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-          for (int tn = 0; tn < p.taps_n; ++tn) {
-            const uint32_t sb = sa + kATileBytes + tn * b_tile_bytes;
+          const uint64_t das = da0 + (uint64_t)((uint32_t)s * stage16);
+          const uint64_t dbs = db0 + (uint64_t)((uint32_t)s * stage16);
+          if (p.a_halo) {  // taps inside the stage: A = halo slab shifted by whole rows (128 B), B = tap tile
+            for (int tp = 0; tp < p.taps_k; ++tp) {
+              const uint64_t dat = das + (uint64_t)((uint32_t)(p.a_tap_row0 + tp * p.a_tap_dir) * 8u);
+              const uint64_t dbt = dbs + (uint64_t)((uint32_t)tp * ((uint32_t)b_tile_bytes >> 4));
 #pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-              const uint64_t da = ptx::make_smem_desc(sa + k8 * a_kstep, a_lbo, a_sbo, a_lt);
-              const uint64_t db = ptx::make_smem_desc(sb + k8 * b_kstep, b_lbo, b_sbo, b_lt);
-              ptx::mma_tf32_ss(acc + (uint32_t)(tn * p.bn), da, db, idesc, (kb > 0 || k8 > 0) ? 1u : 0u);
+              for (int k8 = 0; k8 < 4; ++k8)
+                ptx::mma_tf32_ss(acc, dat + (uint64_t)(k8 * a_k16), dbt + (uint64_t)(k8 * b_k16), idesc,
+                                 (kb > 0 || tp > 0 || k8 > 0) ? 1u : 0u);
             }
+            ptx::mma_commit(&empty_bar[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+            continue;
+          }
+          for (int tn = 0; tn < p.taps_n; ++tn) {
+            const uint64_t dbt = dbs + (uint64_t)((uint32_t)tn * b_tap16);
+            const uint32_t acc_t = acc + (uint32_t)(tn * p.bn);
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8)
+              ptx::mma_tf32_ss(acc_t, das + (uint64_t)(k8 * a_k16), dbt + (uint64_t)(k8 * b_k16), idesc,
+                               (kb > 0 || k8 > 0) ? 1u : 0u);
           }
           ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }

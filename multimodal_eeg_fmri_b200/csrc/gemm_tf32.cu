@@ -8,6 +8,7 @@
 namespace xm {
 
 int g_last_cuda_error = 0;
+int g_conv_halo = 1;  // conv wgrad: one halo tile per k-block instead of one shifted copy per tap (xm_debug_set_conv_halo)
 
 // ---------------------------------------------------------------- TMA descriptor encode
 // cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time
@@ -97,7 +98,33 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
       (tc.stride_bytes[0] & 15) == 0 && (tc.stride_bytes[1] & 15) == 0 && !((p.bn & 31) && grid.y > 1))
     p.tma_store = 1;
   if (!p.tma_store && epi != EPI_LSE && p.c == nullptr) return XM_ERR_INVALID;
-  const int stage_bytes = kATileBytes + p.taps_n * p.bn * 128;
+  p.b_halo = 0;
+  p.b_blk_bytes = 0;
+  if (p.taps_n > 1 && p.b.mn_major && !p.dual && p.n_peers == 0 && g_conv_halo) {
+    p.b_halo = p.taps_n - 1;
+    p.b_blk_bytes = ((32 + p.b_halo) * 128 + 1023) / 1024 * 1024;
+  }
+  p.a_halo = 0;
+  p.a_slab_bytes = 0;
+  if (p.taps_k > 1 && !p.a.mn_major && !p.b.mn_major && !p.dual && p.n_peers == 0 && p.taps_n == 1 && g_conv_halo &&
+      (p.a.tap_step[1] == 1 || p.a.tap_step[1] == -1) && p.a.tap_step[0] == 0 && p.a.tap_step[2] == 0) {
+    // conv fwd / dgrad: tap t reads rows base + t*dir; the slab starts at the lowest of them
+    p.a_halo = p.taps_k - 1;
+    p.a_slab_bytes = ((128 + p.a_halo) * 128 + 1023) / 1024 * 1024;
+    p.a_tap_dir = p.a.tap_step[1];
+    p.a_halo_row_shift = p.a_tap_dir > 0 ? 0 : -p.a_halo;  // dir = -1: rows base - (taps-1) ... base
+    p.a_tap_row0 = p.a_tap_dir > 0 ? 0 : p.a_halo;
+  }
+  int stage_bytes = p.b_halo ? kATileBytes + (p.bn >> 5) * p.b_blk_bytes : kATileBytes + p.taps_n * p.bn * 128;
+  if (p.a_halo) {
+    stage_bytes = p.a_slab_bytes + p.taps_k * p.bn * 128;
+    const int stg = p.tma_store ? staging_bytes(8) : 0;
+    if ((222 * 1024 - 1024 - stg) / stage_bytes < 2) {  // the weight tiles of all taps do not fit twice: per-tap stages
+      p.a_halo = 0;
+      p.a_slab_bytes = 0;
+      stage_bytes = kATileBytes + p.bn * 128;
+    }
+  }
   const int total_kb = p.kout_count * p.taps_k * p.kin_count;
   if (total_kb <= 0) return XM_ERR_INVALID;
   const int epi_warps = (epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) ? 16 : (epi == EPI_LSE ? 4 : 8);
@@ -126,9 +153,9 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
     rc2 = encode_tmap(&mb2, *tb2, 32, p.b2.mn_major ? 32 : (unsigned)p.bn, p.b2.mn_major);
     if (rc2 != XM_OK) return rc2;
   }
-  int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : 128, p.a.mn_major);
+  int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : (unsigned)(128 + p.a_halo), p.a.mn_major);
   if (rc != XM_OK) return rc;
-  rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? 32 : (unsigned)p.bn, p.b.mn_major);
+  rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? (unsigned)(32 + p.b_halo) : (unsigned)p.bn, p.b.mn_major);
   if (rc != XM_OK) return rc;
   if (p.tma_store) {
     rc = encode_tmap(&mc, tc, 32, 32, 0);
@@ -644,6 +671,11 @@ static int conv_like(const float* in, const float* wp, const float* bias, float*
   GemmParams p;
   zero_params(p);
   p.bn = choose_bn(Nc, (int64_t)t_tiles * B, 16);
+  // halo staging (launch_gemm) needs two stages of {activation slab + taps weight tiles}: narrow the N tile
+  // if that is what it takes (the slab is then re-read per N tile, still far less than once per tap)
+  while (taps > 1 && p.bn > 64 && (p.bn / 2) % 16 == 0 &&
+         2 * ((((128 + (int)taps - 1) * 128 + 1023) / 1024 * 1024) + (int)taps * p.bn * 128) > (222 - 1 - 64) * 1024)
+    p.bn /= 2;
   p.taps_k = (int)taps;
   p.kin_count = ceil_div(Kc, 32);
   p.a.mn_major = 0;  // activations: contraction index (channel) contiguous
@@ -900,6 +932,12 @@ __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0,
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = tile[i];
 }
 }  // namespace xm
+
+extern "C" int xm_debug_set_conv_halo(int on) {
+  const int old = xm::g_conv_halo;
+  xm::g_conv_halo = on ? 1 : 0;
+  return old;
+}
 
 extern "C" int xm_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int64_t ld, int c0, int c1,
                                   int swizzle_atom32, float* out, void* stream) {
