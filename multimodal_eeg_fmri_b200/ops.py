@@ -172,7 +172,20 @@ def linear_dgrad(dy, w, round_out=False):
 
 
 def linear_wgrad(dy, x, need_bias=True, splits: int = 0):
+    """dw (N, K) = dy^T x, db (N) = column sums of dy.  When the layer is wide on the output side (N > K,
+    e.g. the packed q/k/v projection 128 -> 384 or the FFN up-projection 128 -> 512) the contraction runs as
+    dw^T = x^T dy: the narrow side becomes the 128-row MMA tile and the wide side the N = 256 MMA width, which
+    halves the shared-memory operand traffic per FLOP of the tensor core (small-N MMAs are smem-bound)."""
     _chk(dy, x)
+    M, N = dy.shape
+    K = x.shape[1]
+    if N > K and N >= 256 and splits <= 0:
+        dwt, _ = _linear_wgrad_nk(x, dy, False, 0)  # (K, N)
+        return dwt.t().contiguous(), (colsum(_rowmajor(dy)) if need_bias else None)
+    return _linear_wgrad_nk(dy, x, need_bias, splits)
+
+
+def _linear_wgrad_nk(dy, x, need_bias=True, splits: int = 0):
     dy, x = _rowmajor(dy), _rowmajor(x)
     M, N = dy.shape
     K = x.shape[1]
