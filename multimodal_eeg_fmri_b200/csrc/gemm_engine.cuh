@@ -453,7 +453,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t a_kstep = p.a.mn_major ? 1024u : 32u;  // bytes per K=8 slab
       const uint32_t b_kstep = p.b.mn_major ? 1024u : 32u;
       const uint32_t a_lbo = p.a.mn_major ? 4096u : 16u;
-      const uint32_t b_lbo = p.b_halo ? (uint32_t)p.b_blk_bytes : (p.b.mn_major ? 4096u : 16u);
+      const uint32_t b_lbo = p.b_halo ? 128u : (p.b.mn_major ? 4096u : 16u);
+      const uint32_t idesc_halo = ptx::make_idesc_tf32(128, p.taps_n * 32, p.a.mn_major, p.b.mn_major);
       const uint32_t a_sbo = p.a.mn_major ? 512u : 1024u;
       const uint32_t b_sbo = p.b.mn_major ? 512u : 1024u;
       const uint32_t a_lt = p.a.mn_major ? 1u : 2u;
@@ -497,6 +498,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (++s == p.stages) { s = 0; ph ^= 1u; }
             continue;
           }
+          if (p.b_halo) {
+            // Halo tile: the taps are 128-B (one k-row) shifts of the same 32-wide block, so ONE MMA per
+            // block covers all taps at once -- its N dimension walks taps_n "blocks" that are 128 B apart
+            // (leading-dimension byte offset = 128).  N = 32*taps instead of bn per MMA: 3.5x fewer reads of
+            // the A tile from shared memory, which is what bounded the small-N tap-by-tap MMAs.
+            const int nblk = p.bn >> 5;
+            for (int cb = 0; cb < nblk; ++cb) {
+              const uint64_t dbc = dbs + (uint64_t)((uint32_t)cb * ((uint32_t)p.b_blk_bytes >> 4));
+              const uint32_t acc_c = acc + (uint32_t)(cb * p.taps_n * 32);
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8)
+                ptx::mma_tf32_ss(acc_c, das + (uint64_t)(k8 * a_k16), dbc + (uint64_t)(k8 * b_k16), idesc_halo,
+                                 (kb > 0 || k8 > 0) ? 1u : 0u);
+            }
+          } else
           for (int tn = 0; tn < p.taps_n; ++tn) {
             const uint64_t dbt = dbs + (uint64_t)((uint32_t)tn * b_tap16);
             const uint32_t acc_t = acc + (uint32_t)(tn * p.bn);
@@ -638,7 +654,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float* cbase = p.c ? p.c + (long long)t.bz * p.c_z_stride + (long long)tn * p.c_tap_stride : nullptr;
           for (int c0 = part * 16; c0 < p.bn; c0 += 16 * NPARTS) {
             uint32_t r[16];
-            ptx::tmem_ld_32x16(acc + (uint32_t)(tn * p.bn + c0), r);
+            // halo layout: [ci block][tap][32 columns]; plain layout: [tap][bn columns]
+            const uint32_t acol = p.b_halo ? (uint32_t)((c0 >> 5) * (p.taps_n * 32) + tn * 32 + (c0 & 31))
+                                           : (uint32_t)(tn * p.bn + c0);
+            ptx::tmem_ld_32x16(acc + acol, r);
             ptx::tmem_ld_wait();
             if (EPI == EPI_LSE) {
 #pragma unroll

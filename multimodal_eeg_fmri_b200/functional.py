@@ -155,7 +155,11 @@ class ConvBnAct(torch.autograd.Function):
         dout = ops.as_nwc(dout)
         dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, pool, pd, seed, dbp, training, True)
         dx = ops.conv1d_dgrad(dy, wt, Cin, round_out=True) if ctx.needs_input_grad[0] else None
-        dw, db = ops.conv1d_wgrad(dy, x, taps, need_bias=True)
+        # A bias in front of a train-mode BatchNorm has an exactly zero gradient (sum over the batch of the BN
+        # input-gradient vanishes identically); the column reduction is only run when BN uses running stats.
+        dw, db = ops.conv1d_wgrad(dy, x, taps, need_bias=not training)
+        if training:
+            db = torch.zeros(dy.shape[2], device=dy.device, dtype=dy.dtype)
         return dx, dw, db, dgamma, dbeta, None, None, None
 
 
@@ -259,7 +263,9 @@ class LinearBnAct(torch.autograd.Function):
         dout = dout.contiguous()
         dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, 0, pd, seed, False, training, False)
         dx = ops.linear_dgrad_precise(dy, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.linear_wgrad_precise(dy, x, need_bias=True)
+        dw, db = ops.linear_wgrad_precise(dy, x, need_bias=not training)
+        if training:  # bias in front of a train-mode BatchNorm: gradient identically zero
+            db = torch.zeros(dy.shape[1], device=dy.device, dtype=dy.dtype)
         return dx, dw, db, dgamma, dbeta, None, None, None
 
 
