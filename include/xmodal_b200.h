@@ -178,6 +178,13 @@ int xm_act_fwd_f32(const float* x, float* out, int64_t n, int act, float drop_p,
 int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int act, float drop_p, uint64_t seed,
                    int round_out, void* stream);
 
+/* xm_act_bwd_f32 over (M, C) rows that also returns per-block column sums of dx in colsum_part
+ * (xm_act_bwd_colsum_nblk(M, C), C) -- the bias gradient of the Linear in front of the activation, without a
+ * second pass over dx (reduce the partials with xm_colsum_f32).  C % 4 == 0. */
+int xm_act_bwd_colsum_nblk(int64_t M, int64_t C);
+int xm_act_bwd_colsum_f32(const float* dout, const float* x, float* dx, int64_t M, int64_t C, int act, float drop_p,
+                          uint64_t seed, int round_out, float* colsum_part, void* stream);
+
 /* out = x rounded to nearest tf32 (10-bit mantissa) in an fp32 container: operands handed to the tensor
  * cores are rounded at their producer so the contraction sees no truncation bias (may run in place). */
 int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream);

@@ -524,6 +524,49 @@ __global__ void act_bwd_v4_kernel(const float* __restrict__ dout, const float* _
   }
 }
 
+// act backward over (M, C) rows that also accumulates the column sums of dx (the bias gradient of the Linear
+// whose output was activated): thread tx owns 4 columns, rows are strided over blockIdx / ty, per-block
+// partial sums -> (gridDim.x, C).  Saves a separate pass over dx.
+__global__ void act_bwd_colsum_v4_kernel(const float* __restrict__ dout, const float* __restrict__ x, float* __restrict__ dx,
+                                         long long M, int C, int act, float drop_scale, uint32_t drop_thresh, uint64_t seed,
+                                         int round_out, float* __restrict__ colsum_part) {
+  extern __shared__ float smf[];  // [RY][C]
+  const int tx = threadIdx.x, ty = threadIdx.y, RY = blockDim.y, c0 = 4 * tx;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = blockIdx.x * (long long)RY + ty; r < M; r += (long long)gridDim.x * RY) {
+    const long long i = r * C + c0;
+    const float4 gv = *reinterpret_cast<const float4*>(dout + i);
+    const float4 xv = *reinterpret_cast<const float4*>(x + i);
+    float g[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (drop_thresh) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = dropout_keep((uint64_t)(i + j), seed, drop_thresh) ? g[j] * drop_scale : 0.f;
+    }
+    if (act == XM_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] *= gelu_erf_grad(xs[j]);
+    } else if (act != XM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] *= act_grad(xs[j], act);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j] += g[j];
+      if (round_out) g[j] = round_tf32(g[j]);
+    }
+    *reinterpret_cast<float4*>(dx + i) = make_float4(g[0], g[1], g[2], g[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) smf[ty * C + c0 + j] = acc[j];
+  __syncthreads();
+  for (int c = ty * blockDim.x + tx; c < C; c += blockDim.x * RY) {
+    float t = 0.f;
+    for (int w = 0; w < RY; ++w) t += smf[w * C + c];
+    colsum_part[(long long)blockIdx.x * C + c] = t;
+  }
+}
+
 // ------------------------------------------------------------------ small reductions
 // out[n] = sum_m x[m, n] in two deterministic stages: block (bx, by) sums rows [by*chunk, (by+1)*chunk)
 // of columns [32 bx, 32 bx + 32) into part[by][n] (or straight into out when gridDim.y == 1); a second
@@ -1219,6 +1262,30 @@ int xm_act_bwd_f32(const float* dout, const float* x, float* dx, int64_t n, int 
   int rc = check_launch();
   if (rc == XM_OK && round_out) rc = xm_round_tf32_f32(dx, dx, n, stream);
   return rc;
+}
+
+int xm_act_bwd_colsum_nblk(int64_t M, int64_t C) {
+  if (C <= 0 || (C & 3) || C > 4096) return 0;
+  const int ry = (int)(C / 4 >= 256 ? 1 : 256 / (C / 4));
+  int64_t n = (M + ry - 1) / ry;
+  if (n > kNumSMs * 8) n = kNumSMs * 8;
+  return (int)(n < 1 ? 1 : n);
+}
+
+int xm_act_bwd_colsum_f32(const float* dout, const float* x, float* dx, int64_t M, int64_t C, int act, float drop_p,
+                          uint64_t seed, int round_out, float* colsum_part, void* stream) {
+  if (!dout || !x || !dx || !colsum_part || M <= 0 || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
+  const int nblk = xm_act_bwd_colsum_nblk(M, C);
+  if (nblk == 0 || C / 4 > 1024) return XM_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dx)) & 15) return XM_ERR_INVALID;
+  float sc;
+  uint32_t th;
+  drop_consts(drop_p, sc, th);
+  const int tx = (int)(C / 4);
+  const int ry = tx >= 256 ? 1 : 256 / tx;
+  act_bwd_colsum_v4_kernel<<<nblk, dim3(tx, ry), (size_t)ry * C * sizeof(float), (cudaStream_t)stream>>>(
+      dout, x, dx, M, (int)C, act, sc, th, seed, round_out, colsum_part);
+  return check_launch();
 }
 
 int xm_round_tf32_f32(const float* x, float* out, int64_t n, void* stream) {

@@ -405,10 +405,10 @@ class TransformerTail(torch.autograd.Function):
             s_attn, s_ao, s_g, s_in = meta[l]
             dg = ops.linear_dgrad(df2, w2_r)
             dw2, _ = ops.linear_wgrad(df2, g, need_bias=False)
-            df1 = ops.act_bwd(dg, f1, act, p, s_g, round_out=True)
+            df1, db1 = ops.act_bwd_colsum(dg, f1, act, p, s_g, round_out=True)  # bias gradient in the same pass
             del dg
             dh2 = ops.linear_dgrad(df1, w1_r)
-            dw1, db1 = ops.linear_wgrad(df1, h2)
+            dw1, _ = ops.linear_wgrad(df1, h2, need_bias=False)
             del df1
             # bias gradients of out_proj / the previous linear2 come out of the fused LayerNorm-backward pass
             dx1, dao, dn2w, dn2b, dbo = ops.resid_ln_bwd(dh2, dxs, x2, n2w, m2, r2, p, s_ao)

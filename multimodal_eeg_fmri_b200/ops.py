@@ -434,6 +434,23 @@ def linear_wgrad_precise(dy, x, need_bias=True):
     return dw, (colsum(dy) if need_bias else None)
 
 
+def act_bwd_colsum(dout, x, act, drop_p=0.0, seed=0, round_out=False):
+    """act_bwd on (M, C) rows + the column sums of the result (bias gradient of the preceding Linear)."""
+    _chk(dout, x)
+    dout, x = dout.contiguous(), x.contiguous()
+    M, C = x.shape
+    nblk = _lib.lib().xm_act_bwd_colsum_nblk(M, C)
+    if nblk == 0:
+        dx = act_bwd(dout, x, act, drop_p, seed, round_out)
+        return dx, colsum(dx)
+    dx = torch.empty_like(x)
+    part = torch.empty(nblk, C, device=x.device, dtype=torch.float32)
+    _w(10.0 * x.numel(), 12.0 * x.numel())
+    _call("xm_act_bwd_colsum_f32", _p(dout), _p(x), _p(dx), M, C, act_code(act), float(drop_p), int(seed), int(round_out),
+          _p(part), _stream())
+    return dx, colsum(part)
+
+
 def round_tf32(x, inplace=False):
     """Round to nearest tf32 (what the tensor cores would otherwise truncate to)."""
     _chk(x)

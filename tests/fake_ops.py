@@ -207,6 +207,11 @@ def linear_wgrad_precise(dy, x, need_bias=True):
     return linear_wgrad(dy, x, need_bias)
 
 
+def act_bwd_colsum(dout, x, act, drop_p=0.0, seed=0, round_out=False):
+    dx = act_bwd(dout, x, act, drop_p, seed, round_out)
+    return dx, dx.double().sum(0).float()
+
+
 def colsum(x):
     return x.double().sum(0).float()
 

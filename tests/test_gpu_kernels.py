@@ -404,3 +404,19 @@ def test_empty_and_degenerate_inputs(ops):
     loss = symmetric_infonce(e, e.detach().clone())  # batch of one: L = log 1 = 0
     loss.backward()
     assert abs(float(loss)) < 1e-5 and float(e.grad.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("M,C,act,p", [(1000, 512, "gelu", 0.0), (257, 128, "relu", 0.3), (64, 36, "gelu", 0.0)])
+def test_act_bwd_with_fused_bias_gradient(ops, M, C, act, p):
+    torch.manual_seed(31)
+    x = torch.randn(M, C, device="cuda")
+    dout = torch.randn(M, C, device="cuda")
+    dx, db = ops.act_bwd_colsum(dout, x, act, p, 99)
+    ref = ops.act_bwd(dout, x, act, p, 99)  # same mask stream
+    assert torch.equal(dx, ref)
+    assert_close_rel(db, ref.double().sum(0), FP32, "fused column sums", atol=1e-5)
+    if p == 0.0:
+        xd = x.double().requires_grad_(True)
+        y = F.gelu(xd) if act == "gelu" else torch.relu(xd)
+        (g,) = torch.autograd.grad(y, xd, dout.double())
+        assert_close_rel(dx, g, FP32, "act backward")
