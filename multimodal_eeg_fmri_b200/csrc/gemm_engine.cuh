@@ -115,13 +115,17 @@ constexpr int kMaxStages = 8;
 constexpr int staging_bufs(int epi_warps) { return epi_warps <= 8 ? 2 : 1; }
 constexpr int staging_bytes(int epi_warps) { return epi_warps * staging_bufs(epi_warps) * 4096; }
 
+// The whole producer warp runs the load loops; `lane` picks who issues which box, so the 4 KB boxes of an
+// MN-major tile (and the per-tap weight tiles of a halo stage) are issued by different lanes of ONE warp
+// instruction instead of one after another by a single thread.
 XM_DEVICE void issue_operand_loads(const CUtensorMap* tm, uint64_t* bar, uint8_t* dst, const OperandCfg& o, int c0,
-                                   int c1, int c2) {
+                                   int c1, int c2, int lane, int lane0 = 0) {
   if (!o.mn_major) {
-    ptx::tma_load_3d(tm, bar, dst, c0, c1, c2);
+    if (lane == lane0) ptx::tma_load_3d(tm, bar, dst, c0, c1, c2);
   } else {
     const int nbox = o.rows >> 5;
-    for (int bx = 0; bx < nbox; ++bx) ptx::tma_load_3d(tm, bar, dst + bx * 4096, c0 + 32 * bx, c1, c2);
+    const int bx = lane - lane0;
+    if (bx >= 0 && bx < nbox) ptx::tma_load_3d(tm, bar, dst + bx * 4096, c0 + 32 * bx, c1, c2);
   }
 }
 
@@ -369,8 +373,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------ TMA producer
+    {
+      // ------------------------------------------------ TMA producer (full warp; lane 0 owns the barriers)
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -386,28 +390,32 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int tk = 0; tk < taps_k_loop; ++tk) {
             for (int kin = 0; kin < p.kin_count; ++kin) {
               ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-              ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_tx_bytes);
+              if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_tx_bytes);
+              __syncwarp();  // the transaction count is armed before any lane's load can complete
               uint8_t* sa = smem + (size_t)s * stage_bytes;
               if (p.a_halo) {
-                // halo slab (rows of every tap) + the taps_k weight tiles of this k-block
-                ptx::tma_load_3d(&tmA, &full_bar[s], sa, ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0],
-                                 ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + p.a_halo_row_shift,
-                                 ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2]);
+                // halo slab (rows of every tap) by lane 0 + the taps_k weight tiles of this k-block, one lane each
+                if (lane == 0)
+                  ptx::tma_load_3d(&tmA, &full_bar[s], sa, ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0],
+                                   ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + p.a_halo_row_shift,
+                                   ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2]);
                 for (int tp = 0; tp < p.taps_k; ++tp)
                   issue_operand_loads(&tmB, &full_bar[s], sa + a_bytes + tp * b_tile_bytes, p.b,
                                       cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tp * p.b.tap_step[0],
                                       cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1] + tp * p.b.tap_step[1],
-                                      cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tp * p.b.tap_step[2]);
+                                      cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tp * p.b.tap_step[2], lane,
+                                      1 + tp);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
                 continue;
               }
               issue_operand_loads(&tmA, &full_bar[s], sa, p.a,
                                   ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0] + tk * p.a.tap_step[0],
                                   ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + tk * p.a.tap_step[1],
-                                  ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2] + tk * p.a.tap_step[2]);
-              if (p.b_halo) {  // one halo box per MN block (rows of tap 0 ... tap taps_n-1 overlap)
+                                  ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2] + tk * p.a.tap_step[2], lane);
+              if (p.b_halo) {  // one halo box per MN block (rows of tap 0 ... tap taps_n-1 overlap), lanes 8..
                 const int nbox = p.bn >> 5;
-                for (int bxi = 0; bxi < nbox; ++bxi)
+                const int bxi = lane - 8;
+                if (bxi >= 0 && bxi < nbox)
                   ptx::tma_load_3d(&tmB, &full_bar[s], sa + a_bytes + bxi * p.b_blk_bytes,
                                    cb[0] + 32 * bxi + kin * p.b.kin_step[0] + kout * p.b.kout_step[0],
                                    cb[1] + kin * p.b.kin_step[1] + kout * p.b.kout_step[1],
@@ -424,7 +432,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 issue_operand_loads(tb, &full_bar[s], sa + a_bytes + tn * b_tile_bytes, p.b,
                                     cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tap * p.b.tap_step[0], b1,
-                                    cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tap * p.b.tap_step[2]);
+                                    cb[2] + kin * p.b.kin_step[2] + kout * p.b.kout_step[2] + tap * p.b.tap_step[2], lane, 8);
               }
               if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
@@ -432,16 +440,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (p.dual) {  // second operand pair of the tile: one k-block into accumulator 1
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-          ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          __syncwarp();
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           issue_operand_loads(&tmA2, &full_bar[s], sa, p.a2,
                               p.a2.base[0] + t.bx * p.a2.sx[0] + t.by * p.a2.sy[0] + t.bz * p.a2.sz[0],
                               p.a2.base[1] + t.bx * p.a2.sx[1] + t.by * p.a2.sy[1] + t.bz * p.a2.sz[1],
-                              p.a2.base[2] + t.bx * p.a2.sx[2] + t.by * p.a2.sy[2] + t.bz * p.a2.sz[2]);
+                              p.a2.base[2] + t.bx * p.a2.sx[2] + t.by * p.a2.sy[2] + t.bz * p.a2.sz[2], lane);
           issue_operand_loads(&tmB2, &full_bar[s], sa + kATileBytes, p.b2,
                               p.b2.base[0] + t.bx * p.b2.sx[0] + t.by * p.b2.sy[0] + t.bz * p.b2.sz[0],
                               p.b2.base[1] + t.bx * p.b2.sx[1] + t.by * p.b2.sy[1] + t.bz * p.b2.sz[1],
-                              p.b2.base[2] + t.bx * p.b2.sx[2] + t.by * p.b2.sy[2] + t.bz * p.b2.sz[2]);
+                              p.b2.base[2] + t.bx * p.b2.sx[2] + t.by * p.b2.sy[2] + t.bz * p.b2.sz[2], lane, 8);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
