@@ -238,6 +238,13 @@ def act_dropout(x, act, drop_p=0.0, training=True):
     return ActDropout.apply(x, act, p, next_seed() if p > 0 else 0)
 
 
+# Contractions at least this long would run single-pass tf32 in LinearBnAct.  Disabled (every K is "short"):
+# measured with tools/acc_probe.py, a single-pass 40 000-d connectivity projection costs 1.2 ms less per step
+# but its 3e-4 forward noise is amplified by the BatchNorm-backward cancellation into a 1.4e-2 error of that
+# layer's weight gradient (7e-4 in the 3-pass mode).
+_PRECISE_MAX_K = 1 << 30
+
+
 class LinearBnAct(torch.autograd.Function):
     """Linear -> BatchNorm1d -> act -> Dropout on (B, F) rows (fMRI_CODE/fmri_utils.py:26-35, 66-71;
     crossmodal_v4_enhancements.py:696-723, 768-773, 909-914).  The projection runs in the fp32-accurate
@@ -247,7 +254,14 @@ class LinearBnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, cfg):
         eps, momentum, act, p, training = cfg
-        y = ops.linear_fwd_precise(x, w, b)
+        # 3-pass (fp32-accurate) projection (see _PRECISE_MAX_K for the single-pass escape hatch)
+        precise = x.shape[1] < _PRECISE_MAX_K
+        if precise:
+            y = ops.linear_fwd_precise(x, w, b)
+        else:
+            x, w = _tf32(x), _tf32(w)
+            y = ops.linear_fwd(x, w, b)
+        ctx.precise = precise
         mean, invstd, count = _bn_stats(y, eps, running_mean, running_var, momentum, training)
         seed = next_seed() if (training and p > 0) else 0
         pd = p if training else 0.0
@@ -261,9 +275,14 @@ class LinearBnAct(torch.autograd.Function):
         x, w, y, mean, invstd, gamma, beta = ctx.saved_tensors
         count, act, pd, seed, training = ctx.meta
         dout = dout.contiguous()
-        dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, 0, pd, seed, False, training, False)
-        dx = ops.linear_dgrad_precise(dy, w) if ctx.needs_input_grad[0] else None
-        dw, db = ops.linear_wgrad_precise(dy, x, need_bias=not training)
+        dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, 0, pd, seed, False, training,
+                                         not ctx.precise)
+        if ctx.precise:
+            dx = ops.linear_dgrad_precise(dy, w) if ctx.needs_input_grad[0] else None
+            dw, db = ops.linear_wgrad_precise(dy, x, need_bias=not training)
+        else:  # x, w were saved tf32-rounded; dy was rounded by the BN backward kernel
+            dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+            dw, db = ops.linear_wgrad(dy, x, need_bias=not training)
         if training:  # bias in front of a train-mode BatchNorm: gradient identically zero
             db = torch.zeros(dy.shape[1], device=dy.device, dtype=dy.dtype)
         return dx, dw, db, dgamma, dbeta, None, None, None
