@@ -87,9 +87,13 @@ int xm_roi_meanstd_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float
  * fMRI_CODE/fmri_utils.py:27,31,45,49,66 ; bridge_utils.py:35,41,61,65 ; enhanced_models_v4.py:164 */
 
 /* y (M,N) = act(x (M,K) @ w (N,K)^T + bias).  splits > 1 splits K across CTAs through
- * `workspace` (splits*M*N floats).  round_out rounds y to tf32. */
+ * `workspace` (splits*M*N floats).  flags: XM_LINEAR_ROUND_TF32 rounds y to tf32; XM_LINEAR_FP32_ACCUM
+ * limits the tensor core's own (truncating) accumulation to 256 contraction elements at a time and adds
+ * those chunks in fp32 round-to-nearest -- for the 3-pass fp32-accurate projections over long K. */
+#define XM_LINEAR_ROUND_TF32 1
+#define XM_LINEAR_FP32_ACCUM 2
 int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int round_out, int splits, float* workspace,
+                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
                       void* stream);
 /* dx (M,K) = dy (M,N) @ w (N,K) */
 int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
@@ -224,10 +228,15 @@ int xm_similarity_f32(const float* a, const float* b, float* S, int64_t Ml, int6
 int xm_infonce_tile_n(void);
 int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D,
                        float inv_tau, int64_t diag_off, float* workspace, void* stream);
-/* G (Ml, Ng) = coef * (exp(S - lse_row[i]) + exp(S - lse_col[j]) - 2*[j == i + diag_off]) */
+/* G (Ml, Ng) = coef * (exp(S - lse_row[i]) + exp(S - lse_col[j]) - 2*[j == i + diag_off]), full fp32 */
 int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
                         int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
                         void* stream);
+
+/* dx (Ml, D) = G @ f_n in the fp32-accurate 3-pass mode: g3 (Ml, 3*Ng) = xm_split3_f32(G, which, axis 1) and
+ * f3 (Ng, 3*D) = the xm_l2norm_split_fwd_f32 split of the unit vectors with the COMPLEMENTARY `which`
+ * (the rows of G sum to ~0, so this product cancels heavily: single-pass tf32 is not enough).  Ng % 4 == 0. */
+int xm_infonce_dgrad_f32(const float* g3, const float* f3, float* dx, int64_t Ml, int64_t Ng, int64_t D, void* stream);
 
 /* Fused all-gather + contraction over NVLink peer memory (data-parallel global negatives).  The second
  * operand is ROW-SHARDED: rank r holds rows [r*rows_per_peer, (r+1)*rows_per_peer) in its own buffer and

@@ -48,6 +48,7 @@ struct PeerMaps {
 
 struct GemmParams {
   OperandCfg a, b;
+  int b_rows_dim2; // MN-major B whose contraction rows run along tensor dimension 2 (TMA box {32, 1, 32})
   int n_peers;     // > 0: operand B lives in n_peers shards of peer_rows rows each (row coordinate = dim 1)
   int peer_rows;
   int bn;          // N of one MMA / one accumulator (multiple of 16, <= 256)
@@ -68,6 +69,10 @@ struct GemmParams {
   int stages;
   int tmem_cols;   // allocated TMEM columns (power of two)
   int acc_bufs;    // 1 or 2 accumulator sets of taps_n*bn columns (2: epilogue of tile i overlaps MMA of tile i+1)
+  int acc_chunk;   // > 0: the tensor core accumulates only acc_chunk k-blocks at a time; the epilogue warps add
+                   // the chunks in fp32 round-to-nearest into a third TMEM region (columns [2*bn, 3*bn)).  The
+                   // MMA's own accumulation truncates (a bias of ~3e-8 per K=8 step, i.e. 4e-4 over K = 120 000),
+                   // which the fp32-accurate 3-pass projections cannot afford.  Needs acc_bufs == 2, taps_n == 1.
   int nx, ny, nz;  // tile grid (persistent CTAs walk tile = by + ny*(bx + nx*bz))
   int dual;        // 1: two k-blocks per tile, (A, B) -> accumulator 0 and (A2, B2) -> accumulator 1 (EPI_ATTN_DS)
   OperandCfg a2, b2;
@@ -480,16 +485,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t b_tap16 = (uint32_t)(p.b_halo ? 128 : b_tile_bytes) >> 4;
       int s = 0;
       uint32_t ph = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      int ait = 0;  // accumulator-set uses so far (one per tile, or one per chunk of a tile with acc_chunk)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         const int total_kb = t.kout_n * taps_k_loop * p.kin_count;
-        const int buf = (p.acc_bufs == 2) ? (it & 1) : 0;
-        const uint32_t use = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it);
+        int buf = (p.acc_bufs == 2) ? (ait & 1) : 0;
+        uint32_t use = (uint32_t)(p.acc_bufs == 2 ? (ait >> 1) : ait);
+        ++ait;
         ptx::mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator set
         ptx::tc_fence_after_sync();
-        const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols);
+        uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols);
+        int kb0 = 0;  // first k-block of the running accumulation
         for (int kb = 0; kb < total_kb; ++kb) {
+          if (p.acc_chunk > 0 && kb - kb0 == p.acc_chunk) {  // hand this chunk over, continue in the other set
+            ptx::mma_commit(&tmem_full_bar[buf]);
+            buf = ait & 1;
+            use = (uint32_t)(ait >> 1);
+            ++ait;
+            ptx::mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);
+            ptx::tc_fence_after_sync();
+            acc = tmem_base + (uint32_t)(buf * acc_cols);
+            kb0 = kb;
+          }
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::tc_fence_after_sync();
           const uint64_t das = da0 + (uint64_t)((uint32_t)s * stage16);
@@ -528,7 +545,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8)
               ptx::mma_tf32_ss(acc_t, das + (uint64_t)(k8 * a_k16), dbt + (uint64_t)(k8 * b_k16), idesc,
-                               (kb > 0 || k8 > 0) ? 1u : 0u);
+                               (kb > kb0 || k8 > 0) ? 1u : 0u);
           }
           ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -560,14 +577,49 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     uint8_t* stg = staging + (warp - 2) * (NBUF * 4096);  // this warp's staging buffer(s)
     int chunk_ctr = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    int ait = 0;  // mirrors the MMA warp's accumulator-set counter
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t sum = tmem_base + (uint32_t)(2 * acc_cols) + lane_base;  // fp32 running sum (acc_chunk only)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      const int buf = (p.acc_bufs == 2) ? (it & 1) : 0;
-      const uint32_t use = (uint32_t)(p.acc_bufs == 2 ? (it >> 1) : it);
+      bool add_sum = false;
+      if (EPI == EPI_ROWMAJOR && p.acc_chunk > 0) {
+        // every chunk but the last: TMEM partial -> registers -> (+ running sum) -> TMEM sum region.  A warp only
+        // ever touches its own lane quadrant and its own 32-column groups, here and in the store loop below.
+        const int n_chunks = (t.kout_n * taps_k_loop * p.kin_count + p.acc_chunk - 1) / p.acc_chunk;
+        for (int c = 0; c + 1 < n_chunks; ++c) {
+          const int cbuf = ait & 1;
+          ptx::mbar_wait(&tmem_full_bar[cbuf], (uint32_t)(ait >> 1) & 1u);
+          ++ait;
+          ptx::tc_fence_after_sync();
+          const uint32_t src = tmem_base + (uint32_t)(cbuf * acc_cols) + lane_base;
+          for (int c0 = part * 32; c0 < p.bn; c0 += 32 * NPARTS) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(src + (uint32_t)c0, r);
+            if (c > 0) {
+              uint32_t u[32];
+              ptx::tmem_ld_32x32(sum + (uint32_t)c0, u);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(u[j]));
+            } else {
+              ptx::tmem_ld_wait();
+            }
+            ptx::tmem_st_32x32(sum + (uint32_t)c0, r);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[cbuf]);
+        }
+        add_sum = n_chunks > 1;
+      }
+      const int buf = (p.acc_bufs == 2) ? (ait & 1) : 0;
+      const uint32_t use = (uint32_t)(p.acc_bufs == 2 ? (ait >> 1) : ait);
+      ++ait;
       ptx::mbar_wait(&tmem_full_bar[buf], use & 1u);
       ptx::tc_fence_after_sync();
-      const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols) + ((uint32_t)(q * 32) << 16);
+      const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols) + lane_base;
       const int m = t.bx * 128 + row;  // row index inside this z-slab
       const bool row_ok = m < p.M;
       const int n0 = t.by * p.n_stride;
@@ -601,6 +653,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 16; ++j) { r[j] = h[j]; r[16 + j] = 0u; }
             }
             ptx::tmem_ld_wait();
+            if (EPI == EPI_ROWMAJOR && add_sum) {  // chunked accumulation: last partial + running sum
+              uint32_t u[32];
+              ptx::tmem_ld_32x32(sum + (uint32_t)c0, u);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(u[j]));
+            }
             // Straight-line code here is executed once per chunk by a single warp per scheduler, so its
             // SIZE matters (instruction fetch): every runtime switch is hoisted out of the element loop.
             float v[32];
@@ -641,7 +700,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float lcj = __shfl_sync(0xffffffffu, lc, j);
                 float g = __expf(v[j] - lse_r) + __expf(v[j] - lcj);
                 if (j == dj) g -= 2.0f;
-                v[j] = round_tf32(g * p.coef);  // rows / columns outside the matrix are clipped by the TMA store
+                v[j] = g * p.coef;  // full fp32 (split 3-way before the dgrad); out-of-matrix parts clipped by TMA
               }
             }
             uint8_t* sb = stg + (NBUF == 2 ? (chunk_ctr & 1) * 4096 : 0);
@@ -692,7 +751,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 } else {
                   float g = __expf(x - lse_r) + __expf(x - __ldg(p.lse_col + n));
                   if (n == m + p.diag_off) g -= 2.0f;
-                  x = round_tf32(g * p.coef);
+                  x = g * p.coef;
                 }
                 crow[j] = x;
               }
@@ -724,7 +783,7 @@ struct TensorView3 {
   unsigned long long stride_bytes[2];  // strides of dim[1], dim[2]
 };
 
-int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major);
+int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major, unsigned box2 = 1);
 // `tc` describes the output for the TMA-store epilogue (dims {N, M, Z}); pass ptr == nullptr to use
 // the direct-store path (p.c / p.ldc).  `grid` is the TILE grid; the launch is persistent.
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,

@@ -31,7 +31,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major) {
+int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned box1, int mn_major, unsigned box2) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return XM_ERR_NO_DRIVER;
   // The driver entry point needs a current context on THIS thread.  The runtime binds the primary
@@ -46,7 +46,7 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
   if ((t.stride_bytes[0] & 15) != 0 || (t.stride_bytes[1] & 15) != 0) return XM_ERR_INVALID;
   cuuint64_t dims[3] = {t.dim[0], t.dim[1], t.dim[2]};
   cuuint64_t strides[2] = {t.stride_bytes[0], t.stride_bytes[1]};
-  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(t.ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -136,6 +136,14 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   const int acc_cols = p.taps_n * p.bn;
   p.acc_bufs = (2 * acc_cols <= 512 && ntiles > 1 && !p.dual) ? 2 : 1;
   p.tmem_cols = tmem_cols_for(p.dual ? 2 * acc_cols : p.acc_bufs * acc_cols);
+  // chunked fp32 accumulation: plain row-major tiles stored by TMA, two accumulator sets + the sum region
+  if (p.acc_chunk > 0 && (epi != EPI_ROWMAJOR || !p.tma_store || p.taps_n != 1 || p.dual || p.a_halo || p.b_halo ||
+                          (p.bn & 31) || 3 * p.bn > 512 || total_kb <= p.acc_chunk))
+    p.acc_chunk = 0;
+  if (p.acc_chunk > 0) {
+    p.acc_bufs = 2;
+    p.tmem_cols = tmem_cols_for(3 * p.bn);
+  }
   if ((epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) && (!p.tma_store || (p.bn & 127))) return XM_ERR_UNSUPPORTED;
   p.a.rows = 128;
   p.b.rows = p.bn;
@@ -155,7 +163,12 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   }
   int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : (unsigned)(128 + p.a_halo), p.a.mn_major);
   if (rc != XM_OK) return rc;
-  rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? (unsigned)(32 + p.b_halo) : (unsigned)p.bn, p.b.mn_major);
+  if (p.b_rows_dim2) {  // MN-major B whose contraction rows run along tensor dimension 2: box {32, 1, 32}
+    if (!p.b.mn_major || p.b_halo) return XM_ERR_INVALID;
+    rc = encode_tmap(&mb, tb, 32, 1, 1, 32);
+  } else {
+    rc = encode_tmap(&mb, tb, 32, p.b.mn_major ? (unsigned)(32 + p.b_halo) : (unsigned)p.bn, p.b.mn_major);
+  }
   if (rc != XM_OK) return rc;
   if (p.tma_store) {
     rc = encode_tmap(&mc, tc, 32, 32, 0);
@@ -496,8 +509,10 @@ const char* xm_strerror(int code) {
 }
 
 int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int round_out, int splits, float* workspace,
+                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
                       void* stream) {
+  const int round_out = (flags & XM_LINEAR_ROUND_TF32) ? 1 : 0;
+  const bool fp32_accum = (flags & XM_LINEAR_FP32_ACCUM) != 0;
   if (!x || !w || !y || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
   if ((ldx & 3) || (ldw & 3)) return XM_ERR_INVALID;
   if (splits < 1) splits = 1;
@@ -524,6 +539,12 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
   // the GEMM epilogue fuses bias + {none, relu, gelu}; tanh / sigmoid run as a second (in-place) pass
   const bool late_act = (act == XM_ACT_TANH || act == XM_ACT_SIGMOID);
   if (late_act && ldy != N) return XM_ERR_UNSUPPORTED;
+  if (fp32_accum) {  // 8 k-blocks = 32 tensor-core accumulation steps per chunk: truncation bias < 1e-6
+    p.acc_chunk = 8;
+    if (p.bn > 128) p.bn = 128;  // three accumulator-sized TMEM regions must fit 512 columns
+    if (p.bn & 31) p.bn = (p.bn + 31) & ~31;
+    p.b.sy[1] = p.bn;
+  }
   if (splits == 1) {
     p.c = y;
     p.ldc = ldy;
@@ -827,6 +848,42 @@ int xm_similarity_f32(const float* a, const float* b, float* S, int64_t Ml, int6
 }
 
 int xm_infonce_tile_n(void) { return 128; }
+
+// dx (Ml, D) = G (Ml, Ng) @ f_n (Ng, D) with both operands 3-way tf32 split (fp32-accurate):
+//   g3 (Ml, 3*Ng) = [G_a | G_b | G_c] (split3 of G along its columns), f3 (Ng, 3*D) = [F_a | F_b | F_c] (the
+//   l2norm split of the unit vectors): dx = G_a F_a + G_b F_b + G_c F_c -- one GEMM whose contraction walks
+//   the three (column block of g3, column block of f3) pairs: kout = block, kin = 32-row steps inside it.
+// The rows of G sum to ~0 (softmax minus one-hot), so G @ f_n cancels against the common component of the
+// embeddings: single-pass tf32 left percent-level errors in every encoder gradient at batch 2048+.
+int xm_infonce_dgrad_f32(const float* g3, const float* f3, float* dx, int64_t Ml, int64_t Ng, int64_t D, void* stream) {
+  if (!g3 || !f3 || !dx || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3) || (Ng & 3)) return XM_ERR_INVALID;
+  const int m_tiles = ceil_div(Ml, 128);
+  GemmParams p;
+  zero_params(p);
+  p.bn = choose_bn(D, m_tiles, 32);
+  p.kin_count = ceil_div(Ng, 32);
+  p.kout_count = 3;
+  p.kout_total = 3;
+  p.a.mn_major = 0;  // g3: contraction (columns) contiguous
+  p.a.sx[1] = 128;
+  p.a.kin_step[0] = 32;
+  p.a.kout_step[0] = (int)Ng;
+  p.b.mn_major = 1;  // f3 viewed as (D, 3 blocks, Ng rows): output index D contiguous, rows along dimension 2
+  p.b.sy[0] = p.bn;
+  p.b.kin_step[2] = 32;
+  p.b.kout_step[1] = 1;
+  p.b_rows_dim2 = 1;
+  p.acc_chunk = 8;  // the contraction runs over 3x the GLOBAL batch: keep the accumulation fp32-accurate
+  if (p.bn > 128) p.bn = 128, p.b.sy[0] = 128;
+  p.M = (int)Ml;
+  p.N = (int)D;
+  p.c = dx;
+  p.ldc = D;
+  TensorView3 ta{g3, {(unsigned long long)(3 * Ng), (unsigned long long)Ml, 1}, {(unsigned long long)(3 * Ng) * 4, (unsigned long long)(Ml * 3 * Ng) * 4}};
+  TensorView3 tb{f3, {(unsigned long long)D, 3, (unsigned long long)Ng}, {(unsigned long long)D * 4, (unsigned long long)(3 * D) * 4}};
+  const TensorView3 tc{dx, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)(Ml * D) * 4}};
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(D, p.bn), 1), (cudaStream_t)stream);
+}
 
 static int infonce_lse_impl(const float* a, const float* b, const void* const* b_peers, int n_peers, int64_t peer_rows,
                             float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off,

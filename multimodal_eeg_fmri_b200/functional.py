@@ -584,18 +584,20 @@ class SymmetricInfoNCE(torch.autograd.Function):
         lse_ef_all = _AllGatherRows.gather(lse_ef)
         lse_fe_all = _AllGatherRows.gather(lse_fe)
         coef = 0.5 * inv_tau / Bg
+        # G (softmax minus one-hot) has rows summing to ~0, so G @ f_n cancels against the common component of
+        # the embeddings: both products run in the fp32-accurate 3-pass mode (G stays fp32, split on the fly).
         if ctx.peers is not None:
             e_ptrs, f_ptrs, Bl = ctx.peers
             G1 = ops.infonce_grad_peers(e3, f_ptrs, Bl, lse_ef, lse_fe_all, inv_tau, off, coef)  # rows: my e, cols: all f
-            den = ops.linear_dgrad_peers(G1, f_ptrs, Bl, D, 3 * D)                                  # hi part = tf32(f_n)
             G2 = ops.infonce_grad_peers(f3, e_ptrs, Bl, lse_fe, lse_ef_all, inv_tau, off, coef)  # rows: my f, cols: all e
-            dfn = ops.linear_dgrad_peers(G2, e_ptrs, Bl, D, 3 * D)
+            f3_all = ops.peer_gather(f_ptrs, Bl, 3 * D, en.device)  # small here (Bl <= 512): local copy for the dgrad
+            e3_all = ops.peer_gather(e_ptrs, Bl, 3 * D, en.device)
         else:
             e3_all, f3_all = sv[8], sv[9]
             G1 = ops.infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, off, coef)
-            den = ops.linear_dgrad(G1, f3_all[:, :D])
             G2 = ops.infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, off, coef)
-            dfn = ops.linear_dgrad(G2, e3_all[:, :D])
+        den = ops.infonce_dgrad(G1, f3_all, 1)  # f3 = [hi | hi | lo]
+        dfn = ops.infonce_dgrad(G2, e3_all, 0)  # e3 = [hi | lo | hi]
         de = ops.l2norm_bwd(den, en, einv) * g
         df = ops.l2norm_bwd(dfn, fn, finv) * g
         return de, df, None

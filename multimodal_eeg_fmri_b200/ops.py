@@ -142,7 +142,7 @@ def to_nwc(x: torch.Tensor, round_out: bool = False) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ linear
-def linear_fwd(x, w, bias=None, act=None, round_out=False, splits: int = 0):
+def linear_fwd(x, w, bias=None, act=None, round_out=False, splits: int = 0, fp32_accum=False):
     _chk(x, w, bias)
     x, w = _rowmajor(x), _rowmajor(w)
     M, K = x.shape
@@ -155,7 +155,7 @@ def linear_fwd(x, w, bias=None, act=None, round_out=False, splits: int = 0):
     ws = torch.empty(splits * M * N, device=x.device, dtype=torch.float32) if splits > 1 else None
     _w(2.0 * M * N * K, 4.0 * (M * K + N * K + M * N))
     _call("xm_linear_fwd_f32", _p(x), _p(w), _p(bias), _p(y), M, N, K, x.stride(0), w.stride(0), y.stride(0),
-          act_code(act), int(round_out), splits, _p(ws), _stream())
+          act_code(act), int(round_out) | (2 if fp32_accum else 0), splits, _p(ws), _stream())
     return y
 
 
@@ -422,7 +422,7 @@ def split3(x, which, axis):
 
 def linear_fwd_precise(x, w, bias=None, act=None):
     """fp32-accurate y = x @ w^T + b: three tf32 passes fused into one GEMM over a tripled K."""
-    return linear_fwd(split3(x, 0, 1), split3(w, 1, 1), bias, act=act)
+    return linear_fwd(split3(x, 0, 1), split3(w, 1, 1), bias, act=act, fp32_accum=True)
 
 
 def linear_dgrad_precise(dy, w):
@@ -705,6 +705,25 @@ def resid_seqmean_bwd(dout, T, drop_p=0.0, seed=0, need_dx=True, need_da=True):
     _w(2.0 * B * T * D, 4.0 * B * T * D * (need_dx + need_da))
     _call("xm_resid_seqmean_bwd_f32", _p(dout), B, T, D, _p(dx), _p(da), float(drop_p), int(seed), _stream())
     return dx, da
+
+
+def infonce_dgrad(G, f3, which_f):
+    """dx = G @ f_n, fp32-accurate: G (Ml, Ng) fp32 is split 3-way complementary to f3 (Ng, 3D), the l2norm split
+    of the unit vectors made with `which_f`."""
+    _chk(G, f3)
+    Ml, Ng = G.shape
+    D = f3.shape[1] // 3
+    if Ng % 4:  # TMA row pitch: pad the contraction with zero columns / rows
+        pad = 4 - Ng % 4
+        G = torch.nn.functional.pad(G, (0, pad))
+        f3 = torch.nn.functional.pad(f3, (0, 0, 0, pad))
+        Ng += pad
+    g3 = split3(G, 1 - which_f, 1)
+    f3 = f3.contiguous()
+    dx = torch.empty(Ml, D, device=G.device, dtype=torch.float32)
+    _w(6.0 * Ml * Ng * D, 4.0 * (3 * Ml * Ng + 3 * Ng * D + Ml * D))
+    _call("xm_infonce_dgrad_f32", _p(g3), _p(f3), _p(dx), Ml, Ng, D, _stream())
+    return dx
 
 
 # ------------------------------------------------------------------ preprocessing

@@ -18,6 +18,16 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+# Optional operand-rounding model, `fn(key_prefix, tensor) -> tensor`, applied to the operands of every
+# matmul/conv below.  None (the default, and what every parity test uses) is the reference's plain
+# arithmetic.  tools/full_scale_parity.py sets it to round-to-nearest tf32 on the EEG encoder to measure the
+# error floor ANY single-pass tf32 implementation of that encoder has (it is not part of the oracle proper).
+OPERAND_ROUNDING = None
+
+
+def _r(pre: str, t):
+    return t if OPERAND_ROUNDING is None else OPERAND_ROUNDING(pre, t)
+
 
 def _bn(P: SD, pre: str, x, train: bool, eps: float = 1e-5):
     # nn.BatchNorm1d: batch statistics in train mode, running statistics in eval mode
@@ -27,12 +37,12 @@ def _bn(P: SD, pre: str, x, train: bool, eps: float = 1e-5):
 
 
 def _lin(P: SD, pre: str, x):
-    return F.linear(x, P[pre + "weight"], P.get(pre + "bias"))
+    return F.linear(_r(pre, x), _r(pre, P[pre + "weight"]), P.get(pre + "bias"))
 
 
 def _conv(P: SD, pre: str, x):
     w = P[pre + "weight"]
-    return F.conv1d(x, w, P.get(pre + "bias"), padding=w.shape[-1] // 2)
+    return F.conv1d(_r(pre, x), _r(pre, w), P.get(pre + "bias"), padding=w.shape[-1] // 2)
 
 
 def _ln(P: SD, pre: str, x, eps: float = 1e-5):
@@ -55,7 +65,8 @@ def multihead_attention(P: SD, pre: str, q, k, v, nhead: int, need_weights: bool
     bridge_utils.py:48,80-82: packed in_proj, scaled dot-product per head, out_proj; the returned
     weights are averaged over heads (need_weights default)."""
     d = q.shape[-1]
-    W, b = P[pre + "in_proj_weight"], P[pre + "in_proj_bias"]
+    W, b = _r(pre, P[pre + "in_proj_weight"]), P[pre + "in_proj_bias"]
+    q, k, v = _r(pre, q), _r(pre, k), _r(pre, v)
     qp = F.linear(q, W[:d], b[:d])
     kp = F.linear(k, W[d:2 * d], b[d:2 * d])
     vp = F.linear(v, W[2 * d:], b[2 * d:])
@@ -65,9 +76,9 @@ def multihead_attention(P: SD, pre: str, q, k, v, nhead: int, need_weights: bool
     qh = qp.view(B, Lq, nhead, dh).transpose(1, 2)
     kh = kp.view(B, Lk, nhead, dh).transpose(1, 2)
     vh = vp.view(B, Lk, nhead, dh).transpose(1, 2)
-    att = torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(dh), dim=-1)
-    out = (att @ vh).transpose(1, 2).reshape(B, Lq, d)
-    out = F.linear(out, P[pre + "out_proj.weight"], P[pre + "out_proj.bias"])
+    att = torch.softmax(_r(pre, qh) @ _r(pre, kh).transpose(-1, -2) / math.sqrt(dh), dim=-1)
+    out = (_r(pre, att) @ _r(pre, vh)).transpose(1, 2).reshape(B, Lq, d)
+    out = F.linear(_r(pre, out), _r(pre, P[pre + "out_proj.weight"]), P[pre + "out_proj.bias"])
     return (out, att.mean(1)) if need_weights else (out, None)
 
 

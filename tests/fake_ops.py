@@ -228,6 +228,11 @@ def l2norm_split_fwd(x, which, eps=1e-12):
     return xn, torch.cat([xn, z, z], 1), inv
 
 
+def infonce_dgrad(G, f3, which_f):
+    D = f3.shape[1] // 3
+    return (G.double() @ f3[:, :D].double()).float()  # the fake split keeps the full value in block 0
+
+
 def l2norm_bwd(dxn, xn, inv):
     d, x = dxn.double(), xn.double()
     return ((d - x * (x * d).sum(1, keepdim=True)) * inv.double()[:, None]).float()

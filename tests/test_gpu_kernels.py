@@ -67,6 +67,41 @@ def test_linear_wgrad(ops, M, N, K, splits):
     assert_close_rel(db, dy.double().sum(0), FP32, "bias grad")
 
 
+@pytest.mark.parametrize("M,N,K,act", [(300, 96, 200, "relu"), (2048, 128, 40000, None), (130, 64, 4000, None),
+                                       (256, 16, 1000, None), (64, 256, 3000, "gelu")])
+def test_linear_precise_is_fp32_accurate(ops, M, N, K, act):
+    """3-pass tf32 + chunked fp32 accumulation: the projections whose outputs feed ReLU masks / BatchNorm
+    statistics must be fp32-accurate at any K (a one-sided error of 4e-5 flips ~20 ReLU masks of the 40 000-d
+    connectivity layer at batch 2048 and shows up as a 1e-2 error of that layer's gradients)."""
+    torch.manual_seed(5)
+    x = torch.randn(M, K, device="cuda") + 0.3  # a common component: the accumulators keep their sign
+    w = torch.randn(N, K, device="cuda") / K ** 0.5 + 0.2 / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    y = ops.linear_fwd_precise(x, w, b, act=act)
+    ref = x.double() @ w.double().t() + b.double()
+    ref = F.gelu(ref) if act == "gelu" else torch.relu(ref) if act == "relu" else ref
+    assert_close_rel(y, ref, 3e-6, "linear_fwd_precise")
+    dy = torch.randn(M, N, device="cuda")
+    assert_close_rel(ops.linear_dgrad_precise(dy, w), dy.double() @ w.double(), 3e-6, "linear_dgrad_precise")
+    dw, db = ops.linear_wgrad_precise(dy, x)
+    assert_close_rel(dw, dy.double().t() @ x.double(), 3e-5, "linear_wgrad_precise")
+    assert_close_rel(db, dy.double().sum(0), FP32, "bias grad")
+
+
+@pytest.mark.parametrize("Ml,Ng,D", [(256, 256, 128), (512, 4096, 128), (100, 36, 64), (1, 1, 128), (130, 8200, 32)])
+def test_infonce_dgrad_is_fp32_accurate(ops, Ml, Ng, D):
+    """dx = G @ f_n with G = softmax - onehot (rows sum to ~0, so the product cancels against the common
+    component of the unit vectors)."""
+    torch.manual_seed(6)
+    f = F.normalize(torch.randn(Ng, D, device="cuda") + 0.7, dim=1)
+    G = torch.softmax(torch.randn(Ml, Ng, device="cuda") * 3, dim=1)
+    G[torch.arange(Ml), torch.arange(Ml) % Ng] -= 1.0
+    for which in (0, 1):
+        fn, f3, _ = ops.l2norm_split_fwd(f, which)
+        dx = ops.infonce_dgrad(G, f3, which)
+        assert_close_rel(dx, G.double() @ fn.double(), 5e-6, "infonce_dgrad", atol=1e-7)
+
+
 # ------------------------------------------------------------------ conv1d
 CONV_CASES = [(1, 32, 32, 128, 1), (2, 32, 32, 128, 3), (3, 64, 64, 500, 7), (2, 64, 128, 500, 5), (2, 128, 128, 250, 3),
               (2, 48, 96, 250, 5), (2, 18, 48, 500, 7), (1, 192, 128, 100, 1), (2, 8, 16, 64, 7), (5, 64, 64, 37, 5)]
