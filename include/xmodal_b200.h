@@ -272,6 +272,18 @@ int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, con
                     int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, int round_out,
                     void* stream);
 
+/* Fused variant (the product path): the L x L probability / score-gradient matrices stay in tensor memory -- the
+ * forward keeps only out and lse (B*H, L); the backward regenerates the probabilities from q, k and lse and needs
+ * the forward's `out` (delta = dO . O) plus a (B*H, L) float workspace `delta`.  Same layouts and limits as above;
+ * the dropout mask is a different pure function of (seed, slab, query, key), exported by xm_attn_fused_mask_u8
+ * (mask (B*H, L, L), 1 = kept) so tests can replay it. */
+int xm_attn_fused_fwd_f32(const float* qkv, float* out, float* lse, int64_t B, int64_t L, int64_t H, int64_t dh, float scale,
+                          float drop_p, uint64_t seed, int round_out, void* stream);
+int xm_attn_fused_bwd_f32(const float* dout, const float* qkv, const float* out, const float* lse, float* dqkv, float* delta,
+                          int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed,
+                          int round_out, void* stream);
+int xm_attn_fused_mask_u8(uint8_t* mask, int64_t B, int64_t L, int64_t H, float drop_p, uint64_t seed, void* stream);
+
 /* ------------------------------------------------------------------ residual stream of the pre-norm transformer block
  * EEG_CODE/enhanced_models_v4.py:89-107 (x + Dropout(branch), LayerNorm) and :44-55 (x + pe, Dropout), fused:
  *   s = x + Dropout(a)            [a may be NULL]      or      s = Dropout(x + pe[row % L])   [pe may be NULL]

@@ -327,23 +327,23 @@ def linear_ln_act(x, lin, ln, act="gelu", drop_p=0.0, training=True):
 class SelfAttentionCore(torch.autograd.Function):
     """softmax(q k^T / sqrt(dh)) -> Dropout -> @ v per (sample, head), on the packed in_proj output
     qkv (B, L, 3d) (nn.MultiheadAttention inside TemporalTransformerBlock, enhanced_models_v4.py:71-73,98).
-    Scores never reach HBM: the softmax (and the whole dS formula in the backward) runs in the epilogue of
-    the score GEMM; the dropped probabilities are the only saved (B*H, L, L) tensor."""
+    Neither scores nor probabilities reach HBM (csrc/attention_fused.cu): only the output and the row
+    logsumexp are saved; the backward regenerates the probabilities (and the dropout mask) on chip."""
 
     @staticmethod
     def forward(ctx, qkv, nhead, p, seed):
         dh = qkv.shape[2] // 3 // nhead
         scale = 1.0 / (dh ** 0.5)
-        out, probs, lse = ops.attn_fwd(qkv, nhead, scale, p, seed)
-        ctx.save_for_backward(qkv, probs, lse)
+        out, lse = ops.attn_fused_fwd(qkv, nhead, scale, p, seed)
+        ctx.save_for_backward(qkv, out, lse)
         ctx.meta = (nhead, scale, p, seed)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, probs, lse = ctx.saved_tensors
+        qkv, out, lse = ctx.saved_tensors
         nhead, scale, p, seed = ctx.meta
-        return ops.attn_bwd(_tf32(dout.contiguous()), qkv, probs, lse, nhead, scale, p, seed), None, None, None
+        return ops.attn_fused_bwd(_tf32(dout.contiguous()), qkv, out, lse, nhead, scale, p, seed), None, None, None
 
 
 def self_attention_core(qkv, nhead, drop_p=0.0, training=True):
@@ -392,7 +392,7 @@ class TransformerTail(torch.autograd.Function):
             wqkv_r, wo_r, w1_r, w2_r = (ops.round_tf32(w) for w in (wqkv, wo, w1, w2))
             qkv = ops.linear_fwd(h1, wqkv_r, bqkv, round_out=True)
             s_attn = seed()
-            att, probs, lse = ops.attn_fwd(qkv.view(B, L, 3 * D), nhead, scale, p, s_attn, round_out=True)
+            att, lse = ops.attn_fused_fwd(qkv.view(B, L, 3 * D), nhead, scale, p, s_attn, round_out=True)
             ao = ops.linear_fwd(att.view(M, D), wo_r, bo)
             s_ao = seed()
             x2, h2, m2, r2 = ops.resid_ln_fwd(x1, ao, n2w, n2b, eps, p, s_ao)
@@ -401,7 +401,7 @@ class TransformerTail(torch.autograd.Function):
             s_g = seed()
             g = ops.act_fwd(f1, act, p, s_g, round_out=True)
             f2 = ops.linear_fwd(g, w2_r, b2)
-            saved += [x1, h1, m1, r1, qkv, probs, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w]
+            saved += [x1, h1, m1, r1, qkv, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w]
             meta.append((s_attn, s_ao, s_g, pend_seed if l > 0 else seed_pe))
             x, pend, pend_seed = x2, f2, seed()
         out = ops.resid_seqmean_fwd(x.view(B, L, D), pend.view(B, L, D), p, pend_seed)
@@ -420,7 +420,7 @@ class TransformerTail(torch.autograd.Function):
         grads = [None] * (nl * 12)
         dh0 = None
         for l in reversed(range(nl)):
-            (x1, h1, m1, r1, qkv, probs, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w) = sv[l * 20:(l + 1) * 20]
+            (x1, h1, m1, r1, qkv, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w) = sv[l * 19:(l + 1) * 19]
             s_attn, s_ao, s_g, s_in = meta[l]
             dg = ops.linear_dgrad(df2, w2_r)
             dw2, _ = ops.linear_wgrad(df2, g, need_bias=False)
@@ -433,7 +433,8 @@ class TransformerTail(torch.autograd.Function):
             dx1, dao, dn2w, dn2b, dbo = ops.resid_ln_bwd(dh2, dxs, x2, n2w, m2, r2, p, s_ao)
             datt = ops.linear_dgrad(dao, wo_r, round_out=True)
             dwo, _ = ops.linear_wgrad(dao, att.view(M, D), need_bias=False)
-            dqkv = ops.attn_bwd(datt.view(B, L, D), qkv.view(B, L, 3 * D), probs, lse, nhead, scale, p, s_attn, round_out=True)
+            dqkv = ops.attn_fused_bwd(datt.view(B, L, D), qkv.view(B, L, 3 * D), att.view(B, L, D), lse, nhead, scale, p, s_attn,
+                                      round_out=True)
             dqkv = dqkv.view(M, 3 * D)
             dh1 = ops.linear_dgrad(dqkv, wqkv_r)
             dwqkv, dbqkv = ops.linear_wgrad(dqkv, h1)

@@ -644,6 +644,41 @@ def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=
     return dqkv
 
 
+def attn_fused_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
+    """Fused attention core: qkv (B, L, 3*H*dh) -> (out (B, L, H*dh), lse (B*H, L)); probabilities stay on chip."""
+    _chk(qkv)
+    qkv = qkv.contiguous()
+    B, L, E = qkv.shape
+    d = E // 3
+    dh = d // nhead
+    out = torch.empty(B, L, d, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * nhead, L, device=qkv.device, dtype=torch.float32)
+    _w(4.0 * B * nhead * L * L * dh, 4.0 * (qkv.numel() + out.numel()))
+    _call("xm_attn_fused_fwd_f32", _p(qkv), _p(out), _p(lse), B, L, nhead, dh, float(scale), float(drop_p), int(seed),
+          int(round_out), _stream())
+    return out, lse
+
+
+def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
+    _chk(dout, qkv, out, lse)
+    dout, out = dout.contiguous(), out.contiguous()
+    B, L, E = qkv.shape
+    dh = E // 3 // nhead
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    _w(14.0 * B * nhead * L * L * dh, 4.0 * (3 * qkv.numel() + 3 * dout.numel()))
+    _call("xm_attn_fused_bwd_f32", _p(dout), _p(qkv), _p(out), _p(lse), _p(dqkv), _p(delta), B, L, nhead, dh, float(scale),
+          float(drop_p), int(seed), int(round_out), _stream())
+    return dqkv
+
+
+def attn_fused_mask(B, L, nhead, drop_p, seed, device="cuda"):
+    """The keep mask (B*H, L, L) the fused attention kernels generate for (drop_p, seed)."""
+    mask = torch.empty(B * nhead, L, L, device=device, dtype=torch.uint8)
+    _call("xm_attn_fused_mask_u8", _p(mask), B, L, nhead, float(drop_p), int(seed), _stream())
+    return mask
+
+
 # ------------------------------------------------------------------ residual stream (transformer block)
 def resid_ln_supported(D: int) -> bool:
     return D % 128 == 0 and 128 <= D <= 512

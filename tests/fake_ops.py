@@ -293,6 +293,19 @@ def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=
     return torch.cat([back(dq), back(dk), back(dv)], dim=-1).float()
 
 
+def attn_fused_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
+    out, _, lse = attn_fwd(qkv, nhead, scale, drop_p, seed, round_out)
+    return out, lse
+
+
+def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
+    _nodrop(drop_p)
+    B, L, E = qkv.shape
+    q, k, _ = _attn_parts(qkv, nhead)
+    probs = torch.exp(q @ k.transpose(-1, -2) * scale - lse.reshape(B, nhead, L, 1).double())
+    return attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
+
+
 # ---------------------------------------------------------------- residual stream (transformer block)
 def resid_ln_supported(D):
     return D % 128 == 0 and 128 <= D <= 512

@@ -380,6 +380,67 @@ def test_attention_core_dropout_consistency(ops):
     assert_close_rel(dqkv, gx, 3e-3, "dqkv with dropout")
 
 
+def _attn_ref(qkv, B, L, H, dh, scale, mask=None):
+    x = qkv.double().requires_grad_(True)
+    q, k, v = (t.reshape(B, L, H, dh).transpose(1, 2) for t in x.chunk(3, dim=-1))
+    s = q @ k.transpose(-1, -2) * scale
+    p = torch.softmax(s, dim=-1)
+    if mask is not None:
+        p = p * mask
+    return x, s, (p @ v).transpose(1, 2).reshape(B, L, H * dh)
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 250, 4), (3, 128, 2), (1, 37, 1), (5, 256, 4), (2, 129, 3), (40, 250, 4), (1, 1, 1),
+                                   (2, 8, 2)])
+def test_fused_attention_fwd_bwd(ops, B, L, H):
+    """The on-chip (flash-style) attention core against fp64 torch, dropout off: out, lse, dqkv."""
+    torch.manual_seed(14)
+    dh = 32
+    d = H * dh
+    qkv = ops.round_tf32(torch.randn(B, L, 3 * d, device="cuda"))
+    dout = ops.round_tf32(torch.randn(B, L, d, device="cuda"))
+    scale = dh ** -0.5
+    out, lse = ops.attn_fused_fwd(qkv, H, scale, 0.0, 0, round_out=False)
+    x, s, ref = _attn_ref(qkv, B, L, H, dh, scale)
+    assert_close_rel(out, ref, TF32, "fused attention out")
+    assert float((lse.double() - torch.logsumexp(s, -1).reshape(B * H, L)).abs().max()) < 2e-3
+    (gx,) = torch.autograd.grad(ref, x, dout.double())
+    dqkv = ops.attn_fused_bwd(dout, qkv, out, lse, H, scale, 0.0, 0)
+    for name, a, b in zip("qkv", dqkv.chunk(3, dim=-1), gx.chunk(3, dim=-1)):
+        assert_close_rel(a, b, 2e-3, f"fused d{name}", atol=1e-6)
+
+
+@pytest.mark.parametrize("B,L,H,pdrop", [(2, 250, 4, 0.3), (3, 100, 2, 0.1), (2, 256, 1, 0.5)])
+def test_fused_attention_dropout(ops, B, L, H, pdrop):
+    """Dropout on the attention weights: the exported mask has the right keep rate and no row / column structure,
+    forward and both backward kernels regenerate exactly that mask (checked against autograd with it)."""
+    torch.manual_seed(15)
+    dh, seed = 32, 777
+    d = H * dh
+    qkv = ops.round_tf32(torch.randn(B, L, 3 * d, device="cuda") * 0.5)
+    dout = ops.round_tf32(torch.randn(B, L, d, device="cuda"))
+    scale = dh ** -0.5
+    keep = ops.attn_fused_mask(B, L, H, pdrop, seed).bool()
+    tol = 4 * (pdrop * (1 - pdrop) / keep.numel()) ** 0.5 + 1e-4
+    assert abs(float(keep.float().mean()) - (1 - pdrop)) < tol
+    # keep rates per query row and per key column scatter like a binomial (no structure along either index)
+    sd = (pdrop * (1 - pdrop) / L) ** 0.5
+    assert float((keep.float().mean(2) - (1 - pdrop)).abs().max()) < 6 * sd
+    assert float((keep.float().mean(1) - (1 - pdrop)).abs().max()) < 6 * sd
+    assert not torch.equal(keep, ops.attn_fused_mask(B, L, H, pdrop, seed + 1).bool())
+    mask = keep.reshape(B, H, L, L).double() / (1 - pdrop)
+    out, lse = ops.attn_fused_fwd(qkv, H, scale, pdrop, seed, round_out=False)
+    out2, _ = ops.attn_fused_fwd(qkv, H, scale, pdrop, seed, round_out=False)
+    assert torch.equal(out, out2)
+    x, s, ref = _attn_ref(qkv, B, L, H, dh, scale, mask)
+    assert_close_rel(out, ref, TF32, "fused attention out with dropout")
+    assert float((lse.double() - torch.logsumexp(s, -1).reshape(B * H, L)).abs().max()) < 2e-3
+    (gx,) = torch.autograd.grad(ref, x, dout.double())
+    dqkv = ops.attn_fused_bwd(dout, qkv, out, lse, H, scale, pdrop, seed)
+    for name, a, b in zip("qkv", dqkv.chunk(3, dim=-1), gx.chunk(3, dim=-1)):
+        assert_close_rel(a, b, 3e-3, f"fused d{name} with dropout")
+
+
 # ------------------------------------------------------------------ out-of-bounds canaries
 def test_ragged_outputs_do_not_write_past_their_extent(ops):
     """compute-sanitizer is closed on this pool, so ragged shapes are checked with canaries: outputs are
