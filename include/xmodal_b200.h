@@ -283,6 +283,9 @@ int xm_attn_fused_bwd_f32(const float* dout, const float* qkv, const float* out,
                           int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed,
                           int round_out, void* stream);
 int xm_attn_fused_mask_u8(uint8_t* mask, int64_t B, int64_t L, int64_t H, float drop_p, uint64_t seed, void* stream);
+/* Debug: when non-NULL, CTA 0 of the fused attention kernels appends clock64() stamps at its phase boundaries
+ * (3 roles x 4096 slots of int64). */
+int xm_debug_set_attn_trace(int64_t* device_buffer);
 
 /* ------------------------------------------------------------------ residual stream of the pre-norm transformer block
  * EEG_CODE/enhanced_models_v4.py:89-107 (x + Dropout(branch), LayerNorm) and :44-55 (x + pe, Dropout), fused:

@@ -43,24 +43,32 @@ XM_DEVICE void mbar_arrive(uint64_t* bar) {
 }
 XM_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the hardware park the thread until the phase completes (or the hint expires)
+  // instead of returning at once: a waiting warp then costs no issue slots of its scheduler
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must surface as a trapped launch (sticky CUDA error the host
-// reports), never as a hung GPU.  ~4e9 cycles is > 2 s at any B200 clock.
+// reports), never as a hung GPU.  ~4e9 cycles is > 2 s at any B200 clock.  The clock is only read every 64
+// failed polls: the clock read shares the transcendental (XU) pipe with the epilogues' exp2.
 XM_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if ((++polls & 63u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ll) __trap();
+    }
   }
 }
 
