@@ -53,10 +53,34 @@ class PairedBridgeModel(nn.Module):
         ps = [p for m in mods for p in m.parameters()]
         return ps + [self.fmri_net.activation_weight, self.fmri_net.connectivity_weight]
 
-    def embed(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: torch.Tensor, eeg_channels_last: bool = False):
-        eeg_feat = self.eeg_encoder(eeg, channels_last=eeg_channels_last)
+    # The fMRI branch is ~150 small launches (ROI aggregation, two MLP encoders in the 3-pass mode, fusion) that
+    # do not depend on the EEG encoder: on a side stream they fill the tails of the encoder's big kernels, in the
+    # forward and -- autograd replays every node on the stream of its forward -- in the backward.  Measured on
+    # B200: 36.17 -> 35.40 ms per step on 1 GPU, 37.85 -> 37.37 on 2 (SyncBN collectives issued from both streams
+    # keep their order; tests/dp_gpu_check.py passes).  Opt-in (XM_OVERLAP_BRANCHES=1): the gain is 1-2 % and
+    # the per-kernel CUDA-event rates that bench.py reports stop being those of a kernel running alone.
+    overlap_branches = os.environ.get("XM_OVERLAP_BRANCHES", "0") == "1"
+
+    def _fmri_features(self, roi_series, conn):
         act = fmri_utils.aggregate_roi_timeseries(roi_series, "both")
-        fmri_feat = self.fmri_net.features(act, conn)
+        return self.fmri_net.features(act, conn)
+
+    def embed(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: torch.Tensor, eeg_channels_last: bool = False):
+        if not (self.overlap_branches and eeg.is_cuda):
+            eeg_feat = self.eeg_encoder(eeg, channels_last=eeg_channels_last)
+            return self.bridge.project(eeg_feat, self._fmri_features(roi_series, conn))
+        cur = torch.cuda.current_stream(eeg.device)
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != eeg.device:
+            side = self._side_stream = torch.cuda.Stream(eeg.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fmri_feat = self._fmri_features(roi_series, conn)
+        eeg_feat = self.eeg_encoder(eeg, channels_last=eeg_channels_last)
+        cur.wait_stream(side)
+        for t in (roi_series, conn):
+            t.record_stream(side)
+        fmri_feat.record_stream(cur)
         return self.bridge.project(eeg_feat, fmri_feat)
 
     def forward(self, eeg, roi_series, conn, eeg_channels_last: bool = False) -> torch.Tensor:
