@@ -64,6 +64,14 @@ def cases(B):
         return {"fwd": lambda: ops.attn_fwd(qkv, 4, 32 ** -0.5, 0.3, 77),
                 "bwd": lambda: ops.attn_bwd(dout, qkv, probs, lse, 4, 32 ** -0.5, 0.3, 77)}
     c["attn"] = attn
+
+    def attn_fused():
+        qkv = ops.round_tf32(torch.randn(B, 250, 384, device="cuda"))
+        dout = ops.round_tf32(torch.randn(B, 250, 128, device="cuda"))
+        out, lse = ops.attn_fused_fwd(qkv, 4, 32 ** -0.5, 0.3, 77)
+        return {"fwd": lambda: ops.attn_fused_fwd(qkv, 4, 32 ** -0.5, 0.3, 77),
+                "bwd": lambda: ops.attn_fused_bwd(dout, qkv, out, lse, 4, 32 ** -0.5, 0.3, 77)}
+    c["attn_fused"] = attn_fused
     def pre():
         rec = r(max(B // 64, 1), 128, 512 * 65)
         from multimodal_eeg_fmri_b200 import eeg_data_utils as edu
