@@ -228,9 +228,9 @@ int xm_similarity_f32(const float* a, const float* b, float* S, int64_t Ml, int6
 int xm_infonce_tile_n(void);
 int xm_infonce_lse_f32(const float* a, const float* b, float* lse, float* diag, int64_t Ml, int64_t Ng, int64_t D,
                        float inv_tau, int64_t diag_off, float* workspace, void* stream);
-/* G (Ml, Ng) = coef * (exp(S - lse_row[i]) + exp(S - lse_col[j]) - 2*[j == i + diag_off]), full fp32 */
+/* G (Ml, Ng) = coef * (exp(S - lse_row[i]) + exp(S - lse_col[j]) - 2*[j == i + diag_off]); round_out: rounded to tf32 (feeds a single-pass product) */
 int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
-                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
+                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef, int round_out,
                         void* stream);
 
 /* dx (Ml, D) = G @ f_n in the fp32-accurate 3-pass mode: g3 (Ml, 3*Ng) = xm_split3_f32(G, which, axis 1) and
@@ -249,7 +249,7 @@ int xm_infonce_lse_peers_f32(const float* a, const void* const* b_peers, int n_p
                              void* stream);
 int xm_infonce_grad_peers_f32(const float* a, const void* const* b_peers, int n_peers, int64_t rows_per_peer,
                               const float* lse_row, const float* lse_col, float* G, int64_t Ml, int64_t D, float inv_tau,
-                              int64_t diag_off, float coef, void* stream);
+                              int64_t diag_off, float coef, int round_out, void* stream);
 /* All-gather through the same peer mappings: dst (n_peers * elems_per_peer) <- concatenation of the ranks'
  * shards, one launch of 128-bit peer loads.  Used instead of the in-GEMM peer reads when a rank has many
  * row tiles (every row tile would otherwise re-fetch every remote tile across NVLink). */

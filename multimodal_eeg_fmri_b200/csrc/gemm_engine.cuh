@@ -700,7 +700,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float lcj = __shfl_sync(0xffffffffu, lc, j);
                 float g = __expf(v[j] - lse_r) + __expf(v[j] - lcj);
                 if (j == dj) g -= 2.0f;
-                v[j] = g * p.coef;  // full fp32 (split 3-way before the dgrad); out-of-matrix parts clipped by TMA
+                v[j] = g * p.coef;  // out-of-matrix parts are clipped by TMA
+              }
+              if (p.round_tf32) {  // G feeds a single-pass tf32 product directly (else: split 3-way first)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
               }
             }
             uint8_t* sb = stg + (NBUF == 2 ? (chunk_ctr & 1) * 4096 : 0);
@@ -752,6 +756,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   float g = __expf(x - lse_r) + __expf(x - __ldg(p.lse_col + n));
                   if (n == m + p.diag_off) g -= 2.0f;
                   x = g * p.coef;
+                  if (p.round_tf32) x = round_tf32(x);
                 }
                 crow[j] = x;
               }

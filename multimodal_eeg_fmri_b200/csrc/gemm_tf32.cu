@@ -928,7 +928,7 @@ int xm_infonce_lse_peers_f32(const float* a, const void* const* b_peers, int n_p
 
 static int infonce_grad_impl(const float* a, const float* b, const void* const* b_peers, int n_peers, int64_t peer_rows,
                              const float* lse_row, const float* lse_col, float* G, int64_t Ml, int64_t Ng, int64_t D,
-                             float inv_tau, int64_t diag_off, float coef, void* stream) {
+                             float inv_tau, int64_t diag_off, float coef, int round_out, void* stream) {
   if (!a || (!b && !b_peers) || !lse_row || !lse_col || !G || Ml <= 0 || Ng <= 0 || D <= 0 || (D & 3)) return XM_ERR_INVALID;
   GemmParams p;
   zero_params(p);
@@ -937,6 +937,7 @@ static int infonce_grad_impl(const float* a, const float* b, const void* const* 
   p.M = (int)Ml;
   p.N = (int)Ng;
   p.alpha = inv_tau;
+  p.round_tf32 = round_out;
   p.c = G;
   p.ldc = Ng;
   p.lse_row = lse_row;
@@ -953,17 +954,17 @@ static int infonce_grad_impl(const float* a, const float* b, const void* const* 
 }
 
 int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,
-                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef,
+                        int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef, int round_out,
                         void* stream) {
-  return infonce_grad_impl(a, b, nullptr, 0, 0, lse_row, lse_col, G, Ml, Ng, D, inv_tau, diag_off, coef, stream);
+  return infonce_grad_impl(a, b, nullptr, 0, 0, lse_row, lse_col, G, Ml, Ng, D, inv_tau, diag_off, coef, round_out, stream);
 }
 
 int xm_infonce_grad_peers_f32(const float* a, const void* const* b_peers, int n_peers, int64_t rows_per_peer,
                               const float* lse_row, const float* lse_col, float* G, int64_t Ml, int64_t D, float inv_tau,
-                              int64_t diag_off, float coef, void* stream) {
+                              int64_t diag_off, float coef, int round_out, void* stream) {
   if (n_peers <= 0 || rows_per_peer <= 0) return XM_ERR_INVALID;
   return infonce_grad_impl(a, nullptr, b_peers, n_peers, rows_per_peer, lse_row, lse_col, G, Ml, n_peers * rows_per_peer, D,
-                           inv_tau, diag_off, coef, stream);
+                           inv_tau, diag_off, coef, round_out, stream);
 }
 
 }  // extern "C"

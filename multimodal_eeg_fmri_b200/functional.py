@@ -9,6 +9,7 @@ stored; values that feed the next tensor-core contraction are rounded to tf32 wh
 from __future__ import annotations
 
 import itertools
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -243,6 +244,7 @@ def act_dropout(x, act, drop_p=0.0, training=True):
 # but its 3e-4 forward noise is amplified by the BatchNorm-backward cancellation into a 1.4e-2 error of that
 # layer's weight gradient (7e-4 in the 3-pass mode).
 _PRECISE_MAX_K = 1 << 30
+_INFONCE_PRECISE_DGRAD = {"0": False, "1": True}.get(os.environ.get("XM_INFONCE_PRECISE_DGRAD", ""), None)
 
 
 class LinearBnAct(torch.autograd.Function):
@@ -585,20 +587,34 @@ class SymmetricInfoNCE(torch.autograd.Function):
         lse_ef_all = _AllGatherRows.gather(lse_ef)
         lse_fe_all = _AllGatherRows.gather(lse_fe)
         coef = 0.5 * inv_tau / Bg
-        # G (softmax minus one-hot) has rows summing to ~0, so G @ f_n cancels against the common component of
-        # the embeddings: both products run in the fp32-accurate 3-pass mode (G stays fp32, split on the fly).
+        # dE = G f_n, dF = G' e_n: either one tf32 pass with G rounded in its producer's epilogue, or the fp32-accurate
+        # 3-pass product (G kept in fp32 and split on the fly).  Measured at batch 2048 (tools/full_scale_parity.py)
+        # the 3-pass variant lowers the median parameter-gradient error from 5.4e-4 to 3.0e-4 (fMRI-side tensors from
+        # ~7e-4 to ~1e-4; the maximum, 9.3e-3 on the first conv layer, is the tf32 floor either way), but its split of
+        # the (local batch x GLOBAL batch) matrix costs ~2 ms per step at 8 x 4096.  Policy: precise while the global
+        # batch is <= 8192 (0.25 ms at 4096), single pass beyond; XM_INFONCE_PRECISE_DGRAD=0/1 forces either.
+        Ng_all = lse_fe_all.shape[0]
+        prec = (Ng_all <= 8192) if _INFONCE_PRECISE_DGRAD is None else _INFONCE_PRECISE_DGRAD
         if ctx.peers is not None:
             e_ptrs, f_ptrs, Bl = ctx.peers
-            G1 = ops.infonce_grad_peers(e3, f_ptrs, Bl, lse_ef, lse_fe_all, inv_tau, off, coef)  # rows: my e, cols: all f
-            G2 = ops.infonce_grad_peers(f3, e_ptrs, Bl, lse_fe, lse_ef_all, inv_tau, off, coef)  # rows: my f, cols: all e
-            f3_all = ops.peer_gather(f_ptrs, Bl, 3 * D, en.device)  # small here (Bl <= 512): local copy for the dgrad
-            e3_all = ops.peer_gather(e_ptrs, Bl, 3 * D, en.device)
+            G1 = ops.infonce_grad_peers(e3, f_ptrs, Bl, lse_ef, lse_fe_all, inv_tau, off, coef, not prec)  # my e x all f
+            G2 = ops.infonce_grad_peers(f3, e_ptrs, Bl, lse_fe, lse_ef_all, inv_tau, off, coef, not prec)  # my f x all e
+            if prec:  # small here (Bl <= 512): local copies for the split product
+                f3_all = ops.peer_gather(f_ptrs, Bl, 3 * D, en.device)
+                e3_all = ops.peer_gather(e_ptrs, Bl, 3 * D, en.device)
+            else:
+                den = ops.linear_dgrad_peers(G1, f_ptrs, Bl, D, 3 * D)
+                dfn = ops.linear_dgrad_peers(G2, e_ptrs, Bl, D, 3 * D)
         else:
             e3_all, f3_all = sv[8], sv[9]
-            G1 = ops.infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, off, coef)
-            G2 = ops.infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, off, coef)
-        den = ops.infonce_dgrad(G1, f3_all, 1)  # f3 = [hi | hi | lo]
-        dfn = ops.infonce_dgrad(G2, e3_all, 0)  # e3 = [hi | lo | hi]
+            G1 = ops.infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, off, coef, not prec)
+            G2 = ops.infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, off, coef, not prec)
+            if not prec:  # the first D columns of a split are the tf32-rounded unit vectors
+                den = ops.linear_dgrad(G1, f3_all[:, :D])
+                dfn = ops.linear_dgrad(G2, e3_all[:, :D])
+        if prec:
+            den = ops.infonce_dgrad(G1, f3_all, 1)  # f3 = [hi | hi | lo]
+            dfn = ops.infonce_dgrad(G2, e3_all, 0)  # e3 = [hi | lo | hi]
         de = ops.l2norm_bwd(den, en, einv) * g
         df = ops.l2norm_bwd(dfn, fn, finv) * g
         return de, df, None

@@ -540,7 +540,7 @@ def infonce_lse(a, b, inv_tau, diag_off=0):
     return lse, diag
 
 
-def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
+def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef, round_out=False):
     _chk(a, b, lse_row, lse_col)
     a, b = a.contiguous(), b.contiguous()
     Ml, D = a.shape
@@ -548,7 +548,7 @@ def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
     G = torch.empty(Ml, Ng, device=a.device, dtype=torch.float32)
     _w(2.0 * Ml * Ng * D, 4.0 * (Ml * D + Ng * D + Ml * Ng))
     _call("xm_infonce_grad_f32", _p(a), _p(b), _p(lse_row), _p(lse_col), _p(G), Ml, Ng, D, float(inv_tau),
-          int(diag_off), float(coef), _stream())
+          int(diag_off), float(coef), int(round_out), _stream())
     return G
 
 
@@ -583,7 +583,7 @@ def infonce_lse_peers(a, peer_ptrs, rows_per_peer, inv_tau, diag_off=0):
     return lse, diag
 
 
-def infonce_grad_peers(a, peer_ptrs, rows_per_peer, lse_row, lse_col, inv_tau, diag_off, coef):
+def infonce_grad_peers(a, peer_ptrs, rows_per_peer, lse_row, lse_col, inv_tau, diag_off, coef, round_out=False):
     _chk(a, lse_row, lse_col)
     a = a.contiguous()
     Ml, D = a.shape
@@ -592,7 +592,7 @@ def infonce_grad_peers(a, peer_ptrs, rows_per_peer, lse_row, lse_col, inv_tau, d
     G = torch.empty(Ml, Ng, device=a.device, dtype=torch.float32)
     _w(2.0 * Ml * Ng * D, 4.0 * (Ml * D + Ng * D + Ml * Ng))
     _call("xm_infonce_grad_peers_f32", _p(a), _ptr_array(peer_ptrs), G_, rows_per_peer, _p(lse_row), _p(lse_col), _p(G), Ml,
-          D, float(inv_tau), int(diag_off), float(coef), _stream())
+          D, float(inv_tau), int(diag_off), float(coef), int(round_out), _stream())
     return G
 
 

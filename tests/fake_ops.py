@@ -248,7 +248,7 @@ def infonce_lse(a, b, inv_tau, diag_off=0):
     return torch.logsumexp(S, 1).float(), S[i, i + diag_off].float()
 
 
-def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef):
+def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef, round_out=False):
     S = a.double() @ b.double().t() * inv_tau
     G = torch.exp(S - lse_row.double()[:, None]) + torch.exp(S - lse_col.double()[None, :])
     i = torch.arange(a.shape[0])
