@@ -261,7 +261,8 @@ int xm_linear_dgrad_peers_f32(const float* dy, const void* const* w_peers, int n
 /* ------------------------------------------------------------------ multi-head self-attention core
  * nn.MultiheadAttention inside TemporalTransformerBlock (EEG_CODE/enhanced_models_v4.py:71-73,98; torch computes
  * softmax(q k^T / sqrt(dh)), dropout on the weights, times v).  qkv (B, L, 3*H*dh) is the packed in_proj output
- * [q | k | v], head h at columns h*dh inside each third; out (B, L, H*dh).  Supported: dh == 32, L <= 256.
+ * [q | k | v], head h at columns h*dh inside each third; out (B, L, H*dh).  Supported: dh == 32, L <= 256
+ * (the fused variant below: L <= 512).
  * probs (B*H, L, NP) with NP = xm_attn_keys_padded(L): the dropped, normalised weights (tf32), saved for the
  * backward; lse (B*H, L).  The dropout mask is a pure function of (seed, slab, query, key). */
 int xm_attn_keys_padded(int64_t L);

@@ -17,7 +17,7 @@
 // slab per 64 clk whatever N is), which with N = dh = 32 is the floor of these kernels.
 //
 // HBM traffic per (sample, head): q, k, v, O, dO read a few times (L2) and dq, dk, dv written once -- the
-// L x L matrices P~ and dS (4.2 GB each per layer at batch 4096) are never stored.  Supported: dh == 32, L <= 256.
+// L x L matrices P~ and dS (4.2 GB each per layer at batch 4096) are never stored.  Supported: dh == 32, L <= 512.
 //
 // Dropout mask (a pure function of seed, slab, query, key, identical in all three kernels and in
 // xm_attn_fused_mask_u8): per (query row r = slab*L + query, 32-key chunk c) a stream seed
@@ -182,8 +182,9 @@ XM_DEVICE void init_common(Bars& bar, uint32_t* tmem_slot, int warp) {
 }
 
 // ============================================================================ forward
-// smem: q tile 16 KB | 2 stages of { k half 16 KB (K-major) | v half 16 KB (MN-major) } | 4 staging boxes
-// TMEM: [0,128) S / P~ of the current half;  output set s (item parity) at 128 + 64*s: O of half 0, O of half 1
+// smem: q tile 16 KB | 2 stages of { k block 16 KB (K-major) | v block 16 KB (MN-major) } | 4 staging boxes
+// TMEM: [0,128) S / P~ of the current 128-key block ("half": L <= 256 has two);  output accumulators at 128 + ...:
+// L <= 256: two sets (item parity) of two blocks;  L <= 512: one set of four blocks
 constexpr int kFwdHalf = 2 * 16384;
 constexpr int kFwdSmem = 16384 + 2 * kFwdHalf + 4 * 4096 + 1024;
 
@@ -207,7 +208,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   init_common(bar, &tmem_slot, warp);
   const uint32_t tmem = tmem_slot;
   const uint32_t tS = tmem, tO = tmem + 128;
-  const int NH = p.T;  // key halves
+  const int NH = p.T;  // 128-key blocks (1..4)
+  const bool two_sets = NH <= 2;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -234,7 +236,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t dq = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, 2);
       int it = 0, hs = 0, tn = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
-        const int s = it & 1;
+        const int s = two_sets ? (it & 1) : 0;
+        const uint32_t ouse = (uint32_t)(two_sets ? (it >> 1) : it);
         ptx::mbar_wait(&bar.full, (uint32_t)it & 1u);
         for (int hf = 0; hf < NH; ++hf, ++hs) {
           const int st = hs & 1;
@@ -252,7 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           FA_TRACE(0, tn);
           ptx::mbar_wait(&bar.p_ready, (uint32_t)hs & 1u);
           FA_TRACE(0, tn);
-          if (hf == 0) ptx::mbar_wait(&bar.o_empty[s], (((uint32_t)it >> 1) & 1u) ^ 1u);
+          if (hf == 0) ptx::mbar_wait(&bar.o_empty[s], (ouse & 1u) ^ 1u);
           ptx::tc_fence_after_sync();
           const int nk = min(16, (p.L - hf * 128 + 7) >> 3);  // K = 8 slabs with a valid key
           const uint32_t acc = tO + (uint32_t)(s * 64 + hf * 32);
@@ -275,7 +278,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool live = m < p.L;
       const unsigned long long row_id = (unsigned long long)z * (unsigned long long)p.L + (unsigned long long)m;
       const uint32_t rs = row_seed(row_id, p.seed);
-      float mh[2] = {0.f, 0.f}, lh[2] = {0.f, 0.f};  // per half: max * c (log2 domain) and sum of exp2
+      float mh[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};  // per block: max * c (log2 domain), sum of exp2
       for (int hf = 0; hf < NH; ++hf, ++hs) {
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
         ptx::mbar_wait(&bar.s_full, (uint32_t)hs & 1u);
@@ -321,38 +324,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
         reds[q][part][lane] = sum;
         pair_barrier(q);
-        mh[hf] = mc;
-        lh[hf] = reds[q][0][lane] + reds[q][1][lane];
+        {
+          const float lsum = reds[q][0][lane] + reds[q][1][lane];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // static indices keep the arrays in registers
+            if (k == hf) { mh[k] = mc; lh[k] = lsum; }
+        }
       }
       if (part == 0) {
-        // combine the halves: out = (O0 * a0 + O1 * a1) / (l0 * a0 + l1 * a1),  a_h = exp2(m_h - max(m0, m1))
-        const int s = it & 1;
-        float a0 = 1.f, a1 = 0.f, mtot = mh[0];
-        if (NH == 2) {
-          mtot = fmaxf(mh[0], mh[1]);
-          a0 = fast_exp2(mh[0] - mtot);
-          a1 = fast_exp2(mh[1] - mtot);
+        // combine the blocks: out = sum_h O_h a_h / sum_h l_h a_h,  a_h = exp2(m_h - max_h m_h)
+        const int s = two_sets ? (it & 1) : 0;
+        const uint32_t ouse = (uint32_t)(two_sets ? (it >> 1) : it);
+        float mtot = mh[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (k < NH) mtot = fmaxf(mtot, mh[k]);
+        float ah[4], denom = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ah[k] = (k < NH) ? fast_exp2(mh[k] - mtot) : 0.f;
+          denom = fmaf(lh[k], ah[k], denom);
         }
-        const float denom = lh[0] * a0 + lh[1] * a1;
         if (live) p.lse[row_id] = (mtot + log2f(denom)) * kLn2;
         const float inv = 1.0f / denom;
-        a0 *= inv;
-        a1 *= inv;
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
-        ptx::mbar_wait(&bar.o_full[s], ((uint32_t)it >> 1) & 1u);
+        ptx::mbar_wait(&bar.o_full[s], ouse & 1u);
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
         ptx::tc_fence_after_sync();
         uint32_t r[32];
         ptx::tmem_ld_32x32(tO + (uint32_t)(s * 64) + lane_base, r);
         ptx::tmem_ld_wait();
+        {
+          const float a0 = ah[0] * inv;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * a0);
-        if (NH == 2) {
-          uint32_t u[32];
-          ptx::tmem_ld_32x32(tO + (uint32_t)(s * 64 + 32) + lane_base, u);
-          ptx::tmem_ld_wait();
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * a0);
+        }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(u[j]), a1, __uint_as_float(r[j])));
+        for (int k = 1; k < 4; ++k) {
+          if (k < NH) {
+            uint32_t u[32];
+            ptx::tmem_ld_32x32(tO + (uint32_t)(s * 64 + k * 32) + lane_base, u);
+            ptx::tmem_ld_wait();
+            const float ak = ah[k] * inv;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaf(__uint_as_float(u[j]), ak, __uint_as_float(r[j])));
+          }
         }
         ptx::tc_fence_before_sync();
         __syncwarp();
@@ -385,8 +401,8 @@ struct BwdCfg {
   static constexpr int kRingOff = kItemBytes;
   static constexpr int kStagingOff = kRingOff + 2 * kChunkBytes;
   static constexpr int kStageRows = KV ? 16 : 32;
-  static constexpr int kTabOff = kStagingOff + 4 * kStageRows * 128;  // KV: lse/delta (256) + seeds [4][256]
-  static constexpr int kSmem = kTabOff + (KV ? 6 * 1024 : 0) + 1024;
+  static constexpr int kTabOff = kStagingOff + 4 * kStageRows * 128;  // KV: lse/delta + seeds [4] of 256 queries
+  static constexpr int kSmem = kTabOff + (KV ? 6 * 1024 : 0) + 1024;   // (refilled mid-item when L > 256)
   static constexpr int kOutCols = KV ? 64 : 32;  // per accumulator set
 };
 
@@ -532,11 +548,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     int it = 0, hs = 0, tn = 0;
     // dk/dv kernel: the per-query lse / delta of the NEXT item are fetched into registers one item ahead, so the
     // table refresh at an item boundary does not wait for global memory
-    float nx_lse = 0.f, nx_delta = 0.f;
-    if (KV && (int)blockIdx.x < p.items && et < p.L) {
-      const unsigned long long o = (unsigned long long)(blockIdx.x / p.T) * (unsigned long long)p.L + et;
-      nx_lse = __ldg(p.lse + o);
-      nx_delta = __ldg(p.delta + o);
+    float nx_lse[2] = {0.f, 0.f}, nx_delta[2] = {0.f, 0.f};  // queries et and et + 256
+    if (KV && (int)blockIdx.x < p.items) {
+      const unsigned long long o = (unsigned long long)(blockIdx.x / p.T) * (unsigned long long)p.L;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (et + 256 * k < p.L) {
+          nx_lse[k] = __ldg(p.lse + o + et + 256 * k);
+          nx_delta[k] = __ldg(p.delta + o + et + 256 * k);
+        }
     }
     for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
       const int z = w / p.T, t = w - z * p.T, b = z / p.H, h = z - b * p.H;
@@ -545,23 +565,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const unsigned long long slab0 = (unsigned long long)z * (unsigned long long)p.L;
       float off = 0.f, delta = 0.f;
       uint32_t rs = 0u;
-      if (KV) {
-        epi_barrier_all();  // every warp is done with the previous item's tables
-        {
-          const int m = et;
-          tab_off[m] = nx_lse * kLog2e - log2_amul;  // rows >= L: 0 (finite; their q / dO rows are zero)
-          tab_delta[m] = nx_delta;
-          const int wn = w + (int)gridDim.x;
-          if (wn < p.items && m < p.L) {
-            const unsigned long long o = (unsigned long long)(wn / p.T) * (unsigned long long)p.L + m;
-            nx_lse = __ldg(p.lse + o);
-            nx_delta = __ldg(p.delta + o);
-          }
-          const uint32_t rsm = row_seed(slab0 + (unsigned long long)m, p.seed);
+      // dk/dv kernel: per-query tables (exponent offset, delta, mask-stream seeds of this tile's four key chunks) for
+      // queries [256 k, 256 k + 256); refilled from the prefetch registers, which then fetch the next item's values
+      auto fill_tables = [&](float& pre_lse, float& pre_delta, int k) {
+        epi_barrier_all();  // every warp is done with the previous contents
+        const int m = et + 256 * k;
+        tab_off[et] = pre_lse * kLog2e - log2_amul;  // rows >= L: 0 (finite; their q / dO rows are zero)
+        tab_delta[et] = pre_delta;
+        const uint32_t rsm = row_seed(slab0 + (unsigned long long)m, p.seed);
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) tab_seed[qd * 256 + m] = chunk_seed(rsm, t * 4 + qd);
+        for (int qd = 0; qd < 4; ++qd) tab_seed[qd * 256 + et] = chunk_seed(rsm, t * 4 + qd);
+        pre_lse = 0.f;
+        pre_delta = 0.f;
+        const int wn = w + (int)gridDim.x;
+        if (wn < p.items && m < p.L) {
+          const unsigned long long on = (unsigned long long)(wn / p.T) * (unsigned long long)p.L + m;
+          pre_lse = __ldg(p.lse + on);
+          pre_delta = __ldg(p.delta + on);
         }
         epi_barrier_all();
+      };
+      if (KV) {
+        fill_tables(nx_lse[0], nx_delta[0], 0);
       } else {
         // delta = dO . O over the head's 32 columns: each part takes 16 of them
         float part_sum = 0.f;
@@ -585,6 +610,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       if (warp == 2 && lane == 0) FA_TRACE(1, tn);
       for (int cc = 0; cc < NC; ++cc, ++hs) {
+        if (KV && cc == 4) fill_tables(nx_lse[1], nx_delta[1], 1);  // L > 256: second half of the queries
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
         ptx::mbar_wait(&bar.s_full, (uint32_t)hs & 1u);
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
@@ -594,13 +620,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         ptx::tmem_ld_32x32(tP + lane_base + (uint32_t)(part * 32), g);
         const int o0 = cc * 64 + part * 32;  // first key (dq kernel) / query (dk/dv kernel) of this chunk
         if (KV) {
-          const uint32_t* sd = tab_seed + q * 256 + o0;
+          const int ot = o0 & 255;  // position inside the resident half of the tables
+          const uint32_t* sd = tab_seed + q * 256 + ot;
           ptx::tmem_ld_wait();
           const float2 c2 = make_float2(c, c);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {  // per-query constants: one broadcast 128-bit load per 4 columns
-            const float4 o4 = *reinterpret_cast<const float4*>(tab_off + o0 + 4 * j4);
-            const float4 d4 = *reinterpret_cast<const float4*>(tab_delta + o0 + 4 * j4);
+            const float4 o4 = *reinterpret_cast<const float4*>(tab_off + ot + 4 * j4);
+            const float4 d4 = *reinterpret_cast<const float4*>(tab_delta + ot + 4 * j4);
             const uint4 s4 = *reinterpret_cast<const uint4*>(sd + 4 * j4);
             const float2 of[2] = {make_float2(-o4.x, -o4.y), make_float2(-o4.z, -o4.w)};
             const float2 de[2] = {make_float2(-d4.x, -d4.y), make_float2(-d4.z, -d4.w)};
@@ -721,7 +748,7 @@ static int set_smem(K kernel, int bytes) {
 static int fill_params(FaParams& p, int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed,
                        int round_out) {
   if (!(drop_p >= 0.f && drop_p < 1.f) || B <= 0 || L <= 0 || H <= 0) return XM_ERR_INVALID;
-  if (dh != 32 || L > 256 || H > 64 || B * H > 500000000ll) return XM_ERR_UNSUPPORTED;
+  if (dh != 32 || L > 512 || H > 64 || B * H > 250000000ll) return XM_ERR_UNSUPPORTED;
   p.L = (int)L; p.H = (int)H; p.d = (int)(H * 32);
   p.T = ceil_div(L, 128);
   p.items = (int)(B * H * p.T);

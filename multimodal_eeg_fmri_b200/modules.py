@@ -80,7 +80,7 @@ class TemporalTransformerBlock(nn.Module):
         fused = mask is None and XF.attention_core_supported(L, d // self.nhead)
         if fused:  # the fused core writes tf32-rounded head outputs (operand of out_proj)
             a = XF.self_attention_core(qkv, self.nhead, self.p, self.training).reshape(B * L, d)
-        else:  # shapes outside the fused kernel (head dim != 32, L > 256, explicit mask): library attention
+        else:  # shapes outside the fused kernel (head dim != 32, L > 512, explicit mask): library attention
             q, k, v = (t.view(B, L, self.nhead, d // self.nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
             a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.p if self.training else 0.0)
             a = a.transpose(1, 2).reshape(B * L, d)
@@ -116,7 +116,7 @@ class _TransformerTail(nn.Module):
                            blk.linear1.weight, blk.linear1.bias, blk.linear2.weight, blk.linear2.bias]
             cfg = (b0.nhead, self.dropout_p, b0.norm1.eps, b0.act, self.training)
             h = XF.TransformerTail.apply(h.contiguous(), self.pos_encoder.pe[:L, 0, :].contiguous(), cfg, *params)
-        else:  # shapes outside the fused kernels (head dim != 32, L > 256, d_model % 128 != 0)
+        else:  # shapes outside the fused kernels (head dim != 32, L > 512, d_model % 128 != 0)
             h = self.pos_encoder(h)
             for blk in blocks:
                 h = blk(h)

@@ -611,7 +611,8 @@ def linear_dgrad_peers(dy, peer_ptrs, rows_per_peer, K, ldw):
 
 # ------------------------------------------------------------------ multi-head self-attention core
 def attn_supported(L: int, dh: int) -> bool:
-    return dh == 32 and 0 < L <= 256
+    """Shapes of the fused attention core (xm_attn_fused_*); the materialising xm_attn_* variant stops at L = 256."""
+    return dh == 32 and 0 < L <= 512
 
 
 def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):

@@ -391,7 +391,7 @@ def _attn_ref(qkv, B, L, H, dh, scale, mask=None):
 
 
 @pytest.mark.parametrize("B,L,H", [(2, 250, 4), (3, 128, 2), (1, 37, 1), (5, 256, 4), (2, 129, 3), (40, 250, 4), (1, 1, 1),
-                                   (2, 8, 2)])
+                                   (2, 8, 2), (2, 500, 4), (3, 257, 2), (1, 512, 1), (2, 385, 3)])
 def test_fused_attention_fwd_bwd(ops, B, L, H):
     """The on-chip (flash-style) attention core against fp64 torch, dropout off: out, lse, dqkv."""
     torch.manual_seed(14)
@@ -410,7 +410,7 @@ def test_fused_attention_fwd_bwd(ops, B, L, H):
         assert_close_rel(a, b, 2e-3, f"fused d{name}", atol=1e-6)
 
 
-@pytest.mark.parametrize("B,L,H,pdrop", [(2, 250, 4, 0.3), (3, 100, 2, 0.1), (2, 256, 1, 0.5)])
+@pytest.mark.parametrize("B,L,H,pdrop", [(2, 250, 4, 0.3), (3, 100, 2, 0.1), (2, 256, 1, 0.5), (2, 500, 2, 0.3)])
 def test_fused_attention_dropout(ops, B, L, H, pdrop):
     """Dropout on the attention weights: the exported mask has the right keep rate and no row / column structure,
     forward and both backward kernels regenerate exactly that mask (checked against autograd with it)."""

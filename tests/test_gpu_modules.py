@@ -219,6 +219,36 @@ def test_erp_v4_config1_shape_vs_oracle():
             assert_close_rel(p.grad, leaves[k].grad, 2e-2, f"grad {k}", atol=2e-5)
 
 
+def test_power_v4_full_length_vs_oracle():
+    """EnhancedPowerEncoder(64, 128, 2, 4) on (4, 64, 500): no pooling in front of the transformer, so the attention
+    runs over L = 500 tokens -- the fused core's four-block path (enhanced_models_v4.py:196-285)."""
+    from multimodal_eeg_fmri_b200.enhanced_models_v4 import EnhancedPowerEncoder
+    from multimodal_eeg_fmri_b200 import functional as XF
+    from oracle import models as om
+    assert XF.transformer_tail_supported(500, 128, 4, "gelu")
+    torch.manual_seed(43)
+    m = EnhancedPowerEncoder(64, 128, 2, 4, 0.0)
+    P = _sd_cpu(m)
+    x = torch.randn(4, 64, 500)
+    cot = torch.randn(4, 128)
+    m = m.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    y = m(xg)
+    y.backward(cot.cuda())
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items() if v.is_floating_point() and "running" not in k and not k.endswith(".pe")}
+    xo = x.clone().requires_grad_(True)
+    yo = om.enhanced_power_encoder({**P, **leaves}, "", xo, nhead=4)
+    yo.backward(cot)
+    assert_close_rel(y, yo, TOL, "encoder output")
+    assert_close_rel(xg.grad, xo.grad, 1.5e-2, "dx")
+    zero = bias_before_batchnorm(m.state_dict().keys())
+    for k, p in m.named_parameters():
+        if k in zero:
+            assert_zero_grad_noise(p.grad, dict(m.named_parameters())[k[: -len("bias")] + "weight"].grad, f"grad {k}")
+        else:
+            assert_close_rel(p.grad, leaves[k].grad, 2e-2, f"grad {k}", atol=2e-5)
+
+
 def test_fmri_config2_shape_vs_oracle():
     """fMRIFusionNet(400, 40000) on batch 64 with the ROI aggregation on the device (config 2)."""
     from multimodal_eeg_fmri_b200 import fmri_utils
