@@ -95,6 +95,13 @@ int xm_roi_meanstd_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float
 int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
                       int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
                       void* stream);
+/* The same product for operands that arrive as three ROW-stacked tf32 split blocks: x3 (3M, K) = [hi; hi; lo],
+ * w3 (3N, K) = [hi; lo; hi] (xm_split3_f32 along axis 0) -> y = x w^T to fp32 accuracy.  The row-stacked split of
+ * x is exactly the operand of the weight gradient (xm_linear_wgrad_f32 over 3M rows), so one split of a large
+ * input (the 40 000-d connectivity features) serves both the forward and the backward. */
+int xm_linear_fwd_stacked3_f32(const float* x3, const float* w3, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                               int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
+                               void* stream);
 /* dx (M,K) = dy (M,N) @ w (N,K) */
 int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
                         int64_t ldw, int64_t lddx, int round_out, void* stream);

@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and is_current():
         return LIB_PATH
     OUT_DIR.mkdir(exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("XM_NVCC_FLAGS", "").split()]  # e.g. -DXM_FA_TRACE (with --force)
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", str(LIB_PATH), *map(str, _sources())]

@@ -77,10 +77,16 @@ constexpr uint32_t kLcgA = 747796405u, kLcgC = 2891336453u;
 constexpr float kTruncComp = 1.0f + 0.7213f / 2048.0f;
 
 static long long* g_attn_trace = nullptr;
+// Phase tracing (clock64() stamps of CTA 0, see xm_debug_set_attn_trace) is compiled in only with -DXM_FA_TRACE:
+// even a never-taken branch per phase costs registers in these register-bound epilogues.
+#ifdef XM_FA_TRACE
 #define FA_TRACE(role, n)                                                                   \
   do {                                                                                      \
     if (p.trace != nullptr && blockIdx.x == 0 && (n) < 4096) p.trace[(role) * 4096 + (n)++] = clock64(); \
   } while (0)
+#else
+#define FA_TRACE(role, n) ((void)(n))
+#endif
 
 // Forward, one 32-column chunk of a row in registers: e' = exp2(s*c - mcs) (mcs carries -log2(keep_mul), so the kept
 // value IS e'), row sum accumulated two lanes wide, dropped / padded entries zeroed.  The arithmetic uses the packed
@@ -188,6 +194,7 @@ XM_DEVICE void init_common(Bars& bar, uint32_t* tmem_slot, int warp) {
 constexpr int kFwdHalf = 2 * 16384;
 constexpr int kFwdSmem = 16384 + 2 * kFwdHalf + 4 * 4096 + 1024;
 
+template <bool LONG>  // LONG: 256 < L <= 512 (up to four key blocks, one output set); else at most two, two sets
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmVmn,
                 const __grid_constant__ CUtensorMap tmO, const FaParams p) {
@@ -209,7 +216,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem = tmem_slot;
   const uint32_t tS = tmem, tO = tmem + 128;
   const int NH = p.T;  // 128-key blocks (1..4)
-  const bool two_sets = NH <= 2;
+  constexpr bool two_sets = !LONG;
+  constexpr int NHMAX = LONG ? 4 : 2;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -278,7 +286,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool live = m < p.L;
       const unsigned long long row_id = (unsigned long long)z * (unsigned long long)p.L + (unsigned long long)m;
       const uint32_t rs = row_seed(row_id, p.seed);
-      float mh[4] = {0.f, 0.f, 0.f, 0.f}, lh[4] = {0.f, 0.f, 0.f, 0.f};  // per block: max * c (log2 domain), sum of exp2
+      float mh[NHMAX], lh[NHMAX];  // per block: max * c (log2 domain), sum of exp2
+#pragma unroll
+      for (int k = 0; k < NHMAX; ++k) mh[k] = lh[k] = 0.f;
       for (int hf = 0; hf < NH; ++hf, ++hs) {
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
         ptx::mbar_wait(&bar.s_full, (uint32_t)hs & 1u);
@@ -327,7 +337,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         {
           const float lsum = reds[q][0][lane] + reds[q][1][lane];
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // static indices keep the arrays in registers
+          for (int k = 0; k < NHMAX; ++k)  // static indices keep the arrays in registers
             if (k == hf) { mh[k] = mc; lh[k] = lsum; }
         }
       }
@@ -337,11 +347,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ouse = (uint32_t)(two_sets ? (it >> 1) : it);
         float mtot = mh[0];
 #pragma unroll
-        for (int k = 1; k < 4; ++k)
+        for (int k = 1; k < NHMAX; ++k)
           if (k < NH) mtot = fmaxf(mtot, mh[k]);
-        float ah[4], denom = 0.f;
+        float ah[NHMAX], denom = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NHMAX; ++k) {
           ah[k] = (k < NH) ? fast_exp2(mh[k] - mtot) : 0.f;
           denom = fmaf(lh[k], ah[k], denom);
         }
@@ -360,7 +370,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * a0);
         }
 #pragma unroll
-        for (int k = 1; k < 4; ++k) {
+        for (int k = 1; k < NHMAX; ++k) {
           if (k < NH) {
             uint32_t u[32];
             ptx::tmem_ld_32x32(tO + (uint32_t)(s * 64 + k * 32) + lane_base, u);
@@ -406,7 +416,7 @@ struct BwdCfg {
   static constexpr int kOutCols = KV ? 64 : 32;  // per accumulator set
 };
 
-template <bool KV>
+template <bool KV, bool LONG>  // LONG (dk/dv only): 256 < L <= 512, the per-query tables are refilled mid-item
 __global__ void __launch_bounds__(kThreads, 2)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDOx,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYmn,
@@ -548,11 +558,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     int it = 0, hs = 0, tn = 0;
     // dk/dv kernel: the per-query lse / delta of the NEXT item are fetched into registers one item ahead, so the
     // table refresh at an item boundary does not wait for global memory
-    float nx_lse[2] = {0.f, 0.f}, nx_delta[2] = {0.f, 0.f};  // queries et and et + 256
+    constexpr int NQH = LONG ? 2 : 1;
+    float nx_lse[NQH], nx_delta[NQH];  // queries et (and et + 256)
+#pragma unroll
+    for (int k = 0; k < NQH; ++k) nx_lse[k] = nx_delta[k] = 0.f;
     if (KV && (int)blockIdx.x < p.items) {
       const unsigned long long o = (unsigned long long)(blockIdx.x / p.T) * (unsigned long long)p.L;
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
+      for (int k = 0; k < NQH; ++k)
         if (et + 256 * k < p.L) {
           nx_lse[k] = __ldg(p.lse + o + et + 256 * k);
           nx_delta[k] = __ldg(p.delta + o + et + 256 * k);
@@ -610,7 +623,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       if (warp == 2 && lane == 0) FA_TRACE(1, tn);
       for (int cc = 0; cc < NC; ++cc, ++hs) {
-        if (KV && cc == 4) fill_tables(nx_lse[1], nx_delta[1], 1);  // L > 256: second half of the queries
+        if (KV && LONG && cc == 4) fill_tables(nx_lse[NQH - 1], nx_delta[NQH - 1], 1);  // second half of the queries
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
         ptx::mbar_wait(&bar.s_full, (uint32_t)hs & 1u);
         if (warp == 2 && lane == 0) FA_TRACE(1, tn);
@@ -779,10 +792,12 @@ int xm_attn_fused_fwd_f32(const float* qkv, float* out, float* lse, int64_t B, i
   rc = encode_tmap(&mq, tq, 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&mv, tq, 32, 128, 1);
   if (rc == XM_OK) rc = encode_tmap(&mo, to, 32, 32, 0);
-  if (rc == XM_OK) rc = set_smem(attn_fwd_kernel, kFwdSmem);
+  const bool lng = L > 256;
+  if (rc == XM_OK) rc = lng ? set_smem(attn_fwd_kernel<true>, kFwdSmem) : set_smem(attn_fwd_kernel<false>, kFwdSmem);
   if (rc != XM_OK) return rc;
   const int ctas = p.items < 2 * kNumSMs ? p.items : 2 * kNumSMs;
-  attn_fwd_kernel<<<ctas, kThreads, kFwdSmem, (cudaStream_t)stream>>>(mq, mv, mo, p);
+  if (lng) attn_fwd_kernel<true><<<ctas, kThreads, kFwdSmem, (cudaStream_t)stream>>>(mq, mv, mo, p);
+  else attn_fwd_kernel<false><<<ctas, kThreads, kFwdSmem, (cudaStream_t)stream>>>(mq, mv, mo, p);
   return check_launch();
 }
 
@@ -808,21 +823,28 @@ int xm_attn_fused_bwd_f32(const float* dout, const float* qkv, const float* out,
   if (rc == XM_OK) rc = encode_tmap(&mdyn, tdo, 32, 64, 1);
   if (rc == XM_OK) rc = encode_tmap(&mo, tdq, 32, 32, 0);
   if (rc == XM_OK) rc = encode_tmap(&mo16, tdq, 32, 16, 0);
-  if (rc == XM_OK) rc = set_smem(attn_bwd_kernel<false>, BwdCfg<false>::kSmem);
-  if (rc == XM_OK) rc = set_smem(attn_bwd_kernel<true>, BwdCfg<true>::kSmem);
+  const bool lng = L > 256;
+  if (rc == XM_OK) rc = set_smem(attn_bwd_kernel<false, false>, BwdCfg<false>::kSmem);
+  if (rc == XM_OK) rc = lng ? set_smem(attn_bwd_kernel<true, true>, BwdCfg<true>::kSmem)
+                            : set_smem(attn_bwd_kernel<true, false>, BwdCfg<true>::kSmem);
   if (rc != XM_OK) return rc;
   const int ctas = p.items < 2 * kNumSMs ? p.items : 2 * kNumSMs;
   cudaStream_t st = (cudaStream_t)stream;
-  attn_bwd_kernel<false><<<ctas, kThreads, BwdCfg<false>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo, p);  // dq, delta
+  attn_bwd_kernel<false, false><<<ctas, kThreads, BwdCfg<false>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo, p);  // dq, delta
   rc = check_launch();
   if (rc != XM_OK) return rc;
-  attn_bwd_kernel<true><<<ctas, kThreads, BwdCfg<true>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo16, p);  // dk, dv
+  if (lng) attn_bwd_kernel<true, true><<<ctas, kThreads, BwdCfg<true>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo16, p);
+  else attn_bwd_kernel<true, false><<<ctas, kThreads, BwdCfg<true>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo16, p);  // dk, dv
   return check_launch();
 }
 
 int xm_debug_set_attn_trace(int64_t* device_buffer) {
   xm::fa::g_attn_trace = reinterpret_cast<long long*>(device_buffer);
+#ifdef XM_FA_TRACE
   return XM_OK;
+#else
+  return device_buffer ? XM_ERR_UNSUPPORTED : XM_OK;  // rebuild with -DXM_FA_TRACE (XM_NVCC_FLAGS) to trace
+#endif
 }
 
 int xm_attn_fused_mask_u8(uint8_t* mask, int64_t B, int64_t L, int64_t H, float drop_p, uint64_t seed, void* stream) {

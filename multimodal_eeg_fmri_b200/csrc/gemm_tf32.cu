@@ -508,9 +508,10 @@ const char* xm_strerror(int code) {
   return "unknown error";
 }
 
-int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
-                      void* stream) {
+// blocks == 3: x is (3M, K) and w is (3N, K), three row-stacked tf32 split blocks each; y = sum_b x[b] w[b]^T
+static int linear_fwd_impl(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                           int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
+                           int blocks, void* stream) {
   const int round_out = (flags & XM_LINEAR_ROUND_TF32) ? 1 : 0;
   const bool fp32_accum = (flags & XM_LINEAR_FP32_ACCUM) != 0;
   if (!x || !w || !y || M <= 0 || N <= 0 || K <= 0) return XM_ERR_INVALID;
@@ -556,8 +557,14 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
     p.ldc = N;
     p.c_z_stride = (long long)M * N;
   }
-  TensorView3 ta{x, {(unsigned long long)K, (unsigned long long)M, 1}, {(unsigned long long)ldx * 4, (unsigned long long)M * ldx * 4}};
-  TensorView3 tb{w, {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
+  TensorView3 ta{x, {(unsigned long long)K, (unsigned long long)M, (unsigned long long)blocks}, {(unsigned long long)ldx * 4, (unsigned long long)M * ldx * 4}};
+  TensorView3 tb{w, {(unsigned long long)K, (unsigned long long)N, (unsigned long long)blocks}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
+  if (blocks > 1) {  // the block index is the outer contraction loop: tensor-map dimension 2 of both operands
+    p.kout_count = blocks;
+    p.kout_total = blocks;
+    p.a.kout_step[2] = 1;
+    p.b.kout_step[2] = 1;
+  }
   p.c_z_mul = 1;
   const TensorView3 tc = splits == 1 ? TensorView3{y, {(unsigned long long)(N), (unsigned long long)(M), (unsigned long long)(1)}, {(unsigned long long)(ldy) * 4, (unsigned long long)(M * ldy) * 4}}
                                      : TensorView3{workspace, {(unsigned long long)(N), (unsigned long long)(M), (unsigned long long)(splits)}, {(unsigned long long)(N) * 4, (unsigned long long)(M * N) * 4}};
@@ -571,6 +578,18 @@ int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* 
     rc = xm_act_fwd_f32(y, y, M * N, act, 0.f, 0, round_out, stream);
   }
   return rc;
+}
+
+int xm_linear_fwd_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                      int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
+                      void* stream) {
+  return linear_fwd_impl(x, w, bias, y, M, N, K, ldx, ldw, ldy, act, flags, splits, workspace, 1, stream);
+}
+
+int xm_linear_fwd_stacked3_f32(const float* x3, const float* w3, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                               int64_t ldx, int64_t ldw, int64_t ldy, int act, int flags, int splits, float* workspace,
+                               void* stream) {
+  return linear_fwd_impl(x3, w3, bias, y, M, N, K, ldx, ldw, ldy, act, flags, splits, workspace, 3, stream);
 }
 
 static int linear_dgrad_impl(const float* dy, const float* w, const void* const* w_peers, int n_peers, int64_t peer_rows,

@@ -259,7 +259,10 @@ class LinearBnAct(torch.autograd.Function):
         # 3-pass (fp32-accurate) projection (see _PRECISE_MAX_K for the single-pass escape hatch)
         precise = x.shape[1] < _PRECISE_MAX_K
         if precise:
-            y = ops.linear_fwd_precise(x, w, b)
+            # one row-stacked tf32 split of the input serves the forward AND the weight gradient (for the 40 000-d
+            # connectivity features that is a 2 GB write saved per step); it replaces x among the saved tensors
+            x = ops.linear_precise_prepare(x)
+            y = ops.linear_fwd_prepared(x, w, b)
         else:
             x, w = _tf32(x), _tf32(w)
             y = ops.linear_fwd(x, w, b)
@@ -281,7 +284,7 @@ class LinearBnAct(torch.autograd.Function):
                                          not ctx.precise)
         if ctx.precise:
             dx = ops.linear_dgrad_precise(dy, w) if ctx.needs_input_grad[0] else None
-            dw, db = ops.linear_wgrad_precise(dy, x, need_bias=not training)
+            dw, db = ops.linear_wgrad_prepared(dy, x, need_bias=not training, K=w.shape[1])
         else:  # x, w were saved tf32-rounded; dy was rounded by the BN backward kernel
             dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
             dw, db = ops.linear_wgrad(dy, x, need_bias=not training)

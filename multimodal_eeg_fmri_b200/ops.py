@@ -425,6 +425,39 @@ def linear_fwd_precise(x, w, bias=None, act=None):
     return linear_fwd(split3(x, 0, 1), split3(w, 1, 1), bias, act=act, fp32_accum=True)
 
 
+def linear_precise_prepare(x):
+    """Row-stacked tf32 split [hi; hi; lo] of x (M, K): the operand of linear_fwd_prepared AND of the weight gradient."""
+    if x.shape[1] % 4:  # TMA row pitch: zero columns up to a multiple of 4 (they contribute nothing)
+        x = torch.nn.functional.pad(x, (0, 4 - x.shape[1] % 4))
+    return split3(x, 1, 0)
+
+
+def linear_fwd_prepared(x3, w, bias=None, act=None):
+    """fp32-accurate y = x @ w^T + b from the row-stacked split of x (see linear_precise_prepare)."""
+    _chk(x3, w, bias)
+    M, K = x3.shape[0] // 3, x3.shape[1]
+    N = w.shape[0]
+    if w.shape[1] != K:
+        w = torch.nn.functional.pad(w, (0, K - w.shape[1]))
+    w3 = split3(w, 0, 0)
+    y = torch.empty(M, N, device=x3.device, dtype=torch.float32)
+    tiles = ((M + 127) // 128) * max(1, (N + 127) // 128)
+    splits = 1 if tiles >= 74 or K < 2048 else min(8, max(1, 148 // tiles), K // 512)
+    ws = torch.empty(splits * M * N, device=x3.device, dtype=torch.float32) if splits > 1 else None
+    _w(6.0 * M * N * K, 4.0 * (3 * M * K + 3 * N * K + M * N))
+    _call("xm_linear_fwd_stacked3_f32", _p(x3), _p(w3), _p(bias), _p(y), M, N, K, x3.stride(0), w3.stride(0), y.stride(0),
+          act_code(act), 2, splits, _p(ws), _stream())
+    return y
+
+
+def linear_wgrad_prepared(dy, x3, need_bias=True, K=None):
+    """dw (N, K) from the row-stacked split of x; K: the layer's true input width when x3 carries padding columns."""
+    dw, _ = linear_wgrad(split3(dy, 0, 0), x3, need_bias=False)
+    if K is not None and K != dw.shape[1]:
+        dw = dw[:, :K].contiguous()
+    return dw, (colsum(dy) if need_bias else None)
+
+
 def linear_dgrad_precise(dy, w):
     return linear_dgrad(split3(dy, 0, 1), split3(w, 1, 0))
 

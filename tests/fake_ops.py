@@ -207,6 +207,18 @@ def linear_wgrad_precise(dy, x, need_bias=True):
     return linear_wgrad(dy, x, need_bias)
 
 
+def linear_precise_prepare(x):
+    return x
+
+
+def linear_fwd_prepared(x3, w, bias=None, act=None):
+    return linear_fwd(x3, w, bias, act)
+
+
+def linear_wgrad_prepared(dy, x3, need_bias=True, K=None):
+    return linear_wgrad(dy, x3, need_bias)
+
+
 def act_bwd_colsum(dout, x, act, drop_p=0.0, seed=0, round_out=False):
     dx = act_bwd(dout, x, act, drop_p, seed, round_out)
     return dx, dx.double().sum(0).float()

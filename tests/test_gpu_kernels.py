@@ -86,6 +86,11 @@ def test_linear_precise_is_fp32_accurate(ops, M, N, K, act):
     dw, db = ops.linear_wgrad_precise(dy, x)
     assert_close_rel(dw, dy.double().t() @ x.double(), 3e-5, "linear_wgrad_precise")
     assert_close_rel(db, dy.double().sum(0), FP32, "bias grad")
+    # the shared row-stacked split: same forward, same weight gradient
+    x3 = ops.linear_precise_prepare(x)
+    assert_close_rel(ops.linear_fwd_prepared(x3, w, b, act=act), ref, 3e-6, "linear_fwd_prepared")
+    dw2, _ = ops.linear_wgrad_prepared(dy, x3)
+    assert torch.equal(dw2, dw)
 
 
 @pytest.mark.parametrize("Ml,Ng,D", [(256, 256, 128), (512, 4096, 128), (100, 36, 64), (1, 1, 128), (130, 8200, 32)])

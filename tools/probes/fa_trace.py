@@ -1,3 +1,6 @@
+"""Phase trace of the fused attention kernels (CTA 0).  Needs a tracing build:
+    XM_NVCC_FLAGS=-DXM_FA_TRACE python -m multimodal_eeg_fmri_b200.build --force
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ctypes, torch
