@@ -255,6 +255,7 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e / args.e2e_steps, 3), "steps": args.e2e_steps},
             "gpu_launches": launches,
             "roofline": roofline,
+            "peak_device_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
             "own_kernels_ms_per_step": round(ours_ms, 3),
             "torch_ops_ms_per_step": round(ms_step - ours_ms, 3),
             "kernels": kernels}

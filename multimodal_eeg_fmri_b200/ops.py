@@ -442,7 +442,8 @@ def linear_fwd_prepared(x3, w, bias=None, act=None):
     w3 = split3(w, 0, 0)
     y = torch.empty(M, N, device=x3.device, dtype=torch.float32)
     tiles = ((M + 127) // 128) * max(1, (N + 127) // 128)
-    splits = 1 if tiles >= 74 or K < 2048 else min(8, max(1, 148 // tiles), K // 512)
+    # split K so that the persistent grid fills about two waves of the 148 SMs (32 row tiles x 9 splits = 288)
+    splits = 1 if tiles >= 74 or K < 2048 else min(16, max(1, round(296 / tiles)), K // 512)
     ws = torch.empty(splits * M * N, device=x3.device, dtype=torch.float32) if splits > 1 else None
     _w(6.0 * M * N * K, 4.0 * (3 * M * K + 3 * N * K + M * N))
     _call("xm_linear_fwd_stacked3_f32", _p(x3), _p(w3), _p(bias), _p(y), M, N, K, x3.stride(0), w3.stride(0), y.stride(0),
