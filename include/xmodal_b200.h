@@ -75,6 +75,18 @@ int xm_bandpower_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_sampl
                      int64_t nfft, float fs, const float* taper, float taper_sumsq, const int32_t* band_bins,
                      int n_bands, float* power, void* stream);
 
+/* The same band powers as a tensor-core DFT (csrc/bandpower_dft.cu): only the bins inside the bands are computed,
+ * X = x . [taper cos | taper sin] as a 3-pass tf32 product with the split samples in tensor memory.  Eligible when
+ * xm_bandpower_dft_supported(...) != 0: total_bins = sum of the band widths <= 32, n_bands <= 8, win <= 1024,
+ * n_samples % 4 == 0, hop % 4 == 0 (nfft: any integer >= win, not only powers of two).  total_bins is the caller's
+ * (host) knowledge of band_bins; workspace: xm_bandpower_dft_workspace_floats(win) floats, 16-B aligned. */
+int64_t xm_bandpower_dft_workspace_floats(int64_t win);
+int xm_bandpower_dft_supported(int64_t C, int64_t n_samples, int64_t win, int64_t hop, int64_t nfft, int n_bands,
+                               int total_bins);
+int xm_bandpower_dft_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
+                         int64_t nfft, float fs, const float* taper, float taper_sumsq, const int32_t* band_bins,
+                         int n_bands, int total_bins, float* workspace, float* power, void* stream);
+
 /* normalize_modality (EEG_CODE/run_training_lite.py:48-51): out = (x - mean)/(std + eps) per item,
  * population std, over `item_len` contiguous elements. */
 int xm_zscore_f32(const float* x, int64_t n_items, int64_t item_len, float eps, float* out, void* stream);

@@ -80,10 +80,13 @@ def _hann(win: int, device) -> Tuple[torch.Tensor, float]:
     return _taper_cache[key]
 
 
-def band_power(rec: torch.Tensor, fs: float, win: int, hop: int, bands=None, nfft: Optional[int] = None) -> torch.Tensor:
+def band_power(rec: torch.Tensor, fs: float, win: int, hop: int, bands=None, nfft: Optional[int] = None,
+               path: str = "auto") -> torch.Tensor:
     """Band power of every window of rec (R, C, n): Hann taper, rfft zero-padded to nfft (next power of
     two >= win by default), one-sided PSD, sum over [lo, hi) bins times the bin width.
-    Returns (R*n_win, C, n_bands) fp32; windows are read in place (never materialised)."""
+    Returns (R*n_win, C, n_bands) fp32; windows are read in place (never materialised).  path: "auto" picks the
+    tensor-core DFT kernel when only a few bins are needed (<= 32) and there are >= 64 channels, else the FFT
+    kernel; "fft" / "dft" force one."""
     bands = list((bands or DEFAULT_BANDS).values()) if isinstance(bands or DEFAULT_BANDS, dict) else list(bands)
     if rec.dim() != 3:
         raise ValueError("rec must be (recordings, channels, samples)")
@@ -92,8 +95,10 @@ def band_power(rec: torch.Tensor, fs: float, win: int, hop: int, bands=None, nff
     if nfft is None:
         nfft = 1 << max(6, (win - 1).bit_length())
     taper, sumsq = _hann(win, rec.device)
-    bins = torch.tensor(band_bins(bands, nfft, fs), dtype=torch.int32, device=rec.device)
-    return ops.bandpower(rec, win, hop, nfft, fs, taper, sumsq, bins)
+    host_bins = band_bins(bands, nfft, fs)
+    bins = torch.tensor(host_bins, dtype=torch.int32, device=rec.device)
+    total = sum(host_bins[2 * b + 1] - host_bins[2 * b] for b in range(len(bands)))
+    return ops.bandpower(rec, win, hop, nfft, fs, taper, sumsq, bins, total_bins=total, path=path)
 
 
 def normalize_modality(feat: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:

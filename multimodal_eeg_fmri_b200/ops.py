@@ -822,13 +822,24 @@ def window_gather(rec, win, hop, channels_last=False, round_out=False):
     return out
 
 
-def bandpower(rec, win, hop, nfft, fs, taper, taper_sumsq, band_bins):
+def bandpower(rec, win, hop, nfft, fs, taper, taper_sumsq, band_bins, total_bins=None, path="auto"):
+    """Band powers of every window.  total_bins: the host's sum of the band widths in `band_bins` -- with it the
+    tensor-core DFT kernel can be chosen (few bins, >= 64 channels); path: "auto" | "fft" | "dft"."""
     _chk(rec, taper)
     rec = rec.contiguous()
     R, C, n = rec.shape
     n_win = (n - win) // hop + 1
     nb = band_bins.numel() // 2
     power = torch.empty(R * n_win, C, nb, device=rec.device, dtype=torch.float32)
+    dft_ok = total_bins is not None and bool(_lib.lib().xm_bandpower_dft_supported(C, n, win, hop, nfft, nb, int(total_bins)))
+    if path == "dft" and not dft_ok:
+        raise ValueError("shape not eligible for the DFT band-power kernel")
+    if path == "dft" or (path == "auto" and dft_ok and C >= 64):
+        ws = torch.empty(int(_lib.lib().xm_bandpower_dft_workspace_floats(win)), device=rec.device, dtype=torch.float32)
+        _w(R * n_win * C * 6.0 * 64 * win, 4.0 * (R * n_win * C * win + power.numel()))
+        _call("xm_bandpower_dft_f32", _p(rec), R, C, n, win, hop, nfft, float(fs), _p(taper), float(taper_sumsq),
+              _p(band_bins), nb, int(total_bins), _p(ws), _p(power), _stream())
+        return power
     _w(R * n_win * C * 2.5 * nfft * max(1, nfft.bit_length() - 1), 4.0 * (R * n_win * C * win + power.numel()))
     _call("xm_bandpower_f32", _p(rec), R, C, n, win, hop, nfft, float(fs), _p(taper), float(taper_sumsq),
           _p(band_bins), nb, _p(power), _stream())

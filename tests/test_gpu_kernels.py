@@ -203,6 +203,30 @@ def test_window_index_gather_bandpower(ops, R, C, n, win, hop, nfft, fs):
     assert err.max() < FP32, f"band power max rel err {err.max():.3e}"
 
 
+@pytest.mark.parametrize("R,C,n,win,hop,nfft,fs", [
+    (2, 128, 8192, 1024, 512, 1024, 1000.0), (1, 64, 4096, 1000, 500, 1024, 1000.0), (2, 130, 4096, 512, 256, 512, 500.0),
+    (1, 96, 2048, 256, 128, 256, 250.0), (3, 8, 2000, 500, 248, 500, 500.0), (1, 128, 1024, 1024, 1024, 1024, 1000.0),
+])
+def test_bandpower_tensor_core_dft(ops, R, C, n, win, hop, nfft, fs):
+    """The DFT-as-GEMM band-power kernel (3-pass tf32 with the split samples in tensor memory) against the fp64
+    oracle, at the same 1e-5 per-element bound as the FFT kernel, and against the FFT kernel itself."""
+    from multimodal_eeg_fmri_b200 import eeg_data_utils as edu
+    from oracle import spectral as osp
+    torch.manual_seed(8)
+    t = torch.arange(n, dtype=torch.float64) / fs
+    tones = sum(a * torch.sin(2 * math.pi * f * t + ph) for a, f, ph in ((2.0, 6.0, 0.3), (1.5, 10.0, 1.1), (1.0, 20.0, 2.0)))
+    rec = (torch.randn(R, C, n, dtype=torch.float64) + tones).float().cuda()
+    p = edu.band_power(rec, fs, win, hop, nfft=nfft, path="dft")
+    want = osp.gather_windows(rec.cpu().numpy(), win, hop)
+    ref = osp.band_power(want, fs, nfft=nfft, taper=torch.hann_window(win, periodic=True, dtype=torch.float64).float().double().numpy())
+    assert p.shape == ref.shape
+    err = np.abs(p.cpu().numpy().astype(np.float64) - ref) / np.maximum(ref, 1e-30)
+    assert err.max() < FP32, f"DFT band power max rel err {err.max():.3e}"
+    if nfft & (nfft - 1) == 0 and nfft >= 64:  # the FFT kernel needs a power-of-two transform length
+        pf = edu.band_power(rec, fs, win, hop, nfft=nfft, path="fft")
+        assert float(((p - pf).abs() / pf.abs().clamp_min(1e-30)).max()) < 2e-5
+
+
 def test_bandpower_pure_tone(ops):
     """Known answer: a 10 Hz sinusoid of amplitude A puts A^2/2 in alpha and ~nothing elsewhere."""
     from multimodal_eeg_fmri_b200 import eeg_data_utils as edu
