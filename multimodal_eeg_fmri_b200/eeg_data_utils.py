@@ -1,20 +1,26 @@
 """Drop-in for the hot-path part of EEG_CODE/eeg_data_utils.py plus the device preprocessing the
 north-star attributes to this module: window index generation, window gather and band power
 (no reference implementation: SURVEY.md section 0; definitions in oracle/spectral.py), and
-`normalize_modality` (EEG_CODE/run_training_lite.py:48-51).  The .mat / HDF5 readers are out of scope."""
+`normalize_modality` (EEG_CODE/run_training_lite.py:48-51), and the .mat feature readers (:46-186; SURVEY.md
+section 8f rank 3: host-side byte movement, bit-exact; MATLAB v7.3 / HDF5 files need `h5py`, which is optional)."""
 from __future__ import annotations
 
+import glob
+import logging
 import math
 import os
 from fractions import Fraction
+from pathlib import Path
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
 from . import ops
 
-__all__ = ["load_eeg_labels", "window_indices", "gather_windows", "band_power", "band_bins", "normalize_modality",
-           "DEFAULT_BANDS"]
+logger = logging.getLogger(__name__)
+
+__all__ = ["load_eeg_labels", "load_eeg_conn_features", "load_eeg_pw_features", "load_eeg_erp_features",
+           "window_indices", "gather_windows", "band_power", "band_bins", "normalize_modality", "DEFAULT_BANDS"]
 
 # EEG_CODE/config.py:35 names the bands; half-open [lo, hi) Hz
 DEFAULT_BANDS: Dict[str, Tuple[float, float]] = {"theta": (4.0, 8.0), "alpha": (8.0, 13.0), "beta": (13.0, 30.0)}
@@ -36,6 +42,111 @@ def load_eeg_labels(label_dir, binary: bool = True) -> Dict[int, int]:
     out = {}
     for sid, score in zip(ids.tolist(), df["Postoperative evaluation"].tolist()):
         out[int(sid)] = 0 if score <= 2 else 1 if binary else score
+    return out
+
+
+# ------------------------------------------------------------------------- .mat feature readers (:46-186)
+def _first_mat_variable(path, flatten: bool):
+    """The first non-private variable of a MATLAB v5 file as fp32 with NaN -> 0 (None if the file has none)."""
+    import numpy as np
+    from scipy.io import loadmat
+
+    mat = loadmat(path)
+    name = next((k for k in mat if not k.startswith("_")), None)
+    if name is None:
+        return None
+    data = np.array(mat[name], dtype=np.float32)
+    return np.nan_to_num(data.flatten() if flatten else data, nan=0.0)
+
+
+def _hdf5_erp(path):
+    """ERP array of a MATLAB v7.3 (HDF5) file: group `erp_struct` | `erp` | first key; dataset `avg`, else `trial`
+    (3-D trials averaged over axis 0), else the first dataset with >= 2 dims (:141-165).  Returns (found, data);
+    raises when the file is not HDF5 or h5py is not installed (the caller then tries the v5 reader)."""
+    import h5py  # optional dependency
+    import numpy as np
+
+    with h5py.File(path, "r") as hf:
+        group = hf["erp_struct"] if "erp_struct" in hf else hf["erp"] if "erp" in hf else hf[list(hf.keys())[0]]
+        if "avg" in group:
+            data = np.array(group["avg"], dtype=np.float32)
+        elif "trial" in group:
+            data = np.array(group["trial"], dtype=np.float32)
+            if data.ndim == 3:
+                data = np.mean(data, axis=0)
+        else:
+            cand = next((group[k] for k in group.keys() if hasattr(group[k], "shape") and len(group[k].shape) >= 2), None)
+            if cand is None:
+                return False, None
+            data = np.array(cand, dtype=np.float32)
+        return True, np.nan_to_num(data, nan=0.0)
+
+
+def load_eeg_conn_features(conn_dir, subject_list, band_list, cond_list):
+    """:46-86 -- {(subject, band_key, condition, 0): flat fp32} from `conn_<BandName>_<cond>_subNN.mat`, falling
+    back to `conn_<band_key>_...` when the capitalised name matches nothing; `band_list` maps key -> name."""
+    conn_dir = Path(conn_dir)
+    out = {}
+    for subj in subject_list:
+        tag = f"{subj:02d}"
+        for band_key, band_name in band_list.items():
+            for cond in cond_list:
+                files = sorted(glob.glob(str(conn_dir / f"conn_{band_name}_{cond}_sub{tag}.mat")))
+                if not files:
+                    files = sorted(glob.glob(str(conn_dir / f"conn_{band_key}_{cond}_sub{tag}.mat")))
+                for f in files:
+                    try:
+                        data = _first_mat_variable(f, flatten=True)
+                        if data is not None:
+                            out[(subj, band_key, cond, 0)] = data
+                    except Exception as e:  # noqa: BLE001 - reference behaviour: log and continue
+                        logger.warning(f"Error loading {f}: {e}")
+    logger.info(f"Loaded {len(out)} EEG connectivity samples")
+    return out
+
+
+def load_eeg_pw_features(pw_dir, subject_list, band_list, freq_list):
+    """:89-125 -- {(subject, band, freq, 0): flat fp32} from `powspctrm_<band>_<freq>_subNN.mat`."""
+    pw_dir = Path(pw_dir)
+    out = {}
+    for subj in subject_list:
+        tag = f"{subj:02d}"
+        for band in band_list:
+            for freq in freq_list:
+                for f in sorted(glob.glob(str(pw_dir / f"powspctrm_{band}_{freq}_sub{tag}.mat"))):
+                    try:
+                        data = _first_mat_variable(f, flatten=True)
+                        if data is not None:
+                            out[(subj, band, freq, 0)] = data
+                    except Exception as e:  # noqa: BLE001
+                        logger.warning(f"Error loading {f}: {e}")
+    logger.info(f"Loaded {len(out)} EEG power spectrum samples")
+    return out
+
+
+def load_eeg_erp_features(erp_dir, subject_list, band_list, freq_list):
+    """:128-186 -- {(subject, band, freq, 0): fp32 array, shape kept} from `ERP_subNN_<band>_<freq>*.mat`: HDF5
+    (v7.3) layout first, MATLAB v5 (`scipy.io.loadmat`, first variable) when that fails; a later file matching the
+    same key overwrites an earlier one (sorted order)."""
+    erp_dir = Path(erp_dir)
+    out = {}
+    for subj in subject_list:
+        tag = f"{subj:02d}"
+        for band in band_list:
+            for freq in freq_list:
+                for f in sorted(glob.glob(str(erp_dir / f"ERP_sub{tag}_{band}_{freq}*.mat"))):
+                    try:
+                        found, data = _hdf5_erp(f)
+                        if found:
+                            out[(subj, band, freq, 0)] = data
+                    except Exception as e:  # noqa: BLE001 - not HDF5 (or no h5py): MATLAB v5 reader
+                        try:
+                            data = _first_mat_variable(f, flatten=False)
+                            if data is not None:
+                                out[(subj, band, freq, 0)] = data
+                        except Exception:  # noqa: BLE001
+                            logger.warning(f"Error loading ERP {f}: {e}")
+    logger.info(f"Loaded {len(out)} EEG ERP samples")
     return out
 
 

@@ -95,8 +95,185 @@ def case_module(name, module, inputs, extra=None, seed=0, train=True):
     print(f"wrote {name}.npz ({len(store)} arrays)")
 
 
+def case_bridge_xai(bu):
+    """Attribution helpers of the reference (bridge_utils.py:158-270) on the `bridge_small` model: gradient
+    saliency (predicted and given target), integrated gradients (50 and 7 steps; the default target is fixed by
+    the alpha = 0 pass) and the per-subject attention / fusion-weight extraction."""
+    torch.manual_seed(48)
+    br = bu.EEGfMRIBridgeFusionNet(32, 16, 32, 2, 4, 0.0)
+    g = torch.Generator().manual_seed(4848)
+    eeg, fmri = torch.randn(6, 32, generator=g), torch.randn(6, 16, generator=g)
+    given = torch.tensor([1, 0, 1, 1, 0, 0])
+    store = {}
+    _pack(store, "sd", br.state_dict())
+    store.update({"eeg": _np(eeg), "fmri": _np(fmri), "given_target": given.numpy()})
+    sal = bu.BridgeGradientSaliency(br, "cpu")
+    for tag, tc in (("pred", None), ("given", given)):
+        r = sal.compute(eeg, fmri, tc)
+        store[f"saliency_{tag}/eeg"], store[f"saliency_{tag}/fmri"] = r["eeg"], r["fmri"]
+    for n in (50, 7):
+        ig = bu.BridgeIntegratedGradients(br, "cpu", n_steps=n)
+        for tag, tc in (("pred", None), ("given", given)):
+            r = ig.compute(eeg, fmri, tc)
+            store[f"ig{n}_{tag}/eeg"], store[f"ig{n}_{tag}/fmri"] = r["eeg"], r["fmri"]
+    labels = {s: int(s % 2) for s in range(1, 7)}
+    ds = bu.BridgeFeatureDataset({s: eeg[s - 1] for s in labels}, {str(s): fmri[s - 1] for s in labels}, labels, [3, 1, 2, 6, 5, 4, 9])
+    rows = bu.extract_attention_and_fusion_weights(br, ds, "cpu")
+    store["extract/subject"] = np.array([r["subject"] for r in rows])
+    store["extract/label"] = np.array([r["label"] for r in rows])
+    store["extract/prediction"] = np.array([r["prediction"] for r in rows])
+    store["extract/fusion_weights"] = np.stack([r["fusion_weights"] for r in rows])
+    store["extract/attn_weights"] = np.stack([r["attn_weights"] for r in rows])
+    np.savez_compressed(OUT / "bridge_xai.npz", **store)
+    print(f"wrote bridge_xai.npz ({len(store)} arrays)")
+
+
+def _import_reference_eeg_data_utils():
+    """EEG_CODE/eeg_data_utils.py imports h5py, which this image lacks.  The stub's File raises OSError, which is
+    what the real h5py does for a MATLAB v5 (non-HDF5) file -- the only kind the fixtures contain -- so the
+    reference takes its own `scipy.io.loadmat` fallback branch (eeg_data_utils.py:170-183)."""
+    if "h5py" not in sys.modules:
+        stub = types.ModuleType("h5py")
+
+        def _not_hdf5(*a, **k):
+            raise OSError("Unable to open file (file signature not found)")
+
+        stub.File = _not_hdf5
+        sys.modules["h5py"] = stub
+    from EEG_CODE import eeg_data_utils as edu
+    return edu
+
+
+def _reference_bridge_raw_dataset():
+    """`_test_bridge.py` runs the whole pipeline at import, so only the source lines of its BridgeRawDataset class
+    (:391-453) are executed, in a namespace holding the names the class uses."""
+    import logging
+    from collections import defaultdict
+    from torch.utils.data import Dataset
+    lines = (REF / "_test_bridge.py").read_text().splitlines()
+    a = next(i for i, l in enumerate(lines) if l.startswith("class BridgeRawDataset(Dataset):"))
+    b = next(i for i, l in enumerate(lines) if l.startswith("bridge_raw_dataset = BridgeRawDataset("))
+    ns = {"Dataset": Dataset, "defaultdict": defaultdict, "np": np, "logger": logging.getLogger("ref")}
+    exec("\n".join(lines[a:b]), ns)
+    return ns["BridgeRawDataset"]
+
+
+def case_loaders(fu):
+    """On-disk formats either side of the path: writes a small fixture tree under
+    tests/golden/data/ (fMRI CSVs, label CSVs, MATLAB v5 files) and stores what the REFERENCE loaders
+    (fmri_utils.py:115-241, eeg_data_utils.py:19-186) and BridgeRawDataset (_test_bridge.py:391-453) return."""
+    import shutil
+    from scipy.io import savemat
+    root = OUT / "data"
+    if root.exists():
+        shutil.rmtree(root)
+    rng = np.random.default_rng(20261018)
+    fm = root / "fmri"
+    subjects = [1, 2, 3, 5]  # 4 has no directory; 5 has only a broken file
+    for s in (1, 2, 3):
+        d = fm / f"sub-{s}"
+        d.mkdir(parents=True)
+        for t, (tr, roi) in (("taskA", (6, 4)), ("taskB", (5, 3))):
+            if s == 3 and t == "taskB":
+                continue  # missing type for one subject
+            x = rng.standard_normal((tr, roi)).round(4)
+            cols = {f"roi{j}": x[:, j] for j in range(roi)}
+            lines_ = [",".join((["Subject"] if s == 2 else []) + list(cols))]
+            for r in range(tr):
+                cells = [("" if (s == 1 and r == 2 and j == 1) else repr(float(x[r, j]))) for j in range(roi)]  # one NaN cell
+                lines_.append(",".join(([str(s)] if s == 2 else []) + cells))
+            (d / f"subject_{s}_activation_{t}.csv").write_text("\n".join(lines_) + "\n")
+        for t in ("rest", "task"):
+            if s == 2 and t == "task":
+                continue
+            m = rng.standard_normal((4, 4)).round(4)
+            rows = [",".join(f"r{j}" for j in range(4))] + [",".join("" if (i == j == 3) else repr(float(m[i, j])) for j in range(4)) for i in range(4)]
+            (d / f"subject_{s}_fdr_PPI_Connectivity_{t}.csv").write_text("\n".join(rows) + "\n")
+    d5 = fm / "sub-5"
+    d5.mkdir()
+    (d5 / "subject_5_activation_taskA.csv").write_text("a,b\nx,y\nz,w\n")  # not numeric: logged and skipped
+    lab1, lab2, lab3 = root / "labels_str", root / "labels_num" / "inner", root / "labels_bad"
+    for d in (lab1, lab2, lab3):
+        d.mkdir(parents=True)
+    (lab1 / "labels.csv").write_text("Subject,Outcome\n1,Good\n2,bad\n3,YES\n7,positive\n5,1\n")
+    (lab2.parent / "labels.csv").write_text("id,group\n1,0\n2,1\n3,3\n9,1\n")  # found through label_path.parent
+    (lab3 / "outcomes.csv").write_text("who,what\n1,2\n")
+    eeg = root / "eeg"
+    for sub in ("conn", "pw", "erp", "labels"):
+        (eeg / sub).mkdir(parents=True)
+    def mat(path, arr):
+        savemat(path, {"data": arr})
+    nan = np.float32("nan")
+    mat(eeg / "conn" / "conn_Alpha_open_sub01.mat", np.array([[1.0, nan], [0.5, 2.0]], dtype=np.float32))
+    mat(eeg / "conn" / "conn_alpha_close_sub01.mat", rng.standard_normal((2, 2)).astype(np.float32))  # band_key fallback name
+    mat(eeg / "conn" / "conn_Beta_open_sub02.mat", rng.standard_normal((2, 2)).astype(np.float32))
+    mat(eeg / "conn" / "conn_Alpha_open_sub03.mat", rng.standard_normal((2, 2)).astype(np.float32))
+    for s_, band, freq in ((1, "alpha", "1_Hz"), (1, "alpha", "2_Hz"), (2, "beta", "1_Hz")):
+        mat(eeg / "pw" / f"powspctrm_{band}_{freq}_sub{s_:02d}.mat", rng.standard_normal((3, 2)).astype(np.float64))
+    for s_, band, freq, suffix in ((1, "alpha", "1_Hz", ""), (1, "alpha", "2_Hz", "_v2"), (2, "beta", "1_Hz", ""), (3, "alpha", "1_Hz", "")):
+        a = rng.standard_normal((3, 5)).astype(np.float32)
+        a[0, 0] = nan
+        mat(eeg / "erp" / f"ERP_sub{s_:02d}_{band}_{freq}{suffix}.mat", a)
+    (eeg / "erp" / "ERP_sub02_beta_2_Hz.mat").write_bytes(b"not a mat file")  # both readers fail: logged
+    (eeg / "labels" / "medical_score.csv").write_text("Subject,Postoperative evaluation\nsub01,1\nsub02,3\nsub03,\nsub05,2\nsub07,4\n")
+
+    edu = _import_reference_eeg_data_utils()
+    store = {}
+    def put(prefix, d):
+        for k, v in d.items():
+            key = k if not isinstance(k, tuple) else "|".join(map(str, k))
+            store[f"{prefix}/{key}"] = np.asarray(v)
+    with contextlib.redirect_stderr(io.StringIO()):  # tqdm bars
+        for agg in ("both", "mean", "std", "median"):
+            put(f"act_{agg}", fu.load_activation_features(fm, subjects, ["taskA", "taskB"], agg))
+        put("act_both_B_only", fu.load_activation_features(fm, subjects, ["taskB"], "both"))
+        put("conn", fu.load_connectivity_features(fm, subjects, ["rest", "task"]))
+    put("labels_str", fu.load_fmri_labels(lab1, [1, 2, 3, 5]))
+    put("labels_num", fu.load_fmri_labels(lab2, [1, 2, 3]))
+    try:
+        fu.load_fmri_labels(lab3, [1])
+        raise AssertionError("expected ValueError")
+    except ValueError as e:
+        store["labels_bad_error"] = np.array(str(e).replace(str(lab3), "<dir>"))
+    bands = {"alpha": "Alpha", "beta": "Beta"}
+    e_conn = edu.load_eeg_conn_features(eeg / "conn", [1, 2, 3], bands, ["open", "close"])
+    e_pw = edu.load_eeg_pw_features(eeg / "pw", [1, 2, 3], ["alpha", "beta"], ["1_Hz", "2_Hz"])
+    e_erp = edu.load_eeg_erp_features(eeg / "erp", [1, 2, 3], ["alpha", "beta"], ["1_Hz", "2_Hz"])
+    put("eeg_conn", e_conn); put("eeg_pw", e_pw); put("eeg_erp", e_erp)
+    # the reference tests `dtype == object` for 'subNN' ids (eeg_data_utils.py:34): pandas >= 3 infers `str`
+    # instead and the reference then fails on 'sub01'; run it with the inference it was written for
+    import pandas as pd
+    with pd.option_context("future.infer_string", False):
+        put("eeg_labels_binary", edu.load_eeg_labels(eeg / "labels", True))
+        put("eeg_labels_raw", edu.load_eeg_labels(eeg / "labels", False))
+        labels = edu.load_eeg_labels(eeg / "labels", True)
+    # BridgeRawDataset on those dicts
+    RawDS = _reference_bridge_raw_dataset()
+    with contextlib.redirect_stderr(io.StringIO()):
+        f_act = fu.load_activation_features(fm, subjects, ["taskA", "taskB"], "both")
+        f_conn = fu.load_connectivity_features(fm, subjects, ["rest", "task"])
+    labels[3] = 1
+    ds = RawDS(e_erp, e_pw, e_conn, f_act, f_conn, labels, ["3", "2", "1", "5", "4", "10"], bands, ["open", "close"])
+    store["raw_ds/subjects"] = np.array([ds[i][4] for i in range(len(ds))])
+    store["raw_ds/labels"] = np.array([ds[i][3] for i in range(len(ds))])
+    store["raw_ds/n_eeg"] = np.array([len(ds[i][0]) for i in range(len(ds))])
+    for i in range(len(ds)):
+        for j, (erp, pw, conn) in enumerate(ds[i][0]):
+            store[f"raw_ds/{i}/{j}/erp"], store[f"raw_ds/{i}/{j}/pw"], store[f"raw_ds/{i}/{j}/conn"] = erp, pw, conn
+        store[f"raw_ds/{i}/fmri_act"], store[f"raw_ds/{i}/fmri_conn"] = _np(ds[i][1]), _np(ds[i][2])
+    np.savez_compressed(OUT / "loaders.npz", **store)
+    print(f"wrote loaders.npz ({len(store)} arrays) and the fixture tree {root}")
+
+
 def main():
     cm, em, fu, bu = import_reference()
+    only = [a for a in sys.argv[1:] if a in ("xai", "loaders")]  # regenerate only these fixtures
+    if only:
+        if "xai" in only:
+            case_bridge_xai(bu)
+        if "loaders" in only:
+            case_loaders(fu)
+        return
     torch.manual_seed(42)
     g = torch.Generator().manual_seed(42)
     rn = lambda *s: torch.randn(*s, generator=g)
@@ -180,6 +357,9 @@ def main():
     store.update({"eeg": _np(eeg), "fmri": _np(fmri), "labels": y.numpy(), "losses": np.array(losses)})
     np.savez_compressed(OUT / "bridge_train3.npz", **store)
     print("wrote bridge_train3.npz")
+
+    case_bridge_xai(bu)
+    case_loaders(fu)
 
     # --- structural known answers at the BASELINE shapes
     def nparams(m):

@@ -149,6 +149,13 @@ def test_bridge_golden():
     assert float(gb[~keep].abs().max()) < 1e-5
 
 
+def test_bridge_attribution_helpers_golden():
+    """BridgeGradientSaliency / BridgeIntegratedGradients (all interpolation points in one batch) /
+    extract_attention_and_fusion_weights against the reference classes' outputs (bridge_utils.py:158-270)."""
+    from test_host_pipeline_cpu import check_bridge_xai
+    check_bridge_xai("cuda", GTOL)
+
+
 def test_bridge_train_recipe_golden():
     """3 steps of CE -> backward -> clip_grad_norm_(1.0) -> AdamW(1e-4, wd 1e-4) through
     train_bridge_epoch reproduce the reference's losses and parameters (_test_bridge.py:775-788,869)."""

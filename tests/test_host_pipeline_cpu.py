@@ -115,3 +115,48 @@ def test_fused_transformer_tail_autograd_vs_oracle(fakes):
     assert_close_rel(xg.grad, xo.grad, 2e-4, "dx")
     for k, p in m.named_parameters():
         assert_close_rel(p.grad, leaves[k].grad, 2e-4, f"grad {k}", atol=1e-6)
+
+
+def _xai_fixture():
+    import numpy as np
+    from conftest import GOLDEN
+    from multimodal_eeg_fmri_b200 import bridge_utils as bu
+    z = np.load(GOLDEN / "bridge_xai.npz")
+    m = bu.EEGfMRIBridgeFusionNet(32, 16, 32, 2, 4, 0.0)
+    m.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}, strict=True)
+    return bu, z, m, torch.from_numpy(z["eeg"]), torch.from_numpy(z["fmri"]), torch.from_numpy(z["given_target"])
+
+
+def check_bridge_xai(device, tol):
+    """Shared by the CPU (fake ops) and GPU tests: batched saliency / integrated gradients / weight extraction
+    against the REAL reference classes' outputs (tests/golden/bridge_xai.npz, bridge_utils.py:158-270)."""
+    import numpy as np
+    bu, z, m, eeg, fmri, given = _xai_fixture()
+    m = m.to(device)
+    sal = bu.BridgeGradientSaliency(m, device)
+    for tag, tc in (("pred", None), ("given", given)):
+        r = sal.compute(eeg, fmri, tc)
+        assert_close_rel(r["eeg"], z[f"saliency_{tag}/eeg"], tol, f"saliency {tag} eeg")
+        assert_close_rel(r["fmri"], z[f"saliency_{tag}/fmri"], tol, f"saliency {tag} fmri")
+    for n in (50, 7):
+        ig = bu.BridgeIntegratedGradients(m, device, n_steps=n)
+        for tag, tc in (("pred", None), ("given", given)):
+            r = ig.compute(eeg, fmri, tc)
+            assert r["eeg"].shape == (6, 32) and r["fmri"].shape == (6, 16)
+            assert_close_rel(r["eeg"], z[f"ig{n}_{tag}/eeg"], tol, f"IG{n} {tag} eeg")
+            assert_close_rel(r["fmri"], z[f"ig{n}_{tag}/fmri"], tol, f"IG{n} {tag} fmri")
+    labels = {s: int(s % 2) for s in range(1, 7)}
+    ds = bu.BridgeFeatureDataset({s: eeg[s - 1] for s in labels}, {str(s): fmri[s - 1] for s in labels}, labels,
+                                 [3, 1, 2, 6, 5, 4, 9])
+    rows = bu.extract_attention_and_fusion_weights(m, ds, device)
+    assert [r["subject"] for r in rows] == z["extract/subject"].tolist()  # bit-exact integer work
+    assert [r["label"] for r in rows] == z["extract/label"].tolist()
+    assert [r["prediction"] for r in rows] == z["extract/prediction"].tolist()
+    assert rows[0]["fusion_weights"].shape == (2,) and rows[0]["attn_weights"].shape == (2,)
+    assert_close_rel(np.stack([r["fusion_weights"] for r in rows]), z["extract/fusion_weights"], tol, "fusion weights")
+    assert_close_rel(np.stack([r["attn_weights"] for r in rows]), z["extract/attn_weights"], tol, "attention weights")
+    assert bu.extract_attention_and_fusion_weights(m, bu.BridgeFeatureDataset({}, {}, {}, []), device) == []
+
+
+def test_bridge_attribution_helpers_vs_reference_golden(fakes):
+    check_bridge_xai("cpu", 1e-5)

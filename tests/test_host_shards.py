@@ -1,0 +1,128 @@
+"""The binary shard format (multimodal_eeg_fmri_b200/shards.py): byte-exact round trips, alignment, ragged batches,
+batch sharding across ranks, corrupt / truncated files, and the reference dataset -> shard conversion."""
+import json
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from multimodal_eeg_fmri_b200 import shards
+
+
+def _arrays(n=10, seed=0):
+    g = np.random.default_rng(seed)
+    return {"eeg": g.standard_normal((n, 3, 7)).astype(np.float32), "roi": g.standard_normal((n, 5)).astype(np.float32),
+            "label": g.integers(0, 2, n).astype(np.int64), "mask": g.integers(0, 255, (n, 2)).astype(np.uint8),
+            "idx32": np.arange(n, dtype=np.int32)}
+
+
+def test_round_trip_is_byte_exact_and_aligned(tmp_path):
+    a = _arrays()
+    a["eeg"][0, 0, 0] = np.nan  # payload bytes are opaque: NaN bit patterns survive
+    size = shards.write_shard(tmp_path / "s.xms", a, meta={"fs": 1000, "bands": ["theta", "alpha"]})
+    sh = shards.Shard(tmp_path / "s.xms")
+    assert size == (tmp_path / "s.xms").stat().st_size and size % shards.ALIGN == 0
+    assert len(sh) == 10 and sh.names() == list(a) and sh.meta == {"fs": 1000, "bands": ["theta", "alpha"]}
+    for k, v in a.items():
+        assert sh.arrays[k]["offset"] % shards.ALIGN == 0
+        got = sh[k]
+        assert got.dtype == v.dtype and got.shape == v.shape and got.tobytes() == v.tobytes()
+    assert not (tmp_path / "s.xms.tmp").exists()
+
+
+def test_torch_and_big_endian_inputs_are_normalised(tmp_path):
+    x = np.arange(12, dtype=">f4").reshape(4, 3)
+    shards.write_shard(tmp_path / "s.xms", {"x": x, "t": torch.arange(4, dtype=torch.int64)})
+    sh = shards.Shard(tmp_path / "s.xms")
+    assert sh["x"].dtype == np.dtype("<f4") and np.array_equal(sh["x"], x.astype(np.float32))
+    assert np.array_equal(sh["t"], np.arange(4))
+
+
+def test_read_rows_and_host_batches_ragged_and_sharded(tmp_path):
+    a = _arrays(n=11, seed=1)
+    shards.write_shard(tmp_path / "s.xms", a)
+    sh = shards.Shard(tmp_path / "s.xms")
+    bufs = sh.alloc_host(["eeg", "label"], 4, pin=False)
+    got = sh.read_rows(8, 11, bufs)  # ragged tail: 3 rows into 4-row buffers
+    assert got["eeg"].shape == (3, 3, 7) and torch.equal(got["eeg"], torch.from_numpy(a["eeg"][8:11]))
+    assert got["label"].dtype == torch.int64 and torch.equal(got["label"], torch.from_numpy(a["label"][8:11]))
+    assert sh.read_rows(5, 5, bufs)["eeg"].shape[0] == 0
+    with pytest.raises(IndexError):
+        sh.read_rows(8, 12, bufs)
+    with pytest.raises(shards.ShardError):
+        sh.read_rows(0, 5, bufs)  # buffers too small
+    full = list(shards.host_batches(sh, ["eeg", "roi"], 4, pin=False))
+    assert [b[0].shape[0] for b in full] == [4, 4]  # drop_last
+    tail = list(shards.host_batches(sh, ["eeg", "roi"], 4, drop_last=False, pin=False))
+    assert [b[0].shape[0] for b in tail] == [4, 4, 3] and torch.equal(tail[2][1], torch.from_numpy(a["roi"][8:]))
+    # batch sharding across two ranks covers every full batch exactly once, in order per rank
+    r0 = list(shards.host_batches(sh, ["label"], 2, pin=False, ranks=(0, 2)))
+    r1 = list(shards.host_batches(sh, ["label"], 2, pin=False, ranks=(1, 2)))
+    seen = torch.cat([b[0] for pair in zip(r0, r1 + [None]) for b in pair if b is not None])
+    assert len(r0) == 3 and len(r1) == 2 and torch.equal(seen, torch.from_numpy(a["label"][:10]))
+
+
+def test_empty_and_invalid_inputs(tmp_path):
+    shards.write_shard(tmp_path / "e.xms", {"x": np.empty((0, 4), np.float32)})
+    sh = shards.Shard(tmp_path / "e.xms")
+    assert len(sh) == 0 and sh["x"].shape == (0, 4) and list(shards.host_batches(sh, ["x"], 4, pin=False)) == []
+    for bad in ({}, {"x": np.zeros((2, 2), np.float64)}, {"x": np.float32(1.0)}, {"x": np.zeros((2, 1), np.float32), "y": np.zeros((3, 1), np.float32)}):
+        with pytest.raises(shards.ShardError):
+            shards.write_shard(tmp_path / "bad.xms", bad)
+    with pytest.raises(shards.ShardError):
+        shards.Shard(tmp_path / "e.xms").to_device(["x"], device="cpu")
+
+
+def test_corrupt_and_truncated_files_are_rejected(tmp_path):
+    p = tmp_path / "s.xms"
+    shards.write_shard(p, _arrays())
+    raw = p.read_bytes()
+    (tmp_path / "magic.xms").write_bytes(b"NOTSHARD" + raw[8:])
+    (tmp_path / "short.xms").write_bytes(raw[:10])
+    (tmp_path / "trunc.xms").write_bytes(raw[:-shards.ALIGN])
+    (tmp_path / "hdr.xms").write_bytes(raw[:16] + b"\xff" * 32 + raw[48:])
+    (hlen,) = struct.unpack("<Q", raw[8:16])
+    header = json.loads(raw[16:16 + hlen])
+    header["version"] = 2
+    blob = json.dumps(header).encode()
+    (tmp_path / "ver.xms").write_bytes(raw[:8] + struct.pack("<Q", len(blob)) + blob + raw[16 + len(blob):])
+    (tmp_path / "hlen.xms").write_bytes(raw[:8] + struct.pack("<Q", 1 << 40) + raw[16:])
+    for name in ("magic", "short", "trunc", "hdr", "ver", "hlen"):
+        with pytest.raises(shards.ShardError):
+            shards.Shard(tmp_path / f"{name}.xms")
+
+
+def test_pack_bridge_raw_dataset(tmp_path):
+    g = np.random.default_rng(3)
+    rows = [([(g.standard_normal((4, 6)).astype(np.float32), g.standard_normal(5).astype(np.float32), g.standard_normal(3).astype(np.float32))
+              for _ in range(1 + s % 2)], torch.from_numpy(g.standard_normal(8).astype(np.float32)),
+             torch.from_numpy(g.standard_normal(16).astype(np.float32)), s % 2, 10 + s) for s in range(5)]
+    shards.pack_bridge_raw_dataset(tmp_path / "b.xms", rows, meta={"source": "test"})
+    sh = shards.Shard(tmp_path / "b.xms")
+    assert sh.names() == ["erp", "pw", "conn", "fmri_act", "fmri_conn", "label", "subject"] and len(sh) == 5
+    assert np.array_equal(sh["subject"], np.arange(10, 15)) and np.array_equal(sh["label"], np.array([0, 1, 0, 1, 0]))
+    for i, r in enumerate(rows):
+        assert np.array_equal(sh["erp"][i], r[0][0][0]) and np.array_equal(sh["fmri_conn"][i], r[2].numpy())
+    rows[2] = (rows[2][0], torch.zeros(9), rows[2][2], 0, 12)
+    with pytest.raises(shards.ShardError):
+        shards.pack_bridge_raw_dataset(tmp_path / "c.xms", rows)
+    with pytest.raises(shards.ShardError):
+        shards.pack_bridge_raw_dataset(tmp_path / "d.xms", [])
+
+
+@pytest.mark.gpu
+def test_shard_to_device_and_pinned_batches(tmp_path):
+    a = _arrays(n=64, seed=5)
+    shards.write_shard(tmp_path / "s.xms", a)
+    sh = shards.Shard(tmp_path / "s.xms")
+    side = torch.cuda.Stream()
+    dev = sh.to_device(["eeg", "label"], 8, 40, stream=side)
+    side.synchronize()
+    assert dev["eeg"].is_cuda and torch.equal(dev["eeg"].cpu(), torch.from_numpy(a["eeg"][8:40]))
+    assert torch.equal(dev["label"].cpu(), torch.from_numpy(a["label"][8:40]))
+    again = sh.to_device(["roi"])  # second call waits for the first staging buffers, default stream
+    torch.cuda.synchronize()
+    assert torch.equal(again["roi"].cpu(), torch.from_numpy(a["roi"]))
+    batches = list(shards.host_batches(sh, ["eeg", "roi"], 16))
+    assert len(batches) == 4 and all(t.is_pinned() for b in batches for t in b)
