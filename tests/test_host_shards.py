@@ -126,3 +126,32 @@ def test_shard_to_device_and_pinned_batches(tmp_path):
     assert torch.equal(again["roi"].cpu(), torch.from_numpy(a["roi"]))
     batches = list(shards.host_batches(sh, ["eeg", "roi"], 16))
     assert len(batches) == 4 and all(t.is_pinned() for b in batches for t in b)
+
+
+def test_random_shards_round_trip_and_row_ranges(tmp_path):
+    """Property test (hypothesis): any mix of supported dtypes / trailing shapes survives the file byte for byte, and
+    any row range read through `read_rows` equals the slice of the source."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    dtypes = st.sampled_from([np.float32, np.int64, np.int32, np.uint8])
+    tails = st.lists(st.integers(0, 5), min_size=0, max_size=3)
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(rows=st.integers(0, 37), specs=st.lists(st.tuples(dtypes, tails), min_size=1, max_size=4), seed=st.integers(0, 2 ** 31),
+           cut=st.tuples(st.integers(0, 37), st.integers(0, 37)))
+    def run(rows, specs, seed, cut):
+        g = np.random.default_rng(seed)
+        arrays = {f"a{i}": (g.integers(0, 200, (rows, *tail)).astype(dt) if dt is not np.float32 else
+                            g.standard_normal((rows, *tail)).astype(np.float32)) for i, (dt, tail) in enumerate(specs)}
+        path = tmp_path / "p.xms"
+        shards.write_shard(path, arrays, meta={"seed": seed})
+        sh = shards.Shard(path)
+        assert len(sh) == rows and sh.meta == {"seed": seed}
+        for k, v in arrays.items():
+            assert sh[k].shape == v.shape and sh[k].dtype == v.dtype and sh[k].tobytes() == v.tobytes()
+        lo, hi = sorted(min(c, rows) for c in cut)
+        got = sh.read_rows(lo, hi, sh.alloc_host(list(arrays), hi - lo, pin=False))
+        for k, v in arrays.items():
+            assert got[k].numpy().tobytes() == v[lo:hi].tobytes()
+
+    run()
