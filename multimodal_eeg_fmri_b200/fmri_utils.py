@@ -63,7 +63,7 @@ def load_activation_features(data_dir, subject_list, activation_types, agg_metho
     CUDA device) over all files of one (TR, ROI) shape at once."""
     data_dir = Path(data_dir)
     parsed = []  # (subject, position, series)
-    for subj in subject_list:
+    for subj in dict.fromkeys(subject_list):  # a repeated subject is loaded once (the reference overwrites its entry)
         subj_dir = data_dir / f"sub-{subj}"
         for pos, act_type in enumerate(activation_types):
             filepath = subj_dir / f"subject_{subj}_activation_{act_type}.csv"

@@ -71,6 +71,9 @@ def test_activation_features_vs_reference(gold, monkeypatch, caplog):
     assert _group(gold, "act_median") == {}
     assert fu.load_activation_features(FM, SUBJECTS, ["taskA", "taskB"], "median", device="cpu") == {}
     assert fu.load_activation_features(FM, [], ["taskA"], device="cpu") == {}
+    twice = fu.load_activation_features(FM, [2, 1, 2], ["taskA", "taskB"], device="cpu")  # repeated subject: one entry
+    assert list(twice) == [2, 1]
+    _same_dict({2: twice[2]}, {"2": gold["act_both/2"]}, exact=False, what="repeated subject")
     with pytest.raises(ValueError):
         fu.aggregate_roi_timeseries(torch.zeros(1, 2, 3), "median")
 
