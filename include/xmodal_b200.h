@@ -303,6 +303,18 @@ int xm_attn_fused_bwd_f32(const float* dout, const float* qkv, const float* out,
                           int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed,
                           int round_out, void* stream);
 int xm_attn_fused_mask_u8(uint8_t* mask, int64_t B, int64_t L, int64_t H, float drop_p, uint64_t seed, void* stream);
+/* Shape-general variant (csrc/attention_general.cu; SIMT fp32): every shape the fused kernel does not cover --
+ * head dim <= 256, any L with xm_attn_general_supported(L, dh) != 0 -- plus nn.MultiheadAttention's attn_mask
+ * (EEG_CODE/enhanced_models_v4.py:89,98 passes `mask` through): `mask` is ADDITIVE fp32 (-inf = not allowed to
+ * attend), shape (L, L) when mask_per_head == 0 or (B*H, L, L) when 1, or NULL.  A fully masked row yields NaN, as
+ * torch's softmax does.  lse / delta: (B*H, L).  Dropout mask = hash(seed, (bh*L + query)*L + key). */
+int xm_attn_general_supported(int64_t L, int64_t dh);
+int xm_attn_general_fwd_f32(const float* qkv, const float* mask, int mask_per_head, float* out, float* lse, int64_t B,
+                            int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, int round_out,
+                            void* stream);
+int xm_attn_general_bwd_f32(const float* dout, const float* qkv, const float* mask, int mask_per_head, const float* lse,
+                            float* dqkv, float* delta, int64_t B, int64_t L, int64_t H, int64_t dh, float scale,
+                            float drop_p, uint64_t seed, int round_out, void* stream);
 /* Debug: when non-NULL, CTA 0 of the fused attention kernels appends clock64() stamps at its phase boundaries
  * (3 roles x 4096 slots of int64). */
 int xm_debug_set_attn_trace(int64_t* device_buffer);

@@ -65,15 +65,22 @@ class BridgeRawDataset(Dataset):
     (`bands` is accepted and unused, as in the reference.)"""
 
     def __init__(self, eeg_erp, eeg_pw, eeg_conn, fmri_act, fmri_conn, labels, subject_list, bands, func_segments):
-        pad_pw = next((np.zeros(v.shape, dtype=np.float32) for v in eeg_pw.values()), None)
-        pad_conn = next((np.zeros(v.shape, dtype=np.float32) for v in eeg_conn.values()), None)
+        # shapes of the zero stand-ins; a FRESH array per missing entry as in the reference (:416-421), so samples
+        # never alias each other (an in-place normalisation of one padded sample must not touch the others)
+        pw_shape = next((v.shape for v in eeg_pw.values()), None)
+        conn_shape = next((v.shape for v in eeg_conn.values()), None)
         eeg_by_subject = {}
         for key, erp in eeg_erp.items():
             sid = key[0] if isinstance(key[0], int) else int(key[0])
-            pw = eeg_pw.get(key, pad_pw)
+            pw = eeg_pw.get(key)
+            if pw is None and pw_shape is not None:
+                pw = np.zeros(pw_shape, dtype=np.float32)
             band = str(key[1]).lower()
             hit = next((c for c in func_segments if (key[0], band, c, key[3]) in eeg_conn), None)
-            conn = pad_conn if hit is None else eeg_conn[(key[0], band, hit, key[3])]
+            if hit is not None:
+                conn = eeg_conn[(key[0], band, hit, key[3])]
+            else:
+                conn = None if conn_shape is None else np.zeros(conn_shape, dtype=np.float32)
             if pw is not None and conn is not None:
                 eeg_by_subject.setdefault(sid, []).append((erp, pw, conn))
         self.samples = []

@@ -24,9 +24,9 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC",
-    "-cudart", "static",
-    "-shared",
 ]
+LINK_FLAGS = ["-cudart", "static", "-shared"]
+OBJ_DIR = PKG_DIR.parent / "build" / "obj"  # git-ignored; per-file objects keyed by a hash of source + headers + flags
 
 
 def _nvcc() -> str:
@@ -45,8 +45,16 @@ def _fingerprint() -> str:
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "xmodal_b200.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + LINK_FLAGS).encode())
     return h.hexdigest()
+
+
+def _object_key(src: Path, extra) -> str:
+    h = hashlib.sha256(src.read_bytes())
+    for p in sorted(list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "xmodal_b200.h"]):
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS + list(extra)).encode())
+    return h.hexdigest()[:20]
 
 
 def is_current() -> bool:
@@ -57,17 +65,35 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile the library if sources changed; returns the .so path."""
     if not force and is_current():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
     OUT_DIR.mkdir(exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("XM_NVCC_FLAGS", "").split()]  # e.g. -DXM_FA_TRACE (with --force)
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    extra = os.environ.get("XM_NVCC_FLAGS", "").split()  # e.g. -DXM_FA_TRACE (with --force)
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB_PATH), *map(str, _sources())]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        extra += ["-Xptxas", "-v"]
+
+    def compile_one(src: Path) -> Path:
+        obj = OBJ_DIR / f"{src.stem}.{_object_key(src, extra)}.o"
+        if obj.exists() and not force and not verbose:
+            return obj
+        res = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra, "-c", "-o", str(obj), str(src)], capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"nvcc failed on {src.name}")
+        if verbose:
+            sys.stderr.write(f"== {src.name}\n" + res.stdout + res.stderr)
+        for old in OBJ_DIR.glob(f"{src.stem}.*.o"):  # drop objects of earlier versions of this file
+            if old != obj:
+                old.unlink()
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:  # one nvcc per translation unit
+        objs = list(pool.map(compile_one, _sources()))
+    res = subprocess.run([_nvcc(), *NVCC_FLAGS, *LINK_FLAGS, "-o", str(LIB_PATH), *map(str, objs)], capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libxmodal_b200.so")
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libxmodal_b200.so")
     STAMP.write_text(_fingerprint())
     return LIB_PATH
 

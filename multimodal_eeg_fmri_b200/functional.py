@@ -85,11 +85,14 @@ def _bn_stats(y, eps, running_mean, running_var, momentum, training):
     if not training:
         invstd = torch.rsqrt(running_var + eps)
         return running_mean, invstd, float(rows)
-    part = ops.bn_partial_stats(y)
     count = float(rows)
     if _CTX.active and _CTX.sync_bn:
-        part = _allreduce_sum(part.sum(0, keepdim=True))
         count *= _CTX.world
+    if count <= 1:  # torch.nn.functional.batch_norm raises here too (the batch variance is undefined)
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(y.shape)}")
+    part = ops.bn_partial_stats(y)
+    if _CTX.active and _CTX.sync_bn:
+        part = _allreduce_sum(part.sum(0, keepdim=True))
     mean, invstd = ops.bn_finalize_stats(part, count, eps, running_mean, running_var, momentum)
     return mean, invstd, count
 
@@ -164,11 +167,21 @@ class ConvBnAct(torch.autograd.Function):
         return dx, dw, db, dgamma, dbeta, None, None, None
 
 
-def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=False, training=True, round_out=True):
-    """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d)."""
+def _bn_momentum(bn, training) -> float:
+    """nn.BatchNorm1d's running-statistics factor for this call: counts the batch, and `momentum=None` means the
+    cumulative moving average 1 / num_batches_tracked (torch/nn/modules/batchnorm.py)."""
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    cfg = (bn.eps, bn.momentum if bn.momentum is not None else 0.1, act, pool, float(drop_p), bool(drop_before_pool),
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    if training and bn.num_batches_tracked is not None:
+        return 1.0 / float(bn.num_batches_tracked.item())
+    return 0.0
+
+
+def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=False, training=True, round_out=True):
+    """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d)."""
+    cfg = (bn.eps, _bn_momentum(bn, training), act, pool, float(drop_p), bool(drop_before_pool),
            bool(training), bool(round_out))
     return ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
 
@@ -236,6 +249,8 @@ class ActDropout(torch.autograd.Function):
 
 def act_dropout(x, act, drop_p=0.0, training=True):
     p = float(drop_p) if training else 0.0
+    if p == 0.0 and act in (None, "none", 0):
+        return x  # identity (a bare nn.Dropout in eval mode / with p = 0)
     return ActDropout.apply(x, act, p, next_seed() if p > 0 else 0)
 
 
@@ -294,9 +309,7 @@ class LinearBnAct(torch.autograd.Function):
 
 
 def linear_bn_act(x, lin, bn, act="relu", drop_p=0.0, training=True):
-    if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-    cfg = (bn.eps, bn.momentum if bn.momentum is not None else 0.1, act, float(drop_p), bool(training))
+    cfg = (bn.eps, _bn_momentum(bn, training), act, float(drop_p), bool(training))
     return LinearBnAct.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
 
 
@@ -358,6 +371,79 @@ def self_attention_core(qkv, nhead, drop_p=0.0, training=True):
 
 def attention_core_supported(L: int, dh: int) -> bool:
     return ops.attn_supported(L, dh)
+
+
+class GeneralAttentionCore(torch.autograd.Function):
+    """The same attention core for the shapes the fused tcgen05 kernel does not cover (head dim != 32, L > 512) and
+    for nn.MultiheadAttention's `attn_mask` (enhanced_models_v4.py:89,98): csrc/attention_general.cu, fp32 SIMT,
+    scores recomputed in the backward from the saved logsumexp.  `mask`: additive fp32 (L, L) | (B*H, L, L) | None."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, nhead, p, seed):
+        scale = 1.0 / ((qkv.shape[2] // 3 // nhead) ** 0.5)
+        out, lse = ops.attn_general_fwd(qkv, nhead, scale, mask, p, seed)
+        ctx.save_for_backward(qkv, lse, mask) if mask is not None else ctx.save_for_backward(qkv, lse)
+        ctx.meta = (nhead, scale, p, seed, mask is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        nhead, scale, p, seed, has_mask = ctx.meta
+        qkv, lse = ctx.saved_tensors[:2]
+        mask = ctx.saved_tensors[2] if has_mask else None
+        return ops.attn_general_bwd(dout.contiguous(), qkv, lse, nhead, scale, mask, p, seed), None, None, None, None
+
+
+def general_attention_core(qkv, nhead, mask=None, drop_p=0.0, training=True):
+    p = float(drop_p) if training else 0.0
+    return GeneralAttentionCore.apply(qkv, mask, nhead, p, next_seed() if p > 0 else 0)
+
+
+def general_attention_supported(L: int, dh: int) -> bool:
+    return ops.attn_general_supported(L, dh)
+
+
+def additive_attention_mask(mask, B: int, nhead: int, L: int):
+    """nn.MultiheadAttention's `attn_mask` -> the additive fp32 mask of the attention kernels: a boolean (or uint8)
+    mask marks positions that may NOT be attended with True (-> -inf); a float mask is added to the scores as is.
+    Accepted shapes, as in torch: (L, L) or (B * num_heads, L, L)."""
+    if mask is None:
+        return None
+    if tuple(mask.shape) not in ((L, L), (B * nhead, L, L)):
+        raise ValueError(f"attn_mask of shape {tuple(mask.shape)}: expected ({L}, {L}) or ({B * nhead}, {L}, {L})")
+    if mask.dtype in (torch.bool, torch.uint8):
+        return torch.zeros(mask.shape, device=mask.device, dtype=torch.float32).masked_fill_(mask.bool(), float("-inf"))
+    if not mask.is_floating_point():
+        raise ValueError(f"attn_mask dtype {mask.dtype}: only bool, uint8 and floating-point masks are defined")
+    return mask.to(torch.float32)
+
+
+class LayerNormAct(torch.autograd.Function):
+    """LayerNorm -> act -> Dropout over (M, D) rows for any D (nn.LayerNorm; the fused residual kernels cover only
+    D % 128 == 0)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, cfg):
+        eps, act, p, seed = cfg
+        out, mean, rstd = ops.ln_act_fwd(x, gamma, beta, eps, act, p, seed)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.meta = (act, p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        act, p, seed = ctx.meta
+        dx, dgamma, dbeta = ops.ln_act_bwd(dout.contiguous(), x, gamma, beta, mean, rstd, act, p, seed)
+        return dx, dgamma, dbeta, None
+
+
+def layer_norm(x, ln, act=None, drop_p=0.0, training=True):
+    """ln: nn.LayerNorm used as a parameter container; x: (..., D)."""
+    p = float(drop_p) if training else 0.0
+    shape = x.shape
+    out = LayerNormAct.apply(x.reshape(-1, shape[-1]), ln.weight, ln.bias, (ln.eps, act, p, next_seed() if p > 0 else 0))
+    return out.view(shape)
 
 
 # ----------------------------------------------------------------------------- transformer tail

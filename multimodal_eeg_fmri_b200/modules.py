@@ -3,9 +3,12 @@
 Same class names, constructor / forward signatures and `state_dict` keys as the reference
 (SURVEY.md section 8b), so reference checkpoints load with strict=True.  torch.nn layer objects are used
 ONLY as parameter containers (identical initialisation and key names); their forwards are never
-called on the conv / projection / loss path -- that runs through multimodal_eeg_fmri_b200.functional
-(hand-written sm_100a kernels).  The transformer tail of the v4 encoders stays on PyTorch ops in this
-round.  CUDA tensors only: there is no CPU fallback.
+called -- every conv / projection / normalisation / attention / loss runs through
+multimodal_eeg_fmri_b200.functional (hand-written sm_100a kernels).  The transformer tail of the v4 encoders is one
+fused autograd function at the BASELINE shapes (d_model % 128 == 0, head dim 32, L <= 512) and a chain of the
+shape-general kernels (LayerNorm, SIMT attention core with attn_mask support) everywhere else; torch supplies only
+glue (residual adds, cat, tiny softmaxes over 2 gate values).  CUDA tensors only: there is no CPU fallback and no
+library-attention fallback -- shapes no kernel covers raise XmodalError.
 """
 from __future__ import annotations
 
@@ -17,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as XF
+from ._lib import XmodalError
 
 
 class Slots(nn.Module):
@@ -35,7 +39,7 @@ class Slots(nn.Module):
         raise RuntimeError("Slots is a parameter container; the owning module implements forward")
 
 
-# ------------------------------------------------------------------------- transformer tail (PyTorch)
+# ------------------------------------------------------------------------- transformer tail
 class PositionalEncoding(nn.Module):
     """EEG_CODE/enhanced_models_v4.py:30-55 -- sinusoidal table `pe` (max_len, 1, d) + dropout."""
 
@@ -52,15 +56,17 @@ class PositionalEncoding(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() == 3 and x.size(1) != 1:  # batch-first (B, L, d)
             x = x + self.pe[: x.size(1), 0, :].unsqueeze(0)
-        else:
+        else:  # sequence-first layout -- also what a batch-first input with L == 1 hits in the reference (:49-52)
             x = x + self.pe[: x.size(0)]
-        return F.dropout(x, self.p, self.training)
+        return XF.act_dropout(x, None, self.p, self.training)
 
 
 class TemporalTransformerBlock(nn.Module):
-    """EEG_CODE/enhanced_models_v4.py:58-107 -- pre-norm MHA + GELU FFN residual block.  Attention
-    runs through scaled_dot_product_attention (the reference's need_weights=True path materialises
-    (B, L, L) weights it then discards)."""
+    """EEG_CODE/enhanced_models_v4.py:58-107 -- pre-norm MHA + GELU FFN residual block, standalone form (the v4
+    encoders run their blocks through the fused XF.TransformerTail when the shape allows).  `mask` has
+    nn.MultiheadAttention's attn_mask semantics (bool True = may NOT attend; float = additive; (L, L) or
+    (B*H, L, L)).  The reference's need_weights=True path materialises (B, L, L) weights it then discards; no kernel
+    here stores them."""
 
     def __init__(self, d_model: int, nhead: int = 4, dim_feedforward: int = 512, dropout: float = 0.1,
                  activation: str = "gelu"):
@@ -74,23 +80,26 @@ class TemporalTransformerBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, L, d = x.shape
+        dh = d // self.nhead
         lin = XF.Linear.apply  # the four projections: single-pass tf32 tcgen05 GEMMs over (B*L, d) rows
-        h = F.layer_norm(x, (d,), self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        qkv = lin(h.reshape(B * L, d), self.self_attn.in_proj_weight, self.self_attn.in_proj_bias, True).view(B, L, 3 * d)
-        fused = mask is None and XF.attention_core_supported(L, d // self.nhead)
+        h = XF.layer_norm(x, self.norm1).reshape(B * L, d)
+        qkv = lin(h, self.self_attn.in_proj_weight, self.self_attn.in_proj_bias, True).view(B, L, 3 * d)
+        fused = mask is None and XF.attention_core_supported(L, dh)
         if fused:  # the fused core writes tf32-rounded head outputs (operand of out_proj)
-            a = XF.self_attention_core(qkv, self.nhead, self.p, self.training).reshape(B * L, d)
-        else:  # shapes outside the fused kernel (head dim != 32, L > 512, explicit mask): library attention
-            q, k, v = (t.view(B, L, self.nhead, d // self.nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
-            a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=self.p if self.training else 0.0)
-            a = a.transpose(1, 2).reshape(B * L, d)
-        a = lin(a, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, False, fused).view(B, L, d)
-        x = x + F.dropout(a, self.p, self.training)
-        h = F.layer_norm(x, (d,), self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        h = lin(h.reshape(B * L, d), self.linear1.weight, self.linear1.bias)
+            a = XF.self_attention_core(qkv, self.nhead, self.p, self.training)
+        elif XF.general_attention_supported(L, dh):
+            a = XF.general_attention_core(qkv, self.nhead, XF.additive_attention_mask(mask, B, self.nhead, L), self.p,
+                                          self.training)
+        else:
+            raise XmodalError(f"no attention kernel covers L = {L}, head dim = {dh} (fused: head dim 32, L <= 512, no "
+                              "mask; general: head dim <= 256 and the score rows of 4 queries within shared memory)")
+        a = lin(a.reshape(B * L, d), self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, False, fused).view(B, L, d)
+        x = x + XF.act_dropout(a, None, self.p, self.training)
+        h = XF.layer_norm(x, self.norm2).reshape(B * L, d)
+        h = lin(h, self.linear1.weight, self.linear1.bias)
         h = XF.act_dropout(h, self.act, self.p, self.training)  # GELU + Dropout in one pass
         h = lin(h, self.linear2.weight, self.linear2.bias).view(B, L, d)
-        return x + F.dropout(h, self.p, self.training)
+        return x + XF.act_dropout(h, None, self.p, self.training)
 
 
 class _TransformerTail(nn.Module):
@@ -107,7 +116,8 @@ class _TransformerTail(nn.Module):
         B, L, D = h.shape
         blocks = list(self.transformer_layers)
         b0 = blocks[0] if blocks else None
-        if b0 is not None and XF.transformer_tail_supported(L, D, b0.nhead, b0.act) and L <= self.pos_encoder.pe.shape[0]:
+        if (b0 is not None and L > 1 and XF.transformer_tail_supported(L, D, b0.nhead, b0.act)
+                and L <= self.pos_encoder.pe.shape[0]):
             # fused tail: PE + blocks + mean-pool as one function over the token matrix
             params = []
             for blk in blocks:
@@ -116,7 +126,8 @@ class _TransformerTail(nn.Module):
                            blk.linear1.weight, blk.linear1.bias, blk.linear2.weight, blk.linear2.bias]
             cfg = (b0.nhead, self.dropout_p, b0.norm1.eps, b0.act, self.training)
             h = XF.TransformerTail.apply(h.contiguous(), self.pos_encoder.pe[:L, 0, :].contiguous(), cfg, *params)
-        else:  # shapes outside the fused kernels (head dim != 32, L > 512, d_model % 128 != 0)
+        else:  # shapes outside the fused tail (head dim != 32, L > 512, d_model % 128 != 0, and L == 1, where the
+            # reference's PositionalEncoding indexes its table by SAMPLE): block by block on the shape-general kernels
             h = self.pos_encoder(h)
             for blk in blocks:
                 h = blk(h)

@@ -707,6 +707,43 @@ def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_
     return dqkv
 
 
+def attn_general_supported(L: int, dh: int) -> bool:
+    return bool(_lib.lib().xm_attn_general_supported(int(L), int(dh)))
+
+
+def attn_general_fwd(qkv, nhead, scale, mask=None, drop_p=0.0, seed=0, round_out=False):
+    """Shape-general attention core (any head dim <= 256, optional additive mask (L, L) or (B*H, L, L))."""
+    _chk(qkv, mask)
+    qkv = qkv.contiguous()
+    B, L, E = qkv.shape
+    d = E // 3
+    dh = d // nhead
+    if mask is not None:
+        mask = mask.contiguous()
+        if tuple(mask.shape) not in ((L, L), (B * nhead, L, L)):
+            raise _lib.XmodalError(f"attention mask {tuple(mask.shape)}: expected ({L}, {L}) or ({B * nhead}, {L}, {L})")
+    out = torch.empty(B, L, d, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * nhead, L, device=qkv.device, dtype=torch.float32)
+    _w(4.0 * B * nhead * L * L * dh, 4.0 * (qkv.numel() + out.numel()))
+    _call("xm_attn_general_fwd_f32", _p(qkv), _p(mask), int(mask is not None and mask.dim() == 3), _p(out), _p(lse), B, L, nhead,
+          dh, float(scale), float(drop_p), int(seed), int(round_out), _stream())
+    return out, lse
+
+
+def attn_general_bwd(dout, qkv, lse, nhead, scale, mask=None, drop_p=0.0, seed=0, round_out=False):
+    _chk(dout, qkv, lse, mask)
+    dout, qkv = dout.contiguous(), qkv.contiguous()
+    B, L, E = qkv.shape
+    dh = E // 3 // nhead
+    mask = None if mask is None else mask.contiguous()
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    _w(10.0 * B * nhead * L * L * dh, 4.0 * (2 * qkv.numel() + dout.numel()))
+    _call("xm_attn_general_bwd_f32", _p(dout), _p(qkv), _p(mask), int(mask is not None and mask.dim() == 3), _p(lse), _p(dqkv),
+          _p(delta), B, L, nhead, dh, float(scale), float(drop_p), int(seed), int(round_out), _stream())
+    return dqkv
+
+
 def attn_fused_mask(B, L, nhead, drop_p, seed, device="cuda"):
     """The keep mask (B*H, L, L) the fused attention kernels generate for (drop_p, seed)."""
     mask = torch.empty(B * nhead, L, L, device=device, dtype=torch.uint8)

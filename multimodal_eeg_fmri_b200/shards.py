@@ -189,9 +189,15 @@ def host_batches(shard: Shard, names: Sequence[str], batch: int, drop_last: bool
                  ranks: Tuple[int, int] = (0, 1)) -> Iterator[Tuple[torch.Tensor, ...]]:
     """Consecutive `batch`-row host batches (tuples in `names` order) for `PairedTrainer.steps_from_host`, each in its
     own page-locked buffers (the trainer copies batch k+1 while batch k trains, so buffers are not recycled here).
-    `ranks = (rank, world)`: rank r takes batches r, r + world, ... (batch sharding, no collective)."""
+    `ranks = (rank, world)`: rank r takes batches r, r + world, ... (batch sharding, no collective).  Every rank gets
+    the SAME number of batches: the trailing `n_batches % world` batches are dropped, because each training step
+    issues collectives (SyncBN, embedding exchange, gradient all-reduce) and a rank with one batch more than the
+    others would wait in them forever."""
     rank, world = ranks
+    if world < 1 or not 0 <= rank < world:
+        raise ShardError(f"ranks=({rank}, {world}): need 0 <= rank < world")
     n_batches = shard.rows // batch if drop_last else (shard.rows + batch - 1) // batch
+    n_batches -= n_batches % world
     for b in range(rank, n_batches, world):
         lo, hi = b * batch, min((b + 1) * batch, shard.rows)
         got = shard.read_rows(lo, hi, shard.alloc_host(names, hi - lo, pin=pin))

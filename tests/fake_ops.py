@@ -318,6 +318,35 @@ def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_
     return attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
 
 
+def attn_general_supported(L, dh):
+    return 0 < dh <= 256 and L > 0
+
+
+def _attn_general_scores(qkv, nhead, scale, mask):
+    B, L, E = qkv.shape
+    q, k, v = _attn_parts(qkv, nhead)
+    s = q @ k.transpose(-1, -2) * scale
+    if mask is not None:
+        s = s + (mask.double() if mask.dim() == 2 else mask.double().reshape(B, nhead, L, L))
+    return q, k, v, s
+
+
+def attn_general_fwd(qkv, nhead, scale, mask=None, drop_p=0.0, seed=0, round_out=False):
+    _nodrop(drop_p)
+    B, L, E = qkv.shape
+    q, k, v, s = _attn_general_scores(qkv, nhead, scale, mask)
+    out = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, L, E // 3)
+    return out.float(), torch.logsumexp(s, -1).reshape(B * nhead, L).float()
+
+
+def attn_general_bwd(dout, qkv, lse, nhead, scale, mask=None, drop_p=0.0, seed=0, round_out=False):
+    _nodrop(drop_p)
+    B, L, E = qkv.shape
+    q, k, v, s = _attn_general_scores(qkv, nhead, scale, mask)
+    probs = torch.exp(s - lse.reshape(B, nhead, L, 1).double())
+    return attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
+
+
 # ---------------------------------------------------------------- residual stream (transformer block)
 def resid_ln_supported(D):
     return D % 128 == 0 and 128 <= D <= 512

@@ -144,5 +144,17 @@ def test_bridge_raw_dataset_alignment_bit_exact(gold, monkeypatch):
                 assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b), (i, j, name)
         assert_close_rel(ds[i][1], gold[f"raw_ds/{i}/fmri_act"], 1e-5, "fmri_act")
         assert np.array_equal(ds[i][2].numpy(), gold[f"raw_ds/{i}/fmri_conn"])
+    # zero stand-ins for missing entries are fresh arrays (reference :416-421): writing to one leaves the others alone
+    one = np.ones((2, 3), np.float32)
+    erp2 = {(1, "alpha", "1_Hz", "a"): one, (1, "beta", "1_Hz", "a"): one, (1, "beta", "2_Hz", "a"): one}
+    pw2 = {(1, "alpha", "1_Hz", "a"): one}
+    ds2 = bu.BridgeRawDataset(erp2, pw2, {}, {1: one}, {1: one}, {1: 0}, [1], BANDS, ["open"])
+    assert len(ds2) == 0  # no connectivity dict at all: nothing to shape the stand-in after, entries dropped
+    conn2 = {(1, "alpha", "open", "a"): one}
+    ds2 = bu.BridgeRawDataset(erp2, pw2, conn2, {1: one}, {1: one}, {1: 0}, [1], BANDS, ["open"])
+    pads = [p for (_, p, _) in ds2[0][0] if not p.any()] + [c for (_, _, c) in ds2[0][0] if not c.any()]
+    assert len(pads) == 4 and len({id(p) for p in pads}) == 4
+    pads[0][...] = 7.0
+    assert not any(p.any() for p in pads[1:])
     empty = bu.BridgeRawDataset({}, {}, {}, {}, {}, {}, [1], BANDS, ["open"])
     assert len(empty) == 0

@@ -177,4 +177,5 @@ def test_shard_batches_feed_the_trainer_identically(fakes, tmp_path):
     assert from_file == in_memory and len(from_file) == 3
     r0 = list(shards.host_batches(sh, names, 16, pin=False, ranks=(0, 2)))
     r1 = list(shards.host_batches(sh, names, 16, pin=False, ranks=(1, 2)))
-    assert torch.equal(r0[0][0], eeg[:16]) and torch.equal(r1[0][0], eeg[16:32]) and torch.equal(r0[1][2], conn[32:48])
+    # 3 batches over 2 ranks: both ranks get ONE batch (an uneven split would leave rank 0 alone in its step's collectives)
+    assert len(r0) == len(r1) == 1 and torch.equal(r0[0][0], eeg[:16]) and torch.equal(r1[0][0], eeg[16:32])

@@ -56,11 +56,17 @@ def test_read_rows_and_host_batches_ragged_and_sharded(tmp_path):
     assert [b[0].shape[0] for b in full] == [4, 4]  # drop_last
     tail = list(shards.host_batches(sh, ["eeg", "roi"], 4, drop_last=False, pin=False))
     assert [b[0].shape[0] for b in tail] == [4, 4, 3] and torch.equal(tail[2][1], torch.from_numpy(a["roi"][8:]))
-    # batch sharding across two ranks covers every full batch exactly once, in order per rank
+    # batch sharding across two ranks: 5 full batches -> every rank gets the SAME count (2; the odd batch is dropped,
+    # a rank with an extra step would deadlock in the step's collectives), each batch exactly once, in order per rank
     r0 = list(shards.host_batches(sh, ["label"], 2, pin=False, ranks=(0, 2)))
     r1 = list(shards.host_batches(sh, ["label"], 2, pin=False, ranks=(1, 2)))
-    seen = torch.cat([b[0] for pair in zip(r0, r1 + [None]) for b in pair if b is not None])
-    assert len(r0) == 3 and len(r1) == 2 and torch.equal(seen, torch.from_numpy(a["label"][:10]))
+    seen = torch.cat([b[0] for pair in zip(r0, r1) for b in pair])
+    assert len(r0) == len(r1) == 2 and torch.equal(seen, torch.from_numpy(a["label"][:8]))
+    for world in (3, 4):
+        counts = {len(list(shards.host_batches(sh, ["label"], 2, pin=False, ranks=(r, world)))) for r in range(world)}
+        assert counts == {5 // world}
+    with pytest.raises(shards.ShardError):
+        list(shards.host_batches(sh, ["label"], 2, pin=False, ranks=(2, 2)))
 
 
 def test_empty_and_invalid_inputs(tmp_path):
