@@ -343,6 +343,27 @@ int xm_resid_seqmean_fwd_f32(const float* x, const float* a, int64_t B, int64_t 
 int xm_resid_seqmean_bwd_f32(const float* dout, int64_t B, int64_t T, int64_t D, float* dx, float* da, float drop_p,
                              uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------ fused feed-forward branch of the transformer block
+ * EEG_CODE/enhanced_models_v4.py:79-80,102-105: linear2(Dropout(act(linear1(x)))) with the (M, hidden) intermediate kept
+ * on chip (csrc/ffn_fused.cu).  xm_ffn_fused_supported: D == 128, hidden % 128 == 0, hidden <= 1024, act GELU | RELU.
+ * x (M, D), w1 (hidden, D), w2 (D, hidden): tf32-rounded by their producers; b1 (hidden), b2 (D), y (M, D) 16-B aligned.
+ *   y = tf32(Dropout(act(x w1^T + b1))) w2^T + b2 */
+int xm_ffn_fused_supported(int64_t D, int64_t hidden, int act);
+int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int64_t M,
+                         int64_t D, int64_t hidden, int act, float drop_p, uint64_t seed, void* stream);
+/* Data-gradient half of the backward: recomputes the hidden activations from x and emits, in ONE pass,
+ *   a  (M, hidden) = tf32(Dropout(act(x w1^T + b1)))           operand of dw2 = dy^T a   (xm_linear_wgrad_f32)
+ *   dh (M, hidden) = tf32(dy w2 * act'(.) * mask / (1 - p))    operand of dw1 = dh^T x
+ *   dx (M, D)      = dh w1
+ *   db1_part (xm_ffn_fused_nblk(M), hidden): partial column sums of dh (reduce with xm_colsum_f32 -> db1); may be NULL.
+ * w2t = w2^T (hidden, D) and w1t = w1^T (D, hidden) are transposed tf32 copies, so every weight operand is K-major. */
+int xm_ffn_fused_nblk(int64_t M);
+int xm_ffn_fused_dgrad_f32(const float* x, const float* dy, const float* w1, const float* b1, const float* w2t, const float* w1t,
+                           float* a, float* dh, float* dx, float* db1_part, int64_t M, int64_t D, int64_t hidden, int act,
+                           float drop_p, uint64_t seed, void* stream);
+/* mask (M, hidden), 1 = kept: the dropout mask both kernels generate for (drop_p, seed), so tests can replay it. */
+int xm_ffn_fused_mask_u8(uint8_t* mask, int64_t M, int64_t hidden, float drop_p, uint64_t seed, void* stream);
+
 /* ------------------------------------------------------------------ diagnostics (not on the product path)
  * Dump the raw shared-memory image of one TMA box {32,32} loaded at (c0, c1) from a (rows, cols)
  * fp32 matrix; swizzle_atom32 selects SWIZZLE_128B_ATOM_32B instead of SWIZZLE_128B. */

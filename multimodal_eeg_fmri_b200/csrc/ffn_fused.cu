@@ -1,0 +1,756 @@
+// Fused feed-forward branch of the pre-norm transformer block for sm_100a (EEG_CODE/enhanced_models_v4.py:79-80,
+// 102-105: linear2(Dropout(GELU(linear1(x))))), d_model = 128, hidden = a multiple of 128 (512 in the reference).
+// The (rows x hidden) intermediate -- 2.1 GB per block at batch 4096 x 250 tokens, which the unfused path wrote or
+// read 11 times per block -- never reaches HBM in the forward and is written exactly once (as the two operands of
+// the weight gradients) in the backward.
+//
+//   forward   y = round_tf32(Dropout(act(x W1^T + b1))) W2^T + b2                                   xm_ffn_fused_fwd_f32
+//   backward  given x, dY:  H = x W1^T + b1 (recomputed),  G = dY W2,
+//             A  = round_tf32(Dropout(act(H)))            (rows, hidden)   operand of dW2 = dY^T A
+//             dH = round_tf32(G * act'(H) * mask/(1-p))    (rows, hidden)   operand of dW1 = dH^T x
+//             dX = dH W1,   db1 partial column sums of dH                                          xm_ffn_fused_dgrad_f32
+//
+// One persistent CTA per SM walks 128-row tiles; per tile the hidden axis is processed in chunks of 128 units:
+//   warp 0      TMA producer: the x (and dY) tile of the tile, then a ring of 16 KB weight k-blocks (from L2)
+//   warp 1      one thread issues every tcgen05.mma (kind::tf32, M = N = 128, fp32 accumulators in TMEM)
+//   warps 2-17  16 transform warps (4 TMEM lane quadrants x 4 column groups of 32): tcgen05.ld the chunk's
+//               accumulator, bias + activation + dropout + tf32 rounding in registers (packed f32x2 arithmetic),
+//               tcgen05.st the result back IN PLACE, where it is the A operand of the next product (A from TMEM)
+// forward MMA order:   M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | M2(2) | M2(3)          M1: H_c = x W1_c^T
+//                                                                                        M2: Y += A_c W2[:, c]^T
+// backward MMA order:  M1(0) M3(0) M1(1) | M4(0) M3(1) M1(2) | M4(1) M3(2) M1(3) | ...   M3: G_c = dY W2t_c^T
+//                                                                                        M4: dX += dH_c W1t[:, c]^T
+// tcgen05.mma executes in issue order, so re-using a TMEM buffer between MMAs needs no barrier; every M2 / M4 waits
+// for the transform warps of its chunk.  TMEM: H0 [0,128) H1 [128,256); forward Y [256,384); backward G [256,384),
+// dX [384,512).  A / dH leave through per-warp 2 KB swizzled staging buffers and TMA stores (row-per-lane register
+// stores of 128 KB per chunk were what bound the first version of this kernel: tools/probes/ffn_fused_dgrad.cu,
+// profiles/r2_ffn_probe_dgrad.log).
+//
+// Dropout mask: a pure function of (seed, row, hidden unit), identical in both kernels and in xm_ffn_fused_mask_u8:
+// per (row, 32-unit group g) a stream seed h0 = mix(rs(row) + (g + 1) * 0x9E3779B1), rs = high word of
+// hash_u64(row, seed); unit g*32 + j takes LCG state h_{j+1} and is kept iff h_{j+1} >= p * 2^32.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/xmodal_b200.h"
+#include "gemm_engine.cuh"
+
+namespace xm {
+namespace ffn {
+
+constexpr int kD = 128, kChunk = 128, kMaxChunks = 8;
+constexpr int kTile = 16384;  // 128 rows x 32 fp32, SWIZZLE_128B
+constexpr int kXfWarps = 16;
+constexpr int kThreads = 64 + 32 * kXfWarps;
+constexpr int kFwdRing = 5, kBwdRing = 4;
+constexpr int kFwdSmem = 2 * 4 * kTile + kFwdRing * kTile + 1024;
+constexpr int kStage = 2048;  // per-warp staging buffer: 16 rows x 128 B
+constexpr int kBwdSmem = 2 * 4 * kTile + kBwdRing * kTile + kXfWarps * kStage + 1024;
+constexpr uint32_t kGold = 0x9E3779B1u;
+constexpr uint32_t kLcgA = 747796405u, kLcgC = 2891336453u;
+enum : int { OP_M1 = 0, OP_M2 = 1, OP_M3 = 2, OP_M4 = 3 };
+
+struct Params {
+  long long M;
+  int tiles, nc, hidden, act;
+  const float* b1;
+  const float* b2;
+  float* y;        // forward: (M, 128)
+  float* dx;       // backward: (M, 128)
+  float* db1_part; // backward: (gridDim.x * 4, hidden) partial column sums of dH
+  float dscale;
+  uint32_t thr;
+  unsigned long long seed;
+};
+
+XM_DEVICE uint32_t mask_mix(uint32_t x) {
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  return x ^ (x >> 16);
+}
+XM_DEVICE uint32_t row_seed(unsigned long long row, unsigned long long seed) { return (uint32_t)(hash_u64(row, seed) >> 32); }
+XM_DEVICE uint32_t group_seed(uint32_t rs, int g) { return mask_mix(rs + (uint32_t)(g + 1) * kGold); }
+
+XM_DEVICE void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// The per-tile MMA schedule, written once into shared memory (kind << 8 | chunk).
+XM_DEVICE int build_fwd_ops(int* ops, int nc) {
+  int n = 0;
+  ops[n++] = OP_M1 << 8;
+  if (nc > 1) ops[n++] = (OP_M1 << 8) | 1;
+  for (int c = 0; c < nc; ++c) {
+    ops[n++] = (OP_M2 << 8) | c;
+    if (c + 2 < nc) ops[n++] = (OP_M1 << 8) | (c + 2);
+  }
+  return n;
+}
+XM_DEVICE int build_bwd_ops(int* ops, int nc) {
+  int n = 0;
+  ops[n++] = OP_M1 << 8;
+  ops[n++] = OP_M3 << 8;
+  if (nc > 1) ops[n++] = (OP_M1 << 8) | 1;
+  for (int c = 0; c < nc; ++c) {
+    ops[n++] = (OP_M4 << 8) | c;
+    if (c + 1 < nc) ops[n++] = (OP_M3 << 8) | (c + 1);
+    if (c + 2 < nc) ops[n++] = (OP_M1 << 8) | (c + 2);
+  }
+  return n;
+}
+
+// ---- packed activation arithmetic (f32x2: one FFMA2 / FMUL2 per two elements; these transforms are issue bound)
+XM_DEVICE float2 f2(float a, float b) { return make_float2(a, b); }
+XM_DEVICE float2 splat(float a) { return make_float2(a, a); }
+// standard normal cdf / pdf of two values (Abramowitz & Stegun 26.2.17, as xm_common.cuh:normal_cdf_pdf)
+XM_DEVICE void normal_cdf_pdf2(float2 x, float2& cdf, float2& pdf) {
+  const float2 e = __fmul2_rn(__fmul2_rn(x, x), splat(-0.72134752f));
+  pdf = __fmul2_rn(f2(approx_ex2(e.x), approx_ex2(e.y)), splat(0.3989422804f));
+  const float2 d = __ffma2_rn(f2(fabsf(x.x), fabsf(x.y)), splat(0.2316419f), splat(1.0f));
+  const float2 t = f2(approx_rcp(d.x), approx_rcp(d.y));
+  float2 poly = __ffma2_rn(t, splat(1.330274429f), splat(-1.821255978f));
+  poly = __ffma2_rn(t, poly, splat(1.781477937f));
+  poly = __ffma2_rn(t, poly, splat(-0.356563782f));
+  poly = __ffma2_rn(t, poly, splat(0.319381530f));
+  const float2 q = __fmul2_rn(pdf, __fmul2_rn(t, poly));           // 1 - Phi(|x|)
+  const float2 h = __ffma2_rn(q, splat(-1.0f), splat(0.5f));       // Phi(|x|) - 0.5
+  cdf = __fadd2_rn(f2(copysignf(h.x, x.x), copysignf(h.y, x.y)), splat(0.5f));
+}
+
+// Forward transform of 32 accumulator columns of one row: bias, activation, dropout, tf32 rounding (in place).
+template <bool DROP>
+XM_DEVICE void fwd_transform(uint32_t (&r)[32], const float* __restrict__ bias, int act, float dscale, uint32_t thr, uint32_t h) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 4) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + e));
+    float2 v0 = __fadd2_rn(f2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), f2(bb.x, bb.y));
+    float2 v1 = __fadd2_rn(f2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), f2(bb.z, bb.w));
+    if (act == XM_ACT_GELU) {
+      float2 c0, c1, p0, p1;
+      normal_cdf_pdf2(v0, c0, p0);
+      normal_cdf_pdf2(v1, c1, p1);
+      v0 = __fmul2_rn(v0, c0);
+      v1 = __fmul2_rn(v1, c1);
+    } else {
+      v0 = f2(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f));
+      v1 = f2(fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f));
+    }
+    if (DROP) {
+      v0 = __fmul2_rn(v0, splat(dscale));
+      v1 = __fmul2_rn(v1, splat(dscale));
+      h = h * kLcgA + kLcgC;
+      v0.x = h >= thr ? v0.x : 0.f;
+      h = h * kLcgA + kLcgC;
+      v0.y = h >= thr ? v0.y : 0.f;
+      h = h * kLcgA + kLcgC;
+      v1.x = h >= thr ? v1.x : 0.f;
+      h = h * kLcgA + kLcgC;
+      v1.y = h >= thr ? v1.y : 0.f;
+    }
+    r[e] = __float_as_uint(round_tf32(v0.x));
+    r[e + 1] = __float_as_uint(round_tf32(v0.y));
+    r[e + 2] = __float_as_uint(round_tf32(v1.x));
+    r[e + 3] = __float_as_uint(round_tf32(v1.y));
+  }
+}
+
+// Backward transform: rh = H (pre-bias) -> A, rg = G -> dH (both tf32-rounded, in place).
+template <bool DROP>
+XM_DEVICE void bwd_transform(uint32_t (&rh)[32], uint32_t (&rg)[32], const float* __restrict__ bias, int act, float dscale,
+                             uint32_t thr, uint32_t h) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) {
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + e));
+    const float2 v = __fadd2_rn(f2(__uint_as_float(rh[e]), __uint_as_float(rh[e + 1])), bb);
+    float2 a, d;  // act(v), act'(v)
+    if (act == XM_ACT_GELU) {
+      float2 cdf, pdf;
+      normal_cdf_pdf2(v, cdf, pdf);
+      a = __fmul2_rn(v, cdf);
+      d = __ffma2_rn(v, pdf, cdf);
+    } else {
+      a = f2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+      d = f2(v.x > 0.f ? 1.f : 0.f, v.y > 0.f ? 1.f : 0.f);
+    }
+    float2 g = __fmul2_rn(f2(__uint_as_float(rg[e]), __uint_as_float(rg[e + 1])), d);
+    if (DROP) {
+      a = __fmul2_rn(a, splat(dscale));
+      g = __fmul2_rn(g, splat(dscale));
+      h = h * kLcgA + kLcgC;
+      const bool k0 = h >= thr;
+      h = h * kLcgA + kLcgC;
+      const bool k1 = h >= thr;
+      a = f2(k0 ? a.x : 0.f, k1 ? a.y : 0.f);
+      g = f2(k0 ? g.x : 0.f, k1 ? g.y : 0.f);
+    }
+    rh[e] = __float_as_uint(round_tf32(a.x));
+    rh[e + 1] = __float_as_uint(round_tf32(a.y));
+    rg[e] = __float_as_uint(round_tf32(g.x));
+    rg[e + 1] = __float_as_uint(round_tf32(g.y));
+  }
+}
+
+// Column sums over the warp's 32 rows of a 32-column block held one row per lane: butterfly reduce-scatter,
+// 31 shuffles; lane j returns the sum of column j.
+XM_DEVICE float warp_column_sums(const uint32_t (&r)[32], int lane) {
+  float v[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float keep = __uint_as_float(up ? r[16 + i] : r[i]);
+      const float send = __uint_as_float(up ? r[i] : r[16 + i]);
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[s + i] : v[i];
+      const float send = up ? v[i] : v[s + i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];  // column index = lane (bit b of the lane selected the upper half at step b)
+}
+
+// 32 x 32 fp32 block of this warp (one row per lane) -> 2 KB swizzled staging buffer, 16 rows at a time -> TMA store.
+XM_DEVICE void store_block(const CUtensorMap* tm, uint8_t* sb, int lane, const uint32_t (&r)[32], int col, int row0) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading this buffer
+    __syncwarp();
+    if ((lane >> 4) == half) {
+      const int lr = lane & 15;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(sb + lr * 128 + ((j ^ (lr & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_3d(tm, sb, col, row0 + half * 16, 0);
+      ptx::bulk_commit();
+    }
+  }
+}
+
+struct FwdBars {
+  uint64_t x_full[2], x_empty[2];
+  uint64_t w_full[kFwdRing], w_empty[kFwdRing];
+  uint64_t h_full[2], a_ready[2];
+  uint64_t y_full, y_free;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+               const __grid_constant__ CUtensorMap tmW2, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ FwdBars bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int ops[2 * kMaxChunks];
+  __shared__ int n_ops_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* xs = smem;                    // [2][4] x k-block tiles
+  uint8_t* ring = smem + 2 * 4 * kTile;  // [kFwdRing] weight k-block tiles
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmW1);
+    ptx::prefetch_tensormap(&tmW2);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bar.x_full[i], 1);
+      ptx::mbar_init(&bar.x_empty[i], 1);
+      ptx::mbar_init(&bar.h_full[i], 1);
+      ptx::mbar_init(&bar.a_ready[i], kXfWarps);
+    }
+    for (int i = 0; i < kFwdRing; ++i) {
+      ptx::mbar_init(&bar.w_full[i], 1);
+      ptx::mbar_init(&bar.w_empty[i], 1);
+    }
+    ptx::mbar_init(&bar.y_full, 1);
+    ptx::mbar_init(&bar.y_free, kXfWarps);
+    ptx::fence_mbar_init();
+    n_ops_s = build_fwd_ops(ops, p.nc);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tY = tmem + 256u;
+  const int n_ops = n_ops_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ws = 0;  // weight k-blocks requested so far
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        const int xb = it & 1;
+        ptx::mbar_wait(&bar.x_empty[xb], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&bar.x_full[xb], 4 * kTile);
+        for (int kb = 0; kb < 4; ++kb)
+          ptx::tma_load_3d(&tmX, &bar.x_full[xb], xs + (xb * 4 + kb) * kTile, kb * 32, tile * 128, 0);
+        for (int op = 0; op < n_ops; ++op) {
+          const int kind = ops[op] >> 8, c = ops[op] & 255;
+          for (int kb = 0; kb < 4; ++kb, ++ws) {
+            const uint32_t st = ws % kFwdRing;
+            ptx::mbar_wait(&bar.w_empty[st], ((ws / kFwdRing) & 1u) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
+            if (kind == OP_M1)
+              ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W1[128c.., 32kb..]
+            else
+              ptx::tma_load_3d(&tmW2, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W2[:, 128c + 32kb..]
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(128, 128, 0, 0);
+      uint32_t ws = 0, hu[2] = {0u, 0u};
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        const int xb = it & 1;
+        for (int op = 0; op < n_ops; ++op) {
+          const int kind = ops[op] >> 8, c = ops[op] & 255, b = c & 1;
+          const uint32_t tH = tmem + (uint32_t)(b * 128);
+          if (kind == OP_M1) {
+            if (c == 0) {
+              ptx::mbar_wait(&bar.x_full[xb], ((uint32_t)it >> 1) & 1u);
+              ptx::tc_fence_after_sync();
+            }
+            for (int kb = 0; kb < 4; ++kb, ++ws) {
+              const uint32_t st = ws % kFwdRing;
+              ptx::mbar_wait(&bar.w_full[st], (ws / kFwdRing) & 1u);
+              ptx::tc_fence_after_sync();
+              const uint64_t da = ptx::make_smem_desc(ptx::smem_u32(xs + (xb * 4 + kb) * kTile), 16, 1024, 2);
+              const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8)
+                ptx::mma_tf32_ss(tH, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+              ptx::mma_commit(&bar.w_empty[st]);
+            }
+            ptx::mma_commit(&bar.h_full[b]);
+            if (c == p.nc - 1) ptx::mma_commit(&bar.x_empty[xb]);
+          } else {
+            ptx::mbar_wait(&bar.a_ready[b], hu[b] & 1u);  // the transform warps have written A_c over H_c
+            ++hu[b];
+            ptx::tc_fence_after_sync();
+            if (c == 0) {
+              ptx::mbar_wait(&bar.y_free, ((uint32_t)it & 1u) ^ 1u);  // the epilogue has read the previous tile's Y
+              ptx::tc_fence_after_sync();
+            }
+            for (int kb = 0; kb < 4; ++kb, ++ws) {
+              const uint32_t st = ws % kFwdRing;
+              ptx::mbar_wait(&bar.w_full[st], (ws / kFwdRing) & 1u);
+              ptx::tc_fence_after_sync();
+              const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8)
+                mma_tf32_ts(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (c | kb | k8) ? 1u : 0u);
+              ptx::mma_commit(&bar.w_empty[st]);
+            }
+            if (c == p.nc - 1) ptx::mma_commit(&bar.y_full);
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int part = (warp - 2) >> 2;   // which 32 of the chunk's 128 columns
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t hu[2] = {0u, 0u};
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      const long long row = (long long)tile * 128 + q * 32 + lane;
+      const uint32_t rs = p.thr ? row_seed((unsigned long long)row, p.seed) : 0u;
+      for (int c = 0; c < p.nc; ++c) {
+        const int b = c & 1;
+        ptx::mbar_wait(&bar.h_full[b], hu[b] & 1u);
+        ++hu[b];
+        ptx::tc_fence_after_sync();
+        const uint32_t addr = tmem + (uint32_t)(b * 128 + part * 32) + lane_base;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(addr, r);
+        ptx::tmem_ld_wait();
+        const float* bias = p.b1 + c * kChunk + part * 32;
+        if (p.thr)
+          fwd_transform<true>(r, bias, p.act, p.dscale, p.thr, group_seed(rs, c * 4 + part));
+        else
+          fwd_transform<false>(r, bias, p.act, 1.0f, 0u, 0u);
+        ptx::tmem_st_32x32(addr, r);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.a_ready[b]);
+      }
+      // ---- tile done: y = Y + b2
+      ptx::mbar_wait(&bar.y_full, (uint32_t)it & 1u);
+      ptx::tc_fence_after_sync();
+      {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tY + (uint32_t)(part * 32) + lane_base, r);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.y_free);  // Y is in registers: the next tile may overwrite it
+        if (row < p.M) {
+          float4* dst = reinterpret_cast<float4*>(p.y + row * kD + part * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + part * 32) + e);
+            dst[e] = make_float4(__uint_as_float(r[4 * e]) + bb.x, __uint_as_float(r[4 * e + 1]) + bb.y,
+                                 __uint_as_float(r[4 * e + 2]) + bb.z, __uint_as_float(r[4 * e + 3]) + bb.w);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+struct BwdBars {
+  uint64_t in_full, in_empty;
+  uint64_t w_full[kBwdRing], w_empty[kBwdRing];
+  uint64_t g_full, d_ready;
+  uint64_t x_done, xacc_free;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2t,
+                 const __grid_constant__ CUtensorMap tmW1t, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmDH, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ BwdBars bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int ops[3 * kMaxChunks];
+  __shared__ int n_ops_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* xs = smem;                       // [4] x k-block tiles (K = input features)
+  uint8_t* ys = smem + 4 * kTile;           // [4] dY k-block tiles (K = output features)
+  uint8_t* ring = smem + 8 * kTile;         // [kBwdRing] weight k-block tiles
+  uint8_t* staging = ring + kBwdRing * kTile;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmDY);
+    ptx::prefetch_tensormap(&tmW1);
+    ptx::prefetch_tensormap(&tmW2t);
+    ptx::prefetch_tensormap(&tmW1t);
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmDH);
+    ptx::mbar_init(&bar.in_full, 1);
+    ptx::mbar_init(&bar.in_empty, 1);
+    for (int i = 0; i < kBwdRing; ++i) {
+      ptx::mbar_init(&bar.w_full[i], 1);
+      ptx::mbar_init(&bar.w_empty[i], 1);
+    }
+    ptx::mbar_init(&bar.g_full, 1);
+    ptx::mbar_init(&bar.d_ready, kXfWarps);
+    ptx::mbar_init(&bar.x_done, 1);
+    ptx::mbar_init(&bar.xacc_free, kXfWarps);
+    ptx::fence_mbar_init();
+    n_ops_s = build_bwd_ops(ops, p.nc);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tG = tmem + 256u, tX = tmem + 384u;
+  const int n_ops = n_ops_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ws = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        ptx::mbar_wait(&bar.in_empty, ((uint32_t)it & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&bar.in_full, 8 * kTile);
+        for (int kb = 0; kb < 4; ++kb) {
+          ptx::tma_load_3d(&tmX, &bar.in_full, xs + kb * kTile, kb * 32, tile * 128, 0);
+          ptx::tma_load_3d(&tmDY, &bar.in_full, ys + kb * kTile, kb * 32, tile * 128, 0);
+        }
+        for (int op = 0; op < n_ops; ++op) {
+          const int kind = ops[op] >> 8, c = ops[op] & 255;
+          for (int kb = 0; kb < 4; ++kb, ++ws) {
+            const uint32_t st = ws % kBwdRing;
+            ptx::mbar_wait(&bar.w_empty[st], ((ws / kBwdRing) & 1u) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
+            if (kind == OP_M1)
+              ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);   // W1[128c.., in 32kb..]
+            else if (kind == OP_M3)
+              ptx::tma_load_3d(&tmW2t, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W2t[128c.., out 32kb..]
+            else
+              ptx::tma_load_3d(&tmW1t, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W1t[:, 128c + 32kb..]
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(128, 128, 0, 0);
+      uint32_t ws = 0, cu = 0;  // cu: chunks whose M4 has been issued
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        for (int op = 0; op < n_ops; ++op) {
+          const int kind = ops[op] >> 8, c = ops[op] & 255;
+          const uint32_t tH = tmem + (uint32_t)((c & 1) * 128);
+          if (kind == OP_M1 && c == 0) {
+            ptx::mbar_wait(&bar.in_full, (uint32_t)it & 1u);
+            ptx::tc_fence_after_sync();
+          }
+          if (kind == OP_M4) {
+            ptx::mbar_wait(&bar.d_ready, cu & 1u);  // the transform warps have read H_c, G_c and written dH_c over G_c
+            ++cu;
+            ptx::tc_fence_after_sync();
+            if (c == 0) {
+              ptx::mbar_wait(&bar.xacc_free, ((uint32_t)it & 1u) ^ 1u);  // the epilogue has read the previous tile's dX
+              ptx::tc_fence_after_sync();
+            }
+          }
+          for (int kb = 0; kb < 4; ++kb, ++ws) {
+            const uint32_t st = ws % kBwdRing;
+            ptx::mbar_wait(&bar.w_full[st], (ws / kBwdRing) & 1u);
+            ptx::tc_fence_after_sync();
+            const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+            if (kind == OP_M4) {
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8)
+                mma_tf32_ts(tX, tG + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (c | kb | k8) ? 1u : 0u);
+            } else {
+              const uint64_t da = ptx::make_smem_desc(ptx::smem_u32((kind == OP_M1 ? xs : ys) + kb * kTile), 16, 1024, 2);
+              const uint32_t acc = kind == OP_M1 ? tH : tG;
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8)
+                ptx::mma_tf32_ss(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+            }
+            ptx::mma_commit(&bar.w_empty[st]);
+          }
+          if (kind == OP_M3) {
+            ptx::mma_commit(&bar.g_full);  // H_c (issued earlier) and G_c are complete
+            if (c == p.nc - 1) ptx::mma_commit(&bar.in_empty);
+          }
+          if (kind == OP_M4 && c == p.nc - 1) ptx::mma_commit(&bar.x_done);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* sb = staging + (warp - 2) * kStage;
+    float colacc[kMaxChunks];  // column sums of dH over this warp's rows of every tile: column c*128 + part*32 + lane
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) colacc[k] = 0.f;
+    uint32_t cu = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * 128 + q * 32;
+      const long long row = (long long)row0 + lane;
+      const uint32_t rs = p.thr ? row_seed((unsigned long long)row, p.seed) : 0u;
+      for (int c = 0; c < p.nc; ++c, ++cu) {
+        ptx::mbar_wait(&bar.g_full, cu & 1u);
+        ptx::tc_fence_after_sync();
+        uint32_t rh[32], rg[32];
+        ptx::tmem_ld_32x32(tmem + (uint32_t)((c & 1) * 128 + part * 32) + lane_base, rh);
+        ptx::tmem_ld_32x32(tG + (uint32_t)(part * 32) + lane_base, rg);
+        ptx::tmem_ld_wait();
+        const float* bias = p.b1 + c * kChunk + part * 32;
+        if (p.thr)
+          bwd_transform<true>(rh, rg, bias, p.act, p.dscale, p.thr, group_seed(rs, c * 4 + part));
+        else
+          bwd_transform<false>(rh, rg, bias, p.act, 1.0f, 0u, 0u);
+        ptx::tmem_st_32x32(tG + (uint32_t)(part * 32) + lane_base, rg);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.d_ready);
+        // the MMA warp proceeds; this warp now streams its A / dH block out and folds dH into the bias gradient
+        const float cs = warp_column_sums(rg, lane);  // rows >= M carry dY = 0, hence dH = 0
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) colacc[k] += (k == c) ? cs : 0.f;
+        const int col = c * kChunk + part * 32;
+        store_block(&tmA, sb, lane, rh, col, row0);
+        store_block(&tmDH, sb, lane, rg, col, row0);
+      }
+      // ---- tile done: dX
+      ptx::mbar_wait(&bar.x_done, (uint32_t)it & 1u);
+      ptx::tc_fence_after_sync();
+      {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tX + (uint32_t)(part * 32) + lane_base, r);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.xacc_free);
+        if (row < p.M) {
+          float4* dst = reinterpret_cast<float4*>(p.dx + row * kD + part * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            dst[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
+                                 __uint_as_float(r[4 * e + 3]));
+        }
+      }
+    }
+    if (p.db1_part != nullptr) {
+      float* dst = p.db1_part + ((long long)blockIdx.x * 4 + q) * p.hidden + part * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < kMaxChunks; ++k)
+        if (k < p.nc) dst[k * kChunk] = colacc[k];
+    }
+    if (lane == 0) ptx::bulk_wait_all();  // staged blocks fully written before the CTA (and its smem) retires
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+__global__ void ffn_mask_kernel(uint8_t* mask, long long M, int hidden, uint32_t thr, unsigned long long seed) {
+  const long long n = M * (hidden / 32);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / (hidden / 32);
+    const int g = (int)(i % (hidden / 32));
+    uint32_t h = group_seed(row_seed((unsigned long long)row, seed), g);
+    for (int j = 0; j < 32; ++j) {
+      h = h * kLcgA + kLcgC;
+      mask[row * hidden + g * 32 + j] = (thr == 0u || h >= thr) ? 1 : 0;
+    }
+  }
+}
+
+static TensorView3 view2(const void* ptr, long long cols, long long rows) {
+  return TensorView3{ptr, {(unsigned long long)cols, (unsigned long long)rows, 1ull},
+                     {(unsigned long long)cols * 4ull, (unsigned long long)cols * (unsigned long long)rows * 4ull}};
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return XM_ERR_LAUNCH;
+  }
+  return XM_OK;
+}
+
+static int fill(Params& p, int64_t M, int64_t D, int64_t hidden, int act, float drop_p, uint64_t seed) {
+  if (M <= 0 || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
+  if (D != kD || hidden <= 0 || hidden % kChunk != 0 || hidden / kChunk > kMaxChunks || (act != XM_ACT_GELU && act != XM_ACT_RELU) ||
+      M > ((int64_t)1 << 31) - 256)
+    return XM_ERR_UNSUPPORTED;
+  p.M = M;
+  p.tiles = (int)((M + 127) / 128);
+  p.hidden = (int)hidden;
+  p.nc = (int)(hidden / kChunk);
+  p.act = act;
+  p.dscale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  p.thr = drop_p > 0.f ? (uint32_t)((double)drop_p * 4294967296.0) : 0u;
+  p.seed = seed;
+  return XM_OK;
+}
+
+}  // namespace ffn
+}  // namespace xm
+
+using namespace xm;
+
+extern "C" {
+
+int xm_ffn_fused_supported(int64_t D, int64_t hidden, int act) {
+  return D == ffn::kD && hidden > 0 && hidden % ffn::kChunk == 0 && hidden / ffn::kChunk <= ffn::kMaxChunks &&
+         (act == XM_ACT_GELU || act == XM_ACT_RELU);
+}
+
+int xm_ffn_fused_nblk(int64_t M) {
+  const int64_t tiles = (M + 127) / 128;
+  return (int)(tiles < kNumSMs ? tiles : kNumSMs) * 4;
+}
+
+int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int64_t M,
+                         int64_t D, int64_t hidden, int act, float drop_p, uint64_t seed, void* stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !y) return XM_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(b2)) & 15) return XM_ERR_INVALID;
+  ffn::Params p{};
+  int rc = ffn::fill(p, M, D, hidden, act, drop_p, seed);
+  if (rc != XM_OK) return rc;
+  p.b1 = b1;
+  p.b2 = b2;
+  p.y = y;
+  CUtensorMap mx, m1, m2;
+  rc = encode_tmap(&mx, ffn::view2(x, D, M), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&m1, ffn::view2(w1, D, hidden), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&m2, ffn::view2(w2, hidden, D), 32, 128, 0);
+  if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_fwd_kernel, ffn::kFwdSmem);
+  if (rc != XM_OK) return rc;
+  const int ctas = p.tiles < kNumSMs ? p.tiles : kNumSMs;
+  ffn::ffn_fwd_kernel<<<ctas, ffn::kThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
+  return check_launch();
+}
+
+int xm_ffn_fused_dgrad_f32(const float* x, const float* dy, const float* w1, const float* b1, const float* w2t, const float* w1t,
+                           float* a, float* dh, float* dx, float* db1_part, int64_t M, int64_t D, int64_t hidden, int act,
+                           float drop_p, uint64_t seed, void* stream) {
+  if (!x || !dy || !w1 || !b1 || !w2t || !w1t || !a || !dh || !dx) return XM_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(b1)) & 15) return XM_ERR_INVALID;
+  ffn::Params p{};
+  int rc = ffn::fill(p, M, D, hidden, act, drop_p, seed);
+  if (rc != XM_OK) return rc;
+  p.b1 = b1;
+  p.dx = dx;
+  p.db1_part = db1_part;
+  CUtensorMap mx, my, m1, m2t, m1t, ma, mdh;
+  rc = encode_tmap(&mx, ffn::view2(x, D, M), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&my, ffn::view2(dy, D, M), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&m1, ffn::view2(w1, D, hidden), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&m2t, ffn::view2(w2t, D, hidden), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&m1t, ffn::view2(w1t, hidden, D), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&ma, ffn::view2(a, hidden, M), 32, 16, 0);
+  if (rc == XM_OK) rc = encode_tmap(&mdh, ffn::view2(dh, hidden, M), 32, 16, 0);
+  if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_dgrad_kernel, ffn::kBwdSmem);
+  if (rc != XM_OK) return rc;
+  const int ctas = p.tiles < kNumSMs ? p.tiles : kNumSMs;
+  ffn::ffn_dgrad_kernel<<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, ma, mdh, p);
+  return check_launch();
+}
+
+int xm_ffn_fused_mask_u8(uint8_t* mask, int64_t M, int64_t hidden, float drop_p, uint64_t seed, void* stream) {
+  if (!mask || M <= 0 || hidden <= 0 || hidden % 32 != 0 || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
+  const uint32_t thr = drop_p > 0.f ? (uint32_t)((double)drop_p * 4294967296.0) : 0u;
+  const long long n = M * (hidden / 32);
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  ffn::ffn_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mask, M, (int)hidden, thr, seed);
+  return check_launch();
+}
+
+}  // extern "C"

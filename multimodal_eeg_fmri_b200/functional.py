@@ -259,6 +259,7 @@ def act_dropout(x, act, drop_p=0.0, training=True):
 # but its 3e-4 forward noise is amplified by the BatchNorm-backward cancellation into a 1.4e-2 error of that
 # layer's weight gradient (7e-4 in the 3-pass mode).
 _PRECISE_MAX_K = 1 << 30
+_FUSED_FFN = os.environ.get("XM_FUSED_FFN", "1") != "0"  # A/B switch: 0 = the unfused linear / act / linear chain
 _INFONCE_PRECISE_DGRAD = {"0": False, "1": True}.get(os.environ.get("XM_INFONCE_PRECISE_DGRAD", ""), None)
 
 
@@ -470,6 +471,7 @@ class TransformerTail(torch.autograd.Function):
         nl = len(params) // TransformerTail.NP
         scale = 1.0 / ((D // nhead) ** 0.5)
         seed = (lambda: next_seed()) if p > 0 else (lambda: 0)
+        fused_ffn = _FUSED_FFN and nl > 0 and ops.ffn_fused_supported(D, params[8].shape[0], act)
         x = h0.reshape(M, D)
         saved, meta = [], []
         pend, pend_seed = None, 0
@@ -488,21 +490,25 @@ class TransformerTail(torch.autograd.Function):
             s_ao = seed()
             x2, h2, m2, r2 = ops.resid_ln_fwd(x1, ao, n2w, n2b, eps, p, s_ao)
             del ao
-            f1 = ops.linear_fwd(h2, w1_r, b1)
             s_g = seed()
-            g = ops.act_fwd(f1, act, p, s_g, round_out=True)
-            f2 = ops.linear_fwd(g, w2_r, b2)
+            if fused_ffn:  # the (M, hidden) activations stay on chip; the backward recomputes them from h2
+                f2 = ops.ffn_fused_fwd(h2, w1_r, b1, w2_r, b2, act, p, s_g)
+                f1, g = b1, None
+            else:
+                f1 = ops.linear_fwd(h2, w1_r, b1)
+                g = ops.act_fwd(f1, act, p, s_g, round_out=True)
+                f2 = ops.linear_fwd(g, w2_r, b2)
             saved += [x1, h1, m1, r1, qkv, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w]
             meta.append((s_attn, s_ao, s_g, pend_seed if l > 0 else seed_pe))
             x, pend, pend_seed = x2, f2, seed()
         out = ops.resid_seqmean_fwd(x.view(B, L, D), pend.view(B, L, D), p, pend_seed)
         ctx.save_for_backward(*saved)
-        ctx.meta = (B, L, D, nl, nhead, p, act, scale, meta, pend_seed)
+        ctx.meta = (B, L, D, nl, nhead, p, act, scale, meta, pend_seed, fused_ffn)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        B, L, D, nl, nhead, p, act, scale, meta, last_seed = ctx.meta
+        B, L, D, nl, nhead, p, act, scale, meta, last_seed, fused_ffn = ctx.meta
         M = B * L
         sv = ctx.saved_tensors
         dxs, df2 = ops.resid_seqmean_bwd(dout.contiguous(), L, p, last_seed)
@@ -513,13 +519,20 @@ class TransformerTail(torch.autograd.Function):
         for l in reversed(range(nl)):
             (x1, h1, m1, r1, qkv, lse, att, x2, h2, m2, r2, f1, g, wqkv_r, wo_r, w1_r, w2_r, n1w, n2w) = sv[l * 19:(l + 1) * 19]
             s_attn, s_ao, s_g, s_in = meta[l]
-            dg = ops.linear_dgrad(df2, w2_r)
-            dw2, _ = ops.linear_wgrad(df2, g, need_bias=False)
-            df1, db1 = ops.act_bwd_colsum(dg, f1, act, p, s_g, round_out=True)  # bias gradient in the same pass
-            del dg
-            dh2 = ops.linear_dgrad(df1, w1_r)
-            dw1, _ = ops.linear_wgrad(df1, h2, need_bias=False)
-            del df1
+            if fused_ffn:
+                # one pass recomputes the hidden activations and emits both weight-gradient operands, dh2 and db1
+                g, df1, dh2, db1 = ops.ffn_fused_dgrad(h2, df2, w1_r, f1, w2_r.t().contiguous(), w1_r.t().contiguous(), act, p, s_g)
+                dw2, _ = ops.linear_wgrad(df2, g, need_bias=False)
+                dw1, _ = ops.linear_wgrad(df1, h2, need_bias=False)
+                del g, df1
+            else:
+                dg = ops.linear_dgrad(df2, w2_r)
+                dw2, _ = ops.linear_wgrad(df2, g, need_bias=False)
+                df1, db1 = ops.act_bwd_colsum(dg, f1, act, p, s_g, round_out=True)  # bias gradient in the same pass
+                del dg
+                dh2 = ops.linear_dgrad(df1, w1_r)
+                dw1, _ = ops.linear_wgrad(df1, h2, need_bias=False)
+                del df1
             # bias gradients of out_proj / the previous linear2 come out of the fused LayerNorm-backward pass
             dx1, dao, dn2w, dn2b, dbo = ops.resid_ln_bwd(dh2, dxs, x2, n2w, m2, r2, p, s_ao)
             datt = ops.linear_dgrad(dao, wo_r, round_out=True)

@@ -751,6 +751,46 @@ def attn_fused_mask(B, L, nhead, drop_p, seed, device="cuda"):
     return mask
 
 
+# ------------------------------------------------------------------ fused feed-forward branch
+def ffn_fused_supported(D: int, hidden: int, act) -> bool:
+    return bool(_lib.lib().xm_ffn_fused_supported(int(D), int(hidden), act_code(act)))
+
+
+def ffn_fused_fwd(x, w1, b1, w2, b2, act, drop_p=0.0, seed=0):
+    """y = tf32(Dropout(act(x w1^T + b1))) w2^T + b2 with the hidden activations kept on chip; x, w1, w2 tf32-rounded."""
+    _chk(x, w1, b1, w2, b2)
+    x, w1, w2 = x.contiguous(), w1.contiguous(), w2.contiguous()
+    M, D = x.shape
+    H = w1.shape[0]
+    y = torch.empty(M, D, device=x.device, dtype=torch.float32)
+    _w(4.0 * M * D * H, 4.0 * (2 * M * D + 2 * D * H))
+    _call("xm_ffn_fused_fwd_f32", _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(y), M, D, H, act_code(act), float(drop_p), int(seed),
+          _stream())
+    return y
+
+
+def ffn_fused_dgrad(x, dy, w1, b1, w2t, w1t, act, drop_p=0.0, seed=0):
+    """-> (a (M, H), dh (M, H), dx (M, D), db1 (H)): see xm_ffn_fused_dgrad_f32; w2t = w2^T, w1t = w1^T (tf32 copies)."""
+    _chk(x, dy, w1, b1, w2t, w1t)
+    x, dy, w1, w2t, w1t = x.contiguous(), dy.contiguous(), w1.contiguous(), w2t.contiguous(), w1t.contiguous()
+    M, D = x.shape
+    H = w1.shape[0]
+    a = torch.empty(M, H, device=x.device, dtype=torch.float32)
+    dh = torch.empty(M, H, device=x.device, dtype=torch.float32)
+    dx = torch.empty(M, D, device=x.device, dtype=torch.float32)
+    part = torch.empty(_lib.lib().xm_ffn_fused_nblk(M), H, device=x.device, dtype=torch.float32)
+    _w(6.0 * M * D * H, 4.0 * (3 * M * D + 2 * M * H + 3 * D * H))
+    _call("xm_ffn_fused_dgrad_f32", _p(x), _p(dy), _p(w1), _p(b1), _p(w2t), _p(w1t), _p(a), _p(dh), _p(dx), _p(part), M, D, H,
+          act_code(act), float(drop_p), int(seed), _stream())
+    return a, dh, dx, colsum(part)
+
+
+def ffn_fused_mask(M, hidden, drop_p, seed, device="cuda"):
+    mask = torch.empty(M, hidden, device=device, dtype=torch.uint8)
+    _call("xm_ffn_fused_mask_u8", _p(mask), M, hidden, float(drop_p), int(seed), _stream())
+    return mask
+
+
 # ------------------------------------------------------------------ residual stream (transformer block)
 def resid_ln_supported(D: int) -> bool:
     return D % 128 == 0 and 128 <= D <= 512

@@ -347,6 +347,26 @@ def attn_general_bwd(dout, qkv, lse, nhead, scale, mask=None, drop_p=0.0, seed=0
     return attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
 
 
+# ---------------------------------------------------------------- fused feed-forward branch
+def ffn_fused_supported(D, hidden, act):
+    return D == 128 and hidden % 128 == 0 and 0 < hidden <= 1024 and _ACT.get(act, act) in ("gelu", "relu")
+
+
+def ffn_fused_fwd(x, w1, b1, w2, b2, act, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    h = _act(F.linear(x.double(), w1.double(), b1.double()), act)
+    return F.linear(h, w2.double(), b2.double()).float()
+
+
+def ffn_fused_dgrad(x, dy, w1, b1, w2t, w1t, act, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    pre = F.linear(x.double(), w1.double(), b1.double()).requires_grad_(True)
+    with torch.enable_grad():
+        a = _act(pre, act)
+    (dh,) = torch.autograd.grad(a, pre, dy.double() @ w2t.double().t())
+    return a.detach().float(), dh.float(), (dh @ w1t.double().t()).float(), dh.sum(0).float()
+
+
 # ---------------------------------------------------------------- residual stream (transformer block)
 def resid_ln_supported(D):
     return D % 128 == 0 and 128 <= D <= 512

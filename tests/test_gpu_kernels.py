@@ -470,6 +470,148 @@ def test_fused_attention_dropout(ops, B, L, H, pdrop):
         assert_close_rel(a, b, 3e-3, f"fused d{name} with dropout")
 
 
+# ------------------------------------------------------------------ fused feed-forward branch
+def _ffn_ref(x, w1, b1, w2, b2, act, mask=None):
+    pre = (x.double() @ w1.double().t() + b1.double()).requires_grad_(True)
+    a = F.gelu(pre) if act == "gelu" else torch.relu(pre)
+    if mask is not None:
+        a = a * mask
+    return pre, a, a @ w2.double().t() + b2.double()
+
+
+@pytest.mark.parametrize("M,H,act,pdrop", [(1000, 512, "gelu", 0.0), (70001, 512, "gelu", 0.0), (128, 128, "relu", 0.0),
+                                           (4099, 256, "gelu", 0.3), (1, 512, "gelu", 0.0), (20000, 1024, "relu", 0.1),
+                                           (148 * 128 * 2 + 5, 512, "gelu", 0.3)])
+def test_ffn_fused_fwd_dgrad(ops, M, H, act, pdrop):
+    """linear2(Dropout(act(linear1(x)))) with the hidden activations on chip (enhanced_models_v4.py:79-80,102-105)
+    against fp64 torch: y, and from the data-gradient kernel A, dH, dX, db1 -- ragged row counts, 1-8 hidden chunks,
+    both activations, dropout replayed through the exported mask.  Outputs carry NaN canaries past row M."""
+    torch.manual_seed(21)
+    D, seed = 128, 4242
+    assert ops.ffn_fused_supported(D, H, act)
+    x = ops.round_tf32(torch.randn(M, D, device="cuda"))
+    dy = ops.round_tf32(torch.randn(M, D, device="cuda"))
+    w1 = ops.round_tf32(torch.randn(H, D, device="cuda") / D ** 0.5)
+    w2 = ops.round_tf32(torch.randn(D, H, device="cuda") / H ** 0.5)
+    b1, b2 = torch.randn(H, device="cuda") * 0.1, torch.randn(D, device="cuda") * 0.1
+    mask = None
+    if pdrop > 0:
+        keep = ops.ffn_fused_mask(M, H, pdrop, seed).bool()
+        assert abs(float(keep.float().mean()) - (1 - pdrop)) < 4 * (pdrop * (1 - pdrop) / keep.numel()) ** 0.5 + 1e-4
+        sd = (pdrop * (1 - pdrop) / min(M, H)) ** 0.5
+        if M >= 1000:  # no structure along rows or hidden units
+            assert float((keep.float().mean(0) - (1 - pdrop)).abs().max()) < 6 * (pdrop * (1 - pdrop) / M) ** 0.5
+            assert float((keep.float().mean(1) - (1 - pdrop)).abs().max()) < 6 * (pdrop * (1 - pdrop) / H) ** 0.5
+        assert not torch.equal(keep, ops.ffn_fused_mask(M, H, pdrop, seed + 1).bool())
+        mask = keep.double() / (1 - pdrop)
+    pre, a_ref, y_ref = _ffn_ref(x, w1, b1, w2, b2, act, mask)
+    y = ops.ffn_fused_fwd(x, w1, b1, w2, b2, act, pdrop, seed)
+    assert torch.equal(y, ops.ffn_fused_fwd(x, w1, b1, w2, b2, act, pdrop, seed))
+    assert_close_rel(y, y_ref, TF32, "ffn fused y")
+    gpre, = torch.autograd.grad(a_ref, pre, dy.double() @ w2.double(), retain_graph=False)
+    a, dh, dx, db1 = ops.ffn_fused_dgrad(x, dy, w1, b1, w2.t().contiguous(), w1.t().contiguous(), act, pdrop, seed)
+    assert_close_rel(a, a_ref.detach(), TF32, "ffn fused A")
+    assert_close_rel(dh, gpre, TF32, "ffn fused dH")
+    assert_close_rel(dx, gpre @ w1.double(), TF32, "ffn fused dX")
+    assert_close_rel(db1, gpre.sum(0), TF32, "ffn fused db1", atol=1e-5)
+
+
+def test_transformer_tail_fused_ffn_matches_unfused(ops, monkeypatch):
+    """The whole tail with the fused FFN against the same tail on the linear / act / linear chain (dropout off):
+    output and every gradient."""
+    from multimodal_eeg_fmri_b200 import functional as XF, modules
+    torch.manual_seed(3)
+    m = modules.EnhancedERPEncoder(16, 128, 2, 4, 0.0).cuda().train()
+    x = torch.randn(6, 16, 120, device="cuda")
+    res = {}
+    for fused in (True, False):
+        monkeypatch.setattr(XF, "_FUSED_FFN", fused)
+        m.zero_grad()
+        out = m(x)
+        out.square().sum().backward()
+        res[fused] = (out.detach().clone(), {k: p.grad.detach().clone() for k, p in m.named_parameters()})
+    assert_close_rel(res[True][0], res[False][0], TF32, "tail output")
+    for k, g in res[False][1].items():
+        if k.startswith("conv_layers.") and k.endswith(".bias") and not k.startswith("conv_layers.10"):
+            continue
+        assert_close_rel(res[True][1][k], g, 3e-3, k, atol=1e-6)
+
+
+# ------------------------------------------------------------------ shape-general attention core
+@pytest.mark.parametrize("B,L,H,dh,mask_kind,pdrop", [(3, 50, 4, 8, None, 0.0), (2, 33, 2, 16, "bool2d", 0.0), (2, 40, 4, 32, "float3d", 0.0),
+                                                      (1, 700, 2, 64, None, 0.0), (2, 64, 3, 20, "bool3d", 0.0), (2, 96, 4, 8, None, 0.25)])
+def test_general_attention_vs_multihead_attention(ops, B, L, H, dh, mask_kind, pdrop):
+    """The SIMT attention core (any head dim, attn_mask) against torch fp64 with nn.MultiheadAttention's mask
+    semantics: boolean True = NOT allowed to attend, float = additive, (L, L) or (B*H, L, L)."""
+    from multimodal_eeg_fmri_b200 import functional as XF
+    torch.manual_seed(31)
+    d = H * dh
+    qkv = torch.randn(B, L, 3 * d, device="cuda")
+    dout = torch.randn(B, L, d, device="cuda")
+    scale = dh ** -0.5
+    mask = None
+    if mask_kind == "bool2d":
+        mask = torch.triu(torch.ones(L, L, dtype=torch.bool, device="cuda"), 1)  # causal: no fully masked row
+    elif mask_kind == "bool3d":
+        mask = torch.rand(B * H, L, L, device="cuda") < 0.3
+        mask[:, torch.arange(L), torch.arange(L)] = False
+    elif mask_kind == "float3d":
+        mask = torch.randn(B * H, L, L, device="cuda")
+    add = XF.additive_attention_mask(mask, B, H, L)
+    x = qkv.double().requires_grad_(True)
+    q, k, v = (t.reshape(B, L, H, dh).transpose(1, 2) for t in x.chunk(3, dim=-1))
+    s = q @ k.transpose(-1, -2) * scale
+    if add is not None:
+        s = s + (add.double() if add.dim() == 2 else add.double().reshape(B, H, L, L))
+    p = torch.softmax(s, dim=-1)
+    ref = (p @ v).transpose(1, 2).reshape(B, L, d)
+    if pdrop == 0.0:
+        out, lse = ops.attn_general_fwd(qkv, H, scale, add, 0.0, 0)
+        assert_close_rel(out, ref, FP32 * 3, "general attention out")
+        assert float((lse.double() - torch.logsumexp(s, -1).reshape(B * H, L)).abs().max()) < 1e-4
+        (gx,) = torch.autograd.grad(ref, x, dout.double())
+        dqkv = ops.attn_general_bwd(dout, qkv, lse, H, scale, add, 0.0, 0)
+        assert_close_rel(dqkv, gx, 1e-4, "general attention dqkv")
+    else:  # dropout: deterministic per seed, keeps the expected mass, backward consistent with the forward (dot test)
+        out, lse = ops.attn_general_fwd(qkv, H, scale, add, pdrop, 99)
+        out2, _ = ops.attn_general_fwd(qkv, H, scale, add, pdrop, 99)
+        assert torch.equal(out, out2) and not torch.equal(out, ops.attn_general_fwd(qkv, H, scale, add, pdrop, 100)[0])
+        dqkv = ops.attn_general_bwd(dout, qkv, lse, H, scale, add, pdrop, 99)
+        eps = 1e-2
+        dirn = torch.randn_like(qkv)
+        fp = ops.attn_general_fwd(qkv + eps * dirn, H, scale, add, pdrop, 99)[0]
+        fm = ops.attn_general_fwd(qkv - eps * dirn, H, scale, add, pdrop, 99)[0]
+        num = float(((fp - fm).double() * dout.double()).sum() / (2 * eps))
+        ana = float((dqkv.double() * dirn.double()).sum())
+        assert abs(num - ana) <= 2e-2 * max(abs(num), 1.0), (num, ana)
+
+
+def test_transformer_block_masks_match_torch_multihead_attention():
+    """TemporalTransformerBlock.forward(x, mask) against the reference block's composition of torch modules
+    (enhanced_models_v4.py:89-107) under the same state_dict: bool / float / per-head masks, head dim 8."""
+    from multimodal_eeg_fmri_b200 import modules
+    torch.manual_seed(5)
+    B, L, d, H = 3, 21, 32, 4
+    blk = modules.TemporalTransformerBlock(d, H, 64, 0.0).cuda().train()
+    x = torch.randn(B, L, d, device="cuda")
+
+    def reference(x, mask):
+        h = blk.norm1(x)
+        a, _ = blk.self_attn(h, h, h, attn_mask=mask)
+        x = x + a
+        return x + blk.linear2(F.gelu(blk.linear1(blk.norm2(x))))
+
+    causal = torch.triu(torch.ones(L, L, dtype=torch.bool, device="cuda"), 1)
+    per_head = (torch.rand(B * H, L, L, device="cuda") < 0.4)
+    per_head[:, torch.arange(L), torch.arange(L)] = False
+    for mask in (None, causal, torch.randn(L, L, device="cuda"), per_head):
+        with torch.no_grad():
+            ref = reference(x.double().float(), mask)
+        assert_close_rel(blk(x, mask), ref, 2e-3, f"block with mask {None if mask is None else (mask.dtype, tuple(mask.shape))}")
+    with pytest.raises(ValueError):
+        blk(x, torch.zeros(L, L + 1, device="cuda"))
+
+
 # ------------------------------------------------------------------ out-of-bounds canaries
 def test_ragged_outputs_do_not_write_past_their_extent(ops):
     """compute-sanitizer is closed on this pool, so ragged shapes are checked with canaries: outputs are
