@@ -95,6 +95,14 @@ int xm_zscore_f32(const float* x, int64_t n_items, int64_t item_len, float eps, 
  * out (B, 2*ROI) = concat(mean over TR, population std over TR); NaN inputs count as 0. */
 int xm_roi_meanstd_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, void* stream);
 
+/* Functional connectivity of the ROI series (csrc/connectivity.cu): out (B, ROI*ROI) = per-sample numpy.corrcoef of the
+ * ROI columns over TR, flattened row-major, after nan_to_num -- the `connectivity` input of fMRIFusionNet
+ * (fMRI_CODE/fmri_utils.py:90-103; the reference reads such matrices from CSV, :161-198; SURVEY.md section 8d defines
+ * the synthetic connectivity input this way).  fp32, 1e-5.  A constant column yields NaN in its row and column.
+ * xm_roi_corrcoef_supported: the (TR, ROI) series of one sample fits shared memory. */
+int xm_roi_corrcoef_supported(int64_t TR, int64_t ROI);
+int xm_roi_corrcoef_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, void* stream);
+
 /* ------------------------------------------------------------------ dense projections (nn.Linear)
  * fMRI_CODE/fmri_utils.py:27,31,45,49,66 ; bridge_utils.py:35,41,61,65 ; enhanced_models_v4.py:164 */
 
@@ -346,14 +354,15 @@ int xm_resid_seqmean_bwd_f32(const float* dout, int64_t B, int64_t T, int64_t D,
 /* ------------------------------------------------------------------ fused feed-forward branch of the transformer block
  * EEG_CODE/enhanced_models_v4.py:79-80,102-105: linear2(Dropout(act(linear1(x)))) with the (M, hidden) intermediate kept
  * on chip (csrc/ffn_fused.cu).  xm_ffn_fused_supported: D == 128, hidden % 128 == 0, hidden <= 1024, act GELU | RELU.
- * x (M, D), w1 (hidden, D), w2 (D, hidden): tf32-rounded by their producers; b1 (hidden), b2 (D), y (M, D) 16-B aligned.
+ * x (M, D), w1 (hidden, D), w2 (D, hidden): tf32-rounded by their producers; b1 (hidden), b2 (D); y / a / dh / dx 32-B aligned.
  *   y = tf32(Dropout(act(x w1^T + b1))) w2^T + b2 */
 int xm_ffn_fused_supported(int64_t D, int64_t hidden, int act);
 int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int64_t M,
                          int64_t D, int64_t hidden, int act, float drop_p, uint64_t seed, void* stream);
 /* Data-gradient half of the backward: recomputes the hidden activations from x and emits, in ONE pass,
- *   a  (M, hidden) = tf32(Dropout(act(x w1^T + b1)))           operand of dw2 = dy^T a   (xm_linear_wgrad_f32)
- *   dh (M, hidden) = tf32(dy w2 * act'(.) * mask / (1 - p))    operand of dw1 = dh^T x
+ *   a  (M, hidden) = Dropout(act(x w1^T + b1))           operand of dw2 = dy^T a   (xm_linear_wgrad_f32)
+ *   dh (M, hidden) = dy w2 * act'(.) * mask / (1 - p)    operand of dw1 = dh^T x
+ *                    (both pre-scaled by 1 + 0.7213 * 2^-11, so that the tensor core's truncation to tf32 is zero-mean)
  *   dx (M, D)      = dh w1
  *   db1_part (xm_ffn_fused_nblk(M), hidden): partial column sums of dh (reduce with xm_colsum_f32 -> db1); may be NULL.
  * w2t = w2^T (hidden, D) and w1t = w1^T (D, hidden) are transposed tf32 copies, so every weight operand is K-major. */
@@ -370,6 +379,11 @@ int xm_ffn_fused_mask_u8(uint8_t* mask, int64_t M, int64_t hidden, float drop_p,
 /* A/B switch for the conv-wgrad operand staging (1: one halo tile per k-block serves every tap through
  * descriptor start-address shifts; 0: one shifted TMA copy per tap).  Returns the previous setting. */
 int xm_debug_set_conv_halo(int on);
+/* When non-NULL (3 * 8192 int64), the next xm_ffn_fused_fwd_f32 launches run the tracing instance of the kernel:
+ * CTA 0 logs, per MMA-schedule step, (kind, chunk, start clock, end clock, cycles waited on the weight ring, cycles
+ * waited on the other roles) for the TMA producer [0, 8192) and the MMA issuer [8192, 16384), and per transformed
+ * chunk (4, chunk, wait start, accumulator ready, handed back) for one warp of each transform group [16384 + g*4096). */
+int xm_debug_set_ffn_trace(int64_t* device_buffer);
 int xm_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int64_t ld, int c0, int c1, int swizzle_atom32,
                        float* out, void* stream);
 

@@ -4,27 +4,27 @@
 // read 11 times per block -- never reaches HBM in the forward and is written exactly once (as the two operands of
 // the weight gradients) in the backward.
 //
-//   forward   y = round_tf32(Dropout(act(x W1^T + b1))) W2^T + b2                                   xm_ffn_fused_fwd_f32
+//   forward   y = tf32(Dropout(act(x W1^T + b1))) W2^T + b2                                         xm_ffn_fused_fwd_f32
 //   backward  given x, dY:  H = x W1^T + b1 (recomputed),  G = dY W2,
-//             A  = round_tf32(Dropout(act(H)))            (rows, hidden)   operand of dW2 = dY^T A
-//             dH = round_tf32(G * act'(H) * mask/(1-p))    (rows, hidden)   operand of dW1 = dH^T x
+//             A  = Dropout(act(H))                (rows, hidden)   operand of dW2 = dY^T A
+//             dH = G * act'(H) * mask / (1 - p)   (rows, hidden)   operand of dW1 = dH^T x
 //             dX = dH W1,   db1 partial column sums of dH                                          xm_ffn_fused_dgrad_f32
+//   (tf32 operands are made by the tensor core's truncation of values pre-scaled by 1 + 0.7213 * 2^-11: see kTruncComp)
 //
 // One persistent CTA per SM walks 128-row tiles; per tile the hidden axis is processed in chunks of 128 units:
 //   warp 0      TMA producer: the x (and dY) tile of the tile, then a ring of 16 KB weight k-blocks (from L2)
 //   warp 1      one thread issues every tcgen05.mma (kind::tf32, M = N = 128, fp32 accumulators in TMEM)
-//   warps 2-17  16 transform warps (4 TMEM lane quadrants x 4 column groups of 32): tcgen05.ld the chunk's
-//               accumulator, bias + activation + dropout + tf32 rounding in registers (packed f32x2 arithmetic),
-//               tcgen05.st the result back IN PLACE, where it is the A operand of the next product (A from TMEM)
+//   warps 2-17  16 transform warps in two groups of 8 that alternate chunks (4 TMEM lane quadrants x 2 column halves):
+//               tcgen05.ld the chunk's accumulator, bias + activation + dropout in registers (packed f32x2
+//               arithmetic), tcgen05.st the result back IN PLACE, where it is the A operand of the next product
 // forward MMA order:   M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | M2(2) | M2(3)          M1: H_c = x W1_c^T
 //                                                                                        M2: Y += A_c W2[:, c]^T
 // backward MMA order:  M1(0) M3(0) M1(1) | M4(0) M3(1) M1(2) | M4(1) M3(2) M1(3) | ...   M3: G_c = dY W2t_c^T
 //                                                                                        M4: dX += dH_c W1t[:, c]^T
 // tcgen05.mma executes in issue order, so re-using a TMEM buffer between MMAs needs no barrier; every M2 / M4 waits
 // for the transform warps of its chunk.  TMEM: H0 [0,128) H1 [128,256); forward Y [256,384); backward G [256,384),
-// dX [384,512).  A / dH leave through per-warp 2 KB swizzled staging buffers and TMA stores (row-per-lane register
-// stores of 128 KB per chunk were what bound the first version of this kernel: tools/probes/ffn_fused_dgrad.cu,
-// profiles/r2_ffn_probe_dgrad.log).
+// dX [384,512).  A / dH / y / dX leave the registers as 256-bit global stores: each lane owns one 128-byte line of a
+// row, so every store instruction writes 32 complete sectors.
 //
 // Dropout mask: a pure function of (seed, row, hidden unit), identical in both kernels and in xm_ffn_fused_mask_u8:
 // per (row, 32-unit group g) a stream seed h0 = mix(rs(row) + (g + 1) * 0x9E3779B1), rs = high word of
@@ -44,10 +44,10 @@ constexpr int kD = 128, kChunk = 128, kMaxChunks = 8;
 constexpr int kTile = 16384;  // 128 rows x 32 fp32, SWIZZLE_128B
 constexpr int kXfWarps = 16;
 constexpr int kThreads = 64 + 32 * kXfWarps;
-constexpr int kFwdRing = 5, kBwdRing = 4;
-constexpr int kFwdSmem = 2 * 4 * kTile + kFwdRing * kTile + 1024;
-constexpr int kStage = 2048;  // per-warp staging buffer: 16 rows x 128 B
-constexpr int kBwdSmem = 2 * 4 * kTile + kBwdRing * kTile + kXfWarps * kStage + 1024;
+constexpr int kFwdRing = 5, kBwdRing = 5;
+constexpr int kBiasBytes = (kMaxChunks * kChunk + kD) * 4;  // b1 (+ b2) staged in shared memory
+constexpr int kFwdSmem = 2 * 4 * kTile + kFwdRing * kTile + kBiasBytes + 1024;
+constexpr int kBwdSmem = 2 * 4 * kTile + kBwdRing * kTile + kBiasBytes + 1024;
 constexpr uint32_t kGold = 0x9E3779B1u;
 constexpr uint32_t kLcgA = 747796405u, kLcgC = 2891336453u;
 enum : int { OP_M1 = 0, OP_M2 = 1, OP_M3 = 2, OP_M4 = 3 };
@@ -59,11 +59,24 @@ struct Params {
   const float* b2;
   float* y;        // forward: (M, 128)
   float* dx;       // backward: (M, 128)
-  float* db1_part; // backward: (gridDim.x * 4, hidden) partial column sums of dH
+  float* db1_part; // backward: (tiles * 4, hidden) partial column sums of dH, one row per (tile, lane quadrant)
   float dscale;
   uint32_t thr;
   unsigned long long seed;
+  long long* trace;  // debug (xm_debug_ffn_fused_fwd_trace_f32): CTA 0 logs per-op clocks, 3 roles x 8192 slots
 };
+
+// mbarrier wait that, in the tracing instance of a kernel, adds the cycles it spent to `acc`
+template <bool TRACE>
+XM_DEVICE void twait(uint64_t* bar, uint32_t parity, long long& acc) {
+  if (TRACE) {
+    const long long t0 = clock64();
+    ptx::mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    ptx::mbar_wait(bar, parity);
+  }
+}
 
 XM_DEVICE uint32_t mask_mix(uint32_t x) {
   x *= 0x7FEB352Du;
@@ -112,42 +125,45 @@ XM_DEVICE int build_bwd_ops(int* ops, int nc) {
 // ---- packed activation arithmetic (f32x2: one FFMA2 / FMUL2 per two elements; these transforms are issue bound)
 XM_DEVICE float2 f2(float a, float b) { return make_float2(a, b); }
 XM_DEVICE float2 splat(float a) { return make_float2(a, a); }
-// standard normal cdf / pdf of two values (Abramowitz & Stegun 26.2.17, as xm_common.cuh:normal_cdf_pdf)
-XM_DEVICE void normal_cdf_pdf2(float2 x, float2& cdf, float2& pdf) {
+// Values written back to TMEM (and the A / dH operands written for the weight gradients) are NOT rounded to tf32:
+// the tensor core truncates them, and their scale carries (1 + 0.7213 * 2^-11), the mean relative truncation loss
+// over a binade, so the truncation is zero-mean like round-to-nearest (attention_fused.cu uses the same device).
+constexpr float kTruncComp = 1.0f + 0.7213f / 2048.0f;
+// cs * (standard normal cdf, pdf) of two values (Abramowitz & Stegun 26.2.17, as xm_common.cuh:normal_cdf_pdf)
+XM_DEVICE void normal_cdf_pdf2(float2 x, float cs, float2& cdf, float2& pdf) {
   const float2 e = __fmul2_rn(__fmul2_rn(x, x), splat(-0.72134752f));
-  pdf = __fmul2_rn(f2(approx_ex2(e.x), approx_ex2(e.y)), splat(0.3989422804f));
+  pdf = __fmul2_rn(f2(approx_ex2(e.x), approx_ex2(e.y)), splat(0.3989422804f * cs));
   const float2 d = __ffma2_rn(f2(fabsf(x.x), fabsf(x.y)), splat(0.2316419f), splat(1.0f));
   const float2 t = f2(approx_rcp(d.x), approx_rcp(d.y));
   float2 poly = __ffma2_rn(t, splat(1.330274429f), splat(-1.821255978f));
   poly = __ffma2_rn(t, poly, splat(1.781477937f));
   poly = __ffma2_rn(t, poly, splat(-0.356563782f));
   poly = __ffma2_rn(t, poly, splat(0.319381530f));
-  const float2 q = __fmul2_rn(pdf, __fmul2_rn(t, poly));           // 1 - Phi(|x|)
-  const float2 h = __ffma2_rn(q, splat(-1.0f), splat(0.5f));       // Phi(|x|) - 0.5
-  cdf = __fadd2_rn(f2(copysignf(h.x, x.x), copysignf(h.y, x.y)), splat(0.5f));
+  const float2 q = __fmul2_rn(pdf, __fmul2_rn(t, poly));           // cs * (1 - Phi(|x|))
+  const float2 h = __fadd2_rn(splat(0.5f * cs), f2(-q.x, -q.y));   // cs * (Phi(|x|) - 0.5)
+  cdf = __fadd2_rn(f2(copysignf(h.x, x.x), copysignf(h.y, x.y)), splat(0.5f * cs));
 }
 
-// Forward transform of 32 accumulator columns of one row: bias, activation, dropout, tf32 rounding (in place).
+// Forward transform of 32 accumulator columns of one row, in place: cs * Dropout(act(acc + bias)), cs = truncation
+// compensation (* 1 / (1 - p) with dropout).  `bias`: shared memory.
 template <bool DROP>
-XM_DEVICE void fwd_transform(uint32_t (&r)[32], const float* __restrict__ bias, int act, float dscale, uint32_t thr, uint32_t h) {
+XM_DEVICE void fwd_transform(uint32_t (&r)[32], const float* bias, int act, float cs, uint32_t thr, uint32_t h) {
 #pragma unroll
   for (int e = 0; e < 32; e += 4) {
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + e));
+    const float4 bb = *reinterpret_cast<const float4*>(bias + e);
     float2 v0 = __fadd2_rn(f2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), f2(bb.x, bb.y));
     float2 v1 = __fadd2_rn(f2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), f2(bb.z, bb.w));
     if (act == XM_ACT_GELU) {
       float2 c0, c1, p0, p1;
-      normal_cdf_pdf2(v0, c0, p0);
-      normal_cdf_pdf2(v1, c1, p1);
+      normal_cdf_pdf2(v0, cs, c0, p0);
+      normal_cdf_pdf2(v1, cs, c1, p1);
       v0 = __fmul2_rn(v0, c0);
       v1 = __fmul2_rn(v1, c1);
     } else {
-      v0 = f2(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f));
-      v1 = f2(fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f));
+      v0 = __fmul2_rn(f2(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f)), splat(cs));
+      v1 = __fmul2_rn(f2(fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f)), splat(cs));
     }
     if (DROP) {
-      v0 = __fmul2_rn(v0, splat(dscale));
-      v1 = __fmul2_rn(v1, splat(dscale));
       h = h * kLcgA + kLcgC;
       v0.x = h >= thr ? v0.x : 0.f;
       h = h * kLcgA + kLcgC;
@@ -157,35 +173,32 @@ XM_DEVICE void fwd_transform(uint32_t (&r)[32], const float* __restrict__ bias, 
       h = h * kLcgA + kLcgC;
       v1.y = h >= thr ? v1.y : 0.f;
     }
-    r[e] = __float_as_uint(round_tf32(v0.x));
-    r[e + 1] = __float_as_uint(round_tf32(v0.y));
-    r[e + 2] = __float_as_uint(round_tf32(v1.x));
-    r[e + 3] = __float_as_uint(round_tf32(v1.y));
+    r[e] = __float_as_uint(v0.x);
+    r[e + 1] = __float_as_uint(v0.y);
+    r[e + 2] = __float_as_uint(v1.x);
+    r[e + 3] = __float_as_uint(v1.y);
   }
 }
 
-// Backward transform: rh = H (pre-bias) -> A, rg = G -> dH (both tf32-rounded, in place).
+// Backward transform, in place: rh = H (pre-bias) -> A = cs * Dropout(act(.)), rg = G -> dH = cs * G * act'(.) * mask.
 template <bool DROP>
-XM_DEVICE void bwd_transform(uint32_t (&rh)[32], uint32_t (&rg)[32], const float* __restrict__ bias, int act, float dscale,
-                             uint32_t thr, uint32_t h) {
+XM_DEVICE void bwd_transform(uint32_t (&rh)[32], uint32_t (&rg)[32], const float* bias, int act, float cs, uint32_t thr, uint32_t h) {
 #pragma unroll
   for (int e = 0; e < 32; e += 2) {
-    const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + e));
+    const float2 bb = *reinterpret_cast<const float2*>(bias + e);
     const float2 v = __fadd2_rn(f2(__uint_as_float(rh[e]), __uint_as_float(rh[e + 1])), bb);
-    float2 a, d;  // act(v), act'(v)
+    float2 a, d;  // cs * act(v), cs * act'(v)
     if (act == XM_ACT_GELU) {
       float2 cdf, pdf;
-      normal_cdf_pdf2(v, cdf, pdf);
+      normal_cdf_pdf2(v, cs, cdf, pdf);
       a = __fmul2_rn(v, cdf);
       d = __ffma2_rn(v, pdf, cdf);
     } else {
-      a = f2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
-      d = f2(v.x > 0.f ? 1.f : 0.f, v.y > 0.f ? 1.f : 0.f);
+      a = __fmul2_rn(f2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)), splat(cs));
+      d = f2(v.x > 0.f ? cs : 0.f, v.y > 0.f ? cs : 0.f);
     }
     float2 g = __fmul2_rn(f2(__uint_as_float(rg[e]), __uint_as_float(rg[e + 1])), d);
     if (DROP) {
-      a = __fmul2_rn(a, splat(dscale));
-      g = __fmul2_rn(g, splat(dscale));
       h = h * kLcgA + kLcgC;
       const bool k0 = h >= thr;
       h = h * kLcgA + kLcgC;
@@ -193,10 +206,10 @@ XM_DEVICE void bwd_transform(uint32_t (&rh)[32], uint32_t (&rg)[32], const float
       a = f2(k0 ? a.x : 0.f, k1 ? a.y : 0.f);
       g = f2(k0 ? g.x : 0.f, k1 ? g.y : 0.f);
     }
-    rh[e] = __float_as_uint(round_tf32(a.x));
-    rh[e + 1] = __float_as_uint(round_tf32(a.y));
-    rg[e] = __float_as_uint(round_tf32(g.x));
-    rg[e + 1] = __float_as_uint(round_tf32(g.y));
+    rh[e] = __float_as_uint(a.x);
+    rh[e + 1] = __float_as_uint(a.y);
+    rg[e] = __float_as_uint(g.x);
+    rg[e + 1] = __float_as_uint(g.y);
   }
 }
 
@@ -226,47 +239,44 @@ XM_DEVICE float warp_column_sums(const uint32_t (&r)[32], int lane) {
   return v[0];  // column index = lane (bit b of the lane selected the upper half at step b)
 }
 
-// 32 x 32 fp32 block of this warp (one row per lane) -> 2 KB swizzled staging buffer, 16 rows at a time -> TMA store.
-XM_DEVICE void store_block(const CUtensorMap* tm, uint8_t* sb, int lane, const uint32_t (&r)[32], int col, int row0) {
+// 32 consecutive fp32 of one row (128 B, one full line per lane) -> global memory as four 256-bit stores: every
+// store instruction writes 32 complete sectors (16-B stores would write each sector in two halves).
+XM_DEVICE void store_row32(float* dst, const uint32_t (&r)[32]) {
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store has finished reading this buffer
-    __syncwarp();
-    if ((lane >> 4) == half) {
-      const int lr = lane & 15;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(sb + lr * 128 + ((j ^ (lr & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-    }
-    ptx::fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      ptx::tma_store_3d(tm, sb, col, row0 + half * 16, 0);
-      ptx::bulk_commit();
-    }
-  }
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "r"(r[8 * j]), "r"(r[8 * j + 1]),
+                 "r"(r[8 * j + 2]), "r"(r[8 * j + 3]), "r"(r[8 * j + 4]), "r"(r[8 * j + 5]), "r"(r[8 * j + 6]), "r"(r[8 * j + 7])
+                 : "memory");
 }
 
 struct FwdBars {
   uint64_t x_full[2], x_empty[2];
   uint64_t w_full[kFwdRing], w_empty[kFwdRing];
   uint64_t h_full[2], a_ready[2];
-  uint64_t y_full, y_free;
+  uint64_t y_full[2], y_free;  // y_full[g]: completed tiles whose output group g writes (a barrier may only have
+                               // waiters that consume EVERY phase: a waiter skipping phases aliases on the parity)
 };
 
+// Forward.  The MMA warp runs ONE software pipeline over the CTA's whole chunk sequence n = 0, 1, ... (tile = n / nc,
+// chunk = n % nc), crossing tile boundaries:  M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | ...  H buffer = n & 1.
+// The 16 transform warps form two groups of 8 (4 lane quadrants x 2 column halves); group g owns H buffer g, i.e. the
+// chunks with n & 1 == g, so the transform of chunk n + 1 overlaps the transform of chunk n and both overlap the MMAs.
+// The group that transforms a tile's last chunk also writes the tile's output.
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ FwdBars bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ int ops[2 * kMaxChunks];
-  __shared__ int n_ops_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* xs = smem;                    // [2][4] x k-block tiles
   uint8_t* ring = smem + 2 * 4 * kTile;  // [kFwdRing] weight k-block tiles
+  float* sb1 = reinterpret_cast<float*>(ring + kFwdRing * kTile);  // [hidden] + [128]: b1, b2
+  float* sb2 = sb1 + p.hidden;
+  for (int i = threadIdx.x; i < p.hidden + kD; i += blockDim.x) sb1[i] = i < p.hidden ? p.b1[i] : p.b2[i - p.hidden];
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmW1);
@@ -275,16 +285,15 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ptx::mbar_init(&bar.x_full[i], 1);
       ptx::mbar_init(&bar.x_empty[i], 1);
       ptx::mbar_init(&bar.h_full[i], 1);
-      ptx::mbar_init(&bar.a_ready[i], kXfWarps);
+      ptx::mbar_init(&bar.a_ready[i], kXfWarps / 2);
+      ptx::mbar_init(&bar.y_full[i], 1);
     }
     for (int i = 0; i < kFwdRing; ++i) {
       ptx::mbar_init(&bar.w_full[i], 1);
       ptx::mbar_init(&bar.w_empty[i], 1);
     }
-    ptx::mbar_init(&bar.y_full, 1);
-    ptx::mbar_init(&bar.y_free, kXfWarps);
+    ptx::mbar_init(&bar.y_free, kXfWarps / 2);
     ptx::fence_mbar_init();
-    n_ops_s = build_fwd_ops(ops, p.nc);
   }
   if (warp == 1) {
     ptx::tmem_alloc(&tmem_slot, 512);
@@ -295,130 +304,183 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   ptx::tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const uint32_t tY = tmem + 256u;
-  const int n_ops = n_ops_s;
+  const int my_tiles = p.tiles > (int)blockIdx.x ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int N = my_tiles * p.nc;  // chunks this CTA processes
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t ws = 0;  // weight k-blocks requested so far
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        const int xb = it & 1;
-        ptx::mbar_wait(&bar.x_empty[xb], (((uint32_t)it >> 1) & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&bar.x_full[xb], 4 * kTile);
-        for (int kb = 0; kb < 4; ++kb)
-          ptx::tma_load_3d(&tmX, &bar.x_full[xb], xs + (xb * 4 + kb) * kTile, kb * 32, tile * 128, 0);
-        for (int op = 0; op < n_ops; ++op) {
-          const int kind = ops[op] >> 8, c = ops[op] & 255;
-          for (int kb = 0; kb < 4; ++kb, ++ws) {
-            const uint32_t st = ws % kFwdRing;
-            ptx::mbar_wait(&bar.w_empty[st], ((ws / kFwdRing) & 1u) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
-            if (kind == OP_M1)
-              ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W1[128c.., 32kb..]
-            else
-              ptx::tma_load_3d(&tmW2, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W2[:, 128c + 32kb..]
-          }
+      long long tw = 0, tx = 0;
+      int tn = 0;
+      auto log = [&](int kind, int n, long long t0) {
+        if (TRACE && blockIdx.x == 0 && tn < 8192 - 6) {
+          long long* t = p.trace + tn;
+          t[0] = kind; t[1] = n; t[2] = t0; t[3] = clock64(); t[4] = tw; t[5] = tx;
+          tn += 6; tw = 0; tx = 0;
         }
+      };
+      auto load_m1 = [&](int n) {
+        const long long t0 = TRACE ? clock64() : 0;
+        const int it = n / p.nc, c = n - it * p.nc;
+        if (c == 0) {  // first use of this tile's x
+          const int xb = it & 1, tile = (int)blockIdx.x + it * (int)gridDim.x;
+          twait<TRACE>(&bar.x_empty[xb], (((uint32_t)it >> 1) & 1u) ^ 1u, tx);
+          ptx::mbar_arrive_expect_tx(&bar.x_full[xb], 4 * kTile);
+          for (int kb = 0; kb < 4; ++kb)
+            ptx::tma_load_3d(&tmX, &bar.x_full[xb], xs + (xb * 4 + kb) * kTile, kb * 32, tile * 128, 0);
+        }
+        for (int kb = 0; kb < 4; ++kb, ++ws) {
+          const uint32_t st = ws % kFwdRing;
+          twait<TRACE>(&bar.w_empty[st], ((ws / kFwdRing) & 1u) ^ 1u, tw);
+          ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
+          ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W1[128c.., 32kb..]
+        }
+        log(OP_M1, n, t0);
+      };
+      auto load_m2 = [&](int n) {
+        const long long t0 = TRACE ? clock64() : 0;
+        const int c = n % p.nc;
+        for (int kb = 0; kb < 4; ++kb, ++ws) {
+          const uint32_t st = ws % kFwdRing;
+          twait<TRACE>(&bar.w_empty[st], ((ws / kFwdRing) & 1u) ^ 1u, tw);
+          ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
+          ptx::tma_load_3d(&tmW2, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W2[:, 128c + 32kb..]
+        }
+        log(OP_M2, n, t0);
+      };
+      if (N > 0) load_m1(0);
+      if (N > 1) load_m1(1);
+      for (int n = 0; n < N; ++n) {
+        load_m2(n);
+        if (n + 2 < N) load_m1(n + 2);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_tf32(128, 128, 0, 0);
-      uint32_t ws = 0, hu[2] = {0u, 0u};
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        const int xb = it & 1;
-        for (int op = 0; op < n_ops; ++op) {
-          const int kind = ops[op] >> 8, c = ops[op] & 255, b = c & 1;
-          const uint32_t tH = tmem + (uint32_t)(b * 128);
-          if (kind == OP_M1) {
-            if (c == 0) {
-              ptx::mbar_wait(&bar.x_full[xb], ((uint32_t)it >> 1) & 1u);
-              ptx::tc_fence_after_sync();
-            }
-            for (int kb = 0; kb < 4; ++kb, ++ws) {
-              const uint32_t st = ws % kFwdRing;
-              ptx::mbar_wait(&bar.w_full[st], (ws / kFwdRing) & 1u);
-              ptx::tc_fence_after_sync();
-              const uint64_t da = ptx::make_smem_desc(ptx::smem_u32(xs + (xb * 4 + kb) * kTile), 16, 1024, 2);
-              const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
-#pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8)
-                ptx::mma_tf32_ss(tH, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
-              ptx::mma_commit(&bar.w_empty[st]);
-            }
-            ptx::mma_commit(&bar.h_full[b]);
-            if (c == p.nc - 1) ptx::mma_commit(&bar.x_empty[xb]);
-          } else {
-            ptx::mbar_wait(&bar.a_ready[b], hu[b] & 1u);  // the transform warps have written A_c over H_c
-            ++hu[b];
-            ptx::tc_fence_after_sync();
-            if (c == 0) {
-              ptx::mbar_wait(&bar.y_free, ((uint32_t)it & 1u) ^ 1u);  // the epilogue has read the previous tile's Y
-              ptx::tc_fence_after_sync();
-            }
-            for (int kb = 0; kb < 4; ++kb, ++ws) {
-              const uint32_t st = ws % kFwdRing;
-              ptx::mbar_wait(&bar.w_full[st], (ws / kFwdRing) & 1u);
-              ptx::tc_fence_after_sync();
-              const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
-#pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8)
-                mma_tf32_ts(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (c | kb | k8) ? 1u : 0u);
-              ptx::mma_commit(&bar.w_empty[st]);
-            }
-            if (c == p.nc - 1) ptx::mma_commit(&bar.y_full);
-          }
+      uint32_t ws = 0;
+      long long tw = 0, ta = 0;
+      int tn = 0;
+      auto log = [&](int kind, int n, long long t0) {
+        if (TRACE && blockIdx.x == 0 && tn < 8192 - 6) {
+          long long* t = p.trace + 8192 + tn;
+          t[0] = kind; t[1] = n; t[2] = t0; t[3] = clock64(); t[4] = tw; t[5] = ta;
+          tn += 6; tw = 0; ta = 0;
         }
+      };
+      auto mma_m1 = [&](int n) {
+        const long long t0 = TRACE ? clock64() : 0;
+        const int it = n / p.nc, c = n - it * p.nc, xb = it & 1, b = n & 1;
+        const uint32_t tH = tmem + (uint32_t)(b * 128);
+        if (c == 0) {
+          twait<TRACE>(&bar.x_full[xb], ((uint32_t)it >> 1) & 1u, ta);
+          ptx::tc_fence_after_sync();
+        }
+        for (int kb = 0; kb < 4; ++kb, ++ws) {
+          const uint32_t st = ws % kFwdRing;
+          twait<TRACE>(&bar.w_full[st], (ws / kFwdRing) & 1u, tw);
+          ptx::tc_fence_after_sync();
+          const uint64_t da = ptx::make_smem_desc(ptx::smem_u32(xs + (xb * 4 + kb) * kTile), 16, 1024, 2);
+          const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8)
+            ptx::mma_tf32_ss(tH, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+          ptx::mma_commit(&bar.w_empty[st]);
+        }
+        ptx::mma_commit(&bar.h_full[b]);
+        if (c == p.nc - 1) ptx::mma_commit(&bar.x_empty[xb]);
+        log(OP_M1, n, t0);
+      };
+      auto mma_m2 = [&](int n) {
+        const long long t0 = TRACE ? clock64() : 0;
+        const int it = n / p.nc, c = n - it * p.nc, b = n & 1;
+        const uint32_t tH = tmem + (uint32_t)(b * 128);
+        twait<TRACE>(&bar.a_ready[b], ((uint32_t)n >> 1) & 1u, ta);  // group b has written A over H
+        ptx::tc_fence_after_sync();
+        if (c == 0) {
+          twait<TRACE>(&bar.y_free, ((uint32_t)it & 1u) ^ 1u, ta);  // the previous tile's Y has been read out
+          ptx::tc_fence_after_sync();
+        }
+        for (int kb = 0; kb < 4; ++kb, ++ws) {
+          const uint32_t st = ws % kFwdRing;
+          twait<TRACE>(&bar.w_full[st], (ws / kFwdRing) & 1u, tw);
+          ptx::tc_fence_after_sync();
+          const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8)
+            mma_tf32_ts(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (c | kb | k8) ? 1u : 0u);
+          ptx::mma_commit(&bar.w_empty[st]);
+        }
+        if (c == p.nc - 1) ptx::mma_commit(&bar.y_full[b]);  // group b transformed this chunk and writes the tile
+        log(OP_M2, n, t0);
+      };
+      if (N > 0) mma_m1(0);
+      if (N > 1) mma_m1(1);
+      for (int n = 0; n < N; ++n) {
+        mma_m2(n);
+        if (n + 2 < N) mma_m1(n + 2);
       }
     }
   } else {
-    const int q = warp & 3;             // TMEM lane quadrant this warp may access
-    const int part = (warp - 2) >> 2;   // which 32 of the chunk's 128 columns
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int pidx = (warp - 2) >> 2;    // 0..3
+    const int g = pidx >> 1;             // transform group = H buffer
+    const int sub = pidx & 1;            // which 64 of the chunk's 128 columns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint32_t hu[2] = {0u, 0u};
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-      const long long row = (long long)tile * 128 + q * 32 + lane;
+    const float cs = kTruncComp * p.dscale;
+    uint32_t n_out = 0;  // tiles this group has written
+    int tn = 0;
+    for (int n = g; n < N; n += 2) {
+      const int it = n / p.nc, c = n - it * p.nc;
+      const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + q * 32 + lane;
+      const long long t0 = TRACE ? clock64() : 0;
+      ptx::mbar_wait(&bar.h_full[g], ((uint32_t)n >> 1) & 1u);
+      const long long t1 = TRACE ? clock64() : 0;
+      ptx::tc_fence_after_sync();
       const uint32_t rs = p.thr ? row_seed((unsigned long long)row, p.seed) : 0u;
-      for (int c = 0; c < p.nc; ++c) {
-        const int b = c & 1;
-        ptx::mbar_wait(&bar.h_full[b], hu[b] & 1u);
-        ++hu[b];
-        ptx::tc_fence_after_sync();
-        const uint32_t addr = tmem + (uint32_t)(b * 128 + part * 32) + lane_base;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col0 = sub * 64 + j * 32;
+        const uint32_t addr = tmem + (uint32_t)(g * 128 + col0) + lane_base;
         uint32_t r[32];
         ptx::tmem_ld_32x32(addr, r);
         ptx::tmem_ld_wait();
-        const float* bias = p.b1 + c * kChunk + part * 32;
+        const float* bias = sb1 + c * kChunk + col0;
         if (p.thr)
-          fwd_transform<true>(r, bias, p.act, p.dscale, p.thr, group_seed(rs, c * 4 + part));
+          fwd_transform<true>(r, bias, p.act, cs, p.thr, group_seed(rs, (c * kChunk + col0) >> 5));
         else
-          fwd_transform<false>(r, bias, p.act, 1.0f, 0u, 0u);
+          fwd_transform<false>(r, bias, p.act, cs, 0u, 0u);
         ptx::tmem_st_32x32(addr, r);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar.a_ready[b]);
       }
-      // ---- tile done: y = Y + b2
-      ptx::mbar_wait(&bar.y_full, (uint32_t)it & 1u);
-      ptx::tc_fence_after_sync();
-      {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tY + (uint32_t)(part * 32) + lane_base, r);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar.a_ready[g]);
+      if (TRACE && blockIdx.x == 0 && q == 0 && sub == 0 && lane == 0 && tn < 4096 - 6) {
+        long long* t = p.trace + 16384 + g * 4096 + tn;
+        t[0] = 4; t[1] = n; t[2] = t0; t[3] = t1; t[4] = clock64(); t[5] = 0;
+        tn += 6;
+      }
+      if (c == p.nc - 1) {
+        // ---- this group also writes the tile's output: y = Y + b2 (64 columns per warp)
+        ptx::mbar_wait(&bar.y_full[g], n_out & 1u);
+        ++n_out;
+        ptx::tc_fence_after_sync();
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(tY + (uint32_t)(sub * 64) + lane_base, r0);
+        ptx::tmem_ld_32x32(tY + (uint32_t)(sub * 64 + 32) + lane_base, r1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar.y_free);  // Y is in registers: the next tile may overwrite it
-        if (row < p.M) {
-          float4* dst = reinterpret_cast<float4*>(p.y + row * kD + part * 32);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + part * 32) + e);
-            dst[e] = make_float4(__uint_as_float(r[4 * e]) + bb.x, __uint_as_float(r[4 * e + 1]) + bb.y,
-                                 __uint_as_float(r[4 * e + 2]) + bb.z, __uint_as_float(r[4 * e + 3]) + bb.w);
-          }
+        for (int e = 0; e < 32; ++e) {
+          r0[e] = __float_as_uint(__uint_as_float(r0[e]) + sb2[sub * 64 + e]);
+          r1[e] = __float_as_uint(__uint_as_float(r1[e]) + sb2[sub * 64 + 32 + e]);
+        }
+        if (row < p.M) {
+          store_row32(p.y + row * kD + sub * 64, r0);
+          store_row32(p.y + row * kD + sub * 64 + 32, r1);
         }
       }
     }
@@ -434,15 +496,18 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 struct BwdBars {
   uint64_t in_full, in_empty;
   uint64_t w_full[kBwdRing], w_empty[kBwdRing];
-  uint64_t g_full, d_ready;
-  uint64_t x_done, xacc_free;
+  uint64_t g_full[2], d_ready;   // g_full[g] / x_done[g]: the phases transform group g consumes (every one of them)
+  uint64_t x_done[2], xacc_free;
 };
 
+// Data gradient.  MMA order per tile as in the header comment; G is single-buffered, so the transform of chunk c
+// sits between M3(c) and [M4(c), M3(c + 1)].  The two transform groups alternate chunks: while group g streams the
+// A / dH block of chunk c out to global memory (256-bit stores, one full line per lane) and folds dH into the bias
+// gradient, the other group already transforms chunk c + 1.
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2t,
-                 const __grid_constant__ CUtensorMap tmW1t, const __grid_constant__ CUtensorMap tmA,
-                 const __grid_constant__ CUtensorMap tmDH, const Params p) {
+                 const __grid_constant__ CUtensorMap tmW1t, float* __restrict__ out_a, float* __restrict__ out_dh, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ BwdBars bar;
   __shared__ uint32_t tmem_slot;
@@ -454,25 +519,26 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* xs = smem;                       // [4] x k-block tiles (K = input features)
   uint8_t* ys = smem + 4 * kTile;           // [4] dY k-block tiles (K = output features)
   uint8_t* ring = smem + 8 * kTile;         // [kBwdRing] weight k-block tiles
-  uint8_t* staging = ring + kBwdRing * kTile;
+  float* sb1 = reinterpret_cast<float*>(ring + kBwdRing * kTile);
+  for (int i = threadIdx.x; i < p.hidden; i += blockDim.x) sb1[i] = p.b1[i];
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmDY);
     ptx::prefetch_tensormap(&tmW1);
     ptx::prefetch_tensormap(&tmW2t);
     ptx::prefetch_tensormap(&tmW1t);
-    ptx::prefetch_tensormap(&tmA);
-    ptx::prefetch_tensormap(&tmDH);
     ptx::mbar_init(&bar.in_full, 1);
     ptx::mbar_init(&bar.in_empty, 1);
     for (int i = 0; i < kBwdRing; ++i) {
       ptx::mbar_init(&bar.w_full[i], 1);
       ptx::mbar_init(&bar.w_empty[i], 1);
     }
-    ptx::mbar_init(&bar.g_full, 1);
-    ptx::mbar_init(&bar.d_ready, kXfWarps);
-    ptx::mbar_init(&bar.x_done, 1);
-    ptx::mbar_init(&bar.xacc_free, kXfWarps);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bar.g_full[i], 1);
+      ptx::mbar_init(&bar.x_done[i], 1);
+    }
+    ptx::mbar_init(&bar.d_ready, kXfWarps / 2);
+    ptx::mbar_init(&bar.xacc_free, kXfWarps / 2);
     ptx::fence_mbar_init();
     n_ops_s = build_bwd_ops(ops, p.nc);
   }
@@ -528,11 +594,11 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             ptx::tc_fence_after_sync();
           }
           if (kind == OP_M4) {
-            ptx::mbar_wait(&bar.d_ready, cu & 1u);  // the transform warps have read H_c, G_c and written dH_c over G_c
+            ptx::mbar_wait(&bar.d_ready, cu & 1u);  // a transform group has read H_c, G_c and written dH_c over G_c
             ++cu;
             ptx::tc_fence_after_sync();
             if (c == 0) {
-              ptx::mbar_wait(&bar.xacc_free, ((uint32_t)it & 1u) ^ 1u);  // the epilogue has read the previous tile's dX
+              ptx::mbar_wait(&bar.xacc_free, ((uint32_t)it & 1u) ^ 1u);  // the previous tile's dX has been read out
               ptx::tc_fence_after_sync();
             }
           }
@@ -554,79 +620,79 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
             ptx::mma_commit(&bar.w_empty[st]);
           }
+          const int n = it * p.nc + c;  // position in the CTA's chunk sequence: group n & 1 transforms it
           if (kind == OP_M3) {
-            ptx::mma_commit(&bar.g_full);  // H_c (issued earlier) and G_c are complete
+            ptx::mma_commit(&bar.g_full[n & 1]);  // H_c (issued earlier) and G_c are complete
             if (c == p.nc - 1) ptx::mma_commit(&bar.in_empty);
           }
-          if (kind == OP_M4 && c == p.nc - 1) ptx::mma_commit(&bar.x_done);
+          if (kind == OP_M4 && c == p.nc - 1) ptx::mma_commit(&bar.x_done[n & 1]);
         }
       }
     }
   } else {
     const int q = warp & 3;
-    const int part = (warp - 2) >> 2;
+    const int pidx = (warp - 2) >> 2;
+    const int g = pidx >> 1;   // transform group: takes every other chunk of the CTA's chunk sequence
+    const int sub = pidx & 1;  // which 64 of the chunk's 128 columns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint8_t* sb = staging + (warp - 2) * kStage;
-    float colacc[kMaxChunks];  // column sums of dH over this warp's rows of every tile: column c*128 + part*32 + lane
-#pragma unroll
-    for (int k = 0; k < kMaxChunks; ++k) colacc[k] = 0.f;
-    uint32_t cu = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-      const int row0 = tile * 128 + q * 32;
-      const long long row = (long long)row0 + lane;
-      const uint32_t rs = p.thr ? row_seed((unsigned long long)row, p.seed) : 0u;
-      for (int c = 0; c < p.nc; ++c, ++cu) {
-        ptx::mbar_wait(&bar.g_full, cu & 1u);
-        ptx::tc_fence_after_sync();
-        uint32_t rh[32], rg[32];
-        ptx::tmem_ld_32x32(tmem + (uint32_t)((c & 1) * 128 + part * 32) + lane_base, rh);
-        ptx::tmem_ld_32x32(tG + (uint32_t)(part * 32) + lane_base, rg);
-        ptx::tmem_ld_wait();
-        const float* bias = p.b1 + c * kChunk + part * 32;
-        if (p.thr)
-          bwd_transform<true>(rh, rg, bias, p.act, p.dscale, p.thr, group_seed(rs, c * 4 + part));
-        else
-          bwd_transform<false>(rh, rg, bias, p.act, 1.0f, 0u, 0u);
-        ptx::tmem_st_32x32(tG + (uint32_t)(part * 32) + lane_base, rg);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar.d_ready);
-        // the MMA warp proceeds; this warp now streams its A / dH block out and folds dH into the bias gradient
-        const float cs = warp_column_sums(rg, lane);  // rows >= M carry dY = 0, hence dH = 0
-#pragma unroll
-        for (int k = 0; k < kMaxChunks; ++k) colacc[k] += (k == c) ? cs : 0.f;
-        const int col = c * kChunk + part * 32;
-        store_block(&tmA, sb, lane, rh, col, row0);
-        store_block(&tmDH, sb, lane, rg, col, row0);
-      }
-      // ---- tile done: dX
-      ptx::mbar_wait(&bar.x_done, (uint32_t)it & 1u);
+    const float cs = kTruncComp * p.dscale;
+    const int my_tiles = p.tiles > (int)blockIdx.x ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int N = my_tiles * p.nc;
+    uint32_t n_out = 0;  // tiles whose dX this group has written
+    for (int n = g; n < N; n += 2) {
+      const int it = n / p.nc, c = n - it * p.nc;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const long long row = (long long)tile * 128 + q * 32 + lane;
+      ptx::mbar_wait(&bar.g_full[g], ((uint32_t)n >> 1) & 1u);
       ptx::tc_fence_after_sync();
-      {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tX + (uint32_t)(part * 32) + lane_base, r);
+      const uint32_t rs = p.thr ? row_seed((unsigned long long)row, p.seed) : 0u;
+      // Column half j = 0 is written out right away, half j = 1 after the hand-over to the MMA warp (holding both
+      // halves' A and dH blocks at once would need 128 registers).
+      uint32_t ra[32], rd[32];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col0 = sub * 64 + j * 32;
+        ptx::tmem_ld_32x32(tmem + (uint32_t)((c & 1) * 128 + col0) + lane_base, ra);
+        ptx::tmem_ld_32x32(tG + (uint32_t)col0 + lane_base, rd);
+        ptx::tmem_ld_wait();
+        const float* bias = sb1 + c * kChunk + col0;
+        if (p.thr)
+          bwd_transform<true>(ra, rd, bias, p.act, cs, p.thr, group_seed(rs, (c * kChunk + col0) >> 5));
+        else
+          bwd_transform<false>(ra, rd, bias, p.act, cs, 0u, 0u);
+        ptx::tmem_st_32x32(tG + (uint32_t)col0 + lane_base, rd);
+        if (j == 1) {
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bar.d_ready);  // the MMA warp (and the other group) proceed
+        }
+        const int col = c * kChunk + col0;
+        if (row < p.M) {
+          store_row32(out_a + row * p.hidden + col, ra);
+          store_row32(out_dh + row * p.hidden + col, rd);
+        }
+        const float csum = warp_column_sums(rd, lane) * (1.0f / kTruncComp);  // rows >= M carry dY = 0, hence dH = 0
+        if (p.db1_part != nullptr) p.db1_part[((long long)tile * 4 + q) * p.hidden + col + lane] = csum;
+      }
+      if (c == p.nc - 1) {
+        // ---- this group also writes the tile's dX (64 columns per warp)
+        ptx::mbar_wait(&bar.x_done[g], n_out & 1u);
+        ++n_out;
+        ptx::tc_fence_after_sync();
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(tX + (uint32_t)(sub * 64) + lane_base, r0);
+        ptx::tmem_ld_32x32(tX + (uint32_t)(sub * 64 + 32) + lane_base, r1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar.xacc_free);
         if (row < p.M) {
-          float4* dst = reinterpret_cast<float4*>(p.dx + row * kD + part * 32);
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            dst[e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]), __uint_as_float(r[4 * e + 2]),
-                                 __uint_as_float(r[4 * e + 3]));
+          store_row32(p.dx + row * kD + sub * 64, r0);
+          store_row32(p.dx + row * kD + sub * 64 + 32, r1);
         }
       }
     }
-    if (p.db1_part != nullptr) {
-      float* dst = p.db1_part + ((long long)blockIdx.x * 4 + q) * p.hidden + part * 32 + lane;
-#pragma unroll
-      for (int k = 0; k < kMaxChunks; ++k)
-        if (k < p.nc) dst[k * kChunk] = colacc[k];
-    }
-    if (lane == 0) ptx::bulk_wait_all();  // staged blocks fully written before the CTA (and its smem) retires
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -685,6 +751,8 @@ static int fill(Params& p, int64_t M, int64_t D, int64_t hidden, int act, float 
 
 using namespace xm;
 
+static long long* g_ffn_trace = nullptr;
+
 extern "C" {
 
 int xm_ffn_fused_supported(int64_t D, int64_t hidden, int act) {
@@ -692,15 +760,12 @@ int xm_ffn_fused_supported(int64_t D, int64_t hidden, int act) {
          (act == XM_ACT_GELU || act == XM_ACT_RELU);
 }
 
-int xm_ffn_fused_nblk(int64_t M) {
-  const int64_t tiles = (M + 127) / 128;
-  return (int)(tiles < kNumSMs ? tiles : kNumSMs) * 4;
-}
+int xm_ffn_fused_nblk(int64_t M) { return (int)((M + 127) / 128) * 4; }
 
 int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y, int64_t M,
                          int64_t D, int64_t hidden, int act, float drop_p, uint64_t seed, void* stream) {
   if (!x || !w1 || !b1 || !w2 || !b2 || !y) return XM_ERR_INVALID;
-  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(b2)) & 15) return XM_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(y) & 31) return XM_ERR_INVALID;
   ffn::Params p{};
   int rc = ffn::fill(p, M, D, hidden, act, drop_p, seed);
   if (rc != XM_OK) return rc;
@@ -711,36 +776,46 @@ int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const
   rc = encode_tmap(&mx, ffn::view2(x, D, M), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m1, ffn::view2(w1, D, hidden), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m2, ffn::view2(w2, hidden, D), 32, 128, 0);
-  if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_fwd_kernel, ffn::kFwdSmem);
-  if (rc != XM_OK) return rc;
   const int ctas = p.tiles < kNumSMs ? p.tiles : kNumSMs;
-  ffn::ffn_fwd_kernel<<<ctas, ffn::kThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
+  if (g_ffn_trace != nullptr) {  // debug instance: CTA 0 logs per-op clocks (xm_debug_set_ffn_trace)
+    p.trace = g_ffn_trace;
+    if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_fwd_kernel<true>, ffn::kFwdSmem);
+    if (rc != XM_OK) return rc;
+    ffn::ffn_fwd_kernel<true><<<ctas, ffn::kThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
+    return check_launch();
+  }
+  if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_fwd_kernel<false>, ffn::kFwdSmem);
+  if (rc != XM_OK) return rc;
+  ffn::ffn_fwd_kernel<false><<<ctas, ffn::kThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
   return check_launch();
+}
+
+int xm_debug_set_ffn_trace(int64_t* device_buffer) {
+  g_ffn_trace = reinterpret_cast<long long*>(device_buffer);
+  return XM_OK;
 }
 
 int xm_ffn_fused_dgrad_f32(const float* x, const float* dy, const float* w1, const float* b1, const float* w2t, const float* w1t,
                            float* a, float* dh, float* dx, float* db1_part, int64_t M, int64_t D, int64_t hidden, int act,
                            float drop_p, uint64_t seed, void* stream) {
   if (!x || !dy || !w1 || !b1 || !w2t || !w1t || !a || !dh || !dx) return XM_ERR_INVALID;
-  if ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(b1)) & 15) return XM_ERR_INVALID;
   ffn::Params p{};
   int rc = ffn::fill(p, M, D, hidden, act, drop_p, seed);
   if (rc != XM_OK) return rc;
   p.b1 = b1;
   p.dx = dx;
   p.db1_part = db1_part;
-  CUtensorMap mx, my, m1, m2t, m1t, ma, mdh;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(dx)) & 31) return XM_ERR_INVALID;
+  CUtensorMap mx, my, m1, m2t, m1t;
   rc = encode_tmap(&mx, ffn::view2(x, D, M), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&my, ffn::view2(dy, D, M), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m1, ffn::view2(w1, D, hidden), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m2t, ffn::view2(w2t, D, hidden), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m1t, ffn::view2(w1t, hidden, D), 32, 128, 0);
-  if (rc == XM_OK) rc = encode_tmap(&ma, ffn::view2(a, hidden, M), 32, 16, 0);
-  if (rc == XM_OK) rc = encode_tmap(&mdh, ffn::view2(dh, hidden, M), 32, 16, 0);
   if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_dgrad_kernel, ffn::kBwdSmem);
   if (rc != XM_OK) return rc;
   const int ctas = p.tiles < kNumSMs ? p.tiles : kNumSMs;
-  ffn::ffn_dgrad_kernel<<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, ma, mdh, p);
+  ffn::ffn_dgrad_kernel<<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, a, dh, p);
   return check_launch();
 }
 

@@ -38,6 +38,19 @@ def aggregate_roi_timeseries(x: torch.Tensor, agg_method: str = "both") -> torch
     return both
 
 
+def connectivity_from_timeseries(x: torch.Tensor) -> torch.Tensor:
+    """x (B, TR, ROI) CUDA fp32 -> (B, ROI*ROI): the flattened ROI x ROI Pearson correlation matrix of every sample
+    (numpy.corrcoef of the columns, NaN -> 0 first) -- fMRIFusionNet's `connectivity` input derived on the device
+    from the same series the activation features come from, instead of a 4*ROI*ROI-byte row per sample crossing
+    PCIe (the reference reads precomputed matrices from CSV, fmri_utils.py:161-198)."""
+    if x.dim() != 3:
+        raise ValueError("expected (subjects, TR, ROI)")
+    if x.shape[0] == 0 or x.shape[2] == 0:
+        return torch.empty(x.shape[0], x.shape[2] * x.shape[2], device=x.device, dtype=torch.float32)
+    from . import ops
+    return ops.roi_corrcoef(x)
+
+
 # ------------------------------------------------------------------------- CSV loaders (fmri_utils.py:115-241)
 def _read_numeric_csv(filepath) -> np.ndarray:
     """One reference CSV as fp32 (rows, columns) with the 'Subject' column dropped and NaN -> 0

@@ -139,11 +139,18 @@ class ConvBnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, cfg):
-        eps, momentum, act, pool, p, dbp, training, round_out = cfg
+        eps, momentum, act, pool, p, dbp, training, round_out, precise = cfg
         Cout, Cin, taps = w.shape
         x = ops.as_nwc(x)
         wk, wt = ops.conv1d_pack_weight(w)
-        y = ops.conv1d_fwd(x, wk, b, Cout)
+        if precise:
+            # fp32-accurate forward on the tf32 tensor cores: x = xh + xl, w = wh + wl, y = xh wh + xl wh + xh wl as
+            # ONE conv over 3 Cin stacked channels [xh | xl | xh] x [wh | wh | wl].  The first two convs of the v4
+            # encoder need it: their single-pass operand rounding alone puts 7e-3 .. 1e-2 on five parameter
+            # gradients (tools/tf32_floor_by_layer.py, profiles/r2_tf32_floor_by_layer.json); the backward does not.
+            y, x = ops.conv1d_fwd_precise(x, w, b)  # x: now the tf32-rounded input, operand of the weight gradient
+        else:
+            y = ops.conv1d_fwd(x, wk, b, Cout)
         mean, invstd, count = _bn_stats(y, eps, running_mean, running_var, momentum, training)
         seed = next_seed() if (training and p > 0) else 0
         pd = p if training else 0.0
@@ -179,10 +186,16 @@ def _bn_momentum(bn, training) -> float:
     return 0.0
 
 
-def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=False, training=True, round_out=True):
-    """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d)."""
+# fp32-accurate (3-pass) forward of the convolutions the modules mark `precise` (XM_CONV_PRECISE=0: single pass, for A/B)
+CONV_PRECISE = os.environ.get("XM_CONV_PRECISE", "1") != "0"
+
+
+def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=False, training=True, round_out=True,
+                precise=False):
+    """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d).  `precise`: the input is
+    NOT tf32-rounded by its producer and the conv forward runs in the 3-pass mode (see ConvBnAct)."""
     cfg = (bn.eps, _bn_momentum(bn, training), act, pool, float(drop_p), bool(drop_before_pool),
-           bool(training), bool(round_out))
+           bool(training), bool(round_out), bool(precise))
     return ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
 
 

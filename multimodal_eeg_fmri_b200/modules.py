@@ -40,6 +40,14 @@ class Slots(nn.Module):
 
 
 # ------------------------------------------------------------------------- transformer tail
+class _PreciseFirstConv:
+    @property
+    def wants_unrounded_input(self) -> bool:
+        """True when the first conv runs in the 3-pass (fp32-accurate) mode: a channels-last input handed in by the
+        caller (e.g. the window gather) must then NOT be tf32-rounded."""
+        return XF.CONV_PRECISE
+
+
 class PositionalEncoding(nn.Module):
     """EEG_CODE/enhanced_models_v4.py:30-55 -- sinusoidal table `pe` (max_len, 1, d) + dropout."""
 
@@ -102,7 +110,7 @@ class TemporalTransformerBlock(nn.Module):
         return x + XF.act_dropout(h, None, self.p, self.training)
 
 
-class _TransformerTail(nn.Module):
+class _TransformerTail(_PreciseFirstConv, nn.Module):
     """pos_encoder / transformer_layers / output_proj members shared by the two v4 encoders."""
 
     def _init_tail(self, hidden_dim, num_layers, num_heads, dropout):
@@ -155,9 +163,10 @@ class EnhancedERPEncoder(_TransformerTail):
         """(B, C, T) [or (B, T, C) with channels_last=True, e.g. straight from the window gather] ->
         channels-last (B, T/2, hidden) output of the `conv_layers` Sequential."""
         c, p, tr = self.conv_layers, self.dropout_p, self.training
-        h = x if channels_last else XF.to_channels_last(x)
-        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 0, p, False, tr)
-        h = XF.conv_bn_act(h, c[4], c[5], "gelu", 2, p, False, tr)           # GELU -> MaxPool -> Dropout
+        pr = XF.CONV_PRECISE  # fp32-accurate forward of the first two convs (their inputs then stay un-rounded)
+        h = x if channels_last else XF.to_channels_last(x, round_out=not pr)
+        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 0, p, False, tr, round_out=not pr, precise=pr)
+        h = XF.conv_bn_act(h, c[4], c[5], "gelu", 2, p, False, tr, precise=pr)  # GELU -> MaxPool -> Dropout
         return XF.conv_bn_act(h, c[9], c[10], "gelu", 0, p, False, tr, round_out=False)
 
     def forward(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
@@ -178,9 +187,10 @@ class EnhancedPowerEncoder(_TransformerTail):
         self._init_tail(hidden_dim, num_transformer_layers, num_heads, dropout)
 
     def conv_stack(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
-        tr = self.training
-        h = x if channels_last else XF.to_channels_last(x)
-        s = [XF.conv_bn_act(h, m[0], m[1], "gelu", 0, 0.0, False, tr) for m in (self.conv_scale1, self.conv_scale2, self.conv_scale3)]
+        tr, pr = self.training, XF.CONV_PRECISE
+        h = x if channels_last else XF.to_channels_last(x, round_out=not pr)
+        s = [XF.conv_bn_act(h, m[0], m[1], "gelu", 0, 0.0, False, tr, precise=pr)
+             for m in (self.conv_scale1, self.conv_scale2, self.conv_scale3)]
         h = torch.cat(s, dim=2)  # channel concat in the channels-last layout
         return XF.conv_bn_act(h, self.fusion[0], self.fusion[1], "gelu", 0, self.dropout_p, False, tr, round_out=False)
 
@@ -188,7 +198,7 @@ class EnhancedPowerEncoder(_TransformerTail):
         return self._tail(self.conv_stack(x, channels_last))
 
 
-class _LiteEncoder(nn.Module):
+class _LiteEncoder(_PreciseFirstConv, nn.Module):
     """crossmodal_v4_enhancements.py:817-877 -- Conv-BN-GELU-Drop-MaxPool2, Conv-BN-GELU-Drop-AvgPool(1),
     Flatten-Linear-GELU-Drop."""
 
@@ -202,9 +212,9 @@ class _LiteEncoder(nn.Module):
         self.output = Slots({1: nn.Linear(hidden_dim, hidden_dim)})
 
     def forward(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
-        c, p, tr = self.conv_layers, self.dropout_p, self.training
-        h = x if channels_last else XF.to_channels_last(x)
-        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 2, p, True, tr)            # Dropout BEFORE MaxPool here
+        c, p, tr, pr = self.conv_layers, self.dropout_p, self.training, XF.CONV_PRECISE
+        h = x if channels_last else XF.to_channels_last(x, round_out=not pr)
+        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 2, p, True, tr, precise=pr)  # Dropout BEFORE MaxPool here
         h = XF.conv_bn_act(h, c[5], c[6], "gelu", 0, p, False, tr, round_out=False)
         h = XF.seq_mean(h)
         return XF.act_dropout(XF.linear(h, self.output[1]), "gelu", p, tr)

@@ -229,6 +229,23 @@ def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
     return y
 
 
+def conv1d_fwd_precise(x, w, bias):
+    """fp32-accurate conv forward on the tf32 tensor cores: x (B, T, Cin) channels-last and NOT rounded, w (Cout, Cin,
+    taps) in the reference layout.  x = xh + xl, w = wh + wl, y = xh wh + xl wh + xh wl as ONE conv over 3 Cin
+    stacked channels [xh | xl | xh] x [wh | wh | wl].  -> (y (B, T, Cout), xh view (B, T, Cin): the tf32-rounded
+    input, what a single-pass weight gradient reads)."""
+    _chk(x, w, bias)
+    x = as_nwc(x)
+    B, T, Cin = x.shape
+    Cout, _, taps = w.shape
+    if x.stride(1) != Cin:
+        x = x.contiguous()
+    x3 = split3(x.view(B * T, Cin), 0, 1).view(B, T, 3 * Cin)
+    w3 = split3(w.reshape(Cout, Cin * taps), 1, 1).view(Cout, 3 * Cin, taps)
+    wk3, _ = conv1d_pack_weight(w3)
+    return conv1d_fwd(x3, wk3, bias, Cout), x3[:, :, :Cin]
+
+
 def conv1d_dgrad(dy, wt, Cin, round_out=False):
     _chk(dy, wt)
     dy = as_nwc(dy)
@@ -941,4 +958,15 @@ def roi_meanstd(x):
     out = torch.empty(B, 2 * ROI, device=x.device, dtype=torch.float32)
     _w(3.0 * x.numel(), 4.0 * (x.numel() + out.numel()))
     _call("xm_roi_meanstd_f32", _p(x), B, TR, ROI, _p(out), _stream())
+    return out
+
+
+def roi_corrcoef(x):
+    """x (B, TR, ROI) -> (B, ROI*ROI): flattened per-sample Pearson correlation matrix of the ROI columns over TR."""
+    _chk(x)
+    x = x.contiguous()
+    B, TR, ROI = x.shape
+    out = torch.empty(B, ROI * ROI, device=x.device, dtype=torch.float32)
+    _w(2.0 * B * TR * ROI * ROI, 4.0 * (x.numel() + out.numel()))
+    _call("xm_roi_corrcoef_f32", _p(x), B, TR, ROI, _p(out), _stream())
     return out

@@ -63,9 +63,14 @@ class PairedBridgeModel(nn.Module):
 
     def _fmri_features(self, roi_series, conn):
         act = fmri_utils.aggregate_roi_timeseries(roi_series, "both")
+        if conn is None:  # functional connectivity derived on the device from the same ROI series
+            conn = fmri_utils.connectivity_from_timeseries(roi_series)
         return self.fmri_net.features(act, conn)
 
-    def embed(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: torch.Tensor, eeg_channels_last: bool = False):
+    def embed(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None,
+              eeg_channels_last: bool = False):
+        """conn: (B, conn_dim) connectivity features, or None to derive them as the flattened ROI x ROI correlation
+        matrix of `roi_series` on the device (conn_dim must then be n_roi ** 2)."""
         if not (self.overlap_branches and eeg.is_cuda):
             eeg_feat = self.eeg_encoder(eeg, channels_last=eeg_channels_last)
             return self.bridge.project(eeg_feat, self._fmri_features(roi_series, conn))
@@ -79,11 +84,12 @@ class PairedBridgeModel(nn.Module):
         eeg_feat = self.eeg_encoder(eeg, channels_last=eeg_channels_last)
         cur.wait_stream(side)
         for t in (roi_series, conn):
-            t.record_stream(side)
+            if t is not None:
+                t.record_stream(side)
         fmri_feat.record_stream(cur)
         return self.bridge.project(eeg_feat, fmri_feat)
 
-    def forward(self, eeg, roi_series, conn, eeg_channels_last: bool = False) -> torch.Tensor:
+    def forward(self, eeg, roi_series, conn=None, eeg_channels_last: bool = False) -> torch.Tensor:
         e, f = self.embed(eeg, roi_series, conn, eeg_channels_last)
         return XF.symmetric_infonce(e, f, self.temperature)
 
@@ -122,14 +128,14 @@ class PairedTrainer:
         self._stage = {}
 
     # -- device-resident step ---------------------------------------------------------------
-    def step(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: torch.Tensor) -> torch.Tensor:
+    def step(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None) -> torch.Tensor:
         """eeg: raw recordings (R, C, n) when a window spec was given (gathered on the device into
-        B = R*n_win channels-last windows), else windows (B, C, T).  Returns the loss (device scalar,
-        this rank's share of the global loss)."""
+        B = R*n_win channels-last windows), else windows (B, C, T); conn None: connectivity derived on the device
+        from roi_series.  Returns the loss (device scalar, this rank's share of the global loss)."""
         self.flat_grad.zero_()
         if self.window is not None:
             x = ops.window_gather(eeg, self.window, self.hop or self.window, channels_last=True,
-                                                 round_out=True)
+                                  round_out=not getattr(self.model.eeg_encoder, "wants_unrounded_input", False))
             loss = self.model(x, roi_series, conn, eeg_channels_last=True)
         else:
             loss = self.model(eeg, roi_series, conn)
@@ -143,11 +149,13 @@ class PairedTrainer:
         return loss.detach()
 
     # -- end-to-end step from pinned host buffers --------------------------------------------
-    def step_from_host(self, eeg_h: torch.Tensor, roi_h: torch.Tensor, conn_h: torch.Tensor) -> float:
+    def step_from_host(self, eeg_h: torch.Tensor, roi_h: torch.Tensor, conn_h: Optional[torch.Tensor] = None) -> float:
         """Host -> device copies of this step's inputs, the step, and the loss read back."""
         dev = self.flat_grad.device
         bufs = []
         for name, h in (("eeg", eeg_h), ("roi", roi_h), ("conn", conn_h)):
+            if h is None:
+                continue
             d = self._stage.get(name)
             if d is None or d.shape != h.shape:
                 d = torch.empty(h.shape, device=dev, dtype=h.dtype)

@@ -194,6 +194,18 @@ def roi_meanstd(x: torch.Tensor) -> torch.Tensor:
     return torch.cat([x.mean(1), x.std(1, unbiased=False)], dim=1)
 
 
+def roi_connectivity(x: torch.Tensor) -> torch.Tensor:
+    """(B, TR, ROI) -> (B, ROI*ROI): flattened per-sample numpy.corrcoef of the ROI columns (NaN -> 0 first).
+    AUTHORED definition, PARITY UNPINNED: the reference only reads precomputed connectivity matrices from CSV
+    (fmri_utils.py:161-198); SURVEY.md section 8d defines the synthetic connectivity input as this corrcoef.
+    Pinned by a numpy.corrcoef known-answer test (tests/test_oracle_paired_step.py)."""
+    xc = torch.nan_to_num(x)
+    xc = xc - xc.mean(1, keepdim=True)
+    c = xc.transpose(1, 2) @ xc
+    d = torch.sqrt(torch.diagonal(c, dim1=1, dim2=2))
+    return (c / d[:, :, None] / d[:, None, :]).clamp(-1, 1).reshape(x.shape[0], -1)
+
+
 def fmri_mlp_encoder(P: SD, pre: str, x, train: bool = True):
     """ActivationEncoder / ConnectivityEncoder, fMRI_CODE/fmri_utils.py:23-56."""
     e = pre + "encoder."

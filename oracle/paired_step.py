@@ -22,7 +22,7 @@ SD = Dict[str, torch.Tensor]
 
 
 def paired_embeddings(P: SD, eeg, roi_series, conn, encoder: str = "v4", nhead: int = 4, train: bool = True):
-    """eeg (B, C, T), roi_series (B, TR, ROI), conn (B, conn_dim) -> the two (B, bridge_dim) embeddings.
+    """eeg (B, C, T), roi_series (B, TR, ROI), conn (B, conn_dim) | None -> the two (B, bridge_dim) embeddings.
 
     EEG encoder (enhanced_models_v4.py:114-193 or crossmodal_v4_enhancements.py:817-845) ->
     eeg_proj (bridge_utils.py:34-39,71); ROI mean/std (fmri_utils.py:140-147) -> fMRIFusionNet fused
@@ -34,6 +34,8 @@ def paired_embeddings(P: SD, eeg, roi_series, conn, encoder: str = "v4", nhead: 
     else:
         raise ValueError(encoder)
     act = om.roi_meanstd(roi_series)
+    if conn is None:  # connectivity derived from the ROI series
+        conn = om.roi_connectivity(roi_series)
     _, fmri_feat = om.fmri_fusion_net(P, "fmri_net.", act, conn, train=train)
     return om.bridge_projections(P, "bridge.", eeg_feat, fmri_feat)
 
@@ -92,5 +94,5 @@ def sharded_paired_loss(P: SD, shards: Sequence[tuple], temperature: float = 0.0
     shards (SyncBN statistics + global negatives).  `shards` = [(eeg_r, roi_r, conn_r), ...]."""
     eeg = torch.cat([s[0] for s in shards], 0)
     roi = torch.cat([s[1] for s in shards], 0)
-    conn = torch.cat([s[2] for s in shards], 0)
+    conn = None if shards[0][2] is None else torch.cat([s[2] for s in shards], 0)
     return paired_loss(P, eeg, roi, conn, temperature, encoder)

@@ -68,6 +68,10 @@ def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
     return y
 
 
+def conv1d_fwd_precise(x, w, bias):
+    return conv1d_fwd(x, w, bias, w.shape[0]), x
+
+
 def conv1d_dgrad(dy, wt, Cin, round_out=False):
     dx = F.conv_transpose1d(dy.double().transpose(1, 2), wt.double(), padding=wt.shape[-1] // 2)
     return dx.transpose(1, 2).float().contiguous()
@@ -412,6 +416,14 @@ def resid_seqmean_bwd(dout, T, drop_p=0.0, seed=0, need_dx=True, need_da=True):
 def roi_meanstd(x):
     xd = torch.nan_to_num(x.double(), nan=0.0)
     return torch.cat([xd.mean(1), xd.std(1, unbiased=False)], dim=1).float()
+
+
+def roi_corrcoef(x):
+    xc = torch.nan_to_num(x.double())
+    xc = xc - xc.mean(1, keepdim=True)
+    c = xc.transpose(1, 2) @ xc
+    d = torch.sqrt(torch.diagonal(c, dim1=1, dim2=2))
+    return (c / d[:, :, None] / d[:, None, :]).clamp(-1, 1).reshape(x.shape[0], -1).float()
 
 
 def zscore(x, eps=1e-8):

@@ -481,7 +481,8 @@ def _ffn_ref(x, w1, b1, w2, b2, act, mask=None):
 
 @pytest.mark.parametrize("M,H,act,pdrop", [(1000, 512, "gelu", 0.0), (70001, 512, "gelu", 0.0), (128, 128, "relu", 0.0),
                                            (4099, 256, "gelu", 0.3), (1, 512, "gelu", 0.0), (20000, 1024, "relu", 0.1),
-                                           (148 * 128 * 2 + 5, 512, "gelu", 0.3)])
+                                           (148 * 128 * 2 + 5, 512, "gelu", 0.3), (148 * 128 * 3 + 77, 384, "gelu", 0.0),
+                                           (148 * 128 * 5, 128, "relu", 0.2)])
 def test_ffn_fused_fwd_dgrad(ops, M, H, act, pdrop):
     """linear2(Dropout(act(linear1(x)))) with the hidden activations on chip (enhanced_models_v4.py:79-80,102-105)
     against fp64 torch: y, and from the data-gradient kernel A, dH, dX, db1 -- ragged row counts, 1-8 hidden chunks,
@@ -610,6 +611,33 @@ def test_transformer_block_masks_match_torch_multihead_attention():
         assert_close_rel(blk(x, mask), ref, 2e-3, f"block with mask {None if mask is None else (mask.dtype, tuple(mask.shape))}")
     with pytest.raises(ValueError):
         blk(x, torch.zeros(L, L + 1, device="cuda"))
+
+
+# ------------------------------------------------------------------ ROI connectivity
+@pytest.mark.parametrize("B,TR,ROI", [(5, 100, 200), (3, 40, 7), (300, 100, 200), (2, 2, 1), (4, 150, 33)])
+def test_roi_corrcoef(ops, B, TR, ROI):
+    """Per-sample Pearson correlation matrix of the ROI columns (numpy.corrcoef, NaN -> 0 first) within 1e-5; the
+    output buffer carries canaries past its extent; a constant column gives NaN in its row / column like numpy."""
+    torch.manual_seed(41)
+    x = torch.randn(B, TR, ROI, device="cuda") * 3 + torch.randn(B, 1, ROI, device="cuda") * 10
+    if TR > 2:
+        x[0, 1, 0] = float("nan")
+    assert ops._lib.lib().xm_roi_corrcoef_supported(TR, ROI)
+    out = ops.roi_corrcoef(x)
+    xc = torch.nan_to_num(x.double())
+    xc = xc - xc.mean(1, keepdim=True)
+    c = xc.transpose(1, 2) @ xc
+    d = torch.sqrt(torch.diagonal(c, dim1=1, dim2=2))
+    ref = (c / d[:, :, None] / d[:, None, :]).clamp(-1, 1).reshape(B, -1)
+    if TR > 2:
+        assert float((out.double() - ref).abs().max()) < 2e-5 and rel_err(out, ref) < FP32
+        ref0 = np.corrcoef(np.nan_to_num(x[0].double().cpu().numpy()).T).reshape(-1)
+        assert np.abs(out[0].double().cpu().numpy() - ref0).max() < 2e-5
+    if ROI >= 7:
+        x[1, :, 4] = 1.25
+        o = ops.roi_corrcoef(x).reshape(B, ROI, ROI)
+        assert torch.isnan(o[1, 4]).all() and torch.isnan(o[1, :, 4]).all() and not torch.isnan(o[1, :4, :4]).any()
+        assert not torch.isnan(o[0]).any()
 
 
 # ------------------------------------------------------------------ out-of-bounds canaries

@@ -65,6 +65,28 @@ def test_erp_v4_golden():
         assert_close_rel(m.state_dict()[k], v, 5e-4 if v.is_floating_point() else 0.0, k)
 
 
+def test_erp_v4_d128_golden_fused_tail():
+    """The REAL reference class at the BASELINE width (d_model 128, 4 heads of 32, 2 blocks, L = 48): here the CUDA
+    path runs its fused transformer tail (fa::attn_* kernels, ffn::* kernels, resid_ln_*) and the 3-pass first
+    convs.  Features 1e-3; parameter gradients 1e-3 except the conv stack in front of 4-sample BatchNorms (5e-3)."""
+    from multimodal_eeg_fmri_b200 import functional as XF
+    from multimodal_eeg_fmri_b200.enhanced_models_v4 import EnhancedERPEncoder
+    g = load_golden("erp_v4_d128")
+    m = EnhancedERPEncoder(16, 128, 2, 4, 0.0)
+    missing = m.load_state_dict(g["sd"], strict=False)  # the fixture omits only the deterministic PE table
+    assert missing.missing_keys == ["pos_encoder.pe"] and not missing.unexpected_keys
+    m = m.cuda().train()
+    assert XF.transformer_tail_supported(48, 128, 4, "gelu")
+    ins, outs = _run(m, g)
+    assert_close_rel(outs[0], g["outputs"][0], TOL, "encoder output")
+    assert_close_rel(ins[0].grad, g["in_grads"][0], GTOL, "dx")
+    named = dict(m.named_parameters())
+    tail = {k: v for k, v in g["grads"].items() if not k.startswith("conv_layers.")}
+    for k, ref in tail.items():
+        assert_close_rel(named[k].grad, ref, TOL, f"grad {k}", atol=2e-5)
+    _check_grads(m, g, skip=set(tail))
+
+
 def test_power_v4_golden():
     from multimodal_eeg_fmri_b200.enhanced_models_v4 import EnhancedPowerEncoder
     g = load_golden("power_v4_small")

@@ -37,6 +37,22 @@ def test_erp_v4_small():
     _check_grads(P, g)
 
 
+def test_erp_v4_d128():
+    """The same encoder at the BASELINE width (d_model 128, 4 heads of 32, 2 blocks): the fixture the fused
+    transformer tail of the CUDA path is held to (tests/test_gpu_modules.py::test_erp_v4_d128_golden_fused_tail)."""
+    from multimodal_eeg_fmri_b200.modules import PositionalEncoding
+    g = load_golden("erp_v4_d128")
+    P = _params(g)
+    P["pos_encoder.pe"] = PositionalEncoding(128).pe  # deterministic table, left out of the fixture (2.5 MB)
+    x = g["inputs"][0].clone().requires_grad_(True)
+    assert_close_rel(om.enhanced_erp_conv_stack(P, "", x), g["raw"]["conv_stack_out"], TOL, "conv stack")
+    y = om.enhanced_erp_encoder(P, "", x, nhead=4)
+    assert_close_rel(y, g["outputs"][0], TOL, "encoder output")
+    y.backward(torch.from_numpy(g["raw"]["cotangent"]))
+    assert_close_rel(x.grad, g["in_grads"][0], 5e-5, "dx")
+    _check_grads(P, g)
+
+
 def test_power_v4_small():
     g = load_golden("power_v4_small")
     P = _params(g)

@@ -61,3 +61,32 @@ def test_synthetic_batches_are_deterministic_and_rank_offset():
     assert a[0].shape == (4, 8, 32) and a[1].shape == (4, 10, 6) and a[2].shape == (4, 36)
     r = synthetic.eeg_recordings(2, 4, 512)
     assert r.shape == (2, 4, 512) and r.dtype == torch.float32
+
+
+def test_roi_connectivity_is_numpy_corrcoef():
+    """Known-answer pin of the authored connectivity definition: numpy.corrcoef of the ROI columns, per sample,
+    NaN -> 0 first; a constant column gives NaN in its row and column (numpy's 0 / 0)."""
+    import numpy as np
+    from oracle import models as om
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 40, 7, generator=g, dtype=torch.float64)
+    x[1, 3, 2] = float("nan")
+    got = om.roi_connectivity(x).reshape(3, 7, 7).numpy()
+    for b in range(3):
+        ref = np.corrcoef(np.nan_to_num(x[b].numpy()).T)
+        assert np.allclose(got[b], ref, rtol=0, atol=1e-12)
+    assert np.allclose(np.diagonal(got, axis1=1, axis2=2), 1.0)
+    x[0, :, 4] = 2.5
+    c = om.roi_connectivity(x).reshape(3, 7, 7)
+    assert torch.isnan(c[0, 4]).all() and torch.isnan(c[0, :, 4]).all() and not torch.isnan(c[0, :4, :4]).any()
+
+
+def test_paired_step_with_derived_connectivity_matches_explicit():
+    """conn=None derives the connectivity from the ROI series: same loss as passing that matrix explicitly."""
+    from oracle import models as om
+    m = _model("lite")  # n_roi 12 -> conn_dim 144
+    P = {k: v.clone() for k, v in m.state_dict().items()}
+    eeg, roi, _ = synthetic.paired_batch(16, 8, 64, 12, 20, seed=5)
+    a = ps.paired_loss(P, eeg, roi, None, 0.07, "lite")
+    b = ps.paired_loss(P, eeg, roi, om.roi_connectivity(roi), 0.07, "lite")
+    assert float(a) == float(b) and math.isfinite(float(a))
