@@ -6,10 +6,15 @@ paired EEG-fMRI train samples/s at 1/2/4/8 B200, with the roofline fraction of t
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (oracle port)
 
 One "step" = one full training step of the composite model (EnhancedERPEncoder on 64 ch x 500 sample
-windows + fMRIFusionNet on 200 ROI x 100 TR series / 40 000-d connectivity + bridge projections +
-symmetric InfoNCE; backward; gradient all-reduce; clip_grad_norm_(1.0); AdamW) on a per-GPU batch of
-4096 synthetic paired samples (BASELINE config 4; weak scaling: global batch = 4096 x N with global
-negatives).  Prints ONE JSON line (rank 0).
+windows + fMRIFusionNet on the mean/std and the 200 x 200 correlation matrix of 200 ROI x 100 TR series +
+bridge projections + symmetric InfoNCE; backward; gradient all-reduce; clip_grad_norm_(1.0); AdamW) on a
+per-GPU batch of 4096 synthetic paired samples (BASELINE config 4; weak scaling: global batch = 4096 x N
+with global negatives).  The inputs of a step are the EEG windows and the ROI series; the 40 000-d
+connectivity feature is derived from the ROI series on the device (`--conn host`
+ships a precomputed connectivity matrix per sample instead, as round 1 did).  Prints ONE JSON line (rank 0)
+which also carries: the whole-step roofline, the other BASELINE configs (1, 2, 3, 5) as `extras`, the same
+step on the PyTorch library path on this GPU (`torch_eager_gpu`), and under torchrun a strong-scaling block
+(global batch 4096 split over the ranks).
 """
 from __future__ import annotations
 
@@ -77,10 +82,27 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference / CPU baseline arm
-def cpu_reference_run(steps: int, warmup: int, sample_batch: int, max_seconds: float = 120.0):
+def _cpu_batch(requested: int) -> int:
+    """The CPU arm runs the GPU arm's batch (4096, InfoNCE over 4096 negatives) when the host has the memory for
+    the oracle's autograd tape (~9 MB per sample with the unfused attention weights); else a smaller sample."""
+    if requested > 0:
+        return requested
+    try:
+        import psutil
+        free = psutil.virtual_memory().available
+    except Exception:  # noqa: BLE001
+        free = 0
+    for b in (4096, 2048, 1024, 512, 256):
+        if free > b * 14e6 + 8e9:
+            return b
+    return 64
+
+
+def cpu_reference_run(steps: int, warmup: int, sample_batch: int, max_seconds: float = 120.0, derive_conn: bool = True):
     """The reference's CPU path for the same step: oracle/paired_step.py (a functional restatement of
     the reference modules, pinned against golden vectors of the real classes, + the authored InfoNCE)
-    on all host cores, on a bounded sample of the workload (`sample_batch` paired samples per step)."""
+    on all host cores, on a bounded sample of the workload (`sample_batch` paired samples per step, as many
+    steps as fit `max_seconds`)."""
     import torch
 
     from multimodal_eeg_fmri_b200 import synthetic
@@ -94,9 +116,14 @@ def cpu_reference_run(steps: int, warmup: int, sample_batch: int, max_seconds: f
     P = {k: v.detach().clone() for k, v in model.state_dict().items()}
     eeg, roi, conn = synthetic.paired_batch(sample_batch, SHAPE["eeg_channels"], SHAPE["eeg_samples"], SHAPE["n_roi"],
                                             SHAPE["n_tr"], SHAPE["conn_dim"], seed=42)
+    if derive_conn:
+        conn = None  # the oracle derives the connectivity from the ROI series, as the GPU arm does
     state = {}
+    tw = time.perf_counter()
     for _ in range(warmup):
         ops_.paired_train_step(P, state, eeg, roi, conn, 0.07, "v4")
+        if time.perf_counter() - tw > max_seconds / 3:
+            break
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
@@ -106,20 +133,24 @@ def cpu_reference_run(steps: int, warmup: int, sample_batch: int, max_seconds: f
             break
     dt = time.perf_counter() - t0
     return {"value": sample_batch * done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{done} steps of the same step on {sample_batch} paired samples (64ch x 500, 200 ROI x 100 TR, conn 40000; "
-                      f"InfoNCE over {sample_batch} negatives), torch {torch.__version__} CPU fp32, dropout 0",
-            "ms_per_step": 1e3 * dt / done, "steps": done}
+            "sample": f"{done} steps of the same step on {sample_batch} paired samples (64ch x 500, 200 ROI x 100 TR, conn 40000 "
+                      f"{'derived from the ROI series' if derive_conn else 'given'}; InfoNCE over {sample_batch} negatives), "
+                      f"torch {torch.__version__} CPU fp32, dropout 0",
+            "ms_per_step": 1e3 * dt / done, "steps": done, "batch": sample_batch}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, args.cpu_batch)
+    batch = _cpu_batch(args.cpu_batch)
+    r = cpu_reference_run(args.steps, min(args.warmup, 1), batch, max_seconds=100.0, derive_conn=args.conn == "device")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
-            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "paired bridge training step, v4 ERP encoder, CPU sample batch %d" % args.cpu_batch, **SHAPE},
+            "config": {"workload": "paired bridge training step (BASELINE config 4), v4 ERP encoder, CPU batch %d "
+                                   "(the GPU arm's per-GPU batch is 4096), connectivity %s" % (batch, args.conn), **SHAPE,
+                       "per_gpu_batch": batch, "global_batch": batch},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -127,6 +158,146 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- this repo's arm
+# Whole-step roofline: 4.36 TFLOP (v4 encoder fwd + bwd) + 0.13 (fMRI net) + 0.013 (similarity)
+# per 4096-sample step.  The north-star floor quotes the bf16 tensor rate; this implementation computes in tf32
+# (the 1e-3 tolerance rules out bf16 operands: DESIGN.md section 2), whose rate is half.
+STEP_TFLOP_PER_4096 = 4.36 + 0.13 + 0.013
+
+
+def _timed(fn, steps, barrier, dev, world):
+    import torch
+    import torch.distributed as dist
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+
+def _extras(dev, rank, world, barrier, hbm):
+    """The other BASELINE configs, each a short event-timed run (config 5 on every rank; 1, 2, 3 on one GPU)."""
+    import torch
+
+    from multimodal_eeg_fmri_b200 import eeg_data_utils as edu, ops, synthetic
+    from multimodal_eeg_fmri_b200.modules import LabelSmoothingCrossEntropy, fMRIFusionNet
+    from multimodal_eeg_fmri_b200.run_training_lite import ImprovedTriModalFusionNetLite
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel, PairedTrainer
+
+    out = {}
+    # ---- config 5: band power of 128-channel 1 kHz recordings, win 1024 / hop 512, windows read in place
+    C, win, hop, wpr, nrec = 128, 1024, 512, 64, 256
+    n = win + (wpr - 1) * hop
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    bufs = [torch.randn(nrec, C, n, device=dev, generator=g) for _ in range(2)]  # 2 x 4.3 GB chunks (> L2), alternating
+    chunks = 8
+    for i in range(2):
+        edu.band_power(bufs[i & 1], 1000.0, win, hop)
+    ms = _timed(lambda it=iter(range(10 ** 9)): edu.band_power(bufs[next(it) & 1], 1000.0, win, hop), chunks, barrier, dev, world)
+    nwin = chunks * nrec * wpr * world
+    by = nwin * (C * win * 4 + C * 3 * 4)
+    out["config5_bandpower"] = {"metric": "EEG band-power windows/sec", "value": round(nwin / (ms * 1e-3), 1), "unit": "windows/s",
+                                "windows": nwin, "channels": C, "win": win, "hop": hop, "n_gpus": world, "ms_total": round(ms, 3),
+                                "roofline": {"bound": "hbm", "achieved": round(by / (ms * 1e-3) / 1e9 / world, 1), "peak": hbm,
+                                             "unit": "GB/s", "frac": round(by / (ms * 1e-3) / 1e9 / world / hbm, 4),
+                                             "algorithmic_bytes_per_window": C * win * 4 + C * 3 * 4},
+                                "note": "1M-window sweep = this rate x 1 048 576 windows; inputs resident in HBM, two alternating chunks"}
+    del bufs
+    if world > 1:
+        return out  # configs 1-3 are single-GPU configurations
+
+    def step_time(step, n_steps=20, warm=5):
+        for _ in range(warm):
+            step()
+        return _timed(step, n_steps, barrier, dev, world) / n_steps
+
+    # ---- config 3: paired InfoNCE bridge step, batch 256
+    torch.manual_seed(42)
+    m3 = PairedBridgeModel(SHAPE["eeg_channels"], SHAPE["n_roi"], SHAPE["conn_dim"], 128, 64, 128, 0.3, 0.4, "v4").to(dev).train()
+    t3 = PairedTrainer(m3)
+    eeg, roi, _ = (t.to(dev) for t in synthetic.paired_batch(256, SHAPE["eeg_channels"], SHAPE["eeg_samples"], SHAPE["n_roi"],
+                                                             SHAPE["n_tr"], 16, seed=42))
+    n0 = ops.launch_count()
+    ms3 = step_time(lambda: t3.step(eeg, roi))
+    out["config3_bridge_b256"] = {"metric": METRIC, "value": round(256 / (ms3 * 1e-3), 1), "unit": UNIT, "batch": 256,
+                                  "ms_per_step": round(ms3, 3), "launches_per_step": (ops.launch_count() - n0) / 25}
+    del m3, t3
+    # ---- config 1: run_training_lite step (tri-modal lite net, label-smoothing CE, AdamW 5e-5 / 0.01, clip 1.0), batch 32
+    torch.manual_seed(42)
+    m1 = ImprovedTriModalFusionNetLite(64, 64, 6048).to(dev).train()
+    crit, opt1 = LabelSmoothingCrossEntropy(0.1), torch.optim.AdamW(m1.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
+    erp, pw, cn = torch.randn(32, 64, 500, device=dev), torch.randn(32, 64, 500, device=dev), torch.randn(32, 6048, device=dev)
+    y = torch.randint(0, 2, (32,), device=dev)
+
+    def step1():
+        opt1.zero_grad(set_to_none=True)
+        crit(m1(pw, erp, cn), y).backward()
+        torch.nn.utils.clip_grad_norm_(m1.parameters(), 1.0)
+        opt1.step()
+    ms1 = step_time(step1)
+    out["config1_lite_b32"] = {"metric": "tri-modal lite train samples/sec", "value": round(32 / (ms1 * 1e-3), 1), "unit": UNIT,
+                               "batch": 32, "ms_per_step": round(ms1, 3)}
+    # ---- config 2: run_fmri_v11 step (fMRIFusionNet 400 / 40 000, weighted CE, AdamW 1e-4, clip 1.0), batch 64
+    torch.manual_seed(42)
+    m2 = fMRIFusionNet(400, 40000).to(dev).train()
+    opt2 = torch.optim.AdamW(m2.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+    act, conn2, y2 = torch.randn(64, 400, device=dev), torch.randn(64, 40000, device=dev), torch.randint(0, 2, (64,), device=dev)
+
+    def step2():
+        opt2.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(m2(act, conn2), y2).backward()
+        torch.nn.utils.clip_grad_norm_(m2.parameters(), 1.0)
+        opt2.step()
+    ms2 = step_time(step2)
+    out["config2_fmri_b64"] = {"metric": "fMRI ROI encoder train samples/sec", "value": round(64 / (ms2 * 1e-3), 1), "unit": UNIT,
+                               "batch": 64, "ms_per_step": round(ms2, 3)}
+    return out
+
+
+def _torch_eager_gpu(dev, batch, derive_conn, barrier):
+    """SURVEY.md section 2's bar: the SAME step on the PyTorch library path of this GPU (cuDNN convolutions, cuBLAS
+    matmuls, torch's unfused attention, foreach optimizer) -- the functional restatement of the reference modules
+    (oracle/) run on cuda tensors.  A baseline leg like cpu_baseline: measured, not shipped."""
+    import torch
+
+    from multimodal_eeg_fmri_b200 import synthetic
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel
+    from oracle import paired_step as ops_
+
+    res = {}
+    torch.manual_seed(42)
+    model = PairedBridgeModel(SHAPE["eeg_channels"], SHAPE["n_roi"], SHAPE["conn_dim"], 128, 64, 128, 0.0, 0.0, "v4")
+    P0 = {k: v.detach().to(dev) for k, v in model.state_dict().items()}
+    eeg, roi, conn = (t.to(dev) for t in synthetic.paired_batch(batch, SHAPE["eeg_channels"], SHAPE["eeg_samples"], SHAPE["n_roi"],
+                                                                SHAPE["n_tr"], SHAPE["conn_dim"] if not derive_conn else 16, seed=42))
+    if derive_conn:
+        conn = None
+    for name, tf32 in (("tf32", True), ("fp32", False)):
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+        try:
+            P, state = {k: v.clone() for k, v in P0.items()}, {}
+            for _ in range(2):
+                ops_.paired_train_step(P, state, eeg, roi, conn, 0.07, "v4")
+            ms = _timed(lambda: ops_.paired_train_step(P, state, eeg, roi, conn, 0.07, "v4"), 3, barrier, dev, 1) / 3
+            res[name] = {"value": round(batch / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 3)}
+        except torch.cuda.OutOfMemoryError:
+            res[name] = {"unavailable": f"out of device memory at batch {batch}"}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+            del P, state
+            torch.cuda.empty_cache()
+    res["batch"] = batch
+    res["what"] = ("oracle/paired_step.py (functional restatement of the reference modules) on cuda tensors, dropout 0: cuDNN / "
+                   "cuBLAS / unfused attention, allow_tf32 on | off; same inputs and batch as the main line")
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -141,18 +312,24 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    _bind_to_gpu_numa_node(local)
     ctx = init_distributed("nccl")
     dev = torch.device("cuda", local)
     B = args.batch
+    derive = args.conn == "device"
 
     torch.manual_seed(42)  # identical initial weights on every rank
     model = PairedBridgeModel(SHAPE["eeg_channels"], SHAPE["n_roi"], SHAPE["conn_dim"], 128, 64, 128, 0.3, 0.4, args.encoder)
     model = model.to(dev).train()
     trainer = PairedTrainer(model, lr=1e-4, weight_decay=1e-4, grad_clip=1.0)
 
+    def make_inputs(batch, offset):
+        ts = synthetic.paired_batch(batch, SHAPE["eeg_channels"], SHAPE["eeg_samples"], SHAPE["n_roi"], SHAPE["n_tr"],
+                                    SHAPE["conn_dim"] if not derive else 16, seed=42, offset=offset)
+        return [t.pin_memory() for t in (ts[:2] if derive else ts)]
+
     # this rank's rows of the global synthetic batch, in pinned host memory (the e2e source) and in HBM
-    host = [t.pin_memory() for t in synthetic.paired_batch(B, SHAPE["eeg_channels"], SHAPE["eeg_samples"], SHAPE["n_roi"],
-                                                            SHAPE["n_tr"], SHAPE["conn_dim"], seed=42, offset=rank * B)]
+    host = make_inputs(B, rank * B)
     devt = [t.to(dev, non_blocking=True) for t in host]
     h2d = sum(t.numel() * t.element_size() for t in host)
     torch.cuda.synchronize()
@@ -162,19 +339,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
     for _ in range(max(args.warmup, 3)):
         trainer.step(*devt)
     barrier()
@@ -183,7 +347,7 @@ def run_ours(args):
     n0 = ops.launch_count()
     ops.start_timeline()
     with ClockSampler(local) as clocks:
-        ms_total = timed(lambda: trainer.step(*devt), args.steps)
+        ms_total = _timed(lambda: trainer.step(*devt), args.steps, barrier, dev, world)
     timeline = ops.stop_timeline()
     launches = ops.launch_count() - n0
     ms_step = ms_total / args.steps
@@ -193,25 +357,34 @@ def run_ours(args):
     # (the public end-to-end call: copies batch k+1 from pinned host memory while batch k trains; every step's
     #  inputs cross PCIe inside the timed region and every step's loss is read back)
     trainer.steps_from_host([host, host])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    trainer.steps_from_host([host] * args.e2e_steps)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t)
+    ms_e2e = _timed(lambda: trainer.steps_from_host([host] * args.e2e_steps), 1, barrier, dev, world)
     e2e_value = world * B * args.e2e_steps / (ms_e2e * 1e-3)
     loss_t = trainer.step(*devt).clone()
     if world > 1:
         dist.all_reduce(loss_t)  # global loss = sum of the per-rank shares
     loss = float(loss_t)
 
-    if rank != 0:
-        return
+    # ---- strong scaling (SURVEY.md section 8e as written): the GLOBAL batch stays 4096, rank r holds 4096 / N rows
+    strong = None
+    if world > 1 and B % world == 0:
+        Bs = B // world
+        sh = [t.to(dev) for t in make_inputs(Bs, rank * Bs)]
+        for _ in range(3):
+            trainer.step(*sh)
+        ms_s = _timed(lambda: trainer.step(*sh), args.steps, barrier, dev, world) / args.steps
+        strong = {"global_batch": B, "per_gpu_batch": Bs, "ms_per_step": round(ms_s, 3), "value": round(B / (ms_s * 1e-3), 1),
+                  "unit": UNIT, "scaling": "strong", "note": "same global batch as the 1-GPU line; in-GEMM peer reads for per-GPU batch <= 512"}
+        del sh
+    peak_mem = torch.cuda.max_memory_allocated()
+    del devt
+    torch.cuda.empty_cache()
+
     hbm, tc_burst, tc_sus, src = _peaks()
+    extras = _extras(dev, rank, world, barrier, hbm) if not args.no_extras else {}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     kernels = {}
     for name, (n, ms, fl, by) in sorted(timeline.items(), key=lambda kv: -kv[1][1]):
         kernels[name] = {"calls_per_step": n / args.steps, "ms_per_step": round(ms / args.steps, 4),
@@ -240,7 +413,18 @@ def run_ours(args):
                 "peak_source": f"{src}: hbm_gbs (copy bandwidth)",
                 "tensor": {"achieved_tflops": round(g_fl / (g_ms * 1e-3) / 1e12, 1), "peak_tflops": round(tc_sus / 2.0, 1),
                            "note": "kind::tf32 peak = measured bf16_tflops_sustained / 2"}}
-    cpu = cpu_reference_run(args.cpu_steps, 1, args.cpu_batch, max_seconds=30.0) if world == 1 and not args.no_cpu else None
+    step_tflop = STEP_TFLOP_PER_4096 * B / 4096.0
+    floor_bf16, floor_tf32 = step_tflop / tc_sus * 1e3, step_tflop / (tc_sus / 2.0) * 1e3
+    step_roofline = {"bound": "tensor", "work_tflop_per_step": round(step_tflop, 3), "floor_ms_bf16_rate": round(floor_bf16, 3),
+                     "floor_ms_tf32_rate": round(floor_tf32, 3), "frac_of_bf16_floor": round(floor_bf16 / ms_step, 4),
+                     "frac_of_tf32_floor": round(floor_tf32 / ms_step, 4),
+                     "note": "SURVEY 8d work per step over the measured sustained tensor rate; the path computes in tf32 (half the bf16 rate)"}
+    cpu = eager = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_reference_run(args.cpu_steps, 1, _cpu_batch(args.cpu_batch), max_seconds=30.0, derive_conn=derive)
+    if world == 1 and not args.no_eager:
+        free = torch.cuda.mem_get_info(dev)[0]
+        eager = _torch_eager_gpu(dev, B if free > 150e9 else B // 4, derive, barrier)
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
             "data": "synthetic",
@@ -248,6 +432,8 @@ def run_ours(args):
                                    f"{args.encoder} ERP encoder + fMRIFusionNet + bridge projections + symmetric InfoNCE (global negatives), "
                                    "backward, grad all-reduce, clip 1.0, AdamW",
                        **SHAPE, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "connectivity": ("derived on the device from the ROI series (per-sample corrcoef, xm_roi_corrcoef_f32)" if derive
+                                        else "precomputed per sample, shipped from the host"),
                        "l2": f"inputs {h2d / 1e6:.0f} MB per step and >10 GB of activations per step, far larger than the 126 MB L2 (no flush needed)",
                        "final_loss": round(loss, 5)},
             "clocks": clocks.summary(),
@@ -255,15 +441,39 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e / args.e2e_steps, 3), "steps": args.e2e_steps},
             "gpu_launches": launches,
             "roofline": roofline,
-            "peak_device_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
+            "step_roofline": step_roofline,
+            "peak_device_memory_gb": round(peak_mem / 2 ** 30, 2),
             "own_kernels_ms_per_step": round(ours_ms, 3),
             "torch_ops_ms_per_step": round(ms_step - ours_ms, 3),
             "kernels": kernels}
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if extras:
+        line["extras"] = extras
+    if eager is not None:
+        line["torch_eager_gpu"] = eager
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _bind_to_gpu_numa_node(local: int) -> None:
+    """Pin this rank's host threads (and so its pinned staging buffers, first-touch) to the CPU cores next to its GPU:
+    with 8 ranks pulling 0.85 GB per step each over PCIe, buffers on the far socket halve the copy rate."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n = (os.cpu_count() or 1 + 63) // 64 + 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # noqa: BLE001 - best effort: NVML or the affinity call may be unavailable in the container
+        pass
 
 
 def main():
@@ -275,9 +485,13 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (paired samples)")
     ap.add_argument("--encoder", default="v4", choices=["v4", "lite"])
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--cpu-batch", type=int, default=64, help="paired samples per CPU-baseline step (bounded sample)")
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="paired samples per CPU-baseline step (0: the GPU arm's batch if host memory allows)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch_eager_gpu baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (1, 2, 3, 5)")
+    ap.add_argument("--conn", default="device", choices=["device", "host"],
+                    help="connectivity features: derived on the device from the ROI series | precomputed, shipped from the host")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -288,22 +288,13 @@ int xm_linear_dgrad_peers_f32(const float* dy, const void* const* w_peers, int n
 /* ------------------------------------------------------------------ multi-head self-attention core
  * nn.MultiheadAttention inside TemporalTransformerBlock (EEG_CODE/enhanced_models_v4.py:71-73,98; torch computes
  * softmax(q k^T / sqrt(dh)), dropout on the weights, times v).  qkv (B, L, 3*H*dh) is the packed in_proj output
- * [q | k | v], head h at columns h*dh inside each third; out (B, L, H*dh).  Supported: dh == 32, L <= 256
- * (the fused variant below: L <= 512).
- * probs (B*H, L, NP) with NP = xm_attn_keys_padded(L): the dropped, normalised weights (tf32), saved for the
- * backward; lse (B*H, L).  The dropout mask is a pure function of (seed, slab, query, key). */
-int xm_attn_keys_padded(int64_t L);
-int xm_attn_fwd_f32(const float* qkv, float* out, float* probs, float* lse, int64_t B, int64_t L, int64_t H, int64_t dh,
-                    float scale, float drop_p, uint64_t seed, int round_out, void* stream);
-/* dqkv (B, L, 3*H*dh) from dout (B, L, H*dh); ds: (B*H, L, NP) workspace for the score gradients. */
-int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, const float* lse, float* dqkv, float* ds,
-                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, int round_out,
-                    void* stream);
+ * [q | k | v], head h at columns h*dh inside each third; out (B, L, H*dh); lse (B*H, L).  No kernel stores the L x L
+ * probabilities (the reference's need_weights path materialises them only to discard them). */
 
-/* Fused variant (the product path): the L x L probability / score-gradient matrices stay in tensor memory -- the
- * forward keeps only out and lse (B*H, L); the backward regenerates the probabilities from q, k and lse and needs
- * the forward's `out` (delta = dO . O) plus a (B*H, L) float workspace `delta`.  Same layouts and limits as above;
- * the dropout mask is a different pure function of (seed, slab, query, key), exported by xm_attn_fused_mask_u8
+/* Fused tcgen05 kernels (head dim 32, L <= 512): the L x L probability / score-gradient matrices stay in tensor
+ * memory -- the forward keeps only out and lse (B*H, L); the backward regenerates the probabilities from q, k and lse
+ * and needs the forward's `out` (delta = dO . O) plus a (B*H, L) float workspace `delta`.
+ * The dropout mask is a pure function of (seed, slab, query, key), exported by xm_attn_fused_mask_u8
  * (mask (B*H, L, L), 1 = kept) so tests can replay it. */
 int xm_attn_fused_fwd_f32(const float* qkv, float* out, float* lse, int64_t B, int64_t L, int64_t H, int64_t dh, float scale,
                           float drop_p, uint64_t seed, int round_out, void* stream);
@@ -373,6 +364,18 @@ int xm_ffn_fused_dgrad_f32(const float* x, const float* dy, const float* w1, con
 /* mask (M, hidden), 1 = kept: the dropout mask both kernels generate for (drop_p, seed), so tests can replay it. */
 int xm_ffn_fused_mask_u8(uint8_t* mask, int64_t M, int64_t hidden, float drop_p, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------ clip_grad_norm_ + AdamW over one flat bucket
+ * The step recipe of _test_bridge.py:775-788,869 (run_fmri_v11.py:430-450, run_training_lite.py:478-489):
+ * clip_grad_norm_(max_norm) then torch.optim.AdamW.step, as two launches over flat fp32 buffers (csrc/optimizer.cu).
+ * partials: xm_sumsq_nblk(n) doubles.  xm_clip_adamw_f32: coef = min(1, max_norm / (sqrt(sum partials) + 1e-6))
+ * (max_norm <= 0: no clipping); g <- coef * g; AdamW update of p, m, v for 1-based `step`; norm_out (1 float, may be
+ * NULL) receives the pre-clip total norm. */
+int xm_sumsq_nblk(int64_t n);
+int xm_sumsq_partials_f32(const float* g, int64_t n, double* partials, void* stream);
+int xm_clip_adamw_f32(float* p, float* g, float* m, float* v, int64_t n, const double* partials, int nblk, float max_norm,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float* norm_out,
+                      void* stream);
+
 /* ------------------------------------------------------------------ diagnostics (not on the product path)
  * Dump the raw shared-memory image of one TMA box {32,32} loaded at (c0, c1) from a (rows, cols)
  * fp32 matrix; swizzle_atom32 selects SWIZZLE_128B_ATOM_32B instead of SWIZZLE_128B. */
@@ -384,6 +387,9 @@ int xm_debug_set_conv_halo(int on);
  * waited on the other roles) for the TMA producer [0, 8192) and the MMA issuer [8192, 16384), and per transformed
  * chunk (4, chunk, wait start, accumulator ready, handed back) for one warp of each transform group [16384 + g*4096). */
 int xm_debug_set_ffn_trace(int64_t* device_buffer);
+/* Timing experiments of the tracing instance (its results are then wrong): bit 0 = transform warps skip their
+ * arithmetic, bit 1 = the weight ring is loaded once and only re-signalled. */
+int xm_debug_set_ffn_flags(int flags);
 int xm_debug_tma_probe(const float* src, int64_t rows, int64_t cols, int64_t ld, int c0, int c1, int swizzle_atom32,
                        float* out, void* stream);
 

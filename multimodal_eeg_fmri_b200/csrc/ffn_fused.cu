@@ -63,7 +63,9 @@ struct Params {
   float dscale;
   uint32_t thr;
   unsigned long long seed;
-  long long* trace;  // debug (xm_debug_ffn_fused_fwd_trace_f32): CTA 0 logs per-op clocks, 3 roles x 8192 slots
+  long long* trace;  // debug (xm_debug_set_ffn_trace): CTA 0 logs per-op clocks, 3 roles x 8192 slots
+  int dbg;           // tracing instance only, timing experiments (results are then WRONG): bit 0 = the transform warps
+                     // skip their arithmetic, bit 1 = the producer loads each ring stage once and only re-signals it
 };
 
 // mbarrier wait that, in the tracing instance of a kernel, adds the cycles it spent to `acc`
@@ -97,6 +99,45 @@ XM_DEVICE void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, ui
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+
+// The MMA warp runs its schedule WARP-UNIFORMLY (all 32 lanes wait on the barriers and compute the operand
+// descriptors, which the compiler can then keep in uniform registers); only the instructions that must come from a
+// single thread are predicated on `leader`.  With the schedule inside `if (lane == 0)` every descriptor went through
+// vector registers and R2UR moves: ~125 cycles of issue per MMA, more than the MMA itself takes (profiles/
+// r2_ffn_trace_v2.json).
+XM_DEVICE void mma_ss_l(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+XM_DEVICE void mma_ts_l(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+XM_DEVICE void commit_l(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(ptx::smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
+constexpr uint32_t kTile16 = kTile >> 4;  // descriptor start-address units (16 B) per 16 KB tile
 
 // The per-tile MMA schedule, written once into shared memory (kind << 8 | chunk).
 XM_DEVICE int build_fwd_ops(int* ops, int nc) {
@@ -309,7 +350,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t ws = 0;  // weight k-blocks requested so far
+      uint32_t st = 0, ph = 0;  // ring stage and its phase parity
       long long tw = 0, tx = 0;
       int tn = 0;
       auto log = [&](int kind, int n, long long t0) {
@@ -329,22 +370,30 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           for (int kb = 0; kb < 4; ++kb)
             ptx::tma_load_3d(&tmX, &bar.x_full[xb], xs + (xb * 4 + kb) * kTile, kb * 32, tile * 128, 0);
         }
-        for (int kb = 0; kb < 4; ++kb, ++ws) {
-          const uint32_t st = ws % kFwdRing;
-          twait<TRACE>(&bar.w_empty[st], ((ws / kFwdRing) & 1u) ^ 1u, tw);
-          ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
-          ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W1[128c.., 32kb..]
+        for (int kb = 0; kb < 4; ++kb) {
+          twait<TRACE>(&bar.w_empty[st], ph ^ 1u, tw);
+          if (TRACE && (p.dbg & 2) && (ph || n > 1)) {
+            ptx::mbar_arrive(&bar.w_full[st]);
+          } else {
+            ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
+            ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W1[128c.., 32kb..]
+          }
+          if (++st == kFwdRing) { st = 0; ph ^= 1u; }
         }
         log(OP_M1, n, t0);
       };
       auto load_m2 = [&](int n) {
         const long long t0 = TRACE ? clock64() : 0;
         const int c = n % p.nc;
-        for (int kb = 0; kb < 4; ++kb, ++ws) {
-          const uint32_t st = ws % kFwdRing;
-          twait<TRACE>(&bar.w_empty[st], ((ws / kFwdRing) & 1u) ^ 1u, tw);
-          ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
-          ptx::tma_load_3d(&tmW2, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W2[:, 128c + 32kb..]
+        for (int kb = 0; kb < 4; ++kb) {
+          twait<TRACE>(&bar.w_empty[st], ph ^ 1u, tw);
+          if (TRACE && (p.dbg & 2)) {
+            ptx::mbar_arrive(&bar.w_full[st]);
+          } else {
+            ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
+            ptx::tma_load_3d(&tmW2, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W2[:, 128c + 32kb..]
+          }
+          if (++st == kFwdRing) { st = 0; ph ^= 1u; }
         }
         log(OP_M2, n, t0);
       };
@@ -356,13 +405,16 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       const uint32_t idesc = ptx::make_idesc_tf32(128, 128, 0, 0);
-      uint32_t ws = 0;
+      const uint64_t dx0 = ptx::make_smem_desc(ptx::smem_u32(xs), 16, 1024, 2);    // x tile 0, k-block 0
+      const uint64_t dw0 = ptx::make_smem_desc(ptx::smem_u32(ring), 16, 1024, 2);  // ring stage 0
+      uint32_t st = 0, ph = 0;  // ring stage and its phase parity
       long long tw = 0, ta = 0;
       int tn = 0;
       auto log = [&](int kind, int n, long long t0) {
-        if (TRACE && blockIdx.x == 0 && tn < 8192 - 6) {
+        if (TRACE && blockIdx.x == 0 && lane == 0 && tn < 8192 - 6) {
           long long* t = p.trace + 8192 + tn;
           t[0] = kind; t[1] = n; t[2] = t0; t[3] = clock64(); t[4] = tw; t[5] = ta;
           tn += 6; tw = 0; ta = 0;
@@ -376,19 +428,20 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           twait<TRACE>(&bar.x_full[xb], ((uint32_t)it >> 1) & 1u, ta);
           ptx::tc_fence_after_sync();
         }
-        for (int kb = 0; kb < 4; ++kb, ++ws) {
-          const uint32_t st = ws % kFwdRing;
-          twait<TRACE>(&bar.w_full[st], (ws / kFwdRing) & 1u, tw);
+        const uint64_t dxa = dx0 + (uint64_t)((uint32_t)xb * 4u * kTile16);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          twait<TRACE>(&bar.w_full[st], ph, tw);
           ptx::tc_fence_after_sync();
-          const uint64_t da = ptx::make_smem_desc(ptx::smem_u32(xs + (xb * 4 + kb) * kTile), 16, 1024, 2);
-          const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+          const uint64_t da = dxa + (uint64_t)(kb * kTile16), db = dw0 + (uint64_t)(st * kTile16);
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8)
-            ptx::mma_tf32_ss(tH, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
-          ptx::mma_commit(&bar.w_empty[st]);
+            mma_ss_l(tH, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u, leader);
+          commit_l(&bar.w_empty[st], leader);
+          if (++st == kFwdRing) { st = 0; ph ^= 1u; }
         }
-        ptx::mma_commit(&bar.h_full[b]);
-        if (c == p.nc - 1) ptx::mma_commit(&bar.x_empty[xb]);
+        commit_l(&bar.h_full[b], leader);
+        if (c == p.nc - 1) commit_l(&bar.x_empty[xb], leader);
         log(OP_M1, n, t0);
       };
       auto mma_m2 = [&](int n) {
@@ -401,17 +454,18 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           twait<TRACE>(&bar.y_free, ((uint32_t)it & 1u) ^ 1u, ta);  // the previous tile's Y has been read out
           ptx::tc_fence_after_sync();
         }
-        for (int kb = 0; kb < 4; ++kb, ++ws) {
-          const uint32_t st = ws % kFwdRing;
-          twait<TRACE>(&bar.w_full[st], (ws / kFwdRing) & 1u, tw);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          twait<TRACE>(&bar.w_full[st], ph, tw);
           ptx::tc_fence_after_sync();
-          const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+          const uint64_t db = dw0 + (uint64_t)(st * kTile16);
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8)
-            mma_tf32_ts(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (c | kb | k8) ? 1u : 0u);
-          ptx::mma_commit(&bar.w_empty[st]);
+            mma_ts_l(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u), leader);
+          commit_l(&bar.w_empty[st], leader);
+          if (++st == kFwdRing) { st = 0; ph ^= 1u; }
         }
-        if (c == p.nc - 1) ptx::mma_commit(&bar.y_full[b]);  // group b transformed this chunk and writes the tile
+        if (c == p.nc - 1) commit_l(&bar.y_full[b], leader);  // group b transformed this chunk and writes the tile
         log(OP_M2, n, t0);
       };
       if (N > 0) mma_m1(0);
@@ -446,7 +500,8 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         ptx::tmem_ld_32x32(addr, r);
         ptx::tmem_ld_wait();
         const float* bias = sb1 + c * kChunk + col0;
-        if (p.thr)
+        if (TRACE && (p.dbg & 1)) {
+        } else if (p.thr)
           fwd_transform<true>(r, bias, p.act, cs, p.thr, group_seed(rs, (c * kChunk + col0) >> 5));
         else
           fwd_transform<false>(r, bias, p.act, cs, 0u, 0u);
@@ -496,14 +551,13 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 struct BwdBars {
   uint64_t in_full, in_empty;
   uint64_t w_full[kBwdRing], w_empty[kBwdRing];
-  uint64_t g_full[2], d_ready;   // g_full[g] / x_done[g]: the phases transform group g consumes (every one of them)
-  uint64_t x_done[2], xacc_free;
+  uint64_t g_full, d_ready;
+  uint64_t x_done, xacc_free;
 };
 
 // Data gradient.  MMA order per tile as in the header comment; G is single-buffered, so the transform of chunk c
-// sits between M3(c) and [M4(c), M3(c + 1)].  The two transform groups alternate chunks: while group g streams the
-// A / dH block of chunk c out to global memory (256-bit stores, one full line per lane) and folds dH into the bias
-// gradient, the other group already transforms chunk c + 1.
+// sits between M3(c) and [M4(c), M3(c + 1)] (see the transform branch below).
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2t,
@@ -533,12 +587,10 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       ptx::mbar_init(&bar.w_full[i], 1);
       ptx::mbar_init(&bar.w_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&bar.g_full[i], 1);
-      ptx::mbar_init(&bar.x_done[i], 1);
-    }
-    ptx::mbar_init(&bar.d_ready, kXfWarps / 2);
-    ptx::mbar_init(&bar.xacc_free, kXfWarps / 2);
+    ptx::mbar_init(&bar.g_full, 1);
+    ptx::mbar_init(&bar.x_done, 1);
+    ptx::mbar_init(&bar.d_ready, kXfWarps);
+    ptx::mbar_init(&bar.xacc_free, kXfWarps);
     ptx::fence_mbar_init();
     n_ops_s = build_bwd_ops(ops, p.nc);
   }
@@ -555,7 +607,7 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t ws = 0;
+      uint32_t st = 0, ph = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
         ptx::mbar_wait(&bar.in_empty, ((uint32_t)it & 1u) ^ 1u);
@@ -566,9 +618,8 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         for (int op = 0; op < n_ops; ++op) {
           const int kind = ops[op] >> 8, c = ops[op] & 255;
-          for (int kb = 0; kb < 4; ++kb, ++ws) {
-            const uint32_t st = ws % kBwdRing;
-            ptx::mbar_wait(&bar.w_empty[st], ((ws / kBwdRing) & 1u) ^ 1u);
+          for (int kb = 0; kb < 4; ++kb) {
+            ptx::mbar_wait(&bar.w_empty[st], ph ^ 1u);
             ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
             if (kind == OP_M1)
               ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);   // W1[128c.., in 32kb..]
@@ -576,82 +627,96 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               ptx::tma_load_3d(&tmW2t, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W2t[128c.., out 32kb..]
             else
               ptx::tma_load_3d(&tmW1t, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W1t[:, 128c + 32kb..]
+            if (++st == kBwdRing) { st = 0; ph ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;  // warp-uniform schedule, single-thread issue (see mma_ss_l)
       const uint32_t idesc = ptx::make_idesc_tf32(128, 128, 0, 0);
-      uint32_t ws = 0, cu = 0;  // cu: chunks whose M4 has been issued
+      const uint64_t dx0 = ptx::make_smem_desc(ptx::smem_u32(xs), 16, 1024, 2);
+      const uint64_t dy0 = ptx::make_smem_desc(ptx::smem_u32(ys), 16, 1024, 2);
+      const uint64_t dw0 = ptx::make_smem_desc(ptx::smem_u32(ring), 16, 1024, 2);
+      uint32_t st = 0, ph = 0, cu = 0;  // cu: chunks whose M4 has been issued
+      long long tw = 0, ta = 0;
+      int tn = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
         for (int op = 0; op < n_ops; ++op) {
+          const long long t0 = TRACE ? clock64() : 0;
           const int kind = ops[op] >> 8, c = ops[op] & 255;
           const uint32_t tH = tmem + (uint32_t)((c & 1) * 128);
           if (kind == OP_M1 && c == 0) {
-            ptx::mbar_wait(&bar.in_full, (uint32_t)it & 1u);
+            twait<TRACE>(&bar.in_full, (uint32_t)it & 1u, ta);
             ptx::tc_fence_after_sync();
           }
           if (kind == OP_M4) {
-            ptx::mbar_wait(&bar.d_ready, cu & 1u);  // a transform group has read H_c, G_c and written dH_c over G_c
+            twait<TRACE>(&bar.d_ready, cu & 1u, ta);  // a transform group has read H_c, G_c and written dH_c over G_c
             ++cu;
             ptx::tc_fence_after_sync();
             if (c == 0) {
-              ptx::mbar_wait(&bar.xacc_free, ((uint32_t)it & 1u) ^ 1u);  // the previous tile's dX has been read out
+              twait<TRACE>(&bar.xacc_free, ((uint32_t)it & 1u) ^ 1u, ta);  // the previous tile's dX has been read out
               ptx::tc_fence_after_sync();
             }
           }
-          for (int kb = 0; kb < 4; ++kb, ++ws) {
-            const uint32_t st = ws % kBwdRing;
-            ptx::mbar_wait(&bar.w_full[st], (ws / kBwdRing) & 1u);
+          const uint64_t da0 = kind == OP_M1 ? dx0 : dy0;
+          const uint32_t acc = kind == OP_M1 ? tH : tG;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            twait<TRACE>(&bar.w_full[st], ph, tw);
             ptx::tc_fence_after_sync();
-            const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(ring + st * kTile), 16, 1024, 2);
+            const uint64_t db = dw0 + (uint64_t)(st * kTile16);
             if (kind == OP_M4) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8)
-                mma_tf32_ts(tX, tG + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (c | kb | k8) ? 1u : 0u);
+                mma_ts_l(tX, tG + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u), leader);
             } else {
-              const uint64_t da = ptx::make_smem_desc(ptx::smem_u32((kind == OP_M1 ? xs : ys) + kb * kTile), 16, 1024, 2);
-              const uint32_t acc = kind == OP_M1 ? tH : tG;
+              const uint64_t da = da0 + (uint64_t)(kb * kTile16);
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8)
-                ptx::mma_tf32_ss(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+                mma_ss_l(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u, leader);
             }
-            ptx::mma_commit(&bar.w_empty[st]);
+            commit_l(&bar.w_empty[st], leader);
+            if (++st == kBwdRing) { st = 0; ph ^= 1u; }
           }
-          const int n = it * p.nc + c;  // position in the CTA's chunk sequence: group n & 1 transforms it
+          const int n = it * p.nc + c;
           if (kind == OP_M3) {
-            ptx::mma_commit(&bar.g_full[n & 1]);  // H_c (issued earlier) and G_c are complete
-            if (c == p.nc - 1) ptx::mma_commit(&bar.in_empty);
+            commit_l(&bar.g_full, leader);  // H_c (issued earlier) and G_c are complete
+            if (c == p.nc - 1) commit_l(&bar.in_empty, leader);
           }
-          if (kind == OP_M4 && c == p.nc - 1) ptx::mma_commit(&bar.x_done[n & 1]);
+          if (kind == OP_M4 && c == p.nc - 1) commit_l(&bar.x_done, leader);
+          if (TRACE && blockIdx.x == 0 && lane == 0 && tn < 8192 - 6) {
+            long long* t = p.trace + 8192 + tn;
+            t[0] = kind; t[1] = n; t[2] = t0; t[3] = clock64(); t[4] = tw; t[5] = ta;
+            tn += 6; tw = 0; ta = 0;
+          }
         }
       }
     }
   } else {
+    // All 16 transform warps work on EVERY chunk (4 lane quadrants x 4 column groups of 32): G is single-buffered, so
+    // M3(c) -> transform(c) -> [M4(c), M3(c + 1)] is a serial chain and the transform has to be as short as possible.
+    // A warp hands its part of dH_c back first and streams its A / dH block out to global memory afterwards, while
+    // the MMA warp already runs M4(c), M3(c + 1) and M1(c + 2).
     const int q = warp & 3;
-    const int pidx = (warp - 2) >> 2;
-    const int g = pidx >> 1;   // transform group: takes every other chunk of the CTA's chunk sequence
-    const int sub = pidx & 1;  // which 64 of the chunk's 128 columns
+    const int part = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float cs = kTruncComp * p.dscale;
-    const int my_tiles = p.tiles > (int)blockIdx.x ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int N = my_tiles * p.nc;
-    uint32_t n_out = 0;  // tiles whose dX this group has written
-    for (int n = g; n < N; n += 2) {
-      const int it = n / p.nc, c = n - it * p.nc;
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    uint32_t cu = 0;
+    int tn = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       const long long row = (long long)tile * 128 + q * 32 + lane;
-      ptx::mbar_wait(&bar.g_full[g], ((uint32_t)n >> 1) & 1u);
-      ptx::tc_fence_after_sync();
       const uint32_t rs = p.thr ? row_seed((unsigned long long)row, p.seed) : 0u;
-      // Column half j = 0 is written out right away, half j = 1 after the hand-over to the MMA warp (holding both
-      // halves' A and dH blocks at once would need 128 registers).
-      uint32_t ra[32], rd[32];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int col0 = sub * 64 + j * 32;
+      for (int c = 0; c < p.nc; ++c, ++cu) {
+        const long long t0 = TRACE ? clock64() : 0;
+        ptx::mbar_wait(&bar.g_full, cu & 1u);
+        const long long t1 = TRACE ? clock64() : 0;
+        ptx::tc_fence_after_sync();
+        const int col0 = part * 32;
+        uint32_t ra[32], rd[32];
         ptx::tmem_ld_32x32(tmem + (uint32_t)((c & 1) * 128 + col0) + lane_base, ra);
         ptx::tmem_ld_32x32(tG + (uint32_t)col0 + lane_base, rd);
         ptx::tmem_ld_wait();
@@ -661,12 +726,11 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         else
           bwd_transform<false>(ra, rd, bias, p.act, cs, 0u, 0u);
         ptx::tmem_st_32x32(tG + (uint32_t)col0 + lane_base, rd);
-        if (j == 1) {
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bar.d_ready);  // the MMA warp (and the other group) proceed
-        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.d_ready);
+        const long long t2 = TRACE ? clock64() : 0;
         const int col = c * kChunk + col0;
         if (row < p.M) {
           store_row32(out_a + row * p.hidden + col, ra);
@@ -674,23 +738,23 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         const float csum = warp_column_sums(rd, lane) * (1.0f / kTruncComp);  // rows >= M carry dY = 0, hence dH = 0
         if (p.db1_part != nullptr) p.db1_part[((long long)tile * 4 + q) * p.hidden + col + lane] = csum;
+        if (TRACE && blockIdx.x == 0 && q == 0 && (part & 1) == 0 && lane == 0 && tn < 4096 - 6) {
+          long long* t = p.trace + 16384 + (part >> 1) * 4096 + tn;
+          t[0] = 4; t[1] = cu; t[2] = t0; t[3] = t1; t[4] = t2; t[5] = clock64();
+          tn += 6;
+        }
       }
-      if (c == p.nc - 1) {
-        // ---- this group also writes the tile's dX (64 columns per warp)
-        ptx::mbar_wait(&bar.x_done[g], n_out & 1u);
-        ++n_out;
-        ptx::tc_fence_after_sync();
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(tX + (uint32_t)(sub * 64) + lane_base, r0);
-        ptx::tmem_ld_32x32(tX + (uint32_t)(sub * 64 + 32) + lane_base, r1);
+      // ---- tile done: dX (32 columns per warp)
+      ptx::mbar_wait(&bar.x_done, (uint32_t)it & 1u);
+      ptx::tc_fence_after_sync();
+      {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tX + (uint32_t)(part * 32) + lane_base, r);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar.xacc_free);
-        if (row < p.M) {
-          store_row32(p.dx + row * kD + sub * 64, r0);
-          store_row32(p.dx + row * kD + sub * 64 + 32, r1);
-        }
+        if (row < p.M) store_row32(p.dx + row * kD + part * 32, r);
       }
     }
   }
@@ -752,6 +816,7 @@ static int fill(Params& p, int64_t M, int64_t D, int64_t hidden, int act, float 
 using namespace xm;
 
 static long long* g_ffn_trace = nullptr;
+static int g_ffn_dbg = 0;
 
 extern "C" {
 
@@ -779,6 +844,7 @@ int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const
   const int ctas = p.tiles < kNumSMs ? p.tiles : kNumSMs;
   if (g_ffn_trace != nullptr) {  // debug instance: CTA 0 logs per-op clocks (xm_debug_set_ffn_trace)
     p.trace = g_ffn_trace;
+    p.dbg = g_ffn_dbg;
     if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_fwd_kernel<true>, ffn::kFwdSmem);
     if (rc != XM_OK) return rc;
     ffn::ffn_fwd_kernel<true><<<ctas, ffn::kThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
@@ -792,6 +858,10 @@ int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const
 
 int xm_debug_set_ffn_trace(int64_t* device_buffer) {
   g_ffn_trace = reinterpret_cast<long long*>(device_buffer);
+  return XM_OK;
+}
+int xm_debug_set_ffn_flags(int flags) {
+  g_ffn_dbg = flags;
   return XM_OK;
 }
 
@@ -812,10 +882,17 @@ int xm_ffn_fused_dgrad_f32(const float* x, const float* dy, const float* w1, con
   if (rc == XM_OK) rc = encode_tmap(&m1, ffn::view2(w1, D, hidden), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m2t, ffn::view2(w2t, D, hidden), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m1t, ffn::view2(w1t, hidden, D), 32, 128, 0);
-  if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_dgrad_kernel, ffn::kBwdSmem);
-  if (rc != XM_OK) return rc;
   const int ctas = p.tiles < kNumSMs ? p.tiles : kNumSMs;
-  ffn::ffn_dgrad_kernel<<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, a, dh, p);
+  if (g_ffn_trace != nullptr) {
+    p.trace = g_ffn_trace;
+    if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_dgrad_kernel<true>, ffn::kBwdSmem);
+    if (rc != XM_OK) return rc;
+    ffn::ffn_dgrad_kernel<true><<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, a, dh, p);
+    return check_launch();
+  }
+  if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_dgrad_kernel<false>, ffn::kBwdSmem);
+  if (rc != XM_OK) return rc;
+  ffn::ffn_dgrad_kernel<false><<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, a, dh, p);
   return check_launch();
 }
 

@@ -27,8 +27,6 @@ enum : int {
   EPI_ROWMAJOR = 0,    // C[z][tap][m][n] = act(alpha*acc + bias[n])
   EPI_LSE = 2,         // partial[ny][m]  = sum_n exp(alpha*acc - shift) ; diag[m] = alpha*acc[m, m+diag_off]
   EPI_NCE_GRAD = 3,    // C[m][n] = coef*(exp(s-lse_row[m]) + exp(s-lse_col[n]) - 2*[n == m+diag_off]),  s = alpha*acc
-  EPI_SOFTMAX = 4,     // attention probabilities: C[m][n] = drop(softmax_n(alpha*acc[m][:n_valid])), lse_out[z][m]
-  EPI_ATTN_DS = 5,     // attention score gradient from two accumulators (S = Q K^T, dP~ = dO V^T), see below
 };
 
 struct OperandCfg {
@@ -74,8 +72,6 @@ struct GemmParams {
                    // MMA's own accumulation truncates (a bias of ~3e-8 per K=8 step, i.e. 4e-4 over K = 120 000),
                    // which the fp32-accurate 3-pass projections cannot afford.  Needs acc_bufs == 2, taps_n == 1.
   int nx, ny, nz;  // tile grid (persistent CTAs walk tile = by + ny*(bx + nx*bz))
-  int dual;        // 1: two k-blocks per tile, (A, B) -> accumulator 0 and (A2, B2) -> accumulator 1 (EPI_ATTN_DS)
-  OperandCfg a2, b2;
   // epilogue
   int M, N;        // valid extents of the output (guards)
   int tma_store;   // 1: tile staged in swizzled smem and written by TMA through tmC (clips ragged edges)
@@ -96,22 +92,14 @@ struct GemmParams {
   int diag_off;
   float coef;
   float shift;
-  // attention epilogues (rows = queries of one (sample, head) slab z = bz*c_z_mul + by*c_y_mul)
-  float* lse_out;       // (Z, rows_valid) logsumexp of the scaled scores (EPI_SOFTMAX)
-  const float* lse_in;  // same, read by EPI_ATTN_DS
-  int n_valid;          // keys per row (columns >= n_valid are written as 0)
-  int rows_valid;       // queries per slab (L)
-  uint32_t drop_thresh32;  // keep <=> 32-bit mask-stream state >= thresh (0: no dropout)
-  float drop_scale;
-  unsigned long long seed;
 };
 
 // Epilogue warps per kernel flavour: 4 per TMEM lane quadrant "part"; the parts split a tile's columns.
-// A single warp per scheduler runs a dependent TMEM-load -> ALU -> store chain at low IPC, so the
-// epilogue-heavy flavours (row softmax, dS) use 16 warps and the plain stores 8.
+// A single warp per scheduler runs a dependent TMEM-load -> ALU -> store chain at low IPC, so the storing
+// flavours use 8 warps (the row-logsumexp flavour, which only reduces, 4).
 template <int EPI>
 struct EpiWarps {
-  static constexpr int value = (EPI == 4 || EPI == 5) ? 16 : (EPI == 2 ? 4 : 8);
+  static constexpr int value = EPI == 2 ? 4 : 8;
 };
 constexpr int gemm_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 32 tf32
@@ -165,170 +153,16 @@ XM_DEVICE uint64_t hash_u64(uint64_t idx, uint64_t seed) {
   return z ^ (z >> 31);
 }
 
-// Stage 32 fp32 values of this lane's row into the warp's swizzled buffer and TMA-store the 32x32 box.
-template <int NBUF>
-XM_DEVICE void stage_and_store(const CUtensorMap* tmC, uint8_t* stg, int& chunk_ctr, int lane, const float (&v)[32], int col,
-                               int row0, int z) {
-  uint8_t* sb = stg + (NBUF == 2 ? (chunk_ctr & 1) * 4096 : 0);
-  if (lane == 0) ptx::bulk_wait_read<NBUF - 1>();  // the store that last read this buffer has drained it
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  ptx::fence_proxy_async();
-  __syncwarp();
-  if (lane == 0) {
-    ptx::tma_store_3d(tmC, sb, col, row0, z);
-    ptx::bulk_commit();
-  }
-  ++chunk_ctr;
-}
-
-// Attention epilogues.  A quadrant's 4 warps ("parts") share 32 query rows of slab z: lane = row, part
-// = a quarter of the bn (<= 256) key columns.  The accumulator holds the raw scores Q K^T of complete
-// rows, so the row softmax only needs one max and one sum exchanged between the 4 parts (shared memory +
-// a 128-thread named barrier per quadrant).
-//   EPI_SOFTMAX:  P~[m][n] = keep(m, n) * softmax_n(alpha * S[m][:n_valid]) / (1 - p_drop)   (tf32-rounded), lse_out
-//   EPI_ATTN_DS:  accumulator 1 holds dP~ = dO V^T;  with P = exp(alpha*S - lse), P~ as above:
-//                 delta = sum_n P~ * dP~ ;  dS[m][n] = alpha * (P~ * dP~ - P * delta)       (tf32-rounded)
-XM_DEVICE void quad_barrier(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
-
-// Dropout mask stream of one (row, 32-column chunk): a well-mixed 32-bit seed, then one LCG step per
-// column; keep <=> state >= threshold (an unsigned compare is decided by the high bits, the good bits of a
-// power-of-two LCG).  3 integer instructions per element -- the epilogue below is issue-bound, and a full
-// hash per element group tripled its instruction count.
-XM_DEVICE uint32_t drop_stream_seed(unsigned long long row_id, int chunk, unsigned long long seed) {
-  return (uint32_t)(hash_u64(row_id * 8ull + (unsigned long long)chunk, seed) >> 32);
-}
-XM_DEVICE uint32_t lcg_next(uint32_t h) { return h * 747796405u + 2891336453u; }
-
-template <int EPI>
-XM_DEVICE void attention_epilogue(const GemmParams& p, const CUtensorMap& tmC, uint32_t acc, const TileCoord& t, int m,
-                                  bool row_ok, int q, int part, int lane, uint8_t* stg, int& chunk_ctr,
-                                  float (*red)[4][32]) {
-  const float kLog2e = 1.4426950408889634f;
-  const float c = p.alpha * kLog2e;
-  const int z = t.bz * p.c_z_mul + t.by * p.c_y_mul;
-  const bool live = row_ok && m < p.rows_valid;
-  const unsigned long long row_id = (unsigned long long)z * (unsigned long long)p.rows_valid + (unsigned long long)m;
-  const int nch = p.bn >> 7;       // 32-column chunks per part (bn is 128 or 256)
-  const int ch0 = part * nch;      // first chunk of this part
-  const uint32_t thr = p.drop_thresh32;
-  const float dscale = p.drop_scale;
-  float off;                       // log2-domain offset: P = exp2(acc*c - off)
-  if (EPI == EPI_SOFTMAX) {
-    float mx = -3.0e38f;
-    for (int ch = ch0; ch < ch0 + nch; ++ch) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
-      ptx::tmem_ld_wait();
-      const int nv = p.n_valid - ch * 32;
-      if (nv >= 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nv) mx = fmaxf(mx, __uint_as_float(r[j]));
-      }
-    }
-    red[q][part][lane] = mx;
-    quad_barrier(q);
-    mx = fmaxf(fmaxf(red[q][0][lane], red[q][1][lane]), fmaxf(red[q][2][lane], red[q][3][lane]));
-    const float mc = mx * c;
-    float sum = 0.f;
-    for (int ch = ch0; ch < ch0 + nch; ++ch) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
-      ptx::tmem_ld_wait();
-      const int nv = p.n_valid - ch * 32;
-      if (nv >= 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum += fast_exp2(fmaf(__uint_as_float(r[j]), c, -mc));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nv) sum += fast_exp2(fmaf(__uint_as_float(r[j]), c, -mc));
-      }
-    }
-    quad_barrier(q);  // every part has read the maxima: the exchange buffer can be reused
-    red[q][part][lane] = sum;
-    quad_barrier(q);
-    sum = (red[q][0][lane] + red[q][1][lane]) + (red[q][2][lane] + red[q][3][lane]);
-    off = mc + log2f(sum);
-    if (live && part == 0) p.lse_out[row_id] = off * 0.6931471805599453f;  // natural-log logsumexp of the scaled scores
-  } else {
-    off = live ? __ldg(p.lse_in + row_id) * kLog2e : 0.f;
-  }
-
-  float delta = 0.f;
-  if (EPI == EPI_ATTN_DS) {
-    for (int ch = ch0; ch < ch0 + nch; ++ch) {
-      uint32_t r[32], g[32];
-      ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
-      ptx::tmem_ld_32x32(acc + (uint32_t)(p.bn + ch * 32), g);
-      ptx::tmem_ld_wait();
-      const int nv = p.n_valid - ch * 32;
-      uint32_t h = drop_stream_seed(row_id, ch, p.seed);
-      float dk = 0.f, da = 0.f;  // kept / all
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        h = lcg_next(h);
-        float t2 = fast_exp2(fmaf(__uint_as_float(r[j]), c, -off)) * __uint_as_float(g[j]);
-        if (nv < 32 && j >= nv) t2 = 0.f;
-        if (h >= thr) dk += t2;
-        da += t2;
-      }
-      delta += thr ? dk * dscale : da;
-    }
-    red[q][part][lane] = delta;
-    quad_barrier(q);
-    delta = (red[q][0][lane] + red[q][1][lane]) + (red[q][2][lane] + red[q][3][lane]);
-  }
-
-  for (int ch = ch0; ch < ch0 + nch; ++ch) {
-    uint32_t r[32];
-    float v[32];
-    ptx::tmem_ld_32x32(acc + (uint32_t)(ch * 32), r);
-    if (EPI == EPI_ATTN_DS) {
-      uint32_t g[32];
-      ptx::tmem_ld_32x32(acc + (uint32_t)(p.bn + ch * 32), g);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(g[j]);
-    } else {
-      ptx::tmem_ld_wait();
-    }
-    const int nv = p.n_valid - ch * 32;
-    uint32_t h = drop_stream_seed(row_id, ch, p.seed);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      h = lcg_next(h);
-      const float pr = fast_exp2(fmaf(__uint_as_float(r[j]), c, -off));
-      const float mk = (h >= thr) ? dscale : 0.f;  // thr == 0 (no dropout): always kept, dscale == 1
-      float o = (EPI == EPI_ATTN_DS) ? p.alpha * pr * fmaf(mk, v[j], -delta) : pr * mk;
-      if (nv < 32 && j >= nv) o = 0.f;
-      v[j] = round_tf32(o);
-    }
-    stage_and_store<1>(&tmC, stg, chunk_ctr, lane, v, p.c_col_base + ch * 32, t.bx * 128 + q * 32, z);
-  }
-  if (EPI == EPI_ATTN_DS) quad_barrier(q);  // delta exchange buffer is free again for the next tile
-}
-
 template <int EPI>
 __global__ void __launch_bounds__(gemm_threads(EpiWarps<EPI>::value), 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ PeerMaps peers,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ PeerMaps peers, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red[4][4][32];  // per-quadrant exchange between the column parts (attention epilogues)
   constexpr int EW = EpiWarps<EPI>::value;
   constexpr int NPARTS = EW / 4;
   constexpr int NBUF = staging_bufs(EW);
@@ -354,10 +188,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     if (p.tma_store) ptx::prefetch_tensormap(&tmC);
-    if (p.dual) {
-      ptx::prefetch_tensormap(&tmA2);
-      ptx::prefetch_tensormap(&tmB2);
-    }
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -442,21 +272,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
           }
-        }
-        if (p.dual) {  // second operand pair of the tile: one k-block into accumulator 1
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-          if (lane == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-          __syncwarp();
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          issue_operand_loads(&tmA2, &full_bar[s], sa, p.a2,
-                              p.a2.base[0] + t.bx * p.a2.sx[0] + t.by * p.a2.sy[0] + t.bz * p.a2.sz[0],
-                              p.a2.base[1] + t.bx * p.a2.sx[1] + t.by * p.a2.sy[1] + t.bz * p.a2.sz[1],
-                              p.a2.base[2] + t.bx * p.a2.sx[2] + t.by * p.a2.sy[2] + t.bz * p.a2.sz[2], lane);
-          issue_operand_loads(&tmB2, &full_bar[s], sa + kATileBytes, p.b2,
-                              p.b2.base[0] + t.bx * p.b2.sx[0] + t.by * p.b2.sy[0] + t.bz * p.b2.sz[0],
-                              p.b2.base[1] + t.bx * p.b2.sx[1] + t.by * p.b2.sy[1] + t.bz * p.b2.sz[1],
-                              p.b2.base[2] + t.bx * p.b2.sx[2] + t.by * p.b2.sy[2] + t.bz * p.b2.sz[2], lane, 8);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -550,23 +365,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        if (p.dual) {
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tc_fence_after_sync();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t idesc2 = ptx::make_idesc_tf32(128, p.bn, p.a2.mn_major, p.b2.mn_major);
-#pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) {
-            const uint64_t da = ptx::make_smem_desc(sa + k8 * (p.a2.mn_major ? 1024u : 32u), p.a2.mn_major ? 4096u : 16u,
-                                                    p.a2.mn_major ? 512u : 1024u, p.a2.mn_major ? 1u : 2u);
-            const uint64_t db = ptx::make_smem_desc(sa + kATileBytes + k8 * (p.b2.mn_major ? 1024u : 32u),
-                                                    p.b2.mn_major ? 4096u : 16u, p.b2.mn_major ? 512u : 1024u,
-                                                    p.b2.mn_major ? 1u : 2u);
-            ptx::mma_tf32_ss(acc + (uint32_t)p.bn, da, db, idesc2, k8 > 0 ? 1u : 0u);
-          }
-          ptx::mma_commit(&empty_bar[s]);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
-        }
         ptx::mma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
     }
@@ -624,14 +422,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = m < p.M;
       const int n0 = t.by * p.n_stride;
       const int col0 = p.c_col_base + t.by * p.c_col_mul;  // tmC column of this tile's first column
-
-      if (EPI == EPI_SOFTMAX || EPI == EPI_ATTN_DS) {
-        attention_epilogue<EPI>(p, tmC, acc, t, m, row_ok, q, part, lane, stg, chunk_ctr, red);
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
-        continue;
-      }
 
       float lse_r = 0.f;
       if (EPI == EPI_NCE_GRAD && row_ok) lse_r = p.lse_row[m];
@@ -792,8 +582,7 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
 // `tc` describes the output for the TMA-store epilogue (dims {N, M, Z}); pass ptr == nullptr to use
 // the direct-store path (p.c / p.ldc).  `grid` is the TILE grid; the launch is persistent.
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
-                cudaStream_t stream, const TensorView3* ta2 = nullptr, const TensorView3* tb2 = nullptr,
-                const void* const* b_peers = nullptr);
+                cudaStream_t stream, const void* const* b_peers = nullptr);
 
 inline int tmem_cols_for(int n) {
   int c = 32;

@@ -61,28 +61,26 @@ int encode_tmap(CUtensorMap* out, const TensorView3& t, unsigned box0, unsigned 
 }
 
 template <int EPI>
-static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& ma2,
-                      const CUtensorMap& mb2, const PeerMaps& pm, const GemmParams& p, int ctas, size_t smem,
+static int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const PeerMaps& pm,
+                      const GemmParams& p, int ctas, size_t smem,
                       cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
-  gemm_tf32_kernel<EPI><<<ctas, gemm_threads(EpiWarps<EPI>::value), smem, stream>>>(ma, mb, mc, ma2, mb2, pm, p);
+  gemm_tf32_kernel<EPI><<<ctas, gemm_threads(EpiWarps<EPI>::value), smem, stream>>>(ma, mb, mc, pm, p);
   return check_launch();
 }
 
 int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const TensorView3& tc, GemmParams& p, dim3 grid,
-                cudaStream_t stream, const TensorView3* ta2, const TensorView3* tb2, const void* const* b_peers) {
+                cudaStream_t stream, const void* const* b_peers) {
   if (p.n_stride < 0) p.n_stride = p.bn;
   if (p.n_peers < 0 || p.n_peers > kMaxPeers || (p.n_peers > 0 && (!b_peers || p.peer_rows <= 0 || p.taps_n != 1)))
     return XM_ERR_INVALID;
   // a tile's row range must not straddle two shards
   if (p.n_peers > 0 && (p.peer_rows % (p.b.mn_major ? 32 : p.bn))) return XM_ERR_UNSUPPORTED;
   if (p.c_col_mul < 0) p.c_col_mul = p.bn;
-  p.dual = (ta2 != nullptr && tb2 != nullptr) ? 1 : 0;
-  if (p.dual && (p.taps_n != 1 || 2 * p.bn > 512)) return XM_ERR_UNSUPPORTED;
   if (p.bn < 16 || p.bn > 256 || (p.bn & 15)) return XM_ERR_UNSUPPORTED;
   if (p.b.mn_major && (p.bn & 31)) return XM_ERR_UNSUPPORTED;
   if (p.taps_n * p.bn > 512) return XM_ERR_UNSUPPORTED;
@@ -100,13 +98,13 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   if (!p.tma_store && epi != EPI_LSE && p.c == nullptr) return XM_ERR_INVALID;
   p.b_halo = 0;
   p.b_blk_bytes = 0;
-  if (p.taps_n > 1 && p.b.mn_major && !p.dual && p.n_peers == 0 && g_conv_halo) {
+  if (p.taps_n > 1 && p.b.mn_major && p.n_peers == 0 && g_conv_halo) {
     p.b_halo = p.taps_n - 1;
     p.b_blk_bytes = ((32 + p.b_halo) * 128 + 1023) / 1024 * 1024;
   }
   p.a_halo = 0;
   p.a_slab_bytes = 0;
-  if (p.taps_k > 1 && !p.a.mn_major && !p.b.mn_major && !p.dual && p.n_peers == 0 && p.taps_n == 1 && g_conv_halo &&
+  if (p.taps_k > 1 && !p.a.mn_major && !p.b.mn_major && p.n_peers == 0 && p.taps_n == 1 && g_conv_halo &&
       (p.a.tap_step[1] == 1 || p.a.tap_step[1] == -1) && p.a.tap_step[0] == 0 && p.a.tap_step[2] == 0) {
     // conv fwd / dgrad: tap t reads rows base + t*dir; the slab starts at the lowest of them
     p.a_halo = p.taps_k - 1;
@@ -127,40 +125,29 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   }
   const int total_kb = p.kout_count * p.taps_k * p.kin_count;
   if (total_kb <= 0) return XM_ERR_INVALID;
-  const int epi_warps = (epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) ? 16 : (epi == EPI_LSE ? 4 : 8);
+  const int epi_warps = epi == EPI_LSE ? 4 : 8;
   const int staging = p.tma_store ? staging_bytes(epi_warps) : 0;
   int stages = (222 * 1024 - 1024 - staging) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return XM_ERR_UNSUPPORTED;
   p.stages = stages;
   const int acc_cols = p.taps_n * p.bn;
-  p.acc_bufs = (2 * acc_cols <= 512 && ntiles > 1 && !p.dual) ? 2 : 1;
-  p.tmem_cols = tmem_cols_for(p.dual ? 2 * acc_cols : p.acc_bufs * acc_cols);
+  p.acc_bufs = (2 * acc_cols <= 512 && ntiles > 1) ? 2 : 1;
+  p.tmem_cols = tmem_cols_for(p.acc_bufs * acc_cols);
   // chunked fp32 accumulation: plain row-major tiles stored by TMA, two accumulator sets + the sum region
-  if (p.acc_chunk > 0 && (epi != EPI_ROWMAJOR || !p.tma_store || p.taps_n != 1 || p.dual || p.a_halo || p.b_halo ||
+  if (p.acc_chunk > 0 && (epi != EPI_ROWMAJOR || !p.tma_store || p.taps_n != 1 || p.a_halo || p.b_halo ||
                           (p.bn & 31) || 3 * p.bn > 512 || total_kb <= p.acc_chunk))
     p.acc_chunk = 0;
   if (p.acc_chunk > 0) {
     p.acc_bufs = 2;
     p.tmem_cols = tmem_cols_for(3 * p.bn);
   }
-  if ((epi == EPI_SOFTMAX || epi == EPI_ATTN_DS) && (!p.tma_store || (p.bn & 127))) return XM_ERR_UNSUPPORTED;
   p.a.rows = 128;
   p.b.rows = p.bn;
   const size_t smem = (size_t)stages * stage_bytes + staging + 1024;
 
-  CUtensorMap ma, mb, mc, ma2, mb2;
+  CUtensorMap ma, mb, mc;
   memset(&mc, 0, sizeof(mc));
-  memset(&ma2, 0, sizeof(ma2));
-  memset(&mb2, 0, sizeof(mb2));
-  if (p.dual) {
-    p.a2.rows = 128;
-    p.b2.rows = p.bn;
-    int rc2 = encode_tmap(&ma2, *ta2, 32, p.a2.mn_major ? 32 : 128, p.a2.mn_major);
-    if (rc2 != XM_OK) return rc2;
-    rc2 = encode_tmap(&mb2, *tb2, 32, p.b2.mn_major ? 32 : (unsigned)p.bn, p.b2.mn_major);
-    if (rc2 != XM_OK) return rc2;
-  }
   int rc = encode_tmap(&ma, ta, 32, p.a.mn_major ? 32 : (unsigned)(128 + p.a_halo), p.a.mn_major);
   if (rc != XM_OK) return rc;
   if (p.b_rows_dim2) {  // MN-major B whose contraction rows run along tensor dimension 2: box {32, 1, 32}
@@ -185,11 +172,9 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
   }
   const int ctas = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   switch (epi) {
-    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
-    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
-    case EPI_SOFTMAX: return launch_epi<EPI_SOFTMAX>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
-    case EPI_ATTN_DS: return launch_epi<EPI_ATTN_DS>(ma, mb, mc, ma2, mb2, pm, p, ctas, smem, stream);
+    case EPI_ROWMAJOR: return launch_epi<EPI_ROWMAJOR>(ma, mb, mc, pm, p, ctas, smem, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ma, mb, mc, pm, p, ctas, smem, stream);
+    case EPI_NCE_GRAD: return launch_epi<EPI_NCE_GRAD>(ma, mb, mc, pm, p, ctas, smem, stream);
   }
   return XM_ERR_INVALID;
 }
@@ -287,206 +272,6 @@ static int grid_for(long long n, int threads) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-
-// ------------------------------------------------------------------ multi-head self-attention
-// nn.MultiheadAttention core as called by TemporalTransformerBlock (EEG_CODE/enhanced_models_v4.py:71-73,98):
-// softmax(q k^T / sqrt(dh)) with dropout on the weights, times v -- per (sample, head) slab, L <= 256 keys.
-// Everything is the GEMM engine: the row softmax (and, in the backward, the whole dS formula) runs in the
-// epilogue of the score GEMM because one 128 x NP accumulator tile holds complete rows.
-struct AttnDims {
-  long long B, L, H, dh, NP, E;  // E = 3*H*dh (row pitch of qkv), NP = padded key count (128 or 256)
-};
-static int attn_dims(AttnDims& d, int64_t B, int64_t L, int64_t H, int64_t dh) {
-  if (B <= 0 || L <= 0 || H <= 0 || dh <= 0) return XM_ERR_INVALID;
-  if (dh != 32 || L > 256 || B > 2000000 || H > 64) return XM_ERR_UNSUPPORTED;
-  d.B = B; d.L = L; d.H = H; d.dh = dh;
-  d.NP = L <= 128 ? 128 : 256;
-  d.E = 3 * H * dh;
-  return XM_OK;
-}
-static TensorView3 view3(const void* ptr, long long d0, long long d1, long long d2, long long ld1, long long ld2) {
-  return TensorView3{ptr, {(unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2},
-                     {(unsigned long long)ld1 * 4, (unsigned long long)ld2 * 4}};
-}
-static void drop16(GemmParams& p, float drop_p, uint64_t seed) {
-  p.seed = seed;
-  if (drop_p > 0.f) {
-    double th = (double)drop_p * 4294967296.0;
-    p.drop_thresh32 = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
-    if (p.drop_thresh32 == 0u) p.drop_thresh32 = 1u;
-    p.drop_scale = 1.0f / (1.0f - drop_p);
-  } else {
-    p.drop_thresh32 = 0u;
-    p.drop_scale = 1.0f;
-  }
-}
-// operand = a (rows, dh) block of qkv: column offset col0 + head*dh, K-major (dh contiguous)
-static void qkv_kmajor(OperandCfg& o, const AttnDims& d, long long col0, bool tile_rows) {
-  o.mn_major = 0;
-  o.base[0] = (int)col0;
-  o.sy[0] = (int)d.dh;
-  if (tile_rows) o.sx[1] = 128;
-  o.sz[2] = 1;
-  o.kin_step[0] = 32;
-}
-// operand = the same block read MN-major (dh = GEMM N or M index contiguous, one row per contraction step)
-static void qkv_mnmajor(OperandCfg& o, const AttnDims& d, long long col0) {
-  o.mn_major = 1;
-  o.base[0] = (int)col0;
-  o.sy[0] = (int)d.dh;
-  o.sz[2] = 1;
-  o.kin_step[1] = 32;
-}
-// score-shaped operand (NP, L, B*H), slab z = bz*H + by
-static void slab_kmajor(OperandCfg& o, const AttnDims& d) {
-  o.mn_major = 0;
-  o.sx[1] = 128;
-  o.sy[2] = 1;
-  o.sz[2] = (int)d.H;
-  o.kin_step[0] = 32;
-}
-static void slab_mnmajor(OperandCfg& o, const AttnDims& d) {
-  o.mn_major = 1;
-  o.sx[0] = 128;
-  o.sy[2] = 1;
-  o.sz[2] = (int)d.H;
-  o.kin_step[1] = 32;
-}
-static void score_epilogue(GemmParams& p, const AttnDims& d, float scale) {
-  p.bn = (int)d.NP;
-  p.kin_count = (int)(d.dh / 32);
-  p.M = (int)d.L;
-  p.N = (int)d.NP;
-  p.n_valid = (int)d.L;
-  p.rows_valid = (int)d.L;
-  p.n_stride = 0;
-  p.c_col_base = 0;
-  p.c_col_mul = 0;
-  p.c_z_mul = (int)d.H;
-  p.c_y_mul = 1;
-  p.alpha = scale;
-}
-// out (B, L, out_pitch) columns [col_base + h*dh, +dh) = slab GEMM result
-static void head_output(GemmParams& p, const AttnDims& d, long long col_base) {
-  p.bn = (int)d.dh;
-  p.M = (int)d.L;
-  p.N = (int)(d.H * d.dh);
-  p.n_stride = (int)d.dh;
-  p.c_col_base = (int)col_base;
-  p.c_col_mul = (int)d.dh;
-  p.c_z_mul = 1;
-  p.c_y_mul = 0;
-}
-
-}  // namespace xm
-
-using namespace xm;
-
-extern "C" {
-
-int xm_attn_keys_padded(int64_t L) { return L <= 128 ? 128 : 256; }
-
-int xm_attn_fwd_f32(const float* qkv, float* out, float* probs, float* lse, int64_t B, int64_t L, int64_t H, int64_t dh,
-                    float scale, float drop_p, uint64_t seed, int round_out, void* stream) {
-  if (!qkv || !out || !probs || !lse || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
-  AttnDims d;
-  int rc = attn_dims(d, B, L, H, dh);
-  if (rc != XM_OK) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const TensorView3 tq = view3(qkv, d.E, L, B, d.E, L * d.E);
-  const TensorView3 tp = view3(probs, d.NP, L, B * H, d.NP, L * d.NP);
-  const dim3 grid(ceil_div(L, 128), (unsigned)H, (unsigned)B);
-  {  // P~ = dropout(softmax(scale * q k^T))
-    GemmParams p;
-    zero_params(p);
-    qkv_kmajor(p.a, d, 0, true);
-    qkv_kmajor(p.b, d, H * dh, false);
-    score_epilogue(p, d, scale);
-    drop16(p, drop_p, seed);
-    p.lse_out = lse;
-    rc = launch_gemm(EPI_SOFTMAX, tq, tq, tp, p, grid, st);
-    if (rc != XM_OK) return rc;
-  }
-  {  // out[:, :, h*dh:(h+1)*dh] = P~ v
-    GemmParams p;
-    zero_params(p);
-    slab_kmajor(p.a, d);
-    qkv_mnmajor(p.b, d, 2 * H * dh);
-    head_output(p, d, 0);
-    p.kin_count = (int)(d.NP / 32);
-    p.round_tf32 = round_out;
-    const TensorView3 to = view3(out, H * dh, L, B, H * dh, L * H * dh);
-    rc = launch_gemm(EPI_ROWMAJOR, tp, tq, to, p, grid, st);
-  }
-  return rc;
-}
-
-int xm_attn_bwd_f32(const float* dout, const float* qkv, const float* probs, const float* lse, float* dqkv, float* ds,
-                    int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed, int round_out,
-                    void* stream) {
-  if (!dout || !qkv || !probs || !lse || !dqkv || !ds || !(drop_p >= 0.f && drop_p < 1.f)) return XM_ERR_INVALID;
-  AttnDims d;
-  int rc = attn_dims(d, B, L, H, dh);
-  if (rc != XM_OK) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const TensorView3 tq = view3(qkv, d.E, L, B, d.E, L * d.E);
-  const TensorView3 tp = view3(probs, d.NP, L, B * H, d.NP, L * d.NP);
-  const TensorView3 ts = view3(ds, d.NP, L, B * H, d.NP, L * d.NP);
-  const TensorView3 tdo = view3(dout, H * dh, L, B, H * dh, L * H * dh);
-  const TensorView3 tdq = view3(dqkv, d.E, L, B, d.E, L * d.E);
-  const dim3 grid(ceil_div(L, 128), (unsigned)H, (unsigned)B);
-  const int kq = ceil_div(L, 32);  // contraction over queries (rows >= L are zero-filled by TMA)
-  {  // dS = scale * (P~ o dP~ - P * rowsum(P~ o dP~)),  S = q k^T and dP~ = dO v^T recomputed side by side in TMEM
-    GemmParams p;
-    zero_params(p);
-    qkv_kmajor(p.a, d, 0, true);
-    qkv_kmajor(p.b, d, H * dh, false);
-    qkv_kmajor(p.a2, d, 0, true);  // dO (B, L, H*dh): head h at column h*dh
-    qkv_kmajor(p.b2, d, 2 * H * dh, false);
-    score_epilogue(p, d, scale);
-    drop16(p, drop_p, seed);
-    p.lse_in = lse;
-    rc = launch_gemm(EPI_ATTN_DS, tq, tq, ts, p, grid, st, &tdo, &tq);
-    if (rc != XM_OK) return rc;
-  }
-  {  // dv = P~^T dO
-    GemmParams p;
-    zero_params(p);
-    slab_mnmajor(p.a, d);
-    qkv_mnmajor(p.b, d, 0);
-    head_output(p, d, 2 * H * dh);
-    p.kin_count = kq;
-    p.round_tf32 = round_out;
-    rc = launch_gemm(EPI_ROWMAJOR, tp, tdo, tdq, p, grid, st);
-    if (rc != XM_OK) return rc;
-  }
-  {  // dk = dS^T q
-    GemmParams p;
-    zero_params(p);
-    slab_mnmajor(p.a, d);
-    qkv_mnmajor(p.b, d, 0);
-    head_output(p, d, H * dh);
-    p.kin_count = kq;
-    p.round_tf32 = round_out;
-    rc = launch_gemm(EPI_ROWMAJOR, ts, tq, tdq, p, grid, st);
-    if (rc != XM_OK) return rc;
-  }
-  {  // dq = dS k
-    GemmParams p;
-    zero_params(p);
-    slab_kmajor(p.a, d);
-    qkv_mnmajor(p.b, d, H * dh);
-    head_output(p, d, 0);
-    p.kin_count = (int)(d.NP / 32);
-    p.round_tf32 = round_out;
-    rc = launch_gemm(EPI_ROWMAJOR, ts, tq, tdq, p, grid, st);
-  }
-  return rc;
-}
-
-}  // extern "C"
-
-namespace xm {
 
 }  // namespace xm
 
@@ -618,8 +403,7 @@ static int linear_dgrad_impl(const float* dy, const float* w, const void* const*
   TensorView3 ta{dy, {(unsigned long long)N, (unsigned long long)M, 1}, {(unsigned long long)lddy * 4, (unsigned long long)M * lddy * 4}};
   TensorView3 tb{w ? (const void*)w : w_peers[0], {(unsigned long long)K, (unsigned long long)N, 1}, {(unsigned long long)ldw * 4, (unsigned long long)N * ldw * 4}};
   const TensorView3 tc = TensorView3{dx, {(unsigned long long)(K), (unsigned long long)(M), (unsigned long long)(1)}, {(unsigned long long)(lddx) * 4, (unsigned long long)(M * lddx) * 4}};
-  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream, nullptr, nullptr,
-                     w_peers);
+  return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(m_tiles, ceil_div(K, p.bn), 1), (cudaStream_t)stream, w_peers);
 }
 
 int xm_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int64_t N, int64_t K, int64_t lddy,
@@ -926,7 +710,7 @@ static int infonce_lse_impl(const float* a, const float* b, const void* const* b
   TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
   TensorView3 tb{b ? (const void*)b : b_peers[0], {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
   const TensorView3 tc{nullptr, {0, 0, 0}, {0, 0}};
-  int rc = launch_gemm(EPI_LSE, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ntiles, 1), st, nullptr, nullptr, b_peers);
+  int rc = launch_gemm(EPI_LSE, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ntiles, 1), st, b_peers);
   if (rc != XM_OK) return rc;
   lse_finalize_kernel<<<ceil_div(Ml, 256), 256, 0, st>>>(workspace, ntiles, Ml, inv_tau, lse);
   return check_launch();
@@ -968,8 +752,7 @@ static int infonce_grad_impl(const float* a, const float* b, const void* const* 
   TensorView3 ta{a, {(unsigned long long)D, (unsigned long long)Ml, 1}, {(unsigned long long)D * 4, (unsigned long long)Ml * D * 4}};
   TensorView3 tb{b ? (const void*)b : b_peers[0], {(unsigned long long)D, (unsigned long long)Ng, 1}, {(unsigned long long)D * 4, (unsigned long long)Ng * D * 4}};
   const TensorView3 tc = TensorView3{G, {(unsigned long long)(Ng), (unsigned long long)(Ml), (unsigned long long)(1)}, {(unsigned long long)(Ng) * 4, (unsigned long long)(Ml * Ng) * 4}};
-  return launch_gemm(EPI_NCE_GRAD, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, 128), 1), (cudaStream_t)stream, nullptr,
-                     nullptr, b_peers);
+  return launch_gemm(EPI_NCE_GRAD, ta, tb, tc, p, dim3(ceil_div(Ml, 128), ceil_div(Ng, 128), 1), (cudaStream_t)stream, b_peers);
 }
 
 int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, const float* lse_col, float* G,

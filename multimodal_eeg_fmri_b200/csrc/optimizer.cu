@@ -1,0 +1,106 @@
+// clip_grad_norm_ + AdamW over ONE flat bucket in two launches (the step recipe of _test_bridge.py:775-788,869 /
+// run_fmri_v11.py:430-450 / run_training_lite.py:478-489: clip_grad_norm_(max_norm) then AdamW.step).  The
+// reference's torch path issues a foreach norm, a clamp, a foreach multiply and the optimizer's foreach kernels per
+// parameter group; here every parameter, gradient and moment lives in one flat fp32 buffer:
+//   1. xm_sumsq_partials_f32: per-block sum of squares of the gradient bucket in fp64 (deterministic two-stage sum)
+//   2. xm_clip_adamw_f32: every block folds the partials into the total norm, derives the clip coefficient
+//      min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_) and applies torch.optim.AdamW's update
+//        p *= 1 - lr * wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+//        p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+//      with g already scaled by the clip coefficient; the clipped gradient is written back (the bucket then holds
+//      what clip_grad_norm_ leaves in .grad).
+#include "xm_common.cuh"
+
+namespace xm {
+namespace opt {
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) sumsq_partials_kernel(const float* __restrict__ g, long long n, double* __restrict__ partials) {
+  double acc = 0.0;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kThreads) {
+    const float4 v = g4[i];
+    acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += kThreads) acc += (double)g[i] * g[i];
+  __shared__ double red[kThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partials[blockIdx.x] = v;
+  }
+}
+
+struct AdamArgs {
+  float max_norm, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt;
+};
+
+__global__ void __launch_bounds__(kThreads)
+clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                  const double* __restrict__ partials, int nblk, AdamArgs a, float* __restrict__ norm_out) {
+  __shared__ double red[kThreads / 32];
+  __shared__ float s_coef;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += kThreads) acc += partials[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      const float norm = (float)sqrt(t);
+      s_coef = a.max_norm > 0.f ? fminf(a.max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+      if (blockIdx.x == 0 && norm_out != nullptr) *norm_out = norm;
+    }
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  const float decay = 1.0f - a.lr * a.weight_decay, step = a.lr / a.bias_c1, inv_c2 = 1.0f / a.bias_c2_sqrt;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    const float gi = g[i] * coef;
+    const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * gi;
+    const float vi = a.beta2 * v[i] + (1.0f - a.beta2) * gi * gi;
+    g[i] = gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] * decay - step * mi / (sqrtf(vi) * inv_c2 + a.eps);
+  }
+}
+
+}  // namespace opt
+}  // namespace xm
+
+using namespace xm;
+
+extern "C" int xm_sumsq_nblk(int64_t n) {
+  int64_t b = (n / 4 + opt::kThreads - 1) / opt::kThreads;
+  if (b > kNumSMs * 4) b = kNumSMs * 4;
+  return (int)(b < 1 ? 1 : b);
+}
+
+extern "C" int xm_sumsq_partials_f32(const float* g, int64_t n, double* partials, void* stream) {
+  if (!g || !partials || n <= 0 || (reinterpret_cast<uintptr_t>(g) & 15)) return XM_ERR_INVALID;
+  opt::sumsq_partials_kernel<<<xm_sumsq_nblk(n), opt::kThreads, 0, (cudaStream_t)stream>>>(g, n, partials);
+  return check_launch();
+}
+
+extern "C" int xm_clip_adamw_f32(float* p, float* g, float* m, float* v, int64_t n, const double* partials, int nblk, float max_norm,
+                                 float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float* norm_out,
+                                 void* stream) {
+  if (!p || !g || !m || !v || !partials || n <= 0 || nblk <= 0 || step <= 0) return XM_ERR_INVALID;
+  opt::AdamArgs a;
+  a.max_norm = max_norm; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
+  a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  int64_t blocks = (n + opt::kThreads - 1) / opt::kThreads;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  opt::clip_adamw_kernel<<<(int)blocks, opt::kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, partials, nblk, a, norm_out);
+  return check_launch();
+}

@@ -56,12 +56,14 @@ def start_timeline() -> None:
     _timeline = []
 
 
-def stop_timeline():
+def stop_timeline(raw: bool = False):
     """-> {entry point: (calls, total ms, algorithmic flops, algorithmic bytes)}; times are CUDA events on the
-    launching stream around each C-ABI call."""
+    launching stream around each C-ABI call.  raw=True: the calls in launch order, [(entry point, ms, flops, bytes)]."""
     global _timeline
     tl, _timeline = _timeline or [], None
     torch.cuda.synchronize()
+    if raw:
+        return [(name, a.elapsed_time(b), fl, by) for name, a, b, (fl, by) in tl]
     out = {}
     for name, a, b, (fl, by) in tl:
         n, ms, f0, b0 = out.get(name, (0, 0.0, 0.0, 0.0))
@@ -662,38 +664,8 @@ def linear_dgrad_peers(dy, peer_ptrs, rows_per_peer, K, ldw):
 
 # ------------------------------------------------------------------ multi-head self-attention core
 def attn_supported(L: int, dh: int) -> bool:
-    """Shapes of the fused attention core (xm_attn_fused_*); the materialising xm_attn_* variant stops at L = 256."""
+    """Shapes of the fused tcgen05 attention core (xm_attn_fused_*); everything else: attn_general_*."""
     return dh == 32 and 0 < L <= 512
-
-
-def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
-    """qkv (B, L, 3*H*dh) packed in_proj output -> (out (B, L, H*dh), probs (B*H, L, NP), lse (B*H, L))."""
-    _chk(qkv)
-    qkv = qkv.contiguous()
-    B, L, E = qkv.shape
-    d = E // 3
-    dh = d // nhead
-    NP = _lib.lib().xm_attn_keys_padded(L)
-    out = torch.empty(B, L, d, device=qkv.device, dtype=torch.float32)
-    probs = torch.empty(B * nhead, L, NP, device=qkv.device, dtype=torch.float32)
-    lse = torch.empty(B * nhead, L, device=qkv.device, dtype=torch.float32)
-    _w(4.0 * B * nhead * L * L * dh, 4.0 * (qkv.numel() + out.numel() + 2 * probs.numel()))
-    _call("xm_attn_fwd_f32", _p(qkv), _p(out), _p(probs), _p(lse), B, L, nhead, dh, float(scale), float(drop_p), int(seed),
-          int(round_out), _stream())
-    return out, probs, lse
-
-
-def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
-    _chk(dout, qkv, probs, lse)
-    dout = dout.contiguous()
-    B, L, E = qkv.shape
-    dh = E // 3 // nhead
-    dqkv = torch.empty_like(qkv)
-    ds = torch.empty_like(probs)
-    _w(10.0 * B * nhead * L * L * dh, 4.0 * (2 * qkv.numel() + dout.numel() + 4 * probs.numel()))
-    _call("xm_attn_bwd_f32", _p(dout), _p(qkv), _p(probs), _p(lse), _p(dqkv), _p(ds), B, L, nhead, dh, float(scale),
-          float(drop_p), int(seed), int(round_out), _stream())
-    return dqkv
 
 
 def attn_fused_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
@@ -970,3 +942,20 @@ def roi_corrcoef(x):
     _w(2.0 * B * TR * ROI * ROI, 4.0 * (x.numel() + out.numel()))
     _call("xm_roi_corrcoef_f32", _p(x), B, TR, ROI, _p(out), _stream())
     return out
+
+
+# ------------------------------------------------------------------ optimizer step over one flat bucket
+def clip_adamw_(p, g, m, v, step, lr, weight_decay, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8):
+    """In place on flat fp32 buffers: clip_grad_norm_(max_norm) + torch.optim.AdamW update for 1-based `step`.
+    -> the pre-clip total gradient norm (1-element device tensor)."""
+    _chk(p, g, m, v)
+    n = p.numel()
+    nblk = _lib.lib().xm_sumsq_nblk(n)
+    part = torch.empty(nblk, device=p.device, dtype=torch.float64)
+    norm = torch.empty(1, device=p.device, dtype=torch.float32)
+    _w(2.0 * n, 4.0 * n)
+    _call("xm_sumsq_partials_f32", _p(g), n, _p(part), _stream())
+    _w(12.0 * n, 28.0 * n)
+    _call("xm_clip_adamw_f32", _p(p), _p(g), _p(m), _p(v), n, _p(part), nblk, float(max_norm), float(lr), float(betas[0]),
+          float(betas[1]), float(eps), float(weight_decay), int(step), _p(norm), _stream())
+    return norm

@@ -108,7 +108,8 @@ def init_distributed(backend: str = "nccl") -> XF.ParallelContext:
 
 
 class PairedTrainer:
-    """zero_grad -> forward -> backward -> [all-reduce] -> clip_grad_norm_ -> AdamW, on one flat gradient bucket."""
+    """zero_grad -> forward -> backward -> [all-reduce] -> clip_grad_norm_ -> AdamW (_test_bridge.py:775-788, :869),
+    on flat parameter / gradient / moment buffers."""
 
     def __init__(self, model: PairedBridgeModel, lr: float = 1e-4, weight_decay: float = 1e-4, grad_clip: float = 1.0,
                  window: Optional[int] = None, hop: Optional[int] = None):
@@ -118,12 +119,26 @@ class PairedTrainer:
         self.params = model.contrastive_parameters()
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
-        o = 0
-        for p in self.params:  # gradients are views into one bucket: one collective, one norm
+        # Parameters, gradients and both AdamW moments live in ONE flat fp32 buffer each (every tensor 16-B aligned in
+        # it): one gradient collective, and norm + clip + update are two launches (ops.clip_adamw_) instead of the
+        # foreach kernels of clip_grad_norm_ / torch.optim.AdamW.  The module's parameters become views of the flat
+        # buffer, so state_dict() / load_state_dict() keep working on the same storage.
+        offs, o = [], 0
+        for p in self.params:
+            offs.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.flat_param = torch.zeros(o, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(o, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(o, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(o, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, offs):
+            view = self.flat_param[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
-            o += p.numel()
-        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=dev.type == "cuda")
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, (0.9, 0.999), 1e-8
+        self.step_count = 0
+        self.last_grad_norm = None  # pre-clip total norm of the last step (device scalar)
         self.ctx = XF.parallel_context()
         self._stage = {}
 
@@ -142,10 +157,9 @@ class PairedTrainer:
         loss.backward()
         if self.ctx.active:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.ctx.group)
-        if self.grad_clip and self.grad_clip > 0:
-            total = torch.linalg.vector_norm(self.flat_grad)
-            self.flat_grad.mul_(torch.clamp(self.grad_clip / (total + 1e-6), max=1.0))
-        self.opt.step()
+        self.step_count += 1
+        self.last_grad_norm = ops.clip_adamw_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
+                                              self.lr, self.weight_decay, self.grad_clip or 0.0, self.betas, self.eps)
         return loss.detach()
 
     # -- end-to-end step from pinned host buffers --------------------------------------------

@@ -274,7 +274,7 @@ def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef, round_out=Fals
 
 # ---------------------------------------------------------------- attention core
 def attn_supported(L, dh):
-    return dh == 32 and 0 < L <= 256
+    return dh == 32 and 0 < L <= 512
 
 
 def _attn_parts(qkv, nhead):
@@ -284,7 +284,7 @@ def _attn_parts(qkv, nhead):
     return q, k, v
 
 
-def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
+def _attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
     _nodrop(drop_p)
     B, L, E = qkv.shape
     q, k, v = _attn_parts(qkv, nhead)
@@ -294,7 +294,7 @@ def attn_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
     return out.float(), p.reshape(B * nhead, L, L).float(), torch.logsumexp(s, -1).reshape(B * nhead, L).float()
 
 
-def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
+def _attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
     _nodrop(drop_p)
     B, L, E = qkv.shape
     d = E // 3
@@ -310,7 +310,7 @@ def attn_bwd(dout, qkv, probs, lse, nhead, scale, drop_p=0.0, seed=0, round_out=
 
 
 def attn_fused_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
-    out, _, lse = attn_fwd(qkv, nhead, scale, drop_p, seed, round_out)
+    out, _, lse = _attn_fwd(qkv, nhead, scale, drop_p, seed, round_out)
     return out, lse
 
 
@@ -319,7 +319,7 @@ def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_
     B, L, E = qkv.shape
     q, k, _ = _attn_parts(qkv, nhead)
     probs = torch.exp(q @ k.transpose(-1, -2) * scale - lse.reshape(B, nhead, L, 1).double())
-    return attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
+    return _attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
 
 
 def attn_general_supported(L, dh):
@@ -348,7 +348,7 @@ def attn_general_bwd(dout, qkv, lse, nhead, scale, mask=None, drop_p=0.0, seed=0
     B, L, E = qkv.shape
     q, k, v, s = _attn_general_scores(qkv, nhead, scale, mask)
     probs = torch.exp(s - lse.reshape(B, nhead, L, 1).double())
-    return attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
+    return _attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
 
 
 # ---------------------------------------------------------------- fused feed-forward branch
@@ -424,6 +424,18 @@ def roi_corrcoef(x):
     c = xc.transpose(1, 2) @ xc
     d = torch.sqrt(torch.diagonal(c, dim1=1, dim2=2))
     return (c / d[:, :, None] / d[:, None, :]).clamp(-1, 1).reshape(x.shape[0], -1).float()
+
+
+def clip_adamw_(p, g, m, v, step, lr, weight_decay, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8):
+    norm = g.double().norm().float()
+    if max_norm > 0:
+        g.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
+    p.mul_(1 - lr * weight_decay)
+    m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    c1, c2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    p.addcdiv_(m, v.sqrt() / c2 ** 0.5 + eps, value=-lr / c1)
+    return norm.reshape(1)
 
 
 def zscore(x, eps=1e-8):

@@ -356,59 +356,6 @@ def test_error_codes_surface_as_exceptions(ops):
 
 
 # ------------------------------------------------------------------ fused attention core
-@pytest.mark.parametrize("B,L,H", [(2, 250, 4), (3, 128, 2), (1, 37, 1), (5, 256, 4), (2, 129, 3)])
-def test_attention_core_fwd_bwd(ops, B, L, H):
-    """softmax(q k^T / sqrt(dh)) v against fp64 torch (dropout off): out, lse, probabilities and dqkv."""
-    torch.manual_seed(12)
-    dh = 32
-    d = H * dh
-    # as on the product path, the projections arrive tf32-rounded from their producer GEMM
-    qkv = ops.round_tf32(torch.randn(B, L, 3 * d, device="cuda"))
-    dout = ops.round_tf32(torch.randn(B, L, d, device="cuda"))
-    scale = dh ** -0.5
-    out, probs, lse = ops.attn_fwd(qkv, H, scale, 0.0, 0, round_out=False)
-    x = qkv.double().requires_grad_(True)
-    q, k, v = (t.reshape(B, L, H, dh).transpose(1, 2) for t in x.chunk(3, dim=-1))
-    s = q @ k.transpose(-1, -2) * scale
-    p = torch.softmax(s, dim=-1)
-    ref = (p @ v).transpose(1, 2).reshape(B, L, d)
-    assert_close_rel(out, ref, TF32, "attention out")
-    assert float((lse.double() - torch.logsumexp(s, -1).reshape(B * H, L)).abs().max()) < 2e-3
-    assert_close_rel(probs[:, :, :L], p.reshape(B * H, L, L), TF32, "probabilities")
-    assert float(probs[:, :, L:].abs().max()) == 0.0 if probs.shape[2] > L else True
-    (gx,) = torch.autograd.grad(ref, x, dout.double())
-    dqkv = ops.attn_bwd(dout, qkv, probs, lse, H, scale, 0.0, 0)
-    for name, a, b in zip("qkv", dqkv.chunk(3, dim=-1), gx.chunk(3, dim=-1)):
-        assert_close_rel(a, b, 2e-3, f"d{name}")
-
-
-def test_attention_core_dropout_consistency(ops):
-    """Dropout on the attention weights: keep rate, inverted scaling, and a backward that regenerates the
-    same mask (checked against autograd through the saved dropped probabilities)."""
-    torch.manual_seed(13)
-    B, L, H, dh, pdrop, seed = 2, 250, 4, 32, 0.3, 4242
-    d = H * dh
-    qkv = ops.round_tf32(torch.randn(B, L, 3 * d, device="cuda") * 0.5)
-    dout = ops.round_tf32(torch.randn(B, L, d, device="cuda"))
-    scale = dh ** -0.5
-    out, probs, lse = ops.attn_fwd(qkv, H, scale, pdrop, seed, round_out=False)
-    _, probs0, _ = ops.attn_fwd(qkv, H, scale, 0.0, 0, round_out=False)
-    keep = probs[:, :, :L] != 0
-    assert abs(float(keep.float().mean()) - (1 - pdrop)) < 3e-3
-    assert torch.allclose(probs[:, :, :L][keep], (probs0[:, :, :L] / (1 - pdrop))[keep], rtol=2e-3, atol=1e-7)
-    out2, probs2, _ = ops.attn_fwd(qkv, H, scale, pdrop, seed, round_out=False)
-    assert torch.equal(probs, probs2) and torch.equal(out, out2)
-    # reference gradient with the SAME mask: P~ = mask/(1-p) * softmax(s)
-    mask = keep.reshape(B, H, L, L).double() / (1 - pdrop)
-    x = qkv.double().requires_grad_(True)
-    q, k, v = (t.reshape(B, L, H, dh).transpose(1, 2) for t in x.chunk(3, dim=-1))
-    ref = ((torch.softmax(q @ k.transpose(-1, -2) * scale, -1) * mask) @ v).transpose(1, 2).reshape(B, L, d)
-    assert_close_rel(out, ref, TF32, "attention out with dropout")
-    (gx,) = torch.autograd.grad(ref, x, dout.double())
-    dqkv = ops.attn_bwd(dout, qkv, probs, lse, H, scale, pdrop, seed)
-    assert_close_rel(dqkv, gx, 3e-3, "dqkv with dropout")
-
-
 def _attn_ref(qkv, B, L, H, dh, scale, mask=None):
     x = qkv.double().requires_grad_(True)
     q, k, v = (t.reshape(B, L, H, dh).transpose(1, 2) for t in x.chunk(3, dim=-1))
@@ -665,17 +612,15 @@ def test_ragged_outputs_do_not_write_past_their_extent(ops):
     B, L, H, dh = 3, 77, 2, 32
     d = H * dh
     qkv = ops.round_tf32(torch.randn(B, L, 3 * d, device="cuda"))
-    NP = _lib.lib().xm_attn_keys_padded(L)
     g = 256
     obuf = torch.full((g + B * L * d + g,), SENT, device="cuda")
-    pbuf = torch.full((g + B * H * L * NP + g,), SENT, device="cuda")
     lbuf = torch.full((g + B * H * L + g,), SENT, device="cuda")
-    out, probs, lse = obuf[g:-g].view(B, L, d), pbuf[g:-g].view(B * H, L, NP), lbuf[g:-g].view(B * H, L)
-    _lib.call("xm_attn_fwd_f32", P(qkv), P(out), P(probs), P(lse), B, L, H, dh, ctypes.c_float(dh ** -0.5), ctypes.c_float(0.0), 0, 0, st)
+    out, lse = obuf[g:-g].view(B, L, d), lbuf[g:-g].view(B * H, L)
+    _lib.call("xm_attn_fused_fwd_f32", P(qkv), P(out), P(lse), B, L, H, dh, ctypes.c_float(dh ** -0.5), ctypes.c_float(0.0), 0, 0, st)
     torch.cuda.synchronize()
-    for b_ in (obuf, pbuf, lbuf):
+    for b_ in (obuf, lbuf):
         assert bool((b_[:g] == SENT).all()) and bool((b_[-g:] == SENT).all())
-    assert not bool((out == SENT).any()) and not bool((lse == SENT).any()) and not bool((probs == SENT).any())
+    assert not bool((out == SENT).any()) and not bool((lse == SENT).any())
 
 
 def test_empty_and_degenerate_inputs(ops):

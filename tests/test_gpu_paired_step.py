@@ -138,6 +138,38 @@ def test_paired_step_config3_shape_vs_oracle():
         assert_close_rel(named[k].grad, ograds[k], 1e-2, f"grad {k}", atol=1e-6)
 
 
+def test_baseline_shape_parity_every_gradient_within_1e3():
+    """The north-star tolerance at the BASELINE shapes (64 ch x 500 samples, 200 ROI x 100 TR, conn 40 000, v4
+    encoder) and a 2048-sample batch -- the largest the fp32 CPU oracle finishes in a few seconds on the box's host
+    cores: loss and EVERY parameter gradient (60 tensors) within 1e-3 relative of the oracle.  The first two convs run
+    their forward in the 3-pass fp32-accurate mode for this (profiles/r2_tf32_floor_by_layer.log: their single-pass
+    operand rounding alone costs 7e-3 .. 1e-2 on five tensors); biases in front of a train-mode BatchNorm have a
+    mathematically zero gradient and only get a noise bound."""
+    from multimodal_eeg_fmri_b200 import synthetic
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel
+    from oracle import paired_step as ops_
+    torch.manual_seed(42)
+    m = PairedBridgeModel(64, 200, None, 128, 64, 128, 0.0, 0.0, "v4")
+    P = _sd_cpu(m)
+    eeg, roi, conn = synthetic.paired_batch(2048, 64, 500, 200, 100, seed=42)
+    m = m.cuda().train()
+    loss = m(eeg.cuda(), roi.cuda(), conn.cuda())
+    loss.backward()
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    oloss, ograds = ops_.paired_loss_and_grads(P, eeg, roi, conn, 0.07, "v4")
+    assert_close_rel(loss, oloss, 1e-5, "InfoNCE loss")
+    named = dict(m.named_parameters())
+    zero = bias_before_batchnorm(m.state_dict().keys())
+    checked = 0
+    for k, g in ograds.items():
+        if k in zero:
+            assert_zero_grad_noise(named[k].grad, named[k[: -len("bias")] + "weight"].grad, f"grad {k}")
+            continue
+        assert_close_rel(named[k].grad, g, 1e-3, f"grad {k}")
+        checked += 1
+    assert checked >= 55
+
+
 def test_full_batch_4096_step_properties():
     """BASELINE config 4 per-GPU shape (B = 4096, v4 encoder): the step runs, the loss starts near
     log(B) for random init, is finite, and decreases over a few steps on a fixed batch."""

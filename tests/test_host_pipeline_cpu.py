@@ -40,6 +40,21 @@ def test_paired_model_autograd_plumbing_vs_oracle(fakes, encoder):
         assert_close_rel(named[k].grad, g, 2e-4, f"grad {k}", atol=1e-6)
 
 
+def test_paired_model_with_derived_connectivity_vs_oracle(fakes):
+    """conn=None: the connectivity features are the flattened ROI x ROI correlation matrix of the series, derived
+    inside the step (n_roi 12 -> conn_dim 144), on both sides."""
+    m = dp_worker.make_model("lite").train()
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    eeg, roi, _ = synthetic.paired_batch(16, 8, 64, 12, 20, seed=3)
+    loss = m(eeg, roi)
+    loss.backward()
+    oloss, ograds = ps.paired_loss_and_grads(P, eeg, roi, None, 0.07, "lite")
+    assert_close_rel(loss, oloss, 1e-5, "loss")
+    named = dict(m.named_parameters())
+    for k, g in ograds.items():
+        assert_close_rel(named[k].grad, g, 2e-4, f"grad {k}", atol=1e-6)
+
+
 def test_trimodal_lite_and_fmri_modules_vs_golden(fakes):
     from conftest import load_golden
     from multimodal_eeg_fmri_b200 import modules
