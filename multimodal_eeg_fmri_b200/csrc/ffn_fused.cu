@@ -434,14 +434,19 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           twait<TRACE>(&bar.w_full[st], ph, tw);
           ptx::tc_fence_after_sync();
           const uint64_t da = dxa + (uint64_t)(kb * kTile16), db = dw0 + (uint64_t)(st * kTile16);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)
-            mma_ss_l(tH, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u, leader);
-          commit_l(&bar.w_empty[st], leader);
+            for (int k8 = 0; k8 < 4; ++k8)
+              ptx::mma_tf32_ss(tH, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+            ptx::mma_commit(&bar.w_empty[st]);
+            if (kb == 3) {
+              ptx::mma_commit(&bar.h_full[b]);
+              if (c == p.nc - 1) ptx::mma_commit(&bar.x_empty[xb]);
+            }
+          }
+          __syncwarp();
           if (++st == kFwdRing) { st = 0; ph ^= 1u; }
         }
-        commit_l(&bar.h_full[b], leader);
-        if (c == p.nc - 1) commit_l(&bar.x_empty[xb], leader);
         log(OP_M1, n, t0);
       };
       auto mma_m2 = [&](int n) {
@@ -459,13 +464,16 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           twait<TRACE>(&bar.w_full[st], ph, tw);
           ptx::tc_fence_after_sync();
           const uint64_t db = dw0 + (uint64_t)(st * kTile16);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)
-            mma_ts_l(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u), leader);
-          commit_l(&bar.w_empty[st], leader);
+            for (int k8 = 0; k8 < 4; ++k8)
+              mma_tf32_ts(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u));
+            ptx::mma_commit(&bar.w_empty[st]);
+            if (kb == 3 && c == p.nc - 1) ptx::mma_commit(&bar.y_full[b]);  // group b transformed this chunk and writes the tile
+          }
+          __syncwarp();
           if (++st == kFwdRing) { st = 0; ph ^= 1u; }
         }
-        if (c == p.nc - 1) commit_l(&bar.y_full[b], leader);  // group b transformed this chunk and writes the tile
         log(OP_M2, n, t0);
       };
       if (N > 0) mma_m1(0);
@@ -668,25 +676,30 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             twait<TRACE>(&bar.w_full[st], ph, tw);
             ptx::tc_fence_after_sync();
             const uint64_t db = dw0 + (uint64_t)(st * kTile16);
-            if (kind == OP_M4) {
+            if (ptx::elect_one()) {
+              if (kind == OP_M4) {
 #pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8)
-                mma_ts_l(tX, tG + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u), leader);
-            } else {
-              const uint64_t da = da0 + (uint64_t)(kb * kTile16);
+                for (int k8 = 0; k8 < 4; ++k8)
+                  mma_tf32_ts(tX, tG + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u));
+              } else {
+                const uint64_t da = da0 + (uint64_t)(kb * kTile16);
 #pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8)
-                mma_ss_l(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u, leader);
+                for (int k8 = 0; k8 < 4; ++k8)
+                  ptx::mma_tf32_ss(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+              }
+              ptx::mma_commit(&bar.w_empty[st]);
+              if (kb == 3) {
+                if (kind == OP_M3) {
+                  ptx::mma_commit(&bar.g_full);  // H_c (issued earlier) and G_c are complete
+                  if (c == p.nc - 1) ptx::mma_commit(&bar.in_empty);
+                }
+                if (kind == OP_M4 && c == p.nc - 1) ptx::mma_commit(&bar.x_done);
+              }
             }
-            commit_l(&bar.w_empty[st], leader);
+            __syncwarp();
             if (++st == kBwdRing) { st = 0; ph ^= 1u; }
           }
           const int n = it * p.nc + c;
-          if (kind == OP_M3) {
-            commit_l(&bar.g_full, leader);  // H_c (issued earlier) and G_c are complete
-            if (c == p.nc - 1) commit_l(&bar.in_empty, leader);
-          }
-          if (kind == OP_M4 && c == p.nc - 1) commit_l(&bar.x_done, leader);
           if (TRACE && blockIdx.x == 0 && lane == 0 && tn < 8192 - 6) {
             long long* t = p.trace + 8192 + tn;
             t[0] = kind; t[1] = n; t[2] = t0; t[3] = clock64(); t[4] = tw; t[5] = ta;
