@@ -62,7 +62,9 @@ int xm_window_index_i64(int64_t n_rec, int64_t n_samples, int64_t win, int64_t h
 /* Gather windows from rec (n_rec, C, n_samples):
  *   channels_last == 0: out (n_rec*n_win, C, ld_out >= win)   -- the reference's (C, T) sample layout
  *   channels_last != 0: out (n_rec*n_win, win, ld_out >= C)   -- the layout the conv GEMMs consume
- * round_tf32 != 0 rounds values to tf32 (removes the truncation bias of the first conv).
+ * round_tf32 == 1 rounds values to tf32 (removes the truncation bias of the first conv); round_tf32 == 2
+ * (channels_last only, ld_out >= 3*C) writes the 3-way tf32 split [hi | lo | hi] along the channel axis, the operand
+ * of a 3-pass (fp32-accurate) first conv.
  * With n_win == 1 (win == n_samples) this is the (B, C, T) -> (B, T, C) layout change. */
 int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
                          float* out, int64_t ld_out, int channels_last, int round_tf32, void* stream);
@@ -99,9 +101,11 @@ int xm_roi_meanstd_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float
  * ROI columns over TR, flattened row-major, after nan_to_num -- the `connectivity` input of fMRIFusionNet
  * (fMRI_CODE/fmri_utils.py:90-103; the reference reads such matrices from CSV, :161-198; SURVEY.md section 8d defines
  * the synthetic connectivity input this way).  fp32, 1e-5.  A constant column yields NaN in its row and column.
+ * split3 != 0: out is (3*B, ROI*ROI), the row-stacked tf32 split [hi; hi; lo] that xm_linear_fwd_stacked3_f32 and the
+ * weight gradient of the connectivity projection consume (what xm_split3_f32(which 1, axis 0) would make of it).
  * xm_roi_corrcoef_supported: the (TR, ROI) series of one sample fits shared memory. */
 int xm_roi_corrcoef_supported(int64_t TR, int64_t ROI);
-int xm_roi_corrcoef_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, void* stream);
+int xm_roi_corrcoef_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, int split3, void* stream);
 
 /* ------------------------------------------------------------------ dense projections (nn.Linear)
  * fMRI_CODE/fmri_utils.py:27,31,45,49,66 ; bridge_utils.py:35,41,61,65 ; enhanced_models_v4.py:164 */
@@ -170,7 +174,8 @@ int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double t
 /* out = drop(pool?(act(gamma*(y-mean)*invstd + beta))) ; pool: 0 none, 2 = MaxPool1d(2) over T
  * (out has B*(T/2) rows).  drop_p in [0,1): keep with prob 1-p, scale 1/(1-p); mask from
  * (seed, element index).  drop_before_pool selects Conv-BN-GELU-Drop-Pool (Lite) vs
- * Conv-BN-GELU-Pool-Drop (v4) ordering. */
+ * Conv-BN-GELU-Pool-Drop (v4) ordering.  round_out: 0 fp32, 1 rounded to tf32, 2 = the 3-way tf32 split [hi | lo | hi]
+ * along the channel axis (ldo >= 3*C), the operand of a following 3-pass conv. */
 int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
                       float* out, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo, int act, int pool,
                       float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream);

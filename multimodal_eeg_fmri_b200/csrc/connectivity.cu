@@ -24,8 +24,8 @@ XM_DEVICE float nan_to_num(float v) {  // fmri_utils.py:140 applies np.nan_to_nu
 
 // The matrix is symmetric: only the 8 x 4 blocks that touch the upper triangle are accumulated; a block writes its
 // elements (i, j >= i) row-wise and mirrors the strictly upper ones to (j, i).
-__global__ void __launch_bounds__(kThreads)
-corrcoef_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int TR, int ROI, int ROIp) {
+__global__ void __launch_bounds__(kThreads, 2)
+corrcoef_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int TR, int ROI, int ROIp, int split3) {
   extern __shared__ float sm[];
   float* xs = sm;                  // [TR][ROIp], columns >= ROI are zero
   float* inv = sm + TR * ROIp;     // [ROIp] 1 / sqrt(C_ii)
@@ -85,19 +85,59 @@ corrcoef_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
       }
+      // scale, clip, store.  Planes: 1 (plain) or 3 (row-stacked tf32 split [hi; hi; lo], see xm_roi_corrcoef_f32).
+      const long long plane = (long long)B * ROI * ROI;
+      const bool interior = j0 >= i0 + 8 && i0 + 8 <= ROI && j0 + 4 <= ROI && (ROI & 3) == 0;
+      float iv[8], jv[4];
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const int i = i0 + a;
-        if (i >= ROI) break;
-        const float ii = inv[i];
+      for (int a = 0; a < 8; ++a) iv[a] = i0 + a < ROIp ? inv[i0 + a] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) jv[c] = inv[j0 + c];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int j = j0 + c;
-          if (j >= ROI || j < i) continue;
-          float v = acc[a][c] * ii * inv[j];
-          v = v != v ? v : fminf(fmaxf(v, -1.0f), 1.0f);  // fminf / fmaxf alone would drop a NaN
-          ob[(long long)i * ROI + j] = v;
-          if (j > i) ob[(long long)j * ROI + i] = v;
+          const float v = acc[a][c] * iv[a] * jv[c];
+          acc[a][c] = v != v ? v : fminf(fmaxf(v, -1.0f), 1.0f);  // fminf / fmaxf alone would drop a NaN
+        }
+      if (interior) {
+        // strictly above the diagonal and inside the matrix: the block itself as 8 rows of 16 B, its mirror as 4 rows
+        // of 32 B (whole sectors), per plane
+        for (int pl = 0; pl < (split3 ? 3 : 1); ++pl) {
+          float* o = ob + pl * plane;
+          auto part = [&](float v) {  // this plane's share of a value
+            if (!split3) return v;
+            const float hi = round_tf32(v);
+            return pl < 2 ? hi : round_tf32(v - hi);
+          };
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+            *reinterpret_cast<float4*>(o + (long long)(i0 + a) * ROI + j0) =
+                make_float4(part(acc[a][0]), part(acc[a][1]), part(acc[a][2]), part(acc[a][3]));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4* m = reinterpret_cast<float4*>(o + (long long)(j0 + c) * ROI + i0);
+            m[0] = make_float4(part(acc[0][c]), part(acc[1][c]), part(acc[2][c]), part(acc[3][c]));
+            m[1] = make_float4(part(acc[4][c]), part(acc[5][c]), part(acc[6][c]), part(acc[7][c]));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int i = i0 + a;
+          if (i >= ROI) break;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = j0 + c;
+            if (j >= ROI || j < i) continue;
+            const float v = acc[a][c];
+            const float hi = round_tf32(v), lo = round_tf32(v - hi);
+            for (int pl = 0; pl < (split3 ? 3 : 1); ++pl) {
+              const float w = !split3 ? v : (pl < 2 ? hi : lo);
+              ob[pl * plane + (long long)i * ROI + j] = w;
+              if (j > i) ob[pl * plane + (long long)j * ROI + i] = w;
+            }
+          }
         }
       }
     }
@@ -115,7 +155,7 @@ extern "C" int xm_roi_corrcoef_supported(int64_t TR, int64_t ROI) {
   return TR >= 2 && ROI >= 1 && ROI <= 4096 && (TR * roip + roip) * 4 + roip * roip / 8 <= 220 * 1024;
 }
 
-extern "C" int xm_roi_corrcoef_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, void* stream) {
+extern "C" int xm_roi_corrcoef_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, int split3, void* stream) {
   if (!x || !out || B <= 0 || TR <= 0 || ROI <= 0) return XM_ERR_INVALID;
   if (!xm_roi_corrcoef_supported(TR, ROI)) return XM_ERR_UNSUPPORTED;
   const int roip = (int)((ROI + 3) / 4 * 4);
@@ -127,6 +167,6 @@ extern "C" int xm_roi_corrcoef_f32(const float* x, int64_t B, int64_t TR, int64_
   }
   const int per_sm = (int)(220 * 1024 / smem) < 1 ? 1 : (int)(220 * 1024 / smem);
   const int64_t grid = B < (int64_t)kNumSMs * per_sm ? B : (int64_t)kNumSMs * per_sm;
-  conn::corrcoef_kernel<<<(int)grid, conn::kThreads, smem, (cudaStream_t)stream>>>(x, out, (int)B, (int)TR, (int)ROI, roip);
+  conn::corrcoef_kernel<<<(int)grid, conn::kThreads, smem, (cudaStream_t)stream>>>(x, out, (int)B, (int)TR, (int)ROI, roip, split3);
   return check_launch();
 }

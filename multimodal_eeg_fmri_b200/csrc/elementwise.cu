@@ -215,7 +215,14 @@ __global__ void bn_act_fwd_kernel(const BnActArgs a, long long R_out, float* __r
     const int c = (int)(i - ro * a.C);
     const float sc = a.gamma[c] * a.invstd[c], sh = a.beta[c] - a.mean[c] * sc;
     const float o = bn_act_fwd_elem(a, ro, c, sc, sh);
-    out[ro * a.ldo + c] = a.round_out ? round_tf32(o) : o;
+    if (a.round_out == 2) {  // 3-way tf32 split along the channel axis [hi | lo | hi] (operand of a 3-pass conv)
+      const float hi = round_tf32(o);
+      out[ro * a.ldo + c] = hi;
+      out[ro * a.ldo + a.C + c] = round_tf32(o - hi);
+      out[ro * a.ldo + 2 * a.C + c] = hi;
+    } else {
+      out[ro * a.ldo + c] = a.round_out ? round_tf32(o) : o;
+    }
   }
 }
 
@@ -865,6 +872,19 @@ __global__ void bn_act_fwd_v4_kernel(const BnActArgs a, long long R_out, float* 
         o.v[j] = v;
       }
     }
+    if (a.round_out == 2) {  // 3-way tf32 split along the channel axis [hi | lo | hi]: operand of a 3-pass conv
+      F4 lo;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hi = round_tf32(o.v[j]);
+        lo.v[j] = round_tf32(o.v[j] - hi);
+        o.v[j] = hi;
+      }
+      st4(out + ro * a.ldo + c0, o);
+      st4(out + ro * a.ldo + a.C + c0, lo);
+      st4(out + ro * a.ldo + 2 * a.C + c0, o);
+      continue;
+    }
     if (a.round_out) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o.v[j] = round_tf32(o.v[j]);
@@ -1114,7 +1134,8 @@ int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double t
 int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
                       float* out, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo, int act, int pool,
                       float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream) {
-  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, T, C, ldy, pool, drop_p) || !out || ldo < C) return XM_ERR_INVALID;
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, T, C, ldy, pool, drop_p) || !out || ldo < (round_out == 2 ? 3 * C : C))
+    return XM_ERR_INVALID;
   BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);
   const long long R_out = B * (pool == 2 ? T / 2 : T);

@@ -38,7 +38,7 @@ def aggregate_roi_timeseries(x: torch.Tensor, agg_method: str = "both") -> torch
     return both
 
 
-def connectivity_from_timeseries(x: torch.Tensor) -> torch.Tensor:
+def connectivity_from_timeseries(x: torch.Tensor, prepared: bool = False) -> torch.Tensor:
     """x (B, TR, ROI) CUDA fp32 -> (B, ROI*ROI): the flattened ROI x ROI Pearson correlation matrix of every sample
     (numpy.corrcoef of the columns, NaN -> 0 first) -- fMRIFusionNet's `connectivity` input derived on the device
     from the same series the activation features come from, instead of a 4*ROI*ROI-byte row per sample crossing
@@ -48,7 +48,7 @@ def connectivity_from_timeseries(x: torch.Tensor) -> torch.Tensor:
     if x.shape[0] == 0 or x.shape[2] == 0:
         return torch.empty(x.shape[0], x.shape[2] * x.shape[2], device=x.device, dtype=torch.float32)
     from . import ops
-    return ops.roi_corrcoef(x)
+    return ops.roi_corrcoef(x, prepared)  # prepared: (3B, ROI*ROI) row-stacked tf32 split for the 3-pass projection
 
 
 # ------------------------------------------------------------------------- CSV loaders (fmri_utils.py:115-241)

@@ -118,17 +118,20 @@ class ToChannelsLast(torch.autograd.Function):
     """(B, C, T) reference layout -> (B, T, C) device layout, rounding to tf32 for the first conv."""
 
     @staticmethod
-    def forward(ctx, x, round_out):
-        return ops.to_nwc(x, round_out)
+    def forward(ctx, x, round_out, split3):
+        ctx.C = x.shape[1]
+        return ops.to_nwc(x, round_out, split3)
 
     @staticmethod
     def backward(ctx, g):
-        # the same transposing kernel maps a dense (B, T, C) gradient back to (B, C, T)
-        return ops.to_nwc(g.contiguous()), None
+        # the same transposing kernel maps a dense (B, T, C) gradient back to (B, C, T); of a channel-stacked split
+        # (B, T, 3C) only the first block carries the gradient (ConvBnAct.backward)
+        return ops.to_nwc(g[:, :, :ctx.C].contiguous()), None, None
 
 
-def to_channels_last(x, round_out=True):
-    return ToChannelsLast.apply(x, round_out)
+def to_channels_last(x, round_out=True, split3=False):
+    """split3: (B, T, 3C) channel-stacked tf32 split [hi | lo | hi], the input of a `precise` conv block."""
+    return ToChannelsLast.apply(x, round_out, split3)
 
 
 # ----------------------------------------------------------------------------- conv block
@@ -142,6 +145,7 @@ class ConvBnAct(torch.autograd.Function):
         eps, momentum, act, pool, p, dbp, training, round_out, precise = cfg
         Cout, Cin, taps = w.shape
         x = ops.as_nwc(x)
+        xin_cols = x.shape[2]
         wk, wt = ops.conv1d_pack_weight(w)
         if precise:
             # fp32-accurate forward on the tf32 tensor cores: x = xh + xl, w = wh + wl, y = xh wh + xl wh + xh wl as
@@ -156,16 +160,22 @@ class ConvBnAct(torch.autograd.Function):
         pd = p if training else 0.0
         out = ops.bn_act_fwd(y, mean, invstd, gamma, beta, act, pool, pd, seed, dbp, round_out)
         ctx.save_for_backward(x, y, wt, mean, invstd, gamma, beta)
-        ctx.meta = (Cin, taps, count, act, pool, pd, seed, dbp, training)
+        ctx.meta = (Cin, taps, count, act, pool, pd, seed, dbp, training, xin_cols)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, y, wt, mean, invstd, gamma, beta = ctx.saved_tensors
-        Cin, taps, count, act, pool, pd, seed, dbp, training = ctx.meta
-        dout = ops.as_nwc(dout)
+        Cin, taps, count, act, pool, pd, seed, dbp, training, xin_cols = ctx.meta
+        dout = ops.as_nwc(dout)  # may be 3 Cout wide (the block fed a precise conv): the kernels read the first Cout columns
         dy, dgamma, dbeta = _bn_backward(dout, y, mean, invstd, gamma, beta, count, act, pool, pd, seed, dbp, training, True)
-        dx = ops.conv1d_dgrad(dy, wt, Cin, round_out=True) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if xin_cols == Cin:
+                dx = ops.conv1d_dgrad(dy, wt, Cin, round_out=True)
+            else:  # the input was a channel-stacked split (B, T, 3 Cin): its gradient lives in the first block
+                dx = ops.empty_pitched((dy.shape[0], dy.shape[1], xin_cols), dy.device)
+                ops.conv1d_dgrad(dy, wt, Cin, round_out=True, out=dx[:, :, :Cin])
         # A bias in front of a train-mode BatchNorm has an exactly zero gradient (sum over the batch of the BN
         # input-gradient vanishes identically); the column reduction is only run when BN uses running stats.
         dw, db = ops.conv1d_wgrad(dy, x, taps, need_bias=not training)
@@ -192,10 +202,11 @@ CONV_PRECISE = os.environ.get("XM_CONV_PRECISE", "1") != "0"
 
 def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=False, training=True, round_out=True,
                 precise=False):
-    """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d).  `precise`: the input is
-    NOT tf32-rounded by its producer and the conv forward runs in the 3-pass mode (see ConvBnAct)."""
+    """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d).  `precise`: the conv forward
+    runs in the 3-pass mode (see ConvBnAct); its input is either NOT tf32-rounded by its producer or already the
+    channel-stacked split (B, T, 3 Cin).  round_out: False | True (tf32) | 2 (emit that split for a following precise conv)."""
     cfg = (bn.eps, _bn_momentum(bn, training), act, pool, float(drop_p), bool(drop_before_pool),
-           bool(training), bool(round_out), bool(precise))
+           bool(training), int(round_out), bool(precise))
     return ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
 
 
@@ -284,13 +295,15 @@ class LinearBnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, cfg):
-        eps, momentum, act, p, training = cfg
+        eps, momentum, act, p, training, prepared = cfg
         # 3-pass (fp32-accurate) projection (see _PRECISE_MAX_K for the single-pass escape hatch)
-        precise = x.shape[1] < _PRECISE_MAX_K
+        precise = prepared or x.shape[1] < _PRECISE_MAX_K
         if precise:
             # one row-stacked tf32 split of the input serves the forward AND the weight gradient (for the 40 000-d
-            # connectivity features that is a 2 GB write saved per step); it replaces x among the saved tensors
-            x = ops.linear_precise_prepare(x)
+            # connectivity features that is a 2 GB write saved per step); it replaces x among the saved tensors.
+            # `prepared`: the producer of x (the connectivity kernel) already wrote that split.
+            if not prepared:
+                x = ops.linear_precise_prepare(x)
             y = ops.linear_fwd_prepared(x, w, b)
         else:
             x, w = _tf32(x), _tf32(w)
@@ -322,8 +335,9 @@ class LinearBnAct(torch.autograd.Function):
         return dx, dw, db, dgamma, dbeta, None, None, None
 
 
-def linear_bn_act(x, lin, bn, act="relu", drop_p=0.0, training=True):
-    cfg = (bn.eps, _bn_momentum(bn, training), act, float(drop_p), bool(training))
+def linear_bn_act(x, lin, bn, act="relu", drop_p=0.0, training=True, prepared=False):
+    """prepared: x is the row-stacked tf32 split (3B, K) of the layer input (data, no gradient)."""
+    cfg = (bn.eps, _bn_momentum(bn, training), act, float(drop_p), bool(training), bool(prepared))
     return LinearBnAct.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
 
 

@@ -44,7 +44,7 @@ class _PreciseFirstConv:
     @property
     def wants_unrounded_input(self) -> bool:
         """True when the first conv runs in the 3-pass (fp32-accurate) mode: a channels-last input handed in by the
-        caller (e.g. the window gather) must then NOT be tf32-rounded."""
+        caller (e.g. the window gather) must then NOT be tf32-rounded -- or be the channel-stacked split (B, T, 3C)."""
         return XF.CONV_PRECISE
 
 
@@ -163,9 +163,9 @@ class EnhancedERPEncoder(_TransformerTail):
         """(B, C, T) [or (B, T, C) with channels_last=True, e.g. straight from the window gather] ->
         channels-last (B, T/2, hidden) output of the `conv_layers` Sequential."""
         c, p, tr = self.conv_layers, self.dropout_p, self.training
-        pr = XF.CONV_PRECISE  # fp32-accurate forward of the first two convs (their inputs then stay un-rounded)
-        h = x if channels_last else XF.to_channels_last(x, round_out=not pr)
-        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 0, p, False, tr, round_out=not pr, precise=pr)
+        pr = XF.CONV_PRECISE  # fp32-accurate forward of the first two convs: their producers emit the tf32 split
+        h = x if channels_last else XF.to_channels_last(x, round_out=not pr, split3=pr)
+        h = XF.conv_bn_act(h, c[0], c[1], "gelu", 0, p, False, tr, round_out=2 if pr else True, precise=pr)
         h = XF.conv_bn_act(h, c[4], c[5], "gelu", 2, p, False, tr, precise=pr)  # GELU -> MaxPool -> Dropout
         return XF.conv_bn_act(h, c[9], c[10], "gelu", 0, p, False, tr, round_out=False)
 
@@ -188,7 +188,7 @@ class EnhancedPowerEncoder(_TransformerTail):
 
     def conv_stack(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
         tr, pr = self.training, XF.CONV_PRECISE
-        h = x if channels_last else XF.to_channels_last(x, round_out=not pr)
+        h = x if channels_last else XF.to_channels_last(x, round_out=not pr, split3=pr)
         s = [XF.conv_bn_act(h, m[0], m[1], "gelu", 0, 0.0, False, tr, precise=pr)
              for m in (self.conv_scale1, self.conv_scale2, self.conv_scale3)]
         h = torch.cat(s, dim=2)  # channel concat in the channels-last layout
@@ -213,7 +213,7 @@ class _LiteEncoder(_PreciseFirstConv, nn.Module):
 
     def forward(self, x: torch.Tensor, channels_last: bool = False) -> torch.Tensor:
         c, p, tr, pr = self.conv_layers, self.dropout_p, self.training, XF.CONV_PRECISE
-        h = x if channels_last else XF.to_channels_last(x, round_out=not pr)
+        h = x if channels_last else XF.to_channels_last(x, round_out=not pr, split3=pr)
         h = XF.conv_bn_act(h, c[0], c[1], "gelu", 2, p, True, tr, precise=pr)  # Dropout BEFORE MaxPool here
         h = XF.conv_bn_act(h, c[5], c[6], "gelu", 0, p, False, tr, round_out=False)
         h = XF.seq_mean(h)
@@ -360,9 +360,10 @@ class _FmriEncoder(nn.Module):
         self.encoder = Slots({0: nn.Linear(in_dim, hidden_dim * 2), 1: nn.BatchNorm1d(hidden_dim * 2),
                               4: nn.Linear(hidden_dim * 2, hidden_dim), 5: nn.BatchNorm1d(hidden_dim)})
 
-    def forward(self, x):
+    def forward(self, x, prepared: bool = False):
+        """prepared: x is already the row-stacked tf32 split (3B, in_dim) of the features (ops.roi_corrcoef)."""
         e, p, tr = self.encoder, self.dropout_p, self.training
-        return XF.linear_bn_act(XF.linear_bn_act(x, e[0], e[1], "relu", p, tr), e[4], e[5], "relu", p, tr)
+        return XF.linear_bn_act(XF.linear_bn_act(x, e[0], e[1], "relu", p, tr, prepared=prepared), e[4], e[5], "relu", p, tr)
 
 
 class ActivationEncoder(_FmriEncoder):
@@ -388,10 +389,10 @@ class fMRIFusionNet(nn.Module):  # noqa: N801 - reference spelling
         out_dim = num_classes if task == "classification" else 1
         self.head = Slots({0: nn.Linear(hidden_dim, hidden_dim // 2), 3: nn.Linear(hidden_dim // 2, out_dim)})
 
-    def features(self, activation, connectivity):
+    def features(self, activation, connectivity, connectivity_prepared: bool = False):
         """The fused (B, hidden) feature of forward(..., return_features=True) without the head."""
         a = self.activation_encoder(activation)
-        c = self.connectivity_encoder(connectivity)
+        c = self.connectivity_encoder(connectivity, prepared=connectivity_prepared)
         w = torch.softmax(torch.stack([self.activation_weight, self.connectivity_weight]), dim=0)
         return XF.linear_bn_act(torch.cat([a * w[0], c * w[1]], dim=1), self.fusion[0], self.fusion[1], "relu",
                                 self.dropout_p, self.training)

@@ -138,9 +138,10 @@ def as_nwc(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def to_nwc(x: torch.Tensor, round_out: bool = False) -> torch.Tensor:
-    """(B, C, T) reference layout -> channels-last (B, T, C) (pitched), one transposing pass."""
-    return window_gather(x, x.shape[2], 1, channels_last=True, round_out=round_out)
+def to_nwc(x: torch.Tensor, round_out: bool = False, split3: bool = False) -> torch.Tensor:
+    """(B, C, T) reference layout -> channels-last (B, T, C) (pitched), one transposing pass; split3: (B, T, 3C), the
+    channel-stacked tf32 split [hi | lo | hi] (operand of a 3-pass first conv)."""
+    return window_gather(x, x.shape[2], 1, channels_last=True, round_out=round_out, split3=split3)
 
 
 # ------------------------------------------------------------------ linear
@@ -234,26 +235,30 @@ def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
 def conv1d_fwd_precise(x, w, bias):
     """fp32-accurate conv forward on the tf32 tensor cores: x (B, T, Cin) channels-last and NOT rounded, w (Cout, Cin,
     taps) in the reference layout.  x = xh + xl, w = wh + wl, y = xh wh + xl wh + xh wl as ONE conv over 3 Cin
-    stacked channels [xh | xl | xh] x [wh | wh | wl].  -> (y (B, T, Cout), xh view (B, T, Cin): the tf32-rounded
-    input, what a single-pass weight gradient reads)."""
+    stacked channels [xh | xl | xh] x [wh | wh | wl]; x may also BE that split already, (B, T, 3 Cin).
+    -> (y (B, T, Cout), xh view (B, T, Cin): the tf32-rounded input, what a single-pass weight gradient reads)."""
     _chk(x, w, bias)
     x = as_nwc(x)
-    B, T, Cin = x.shape
-    Cout, _, taps = w.shape
-    if x.stride(1) != Cin:
-        x = x.contiguous()
-    x3 = split3(x.view(B * T, Cin), 0, 1).view(B, T, 3 * Cin)
+    B, T, _ = x.shape
+    Cout, Cin, taps = w.shape
+    if x.shape[2] == 3 * Cin:  # the producer already wrote the channel-stacked split (window gather / BatchNorm block)
+        x3 = x
+    else:
+        if x.stride(1) != Cin:
+            x = x.contiguous()
+        x3 = split3(x.view(B * T, Cin), 0, 1).view(B, T, 3 * Cin)
     w3 = split3(w.reshape(Cout, Cin * taps), 1, 1).view(Cout, 3 * Cin, taps)
     wk3, _ = conv1d_pack_weight(w3)
     return conv1d_fwd(x3, wk3, bias, Cout), x3[:, :, :Cin]
 
 
-def conv1d_dgrad(dy, wt, Cin, round_out=False):
+def conv1d_dgrad(dy, wt, Cin, round_out=False, out=None):
+    """`out`: write dx into this (B, T, Cin) view of a wider buffer (row pitch = out.stride(1))."""
     _chk(dy, wt)
     dy = as_nwc(dy)
     B, T, Cout = dy.shape
     taps, _, ldt = wt.shape
-    dx = empty_pitched((B, T, Cin), dy.device)
+    dx = empty_pitched((B, T, Cin), dy.device) if out is None else out
     _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cin + Cout) + taps * Cin * Cout))
     _call("xm_conv1d_dgrad_f32", _p(dy), _p(wt), _p(dx), B, Cin, Cout, T, taps, dy.stride(1), ldt, dx.stride(1),
           int(round_out), _stream())
@@ -312,11 +317,12 @@ def bn_act_fwd(y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, dr
                round_out=False):
     _chk(y, mean, invstd, gamma, beta)
     B, T, C, ld = _bn_dims(y)
+    split = int(round_out) == 2  # (B, T', 3C): channel-stacked tf32 split [hi | lo | hi] for a following 3-pass conv
     if y.dim() == 2:
-        out = torch.empty(B, C, device=y.device, dtype=torch.float32)
-        ldo = C
+        out = torch.empty(B, 3 * C if split else C, device=y.device, dtype=torch.float32)
+        ldo = out.stride(0)
     else:
-        out = empty_pitched((B, T // 2 if pool == 2 else T, C), y.device)
+        out = empty_pitched((B, T // 2 if pool == 2 else T, 3 * C if split else C), y.device)
         ldo = out.stride(1)
     _w(20.0 * B * T * C, 4.0 * (B * T * C + out.numel()))
     _call("xm_bn_act_fwd_f32", _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(out), B, T, C, ld, ldo,
@@ -875,16 +881,22 @@ def window_index(n_rec, n_samples, win, hop, rec_labels=None, rec_subjects=None,
     return starts, rec_ids, labels, subjects
 
 
-def window_gather(rec, win, hop, channels_last=False, round_out=False):
-    """rec (R, C, n) -> (R*n_win, C, win) [reference layout] or (R*n_win, win, C) [channels-last]."""
+def window_gather(rec, win, hop, channels_last=False, round_out=False, split3=False):
+    """rec (R, C, n) -> (R*n_win, C, win) [reference layout] or (R*n_win, win, C) [channels-last]; with split3
+    (channels-last only) (R*n_win, win, 3C): the channel-stacked tf32 split [hi | lo | hi] of every window."""
     _chk(rec)
     rec = rec.contiguous()
     R, C, n = rec.shape
     n_win = (n - win) // hop + 1
-    out = empty_pitched((R * n_win, win, C) if channels_last else (R * n_win, C, win), rec.device)
-    _w(0.0, 8.0 * out.shape[0] * C * win)
+    if split3:
+        if not channels_last:
+            raise _lib.XmodalError("split3 needs the channels-last layout")
+        out = empty_pitched((R * n_win, win, 3 * C), rec.device)
+    else:
+        out = empty_pitched((R * n_win, win, C) if channels_last else (R * n_win, C, win), rec.device)
+    _w(0.0, 4.0 * out.shape[0] * C * win * (4 if split3 else 2))
     _call("xm_window_gather_f32", _p(rec), R, C, n, win, hop, _p(out), out.stride(1), int(channels_last),
-          int(round_out), _stream())
+          2 if split3 else int(round_out), _stream())
     return out
 
 
@@ -933,14 +945,17 @@ def roi_meanstd(x):
     return out
 
 
-def roi_corrcoef(x):
-    """x (B, TR, ROI) -> (B, ROI*ROI): flattened per-sample Pearson correlation matrix of the ROI columns over TR."""
+def roi_corrcoef(x, prepared=False):
+    """x (B, TR, ROI) -> (B, ROI*ROI): flattened per-sample Pearson correlation matrix of the ROI columns over TR.
+    prepared: (3B, ROI*ROI), the row-stacked tf32 split of that matrix (what linear_precise_prepare makes of it)."""
     _chk(x)
     x = x.contiguous()
     B, TR, ROI = x.shape
-    out = torch.empty(B, ROI * ROI, device=x.device, dtype=torch.float32)
+    if prepared and (ROI * ROI) % 4:
+        raise _lib.XmodalError("prepared connectivity needs ROI*ROI % 4 == 0")
+    out = torch.empty(3 * B if prepared else B, ROI * ROI, device=x.device, dtype=torch.float32)
     _w(2.0 * B * TR * ROI * ROI, 4.0 * (x.numel() + out.numel()))
-    _call("xm_roi_corrcoef_f32", _p(x), B, TR, ROI, _p(out), _stream())
+    _call("xm_roi_corrcoef_f32", _p(x), B, TR, ROI, _p(out), int(prepared), _stream())
     return out
 
 

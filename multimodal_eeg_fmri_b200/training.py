@@ -53,18 +53,21 @@ class PairedBridgeModel(nn.Module):
         ps = [p for m in mods for p in m.parameters()]
         return ps + [self.fmri_net.activation_weight, self.fmri_net.connectivity_weight]
 
-    # The fMRI branch is ~150 small launches (ROI aggregation, two MLP encoders in the 3-pass mode, fusion) that
-    # do not depend on the EEG encoder: on a side stream they fill the tails of the encoder's big kernels, in the
-    # forward and -- autograd replays every node on the stream of its forward -- in the backward.  Measured on
-    # B200: 36.17 -> 35.40 ms per step on 1 GPU, 37.85 -> 37.37 on 2 (SyncBN collectives issued from both streams
-    # keep their order; tests/dp_gpu_check.py passes).  Opt-in (XM_OVERLAP_BRANCHES=1): the gain is 1-2 % and
-    # the per-kernel CUDA-event rates that bench.py reports stop being those of a kernel running alone.
-    overlap_branches = os.environ.get("XM_OVERLAP_BRANCHES", "0") == "1"
+    # The fMRI branch (ROI aggregation, the connectivity kernel, two MLP encoders in the 3-pass mode, fusion: ~150 mostly
+    # small launches) does not depend on the EEG encoder: on a side stream it fills the tails of the encoder's big
+    # kernels, in the forward and -- autograd replays every node on the stream of its forward -- in the backward.
+    # Measured on B200 (profiles/r2_bench_overlap.txt): 36.27 -> 35.20 ms per step on 1 GPU; SyncBN collectives issued
+    # from both streams keep their order (tests/dp_gpu_check.py).  XM_OVERLAP_BRANCHES=0 serialises the branches
+    # (bench.py does so for its per-kernel CUDA-event pass, whose rates must be those of kernels running alone).
+    overlap_branches = os.environ.get("XM_OVERLAP_BRANCHES", "1") == "1"
 
     def _fmri_features(self, roi_series, conn):
         act = fmri_utils.aggregate_roi_timeseries(roi_series, "both")
-        if conn is None:  # functional connectivity derived on the device from the same ROI series
-            conn = fmri_utils.connectivity_from_timeseries(roi_series)
+        if conn is None:  # functional connectivity derived on the device from the same ROI series, written directly as
+            # the row-stacked tf32 split the 3-pass connectivity projection (and its weight gradient) consumes
+            prepared = (roi_series.shape[2] ** 2) % 4 == 0
+            conn = fmri_utils.connectivity_from_timeseries(roi_series, prepared=prepared)
+            return self.fmri_net.features(act, conn, connectivity_prepared=prepared)
         return self.fmri_net.features(act, conn)
 
     def embed(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None,
@@ -149,8 +152,9 @@ class PairedTrainer:
         from roi_series.  Returns the loss (device scalar, this rank's share of the global loss)."""
         self.flat_grad.zero_()
         if self.window is not None:
-            x = ops.window_gather(eeg, self.window, self.hop or self.window, channels_last=True,
-                                  round_out=not getattr(self.model.eeg_encoder, "wants_unrounded_input", False))
+            split = bool(getattr(self.model.eeg_encoder, "wants_unrounded_input", False))  # 3-pass first conv
+            x = ops.window_gather(eeg, self.window, self.hop or self.window, channels_last=True, round_out=not split,
+                                  split3=split)
             loss = self.model(x, roi_series, conn, eeg_channels_last=True)
         else:
             loss = self.model(eeg, roi_series, conn)

@@ -66,6 +66,8 @@ def assert_close_rel(a, b, tol, what="", atol=0.0):
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} != {tuple(b.shape)}"
     err = float((a - b).norm())
     bound = tol * float(b.norm()) + atol * (b.numel() ** 0.5)
+    if os.environ.get("XM_PRINT_ERRS"):  # tolerance audit: every comparison's measured error next to its bound
+        print(f"[err] {what}: rel {err / (float(b.norm()) + 1e-30):.3e} (tol {tol:.1e}, used {err / (bound + 1e-300):.2f} of the bound)")
     assert err <= bound, f"{what}: ||a-b|| = {err:.3e} > {bound:.3e} (rel {err / (float(b.norm()) + 1e-30):.3e}, tol {tol:.1e})"
 
 

@@ -31,14 +31,21 @@ def empty_pitched(shape, device):
     return torch.empty(*shape, device=device, dtype=torch.float32)
 
 
-def window_gather(rec, win, hop, channels_last=False, round_out=False):
+def _stack3(t):
+    """The fake's channel-stacked 'split' [hi | lo | hi] of an exact value: hi = the value, lo = 0."""
+    return torch.cat([t, torch.zeros_like(t), t], dim=-1).contiguous()
+
+
+def window_gather(rec, win, hop, channels_last=False, round_out=False, split3=False):
     R, C, n = rec.shape
     w = rec.unfold(2, win, hop).permute(0, 2, 1, 3).reshape(-1, C, win)  # (R*n_win, C, win)
-    return (w.transpose(1, 2) if channels_last else w).contiguous()
+    w = (w.transpose(1, 2) if channels_last else w).contiguous()
+    return _stack3(w) if split3 else w
 
 
-def to_nwc(x, round_out=False):
-    return x.transpose(1, 2).contiguous()
+def to_nwc(x, round_out=False, split3=False):
+    y = x.transpose(1, 2).contiguous()
+    return _stack3(y) if split3 else y
 
 
 # ---------------------------------------------------------------- linear
@@ -69,12 +76,18 @@ def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
 
 
 def conv1d_fwd_precise(x, w, bias):
+    if x.shape[2] == 3 * w.shape[1]:  # channel-stacked split from the producer
+        x = x[:, :, : w.shape[1]]
     return conv1d_fwd(x, w, bias, w.shape[0]), x
 
 
-def conv1d_dgrad(dy, wt, Cin, round_out=False):
+def conv1d_dgrad(dy, wt, Cin, round_out=False, out=None):
     dx = F.conv_transpose1d(dy.double().transpose(1, 2), wt.double(), padding=wt.shape[-1] // 2)
-    return dx.transpose(1, 2).float().contiguous()
+    dx = dx.transpose(1, 2).float().contiguous()
+    if out is not None:
+        out.copy_(dx)
+        return out
+    return dx
 
 
 @torch.enable_grad()
@@ -118,7 +131,8 @@ def _bn_formula(y, mean, invstd, gamma, beta, act, pool):
 def bn_act_fwd(y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, drop_before_pool=False, round_out=False):
     _nodrop(drop_p)
     _, a = _bn_formula(y.double(), mean.double(), invstd.double(), gamma.double(), beta.double(), act, pool)
-    return a.float().contiguous()
+    a = a.float().contiguous()
+    return _stack3(a) if int(round_out) == 2 else a
 
 
 @torch.enable_grad()
@@ -128,7 +142,7 @@ def _dz(dout, y, mean, invstd, gamma, beta, act, pool):
     if pool == 2:
         B, T, C = a.shape
         a = a[:, : T // 2 * 2].reshape(B, T // 2, 2, C).amax(2)
-    (dz,) = torch.autograd.grad(a, z0, dout.double())
+    (dz,) = torch.autograd.grad(a, z0, dout[..., : y.shape[-1]].double())  # a 3C-wide dout: gradient in the first block
     xhat = (y.double() - mean.double()) * invstd.double()
     return dz, xhat
 
@@ -418,7 +432,7 @@ def roi_meanstd(x):
     return torch.cat([xd.mean(1), xd.std(1, unbiased=False)], dim=1).float()
 
 
-def roi_corrcoef(x):
+def roi_corrcoef(x, prepared=False):  # the fake's "prepared" split is the identity (linear_precise_prepare above)
     xc = torch.nan_to_num(x.double())
     xc = xc - xc.mean(1, keepdim=True)
     c = xc.transpose(1, 2) @ xc

@@ -587,6 +587,28 @@ def test_roi_corrcoef(ops, B, TR, ROI):
         assert not torch.isnan(o[0]).any()
 
 
+# ------------------------------------------------------------------ producers that emit the tf32 split directly
+def test_producers_emit_the_tf32_split(ops):
+    """window gather, BatchNorm block and connectivity kernel can write the 3-way tf32 split of their output in place of
+    a separate xm_split3_f32 pass: bit-identical to splitting the plain output."""
+    torch.manual_seed(51)
+    rec = torch.randn(3, 20, 700, device="cuda")
+    plain = ops.window_gather(rec, 256, 128, channels_last=True)
+    got = ops.window_gather(rec, 256, 128, channels_last=True, split3=True)
+    G, W, C = plain.shape
+    assert got.shape == (G, W, 3 * C) and torch.equal(got.reshape(G * W, 3 * C), ops.split3(plain.reshape(G * W, C), 0, 1))
+    y = torch.randn(4, 50, 64, device="cuda")
+    mean, invstd = torch.randn(64, device="cuda") * 0.1, torch.rand(64, device="cuda") + 0.5
+    gamma, beta = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1
+    for pool in (0, 2):
+        o = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "gelu", pool)
+        o3 = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "gelu", pool, round_out=2)
+        assert torch.equal(o3.reshape(-1, 192), ops.split3(o.reshape(-1, 64), 0, 1))
+    x = torch.randn(5, 40, 12, device="cuda")
+    c = ops.roi_corrcoef(x)
+    assert torch.equal(ops.roi_corrcoef(x, prepared=True), ops.linear_precise_prepare(c))
+
+
 # ------------------------------------------------------------------ out-of-bounds canaries
 def test_ragged_outputs_do_not_write_past_their_extent(ops):
     """compute-sanitizer is closed on this pool, so ragged shapes are checked with canaries: outputs are
