@@ -63,11 +63,11 @@ class PairedBridgeModel(nn.Module):
 
     def _fmri_features(self, roi_series, conn):
         act = fmri_utils.aggregate_roi_timeseries(roi_series, "both")
-        if conn is None:  # functional connectivity derived on the device from the same ROI series, written directly as
-            # the row-stacked tf32 split the 3-pass connectivity projection (and its weight gradient) consumes
-            prepared = (roi_series.shape[2] ** 2) % 4 == 0
-            conn = fmri_utils.connectivity_from_timeseries(roi_series, prepared=prepared)
-            return self.fmri_net.features(act, conn, connectivity_prepared=prepared)
+        if conn is None:  # functional connectivity derived on the device from the same ROI series
+            # (the kernel can also write the row-stacked tf32 split the 3-pass projection consumes, `prepared=True`;
+            # measured on B200 that costs more than the separate split pass: 1.50 vs 0.79 + 0.51 ms, its mirrored
+            # stores then scatter over three planes -- tools/corr_bench.py)
+            conn = fmri_utils.connectivity_from_timeseries(roi_series)
         return self.fmri_net.features(act, conn)
 
     def embed(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None,

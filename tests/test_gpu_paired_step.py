@@ -1,7 +1,7 @@
 """The composite paired EEG/fMRI training step on a B200 against the CPU oracle
 (oracle/paired_step.py: pinned reference modules + authored InfoNCE), plus size-independent
-properties at the BASELINE batch sizes.  Tolerances: losses / features 1e-3 relative, gradients 3e-3
-(chains of tf32 contractions), InfoNCE reductions 1e-5 where stated."""
+properties at the BASELINE batch sizes.  Tolerances: losses, features and gradients 1e-3 relative (the north-star's
+bound for tf32 contractions; measured <= 8.8e-4, profiles/r2_tolerance_audit.txt), InfoNCE reductions 1e-5 where stated."""
 import math
 
 import pytest
@@ -41,8 +41,8 @@ def test_paired_loss_and_grads_small(encoder):
         assert named[k].grad is not None, k
         if k in zero:
             assert_zero_grad_noise(named[k].grad, named[k[: -len("bias")] + "weight"].grad, f"grad {k}")
-        else:  # 16-sample batch: BatchNorm statistics from 16 samples amplify the tf32 noise of deep chains
-            assert_close_rel(named[k].grad, g, 1.5e-2, f"grad {k}", atol=3e-5)
+        else:
+            assert_close_rel(named[k].grad, g, 1e-3, f"grad {k}", atol=3e-5)
     for k in set(named) - set(ograds):  # supervised heads are not reached by the contrastive loss
         assert named[k].grad is None, k
 
@@ -113,8 +113,8 @@ def test_infonce_gradient_matches_oracle_closed_form():
         lo = oi.symmetric_infonce(eo, fo, 0.07)
         lo.backward()
         assert_close_rel(loss, lo, 1e-3, f"loss B={B}")
-        assert_close_rel(eg.grad, eo.grad, 3e-3, f"de B={B}")
-        assert_close_rel(fg.grad, fo.grad, 3e-3, f"df B={B}")
+        assert_close_rel(eg.grad, eo.grad, 1e-3, f"de B={B}")
+        assert_close_rel(fg.grad, fo.grad, 1e-3, f"df B={B}")
 
 
 def test_paired_step_config3_shape_vs_oracle():
@@ -135,7 +135,7 @@ def test_paired_step_config3_shape_vs_oracle():
     named = dict(m.named_parameters())
     for k in ("eeg_encoder.conv_layers.0.weight", "eeg_encoder.conv_layers.5.weight", "bridge.eeg_proj.0.weight",
               "fmri_net.connectivity_encoder.encoder.0.weight", "fmri_net.activation_encoder.encoder.0.weight"):
-        assert_close_rel(named[k].grad, ograds[k], 1e-2, f"grad {k}", atol=1e-6)
+        assert_close_rel(named[k].grad, ograds[k], 1e-3, f"grad {k}", atol=1e-6)
 
 
 def test_baseline_shape_parity_every_gradient_within_1e3():
