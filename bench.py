@@ -364,6 +364,8 @@ def run_ours(args):
     # ---- timed region 2: end to end from pinned host buffers (H2D of the inputs + loss read back, every step)
     # (the public end-to-end call: copies batch k+1 from pinned host memory while batch k trains; every step's
     #  inputs cross PCIe inside the timed region and every step's loss is read back)
+    if args.e2e_steps <= 0:
+        args.e2e_steps = max(args.steps, 10)
     trainer.steps_from_host([host, host])
     ms_e2e = _timed(lambda: trainer.steps_from_host([host] * args.e2e_steps), 1, barrier, dev, world)
     e2e_value = world * B * args.e2e_steps / (ms_e2e * 1e-3)
@@ -494,7 +496,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (paired samples)")
     ap.add_argument("--encoder", default="v4", choices=["v4", "lite"])
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end region (0: max(--steps, 10))")
     ap.add_argument("--cpu-batch", type=int, default=0, help="paired samples per CPU-baseline step (0: the GPU arm's batch if host memory allows)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")

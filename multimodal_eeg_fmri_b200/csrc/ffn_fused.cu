@@ -44,10 +44,11 @@ constexpr int kD = 128, kChunk = 128, kMaxChunks = 8;
 constexpr int kTile = 16384;  // 128 rows x 32 fp32, SWIZZLE_128B
 constexpr int kXfWarps = 16;
 constexpr int kThreads = 64 + 32 * kXfWarps;
-constexpr int kFwdRing = 5, kBwdRing = 5;
+constexpr int kFwdRing = 5, kBwdRing = 9;
 constexpr int kBiasBytes = (kMaxChunks * kChunk + kD) * 4;  // b1 (+ b2) staged in shared memory
 constexpr int kFwdSmem = 2 * 4 * kTile + kFwdRing * kTile + kBiasBytes + 1024;
-constexpr int kBwdSmem = 2 * 4 * kTile + kBwdRing * kTile + kBiasBytes + 1024;
+constexpr int kStage = 4096;  // per-warp staging buffer of the data-gradient kernel: one 32 x 32 fp32 block
+constexpr int kBwdSmem = kBwdRing * kTile + kXfWarps * kStage + kBiasBytes + 1024;
 constexpr uint32_t kGold = 0x9E3779B1u;
 constexpr uint32_t kLcgA = 747796405u, kLcgC = 2891336453u;
 enum : int { OP_M1 = 0, OP_M2 = 1, OP_M3 = 2, OP_M4 = 3 };
@@ -66,6 +67,7 @@ struct Params {
   long long* trace;  // debug (xm_debug_set_ffn_trace): CTA 0 logs per-op clocks, 3 roles x 8192 slots
   int dbg;           // tracing instance only, timing experiments (results are then WRONG): bit 0 = the transform warps
                      // skip their arithmetic, bit 1 = the producer loads each ring stage once and only re-signals it
+                     // (forward), bit 2 = the data-gradient kernel does not store A / dH
 };
 
 // mbarrier wait that, in the tracing instance of a kernel, adds the cycles it spent to `acc`
@@ -101,42 +103,10 @@ XM_DEVICE void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, ui
 }
 
 // The MMA warp runs its schedule WARP-UNIFORMLY (all 32 lanes wait on the barriers and compute the operand
-// descriptors, which the compiler can then keep in uniform registers); only the instructions that must come from a
-// single thread are predicated on `leader`.  With the schedule inside `if (lane == 0)` every descriptor went through
-// vector registers and R2UR moves: ~125 cycles of issue per MMA, more than the MMA itself takes (profiles/
-// r2_ffn_trace_v2.json).
-XM_DEVICE void mma_ss_l(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
-}
-XM_DEVICE void mma_ts_l(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
-}
-XM_DEVICE void commit_l(uint64_t* bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}\n" ::"r"(ptx::smem_u32(bar)),
-      "r"(leader)
-      : "memory");
-}
+// descriptors, which the compiler then keeps in uniform registers) and issues each k-block's four MMAs + commit from
+// an `elect_one` branch: in SASS the four UTCHMMA follow each other without an instruction in between.  With the
+// whole schedule inside `if (lane == 0)` every descriptor went through vector registers and R2UR moves, ~125 cycles
+// of issue per MMA against 76 for the MMA itself (profiles/r2_ffn_trace_v2.json, profiles/r2_mma_rate_probe.txt).
 constexpr uint32_t kTile16 = kTile >> 4;  // descriptor start-address units (16 B) per 16 KB tile
 
 // The per-tile MMA schedule, written once into shared memory (kind << 8 | chunk).
@@ -290,6 +260,23 @@ XM_DEVICE void store_row32(float* dst, const uint32_t (&r)[32]) {
                  : "memory");
 }
 
+// 32 x 32 fp32 block of this warp (one row per lane) -> the warp's 4 KB swizzled staging buffer -> one asynchronous
+// TMA store (rows / columns outside the tensor are clipped).  The warp only waits until the PREVIOUS store has read
+// the buffer out of shared memory, never for the global write.
+XM_DEVICE void stage_block(const CUtensorMap* tm, uint8_t* sb, int lane, const uint32_t (&r)[32], int col, int row0) {
+  if (lane == 0) ptx::bulk_wait_read<0>();
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_3d(tm, sb, col, row0, 0);
+    ptx::bulk_commit();
+  }
+}
+
 struct FwdBars {
   uint64_t x_full[2], x_empty[2];
   uint64_t w_full[kFwdRing], w_empty[kFwdRing];
@@ -406,7 +393,6 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else if (warp == 1) {
     {
-      const uint32_t leader = lane == 0 ? 1u : 0u;
       const uint32_t idesc = ptx::make_idesc_tf32(128, 128, 0, 0);
       const uint64_t dx0 = ptx::make_smem_desc(ptx::smem_u32(xs), 16, 1024, 2);    // x tile 0, k-block 0
       const uint64_t dw0 = ptx::make_smem_desc(ptx::smem_u32(ring), 16, 1024, 2);  // ring stage 0
@@ -557,7 +543,6 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 struct BwdBars {
-  uint64_t in_full, in_empty;
   uint64_t w_full[kBwdRing], w_empty[kBwdRing];
   uint64_t g_full, d_ready;
   uint64_t x_done, xacc_free;
@@ -569,7 +554,8 @@ template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2t,
-                 const __grid_constant__ CUtensorMap tmW1t, float* __restrict__ out_a, float* __restrict__ out_dh, const Params p) {
+                 const __grid_constant__ CUtensorMap tmW1t, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmDH, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ BwdBars bar;
   __shared__ uint32_t tmem_slot;
@@ -578,19 +564,23 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t raw = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint8_t* xs = smem;                       // [4] x k-block tiles (K = input features)
-  uint8_t* ys = smem + 4 * kTile;           // [4] dY k-block tiles (K = output features)
-  uint8_t* ring = smem + 8 * kTile;         // [kBwdRing] weight k-block tiles
-  float* sb1 = reinterpret_cast<float*>(ring + kBwdRing * kTile);
+  // Shared memory: NO operand tile is resident.  The x and dY k-blocks are streamed through the ring in front of the
+  // W1 / W2t k-blocks they are multiplied with (each is re-read from L2 once per chunk: +384 KB per tile), which
+  // leaves room for a 9-slot ring and one 4 KB staging buffer per transform warp, from which the A / dH blocks leave
+  // as asynchronous TMA stores.  Stores issued from registers (st.global) blocked the transform warps and slowed the
+  // concurrent MMAs: 0.78 of 2.1 ms (profiles/r2_ffn_dgrad_experiments.txt).
+  uint8_t* ring = smem;                     // [kBwdRing] 16 KB slots
+  uint8_t* staging = ring + kBwdRing * kTile;
+  float* sb1 = reinterpret_cast<float*>(staging + kXfWarps * kStage);
   for (int i = threadIdx.x; i < p.hidden; i += blockDim.x) sb1[i] = p.b1[i];
   if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmDH);
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmDY);
     ptx::prefetch_tensormap(&tmW1);
     ptx::prefetch_tensormap(&tmW2t);
     ptx::prefetch_tensormap(&tmW1t);
-    ptx::mbar_init(&bar.in_full, 1);
-    ptx::mbar_init(&bar.in_empty, 1);
     for (int i = 0; i < kBwdRing; ++i) {
       ptx::mbar_init(&bar.w_full[i], 1);
       ptx::mbar_init(&bar.w_empty[i], 1);
@@ -617,35 +607,33 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
       int it = 0;
+      auto slot = [&](const CUtensorMap* tm, int c0, int c1) {  // one 16 KB k-block tile into the next ring slot
+        ptx::mbar_wait(&bar.w_empty[st], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
+        ptx::tma_load_3d(tm, &bar.w_full[st], ring + st * kTile, c0, c1, 0);
+        if (++st == kBwdRing) { st = 0; ph ^= 1u; }
+      };
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        ptx::mbar_wait(&bar.in_empty, ((uint32_t)it & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(&bar.in_full, 8 * kTile);
-        for (int kb = 0; kb < 4; ++kb) {
-          ptx::tma_load_3d(&tmX, &bar.in_full, xs + kb * kTile, kb * 32, tile * 128, 0);
-          ptx::tma_load_3d(&tmDY, &bar.in_full, ys + kb * kTile, kb * 32, tile * 128, 0);
-        }
         for (int op = 0; op < n_ops; ++op) {
           const int kind = ops[op] >> 8, c = ops[op] & 255;
           for (int kb = 0; kb < 4; ++kb) {
-            ptx::mbar_wait(&bar.w_empty[st], ph ^ 1u);
-            ptx::mbar_arrive_expect_tx(&bar.w_full[st], kTile);
-            if (kind == OP_M1)
-              ptx::tma_load_3d(&tmW1, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);   // W1[128c.., in 32kb..]
-            else if (kind == OP_M3)
-              ptx::tma_load_3d(&tmW2t, &bar.w_full[st], ring + st * kTile, kb * 32, c * kChunk, 0);  // W2t[128c.., out 32kb..]
-            else
-              ptx::tma_load_3d(&tmW1t, &bar.w_full[st], ring + st * kTile, c * kChunk + kb * 32, 0, 0);  // W1t[:, 128c + 32kb..]
-            if (++st == kBwdRing) { st = 0; ph ^= 1u; }
+            if (kind == OP_M1) {
+              slot(&tmX, kb * 32, tile * 128);          // x[tile rows, in 32kb..]
+              slot(&tmW1, kb * 32, c * kChunk);         // W1[128c.., in 32kb..]
+            } else if (kind == OP_M3) {
+              slot(&tmDY, kb * 32, tile * 128);         // dY[tile rows, out 32kb..]
+              slot(&tmW2t, kb * 32, c * kChunk);        // W2t[128c.., out 32kb..]
+            } else {
+              slot(&tmW1t, c * kChunk + kb * 32, 0);    // W1t[:, 128c + 32kb..]
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     {
-      const uint32_t leader = lane == 0 ? 1u : 0u;  // warp-uniform schedule, single-thread issue (see mma_ss_l)
+      // warp-uniform schedule, single-thread issue from elect_one branches (see the note above build_fwd_ops)
       const uint32_t idesc = ptx::make_idesc_tf32(128, 128, 0, 0);
-      const uint64_t dx0 = ptx::make_smem_desc(ptx::smem_u32(xs), 16, 1024, 2);
-      const uint64_t dy0 = ptx::make_smem_desc(ptx::smem_u32(ys), 16, 1024, 2);
       const uint64_t dw0 = ptx::make_smem_desc(ptx::smem_u32(ring), 16, 1024, 2);
       uint32_t st = 0, ph = 0, cu = 0;  // cu: chunks whose M4 has been issued
       long long tw = 0, ta = 0;
@@ -656,12 +644,8 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const long long t0 = TRACE ? clock64() : 0;
           const int kind = ops[op] >> 8, c = ops[op] & 255;
           const uint32_t tH = tmem + (uint32_t)((c & 1) * 128);
-          if (kind == OP_M1 && c == 0) {
-            twait<TRACE>(&bar.in_full, (uint32_t)it & 1u, ta);
-            ptx::tc_fence_after_sync();
-          }
           if (kind == OP_M4) {
-            twait<TRACE>(&bar.d_ready, cu & 1u, ta);  // a transform group has read H_c, G_c and written dH_c over G_c
+            twait<TRACE>(&bar.d_ready, cu & 1u, ta);  // the transform warps have read H_c, G_c and written dH_c over G_c
             ++cu;
             ptx::tc_fence_after_sync();
             if (c == 0) {
@@ -669,10 +653,14 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               ptx::tc_fence_after_sync();
             }
           }
-          const uint64_t da0 = kind == OP_M1 ? dx0 : dy0;
-          const uint32_t acc = kind == OP_M1 ? tH : tG;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
+            uint32_t sa = 0;  // M1 / M3: the slot holding the x / dY k-block, followed by the slot of the weight k-block
+            if (kind != OP_M4) {
+              twait<TRACE>(&bar.w_full[st], ph, tw);
+              sa = st;
+              if (++st == kBwdRing) { st = 0; ph ^= 1u; }
+            }
             twait<TRACE>(&bar.w_full[st], ph, tw);
             ptx::tc_fence_after_sync();
             const uint64_t db = dw0 + (uint64_t)(st * kTile16);
@@ -682,17 +670,16 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 for (int k8 = 0; k8 < 4; ++k8)
                   mma_tf32_ts(tX, tG + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u));
               } else {
-                const uint64_t da = da0 + (uint64_t)(kb * kTile16);
+                const uint64_t da = dw0 + (uint64_t)(sa * kTile16);
+                const uint32_t acc = kind == OP_M1 ? tH : tG;
 #pragma unroll
                 for (int k8 = 0; k8 < 4; ++k8)
                   ptx::mma_tf32_ss(acc, da + (uint64_t)(k8 * 2), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : 0u);
+                ptx::mma_commit(&bar.w_empty[sa]);
               }
               ptx::mma_commit(&bar.w_empty[st]);
               if (kb == 3) {
-                if (kind == OP_M3) {
-                  ptx::mma_commit(&bar.g_full);  // H_c (issued earlier) and G_c are complete
-                  if (c == p.nc - 1) ptx::mma_commit(&bar.in_empty);
-                }
+                if (kind == OP_M3) ptx::mma_commit(&bar.g_full);  // H_c (issued earlier) and G_c are complete
                 if (kind == OP_M4 && c == p.nc - 1) ptx::mma_commit(&bar.x_done);
               }
             }
@@ -717,6 +704,7 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int part = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float cs = kTruncComp * p.dscale;
+    uint8_t* sb = staging + (warp - 2) * kStage;
     uint32_t cu = 0;
     int tn = 0;
     int it = 0;
@@ -734,7 +722,8 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         ptx::tmem_ld_32x32(tG + (uint32_t)col0 + lane_base, rd);
         ptx::tmem_ld_wait();
         const float* bias = sb1 + c * kChunk + col0;
-        if (p.thr)
+        if (TRACE && (p.dbg & 1)) {
+        } else if (p.thr)
           bwd_transform<true>(ra, rd, bias, p.act, cs, p.thr, group_seed(rs, (c * kChunk + col0) >> 5));
         else
           bwd_transform<false>(ra, rd, bias, p.act, cs, 0u, 0u);
@@ -745,9 +734,9 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(&bar.d_ready);
         const long long t2 = TRACE ? clock64() : 0;
         const int col = c * kChunk + col0;
-        if (row < p.M) {
-          store_row32(out_a + row * p.hidden + col, ra);
-          store_row32(out_dh + row * p.hidden + col, rd);
+        if (!(TRACE && (p.dbg & 4))) {
+          stage_block(&tmA, sb, lane, ra, col, tile * 128 + q * 32);   // rows >= M are clipped by the TMA unit
+          stage_block(&tmDH, sb, lane, rd, col, tile * 128 + q * 32);
         }
         const float csum = warp_column_sums(rd, lane) * (1.0f / kTruncComp);  // rows >= M carry dY = 0, hence dH = 0
         if (p.db1_part != nullptr) p.db1_part[((long long)tile * 4 + q) * p.hidden + col + lane] = csum;
@@ -770,6 +759,7 @@ ffn_dgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (row < p.M) store_row32(p.dx + row * kD + part * 32, r);
       }
     }
+    if (lane == 0) ptx::bulk_wait_all();  // staged blocks fully written before the CTA (and its shared memory) retires
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -888,24 +878,27 @@ int xm_ffn_fused_dgrad_f32(const float* x, const float* dy, const float* w1, con
   p.b1 = b1;
   p.dx = dx;
   p.db1_part = db1_part;
-  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(dh) | reinterpret_cast<uintptr_t>(dx)) & 31) return XM_ERR_INVALID;
-  CUtensorMap mx, my, m1, m2t, m1t;
+  if (reinterpret_cast<uintptr_t>(dx) & 31) return XM_ERR_INVALID;
+  CUtensorMap mx, my, m1, m2t, m1t, ma, mdh;
   rc = encode_tmap(&mx, ffn::view2(x, D, M), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&my, ffn::view2(dy, D, M), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m1, ffn::view2(w1, D, hidden), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m2t, ffn::view2(w2t, D, hidden), 32, 128, 0);
   if (rc == XM_OK) rc = encode_tmap(&m1t, ffn::view2(w1t, hidden, D), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&ma, ffn::view2(a, hidden, M), 32, 32, 0);
+  if (rc == XM_OK) rc = encode_tmap(&mdh, ffn::view2(dh, hidden, M), 32, 32, 0);
   const int ctas = p.tiles < kNumSMs ? p.tiles : kNumSMs;
   if (g_ffn_trace != nullptr) {
     p.trace = g_ffn_trace;
+    p.dbg = g_ffn_dbg;
     if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_dgrad_kernel<true>, ffn::kBwdSmem);
     if (rc != XM_OK) return rc;
-    ffn::ffn_dgrad_kernel<true><<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, a, dh, p);
+    ffn::ffn_dgrad_kernel<true><<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, ma, mdh, p);
     return check_launch();
   }
   if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_dgrad_kernel<false>, ffn::kBwdSmem);
   if (rc != XM_OK) return rc;
-  ffn::ffn_dgrad_kernel<false><<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, a, dh, p);
+  ffn::ffn_dgrad_kernel<false><<<ctas, ffn::kThreads, ffn::kBwdSmem, (cudaStream_t)stream>>>(mx, my, m1, m2t, m1t, ma, mdh, p);
   return check_launch();
 }
 
