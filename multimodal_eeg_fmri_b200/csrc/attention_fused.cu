@@ -238,10 +238,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // Warp-uniform schedule: all 32 lanes wait on the barriers and form the descriptors (which then live in uniform
+      // registers); each group of MMAs and its commits issue from one `elect_one` branch, back to back in SASS.  With
+      // the schedule inside `if (lane == 0)` every MMA paid an R2UR move and an ELECT loop (~125 clk of issue against
+      // ~80 for an N = 32 MMA, profiles/r2_mma_rate_probe.txt).
       const uint32_t idesc_s = ptx::make_idesc_tf32(128, 128, 0, 0);
       const uint32_t idesc_o = ptx::make_idesc_tf32(128, 32, 0, 1);
       const uint64_t dq = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, 2);
+      const uint64_t dring = ptx::make_smem_desc(ptx::smem_u32(ring), 16, 1024, 2);
+      const uint64_t dvring = ptx::make_smem_desc(ptx::smem_u32(ring) + 16384, 4096, 512, 1);
       int it = 0, hs = 0, tn = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
         const int s = two_sets ? (it & 1) : 0;
@@ -253,13 +259,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::mbar_wait(&bar.hfull[st], ((uint32_t)hs >> 1) & 1u);
           FA_TRACE(0, tn);
           ptx::tc_fence_after_sync();
-          const uint32_t ya = ptx::smem_u32(ring + st * kFwdHalf);
-          const uint64_t dk = ptx::make_smem_desc(ya, 16, 1024, 2);
-          const uint64_t dv = ptx::make_smem_desc(ya + 16384, 4096, 512, 1);
+          const uint64_t dk = dring + (uint64_t)(st * (kFwdHalf >> 4));
+          const uint64_t dv = dvring + (uint64_t)(st * (kFwdHalf >> 4));
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) ptx::mma_tf32_ss(tS, dq + (uint64_t)(k8 * 2), dk + (uint64_t)(k8 * 2), idesc_s, k8 > 0);
-          ptx::mma_commit(&bar.s_full);
-          if (hf == NH - 1) ptx::mma_commit(&bar.empty);  // the q tile is not read again: prefetch the next item's
+            for (int k8 = 0; k8 < 4; ++k8) ptx::mma_tf32_ss(tS, dq + (uint64_t)(k8 * 2), dk + (uint64_t)(k8 * 2), idesc_s, k8 > 0);
+            ptx::mma_commit(&bar.s_full);
+            if (hf == NH - 1) ptx::mma_commit(&bar.empty);  // the q tile is not read again: prefetch the next item's
+          }
+          __syncwarp();
           FA_TRACE(0, tn);
           ptx::mbar_wait(&bar.p_ready, (uint32_t)hs & 1u);
           FA_TRACE(0, tn);
@@ -267,10 +275,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ptx::tc_fence_after_sync();
           const int nk = min(16, (p.L - hf * 128 + 7) >> 3);  // K = 8 slabs with a valid key
           const uint32_t acc = tO + (uint32_t)(s * 64 + hf * 32);
-          for (int k8 = 0; k8 < nk; ++k8) mma_tf32_ts(acc, tS + (uint32_t)(k8 * 8), dv + (uint64_t)(k8 * 64), idesc_o, k8 > 0);
-          ptx::mma_commit(&bar.hempty[st]);
+          if (ptx::elect_one()) {
+            if (nk == 16) {
+#pragma unroll
+              for (int k8 = 0; k8 < 16; ++k8) mma_tf32_ts(acc, tS + (uint32_t)(k8 * 8), dv + (uint64_t)(k8 * 64), idesc_o, k8 > 0);
+            } else {
+              for (int k8 = 0; k8 < nk; ++k8) mma_tf32_ts(acc, tS + (uint32_t)(k8 * 8), dv + (uint64_t)(k8 * 64), idesc_o, k8 > 0);
+            }
+            ptx::mma_commit(&bar.hempty[st]);
+            if (hf == NH - 1) ptx::mma_commit(&bar.o_full[s]);
+          }
+          __syncwarp();
         }
-        ptx::mma_commit(&bar.o_full[s]);
       }
     }
   } else {
@@ -484,12 +500,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // warp-uniform schedule, MMAs issued from elect_one branches (see the forward kernel's issuer)
       const uint32_t idesc_s = ptx::make_idesc_tf32(128, 64, 0, 0);
       const uint32_t idesc_o = ptx::make_idesc_tf32(128, 32, 0, 1);
       const uint32_t xa = ptx::smem_u32(smem);
       const uint64_t dx0 = ptx::make_smem_desc(xa, 16, 1024, 2);
       const uint64_t dx1 = ptx::make_smem_desc(xa + 16384, 16, 1024, 2);
+      const uint32_t ra = ptx::smem_u32(ring);
+      const uint64_t dr0 = ptx::make_smem_desc(ra, 16, 1024, 2);
+      const uint64_t dr1 = ptx::make_smem_desc(ra + 8192, 16, 1024, 2);
+      const uint64_t drm0 = ptx::make_smem_desc(ra + 16384, 4096, 512, 1);
+      const uint64_t drm1 = ptx::make_smem_desc(ra + 24576, 4096, 512, 1);
       int it = 0, hs = 0, tn = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
         const int s = it & 1;
@@ -502,39 +524,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           ptx::mbar_wait(&bar.hfull[st], ((uint32_t)hs >> 1) & 1u);
           FA_TRACE(0, tn);
           ptx::tc_fence_after_sync();
-          const uint32_t ya = ptx::smem_u32(ring + st * C::kChunkBytes);
-          const uint64_t dy0 = ptx::make_smem_desc(ya, 16, 1024, 2);
-          const uint64_t dy1 = ptx::make_smem_desc(ya + 8192, 16, 1024, 2);
+          const uint64_t so = (uint64_t)(st * (C::kChunkBytes >> 4));
+          const uint64_t dy0 = dr0 + so, dy1 = dr1 + so;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)  // S (or S^T): lane-side tile 0 times chunk tile 0
-            ptx::mma_tf32_ss(tS, dx0 + (uint64_t)(k8 * 2), dy0 + (uint64_t)(k8 * 2), idesc_s, k8 > 0);
+            for (int k8 = 0; k8 < 4; ++k8)  // S (or S^T): lane-side tile 0 times chunk tile 0
+              ptx::mma_tf32_ss(tS, dx0 + (uint64_t)(k8 * 2), dy0 + (uint64_t)(k8 * 2), idesc_s, k8 > 0);
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)  // dP~ (or its transpose): lane-side tile 1 times chunk tile 1
-            ptx::mma_tf32_ss(tP, dx1 + (uint64_t)(k8 * 2), dy1 + (uint64_t)(k8 * 2), idesc_s, k8 > 0);
-          ptx::mma_commit(&bar.s_full);
-          if (cc == NC - 1) ptx::mma_commit(&bar.empty);  // the item tiles are not read again: prefetch the next item's
+            for (int k8 = 0; k8 < 4; ++k8)  // dP~ (or its transpose): lane-side tile 1 times chunk tile 1
+              ptx::mma_tf32_ss(tP, dx1 + (uint64_t)(k8 * 2), dy1 + (uint64_t)(k8 * 2), idesc_s, k8 > 0);
+            ptx::mma_commit(&bar.s_full);
+            if (cc == NC - 1) ptx::mma_commit(&bar.empty);  // the item tiles are not read again: prefetch the next item's
+          }
+          __syncwarp();
           FA_TRACE(0, tn);
           ptx::mbar_wait(&bar.p_ready, (uint32_t)hs & 1u);
           FA_TRACE(0, tn);
           if (cc == 0) ptx::mbar_wait(&bar.o_empty[s], (((uint32_t)it >> 1) & 1u) ^ 1u);
           ptx::tc_fence_after_sync();
-          const uint64_t dm0 = ptx::make_smem_desc(ya + 16384, 4096, 512, 1);
-          if (KV) {
-            const uint64_t dm1 = ptx::make_smem_desc(ya + 24576, 4096, 512, 1);
+          const uint64_t dm0 = drm0 + so, dm1 = drm1 + so;
+          const uint32_t acc0 = cc > 0 ? 1u : 0u;
+          if (ptx::elect_one()) {
+            if (KV) {
 #pragma unroll
-            for (int k8 = 0; k8 < 8; ++k8)  // dv += P~^T dO
-              mma_tf32_ts(out + 32, tS + (uint32_t)(k8 * 8), dm0 + (uint64_t)(k8 * 64), idesc_o, (cc > 0 || k8 > 0));
+              for (int k8 = 0; k8 < 8; ++k8)  // dv += P~^T dO
+                mma_tf32_ts(out + 32, tS + (uint32_t)(k8 * 8), dm0 + (uint64_t)(k8 * 64), idesc_o, k8 > 0 ? 1u : acc0);
 #pragma unroll
-            for (int k8 = 0; k8 < 8; ++k8)  // dk += dS^T q
-              mma_tf32_ts(out, tP + (uint32_t)(k8 * 8), dm1 + (uint64_t)(k8 * 64), idesc_o, (cc > 0 || k8 > 0));
-          } else {
+              for (int k8 = 0; k8 < 8; ++k8)  // dk += dS^T q
+                mma_tf32_ts(out, tP + (uint32_t)(k8 * 8), dm1 + (uint64_t)(k8 * 64), idesc_o, k8 > 0 ? 1u : acc0);
+            } else {
 #pragma unroll
-            for (int k8 = 0; k8 < 8; ++k8)  // dq += dS k
-              mma_tf32_ts(out, tS + (uint32_t)(k8 * 8), dm0 + (uint64_t)(k8 * 64), idesc_o, (cc > 0 || k8 > 0));
+              for (int k8 = 0; k8 < 8; ++k8)  // dq += dS k
+                mma_tf32_ts(out, tS + (uint32_t)(k8 * 8), dm0 + (uint64_t)(k8 * 64), idesc_o, k8 > 0 ? 1u : acc0);
+            }
+            ptx::mma_commit(&bar.hempty[st]);
+            if (cc == NC - 1) ptx::mma_commit(&bar.o_full[s]);
           }
-          ptx::mma_commit(&bar.hempty[st]);
+          __syncwarp();
         }
-        ptx::mma_commit(&bar.o_full[s]);
       }
     }
   } else {

@@ -163,8 +163,12 @@ bandpower_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // warp-uniform schedule; each k-block's twelve MMAs and two commits issue from one elect_one branch, back to back
+      // in SASS (inside `if (lane == 0)` every MMA paid an R2UR move and an ELECT loop, profiles/r2_mma_rate_probe.txt)
       const uint32_t idesc = ptx::make_idesc_tf32(128, 64, 0, 0);
+      const uint64_t dh0 = ptx::make_smem_desc(ptx::smem_u32(smem) + 16384, 16, 1024, 2);
+      const uint64_t dl0 = ptx::make_smem_desc(ptx::smem_u32(smem) + 24576, 16, 1024, 2);
       int s = 0;
       uint32_t ph = 0;
       uint32_t kbg = 0;  // k-blocks issued so far (lo buffer = kbg & 1)
@@ -178,27 +182,30 @@ bandpower_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t acc = tmem + (uint32_t)(chunk * 64);
           ptx::mbar_wait(&bar.full[s], ph);
           ptx::tc_fence_after_sync();
-          const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes);
-          const uint64_t dh = ptx::make_smem_desc(sa + 16384, 16, 1024, 2);
-          const uint64_t dl = ptx::make_smem_desc(sa + 24576, 16, 1024, 2);
+          const uint64_t dh = dh0 + (uint64_t)((uint32_t)s * (uint32_t)(kStageBytes >> 4));
+          const uint64_t dl = dl0 + (uint64_t)((uint32_t)s * (uint32_t)(kStageBytes >> 4));
           const uint32_t lb = kbg & 1u;
           ptx::mbar_wait(&bar.lo_ready[lb], (kbg >> 1) & 1u);  // hi and lo of this block are in tensor memory
           ptx::tc_fence_after_sync();
           const uint32_t th = tOp + lb * 64u, tl = th + 32u;
+          const uint32_t acc0 = first ? 0u : 1u;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)  // hi * Thi
-            mma_tf32_ts(acc, th + (uint32_t)(k8 * 8), dh + (uint64_t)(k8 * 2), idesc, (first && k8 == 0) ? 0u : 1u);
+            for (int k8 = 0; k8 < 4; ++k8)  // hi * Thi
+              mma_tf32_ts(acc, th + (uint32_t)(k8 * 8), dh + (uint64_t)(k8 * 2), idesc, k8 == 0 ? acc0 : 1u);
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)  // hi * Tlo
-            mma_tf32_ts(acc, th + (uint32_t)(k8 * 8), dl + (uint64_t)(k8 * 2), idesc, 1u);
+            for (int k8 = 0; k8 < 4; ++k8)  // hi * Tlo
+              mma_tf32_ts(acc, th + (uint32_t)(k8 * 8), dl + (uint64_t)(k8 * 2), idesc, 1u);
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8)  // lo * Thi
-            mma_tf32_ts(acc, tl + (uint32_t)(k8 * 8), dh + (uint64_t)(k8 * 2), idesc, 1u);
-          ptx::mma_commit(&bar.empty[s]);
-          ptx::mma_commit(&bar.lo_free[lb]);
+            for (int k8 = 0; k8 < 4; ++k8)  // lo * Thi
+              mma_tf32_ts(acc, tl + (uint32_t)(k8 * 8), dh + (uint64_t)(k8 * 2), idesc, 1u);
+            ptx::mma_commit(&bar.empty[s]);
+            ptx::mma_commit(&bar.lo_free[lb]);
+            if (kb == p.KB - 1) ptx::mma_commit(&bar.acc_full);
+          }
+          __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
-        ptx::mma_commit(&bar.acc_full);
       }
     }
   } else {

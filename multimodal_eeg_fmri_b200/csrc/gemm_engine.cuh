@@ -276,8 +276,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------ MMA issuer
+      // The schedule runs warp-uniformly (all lanes wait on the barriers and form the descriptors, which the compiler
+      // keeps in uniform registers); the MMAs and commits of a k-block issue from one `elect_one` branch.  Inside
+      // `if (lane == 0)` every MMA paid an R2UR move and an ELECT loop (profiles/r2_mma_rate_probe.txt).
       const uint32_t idesc = ptx::make_idesc_tf32(128, p.bn, p.a.mn_major, p.b.mn_major);
       const uint32_t a_kstep = p.a.mn_major ? 1024u : 32u;  // bytes per K=8 slab
       const uint32_t b_kstep = p.b.mn_major ? 1024u : 32u;
@@ -313,7 +316,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int kb0 = 0;  // first k-block of the running accumulation
         for (int kb = 0; kb < total_kb; ++kb) {
           if (p.acc_chunk > 0 && kb - kb0 == p.acc_chunk) {  // hand this chunk over, continue in the other set
-            ptx::mma_commit(&tmem_full_bar[buf]);
+            if (ptx::elect_one()) ptx::mma_commit(&tmem_full_bar[buf]);
+            __syncwarp();
             buf = ait & 1;
             use = (uint32_t)(ait >> 1);
             ++ait;
@@ -326,46 +330,58 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::tc_fence_after_sync();
           const uint64_t das = da0 + (uint64_t)((uint32_t)s * stage16);
           const uint64_t dbs = db0 + (uint64_t)((uint32_t)s * stage16);
+          const bool last_kb = kb == total_kb - 1;
           if (p.a_halo) {  // taps inside the stage: A = halo slab shifted by whole rows (128 B), B = tap tile
-            for (int tp = 0; tp < p.taps_k; ++tp) {
-              const uint64_t dat = das + (uint64_t)((uint32_t)(p.a_tap_row0 + tp * p.a_tap_dir) * 8u);
-              const uint64_t dbt = dbs + (uint64_t)((uint32_t)tp * ((uint32_t)b_tile_bytes >> 4));
+            if (ptx::elect_one()) {
+              for (int tp = 0; tp < p.taps_k; ++tp) {
+                const uint64_t dat = das + (uint64_t)((uint32_t)(p.a_tap_row0 + tp * p.a_tap_dir) * 8u);
+                const uint64_t dbt = dbs + (uint64_t)((uint32_t)tp * ((uint32_t)b_tile_bytes >> 4));
 #pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8)
-                ptx::mma_tf32_ss(acc, dat + (uint64_t)(k8 * a_k16), dbt + (uint64_t)(k8 * b_k16), idesc,
-                                 (kb > 0 || tp > 0 || k8 > 0) ? 1u : 0u);
+                for (int k8 = 0; k8 < 4; ++k8)
+                  ptx::mma_tf32_ss(acc, dat + (uint64_t)(k8 * a_k16), dbt + (uint64_t)(k8 * b_k16), idesc,
+                                   (kb > 0 || tp > 0 || k8 > 0) ? 1u : 0u);
+              }
+              ptx::mma_commit(&empty_bar[s]);
+              if (last_kb) ptx::mma_commit(&tmem_full_bar[buf]);  // accumulator complete
             }
-            ptx::mma_commit(&empty_bar[s]);
+            __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
             continue;
           }
-          if (p.b_halo) {
-            // Halo tile: the taps are 128-B (one k-row) shifts of the same 32-wide block, so ONE MMA per
-            // block covers all taps at once -- its N dimension walks taps_n "blocks" that are 128 B apart
-            // (leading-dimension byte offset = 128).  N = 32*taps instead of bn per MMA: 3.5x fewer reads of
-            // the A tile from shared memory, which is what bounded the small-N tap-by-tap MMAs.
-            const int nblk = p.bn >> 5;
-            for (int cb = 0; cb < nblk; ++cb) {
-              const uint64_t dbc = dbs + (uint64_t)((uint32_t)cb * ((uint32_t)p.b_blk_bytes >> 4));
-              const uint32_t acc_c = acc + (uint32_t)(cb * p.taps_n * 32);
+          if (ptx::elect_one()) {
+            if (p.b_halo) {
+              // Halo tile: the taps are 128-B (one k-row) shifts of the same 32-wide block, so ONE MMA per
+              // block covers all taps at once -- its N dimension walks taps_n "blocks" that are 128 B apart
+              // (leading-dimension byte offset = 128).  N = 32*taps instead of bn per MMA: 3.5x fewer reads of
+              // the A tile from shared memory, which is what bounded the small-N tap-by-tap MMAs.
+              const int nblk = p.bn >> 5;
+              for (int cb = 0; cb < nblk; ++cb) {
+                const uint64_t dbc = dbs + (uint64_t)((uint32_t)cb * ((uint32_t)p.b_blk_bytes >> 4));
+                const uint32_t acc_c = acc + (uint32_t)(cb * p.taps_n * 32);
+#pragma unroll
+                for (int k8 = 0; k8 < 4; ++k8)
+                  ptx::mma_tf32_ss(acc_c, das + (uint64_t)(k8 * a_k16), dbc + (uint64_t)(k8 * b_k16), idesc_halo,
+                                   (kb > 0 || k8 > 0) ? 1u : 0u);
+              }
+            } else
+            for (int tn = 0; tn < p.taps_n; ++tn) {
+              const uint64_t dbt = dbs + (uint64_t)((uint32_t)tn * b_tap16);
+              const uint32_t acc_t = acc + (uint32_t)(tn * p.bn);
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8)
-                ptx::mma_tf32_ss(acc_c, das + (uint64_t)(k8 * a_k16), dbc + (uint64_t)(k8 * b_k16), idesc_halo,
-                                 (kb > 0 || k8 > 0) ? 1u : 0u);
+                ptx::mma_tf32_ss(acc_t, das + (uint64_t)(k8 * a_k16), dbt + (uint64_t)(k8 * b_k16), idesc,
+                                 (kb > kb0 || k8 > 0) ? 1u : 0u);
             }
-          } else
-          for (int tn = 0; tn < p.taps_n; ++tn) {
-            const uint64_t dbt = dbs + (uint64_t)((uint32_t)tn * b_tap16);
-            const uint32_t acc_t = acc + (uint32_t)(tn * p.bn);
-#pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8)
-              ptx::mma_tf32_ss(acc_t, das + (uint64_t)(k8 * a_k16), dbt + (uint64_t)(k8 * b_k16), idesc,
-                               (kb > kb0 || k8 > 0) ? 1u : 0u);
+            ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+            if (last_kb) ptx::mma_commit(&tmem_full_bar[buf]);  // accumulator complete
           }
-          ptx::mma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        ptx::mma_commit(&tmem_full_bar[buf]);  // accumulator complete
+        if (total_kb == 0) {  // nothing to accumulate (cannot happen for a launched tile; keeps the hand-off complete)
+          if (ptx::elect_one()) ptx::mma_commit(&tmem_full_bar[buf]);
+          __syncwarp();
+        }
       }
     }
   } else {
