@@ -270,6 +270,23 @@ int xm_infonce_grad_f32(const float* a, const float* b, const float* lse_row, co
  * (the rows of G sum to ~0, so this product cancels heavily: single-pass tf32 is not enough).  Ng % 4 == 0. */
 int xm_infonce_dgrad_f32(const float* g3, const float* f3, float* dx, int64_t Ml, int64_t Ng, int64_t D, void* stream);
 
+/* Fused backward of the symmetric InfoNCE loss (csrc/infonce_fused.cu): both softmax-gradient blocks of
+ * xm_infonce_grad_f32 are formed tile by tile in tensor memory and contracted in place,
+ *   de (Ml, D) = G1 f_n,  G1 = coef * (exp(S - lse_ef[i]) + exp(S - lse_fe_all[j]) - 2 [j == i + diag_off]),  S = e_n f_n^T * inv_tau
+ *   df (Ml, D) = G2 e_n,  G2 = the same with e and f exchanged (lse_fe[i], lse_ef_all[j]),
+ * without writing anything of size (Ml, Ng).  e3 / f3 (Ml, 3D): this rank's xm_l2norm_split_fwd_f32 splits (which = 0 / 1),
+ * e3_all / f3_all (Ng, 3D): the splits of the global batch (all ranks' rows, this rank's at row diag_off).
+ * precise != 0: G is split hi/lo on the fly and the contraction runs in the 3-pass mode (fp32-accurate, as
+ * xm_infonce_dgrad_f32); 0: one tf32 pass.  The sum over the global batch is accumulated in fp32 registers per
+ * 128-column chunk.  D == 128, Ml % 128 == Ng % 128 == diag_off % 128 == 0 (xm_infonce_bwd_fused_supported).
+ * workspace: xm_infonce_bwd_fused_workspace(Ng, D) floats, 32-B aligned (column scales + the transposed unit vectors). */
+int xm_infonce_bwd_fused_supported(int64_t Ml, int64_t Ng, int64_t D, int64_t diag_off);
+int64_t xm_infonce_bwd_fused_workspace(int64_t Ng, int64_t D);
+int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_all, const float* f3_all, const float* lse_ef,
+                             const float* lse_fe, const float* lse_ef_all, const float* lse_fe_all, float* de, float* df,
+                             int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef, int precise,
+                             float* workspace, void* stream);
+
 /* Fused all-gather + contraction over NVLink peer memory (data-parallel global negatives).  The second
  * operand is ROW-SHARDED: rank r holds rows [r*rows_per_peer, (r+1)*rows_per_peer) in its own buffer and
  * b_peers[r] (a HOST array of n_peers <= 8 device pointers) is that buffer mapped into this process

@@ -285,6 +285,7 @@ def act_dropout(x, act, drop_p=0.0, training=True):
 _PRECISE_MAX_K = 1 << 30
 _FUSED_FFN = os.environ.get("XM_FUSED_FFN", "1") != "0"  # A/B switch: 0 = the unfused linear / act / linear chain
 _INFONCE_PRECISE_DGRAD = {"0": False, "1": True}.get(os.environ.get("XM_INFONCE_PRECISE_DGRAD", ""), None)
+_FUSED_INFONCE_BWD = os.environ.get("XM_FUSED_INFONCE_BWD", "1") != "0"  # A/B switch: 0 = grad -> split -> dgrad chain
 
 
 class LinearBnAct(torch.autograd.Function):
@@ -736,6 +737,11 @@ class SymmetricInfoNCE(torch.autograd.Function):
                 dfn = ops.linear_dgrad_peers(G2, e_ptrs, Bl, D, 3 * D)
         else:
             e3_all, f3_all = sv[8], sv[9]
+            if _FUSED_INFONCE_BWD and ops.infonce_bwd_fused_supported(e3.shape[0], Ng_all, D, off):
+                # both (local x global) gradient blocks are formed and contracted in tensor memory, never written
+                den, dfn = ops.infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef, lse_fe, lse_ef_all, lse_fe_all, inv_tau,
+                                                 off, coef, prec)
+                return ops.l2norm_bwd(den, en, einv) * g, ops.l2norm_bwd(dfn, fn, finv) * g, None
             G1 = ops.infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, off, coef, not prec)
             G2 = ops.infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, off, coef, not prec)
             if not prec:  # the first D columns of a split are the tf32-rounded unit vectors

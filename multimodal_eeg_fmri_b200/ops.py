@@ -868,6 +868,29 @@ def infonce_dgrad(G, f3, which_f):
     return dx
 
 
+def infonce_bwd_fused_supported(Ml, Ng, D, diag_off):
+    return bool(_lib.lib().xm_infonce_bwd_fused_supported(int(Ml), int(Ng), int(D), int(diag_off)))
+
+
+def infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef, lse_fe, lse_ef_all, lse_fe_all, inv_tau, diag_off, coef, precise=True):
+    """-> (de, df) (Ml, D): the InfoNCE gradients with respect to this rank's unit embeddings, both softmax-gradient
+    blocks formed and contracted on chip (xm_infonce_bwd_fused_f32).  e3 / f3: local l2norm splits (which 0 / 1),
+    e3_all / f3_all: the global batch's."""
+    _chk(e3, f3, e3_all, f3_all, lse_ef, lse_fe, lse_ef_all, lse_fe_all)
+    e3, f3, e3_all, f3_all = e3.contiguous(), f3.contiguous(), e3_all.contiguous(), f3_all.contiguous()
+    Ml, D = e3.shape[0], e3.shape[1] // 3
+    Ng = e3_all.shape[0]
+    de = torch.empty(Ml, D, device=e3.device, dtype=torch.float32)
+    df = torch.empty(Ml, D, device=e3.device, dtype=torch.float32)
+    ws = torch.empty(int(_lib.lib().xm_infonce_bwd_fused_workspace(Ng, D)), device=e3.device, dtype=torch.float32)
+    passes = 6.0 if precise else 4.0  # 3 score passes + 3 / 1 contraction passes, two directions
+    _w(2.0 * passes * 2.0 * Ml * Ng * D, 4.0 * (2 * 3 * Ml * D + 2 * 3 * Ng * D + 2 * 2 * Ng * D + 2 * Ml * D))
+    _call("xm_infonce_bwd_fused_f32", _p(e3), _p(f3), _p(e3_all), _p(f3_all), _p(lse_ef.contiguous()), _p(lse_fe.contiguous()),
+          _p(lse_ef_all.contiguous()), _p(lse_fe_all.contiguous()), _p(de), _p(df), Ml, Ng, D, float(inv_tau), int(diag_off),
+          float(coef), int(bool(precise)), _p(ws), _stream())
+    return de, df
+
+
 # ------------------------------------------------------------------ preprocessing
 def window_index(n_rec, n_samples, win, hop, rec_labels=None, rec_subjects=None, device="cuda"):
     n_win = (n_samples - win) // hop + 1

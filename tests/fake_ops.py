@@ -286,6 +286,17 @@ def infonce_grad(a, b, lse_row, lse_col, inv_tau, diag_off, coef, round_out=Fals
     return (G * coef).float()
 
 
+def infonce_bwd_fused_supported(Ml, Ng, D, diag_off):
+    return D == 128 and Ml % 128 == 0 and Ng % 128 == 0 and diag_off % 128 == 0 and diag_off + Ml <= Ng
+
+
+def infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef, lse_fe, lse_ef_all, lse_fe_all, inv_tau, diag_off, coef, precise=True):
+    D = e3.shape[1] // 3
+    G1 = infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, diag_off, coef)
+    G2 = infonce_grad(f3, e3_all, lse_fe, lse_ef_all, inv_tau, diag_off, coef)
+    return (G1.double() @ f3_all[:, :D].double()).float(), (G2.double() @ e3_all[:, :D].double()).float()
+
+
 # ---------------------------------------------------------------- attention core
 def attn_supported(L, dh):
     return dh == 32 and 0 < L <= 512

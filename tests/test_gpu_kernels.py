@@ -174,6 +174,38 @@ def test_infonce_kernels(ops, Ml, Ng, D, off):
     assert_close_rel(ops.l2norm_bwd(d, en, einv), gx, 5e-4, "l2norm bwd")
 
 
+@pytest.mark.parametrize("Ml,Ng,off,precise", [(128, 128, 0, True), (256, 256, 0, True), (256, 1024, 512, True),
+                                                (4096, 4096, 0, True), (512, 2560, 1024, False), (4096, 4096, 0, False),
+                                                (384, 9088, 384, False)])
+def test_infonce_bwd_fused(ops, Ml, Ng, off, precise):
+    """de = G1 f_n, df = G2 e_n with both gradient blocks formed in tensor memory: against fp64, and the precise mode at
+    the accuracy of the unfused 3-pass chain (rows of G sum to ~0: the products cancel against the common component)."""
+    torch.manual_seed(11)
+    D, it = 128, 1 / 0.07
+    e_all = torch.randn(Ng, D, device="cuda") + 0.7
+    f_all = e_all * 0.5 + torch.randn(Ng, D, device="cuda") + 0.4
+    en_all, e3_all, _ = ops.l2norm_split_fwd(e_all, 0)
+    fn_all, f3_all, _ = ops.l2norm_split_fwd(f_all, 1)
+    e3, f3 = e3_all[off:off + Ml].contiguous(), f3_all[off:off + Ml].contiguous()
+    assert ops.infonce_bwd_fused_supported(Ml, Ng, D, off)
+    S = en_all.double() @ fn_all.double().t() * it  # (e rows, f rows) of the global batch
+    lse_ef_all, lse_fe_all = torch.logsumexp(S, 1), torch.logsumexp(S, 0)
+    coef = 0.5 * it / Ng
+    idx = torch.arange(Ml, device="cuda")
+    Sl = S[off:off + Ml]                       # my e x all f
+    G1 = torch.exp(Sl - lse_ef_all[off:off + Ml, None]) + torch.exp(Sl - lse_fe_all[None, :])
+    G1[idx, idx + off] -= 2
+    St = S[:, off:off + Ml].t()                # my f x all e
+    G2 = torch.exp(St - lse_fe_all[off:off + Ml, None]) + torch.exp(St - lse_ef_all[None, :])
+    G2[idx, idx + off] -= 2
+    de_ref, df_ref = coef * G1 @ fn_all.double(), coef * G2 @ en_all.double()
+    de, df = ops.infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef_all[off:off + Ml].float(), lse_fe_all[off:off + Ml].float(),
+                                   lse_ef_all.float(), lse_fe_all.float(), it, off, coef, precise)
+    tol = 2e-5 if precise else TF32
+    assert_close_rel(de, de_ref, tol, "fused infonce de", atol=1e-9)
+    assert_close_rel(df, df_ref, tol, "fused infonce df", atol=1e-9)
+
+
 # ------------------------------------------------------------------ windowing + band power
 @pytest.mark.parametrize("R,C,n,win,hop,nfft,fs", [
     (2, 4, 3000, 1024, 512, 1024, 1000.0), (3, 8, 2000, 500, 250, 512, 250.0), (1, 3, 1001, 100, 37, 128, 128.0),
