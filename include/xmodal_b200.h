@@ -281,6 +281,13 @@ int xm_infonce_dgrad_f32(const float* g3, const float* f3, float* dx, int64_t Ml
  * 128-column chunk.  D == 128, Ml % 128 == Ng % 128 == diag_off % 128 == 0 (xm_infonce_bwd_fused_supported).
  * workspace: xm_infonce_bwd_fused_workspace(Ng, D) floats, 32-B aligned (column scales + the transposed unit vectors). */
 int xm_infonce_bwd_fused_supported(int64_t Ml, int64_t Ng, int64_t D, int64_t diag_off);
+/* Forward of the same kernel family: lse_ef[i] = logsumexp_j S[i, j] (my e x all f), lse_fe[i] = logsumexp_j S'[i, j] (my f x
+ * all e), diag[i] = S[i, i + diag_off], scores in the 3-pass mode, nothing of size (Ml, Ng) written; same shape rules.
+ * workspace: xm_infonce_lse_fused_workspace(Ml, Ng) floats (per-thread partial sums, combined in a fixed order). */
+int64_t xm_infonce_lse_fused_workspace(int64_t Ml, int64_t Ng);
+int xm_infonce_lse_fused_f32(const float* e3, const float* f3, const float* e3_all, const float* f3_all, float* lse_ef,
+                             float* lse_fe, float* diag, int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off,
+                             float* workspace, void* stream);
 int64_t xm_infonce_bwd_fused_workspace(int64_t Ng, int64_t D);
 int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_all, const float* f3_all, const float* lse_ef,
                              const float* lse_fe, const float* lse_ef_all, const float* lse_fe_all, float* de, float* df,

@@ -21,6 +21,10 @@
 //          accumulation keeps the sum over the global batch fp32-accurate, as GemmParams::acc_chunk does for the
 //          unfused product); the running sums are written at the end of the unit (red.add when a row tile is split).
 // MMA order  M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | ...   TMEM: S0 [0,128) S1 [128,256) L [256,384) X [384,512).
+//
+// The forward (xm_infonce_lse_fused_f32) is the same kernel without M2 / D: T(j) adds exp(S_ij - 1/tau) of its columns
+// to a per-thread row sum (|S| <= 1/tau for unit vectors: no running maximum needed) and picks up the positive S_ii;
+// the per-thread partial sums go to a workspace and are combined in a fixed order (deterministic).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -52,7 +56,13 @@ struct Params {
   int atomic;   // a row tile is split over several units: outputs are zeroed and accumulated with red.add
   float c;      // log2(e) / tau
   float scale;  // coef (x truncation compensation in the single-pass mode)
+  // forward (MODE_LSE) only
+  float* partial[2];  // (Ml, slots) partial sums of exp(S - 1/tau): slot = (column split * 2 + transform group) * 2 + column half
+  float* diag;        // (Ml) S[i, i + diag_off]
+  int slots;
+  float inv_tau;
 };
+enum : int { MODE_SINGLE = 0, MODE_PRECISE = 1, MODE_LSE = 2 };
 
 struct Bars {
   uint64_t a_full, a_empty;
@@ -63,7 +73,7 @@ struct Bars {
 
 // Position in the CTA's chunk sequence: unit ordinal k (unit = blockIdx.x + k * gridDim.x), running index n.
 struct Cursor {
-  int k, n, c, c0, c1, dir, row0;
+  int k, n, c, c0, c1, dir, row0, sp;
   bool ok;
 };
 XM_DEVICE void cur_load(Cursor& cu, const Params& p) {
@@ -73,6 +83,7 @@ XM_DEVICE void cur_load(Cursor& cu, const Params& p) {
   cu.dir = u & 1;
   const int rest = u >> 1, sp = rest / p.row_tiles;
   cu.row0 = (rest - sp * p.row_tiles) * 128;
+  cu.sp = sp;
   cu.c0 = sp * p.cps;
   cu.c1 = min(p.nc, cu.c0 + p.cps);
   cu.c = cu.c0;
@@ -121,11 +132,12 @@ XM_DEVICE void store_row32(float* dst, const float (&r)[32]) {
                  : "memory");
 }
 
-template <bool PRECISE>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-nce_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+nce_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, const Params p) {
+  constexpr bool PRECISE = MODE == MODE_PRECISE, LSE = MODE == MODE_LSE;
   extern __shared__ uint8_t smem_raw[];
   __shared__ Bars bar;
   __shared__ uint32_t tmem_slot;
@@ -203,7 +215,7 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           cur_next(c1, p);
         }
       while (c2.ok) {
-        load_m2(c2);
+        if (!LSE) load_m2(c2);
         cur_next(c2, p);
         if (c1.ok) {
           load_m1(c1);
@@ -225,6 +237,10 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         ptx::tc_fence_after_sync();
       }
       const bool last = cu.c == cu.c1 - 1;
+      if (LSE) {  // no M2 in front of this product: the transform warps have read chunk n - 2 out of this S buffer
+        ptx::mbar_wait(&bar.a_ready[b], (((uint32_t)cu.n >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after_sync();
+      }
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {  // b_hi k-blocks: a_hi b_hi^T + a_lo b_hi^T
         ptx::mbar_wait(&bar.w_full[st], ph);
@@ -316,7 +332,7 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         cur_next(c1, p);
       }
     while (c2.ok) {
-      mma_m2(c2);
+      if (!LSE) mma_m2(c2);
       cur_next(c2, p);
       if (c1.ok) {
         mma_m1(c1);
@@ -330,6 +346,57 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int sub = pidx & 1;          // which 64 of the chunk's 128 columns this warp transforms
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int rit = q * 32 + lane;     // row inside the tile
+    if (LSE) {
+      // forward: row sums of exp(S - 1/tau) over this warp's 64 columns of its group's chunks
+      const float cmax = p.inv_tau * kLog2e;
+      float acc = 0.f;
+      int acc_k = -1, acc_dir = 0, acc_row = 0, acc_sp = 0;
+      auto flush = [&]() {
+        if (acc_k >= 0) p.partial[acc_dir][(long long)acc_row * p.slots + (acc_sp * 2 + g) * 2 + sub] = acc;
+      };
+      Cursor cu;
+      cur_init(cu, p);
+      for (; cu.ok; cur_next(cu, p)) {
+        if (((uint32_t)cu.n & 1u) != (uint32_t)g) continue;
+        if (acc_k != cu.k) {
+          flush();
+          acc = 0.f;
+          acc_k = cu.k;
+          acc_dir = cu.dir;
+          acc_row = cu.row0 + rit;
+          acc_sp = cu.sp;
+        }
+        ptx::mbar_wait(&bar.s_full[g], ((uint32_t)cu.n >> 1) & 1u);
+        ptx::tc_fence_after_sync();
+        const bool diag_chunk = cu.c * kChunk == cu.row0 + p.diag_off;
+        const uint32_t tS = tmem + (uint32_t)(g * 128) + lane_base;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          const int col0 = sub * 64 + blk * 32;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tS + (uint32_t)col0, r);
+          ptx::tmem_ld_wait();
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            a0 += approx_ex2(fmaf(__uint_as_float(r[e]), p.c, -cmax));
+            a1 += approx_ex2(fmaf(__uint_as_float(r[e + 1]), p.c, -cmax));
+          }
+          acc += a0 + a1;
+          if (diag_chunk && (col0 >> 5) == q && cu.dir == 0) {  // S_ii is the same in both directions
+            float dv = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e == lane) dv = __uint_as_float(r[e]);
+            p.diag[cu.row0 + rit] = dv * p.inv_tau;
+          }
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.a_ready[g]);  // this S buffer may be overwritten
+      }
+      flush();
+    } else {
     float xs[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) xs[e] = 0.f;
@@ -427,6 +494,7 @@ nce_bwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (ct.ok) cur_next(ct, p);
       cur_next(cd, p);
     }
+    }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -463,6 +531,38 @@ nce_prep_kernel(const float* __restrict__ b0, const float* __restrict__ b1, int 
   }
 }
 
+// lse[d][i] = 1/tau + log(sum of the row's partial sums), fixed summation order
+__global__ void __launch_bounds__(256)
+nce_lse_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, float* __restrict__ lse0,
+                        float* __restrict__ lse1, int Ml, int slots, float inv_tau) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * Ml; i += gridDim.x * blockDim.x) {
+    const int dir = i >= Ml, row = i - dir * Ml;
+    const float* pr = (dir ? part1 : part0) + (long long)row * slots;
+    float s = 0.f;
+    for (int k = 0; k < slots; ++k) s += pr[k];
+    (dir ? lse1 : lse0)[row] = inv_tau + logf(s);
+  }
+}
+
+// units = direction x row tile x column split, the split chosen so that one wave of CTAs covers the SMs
+static void plan(Params& p, int64_t Ml, int64_t Ng) {
+  p.row_tiles = (int)(Ml / 128);
+  p.nc = (int)(Ng / 128);
+  int split = kNumSMs / (2 * p.row_tiles);
+  if (split < 1) split = 1;
+  if (split > p.nc) split = p.nc;
+  p.cps = (p.nc + split - 1) / split;
+  split = (p.nc + p.cps - 1) / p.cps;
+  p.units = 2 * p.row_tiles * split;
+  p.atomic = split > 1;
+  p.slots = 4 * split;
+  // e3 = [hi | lo | hi], f3 = [hi | hi | lo] (xm_l2norm_split_fwd_f32, which = 0 / 1)
+  p.a_lo_col[0] = kD;      // local e
+  p.b_lo_col[0] = 2 * kD;  // global f
+  p.a_lo_col[1] = 2 * kD;  // local f
+  p.b_lo_col[1] = kD;      // global e
+}
+
 static TensorView3 view2(const void* ptr, long long cols, long long rows) {
   return TensorView3{ptr, {(unsigned long long)cols, (unsigned long long)rows, 1ull},
                      {(unsigned long long)cols * 4ull, (unsigned long long)cols * (unsigned long long)rows * 4ull}};
@@ -497,20 +597,7 @@ int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_a
   float* bt0 = workspace + 2 * Ng;             // f^T [hi; lo]
   float* bt1 = bt0 + 2 * nce::kD * Ng;         // e^T [hi; lo]
   nce::Params p{};
-  p.row_tiles = (int)(Ml / 128);
-  p.nc = (int)(Ng / 128);
-  int split = kNumSMs / (2 * p.row_tiles);
-  if (split < 1) split = 1;
-  if (split > p.nc) split = p.nc;
-  p.cps = (p.nc + split - 1) / split;
-  split = (p.nc + p.cps - 1) / p.cps;
-  p.units = 2 * p.row_tiles * split;
-  p.atomic = split > 1;
-  // e3 = [hi | lo | hi], f3 = [hi | hi | lo] (xm_l2norm_split_fwd_f32, which = 0 / 1)
-  p.a_lo_col[0] = nce::kD;      // local e
-  p.b_lo_col[0] = 2 * nce::kD;  // global f
-  p.a_lo_col[1] = 2 * nce::kD;  // local f
-  p.b_lo_col[1] = nce::kD;      // global e
+  nce::plan(p, Ml, Ng);
   p.lse_row[0] = lse_ef;
   p.lse_row[1] = lse_fe;
   p.colscale[0] = cs0;
@@ -546,16 +633,63 @@ int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_a
   const int ctas = p.units < kNumSMs ? p.units : kNumSMs;
   cudaError_t e;
   if (precise) {
-    e = cudaFuncSetAttribute(nce::nce_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nce::kSmem);
-    if (e == cudaSuccess) nce::nce_bwd_kernel<true><<<ctas, nce::kThreads, nce::kSmem, st>>>(ma0, ma1, mb0, mb1, mt0, mt1, p);
+    e = cudaFuncSetAttribute(nce::nce_kernel<nce::MODE_PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, nce::kSmem);
+    if (e == cudaSuccess) nce::nce_kernel<nce::MODE_PRECISE><<<ctas, nce::kThreads, nce::kSmem, st>>>(ma0, ma1, mb0, mb1, mt0, mt1, p);
   } else {
-    e = cudaFuncSetAttribute(nce::nce_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nce::kSmem);
-    if (e == cudaSuccess) nce::nce_bwd_kernel<false><<<ctas, nce::kThreads, nce::kSmem, st>>>(ma0, ma1, mb0, mb1, mt0, mt1, p);
+    e = cudaFuncSetAttribute(nce::nce_kernel<nce::MODE_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, nce::kSmem);
+    if (e == cudaSuccess) nce::nce_kernel<nce::MODE_SINGLE><<<ctas, nce::kThreads, nce::kSmem, st>>>(ma0, ma1, mb0, mb1, mt0, mt1, p);
   }
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
+  return check_launch();
+}
+
+int64_t xm_infonce_lse_fused_workspace(int64_t Ml, int64_t Ng) {
+  if (Ml <= 0 || Ng <= 0 || Ml % 128 || Ng % 128) return 0;
+  nce::Params p{};
+  nce::plan(p, Ml, Ng);
+  return 2 * Ml * p.slots;
+}
+
+int xm_infonce_lse_fused_f32(const float* e3, const float* f3, const float* e3_all, const float* f3_all, float* lse_ef,
+                             float* lse_fe, float* diag, int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off,
+                             float* workspace, void* stream) {
+  if (!e3 || !f3 || !e3_all || !f3_all || !lse_ef || !lse_fe || !diag || !workspace) return XM_ERR_INVALID;
+  if (!xm_infonce_bwd_fused_supported(Ml, Ng, D, diag_off)) return XM_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  nce::Params p{};
+  nce::plan(p, Ml, Ng);
+  p.partial[0] = workspace;
+  p.partial[1] = workspace + Ml * p.slots;
+  p.diag = diag;
+  p.diag_off = (int)diag_off;
+  p.inv_tau = inv_tau;
+  p.c = inv_tau * nce::kLog2e;
+  CUtensorMap ma0, ma1, mb0, mb1;
+  int rc = encode_tmap(&ma0, nce::view2(e3, 3 * D, Ml), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&ma1, nce::view2(f3, 3 * D, Ml), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&mb0, nce::view2(f3_all, 3 * D, Ng), 32, 128, 0);
+  if (rc == XM_OK) rc = encode_tmap(&mb1, nce::view2(e3_all, 3 * D, Ng), 32, 128, 0);
+  if (rc != XM_OK) return rc;
+  // every (row, slot) of the workspace is written: each unit's 16 transform warps cover 2 groups x 2 column halves.  A
+  // group that gets no chunk of a unit (single-chunk units) leaves its slots untouched: clear them first.
+  if (cudaMemsetAsync(workspace, 0, (size_t)(2 * Ml * p.slots) * 4, st) != cudaSuccess) {
+    g_last_cuda_error = (int)cudaGetLastError();
+    return XM_ERR_LAUNCH;
+  }
+  const int ctas = p.units < kNumSMs ? p.units : kNumSMs;
+  cudaError_t e = cudaFuncSetAttribute(nce::nce_kernel<nce::MODE_LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, nce::kSmem);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return XM_ERR_LAUNCH;
+  }
+  nce::nce_kernel<nce::MODE_LSE><<<ctas, nce::kThreads, nce::kSmem, st>>>(ma0, ma1, mb0, mb1, mb0, mb1, p);
+  rc = check_launch();
+  if (rc != XM_OK) return rc;
+  const int blocks = (int)((2 * Ml + 255) / 256);
+  nce::nce_lse_finalize_kernel<<<blocks, 256, 0, st>>>(p.partial[0], p.partial[1], lse_ef, lse_fe, (int)Ml, p.slots, inv_tau);
   return check_launch();
 }
 

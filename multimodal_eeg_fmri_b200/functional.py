@@ -285,7 +285,7 @@ def act_dropout(x, act, drop_p=0.0, training=True):
 _PRECISE_MAX_K = 1 << 30
 _FUSED_FFN = os.environ.get("XM_FUSED_FFN", "1") != "0"  # A/B switch: 0 = the unfused linear / act / linear chain
 _INFONCE_PRECISE_DGRAD = {"0": False, "1": True}.get(os.environ.get("XM_INFONCE_PRECISE_DGRAD", ""), None)
-_FUSED_INFONCE_BWD = os.environ.get("XM_FUSED_INFONCE_BWD", "1") != "0"  # A/B switch: 0 = grad -> split -> dgrad chain
+_FUSED_INFONCE_BWD = os.environ.get("XM_FUSED_INFONCE", os.environ.get("XM_FUSED_INFONCE_BWD", "1")) != "0"  # A/B switch: 0 = the unfused lse / grad / split / dgrad GEMM chain
 
 
 class LinearBnAct(torch.autograd.Function):
@@ -655,6 +655,15 @@ class _PeerShards:
         return ent["sets"][ent["turn"]]
 
 
+def _infonce_lse_pair(e3, f3, e3_all, f3_all, inv_tau, off):
+    """(lse of my e x all f, lse of my f x all e, positives): one fused launch where the shapes allow, else two GEMMs."""
+    if _FUSED_INFONCE_BWD and ops.infonce_bwd_fused_supported(e3.shape[0], e3_all.shape[0], e3.shape[1] // 3, off):
+        return ops.infonce_lse_fused(e3, f3, e3_all, f3_all, inv_tau, off)
+    lse_ef, diag = ops.infonce_lse(e3, f3_all, inv_tau, off)
+    lse_fe, _ = ops.infonce_lse(f3, e3_all, inv_tau, off)
+    return lse_ef, lse_fe, diag
+
+
 class SymmetricInfoNCE(torch.autograd.Function):
     """L = 1/(2B) sum_i [lse_j S_ij - S_ii] + [lse_j S_ji - S_ii],  S = norm(e) norm(f)^T / tau, over the
     GLOBAL batch: each rank holds B/G rows of e and f; the similarity kernels read the other ranks' unit
@@ -689,8 +698,7 @@ class SymmetricInfoNCE(torch.autograd.Function):
                 # in the local L2), so gather once through the peer mappings and contract against the local copy
                 e3_all = ops.peer_gather(e_ptrs, Bl, 3 * D, e.device)
                 f3_all = ops.peer_gather(f_ptrs, Bl, 3 * D, e.device)
-                lse_ef, diag = ops.infonce_lse(e3, f3_all, inv_tau, off)
-                lse_fe, _ = ops.infonce_lse(f3, e3_all, inv_tau, off)
+                lse_ef, lse_fe, diag = _infonce_lse_pair(e3, f3, e3_all, f3_all, inv_tau, off)
                 ctx.peers = None
                 ctx.save_for_backward(en, fn, einv, finv, e3, f3, lse_ef, lse_fe, e3_all, f3_all)
         else:
@@ -700,8 +708,7 @@ class SymmetricInfoNCE(torch.autograd.Function):
             f3_all = _AllGatherRows.gather(f3)
             Bg = e3_all.shape[0]
             off = _CTX.rank * Bl if _CTX.active else 0
-            lse_ef, diag = ops.infonce_lse(e3, f3_all, inv_tau, off)
-            lse_fe, _ = ops.infonce_lse(f3, e3_all, inv_tau, off)
+            lse_ef, lse_fe, diag = _infonce_lse_pair(e3, f3, e3_all, f3_all, inv_tau, off)
             ctx.peers = None
             ctx.save_for_backward(en, fn, einv, finv, e3, f3, lse_ef, lse_fe, e3_all, f3_all)
         loss = (0.5 / Bg) * ((lse_ef - diag).sum() + (lse_fe - diag).sum())

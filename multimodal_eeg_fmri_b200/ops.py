@@ -872,6 +872,23 @@ def infonce_bwd_fused_supported(Ml, Ng, D, diag_off):
     return bool(_lib.lib().xm_infonce_bwd_fused_supported(int(Ml), int(Ng), int(D), int(diag_off)))
 
 
+def infonce_lse_fused(e3, f3, e3_all, f3_all, inv_tau, diag_off=0):
+    """-> (lse_ef, lse_fe, diag): row logsumexps of (my e x all f) and (my f x all e) scores and the positives S_ii, one
+    launch, scores never written (xm_infonce_lse_fused_f32; shapes as infonce_bwd_fused_supported)."""
+    _chk(e3, f3, e3_all, f3_all)
+    e3, f3, e3_all, f3_all = e3.contiguous(), f3.contiguous(), e3_all.contiguous(), f3_all.contiguous()
+    Ml, D = e3.shape[0], e3.shape[1] // 3
+    Ng = e3_all.shape[0]
+    lse_ef = torch.empty(Ml, device=e3.device, dtype=torch.float32)
+    lse_fe = torch.empty(Ml, device=e3.device, dtype=torch.float32)
+    diag = torch.empty(Ml, device=e3.device, dtype=torch.float32)
+    ws = torch.empty(int(_lib.lib().xm_infonce_lse_fused_workspace(Ml, Ng)), device=e3.device, dtype=torch.float32)
+    _w(2.0 * 6.0 * Ml * Ng * D, 4.0 * (2 * 3 * Ml * D + 2 * 3 * Ng * D + 3 * Ml))
+    _call("xm_infonce_lse_fused_f32", _p(e3), _p(f3), _p(e3_all), _p(f3_all), _p(lse_ef), _p(lse_fe), _p(diag), Ml, Ng, D,
+          float(inv_tau), int(diag_off), _p(ws), _stream())
+    return lse_ef, lse_fe, diag
+
+
 def infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef, lse_fe, lse_ef_all, lse_fe_all, inv_tau, diag_off, coef, precise=True):
     """-> (de, df) (Ml, D): the InfoNCE gradients with respect to this rank's unit embeddings, both softmax-gradient
     blocks formed and contracted on chip (xm_infonce_bwd_fused_f32).  e3 / f3: local l2norm splits (which 0 / 1),

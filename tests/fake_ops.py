@@ -290,6 +290,12 @@ def infonce_bwd_fused_supported(Ml, Ng, D, diag_off):
     return D == 128 and Ml % 128 == 0 and Ng % 128 == 0 and diag_off % 128 == 0 and diag_off + Ml <= Ng
 
 
+def infonce_lse_fused(e3, f3, e3_all, f3_all, inv_tau, diag_off=0):
+    lse_ef, diag = infonce_lse(e3, f3_all, inv_tau, diag_off)
+    lse_fe, _ = infonce_lse(f3, e3_all, inv_tau, diag_off)
+    return lse_ef, lse_fe, diag
+
+
 def infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef, lse_fe, lse_ef_all, lse_fe_all, inv_tau, diag_off, coef, precise=True):
     D = e3.shape[1] // 3
     G1 = infonce_grad(e3, f3_all, lse_ef, lse_fe_all, inv_tau, diag_off, coef)

@@ -201,6 +201,12 @@ def test_infonce_bwd_fused(ops, Ml, Ng, off, precise):
     de_ref, df_ref = coef * G1 @ fn_all.double(), coef * G2 @ en_all.double()
     de, df = ops.infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef_all[off:off + Ml].float(), lse_fe_all[off:off + Ml].float(),
                                    lse_ef_all.float(), lse_fe_all.float(), it, off, coef, precise)
+    l_ef, l_fe, dg = ops.infonce_lse_fused(e3, f3, e3_all, f3_all, it, off)
+    assert float((l_ef.double() - lse_ef_all[off:off + Ml]).abs().max()) < 1e-4, "fused row lse, e x f"
+    assert float((l_fe.double() - lse_fe_all[off:off + Ml]).abs().max()) < 1e-4, "fused row lse, f x e"
+    assert float((dg.double() - S[idx + off, idx + off]).abs().max()) < 1e-4, "fused positives"
+    l2 = ops.infonce_lse_fused(e3, f3, e3_all, f3_all, it, off)
+    assert torch.equal(l2[0], l_ef) and torch.equal(l2[1], l_fe), "fixed summation order: bit-identical reruns"
     tol = 2e-5 if precise else TF32
     assert_close_rel(de, de_ref, tol, "fused infonce de", atol=1e-9)
     assert_close_rel(df, df_ref, tol, "fused infonce df", atol=1e-9)
