@@ -310,6 +310,16 @@ int xm_infonce_grad_peers_f32(const float* a, const void* const* b_peers, int n_
  * shards, one launch of 128-bit peer loads.  Used instead of the in-GEMM peer reads when a rank has many
  * row tiles (every row tile would otherwise re-fetch every remote tile across NVLink). */
 int xm_peer_gather_f32(const void* const* src_peers, int n_peers, int64_t elems_per_peer, float* dst, void* stream);
+/* Small all-reduce (SUM) of n doubles over peer memory (csrc/peer_exchange.cu; SyncBN statistics of the data-parallel
+ * step): this rank pushes x into row `rank` of the current slot of every peer's symmetric buffer (data_dst[p], p <
+ * n_peers <= 8, self included), publishes `seq` at flag_dst[p], waits until slot_flags[0..n_peers) of ITS OWN buffer
+ * all equal seq, and writes out[i] = sum over r of slot_data[r * row_stride + i] (rank order: identical on all ranks).
+ * The caller rotates >= 2 slots per channel and increases seq by one per call of the channel (seq > 0; flags start
+ * at 0); calls of one channel are issued in the same order on every rank.  A peer that never arrives poisons the
+ * result with NaN after ~10 s instead of hanging the device. */
+int xm_peer_allreduce_f64(const double* x, double* out, int64_t n, const void* const* data_dst, const void* const* flag_dst,
+                          int n_peers, const double* slot_data, const uint64_t* slot_flags, int64_t row_stride, uint64_t seq,
+                          void* stream);
 /* dx (M, K) = dy (M, n_peers*rows_per_peer) @ w, w row-sharded across peers (pitch ldw). */
 int xm_linear_dgrad_peers_f32(const float* dy, const void* const* w_peers, int n_peers, int64_t rows_per_peer, float* dx,
                               int64_t M, int64_t K, int64_t lddy, int64_t ldw, int64_t lddx, int round_out, void* stream);

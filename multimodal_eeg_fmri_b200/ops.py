@@ -624,6 +624,18 @@ def peer_gather(peer_ptrs, rows_per_peer, cols, device):
     return out
 
 
+def peer_allreduce_f64(x, data_dst, flag_dst, slot_data_ptr, slot_flags_ptr, row_stride, seq):
+    """Sum of the ranks' fp64 vectors `x` through peer memory (xm_peer_allreduce_f64); pointers are raw device
+    addresses into the symmetric buffers (functional._PeerReduce owns slots and sequence numbers)."""
+    if not x.is_cuda or x.dtype != torch.float64:
+        raise _lib.XmodalError(f"expected a CUDA float64 tensor, got {x.device} {x.dtype}")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _call("xm_peer_allreduce_f64", _p(x), _p(out), x.numel(), _ptr_array(data_dst), _ptr_array(flag_dst), len(data_dst),
+          ctypes.c_void_p(int(slot_data_ptr)), ctypes.c_void_p(int(slot_flags_ptr)), int(row_stride), int(seq), _stream())
+    return out
+
+
 def infonce_lse_peers(a, peer_ptrs, rows_per_peer, inv_tau, diag_off=0):
     """Row logsumexp of a @ [b_0; b_1; ...]^T * inv_tau where shard r of the second operand is read IN PLACE
     from rank r's memory (peer_ptrs[r], NVLink-mapped): all-gather fused into the GEMM's TMA loads."""

@@ -119,7 +119,13 @@ class PairedTrainer:
         self.model = model
         self.grad_clip = grad_clip
         self.window, self.hop = window, hop
-        self.params = model.contrastive_parameters()
+        params = model.contrastive_parameters()
+        # flat layout [early | late]: the fMRI branch finishes its backward long before the EEG encoder does (it runs on
+        # a side stream), so its gradients -- 10.3 of the 11.6 M parameters -- are all-reduced while the encoder's
+        # backward is still running; only the small late bucket stays on the critical path.
+        early = {id(p) for p in model.fmri_net.parameters()}
+        self.params = [p for p in params if id(p) in early] + [p for p in params if id(p) not in early]
+        self._early_params = [p for p in self.params if id(p) in early]
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         # Parameters, gradients and both AdamW moments live in ONE flat fp32 buffer each (every tensor 16-B aligned in
@@ -130,6 +136,7 @@ class PairedTrainer:
         for p in self.params:
             offs.append(o)
             o += (p.numel() + 3) // 4 * 4
+        self._n_early = offs[len(self._early_params)] if len(self._early_params) < len(self.params) else o
         self.flat_param = torch.zeros(o, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(o, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(o, device=dev, dtype=torch.float32)
@@ -144,6 +151,31 @@ class PairedTrainer:
         self.last_grad_norm = None  # pre-clip total norm of the last step (device scalar)
         self.ctx = XF.parallel_context()
         self._stage = {}
+        self._early_left = 0
+        self._early_event = None
+        self._comm_stream = None
+        if self.ctx.active and dev.type == "cuda" and self._early_params:
+            self._early_event = torch.cuda.Event()
+            self._comm_stream = torch.cuda.Stream(dev)
+            for p in self._early_params:
+                p.register_post_accumulate_grad_hook(self._early_grad_ready)
+
+    def _early_grad_ready(self, _param) -> None:
+        """Runs on the stream that accumulated the gradient: after the last early parameter, mark the early bucket ready."""
+        self._early_left -= 1
+        if self._early_left == 0:
+            self._early_event.record(torch.cuda.current_stream())
+
+    def _allreduce_gradients(self) -> None:
+        g = self.ctx.group
+        if self._early_event is None or self._early_left != 0:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=g)
+            return
+        self._comm_stream.wait_event(self._early_event)
+        with torch.cuda.stream(self._comm_stream):
+            work = dist.all_reduce(self.flat_grad[:self._n_early], op=dist.ReduceOp.SUM, group=g, async_op=True)
+        dist.all_reduce(self.flat_grad[self._n_early:], op=dist.ReduceOp.SUM, group=g)
+        work.wait()  # the current stream continues after the early bucket has arrived
 
     # -- device-resident step ---------------------------------------------------------------
     def step(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -158,9 +190,10 @@ class PairedTrainer:
             loss = self.model(x, roi_series, conn, eeg_channels_last=True)
         else:
             loss = self.model(eeg, roi_series, conn)
+        self._early_left = len(self._early_params)
         loss.backward()
         if self.ctx.active:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.ctx.group)
+            self._allreduce_gradients()
         self.step_count += 1
         self.last_grad_norm = ops.clip_adamw_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
                                               self.lr, self.weight_decay, self.grad_clip or 0.0, self.betas, self.eps)

@@ -38,25 +38,31 @@ def main():
                                   fmri_dropout=0.0, encoder="lite")
         P = {k: v.detach().clone() for k, v in model.state_dict().items()}
         trainer = PairedTrainer(model.cuda().train())
-        losses = []
+        losses, norms = [], []
         for _ in range(steps):
             loss = trainer.step(eeg[sl].cuda(), roi[sl].cuda(), conn[sl].cuda()).clone()
             dist.all_reduce(loss)
             losses.append(float(loss))
+            norms.append(float(trainer.last_grad_norm))  # norm of the ALL-REDUCED gradient (both buckets)
         used_peer = peer and not XF._PeerShards._failed
         if rank == 0:
-            state, want = {}, []
+            state, want, want_norm = {}, [], []
             for _ in range(steps):
-                want.append(float(ps.paired_train_step(P, state, eeg, roi, conn, 0.07, "lite")[0]))
+                l, nrm = ps.paired_train_step(P, state, eeg, roi, conn, 0.07, "lite")
+                want.append(float(l))
+                want_norm.append(float(nrm))
             lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, want))
+            nerr = max(abs(a - b) / abs(b) for a, b in zip(norms, want_norm))
             keys = set(ps.trainable_keys(P)) - set(ps.bias_before_batchnorm_keys(P))
             sd = model.state_dict()
             perr = max(float((sd[k].cpu() - P[k]).abs().max()) for k in keys)
             # AdamW steps of lr 1e-4: a sign flip of a ~zero gradient moves a weight by 2*lr per step
-            good = lerr < 1e-3 and perr < 2.25e-4 * steps
+            # (AdamW normalises the step, so the parameters alone would not notice a gradient bucket that missed its
+            # all-reduce: the pre-clip norm of the reduced gradient does)
+            good = lerr < 1e-3 and perr < 2.25e-4 * steps and nerr < 2e-3
             ok = ok and good
             path = ("peer-memory/in-GEMM" if Bl <= 512 else "peer-memory/gather-once") if used_peer else "nccl-all-gather"
-            print(f"dp_gpu_check world={world} local_batch={Bl} path={path} loss_rel_err={lerr:.2e} "
+            print(f"dp_gpu_check world={world} local_batch={Bl} path={path} loss_rel_err={lerr:.2e} grad_norm_rel_err={nerr:.2e} "
                   f"param_max_abs_err={perr:.2e} {'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
