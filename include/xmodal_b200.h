@@ -337,9 +337,12 @@ int xm_linear_dgrad_peers_f32(const float* dy, const void* const* w_peers, int n
  * (mask (B*H, L, L), 1 = kept) so tests can replay it. */
 int xm_attn_fused_fwd_f32(const float* qkv, float* out, float* lse, int64_t B, int64_t L, int64_t H, int64_t dh, float scale,
                           float drop_p, uint64_t seed, int round_out, void* stream);
+/* dbias_part (may be NULL): (xm_attn_fused_bwd_nblk(), 3*H*dh) partial column sums of dqkv (zeroed by the call; reduce
+ * with xm_colsum_f32): the bias gradient of the in-projection, accumulated where dq / dk / dv leave tensor memory. */
+int xm_attn_fused_bwd_nblk(void);
 int xm_attn_fused_bwd_f32(const float* dout, const float* qkv, const float* out, const float* lse, float* dqkv, float* delta,
-                          int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed,
-                          int round_out, void* stream);
+                          float* dbias_part, int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p,
+                          uint64_t seed, int round_out, void* stream);
 int xm_attn_fused_mask_u8(uint8_t* mask, int64_t B, int64_t L, int64_t H, float drop_p, uint64_t seed, void* stream);
 /* Shape-general variant (csrc/attention_general.cu; SIMT fp32): every shape the fused kernel does not cover --
  * head dim <= 256, any L with xm_attn_general_supported(L, dh) != 0 -- plus nn.MultiheadAttention's attn_mask

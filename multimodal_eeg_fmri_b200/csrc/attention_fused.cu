@@ -61,6 +61,8 @@ struct FaParams {
   const float* out;  // (B, L, d) forward output (backward: delta = dO . O)
   const float* dout; // (B, L, d)
   long long* trace;  // debug (xm_debug_set_attn_trace): CTA 0 appends clock64() at phase boundaries, 4096 slots per role
+  float* bias_part;  // backward, may be NULL: (2 * 148 * 4, 3d) zero-initialised partial column sums of dqkv, one row
+                     // per (CTA, output warp) -- the bias gradient of the in-projection without a pass over dqkv
 };
 
 XM_DEVICE uint32_t row_seed(unsigned long long row_id, unsigned long long seed) {
@@ -164,7 +166,7 @@ struct Bars {
   uint64_t o_full[2], o_empty[2];  // output accumulator sets
 };
 
-XM_DEVICE void init_common(Bars& bar, uint32_t* tmem_slot, int warp) {
+XM_DEVICE void init_common(Bars& bar, uint32_t* tmem_slot, int warp, int out_readers = 4) {
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bar.full, 1);
     ptx::mbar_init(&bar.empty, 1);
@@ -172,7 +174,8 @@ XM_DEVICE void init_common(Bars& bar, uint32_t* tmem_slot, int warp) {
       ptx::mbar_init(&bar.hfull[i], 1);
       ptx::mbar_init(&bar.hempty[i], 1);
       ptx::mbar_init(&bar.o_full[i], 1);
-      ptx::mbar_init(&bar.o_empty[i], 4);  // the four part-0 warps drain an output accumulator set
+      ptx::mbar_init(&bar.o_empty[i], out_readers);  // the four part-0 warps drain an output accumulator set (backward
+                                                     // with bias sums: the four part-1 warps read it too)
     }
     ptx::mbar_init(&bar.s_full, 1);
     ptx::mbar_init(&bar.p_ready, kEpiWarps);
@@ -432,8 +435,8 @@ struct BwdCfg {
   static constexpr int kOutCols = KV ? 64 : 32;  // per accumulator set
 };
 
-template <bool KV, bool LONG>  // LONG (dk/dv only): 256 < L <= 512, the per-query tables are refilled mid-item
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool KV, bool LONG, bool BIAS>  // LONG (dk/dv only): 256 < L <= 512, the per-query tables are refilled mid-item
+__global__ void __launch_bounds__(kThreads, 2)                   // BIAS: also emit partial column sums of the outputs
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDOx,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYmn,
                 const __grid_constant__ CUtensorMap tmDOy, const __grid_constant__ CUtensorMap tmDOymn,
@@ -462,7 +465,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     ptx::prefetch_tensormap(&tmDOymn);
     ptx::prefetch_tensormap(&tmDQKV);
   }
-  init_common(bar, &tmem_slot, warp);
+  init_common(bar, &tmem_slot, warp, BIAS ? 8 : 4);
   const uint32_t tmem = tmem_slot;
   const uint32_t tS = tmem, tP = tmem + 64, tOut = tmem + 128;
   const int NC = (p.L + 63) >> 6;  // 64-wide chunks of the other index
@@ -734,6 +737,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar.o_empty[s]);
         store_box<C::kStageRows>(&tmDQKV, sb, lane, r, p.round_out != 0, (KV ? 2 * p.d : 0) + h * 32, t * 128 + q * 32, b);
+      } else if (BIAS) {
+        // The part-1 warps are idle between items: they read the same output accumulators (their lane quadrant) and add
+        // the column sums of the 32 output rows to this warp's private row of partial sums -- the in-projection's bias
+        // gradient without a pass over dqkv.  Rows past L hold products of zero-filled tiles with nonzero
+        // probabilities: excluded.  RED (fire and forget): the row is private to the warp, so the sum's order is fixed.
+        const int s = it & 1;
+        ptx::mbar_wait(&bar.o_full[s], ((uint32_t)it >> 1) & 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t out = tOut + (uint32_t)(s * C::kOutCols) + lane_base;
+        const bool live_row = t * 128 + q * 32 + lane < p.L;
+        float* bp = p.bias_part + (long long)(blockIdx.x * 4 + q) * (3 * p.d) + h * 32 + lane;
+        uint32_t r[32];
+#pragma unroll
+        for (int o = 0; o < (KV ? 2 : 1); ++o) {
+          ptx::tmem_ld_32x32(out + (uint32_t)(o * 32), r);
+          ptx::tmem_ld_wait();
+          if (o == (KV ? 1 : 0)) {
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bar.o_empty[s]);
+          }
+          if (!live_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          const float cs = warp_column_sums(r, lane);
+          atomicAdd(bp + (KV ? (o == 0 ? p.d : 2 * p.d) : 0), cs);
+        }
       }
     }
     if (part == 0 && lane == 0) ptx::bulk_wait_all();
@@ -828,13 +859,21 @@ int xm_attn_fused_fwd_f32(const float* qkv, float* out, float* lse, int64_t B, i
   return check_launch();
 }
 
+int xm_attn_fused_bwd_nblk(void) { return 2 * kNumSMs * 4; }
+
 int xm_attn_fused_bwd_f32(const float* dout, const float* qkv, const float* out, const float* lse, float* dqkv, float* delta,
-                          int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p, uint64_t seed,
-                          int round_out, void* stream) {
+                          float* dbias_part, int64_t B, int64_t L, int64_t H, int64_t dh, float scale, float drop_p,
+                          uint64_t seed, int round_out, void* stream) {
   if (!dout || !qkv || !out || !lse || !dqkv || !delta) return XM_ERR_INVALID;
   FaParams p{};
   int rc = fill_params(p, B, L, H, dh, scale, drop_p, seed, round_out);
   if (rc != XM_OK) return rc;
+  p.bias_part = dbias_part;
+  if (dbias_part &&
+      cudaMemsetAsync(dbias_part, 0, (size_t)xm_attn_fused_bwd_nblk() * 3 * p.d * sizeof(float), (cudaStream_t)stream) != cudaSuccess) {
+    g_last_cuda_error = (int)cudaGetLastError();
+    return XM_ERR_LAUNCH;
+  }
   p.lse = const_cast<float*>(lse);
   p.delta = delta;
   p.out = out;
@@ -851,18 +890,24 @@ int xm_attn_fused_bwd_f32(const float* dout, const float* qkv, const float* out,
   if (rc == XM_OK) rc = encode_tmap(&mo, tdq, 32, 32, 0);
   if (rc == XM_OK) rc = encode_tmap(&mo16, tdq, 32, 16, 0);
   const bool lng = L > 256;
-  if (rc == XM_OK) rc = set_smem(attn_bwd_kernel<false, false>, BwdCfg<false>::kSmem);
-  if (rc == XM_OK) rc = lng ? set_smem(attn_bwd_kernel<true, true>, BwdCfg<true>::kSmem)
-                            : set_smem(attn_bwd_kernel<true, false>, BwdCfg<true>::kSmem);
-  if (rc != XM_OK) return rc;
   const int ctas = p.items < 2 * kNumSMs ? p.items : 2 * kNumSMs;
   cudaStream_t st = (cudaStream_t)stream;
-  attn_bwd_kernel<false, false><<<ctas, kThreads, BwdCfg<false>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo, p);  // dq, delta
-  rc = check_launch();
+  auto launch = [&](auto kernel, int smem, const CUtensorMap& out_map) {
+    int r = set_smem(kernel, smem);
+    if (r != XM_OK) return r;
+    kernel<<<ctas, kThreads, smem, st>>>(mx, mdx, my, myn, mdy, mdyn, out_map, p);
+    return check_launch();
+  };
+  const bool bias = dbias_part != nullptr;
+  // dq, delta
+  rc = bias ? launch(attn_bwd_kernel<false, false, true>, BwdCfg<false>::kSmem, mo)
+            : launch(attn_bwd_kernel<false, false, false>, BwdCfg<false>::kSmem, mo);
   if (rc != XM_OK) return rc;
-  if (lng) attn_bwd_kernel<true, true><<<ctas, kThreads, BwdCfg<true>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo16, p);
-  else attn_bwd_kernel<true, false><<<ctas, kThreads, BwdCfg<true>::kSmem, st>>>(mx, mdx, my, myn, mdy, mdyn, mo16, p);  // dk, dv
-  return check_launch();
+  // dk, dv
+  if (lng) return bias ? launch(attn_bwd_kernel<true, true, true>, BwdCfg<true>::kSmem, mo16)
+                       : launch(attn_bwd_kernel<true, true, false>, BwdCfg<true>::kSmem, mo16);
+  return bias ? launch(attn_bwd_kernel<true, false, true>, BwdCfg<true>::kSmem, mo16)
+              : launch(attn_bwd_kernel<true, false, false>, BwdCfg<true>::kSmem, mo16);
 }
 
 int xm_debug_set_attn_trace(int64_t* device_buffer) {

@@ -14,7 +14,7 @@
 // One persistent CTA per SM walks 128-row tiles; per tile the hidden axis is processed in chunks of 128 units:
 //   warp 0      TMA producer: the x (and dY) tile of the tile, then a ring of 16 KB weight k-blocks (from L2)
 //   warp 1      one thread issues every tcgen05.mma (kind::tf32, M = N = 128, fp32 accumulators in TMEM)
-//   warps 2-17  16 transform warps in two groups of 8 that alternate chunks (4 TMEM lane quadrants x 2 column halves):
+//   warps 2-17  16 transform warps (4 TMEM lane quadrants x 4 blocks of 32 columns), all on every chunk:
 //               tcgen05.ld the chunk's accumulator, bias + activation + dropout in registers (packed f32x2
 //               arithmetic), tcgen05.st the result back IN PLACE, where it is the A operand of the next product
 // forward MMA order:   M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | M2(2) | M2(3)          M1: H_c = x W1_c^T
@@ -224,32 +224,6 @@ XM_DEVICE void bwd_transform(uint32_t (&rh)[32], uint32_t (&rg)[32], const float
   }
 }
 
-// Column sums over the warp's 32 rows of a 32-column block held one row per lane: butterfly reduce-scatter,
-// 31 shuffles; lane j returns the sum of column j.
-XM_DEVICE float warp_column_sums(const uint32_t (&r)[32], int lane) {
-  float v[16];
-  {
-    const bool up = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float keep = __uint_as_float(up ? r[16 + i] : r[i]);
-      const float send = __uint_as_float(up ? r[i] : r[16 + i]);
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-#pragma unroll
-  for (int s = 8; s >= 1; s >>= 1) {
-    const bool up = lane & s;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float keep = up ? v[s + i] : v[i];
-      const float send = up ? v[i] : v[s + i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];  // column index = lane (bit b of the lane selected the upper half at step b)
-}
-
 // 32 consecutive fp32 of one row (128 B, one full line per lane) -> global memory as four 256-bit stores: every
 // store instruction writes 32 complete sectors (16-B stores would write each sector in two halves).
 XM_DEVICE void store_row32(float* dst, const uint32_t (&r)[32]) {
@@ -280,16 +254,18 @@ XM_DEVICE void stage_block(const CUtensorMap* tm, uint8_t* sb, int lane, const u
 struct FwdBars {
   uint64_t x_full[2], x_empty[2];
   uint64_t w_full[kFwdRing], w_empty[kFwdRing];
-  uint64_t h_full[2], a_ready[2];
-  uint64_t y_full[2], y_free;  // y_full[g]: completed tiles whose output group g writes (a barrier may only have
-                               // waiters that consume EVERY phase: a waiter skipping phases aliases on the parity)
+  uint64_t h_full[2], a_ready[2];  // per H buffer
+  uint64_t y_full, y_free;         // (a barrier may only have waiters that consume EVERY phase: a waiter that skips
+                                   // phases aliases on the parity -- all 16 transform warps wait on every one of these)
 };
 
 // Forward.  The MMA warp runs ONE software pipeline over the CTA's whole chunk sequence n = 0, 1, ... (tile = n / nc,
 // chunk = n % nc), crossing tile boundaries:  M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | ...  H buffer = n & 1.
-// The 16 transform warps form two groups of 8 (4 lane quadrants x 2 column halves); group g owns H buffer g, i.e. the
-// chunks with n & 1 == g, so the transform of chunk n + 1 overlaps the transform of chunk n and both overlap the MMAs.
-// The group that transforms a tile's last chunk also writes the tile's output.
+// ALL 16 transform warps work on every chunk (4 lane quadrants x 4 blocks of 32 columns): with two H buffers the
+// transform of chunk n has exactly the time of [M2(n - 1) M1(n + 1)] -- M1(n) ends where that slot starts and M2(n) opens
+// the next one -- so its LATENCY, not its throughput, decides whether the MMA warp waits.  (Two groups of 8 warps
+// alternating chunks had the same throughput but never overlapped: each group's chunk took ~6.5k clk of a 4.9k slot,
+// profiles/r2_ffn_fwd_trace_v4.json; ncu: tensor pipe 35 %, issue 45 %, nothing saturated.)  They also write the tile.
 template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -313,14 +289,14 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ptx::mbar_init(&bar.x_full[i], 1);
       ptx::mbar_init(&bar.x_empty[i], 1);
       ptx::mbar_init(&bar.h_full[i], 1);
-      ptx::mbar_init(&bar.a_ready[i], kXfWarps / 2);
-      ptx::mbar_init(&bar.y_full[i], 1);
+      ptx::mbar_init(&bar.a_ready[i], kXfWarps);
     }
+    ptx::mbar_init(&bar.y_full, 1);
     for (int i = 0; i < kFwdRing; ++i) {
       ptx::mbar_init(&bar.w_full[i], 1);
       ptx::mbar_init(&bar.w_empty[i], 1);
     }
-    ptx::mbar_init(&bar.y_free, kXfWarps / 2);
+    ptx::mbar_init(&bar.y_free, kXfWarps);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -455,7 +431,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int k8 = 0; k8 < 4; ++k8)
               mma_tf32_ts(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u));
             ptx::mma_commit(&bar.w_empty[st]);
-            if (kb == 3 && c == p.nc - 1) ptx::mma_commit(&bar.y_full[b]);  // group b transformed this chunk and writes the tile
+            if (kb == 3 && c == p.nc - 1) ptx::mma_commit(&bar.y_full);  // the tile's output is complete
           }
           __syncwarp();
           if (++st == kFwdRing) { st = 0; ph ^= 1u; }
@@ -470,67 +446,56 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
   } else {
-    const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int pidx = (warp - 2) >> 2;    // 0..3
-    const int g = pidx >> 1;             // transform group = H buffer
-    const int sub = pidx & 1;            // which 64 of the chunk's 128 columns
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int cb = (warp - 2) >> 2;    // which 32 of the chunk's (and of the output's) 128 columns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float cs = kTruncComp * p.dscale;
-    uint32_t n_out = 0;  // tiles this group has written
     int tn = 0;
-    for (int n = g; n < N; n += 2) {
-      const int it = n / p.nc, c = n - it * p.nc;
+    for (int n = 0; n < N; ++n) {
+      const int it = n / p.nc, c = n - it * p.nc, g = n & 1;
       const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + q * 32 + lane;
       const long long t0 = TRACE ? clock64() : 0;
       ptx::mbar_wait(&bar.h_full[g], ((uint32_t)n >> 1) & 1u);
       const long long t1 = TRACE ? clock64() : 0;
       ptx::tc_fence_after_sync();
-      const uint32_t rs = p.thr ? row_seed((unsigned long long)row, p.seed) : 0u;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int col0 = sub * 64 + j * 32;
+      {
+        const int col0 = cb * 32;
         const uint32_t addr = tmem + (uint32_t)(g * 128 + col0) + lane_base;
         uint32_t r[32];
         ptx::tmem_ld_32x32(addr, r);
         ptx::tmem_ld_wait();
         const float* bias = sb1 + c * kChunk + col0;
         if (TRACE && (p.dbg & 1)) {
-        } else if (p.thr)
+        } else if (p.thr) {
+          const uint32_t rs = row_seed((unsigned long long)row, p.seed);
           fwd_transform<true>(r, bias, p.act, cs, p.thr, group_seed(rs, (c * kChunk + col0) >> 5));
-        else
+        } else {
           fwd_transform<false>(r, bias, p.act, cs, 0u, 0u);
+        }
         ptx::tmem_st_32x32(addr, r);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar.a_ready[g]);
-      if (TRACE && blockIdx.x == 0 && q == 0 && sub == 0 && lane == 0 && tn < 4096 - 6) {
-        long long* t = p.trace + 16384 + g * 4096 + tn;
+      if (TRACE && blockIdx.x == 0 && q == 0 && cb == 0 && lane == 0 && tn < 4096 - 6) {
+        long long* t = p.trace + 16384 + tn;
         t[0] = 4; t[1] = n; t[2] = t0; t[3] = t1; t[4] = clock64(); t[5] = 0;
         tn += 6;
       }
       if (c == p.nc - 1) {
-        // ---- this group also writes the tile's output: y = Y + b2 (64 columns per warp)
-        ptx::mbar_wait(&bar.y_full[g], n_out & 1u);
-        ++n_out;
+        // ---- the tile's output: y = Y + b2 (32 columns per warp)
+        ptx::mbar_wait(&bar.y_full, (uint32_t)it & 1u);
         ptx::tc_fence_after_sync();
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(tY + (uint32_t)(sub * 64) + lane_base, r0);
-        ptx::tmem_ld_32x32(tY + (uint32_t)(sub * 64 + 32) + lane_base, r1);
+        uint32_t r0[32];
+        ptx::tmem_ld_32x32(tY + (uint32_t)(cb * 32) + lane_base, r0);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar.y_free);  // Y is in registers: the next tile may overwrite it
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          r0[e] = __float_as_uint(__uint_as_float(r0[e]) + sb2[sub * 64 + e]);
-          r1[e] = __float_as_uint(__uint_as_float(r1[e]) + sb2[sub * 64 + 32 + e]);
-        }
-        if (row < p.M) {
-          store_row32(p.y + row * kD + sub * 64, r0);
-          store_row32(p.y + row * kD + sub * 64 + 32, r1);
-        }
+        for (int e = 0; e < 32; ++e) r0[e] = __float_as_uint(__uint_as_float(r0[e]) + sb2[cb * 32 + e]);
+        if (row < p.M) store_row32(p.y + row * kD + cb * 32, r0);
       }
     }
   }

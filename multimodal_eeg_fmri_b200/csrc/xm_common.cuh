@@ -104,6 +104,32 @@ XM_DEVICE bool dropout_keep(uint64_t idx, uint64_t seed, uint32_t threshold) {
   return hash_u32(idx, seed) >= threshold;
 }
 
+// Column sums over the warp's 32 rows of a 32-column block held one row per lane: butterfly reduce-scatter,
+// 31 shuffles; lane j returns the sum of column j.
+XM_DEVICE float warp_column_sums(const uint32_t (&r)[32], int lane) {
+  float v[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float keep = __uint_as_float(up ? r[16 + i] : r[i]);
+      const float send = __uint_as_float(up ? r[i] : r[16 + i]);
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[s + i] : v[i];
+      const float send = up ? v[i] : v[s + i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];  // column index = lane (bit b of the lane selected the upper half at step b)
+}
+
 // act codes shared with the host (include/xmodal_b200.h)
 XM_DEVICE float apply_act(float x, int act) {
   if (act == XM_ACT_RELU) return fmaxf(x, 0.0f);

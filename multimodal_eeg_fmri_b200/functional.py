@@ -629,11 +629,12 @@ class TransformerTail(torch.autograd.Function):
             dx1, dao, dn2w, dn2b, dbo = ops.resid_ln_bwd(dh2, dxs, x2, n2w, m2, r2, p, s_ao)
             datt = ops.linear_dgrad(dao, wo_r, round_out=True)
             dwo, _ = ops.linear_wgrad(dao, att.view(M, D), need_bias=False)
-            dqkv = ops.attn_fused_bwd(datt.view(B, L, D), qkv.view(B, L, 3 * D), att.view(B, L, D), lse, nhead, scale, p, s_attn,
-                                      round_out=True)
+            # the in-projection's bias gradient (column sums of dqkv) is accumulated where dq / dk / dv leave tensor memory
+            dqkv, dbqkv = ops.attn_fused_bwd(datt.view(B, L, D), qkv.view(B, L, 3 * D), att.view(B, L, D), lse, nhead, scale, p,
+                                             s_attn, round_out=True, need_bias=True)
             dqkv = dqkv.view(M, 3 * D)
             dh1 = ops.linear_dgrad(dqkv, wqkv_r)
-            dwqkv, dbqkv = ops.linear_wgrad(dqkv, h1)
+            dwqkv, _ = ops.linear_wgrad(dqkv, h1, need_bias=False)
             need_in = l > 0 or ctx.needs_input_grad[0]
             dxs, dprev, dn1w, dn1b, dbprev = ops.resid_ln_bwd(dh1, dx1, x1, n1w, m1, r1, p, s_in, need_da=need_in)
             grads[l * 12:(l + 1) * 12] = [dn1w, dn1b, dwqkv, dbqkv, dwo, dbo, dn2w, dn2b, dw1, db1, dw2, db2]

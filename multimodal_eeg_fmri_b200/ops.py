@@ -701,17 +701,20 @@ def attn_fused_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
     return out, lse
 
 
-def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
+def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False, need_bias=False):
+    """-> dqkv, or (dqkv, dbias (3d)) with need_bias: the column sums of dqkv (the in-projection's bias gradient)
+    accumulated inside the kernels."""
     _chk(dout, qkv, out, lse)
     dout, out = dout.contiguous(), out.contiguous()
     B, L, E = qkv.shape
     dh = E // 3 // nhead
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
+    part = torch.empty(_lib.lib().xm_attn_fused_bwd_nblk(), E, device=qkv.device, dtype=torch.float32) if need_bias else None
     _w(14.0 * B * nhead * L * L * dh, 4.0 * (3 * qkv.numel() + 3 * dout.numel()))
-    _call("xm_attn_fused_bwd_f32", _p(dout), _p(qkv), _p(out), _p(lse), _p(dqkv), _p(delta), B, L, nhead, dh, float(scale),
-          float(drop_p), int(seed), int(round_out), _stream())
-    return dqkv
+    _call("xm_attn_fused_bwd_f32", _p(dout), _p(qkv), _p(out), _p(lse), _p(dqkv), _p(delta), _p(part), B, L, nhead, dh,
+          float(scale), float(drop_p), int(seed), int(round_out), _stream())
+    return (dqkv, colsum(part)) if need_bias else dqkv
 
 
 def attn_general_supported(L: int, dh: int) -> bool:

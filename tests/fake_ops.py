@@ -345,12 +345,13 @@ def attn_fused_fwd(qkv, nhead, scale, drop_p=0.0, seed=0, round_out=True):
     return out, lse
 
 
-def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False):
+def attn_fused_bwd(dout, qkv, out, lse, nhead, scale, drop_p=0.0, seed=0, round_out=False, need_bias=False):
     _nodrop(drop_p)
     B, L, E = qkv.shape
     q, k, _ = _attn_parts(qkv, nhead)
     probs = torch.exp(q @ k.transpose(-1, -2) * scale - lse.reshape(B, nhead, L, 1).double())
-    return _attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
+    dqkv = _attn_bwd(dout, qkv, probs.reshape(B * nhead, L, L), lse, nhead, scale, drop_p, seed, round_out)
+    return (dqkv, dqkv.double().sum((0, 1)).float()) if need_bias else dqkv
 
 
 def attn_general_supported(L, dh):

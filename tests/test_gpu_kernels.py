@@ -422,6 +422,10 @@ def test_fused_attention_fwd_bwd(ops, B, L, H):
     dqkv = ops.attn_fused_bwd(dout, qkv, out, lse, H, scale, 0.0, 0)
     for name, a, b in zip("qkv", dqkv.chunk(3, dim=-1), gx.chunk(3, dim=-1)):
         assert_close_rel(a, b, 2e-3, f"fused d{name}", atol=1e-6)
+    # the in-projection's bias gradient, accumulated inside the kernels: same dqkv, column sums of it (rows past L excluded)
+    dqkv2, dbias = ops.attn_fused_bwd(dout, qkv, out, lse, H, scale, 0.0, 0, need_bias=True)
+    assert torch.equal(dqkv2, dqkv)
+    assert_close_rel(dbias, dqkv.double().sum((0, 1)), 1e-5, "fused in-projection bias gradient", atol=1e-5)
 
 
 @pytest.mark.parametrize("B,L,H,pdrop", [(2, 250, 4, 0.3), (3, 100, 2, 0.1), (2, 256, 1, 0.5), (2, 500, 2, 0.3)])

@@ -71,8 +71,8 @@ def main():
                                "mma_wait_other_per_tile": float(m[:, 5].sum() / per),
                                "transform_busy_per_chunk_g0": float((g0[4:, 4] - g0[4:, 3]).mean()),
                                "transform_wait_per_chunk_g0": float((g0[4:, 3] - g0[4:, 2]).mean()),
-                               "transform_busy_per_chunk_g1": float((g1[4:, 4] - g1[4:, 3]).mean()),
-                               "transform_wait_per_chunk_g1": float((g1[4:, 3] - g1[4:, 2]).mean())}
+                               "transform_busy_per_chunk_g1": float((g1[4:, 4] - g1[4:, 3]).mean()) if len(g1) > 4 else None,
+                               "transform_wait_per_chunk_g1": float((g1[4:, 3] - g1[4:, 2]).mean()) if len(g1) > 4 else None}
     print(json.dumps(out, indent=1))
 
 
