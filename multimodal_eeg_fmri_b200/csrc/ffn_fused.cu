@@ -44,6 +44,7 @@ constexpr int kD = 128, kChunk = 128, kMaxChunks = 8;
 constexpr int kTile = 16384;  // 128 rows x 32 fp32, SWIZZLE_128B
 constexpr int kXfWarps = 16;
 constexpr int kThreads = 64 + 32 * kXfWarps;
+constexpr int kFwdThreads = kThreads + 128;  // forward: + 4 output warps (one per TMEM lane quadrant)
 constexpr int kFwdRing = 5, kBwdRing = 9;
 constexpr int kBiasBytes = (kMaxChunks * kChunk + kD) * 4;  // b1 (+ b2) staged in shared memory
 constexpr int kFwdSmem = 2 * 4 * kTile + kFwdRing * kTile + kBiasBytes + 1024;
@@ -254,9 +255,9 @@ XM_DEVICE void stage_block(const CUtensorMap* tm, uint8_t* sb, int lane, const u
 struct FwdBars {
   uint64_t x_full[2], x_empty[2];
   uint64_t w_full[kFwdRing], w_empty[kFwdRing];
-  uint64_t h_full[2], a_ready[2];  // per H buffer
-  uint64_t y_full, y_free;         // (a barrier may only have waiters that consume EVERY phase: a waiter that skips
-                                   // phases aliases on the parity -- all 16 transform warps wait on every one of these)
+  uint64_t h_full[2], a_ready[2];  // per H buffer (a barrier may only have waiters that consume EVERY phase: a waiter
+                                   // that skips phases aliases on the parity -- all 16 transform warps wait on these)
+  uint64_t y_full[2], y_free[2];   // per Y accumulator (tile parity); waited on by the four output warps / the MMA warp
 };
 
 // Forward.  The MMA warp runs ONE software pipeline over the CTA's whole chunk sequence n = 0, 1, ... (tile = n / nc,
@@ -265,9 +266,12 @@ struct FwdBars {
 // transform of chunk n has exactly the time of [M2(n - 1) M1(n + 1)] -- M1(n) ends where that slot starts and M2(n) opens
 // the next one -- so its LATENCY, not its throughput, decides whether the MMA warp waits.  (Two groups of 8 warps
 // alternating chunks had the same throughput but never overlapped: each group's chunk took ~6.5k clk of a 4.9k slot,
-// profiles/r2_ffn_fwd_trace_v4.json; ncu: tensor pipe 35 %, issue 45 %, nothing saturated.)  They also write the tile.
+// profiles/r2_ffn_fwd_trace_v4.json; ncu: tensor pipe 35 %, issue 45 %, nothing saturated.)
+// The tile's output leaves through FOUR EXTRA WARPS and two Y accumulators (tile parity): when the transform warps
+// wrote y themselves every tile boundary cost ~8k of 23.7k clk -- M2 of the last chunk had to finish, the row-per-lane
+// global stores block their warp, and the next tile's first chunk waited behind both (trace of that version).
 template <bool TRACE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                const __grid_constant__ CUtensorMap tmW2, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -290,13 +294,13 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ptx::mbar_init(&bar.x_empty[i], 1);
       ptx::mbar_init(&bar.h_full[i], 1);
       ptx::mbar_init(&bar.a_ready[i], kXfWarps);
+      ptx::mbar_init(&bar.y_full[i], 1);
+      ptx::mbar_init(&bar.y_free[i], 4);
     }
-    ptx::mbar_init(&bar.y_full, 1);
     for (int i = 0; i < kFwdRing; ++i) {
       ptx::mbar_init(&bar.w_full[i], 1);
       ptx::mbar_init(&bar.w_empty[i], 1);
     }
-    ptx::mbar_init(&bar.y_free, kXfWarps);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -307,7 +311,6 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tY = tmem + 256u;
   const int my_tiles = p.tiles > (int)blockIdx.x ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int N = my_tiles * p.nc;  // chunks this CTA processes
 
@@ -415,10 +418,11 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const long long t0 = TRACE ? clock64() : 0;
         const int it = n / p.nc, c = n - it * p.nc, b = n & 1;
         const uint32_t tH = tmem + (uint32_t)(b * 128);
-        twait<TRACE>(&bar.a_ready[b], ((uint32_t)n >> 1) & 1u, ta);  // group b has written A over H
+        const uint32_t tY = tmem + 256u + (uint32_t)((it & 1) * 128);
+        twait<TRACE>(&bar.a_ready[b], ((uint32_t)n >> 1) & 1u, ta);  // the transform warps have written A over H
         ptx::tc_fence_after_sync();
         if (c == 0) {
-          twait<TRACE>(&bar.y_free, ((uint32_t)it & 1u) ^ 1u, ta);  // the previous tile's Y has been read out
+          twait<TRACE>(&bar.y_free[it & 1], (((uint32_t)it >> 1) & 1u) ^ 1u, ta);  // tile it - 2 has been read out of this Y
           ptx::tc_fence_after_sync();
         }
 #pragma unroll
@@ -431,7 +435,7 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             for (int k8 = 0; k8 < 4; ++k8)
               mma_tf32_ts(tY, tH + (uint32_t)(kb * 32 + k8 * 8), db + (uint64_t)(k8 * 2), idesc, (kb | k8) ? 1u : (c ? 1u : 0u));
             ptx::mma_commit(&bar.w_empty[st]);
-            if (kb == 3 && c == p.nc - 1) ptx::mma_commit(&bar.y_full);  // the tile's output is complete
+            if (kb == 3 && c == p.nc - 1) ptx::mma_commit(&bar.y_full[it & 1]);  // the tile's output is complete
           }
           __syncwarp();
           if (++st == kFwdRing) { st = 0; ph ^= 1u; }
@@ -445,9 +449,9 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (n + 2 < N) mma_m1(n + 2);
       }
     }
-  } else {
+  } else if (warp < 2 + kXfWarps) {
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int cb = (warp - 2) >> 2;    // which 32 of the chunk's (and of the output's) 128 columns
+    const int cb = (warp - 2) >> 2;    // which 32 of the chunk's 128 columns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float cs = kTruncComp * p.dscale;
     int tn = 0;
@@ -483,16 +487,26 @@ ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         t[0] = 4; t[1] = n; t[2] = t0; t[3] = t1; t[4] = clock64(); t[5] = 0;
         tn += 6;
       }
-      if (c == p.nc - 1) {
-        // ---- the tile's output: y = Y + b2 (32 columns per warp)
-        ptx::mbar_wait(&bar.y_full, (uint32_t)it & 1u);
-        ptx::tc_fence_after_sync();
+    }
+  } else {
+    // ---- output warps: y = Y + b2, one TMEM lane quadrant (32 rows) each, 32 columns at a time
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < my_tiles; ++it) {
+      const long long row = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + q * 32 + lane;
+      const uint32_t tY = tmem + 256u + (uint32_t)((it & 1) * 128) + lane_base;
+      ptx::mbar_wait(&bar.y_full[it & 1], ((uint32_t)it >> 1) & 1u);
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
         uint32_t r0[32];
-        ptx::tmem_ld_32x32(tY + (uint32_t)(cb * 32) + lane_base, r0);
+        ptx::tmem_ld_32x32(tY + (uint32_t)(cb * 32), r0);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar.y_free);  // Y is in registers: the next tile may overwrite it
+        if (cb == 3) {
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bar.y_free[it & 1]);  // Y is in registers: tile it + 2 may overwrite it
+        }
 #pragma unroll
         for (int e = 0; e < 32; ++e) r0[e] = __float_as_uint(__uint_as_float(r0[e]) + sb2[cb * 32 + e]);
         if (row < p.M) store_row32(p.y + row * kD + cb * 32, r0);
@@ -815,12 +829,12 @@ int xm_ffn_fused_fwd_f32(const float* x, const float* w1, const float* b1, const
     p.dbg = g_ffn_dbg;
     if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_fwd_kernel<true>, ffn::kFwdSmem);
     if (rc != XM_OK) return rc;
-    ffn::ffn_fwd_kernel<true><<<ctas, ffn::kThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
+    ffn::ffn_fwd_kernel<true><<<ctas, ffn::kFwdThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
     return check_launch();
   }
   if (rc == XM_OK) rc = ffn::set_smem(ffn::ffn_fwd_kernel<false>, ffn::kFwdSmem);
   if (rc != XM_OK) return rc;
-  ffn::ffn_fwd_kernel<false><<<ctas, ffn::kThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
+  ffn::ffn_fwd_kernel<false><<<ctas, ffn::kFwdThreads, ffn::kFwdSmem, (cudaStream_t)stream>>>(mx, m1, m2, p);
   return check_launch();
 }
 
