@@ -44,33 +44,47 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): ONE long-running
+    `nvidia-smi -lms 200` process, started before the warm-up steps.  (Forking a new nvidia-smi every 200 ms put its
+    driver initialisation inside the timed region: two of twelve runs of this bench lost ~90 ms of launches to it.)
+    `mark()` notes where the timed region starts; only samples taken after it are summarised."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.rows, self._proc, self._t, self._skip = index, [], None, None, 0
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
-            except Exception:  # noqa: BLE001 - sampling is best effort
-                pass
-            self._stop.wait(0.2)
+        for line in self._proc.stdout:
+            line = line.strip()
+            if line:
+                self.rows.append([c.strip() for c in line.split(",")])
 
-    def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+    def start(self):
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:  # noqa: BLE001 - sampling is best effort
+            self._proc = None
         return self
 
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+    def mark(self):
+        self._skip = len(self.rows)
+
+    def stop(self):
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self._proc.kill()
+            if self._t is not None:
+                self._t.join(timeout=5)
+        rows = self.rows[self._skip:]
+        self.rows = rows if rows else self.rows[-2:]  # a very short timed region may fall between two samples
 
     def summary(self):
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -339,14 +353,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local).start()  # started before the warm-up: its start-up cost stays outside the timed region
     for _ in range(max(args.warmup, 3)):
         trainer.step(*devt)
     barrier()
 
     # ---- timed region 1: device-resident inputs
     n0 = ops.launch_count()
-    with ClockSampler(local) as clocks:
-        ms_total = _timed(lambda: trainer.step(*devt), args.steps, barrier, dev, world)
+    clocks.mark()
+    ms_total = _timed(lambda: trainer.step(*devt), args.steps, barrier, dev, world)
+    clocks.stop()
     launches = ops.launch_count() - n0
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
@@ -365,7 +381,9 @@ def run_ours(args):
     # (the public end-to-end call: copies batch k+1 from pinned host memory while batch k trains; every step's
     #  inputs cross PCIe inside the timed region and every step's loss is read back)
     if args.e2e_steps <= 0:
-        args.e2e_steps = max(args.steps, 10)
+        # the first batch's host->device copy cannot hide behind a previous step (15 ms at 852 MB): 30 steps keep that
+        # pipeline fill at ~0.5 ms per step instead of 1.5 ms with 10 (an epoch of the reference has hundreds of steps)
+        args.e2e_steps = max(args.steps, 30)
     trainer.steps_from_host([host, host])
     ms_e2e = _timed(lambda: trainer.steps_from_host([host] * args.e2e_steps), 1, barrier, dev, world)
     e2e_value = world * B * args.e2e_steps / (ms_e2e * 1e-3)
@@ -496,7 +514,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="per-GPU batch (paired samples)")
     ap.add_argument("--encoder", default="v4", choices=["v4", "lite"])
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end region (0: max(--steps, 10))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end region (0: max(--steps, 30))")
     ap.add_argument("--cpu-batch", type=int, default=0, help="paired samples per CPU-baseline step (0: the GPU arm's batch if host memory allows)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")

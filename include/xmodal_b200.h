@@ -417,6 +417,10 @@ int xm_sumsq_partials_f32(const float* g, int64_t n, double* partials, void* str
 int xm_clip_adamw_f32(float* p, float* g, float* m, float* v, int64_t n, const double* partials, int nblk, float max_norm,
                       float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float* norm_out,
                       void* stream);
+/* dst[dst_off[t] .. + numel[t]) = src[t][0 .. numel[t]) for t < n_tensors, one launch per 96 tensors: gathers the
+ * per-parameter gradient tensors autograd produces into the flat bucket.  src / dst_off / numel are HOST arrays. */
+int xm_gather_flat_f32(const void* const* src, const int64_t* dst_off, const int64_t* numel, int n_tensors, float* dst,
+                       void* stream);
 
 /* ------------------------------------------------------------------ diagnostics (not on the product path)
  * Dump the raw shared-memory image of one TMA box {32,32} loaded at (c0, c1) from a (rows, cols)

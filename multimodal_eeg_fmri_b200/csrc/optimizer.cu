@@ -74,6 +74,32 @@ clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
   }
 }
 
+
+// Gather of per-parameter gradient tensors into the flat bucket in ONE launch (autograd hands every parameter its own
+// gradient tensor; accumulating each into a preset view of the bucket costs one tiny add kernel per parameter and
+// step).  blockIdx.y = tensor, blockIdx.x strides over its elements.
+constexpr int kMaxGather = 96;
+struct GatherArgs {
+  const float* src[kMaxGather];
+  long long dst_off[kMaxGather];
+  long long numel[kMaxGather];
+};
+__global__ void __launch_bounds__(kThreads) gather_flat_kernel(const __grid_constant__ GatherArgs a, float* __restrict__ dst) {
+  const int t = blockIdx.y;
+  const float* __restrict__ s = a.src[t];
+  float* __restrict__ d = dst + a.dst_off[t];
+  const long long n = a.numel[t];
+  if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kThreads)
+      reinterpret_cast<float4*>(d)[i] = reinterpret_cast<const float4*>(s)[i];
+    if (blockIdx.x == 0)
+      for (long long i = (n4 << 2) + threadIdx.x; i < n; i += kThreads) d[i] = s[i];
+  } else {
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) d[i] = s[i];
+  }
+}
+
 }  // namespace opt
 }  // namespace xm
 
@@ -103,4 +129,28 @@ extern "C" int xm_clip_adamw_f32(float* p, float* g, float* m, float* v, int64_t
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   opt::clip_adamw_kernel<<<(int)blocks, opt::kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, partials, nblk, a, norm_out);
   return check_launch();
+}
+
+extern "C" int xm_gather_flat_f32(const void* const* src, const int64_t* dst_off, const int64_t* numel, int n_tensors, float* dst,
+                                  void* stream) {
+  if (!src || !dst_off || !numel || !dst || n_tensors <= 0) return XM_ERR_INVALID;
+  for (int t0 = 0; t0 < n_tensors; t0 += opt::kMaxGather) {
+    const int nt = n_tensors - t0 < opt::kMaxGather ? n_tensors - t0 : opt::kMaxGather;
+    opt::GatherArgs a{};
+    long long biggest = 0;
+    for (int i = 0; i < nt; ++i) {
+      if (!src[t0 + i] || numel[t0 + i] < 0 || dst_off[t0 + i] < 0) return XM_ERR_INVALID;
+      a.src[i] = (const float*)src[t0 + i];
+      a.dst_off[i] = dst_off[t0 + i];
+      a.numel[i] = numel[t0 + i];
+      if (numel[t0 + i] > biggest) biggest = numel[t0 + i];
+    }
+    long long bx = (biggest / 4 + opt::kThreads - 1) / opt::kThreads;
+    if (bx < 1) bx = 1;
+    if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+    opt::gather_flat_kernel<<<dim3((unsigned)bx, (unsigned)nt), opt::kThreads, 0, (cudaStream_t)stream>>>(a, dst);
+    int rc = check_launch();
+    if (rc != XM_OK) return rc;
+  }
+  return XM_OK;
 }

@@ -1015,6 +1015,24 @@ def roi_corrcoef(x, prepared=False):
 
 
 # ------------------------------------------------------------------ optimizer step over one flat bucket
+def gather_flat_(dst, tensors, offsets):
+    """dst[offsets[t] : offsets[t] + tensors[t].numel()] = tensors[t] (flattened), all tensors in one launch per 96:
+    the per-parameter gradients autograd produced, gathered into the flat bucket (xm_gather_flat_f32)."""
+    if not tensors:
+        return dst
+    srcs = []
+    for t in tensors:
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise _lib.XmodalError(f"expected CUDA float32 gradients, got {t.device} {t.dtype}")
+        srcs.append(t if t.is_contiguous() else t.contiguous())
+    n = len(srcs)
+    off = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+    num = (ctypes.c_int64 * n)(*[int(t.numel()) for t in srcs])
+    _w(0.0, 8.0 * sum(t.numel() for t in srcs))
+    _call("xm_gather_flat_f32", _ptr_array([t.data_ptr() for t in srcs]), off, num, n, _p(dst), _stream())
+    return dst
+
+
 def clip_adamw_(p, g, m, v, step, lr, weight_decay, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8):
     """In place on flat fp32 buffers: clip_grad_norm_(max_norm) + torch.optim.AdamW update for 1-based `step`.
     -> the pre-clip total gradient norm (1-element device tensor)."""

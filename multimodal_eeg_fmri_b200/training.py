@@ -141,11 +141,18 @@ class PairedTrainer:
         self.flat_grad = torch.zeros(o, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(o, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(o, device=dev, dtype=torch.float32)
+        self._offs = offs
+        self._grad_views = []
         for p, o in zip(self.params, offs):
             view = self.flat_param[o:o + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
-            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+            # Gradients: autograd hands every parameter its own tensor (p.grad is None during backward, so nothing is
+            # accumulated); ONE gather launch per bucket copies them into the flat buffer (ops.gather_flat_) and p.grad
+            # then points at its range of it.  Presetting p.grad to the views instead costs one tiny add kernel per
+            # parameter and step (95 of ~300 launches, profiles/r2_launches_v9.md).
+            self._grad_views.append(self.flat_grad[o:o + p.numel()].view_as(p))
+            p.grad = None
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, (0.9, 0.999), 1e-8
         self.step_count = 0
         self.last_grad_norm = None  # pre-clip total norm of the last step (device scalar)
@@ -160,10 +167,25 @@ class PairedTrainer:
             for p in self._early_params:
                 p.register_post_accumulate_grad_hook(self._early_grad_ready)
 
+    def _gather(self, lo: int, hi: int) -> None:
+        """Parameters [lo, hi): their freshly produced gradient tensors -> the flat buffer (one launch), on the current
+        stream; p.grad then aliases the buffer."""
+        ps = self.params[lo:hi]
+        have = [(p.grad, o) for p, o in zip(ps, self._offs[lo:hi]) if p.grad is not None]
+        for p, v in zip(ps, self._grad_views[lo:hi]):
+            if p.grad is None:
+                v.zero_()  # a parameter the loss did not reach
+        if have:
+            ops.gather_flat_(self.flat_grad, [g for g, _ in have], [o for _, o in have])
+        for p, v in zip(ps, self._grad_views[lo:hi]):
+            p.grad = v
+
     def _early_grad_ready(self, _param) -> None:
-        """Runs on the stream that accumulated the gradient: after the last early parameter, mark the early bucket ready."""
+        """Runs on the stream that produced the gradient: after the last early parameter, gather the early bucket there
+        and mark it ready."""
         self._early_left -= 1
         if self._early_left == 0:
+            self._gather(0, len(self._early_params))
             self._early_event.record(torch.cuda.current_stream())
 
     def _allreduce_gradients(self) -> None:
@@ -182,7 +204,8 @@ class PairedTrainer:
         """eeg: raw recordings (R, C, n) when a window spec was given (gathered on the device into
         B = R*n_win channels-last windows), else windows (B, C, T); conn None: connectivity derived on the device
         from roi_series.  Returns the loss (device scalar, this rank's share of the global loss)."""
-        self.flat_grad.zero_()
+        for p in self.params:
+            p.grad = None
         if self.window is not None:
             split = bool(getattr(self.model.eeg_encoder, "wants_unrounded_input", False))  # 3-pass first conv
             x = ops.window_gather(eeg, self.window, self.hop or self.window, channels_last=True, round_out=not split,
@@ -192,6 +215,8 @@ class PairedTrainer:
             loss = self.model(eeg, roi_series, conn)
         self._early_left = len(self._early_params)
         loss.backward()
+        early_done = self._early_event is not None and self._early_left == 0
+        self._gather(len(self._early_params) if early_done else 0, len(self.params))
         if self.ctx.active:
             self._allreduce_gradients()
         self.step_count += 1

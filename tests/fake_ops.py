@@ -476,6 +476,12 @@ def zscore(x, eps=1e-8):
     return out.reshape(x.shape).float()
 
 
+def gather_flat_(dst, tensors, offsets):
+    for t, o in zip(tensors, offsets):
+        dst[o:o + t.numel()].copy_(t.reshape(-1))
+    return dst
+
+
 FAKES = [n for n, v in list(globals().items()) if callable(v) and not n.startswith("_") and n not in ("F", "torch", "annotations")]
 
 
