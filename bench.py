@@ -181,13 +181,22 @@ STEP_TFLOP_PER_4096 = 4.36 + 0.13 + 0.013
 def _timed(fn, steps, barrier, dev, world):
     import torch
     import torch.distributed as dist
+    import gc
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(steps):
-        fn()
-    e1.record()
-    barrier()
+    # Python's cyclic collector is kept out of the timed region: a generation-2 pass in the launch thread right after
+    # the opening synchronize (empty GPU queue) stalled the first timed step by 100 - 200 ms in 3 of 20 runs
+    # (tools/step_jitter.py, profiles/r2_step_jitter.txt); the step itself leaves no cyclic garbage (tools/gc_probe.py)
+    gc.collect()
+    gc.disable()
+    try:
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+    finally:
+        gc.enable()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -149,6 +149,16 @@ int xm_conv1d_pack_weight_f32(const float* w, int64_t Cout, int64_t Cin, int64_t
 int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,
                       int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy, int round_out,
                       void* stream);
+/* The same convolution that also emits the BatchNorm batch statistics of its output: stat_part
+ * (xm_conv1d_fwd_stat_rows(), Cout, 2) doubles = per-(CTA, lane quadrant) column sums and sums of squares of y over
+ * (B, T), the `partials` argument of xm_bn_finalize_stats -- accumulated in the epilogue warps (fp32 butterfly per
+ * 32-row block, fp64 across blocks), so xm_bn_partial_stats_f32's pass over y is not needed
+ * (EEG_CODE/enhanced_models_v4.py:128-144: Conv1d -> BatchNorm1d).  Cout <= the N tile (256), y 16-B aligned, ldy % 4 == 0;
+ * XM_ERR_UNSUPPORTED otherwise (callers then use the two-kernel path). */
+int xm_conv1d_fwd_stat_rows(void);
+int xm_conv1d_fwd_stats_f32(const float* x, const float* wk, const float* bias, float* y, double* stat_part, int64_t B,
+                            int64_t Cin, int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy,
+                            int round_out, void* stream);
 /* dx (B,T,Cin) from dy (B,T,Cout) */
 int xm_conv1d_dgrad_f32(const float* dy, const float* wt, float* dx, int64_t B, int64_t Cin, int64_t Cout, int64_t T,
                         int64_t taps, int64_t lddy, int64_t ldt, int64_t lddx, int round_out, void* stream);
@@ -279,7 +289,8 @@ int xm_infonce_dgrad_f32(const float* g3, const float* f3, float* dx, int64_t Ml
  * precise != 0: G is split hi/lo on the fly and the contraction runs in the 3-pass mode (fp32-accurate, as
  * xm_infonce_dgrad_f32); 0: one tf32 pass.  The sum over the global batch is accumulated in fp32 registers per
  * 128-column chunk.  D == 128, Ml % 128 == Ng % 128 == diag_off % 128 == 0 (xm_infonce_bwd_fused_supported).
- * workspace: xm_infonce_bwd_fused_workspace(Ng, D) floats, 32-B aligned (column scales + the transposed unit vectors). */
+ * workspace: xm_infonce_bwd_fused_workspace(Ml, Ng, D) floats, 32-B aligned (column scales, the transposed unit vectors,
+ * per-unit partial outputs when a row tile is split over more than two units).  Results are bit-reproducible. */
 int xm_infonce_bwd_fused_supported(int64_t Ml, int64_t Ng, int64_t D, int64_t diag_off);
 /* Forward of the same kernel family: lse_ef[i] = logsumexp_j S[i, j] (my e x all f), lse_fe[i] = logsumexp_j S'[i, j] (my f x
  * all e), diag[i] = S[i, i + diag_off], scores in the 3-pass mode, nothing of size (Ml, Ng) written; same shape rules.
@@ -288,7 +299,7 @@ int64_t xm_infonce_lse_fused_workspace(int64_t Ml, int64_t Ng);
 int xm_infonce_lse_fused_f32(const float* e3, const float* f3, const float* e3_all, const float* f3_all, float* lse_ef,
                              float* lse_fe, float* diag, int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off,
                              float* workspace, void* stream);
-int64_t xm_infonce_bwd_fused_workspace(int64_t Ng, int64_t D);
+int64_t xm_infonce_bwd_fused_workspace(int64_t Ml, int64_t Ng, int64_t D);
 int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_all, const float* f3_all, const float* lse_ef,
                              const float* lse_fe, const float* lse_ef_all, const float* lse_fe_all, float* de, float* df,
                              int64_t Ml, int64_t Ng, int64_t D, float inv_tau, int64_t diag_off, float coef, int precise,

@@ -25,7 +25,11 @@ _CTYPES = {
 
 
 class XmodalError(RuntimeError):
-    pass
+    """status: the XM_ERR_* code of the failed call (-2 = XM_ERR_UNSUPPORTED), None when raised by the Python layer."""
+
+    def __init__(self, msg, status=None):
+        super().__init__(msg)
+        self.status = status
 
 
 def _parse_type(tok: str):
@@ -75,7 +79,9 @@ def check(status: int, what: str) -> None:
     if status != 0:
         dll = lib()
         msg = dll.xm_strerror(status).decode()
-        raise XmodalError(f"{what} failed: {msg} (status {status}, cuda error {dll.xm_last_cuda_error()})")
+        # (raised without binding it to a local: `err = ...; raise err` would tie the exception to this frame and the
+        #  frame to the exception -- a reference cycle that keeps the caller's tensors alive until a garbage collection)
+        raise XmodalError(f"{what} failed: {msg} (status {status}, cuda error {dll.xm_last_cuda_error()})", int(status))
 
 
 def call(name: str, *args) -> None:

@@ -380,14 +380,17 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ dout, const float* _
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
                                   float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, long long M, int D,
-                                  int act, float drop_scale, uint32_t drop_thresh, uint64_t seed) {
-  extern __shared__ float sm[];  // 2 * D
-  float* sg = sm;
-  float* sb = sm + D;
-  for (int d = threadIdx.x; d < 2 * D; d += blockDim.x) sm[d] = 0.f;
-  __syncthreads();
+                                  int act, float drop_scale, uint32_t drop_thresh, uint64_t seed, int per_warp) {
+  // per_warp: every warp owns a private (2, D) accumulator (element d is only ever touched by lane d % 32 of that warp,
+  // in row order) and the block adds the warps in a fixed order -> bit-reproducible partials.  Wide rows (D > 768: the
+  // private copies would not fit 48 KB) share one accumulator through shared-memory atomics.
+  extern __shared__ float sm[];  // per_warp ? warps * 2 * D : 2 * D
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  float* sg = sm + (per_warp ? (threadIdx.x >> 5) * 2 * D : 0);
+  float* sb = sg + D;
+  for (int d = threadIdx.x; d < (per_warp ? wpb : 1) * 2 * D; d += blockDim.x) sm[d] = 0.f;
+  __syncthreads();
   for (long long row = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
     const float* xr = x + row * D;
@@ -399,8 +402,13 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ dout, const float* _
       float g = dr[d];
       if (drop_thresh) g = dropout_keep((uint64_t)(row * D + d), seed, drop_thresh) ? g * drop_scale : 0.f;
       const float dz = g * act_grad(z, act);
-      atomicAdd(&sg[d], dz * xh);
-      atomicAdd(&sb[d], dz);
+      if (per_warp) {
+        sg[d] += dz * xh;
+        sb[d] += dz;
+      } else {
+        atomicAdd(&sg[d], dz * xh);
+        atomicAdd(&sb[d], dz);
+      }
       const float dzg = dz * gamma[d];
       s1 += dzg;
       s2 += dzg * xh;
@@ -418,8 +426,13 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ dout, const float* _
   }
   __syncthreads();
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    dgamma_part[(long long)blockIdx.x * D + d] = sg[d];
-    dbeta_part[(long long)blockIdx.x * D + d] = sb[d];
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (per_warp ? wpb : 1); ++w) {
+      a += sm[w * 2 * D + d];
+      b += sm[w * 2 * D + D + d];
+    }
+    dgamma_part[(long long)blockIdx.x * D + d] = a;
+    dbeta_part[(long long)blockIdx.x * D + d] = b;
   }
 }
 
@@ -1248,8 +1261,9 @@ int xm_ln_act_bwd_f32(const float* dout, const float* x, const float* gamma, con
   float sc;
   uint32_t th;
   drop_consts(drop_p, sc, th);
-  ln_act_bwd_kernel<<<xm_ln_nblk(M), 256, 2 * D * sizeof(float), (cudaStream_t)stream>>>(
-      dout, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, M, (int)D, act, sc, th, seed);
+  const int per_warp = D <= 768;
+  ln_act_bwd_kernel<<<xm_ln_nblk(M), 256, (per_warp ? 8 : 1) * 2 * D * sizeof(float), (cudaStream_t)stream>>>(
+      dout, x, gamma, beta, mean, rstd, dx, dgamma_part, dbeta_part, M, (int)D, act, sc, th, seed, per_warp);
   return check_launch();
 }
 

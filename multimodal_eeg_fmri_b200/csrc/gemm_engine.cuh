@@ -84,6 +84,9 @@ struct GemmParams {
   float alpha;
   int act;
   int round_tf32;
+  double* colstat_part;  // EPI_ROWMAJOR with TMA store, bn % 64 == 0, ny * bn <= 256, may be NULL: (gridDim.x * 4, N, 2) per-(CTA, lane quadrant)
+                         // column sums and sums of squares of the OUTPUT over the rows this CTA produced -- the
+                         // BatchNorm batch statistics of a conv output without a pass over it (xm_bn_finalize_stats input)
   // InfoNCE epilogues
   const float* lse_row;
   const float* lse_col;
@@ -394,6 +397,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int ait = 0;  // mirrors the MMA warp's accumulator-set counter
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t sum = tmem_base + (uint32_t)(2 * acc_cols) + lane_base;  // fp32 running sum (acc_chunk only)
+    double cstat[4][2];  // column statistics of this warp's (up to 4) 32-column chunks: lane j owns column c0 + j
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cstat[i][0] = cstat[i][1] = 0.0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       bool add_sum = false;
@@ -513,6 +519,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
               }
             }
+            if (EPI == EPI_ROWMAJOR && p.colstat_part != nullptr) {
+              // batch statistics of the output: column sums over this warp's 32 rows (rows past M excluded), then
+              // one fp64 add per lane and chunk -- rounding of the tile-level fp32 sums stays at the 1e-7 level
+              uint32_t u[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) u[j] = row_ok ? __float_as_uint(v[j]) : 0u;
+              const float s1 = warp_column_sums(u, lane);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) u[j] = row_ok ? __float_as_uint(v[j] * v[j]) : 0u;
+              const float s2 = warp_column_sums(u, lane);
+              const int slot = t.by * (p.bn / (32 * NPARTS)) + (c0 - part * 32) / (32 * NPARTS);  // (N tile, chunk of this warp)
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i == slot) {
+                  cstat[i][0] += (double)s1;
+                  cstat[i][1] += (double)s2;
+                }
+            }
             uint8_t* sb = stg + (NBUF == 2 ? (chunk_ctr & 1) * 4096 : 0);
             if (lane == 0) ptx::bulk_wait_read<NBUF - 1>();  // the store that last read this buffer has drained it
             __syncwarp();
@@ -575,6 +599,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+    }
+    if (EPI == EPI_ROWMAJOR && p.colstat_part != nullptr) {
+      double* dst = p.colstat_part + (long long)(blockIdx.x * 4 + q) * p.N * 2;
+      const int per_tile = p.bn / (32 * NPARTS);  // 32-column chunks of one N tile that this warp owns (host: ny * per_tile <= 4)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int by = i / per_tile, ch = i - by * per_tile;
+        const int col = by * p.n_stride + part * 32 + ch * 32 * NPARTS + lane;
+        if (by < p.ny && col < p.N) {
+          dst[col * 2 + 0] = cstat[i][0];
+          dst[col * 2 + 1] = cstat[i][1];
+        }
+      }
     }
     if (lane == 0) ptx::bulk_wait_all();  // staged tiles fully written before the CTA (and its smem) retires
   }

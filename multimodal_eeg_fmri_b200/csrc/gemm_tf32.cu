@@ -96,6 +96,9 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
       (tc.stride_bytes[0] & 15) == 0 && (tc.stride_bytes[1] & 15) == 0 && !((p.bn & 31) && grid.y > 1))
     p.tma_store = 1;
   if (!p.tma_store && epi != EPI_LSE && p.c == nullptr) return XM_ERR_INVALID;
+  if (p.colstat_part != nullptr && (!p.tma_store || epi != EPI_ROWMAJOR || p.taps_n != 1 || (p.bn & 63) ||
+                                    (int)grid.y * p.bn > 256))  // each epilogue warp keeps <= 4 (N tile, 32-column chunk) sums
+    return XM_ERR_UNSUPPORTED;
   p.b_halo = 0;
   p.b_blk_bytes = 0;
   if (p.taps_n > 1 && p.b.mn_major && p.n_peers == 0 && g_conv_halo) {
@@ -487,7 +490,7 @@ int xm_conv1d_pack_weight_f32(const float* w, int64_t Cout, int64_t Cin, int64_t
 //   out[b, t, n] = sum_tap sum_k in[b, t + dir*(tap - pad), k] * wp[tap, n, k]  (+ bias[n])
 static int conv_like(const float* in, const float* wp, const float* bias, float* out, int64_t B, int64_t Kc, int64_t Nc,
                      int64_t T, int64_t taps, int64_t ld_in, int64_t ld_w, int64_t ld_out, int dir, int round_out,
-                     cudaStream_t st) {
+                     cudaStream_t st, double* stat_part = nullptr) {
   if (!in || !wp || !out || B <= 0 || Kc <= 0 || Nc <= 0 || T <= 0 || taps <= 0 || !(taps & 1)) return XM_ERR_INVALID;
   if ((ld_in & 3) || (ld_w & 3) || ld_in < Kc || ld_out < Nc || B > 65535) return XM_ERR_INVALID;
   const int pad = (int)(taps / 2);
@@ -525,7 +528,25 @@ static int conv_like(const float* in, const float* wp, const float* bias, float*
                  {(unsigned long long)ld_w * 4, (unsigned long long)Nc * ld_w * 4}};
   p.c_z_mul = 1;
   const TensorView3 tc = TensorView3{out, {(unsigned long long)(Nc), (unsigned long long)(T), (unsigned long long)(B)}, {(unsigned long long)(ld_out) * 4, (unsigned long long)(T * ld_out) * 4}};
+  if (stat_part != nullptr) {
+    // the statistics epilogue covers single-N-tile launches whose tiles leave through the TMA store
+    if ((reinterpret_cast<uintptr_t>(out) & 15) || (ld_out & 3)) return XM_ERR_UNSUPPORTED;
+    if (cudaMemsetAsync(stat_part, 0, (size_t)xm_conv1d_fwd_stat_rows() * Nc * 2 * sizeof(double), st) != cudaSuccess) {
+      g_last_cuda_error = (int)cudaGetLastError();
+      return XM_ERR_LAUNCH;
+    }
+    p.colstat_part = stat_part;
+  }
   return launch_gemm(EPI_ROWMAJOR, ta, tb, tc, p, dim3(t_tiles, ceil_div(Nc, p.bn), (unsigned)B), st);
+}
+
+int xm_conv1d_fwd_stat_rows(void) { return kNumSMs * 4; }
+
+int xm_conv1d_fwd_stats_f32(const float* x, const float* wk, const float* bias, float* y, double* stat_part, int64_t B,
+                            int64_t Cin, int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy,
+                            int round_out, void* stream) {
+  if (!stat_part) return XM_ERR_INVALID;
+  return conv_like(x, wk, bias, y, B, Cin, Cout, T, taps, ldx, ldk, ldy, +1, round_out, (cudaStream_t)stream, stat_part);
 }
 
 int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,

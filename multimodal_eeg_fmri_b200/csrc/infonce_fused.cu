@@ -53,7 +53,10 @@ struct Params {
   const float* colscale[2];       // scale * exp(-lse_col[j])
   float* out[2];                  // (Ml, 128)
   int diag_off;
-  int atomic;   // a row tile is split over several units: outputs are zeroed and accumulated with red.add
+  int atomic;   // a row tile is split over several units: 1 (two units) = outputs zeroed and accumulated with red.add
+                // (0 + a + b is the same in either order); 2 (more) = unit sp writes slab sp of `part`, summed in order
+  float* part[2];         // atomic == 2: (splits, Ml, 128) partial outputs per direction
+  long long part_stride;  // Ml * 128
   float c;      // log2(e) / tau
   float scale;  // coef (x truncation compensation in the single-pass mode)
   // forward (MODE_LSE) only
@@ -471,8 +474,8 @@ nce_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUt
 #pragma unroll
       for (int e = 0; e < 32; ++e) xs[e] += __uint_as_float(r[e]);
       if (cu.c == cu.c1 - 1) {  // end of the unit: this thread's 32 columns of one output row
-        float* dst = p.out[cu.dir] + (long long)(cu.row0 + rit) * kD + pidx * 32;
-        if (p.atomic) {
+        float* dst = (p.atomic == 2 ? p.part[cu.dir] + cu.sp * p.part_stride : p.out[cu.dir]) + (long long)(cu.row0 + rit) * kD + pidx * 32;
+        if (p.atomic == 1) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) atomicAdd(dst + e, xs[e]);
         } else {
@@ -544,6 +547,23 @@ nce_lse_finalize_kernel(const float* __restrict__ part0, const float* __restrict
   }
 }
 
+// out[d][i] = sum over sp of part[d][sp][i], fixed order (row tiles split over more than two units)
+__global__ void __launch_bounds__(256)
+nce_sum_parts_kernel(const float* __restrict__ p0, const float* __restrict__ p1, float* __restrict__ o0, float* __restrict__ o1,
+                     long long n4, int splits) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < 2 * n4; i += (long long)gridDim.x * blockDim.x) {
+    const int dir = i >= n4;
+    const long long j = i - dir * n4;
+    const float4* src = reinterpret_cast<const float4*>(dir ? p1 : p0);
+    float4 acc = src[j];
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = src[(long long)s * n4 + j];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dir ? o1 : o0)[j] = acc;
+  }
+}
+
 // units = direction x row tile x column split, the split chosen so that one wave of CTAs covers the SMs
 static void plan(Params& p, int64_t Ml, int64_t Ng) {
   p.row_tiles = (int)(Ml / 128);
@@ -554,7 +574,7 @@ static void plan(Params& p, int64_t Ml, int64_t Ng) {
   p.cps = (p.nc + split - 1) / split;
   split = (p.nc + p.cps - 1) / p.cps;
   p.units = 2 * p.row_tiles * split;
-  p.atomic = split > 1;
+  p.atomic = split > 2 ? 2 : (split > 1 ? 1 : 0);
   p.slots = 4 * split;
   // e3 = [hi | lo | hi], f3 = [hi | hi | lo] (xm_l2norm_split_fwd_f32, which = 0 / 1)
   p.a_lo_col[0] = kD;      // local e
@@ -580,7 +600,12 @@ int xm_infonce_bwd_fused_supported(int64_t Ml, int64_t Ng, int64_t D, int64_t di
          diag_off + Ml <= Ng && Ng < ((int64_t)1 << 30);
 }
 
-int64_t xm_infonce_bwd_fused_workspace(int64_t Ng, int64_t D) { return 2 * Ng + 4 * D * Ng; }
+int64_t xm_infonce_bwd_fused_workspace(int64_t Ml, int64_t Ng, int64_t D) {
+  if (Ml <= 0 || Ng <= 0 || Ml % 128 || Ng % 128) return 0;
+  nce::Params p{};
+  nce::plan(p, Ml, Ng);
+  return 2 * Ng + 4 * D * Ng + (p.atomic == 2 ? 2 * (int64_t)(p.slots / 4) * Ml * D : 0);
+}
 
 int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_all, const float* f3_all, const float* lse_ef,
                              const float* lse_fe, const float* lse_ef_all, const float* lse_fe_all, float* de, float* df,
@@ -615,7 +640,12 @@ int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_a
     int rc = check_launch();
     if (rc != XM_OK) return rc;
   }
-  if (p.atomic) {
+  if (p.atomic == 2) {
+    p.part[0] = bt1 + 2 * nce::kD * Ng;
+    p.part_stride = Ml * nce::kD;
+    p.part[1] = p.part[0] + (p.slots / 4) * p.part_stride;
+  }
+  if (p.atomic == 1) {
     if (cudaMemsetAsync(de, 0, (size_t)Ml * nce::kD * 4, st) != cudaSuccess ||
         cudaMemsetAsync(df, 0, (size_t)Ml * nce::kD * 4, st) != cudaSuccess) {
       g_last_cuda_error = (int)cudaGetLastError();
@@ -643,6 +673,11 @@ int xm_infonce_bwd_fused_f32(const float* e3, const float* f3, const float* e3_a
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
+  rc = check_launch();
+  if (rc != XM_OK || p.atomic != 2) return rc;
+  const long long n4 = Ml * nce::kD / 4;
+  nce::nce_sum_parts_kernel<<<(int)((2 * n4 + 255) / 256 < 1184 ? (2 * n4 + 255) / 256 : 1184), 256, 0, st>>>(p.part[0], p.part[1], de, df, n4,
+                                                                                                              p.slots / 4);
   return check_launch();
 }
 

@@ -142,9 +142,10 @@ def _allreduce_sum(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def _bn_stats(y, eps, running_mean, running_var, momentum, training):
+def _bn_stats(y, eps, running_mean, running_var, momentum, training, part=None):
     """mean / invstd / count for a (B,T,C) or (B,C) tensor: batch statistics (optionally synchronised
-    across ranks) in training, running statistics in eval."""
+    across ranks) in training, running statistics in eval.  part: the partial sums (rows, C, 2) fp64 of y when its
+    producer already accumulated them (conv epilogue)."""
     rows = y.shape[0] * (y.shape[1] if y.dim() == 3 else 1)
     if not training:
         invstd = torch.rsqrt(running_var + eps)
@@ -154,7 +155,8 @@ def _bn_stats(y, eps, running_mean, running_var, momentum, training):
         count *= _CTX.world
     if count <= 1:  # torch.nn.functional.batch_norm raises here too (the batch variance is undefined)
         raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(y.shape)}")
-    part = ops.bn_partial_stats(y)
+    if part is None:
+        part = ops.bn_partial_stats(y)
     if _CTX.active and _CTX.sync_bn:
         part = _allreduce_sum(part.sum(0, keepdim=True))
     mean, invstd = ops.bn_finalize_stats(part, count, eps, running_mean, running_var, momentum)
@@ -216,10 +218,15 @@ class ConvBnAct(torch.autograd.Function):
             # ONE conv over 3 Cin stacked channels [xh | xl | xh] x [wh | wh | wl].  The first two convs of the v4
             # encoder need it: their single-pass operand rounding alone puts 7e-3 .. 1e-2 on five parameter
             # gradients (tools/tf32_floor_by_layer.py, profiles/r2_tf32_floor_by_layer.json); the backward does not.
-            y, x = ops.conv1d_fwd_precise(x, w, b)  # x: now the tf32-rounded input, operand of the weight gradient
+            if training:  # the conv epilogue also accumulates the BatchNorm batch statistics of y
+                y, x, part = ops.conv1d_fwd_precise(x, w, b, stats=True)
+            else:
+                (y, x), part = ops.conv1d_fwd_precise(x, w, b), None  # x: now the tf32-rounded input, operand of the weight gradient
+        elif training:
+            y, part = ops.conv1d_fwd(x, wk, b, Cout, stats=True)
         else:
-            y = ops.conv1d_fwd(x, wk, b, Cout)
-        mean, invstd, count = _bn_stats(y, eps, running_mean, running_var, momentum, training)
+            y, part = ops.conv1d_fwd(x, wk, b, Cout), None
+        mean, invstd, count = _bn_stats(y, eps, running_mean, running_var, momentum, training, part)
         seed = next_seed() if (training and p > 0) else 0
         pd = p if training else 0.0
         out = ops.bn_act_fwd(y, mean, invstd, gamma, beta, act, pool, pd, seed, dbp, round_out)

@@ -218,21 +218,34 @@ def conv1d_pack_weight(w):
     return wk, wt
 
 
-def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
+def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None, stats=False):
     """x (B, T, Cin) channels-last -> y (B, T, Cout).  `out` may be a channel slice of a wider
-    (B, T, Ctot) buffer (free concat of parallel branches)."""
+    (B, T, Ctot) buffer (free concat of parallel branches).  stats: -> (y, part) with part (rows, Cout, 2) fp64 = the
+    BatchNorm partial statistics of y accumulated in the conv epilogue (what bn_partial_stats(y) returns, other split)."""
     _chk(x, wk, bias)
     x = as_nwc(x)
     B, T, Cin = x.shape
     taps, _, ldk = wk.shape
     y = empty_pitched((B, T, Cout), x.device) if out is None else out
     _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cin + Cout) + taps * Cin * Cout))
+    if stats:
+        part = torch.empty(_lib.lib().xm_conv1d_fwd_stat_rows(), Cout, 2, device=x.device, dtype=torch.float64)
+        try:
+            _call("xm_conv1d_fwd_stats_f32", _p(x), _p(wk), _p(bias), _p(y), _p(part), B, Cin, Cout, T, taps, x.stride(1), ldk,
+                  y.stride(1), int(round_out), _stream())
+            return y, part
+        except _lib.XmodalError as exc:
+            if getattr(exc, "status", 0) != -2:  # only XM_ERR_UNSUPPORTED (shape outside the statistics epilogue)
+                raise
+        _call("xm_conv1d_fwd_f32", _p(x), _p(wk), _p(bias), _p(y), B, Cin, Cout, T, taps, x.stride(1), ldk, y.stride(1),
+              int(round_out), _stream())
+        return y, bn_partial_stats(y)
     _call("xm_conv1d_fwd_f32", _p(x), _p(wk), _p(bias), _p(y), B, Cin, Cout, T, taps, x.stride(1), ldk, y.stride(1),
           int(round_out), _stream())
     return y
 
 
-def conv1d_fwd_precise(x, w, bias):
+def conv1d_fwd_precise(x, w, bias, stats=False):
     """fp32-accurate conv forward on the tf32 tensor cores: x (B, T, Cin) channels-last and NOT rounded, w (Cout, Cin,
     taps) in the reference layout.  x = xh + xl, w = wh + wl, y = xh wh + xl wh + xh wl as ONE conv over 3 Cin
     stacked channels [xh | xl | xh] x [wh | wh | wl]; x may also BE that split already, (B, T, 3 Cin).
@@ -249,6 +262,9 @@ def conv1d_fwd_precise(x, w, bias):
         x3 = split3(x.view(B * T, Cin), 0, 1).view(B, T, 3 * Cin)
     w3 = split3(w.reshape(Cout, Cin * taps), 1, 1).view(Cout, 3 * Cin, taps)
     wk3, _ = conv1d_pack_weight(w3)
+    if stats:
+        y, part = conv1d_fwd(x3, wk3, bias, Cout, stats=True)
+        return y, x3[:, :, :Cin], part
     return conv1d_fwd(x3, wk3, bias, Cout), x3[:, :, :Cin]
 
 
@@ -914,7 +930,7 @@ def infonce_bwd_fused(e3, f3, e3_all, f3_all, lse_ef, lse_fe, lse_ef_all, lse_fe
     Ng = e3_all.shape[0]
     de = torch.empty(Ml, D, device=e3.device, dtype=torch.float32)
     df = torch.empty(Ml, D, device=e3.device, dtype=torch.float32)
-    ws = torch.empty(int(_lib.lib().xm_infonce_bwd_fused_workspace(Ng, D)), device=e3.device, dtype=torch.float32)
+    ws = torch.empty(int(_lib.lib().xm_infonce_bwd_fused_workspace(Ml, Ng, D)), device=e3.device, dtype=torch.float32)
     passes = 6.0 if precise else 4.0  # 3 score passes + 3 / 1 contraction passes, two directions
     _w(2.0 * passes * 2.0 * Ml * Ng * D, 4.0 * (2 * 3 * Ml * D + 2 * 3 * Ng * D + 2 * 2 * Ng * D + 2 * Ml * D))
     _call("xm_infonce_bwd_fused_f32", _p(e3), _p(f3), _p(e3_all), _p(f3_all), _p(lse_ef.contiguous()), _p(lse_fe.contiguous()),

@@ -66,18 +66,21 @@ def conv1d_pack_weight(w):
     return w.detach().clone(), w.detach().clone()  # both "packed" forms are just the weight here
 
 
-def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None):
+def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None, stats=False):
     y = F.conv1d(x.double().transpose(1, 2), wk.double(), None if bias is None else bias.double(), padding=wk.shape[-1] // 2)
     y = y.transpose(1, 2).float().contiguous()
     if out is not None:
         out.copy_(y)
-        return out
-    return y
+        y = out
+    return (y, bn_partial_stats(y)) if stats else y
 
 
-def conv1d_fwd_precise(x, w, bias):
+def conv1d_fwd_precise(x, w, bias, stats=False):
     if x.shape[2] == 3 * w.shape[1]:  # channel-stacked split from the producer
         x = x[:, :, : w.shape[1]]
+    if stats:
+        y, part = conv1d_fwd(x, w, bias, w.shape[0], stats=True)
+        return y, x, part
     return conv1d_fwd(x, w, bias, w.shape[0]), x
 
 

@@ -133,6 +133,26 @@ def test_conv1d_fwd_dgrad_wgrad(ops, B, Cin, Cout, T, k):
     assert_close_rel(db, dy.double().sum((0, 2)), FP32, "conv bias grad", atol=1e-5)
 
 
+@pytest.mark.parametrize("B,Cin,Cout,T,k", [(3, 64, 64, 500, 7), (2, 64, 128, 250, 5), (300, 64, 64, 500, 7), (2, 18, 48, 37, 3),
+                                            (5, 192, 128, 100, 1)])
+def test_conv1d_fwd_emits_batchnorm_statistics(ops, B, Cin, Cout, T, k):
+    """The statistics epilogue: same y, and partial sums whose total is (sum y, sum y^2) per channel over (B, T)."""
+    torch.manual_seed(4)
+    x = _nwc(torch.randn(B, Cin, T, device="cuda"))
+    w = torch.randn(Cout, Cin, k, device="cuda") / (Cin * k) ** 0.5
+    b = torch.randn(Cout, device="cuda")
+    wk, _ = ops.conv1d_pack_weight(w)
+    y0 = ops.conv1d_fwd(x, wk, b, Cout)
+    y, part = ops.conv1d_fwd(x, wk, b, Cout, stats=True)
+    assert torch.equal(y, y0)
+    tot = part.sum(0)  # (Cout, 2) fp64
+    yd = y.double().reshape(-1, Cout)
+    assert_close_rel(tot[:, 0], yd.sum(0), 1e-6, "conv epilogue: sum of y", atol=1e-6 * (B * T) ** 0.5)
+    assert_close_rel(tot[:, 1], (yd * yd).sum(0), 1e-6, "conv epilogue: sum of y^2")
+    want = ops.bn_partial_stats(y).sum(0)
+    assert_close_rel(tot, want, 1e-6, "against the separate statistics pass", atol=1e-6 * (B * T) ** 0.5)
+
+
 def test_conv1d_wgrad_many_samples(ops):
     torch.manual_seed(5)
     B, Cin, Cout, T, k = 300, 64, 64, 500, 7

@@ -170,6 +170,32 @@ def test_baseline_shape_parity_every_gradient_within_1e3():
     assert checked >= 55
 
 
+def test_step_gradients_are_bit_reproducible():
+    """Two identical forward / backward passes give bit-identical gradients (no floating-point atomics on the path): the
+    gradients of the first conv / BatchNorm layers amplify a 1e-7 perturbation of the loss gradient to ~3e-4 (every
+    tf32 rounding of a gradient tensor re-quantises it), so run-to-run noise in ANY kernel would show up as run-to-run
+    changes of the parity errors (profiles/r2_determinism.txt).  Batch 1024: the InfoNCE row tiles are split over 8 units
+    each, the case that used red.add before."""
+    from multimodal_eeg_fmri_b200 import synthetic
+    from multimodal_eeg_fmri_b200.training import PairedBridgeModel
+    torch.manual_seed(1)
+    m = PairedBridgeModel(16, 24, None, 128, 32, 128, 0.0, 0.0, "v4").cuda().train()
+    eeg, roi, conn = (t.cuda() for t in synthetic.paired_batch(1024, 16, 128, 24, 20, seed=9))
+    runs = []
+    for overlap in (True, True, False):
+        m.overlap_branches = overlap
+        for p in m.parameters():
+            p.grad = None
+        loss = m(eeg, roi, conn)
+        loss.backward()
+        torch.cuda.synchronize()
+        runs.append((loss.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    for loss, g in runs[1:]:
+        assert torch.equal(loss, runs[0][0])
+        bad = [k for k in g if not torch.equal(g[k], runs[0][1][k])]
+        assert not bad, f"gradients differ between identical passes: {bad[:6]}"
+
+
 def test_full_batch_4096_step_properties():
     """BASELINE config 4 per-GPU shape (B = 4096, v4 encoder): the step runs, the loss starts near
     log(B) for random init, is finite, and decreases over a few steps on a fixed batch."""
