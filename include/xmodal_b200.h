@@ -417,6 +417,18 @@ int xm_ffn_fused_dgrad_f32(const float* x, const float* dy, const float* w1, con
 /* mask (M, hidden), 1 = kept: the dropout mask both kernels generate for (drop_p, seed), so tests can replay it. */
 int xm_ffn_fused_mask_u8(uint8_t* mask, int64_t M, int64_t hidden, float drop_p, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------ bridge head: cross-attention over two tokens
+ * bridge_utils.py:74-83 (nn.MultiheadAttention(query = eeg token, key = value = [eeg, fmri])): per (sample, head) two
+ * scores, a two-way softmax, dropout on the weights, a weighted sum of two value vectors (csrc/bridge_head.cu).
+ * q (B, H*dh); kv (2B, 2*H*dh): row t*B + b = token t of sample b, columns [0, d) keys, [d, 2d) values (the packed k / v
+ * in-projection of the stacked tokens).  out (B, H*dh); att (B, H, 2) = the dropped, rescaled weights (what
+ * need_weights returns before the head average).  The backward recomputes the softmax from q and k and regenerates
+ * the mask from (seed, sample, head, token): dq (B, d), dkv (2B, 2d). */
+int xm_cross2_attn_fwd_f32(const float* q, const float* kv, float* out, float* att, int64_t B, int64_t H, int64_t dh, float drop_p,
+                           uint64_t seed, void* stream);
+int xm_cross2_attn_bwd_f32(const float* dout, const float* q, const float* kv, float* dq, float* dkv, int64_t B, int64_t H, int64_t dh,
+                           float drop_p, uint64_t seed, void* stream);
+
 /* ------------------------------------------------------------------ clip_grad_norm_ + AdamW over one flat bucket
  * The step recipe of _test_bridge.py:775-788,869 (run_fmri_v11.py:430-450, run_training_lite.py:478-489):
  * clip_grad_norm_(max_norm) then torch.optim.AdamW.step, as two launches over flat fp32 buffers (csrc/optimizer.cu).

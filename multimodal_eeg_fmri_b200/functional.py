@@ -727,6 +727,32 @@ class _PeerShards:
         return ent["sets"][ent["turn"]]
 
 
+class Cross2Attention(torch.autograd.Function):
+    """The bridge head's cross-attention core: one query per sample over the two-token sequence [eeg, fmri]
+    (bridge_utils.py:74-83), forward and backward in one launch each; returns (out, dropped weights (B, H, 2))."""
+
+    @staticmethod
+    def forward(ctx, q, kv, nhead, p, training):
+        seed = next_seed() if (training and p > 0) else 0
+        pd = p if training else 0.0
+        out, att = ops.cross2_attn_fwd(q, kv, nhead, pd, seed)
+        ctx.save_for_backward(q, kv)
+        ctx.meta = (nhead, pd, seed)
+        ctx.mark_non_differentiable(att)
+        return out, att
+
+    @staticmethod
+    def backward(ctx, dout, _datt):
+        q, kv = ctx.saved_tensors
+        nhead, pd, seed = ctx.meta
+        dq, dkv = ops.cross2_attn_bwd(dout.contiguous(), q, kv, nhead, pd, seed)
+        return dq, dkv, None, None, None
+
+
+def cross2_attention(q, kv, nhead, p=0.0, training=False):
+    return Cross2Attention.apply(q.contiguous(), kv.contiguous(), nhead, p, training)
+
+
 def _infonce_lse_pair(e3, f3, e3_all, f3_all, inv_tau, off):
     """(lse of my e x all f, lse of my f x all e, positives): one fused launch where the shapes allow, else two GEMMs."""
     if _FUSED_INFONCE_BWD and ops.infonce_bwd_fused_supported(e3.shape[0], e3_all.shape[0], e3.shape[1] // 3, off):

@@ -436,15 +436,12 @@ class EEGfMRIBridgeFusionNet(nn.Module):
         B, d = e.shape
         H, dh = self.num_heads, d // self.num_heads
         W, b = self.cross_attn.in_proj_weight, self.cross_attn.in_proj_bias
-        q = XF.Linear.apply(e, W[:d], b[:d], False, False, True).view(B, H, dh)
+        q = XF.Linear.apply(e, W[:d], b[:d], False, False, True)
         kv = XF.Linear.apply(torch.cat([e, f], dim=0), W[d:], b[d:], False, False, True)  # keys and values of both tokens
-        k = kv[:, :d].reshape(2, B, H, dh)
-        v = kv[:, d:].reshape(2, B, H, dh)
-        att = torch.softmax((q.unsqueeze(0) * k).sum(-1) / math.sqrt(dh), dim=0)  # (2, B, H)
-        att_d = F.dropout(att, self.dropout_p, self.training)
-        o = (att_d.unsqueeze(-1) * v).sum(0).reshape(B, d)
+        # scores, two-way softmax, dropout on the weights and the weighted value sum: one kernel (xm_cross2_attn_*)
+        o, att_d = XF.cross2_attention(q, kv, H, self.dropout_p, self.training)
         o = XF.linear(o, self.cross_attn.out_proj)
-        return o, att_d.mean(-1).t().unsqueeze(1)  # weights averaged over heads: (B, 1, 2)
+        return o, att_d.mean(1).unsqueeze(1)  # weights averaged over heads: (B, 1, 2)
 
     def forward(self, eeg_feats, fmri_feats, return_features=False, return_weights=False):
         e, f = self.project(eeg_feats, fmri_feats)

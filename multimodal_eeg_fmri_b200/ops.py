@@ -1031,6 +1031,31 @@ def roi_corrcoef(x, prepared=False):
 
 
 # ------------------------------------------------------------------ optimizer step over one flat bucket
+def cross2_attn_fwd(q, kv, nhead, drop_p=0.0, seed=0):
+    """Bridge head: one query per sample over two tokens.  q (B, d), kv (2B, 2d) -> (out (B, d), att (B, H, 2))."""
+    _chk(q, kv)
+    q, kv = q.contiguous(), kv.contiguous()
+    B, d = q.shape
+    out = torch.empty(B, d, device=q.device, dtype=torch.float32)
+    att = torch.empty(B, nhead, 2, device=q.device, dtype=torch.float32)
+    _w(8.0 * B * d, 4.0 * (6 * B * d))
+    _call("xm_cross2_attn_fwd_f32", _p(q), _p(kv), _p(out), _p(att), B, nhead, d // nhead, float(drop_p), int(seed), _stream())
+    return out, att
+
+
+def cross2_attn_bwd(dout, q, kv, nhead, drop_p=0.0, seed=0):
+    """-> (dq (B, d), dkv (2B, 2d))"""
+    _chk(dout, q, kv)
+    dout, q, kv = dout.contiguous(), q.contiguous(), kv.contiguous()
+    B, d = q.shape
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    _w(16.0 * B * d, 4.0 * (10 * B * d))
+    _call("xm_cross2_attn_bwd_f32", _p(dout), _p(q), _p(kv), _p(dq), _p(dkv), B, nhead, d // nhead, float(drop_p), int(seed),
+          _stream())
+    return dq, dkv
+
+
 def gather_flat_(dst, tensors, offsets):
     """dst[offsets[t] : offsets[t] + tensors[t].numel()] = tensors[t] (flattened), all tensors in one launch per 96:
     the per-parameter gradients autograd produced, gathered into the flat bucket (xm_gather_flat_f32)."""

@@ -479,6 +479,37 @@ def zscore(x, eps=1e-8):
     return out.reshape(x.shape).float()
 
 
+def _cross2_parts(q, kv, nhead):
+    B, d = q.shape
+    dh = d // nhead
+    qd = q.double().reshape(B, nhead, dh)
+    k = kv[:, :d].double().reshape(2, B, nhead, dh)
+    v = kv[:, d:].double().reshape(2, B, nhead, dh)
+    p = torch.softmax((qd.unsqueeze(0) * k).sum(-1) / dh ** 0.5, dim=0)  # (2, B, H)
+    return qd, k, v, p
+
+
+def cross2_attn_fwd(q, kv, nhead, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    qd, k, v, p = _cross2_parts(q, kv, nhead)
+    out = (p.unsqueeze(-1) * v).sum(0).reshape(q.shape)
+    return out.float(), p.permute(1, 2, 0).contiguous().float()
+
+
+@torch.enable_grad()
+def cross2_attn_bwd(dout, q, kv, nhead, drop_p=0.0, seed=0):
+    _nodrop(drop_p)
+    qd, kvd = q.double().requires_grad_(True), kv.double().requires_grad_(True)
+    B, d = q.shape
+    dh = d // nhead
+    k = kvd[:, :d].reshape(2, B, nhead, dh)
+    v = kvd[:, d:].reshape(2, B, nhead, dh)
+    p = torch.softmax((qd.reshape(B, nhead, dh).unsqueeze(0) * k).sum(-1) / dh ** 0.5, dim=0)
+    out = (p.unsqueeze(-1) * v).sum(0).reshape(B, d)
+    dq, dkv = torch.autograd.grad(out, (qd, kvd), dout.double())
+    return dq.float(), dkv.float()
+
+
 def gather_flat_(dst, tensors, offsets):
     for t, o in zip(tensors, offsets):
         dst[o:o + t.numel()].copy_(t.reshape(-1))

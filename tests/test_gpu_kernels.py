@@ -232,6 +232,38 @@ def test_infonce_bwd_fused(ops, Ml, Ng, off, precise):
     assert_close_rel(df, df_ref, tol, "fused infonce df", atol=1e-9)
 
 
+@pytest.mark.parametrize("B,H,dh,pdrop", [(37, 4, 32, 0.0), (256, 4, 32, 0.3), (5, 2, 64, 0.0), (3, 1, 16, 0.0), (64, 8, 16, 0.5)])
+def test_cross2_attention_of_the_bridge_head(ops, B, H, dh, pdrop):
+    """One query over two tokens (bridge_utils.py:74-83) against fp64 autograd; with dropout the kernel's own mask is
+    read back from the returned weights (w = mask * p / (1 - drop)) and replayed."""
+    torch.manual_seed(21)
+    d = H * dh
+    q = torch.randn(B, d, device="cuda")
+    kv = torch.randn(2 * B, 2 * d, device="cuda")
+    dout = torch.randn(B, d, device="cuda")
+    out, att = ops.cross2_attn_fwd(q, kv, H, pdrop, 99)
+    qd, kvd = q.double().requires_grad_(True), kv.double().requires_grad_(True)
+    k = kvd[:, :d].reshape(2, B, H, dh)
+    v = kvd[:, d:].reshape(2, B, H, dh)
+    p = torch.softmax((qd.reshape(B, H, dh).unsqueeze(0) * k).sum(-1) / dh ** 0.5, dim=0)  # (2, B, H)
+    mask = torch.ones_like(p)
+    if pdrop > 0:
+        mask = (att.permute(2, 0, 1).double() != 0).double() / (1 - pdrop)
+        keep = float((mask != 0).double().mean())
+        assert abs(keep - (1 - pdrop)) < 4 * (pdrop * (1 - pdrop) / mask.numel()) ** 0.5 + 1e-3
+        out2, att2 = ops.cross2_attn_fwd(q, kv, H, pdrop, 99)
+        assert torch.equal(att, att2) and torch.equal(out, out2)
+        assert not torch.equal(att, ops.cross2_attn_fwd(q, kv, H, pdrop, 100)[1])
+    w = p * mask
+    ref = (w.unsqueeze(-1) * v).sum(0).reshape(B, d)
+    assert_close_rel(out, ref, 1e-5, "cross2 out")
+    assert_close_rel(att, w.permute(1, 2, 0), 1e-5, "cross2 weights")
+    gq, gkv = torch.autograd.grad(ref, (qd, kvd), dout.double())
+    dq, dkv = ops.cross2_attn_bwd(dout, q, kv, H, pdrop, 99)
+    assert_close_rel(dq, gq, 1e-5, "cross2 dq", atol=1e-7)
+    assert_close_rel(dkv, gkv, 1e-5, "cross2 dkv", atol=1e-7)
+
+
 # ------------------------------------------------------------------ windowing + band power
 @pytest.mark.parametrize("R,C,n,win,hop,nfft,fs", [
     (2, 4, 3000, 1024, 512, 1024, 1000.0), (3, 8, 2000, 500, 250, 512, 250.0), (1, 3, 1001, 100, 37, 128, 128.0),
