@@ -63,8 +63,8 @@ int xm_window_index_i64(int64_t n_rec, int64_t n_samples, int64_t win, int64_t h
  *   channels_last == 0: out (n_rec*n_win, C, ld_out >= win)   -- the reference's (C, T) sample layout
  *   channels_last != 0: out (n_rec*n_win, win, ld_out >= C)   -- the layout the conv GEMMs consume
  * round_tf32 == 1 rounds values to tf32 (removes the truncation bias of the first conv); round_tf32 == 2
- * (channels_last only, ld_out >= 3*C) writes the 3-way tf32 split [hi | lo | hi] along the channel axis, the operand
- * of a 3-pass (fp32-accurate) first conv.
+ * (channels_last only, ld_out >= 2*C) writes the tf32 split [hi | lo] along the channel axis, the operand of a 3-pass
+ * (fp32-accurate) first conv (xm_conv1d_fwd_stats_f32 with x_cols = 2*C).
  * With n_win == 1 (win == n_samples) this is the (B, C, T) -> (B, T, C) layout change. */
 int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_samples, int64_t win, int64_t hop,
                          float* out, int64_t ld_out, int channels_last, int round_tf32, void* stream);
@@ -154,11 +154,14 @@ int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float*
  * (B, T), the `partials` argument of xm_bn_finalize_stats -- accumulated in the epilogue warps (fp32 butterfly per
  * 32-row block, fp64 across blocks), so xm_bn_partial_stats_f32's pass over y is not needed
  * (EEG_CODE/enhanced_models_v4.py:128-144: Conv1d -> BatchNorm1d).  Cout <= the N tile (256), y 16-B aligned, ldy % 4 == 0;
- * XM_ERR_UNSUPPORTED otherwise (callers then use the two-kernel path). */
+ * XM_ERR_UNSUPPORTED otherwise (callers then use the two-kernel path).  stat_part may be NULL (plain convolution).
+ * x_cols (0 = Cin): the number of channels x physically stores when that is fewer than the Cin the contraction walks:
+ * channel coordinates >= x_cols wrap back by x_cols, so the 3-pass convolution over [hi | lo | hi] x [wh | wh | wl]
+ * (Cin = 3 C) reads a tensor that holds [hi | lo] (x_cols = 2 C, a multiple of 32, taps > 1). */
 int xm_conv1d_fwd_stat_rows(void);
 int xm_conv1d_fwd_stats_f32(const float* x, const float* wk, const float* bias, float* y, double* stat_part, int64_t B,
                             int64_t Cin, int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy,
-                            int round_out, void* stream);
+                            int round_out, int64_t x_cols, void* stream);
 /* dx (B,T,Cin) from dy (B,T,Cout) */
 int xm_conv1d_dgrad_f32(const float* dy, const float* wt, float* dx, int64_t B, int64_t Cin, int64_t Cout, int64_t T,
                         int64_t taps, int64_t lddy, int64_t ldt, int64_t lddx, int round_out, void* stream);
@@ -184,8 +187,8 @@ int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double t
 /* out = drop(pool?(act(gamma*(y-mean)*invstd + beta))) ; pool: 0 none, 2 = MaxPool1d(2) over T
  * (out has B*(T/2) rows).  drop_p in [0,1): keep with prob 1-p, scale 1/(1-p); mask from
  * (seed, element index).  drop_before_pool selects Conv-BN-GELU-Drop-Pool (Lite) vs
- * Conv-BN-GELU-Pool-Drop (v4) ordering.  round_out: 0 fp32, 1 rounded to tf32, 2 = the 3-way tf32 split [hi | lo | hi]
- * along the channel axis (ldo >= 3*C), the operand of a following 3-pass conv. */
+ * Conv-BN-GELU-Pool-Drop (v4) ordering.  round_out: 0 fp32, 1 rounded to tf32, 2 = the tf32 split [hi | lo] along the
+ * channel axis (ldo >= 2*C), the operand of a following 3-pass conv (xm_conv1d_fwd_stats_f32, x_cols = 2*C). */
 int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
                       float* out, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo, int act, int pool,
                       float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream);

@@ -215,11 +215,10 @@ __global__ void bn_act_fwd_kernel(const BnActArgs a, long long R_out, float* __r
     const int c = (int)(i - ro * a.C);
     const float sc = a.gamma[c] * a.invstd[c], sh = a.beta[c] - a.mean[c] * sc;
     const float o = bn_act_fwd_elem(a, ro, c, sc, sh);
-    if (a.round_out == 2) {  // 3-way tf32 split along the channel axis [hi | lo | hi] (operand of a 3-pass conv)
+    if (a.round_out == 2) {  // tf32 split along the channel axis [hi | lo] (operand of a 3-pass conv)
       const float hi = round_tf32(o);
       out[ro * a.ldo + c] = hi;
       out[ro * a.ldo + a.C + c] = round_tf32(o - hi);
-      out[ro * a.ldo + 2 * a.C + c] = hi;
     } else {
       out[ro * a.ldo + c] = a.round_out ? round_tf32(o) : o;
     }
@@ -885,7 +884,7 @@ __global__ void bn_act_fwd_v4_kernel(const BnActArgs a, long long R_out, float* 
         o.v[j] = v;
       }
     }
-    if (a.round_out == 2) {  // 3-way tf32 split along the channel axis [hi | lo | hi]: operand of a 3-pass conv
+    if (a.round_out == 2) {  // tf32 split along the channel axis [hi | lo]: operand of a 3-pass conv
       F4 lo;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -895,7 +894,6 @@ __global__ void bn_act_fwd_v4_kernel(const BnActArgs a, long long R_out, float* 
       }
       st4(out + ro * a.ldo + c0, o);
       st4(out + ro * a.ldo + a.C + c0, lo);
-      st4(out + ro * a.ldo + 2 * a.C + c0, o);
       continue;
     }
     if (a.round_out) {
@@ -1147,7 +1145,7 @@ int xm_bn_finalize_stats(const double* partials, int nsplit, int64_t C, double t
 int xm_bn_act_fwd_f32(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
                       float* out, int64_t B, int64_t T, int64_t C, int64_t ldy, int64_t ldo, int act, int pool,
                       float drop_p, uint64_t seed, int drop_before_pool, int round_out, void* stream) {
-  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, T, C, ldy, pool, drop_p) || !out || ldo < (round_out == 2 ? 3 * C : C))
+  if (!bn_args_ok(y, mean, invstd, gamma, beta, B, T, C, ldy, pool, drop_p) || !out || ldo < (round_out == 2 ? 2 * C : C))
     return XM_ERR_INVALID;
   BnActArgs a = make_bn_args(y, mean, invstd, gamma, beta, B, T, C, ldy, ldo, act, pool, drop_p, seed, drop_before_pool,
                              round_out);

@@ -60,6 +60,8 @@ struct GemmParams {
                    // serves every tap (tap t = the slab read from row a_tap_row0 + t*a_tap_dir) and the stage
                    // carries the taps_k weight tiles: the activations cross L2 -> smem once, not taps_k times
   int a_slab_bytes, a_tap_row0, a_tap_dir, a_halo_row_shift;  // slab starts a_halo_row_shift rows from a.base[1]
+  int a_wrap;      // > 0 (halo path): inner coordinates >= a_wrap wrap back by a_wrap -- a 3-pass conv reads the channel
+                   // blocks [hi | lo | hi] of a tensor that stores [hi | lo] only
   int kin_count;   // inner k-blocks per (kout, tap)
   int kout_count;  // outer k iterations per tile (split along the z tile index when kout_split != 0)
   int kout_total;  // total outer k iterations (only used when kout_split != 0)
@@ -233,10 +235,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint8_t* sa = smem + (size_t)s * stage_bytes;
               if (p.a_halo) {
                 // halo slab (rows of every tap) by lane 0 + the taps_k weight tiles of this k-block, one lane each
-                if (lane == 0)
-                  ptx::tma_load_3d(&tmA, &full_bar[s], sa, ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0],
+                if (lane == 0) {
+                  int c0 = ca[0] + kin * p.a.kin_step[0] + kout * p.a.kout_step[0];
+                  if (p.a_wrap > 0 && c0 >= p.a_wrap) c0 -= p.a_wrap;
+                  ptx::tma_load_3d(&tmA, &full_bar[s], sa, c0,
                                    ca[1] + kin * p.a.kin_step[1] + kout * p.a.kout_step[1] + p.a_halo_row_shift,
                                    ca[2] + kin * p.a.kin_step[2] + kout * p.a.kout_step[2]);
+                }
                 for (int tp = 0; tp < p.taps_k; ++tp)
                   issue_operand_loads(&tmB, &full_bar[s], sa + a_bytes + tp * b_tile_bytes, p.b,
                                       cb[0] + kin * p.b.kin_step[0] + kout * p.b.kout_step[0] + tp * p.b.tap_step[0],

@@ -126,6 +126,7 @@ int launch_gemm(int epi, const TensorView3& ta, const TensorView3& tb, const Ten
       stage_bytes = kATileBytes + p.bn * 128;
     }
   }
+  if (p.a_wrap > 0 && !p.a_halo) return XM_ERR_UNSUPPORTED;  // the wrap lives in the halo producer
   const int total_kb = p.kout_count * p.taps_k * p.kin_count;
   if (total_kb <= 0) return XM_ERR_INVALID;
   const int epi_warps = epi == EPI_LSE ? 4 : 8;
@@ -490,9 +491,13 @@ int xm_conv1d_pack_weight_f32(const float* w, int64_t Cout, int64_t Cin, int64_t
 //   out[b, t, n] = sum_tap sum_k in[b, t + dir*(tap - pad), k] * wp[tap, n, k]  (+ bias[n])
 static int conv_like(const float* in, const float* wp, const float* bias, float* out, int64_t B, int64_t Kc, int64_t Nc,
                      int64_t T, int64_t taps, int64_t ld_in, int64_t ld_w, int64_t ld_out, int dir, int round_out,
-                     cudaStream_t st, double* stat_part = nullptr) {
+                     cudaStream_t st, double* stat_part = nullptr, int64_t in_cols = 0) {
+  // in_cols (0 = Kc): physical channel count of `in` when the tensor stores fewer channel blocks than the contraction
+  // walks -- [hi | lo] for a 3-pass conv over [hi | lo | hi]: block coordinates >= in_cols wrap back by in_cols
+  if (in_cols <= 0) in_cols = Kc;
+  if (in_cols != Kc && (in_cols > Kc || (in_cols & 31) || Kc > 2 * in_cols || taps == 1)) return XM_ERR_UNSUPPORTED;
   if (!in || !wp || !out || B <= 0 || Kc <= 0 || Nc <= 0 || T <= 0 || taps <= 0 || !(taps & 1)) return XM_ERR_INVALID;
-  if ((ld_in & 3) || (ld_w & 3) || ld_in < Kc || ld_out < Nc || B > 65535) return XM_ERR_INVALID;
+  if ((ld_in & 3) || (ld_w & 3) || ld_in < in_cols || ld_out < Nc || B > 65535) return XM_ERR_INVALID;
   const int pad = (int)(taps / 2);
   const int t_tiles = ceil_div(T, 128);
   GemmParams p;
@@ -522,7 +527,8 @@ static int conv_like(const float* in, const float* wp, const float* bias, float*
   p.c_z_stride = (long long)T * ld_out;
   p.bias = bias;
   p.round_tf32 = round_out;
-  TensorView3 ta{in, {(unsigned long long)Kc, (unsigned long long)T, (unsigned long long)B},
+  p.a_wrap = in_cols != Kc ? (int)in_cols : 0;
+  TensorView3 ta{in, {(unsigned long long)in_cols, (unsigned long long)T, (unsigned long long)B},
                  {(unsigned long long)ld_in * 4, (unsigned long long)T * ld_in * 4}};
   TensorView3 tb{wp, {(unsigned long long)Kc, (unsigned long long)Nc, (unsigned long long)taps},
                  {(unsigned long long)ld_w * 4, (unsigned long long)Nc * ld_w * 4}};
@@ -544,9 +550,8 @@ int xm_conv1d_fwd_stat_rows(void) { return kNumSMs * 4; }
 
 int xm_conv1d_fwd_stats_f32(const float* x, const float* wk, const float* bias, float* y, double* stat_part, int64_t B,
                             int64_t Cin, int64_t Cout, int64_t T, int64_t taps, int64_t ldx, int64_t ldk, int64_t ldy,
-                            int round_out, void* stream) {
-  if (!stat_part) return XM_ERR_INVALID;
-  return conv_like(x, wk, bias, y, B, Cin, Cout, T, taps, ldx, ldk, ldy, +1, round_out, (cudaStream_t)stream, stat_part);
+                            int round_out, int64_t x_cols, void* stream) {
+  return conv_like(x, wk, bias, y, B, Cin, Cout, T, taps, ldx, ldk, ldy, +1, round_out, (cudaStream_t)stream, stat_part, x_cols);
 }
 
 int xm_conv1d_fwd_f32(const float* x, const float* wk, const float* bias, float* y, int64_t B, int64_t Cin,

@@ -68,11 +68,10 @@ __global__ void window_gather_nwc_kernel(const float* __restrict__ rec, long lon
     if (t < win && c < C) {
       const float v = tile[tx][j];
       float* o = out + (g * win + t) * ld_out + c;
-      if (round_out == 2) {  // 3-way tf32 split along the channel axis [hi | lo | hi]: operand of a 3-pass conv
-        const float hi = round_tf32(v);
+      if (round_out == 2) {  // tf32 split along the channel axis [hi | lo]: operand of a 3-pass conv, which reads
+        const float hi = round_tf32(v);  // [hi | lo | hi] by wrapping its third channel block back onto the first
         o[0] = hi;
         o[C] = round_tf32(v - hi);
-        o[2 * C] = hi;
       } else {
         o[0] = round_out ? round_tf32(v) : v;
       }
@@ -302,7 +301,7 @@ int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_s
   const long long G = n_rec * n_win;
   if (round_tf32 == 2 && !channels_last) return XM_ERR_UNSUPPORTED;
   if (channels_last) {
-    if (ld_out < (round_tf32 == 2 ? 3 * C : C)) return XM_ERR_INVALID;
+    if (ld_out < (round_tf32 == 2 ? 2 * C : C)) return XM_ERR_INVALID;
     if (G > 2147483647ll || ceil_div(win, 32) > 65535 || ceil_div(C, 32) > 65535) return XM_ERR_UNSUPPORTED;
     dim3 grid((unsigned)G, ceil_div(win, 32), ceil_div(C, 32));
     window_gather_nwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rec, C, n_samples, n_win, win, hop, out, ld_out,

@@ -191,12 +191,12 @@ class ToChannelsLast(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         # the same transposing kernel maps a dense (B, T, C) gradient back to (B, C, T); of a channel-stacked split
-        # (B, T, 3C) only the first block carries the gradient (ConvBnAct.backward)
+        # (B, T, 2C) only the first block carries the gradient (ConvBnAct.backward)
         return ops.to_nwc(g[:, :, :ctx.C].contiguous()), None, None
 
 
 def to_channels_last(x, round_out=True, split3=False):
-    """split3: (B, T, 3C) channel-stacked tf32 split [hi | lo | hi], the input of a `precise` conv block."""
+    """split3: (B, T, 2C) channel-stacked tf32 split [hi | lo], the input of a `precise` conv block (read as [hi | lo | hi])."""
     return ToChannelsLast.apply(x, round_out, split3)
 
 
@@ -244,7 +244,7 @@ class ConvBnAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if xin_cols == Cin:
                 dx = ops.conv1d_dgrad(dy, wt, Cin, round_out=True)
-            else:  # the input was a channel-stacked split (B, T, 3 Cin): its gradient lives in the first block
+            else:  # the input was a channel-stacked split [hi | lo] (B, T, 2 Cin): its gradient lives in the first block
                 dx = ops.empty_pitched((dy.shape[0], dy.shape[1], xin_cols), dy.device)
                 ops.conv1d_dgrad(dy, wt, Cin, round_out=True, out=dx[:, :, :Cin])
         # A bias in front of a train-mode BatchNorm has an exactly zero gradient (sum over the batch of the BN
@@ -275,7 +275,7 @@ def conv_bn_act(x, conv, bn, act="gelu", pool=0, drop_p=0.0, drop_before_pool=Fa
                 precise=False):
     """conv / bn: torch modules used as parameter containers (nn.Conv1d, nn.BatchNorm1d).  `precise`: the conv forward
     runs in the 3-pass mode (see ConvBnAct); its input is either NOT tf32-rounded by its producer or already the
-    channel-stacked split (B, T, 3 Cin).  round_out: False | True (tf32) | 2 (emit that split for a following precise conv)."""
+    channel-stacked split [hi | lo] (B, T, 2 Cin).  round_out: False | True (tf32) | 2 (emit that split for a following precise conv)."""
     cfg = (bn.eps, _bn_momentum(bn, training), act, pool, float(drop_p), bool(drop_before_pool),
            bool(training), int(round_out), bool(precise))
     return ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)

@@ -44,7 +44,7 @@ class _PreciseFirstConv:
     @property
     def wants_unrounded_input(self) -> bool:
         """True when the first conv runs in the 3-pass (fp32-accurate) mode: a channels-last input handed in by the
-        caller (e.g. the window gather) must then NOT be tf32-rounded -- or be the channel-stacked split (B, T, 3C)."""
+        caller (e.g. the window gather) must then NOT be tf32-rounded -- or be the channel-stacked split [hi | lo] (B, T, 2C)."""
         return XF.CONV_PRECISE
 
 

@@ -139,8 +139,8 @@ def as_nwc(t: torch.Tensor) -> torch.Tensor:
 
 
 def to_nwc(x: torch.Tensor, round_out: bool = False, split3: bool = False) -> torch.Tensor:
-    """(B, C, T) reference layout -> channels-last (B, T, C) (pitched), one transposing pass; split3: (B, T, 3C), the
-    channel-stacked tf32 split [hi | lo | hi] (operand of a 3-pass first conv)."""
+    """(B, C, T) reference layout -> channels-last (B, T, C) (pitched), one transposing pass; split3: (B, T, 2C), the
+    channel-stacked tf32 split [hi | lo] (operand of a 3-pass first conv, which reads it as [hi | lo | hi])."""
     return window_gather(x, x.shape[2], 1, channels_last=True, round_out=round_out, split3=split3)
 
 
@@ -218,44 +218,60 @@ def conv1d_pack_weight(w):
     return wk, wt
 
 
-def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None, stats=False):
+def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None, stats=False, wrap_cin=0):
     """x (B, T, Cin) channels-last -> y (B, T, Cout).  `out` may be a channel slice of a wider
     (B, T, Ctot) buffer (free concat of parallel branches).  stats: -> (y, part) with part (rows, Cout, 2) fp64 = the
-    BatchNorm partial statistics of y accumulated in the conv epilogue (what bn_partial_stats(y) returns, other split)."""
+    BatchNorm partial statistics of y accumulated in the conv epilogue (what bn_partial_stats(y) returns, other split).
+    wrap_cin > x.shape[2]: the contraction walks wrap_cin channels, x stores the first x.shape[2] of them and the rest
+    wrap around ([hi | lo] read as [hi | lo | hi] by a 3-pass conv)."""
     _chk(x, wk, bias)
     x = as_nwc(x)
-    B, T, Cin = x.shape
+    B, T, Cx = x.shape
+    Cin = int(wrap_cin) if wrap_cin else Cx
     taps, _, ldk = wk.shape
     y = empty_pitched((B, T, Cout), x.device) if out is None else out
-    _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cin + Cout) + taps * Cin * Cout))
+    _w(2.0 * B * T * Cin * Cout * taps, 4.0 * (B * T * (Cx + Cout) + taps * Cin * Cout))
+    st = _stream()
+
+    def attempt(xx, want_part, x_cols):
+        """One launch of the statistics / wrap entry point; False when the shape is outside it (XM_ERR_UNSUPPORTED)."""
+        try:
+            _call("xm_conv1d_fwd_stats_f32", _p(xx), _p(wk), _p(bias), _p(y), _p(want_part), B, Cin, Cout, T, taps, xx.stride(1), ldk,
+                  y.stride(1), int(round_out), x_cols, st)
+            return True
+        except _lib.XmodalError as exc:
+            if getattr(exc, "status", 0) != -2:
+                raise
+            return False
+
+    wrapped = Cin != Cx
     if stats:
         part = torch.empty(_lib.lib().xm_conv1d_fwd_stat_rows(), Cout, 2, device=x.device, dtype=torch.float64)
-        try:
-            _call("xm_conv1d_fwd_stats_f32", _p(x), _p(wk), _p(bias), _p(y), _p(part), B, Cin, Cout, T, taps, x.stride(1), ldk,
-                  y.stride(1), int(round_out), _stream())
+        if attempt(x, part, Cx if wrapped else 0):
             return y, part
-        except _lib.XmodalError as exc:
-            if getattr(exc, "status", 0) != -2:  # only XM_ERR_UNSUPPORTED (shape outside the statistics epilogue)
-                raise
+    if wrapped and not attempt(x, None, Cx):  # the wrap needs the halo producer: else materialise the wrapped blocks
+        x = torch.cat([x, x[:, :, :Cin - Cx]], dim=2)
+        wrapped = False
+    if not wrapped:
         _call("xm_conv1d_fwd_f32", _p(x), _p(wk), _p(bias), _p(y), B, Cin, Cout, T, taps, x.stride(1), ldk, y.stride(1),
-              int(round_out), _stream())
-        return y, bn_partial_stats(y)
-    _call("xm_conv1d_fwd_f32", _p(x), _p(wk), _p(bias), _p(y), B, Cin, Cout, T, taps, x.stride(1), ldk, y.stride(1),
-          int(round_out), _stream())
-    return y
+              int(round_out), st)
+    return (y, bn_partial_stats(y)) if stats else y
 
 
 def conv1d_fwd_precise(x, w, bias, stats=False):
     """fp32-accurate conv forward on the tf32 tensor cores: x (B, T, Cin) channels-last and NOT rounded, w (Cout, Cin,
     taps) in the reference layout.  x = xh + xl, w = wh + wl, y = xh wh + xl wh + xh wl as ONE conv over 3 Cin
-    stacked channels [xh | xl | xh] x [wh | wh | wl]; x may also BE that split already, (B, T, 3 Cin).
+    stacked channels [xh | xl | xh] x [wh | wh | wl]; x may also be the split [xh | xl] already, (B, T, 2 Cin).
     -> (y (B, T, Cout), xh view (B, T, Cin): the tf32-rounded input, what a single-pass weight gradient reads)."""
     _chk(x, w, bias)
     x = as_nwc(x)
     B, T, _ = x.shape
     Cout, Cin, taps = w.shape
-    if x.shape[2] == 3 * Cin:  # the producer already wrote the channel-stacked split (window gather / BatchNorm block)
-        x3 = x
+    wrap = 0
+    if x.shape[2] == 2 * Cin and Cin != 0:  # the producer already wrote the split [hi | lo] (window gather / BatchNorm block)
+        x3, wrap = x, 3 * Cin                # read as [hi | lo | hi]: the third channel block wraps onto the first
+        if (2 * Cin) % 32 or taps == 1:      # (the wrap needs whole 32-channel blocks and the halo producer)
+            x3, wrap = torch.cat([x, x[:, :, :Cin]], dim=2), 0
     else:
         if x.stride(1) != Cin:
             x = x.contiguous()
@@ -263,9 +279,9 @@ def conv1d_fwd_precise(x, w, bias, stats=False):
     w3 = split3(w.reshape(Cout, Cin * taps), 1, 1).view(Cout, 3 * Cin, taps)
     wk3, _ = conv1d_pack_weight(w3)
     if stats:
-        y, part = conv1d_fwd(x3, wk3, bias, Cout, stats=True)
+        y, part = conv1d_fwd(x3, wk3, bias, Cout, stats=True, wrap_cin=wrap)
         return y, x3[:, :, :Cin], part
-    return conv1d_fwd(x3, wk3, bias, Cout), x3[:, :, :Cin]
+    return conv1d_fwd(x3, wk3, bias, Cout, wrap_cin=wrap), x3[:, :, :Cin]
 
 
 def conv1d_dgrad(dy, wt, Cin, round_out=False, out=None):
@@ -333,12 +349,12 @@ def bn_act_fwd(y, mean, invstd, gamma, beta, act, pool=0, drop_p=0.0, seed=0, dr
                round_out=False):
     _chk(y, mean, invstd, gamma, beta)
     B, T, C, ld = _bn_dims(y)
-    split = int(round_out) == 2  # (B, T', 3C): channel-stacked tf32 split [hi | lo | hi] for a following 3-pass conv
+    split = int(round_out) == 2  # (B, T', 2C): channel-stacked tf32 split [hi | lo] for a following 3-pass conv
     if y.dim() == 2:
-        out = torch.empty(B, 3 * C if split else C, device=y.device, dtype=torch.float32)
+        out = torch.empty(B, 2 * C if split else C, device=y.device, dtype=torch.float32)
         ldo = out.stride(0)
     else:
-        out = empty_pitched((B, T // 2 if pool == 2 else T, 3 * C if split else C), y.device)
+        out = empty_pitched((B, T // 2 if pool == 2 else T, 2 * C if split else C), y.device)
         ldo = out.stride(1)
     _w(20.0 * B * T * C, 4.0 * (B * T * C + out.numel()))
     _call("xm_bn_act_fwd_f32", _p(y), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(out), B, T, C, ld, ldo,
@@ -962,10 +978,10 @@ def window_gather(rec, win, hop, channels_last=False, round_out=False, split3=Fa
     if split3:
         if not channels_last:
             raise _lib.XmodalError("split3 needs the channels-last layout")
-        out = empty_pitched((R * n_win, win, 3 * C), rec.device)
+        out = empty_pitched((R * n_win, win, 2 * C), rec.device)
     else:
         out = empty_pitched((R * n_win, win, C) if channels_last else (R * n_win, C, win), rec.device)
-    _w(0.0, 4.0 * out.shape[0] * C * win * (4 if split3 else 2))
+    _w(0.0, 4.0 * out.shape[0] * C * win * (3 if split3 else 2))
     _call("xm_window_gather_f32", _p(rec), R, C, n, win, hop, _p(out), out.stride(1), int(channels_last),
           2 if split3 else int(round_out), _stream())
     return out

@@ -32,8 +32,8 @@ def empty_pitched(shape, device):
 
 
 def _stack3(t):
-    """The fake's channel-stacked 'split' [hi | lo | hi] of an exact value: hi = the value, lo = 0."""
-    return torch.cat([t, torch.zeros_like(t), t], dim=-1).contiguous()
+    """The fake's channel-stacked 'split' [hi | lo] of an exact value: hi = the value, lo = 0."""
+    return torch.cat([t, torch.zeros_like(t)], dim=-1).contiguous()
 
 
 def window_gather(rec, win, hop, channels_last=False, round_out=False, split3=False):
@@ -66,7 +66,7 @@ def conv1d_pack_weight(w):
     return w.detach().clone(), w.detach().clone()  # both "packed" forms are just the weight here
 
 
-def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None, stats=False):
+def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None, stats=False, wrap_cin=0):
     y = F.conv1d(x.double().transpose(1, 2), wk.double(), None if bias is None else bias.double(), padding=wk.shape[-1] // 2)
     y = y.transpose(1, 2).float().contiguous()
     if out is not None:
@@ -76,7 +76,7 @@ def conv1d_fwd(x, wk, bias, Cout, round_out=False, out=None, stats=False):
 
 
 def conv1d_fwd_precise(x, w, bias, stats=False):
-    if x.shape[2] == 3 * w.shape[1]:  # channel-stacked split from the producer
+    if x.shape[2] == 2 * w.shape[1]:  # channel-stacked split [hi | lo] from the producer
         x = x[:, :, : w.shape[1]]
     if stats:
         y, part = conv1d_fwd(x, w, bias, w.shape[0], stats=True)
@@ -145,7 +145,7 @@ def _dz(dout, y, mean, invstd, gamma, beta, act, pool):
     if pool == 2:
         B, T, C = a.shape
         a = a[:, : T // 2 * 2].reshape(B, T // 2, 2, C).amax(2)
-    (dz,) = torch.autograd.grad(a, z0, dout[..., : y.shape[-1]].double())  # a 3C-wide dout: gradient in the first block
+    (dz,) = torch.autograd.grad(a, z0, dout[..., : y.shape[-1]].double())  # a 2C-wide dout: gradient in the first block
     xhat = (y.double() - mean.double()) * invstd.double()
     return dz, xhat
 

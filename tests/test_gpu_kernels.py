@@ -683,24 +683,46 @@ def test_roi_corrcoef(ops, B, TR, ROI):
 
 # ------------------------------------------------------------------ producers that emit the tf32 split directly
 def test_producers_emit_the_tf32_split(ops):
-    """window gather, BatchNorm block and connectivity kernel can write the 3-way tf32 split of their output in place of
+    """window gather, BatchNorm block and connectivity kernel can write the tf32 split of their output in place of
     a separate xm_split3_f32 pass: bit-identical to splitting the plain output."""
     torch.manual_seed(51)
     rec = torch.randn(3, 20, 700, device="cuda")
     plain = ops.window_gather(rec, 256, 128, channels_last=True)
     got = ops.window_gather(rec, 256, 128, channels_last=True, split3=True)
     G, W, C = plain.shape
-    assert got.shape == (G, W, 3 * C) and torch.equal(got.reshape(G * W, 3 * C), ops.split3(plain.reshape(G * W, C), 0, 1))
+    # [hi | lo]: the first two blocks of xm_split3_f32's [hi | lo | hi] (a 3-pass conv wraps its third block onto the first)
+    assert got.shape == (G, W, 2 * C) and torch.equal(got.reshape(G * W, 2 * C), ops.split3(plain.reshape(G * W, C), 0, 1)[:, :2 * C])
     y = torch.randn(4, 50, 64, device="cuda")
     mean, invstd = torch.randn(64, device="cuda") * 0.1, torch.rand(64, device="cuda") + 0.5
     gamma, beta = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1
     for pool in (0, 2):
         o = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "gelu", pool)
         o3 = ops.bn_act_fwd(y, mean, invstd, gamma, beta, "gelu", pool, round_out=2)
-        assert torch.equal(o3.reshape(-1, 192), ops.split3(o.reshape(-1, 64), 0, 1))
+        assert torch.equal(o3.reshape(-1, 128), ops.split3(o.reshape(-1, 64), 0, 1)[:, :128])
     x = torch.randn(5, 40, 12, device="cuda")
     c = ops.roi_corrcoef(x)
     assert torch.equal(ops.roi_corrcoef(x, prepared=True), ops.linear_precise_prepare(c))
+
+
+@pytest.mark.parametrize("B,Cin,Cout,T,k", [(3, 64, 64, 500, 7), (2, 64, 128, 250, 5), (2, 32, 48, 100, 3), (2, 20, 32, 64, 5)])
+def test_precise_conv_reads_the_two_block_split(ops, B, Cin, Cout, T, k):
+    """The 3-pass conv over a producer-written [hi | lo] input (third channel block wrapped onto the first) equals the
+    3-pass conv over the explicit [hi | lo | hi] split bit for bit, and is fp32-accurate."""
+    torch.manual_seed(8)
+    x = torch.randn(B, Cin, T, device="cuda")
+    w = torch.randn(Cout, Cin, k, device="cuda") / (Cin * k) ** 0.5
+    b = torch.randn(Cout, device="cuda")
+    x2 = ops.to_nwc(x, split3=True)  # (B, T, 2 Cin)
+    assert x2.shape[2] == 2 * Cin
+    y2, xh = ops.conv1d_fwd_precise(x2, w, b)
+    y3, _ = ops.conv1d_fwd_precise(ops.to_nwc(x), w, b)
+    assert torch.equal(y2, y3)
+    assert torch.equal(xh.contiguous(), ops.to_nwc(x, round_out=True))
+    ref = _nwc(F.conv1d(x.double(), w.double(), b.double(), padding=k // 2))
+    assert_close_rel(y2, ref, 1e-5, "3-pass conv over [hi | lo]")
+    y2s, _, part = ops.conv1d_fwd_precise(x2, w, b, stats=True)
+    assert torch.equal(y2s, y2)
+    assert_close_rel(part.sum(0)[:, 0], y2.double().reshape(-1, Cout).sum(0), 1e-6, "statistics with the wrapped read", atol=1e-6 * (B * T) ** 0.5)
 
 
 # ------------------------------------------------------------------ out-of-bounds canaries

@@ -1,9 +1,8 @@
 #!/usr/bin/env bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "attention or ffn or tail" > gpurun_out/s_k.log 2>&1; echo "kernel tests rc=$?"; tail -5 gpurun_out/s_k.log
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "conv or split or precise or bn_ or window" > gpurun_out/s_k.log 2>&1; echo "kernel tests rc=$?"; tail -5 gpurun_out/s_k.log
 timeout 600 python -m pytest tests/test_gpu_paired_step.py tests/test_gpu_modules.py -x -q -m gpu > gpurun_out/s_step.log 2>&1; echo "step tests rc=$?"; tail -3 gpurun_out/s_step.log
-timeout 300 python tools/ffn_bench.py --only-fused > gpurun_out/s_ffn_bench.json 2> gpurun_out/s_ffn_bench.err; cat gpurun_out/s_ffn_bench.json
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-eager --no-extras > gpurun_out/s_bench.json 2> gpurun_out/s_bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json
