@@ -67,6 +67,11 @@ class ClockSampler:
                                            "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
+            # nvidia-smi takes 0.5 - 2 s to initialise NVML over all GPUs of the box and holds driver locks while it
+            # does: wait for its first sample, so that neither the warm-up nor the timed region overlaps that start-up
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 10.0 and self._proc.poll() is None:
+                time.sleep(0.02)
         except Exception:  # noqa: BLE001 - sampling is best effort
             self._proc = None
         return self
@@ -362,8 +367,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(local).start()  # started before the warm-up: its start-up cost stays outside the timed region
-    for _ in range(max(args.warmup, 3)):
+    clocks = ClockSampler(local).start()  # started (and initialised) before the warm-up: its start-up stays outside the timed region
+    # W warm-up steps as asked, plus 5 settling steps of our own (all untimed): the caching allocator of the two streams
+    # reaches its steady state and every kernel has been loaded before the timed region opens
+    for _ in range(max(args.warmup, 3) + 5):
         trainer.step(*devt)
     barrier()
 
