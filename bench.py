@@ -254,7 +254,13 @@ def _extras(dev, rank, world, barrier, hbm):
     ms3 = step_time(lambda: t3.step(eeg, roi))
     out["config3_bridge_b256"] = {"metric": METRIC, "value": round(256 / (ms3 * 1e-3), 1), "unit": UNIT, "batch": 256,
                                   "ms_per_step": round(ms3, 3), "launches_per_step": (ops.launch_count() - n0) / 25}
-    del m3, t3
+    # the same step captured once and replayed as ONE CUDA-graph launch (PairedTrainer.capture: device-resident seed epoch,
+    # AdamW step count and learning rate; replays equal eager steps bit for bit, tests/test_gpu_graphed_step.py)
+    g3 = t3.capture(eeg, roi)
+    ms3g = step_time(g3.replay)
+    out["config3_bridge_b256"]["graphed"] = {"value": round(256 / (ms3g * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms3g, 3),
+                                             "c_abi_calls_captured": g3.launches_captured, "graph_launches_per_step": 1}
+    del g3, m3, t3
     # ---- config 1: run_training_lite step (tri-modal lite net, label-smoothing CE, AdamW 5e-5 / 0.01, clip 1.0), batch 32
     torch.manual_seed(42)
     m1 = ImprovedTriModalFusionNetLite(64, 64, 6048).to(dev).train()

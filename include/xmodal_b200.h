@@ -443,6 +443,25 @@ int xm_sumsq_partials_f32(const float* g, int64_t n, double* partials, void* str
 int xm_clip_adamw_f32(float* p, float* g, float* m, float* v, int64_t n, const double* partials, int nblk, float max_norm,
                       float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step, float* norm_out,
                       void* stream);
+/* The same update with the 1-based step count (int64) and the learning rate (float) read from DEVICE memory, so a step
+ * captured in a CUDA graph replays with the values the host (or an increment node of the graph) left there. */
+int xm_clip_adamw_dev_f32(float* p, float* g, float* m, float* v, int64_t n, const double* partials, int nblk, float max_norm,
+                          const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, const int64_t* step_dev,
+                          float* norm_out, void* stream);
+
+/* ------------------------------------------------------------------ seed epoch (CUDA-graph replay of the step)
+ * Every dropout mask of this library is hash(seed, element); a captured launch freezes `seed`.  The library therefore
+ * folds a device-resident 64-bit epoch into every hash: masks = f(seed + epoch * odd constant, element).  The epoch is 0
+ * (seeds used as passed) until these entry points change it.
+ * xm_seed_epoch_init: allocates the counter on the current device (call once, outside stream capture).
+ * xm_seed_epoch_advance: epoch += 1 on `stream` -- one kernel node + six 8-byte device-to-device copies, capturable:
+ * placed first in a captured step, every replay draws fresh masks, identical in its forward and backward.
+ * xm_seed_epoch_set / _get: set (on `stream`) / read back (synchronous) the epoch, for tests and eager replays. */
+int xm_seed_epoch_init(void);
+int xm_seed_epoch_advance(void* stream);
+int xm_seed_epoch_set(uint64_t value, void* stream);
+int xm_seed_epoch_get(uint64_t* value_out);
+
 /* dst[dst_off[t] .. + numel[t]) = src[t][0 .. numel[t]) for t < n_tensors, one launch per 96 tensors: gathers the
  * per-parameter gradient tensors autograd produces into the flat bucket.  src / dst_off / numel are HOST arrays. */
 int xm_gather_flat_f32(const void* const* src, const int64_t* dst_off, const int64_t* numel, int n_tensors, float* dst,

@@ -833,6 +833,8 @@ static int fill_params(FaParams& p, int64_t B, int64_t L, int64_t H, int64_t dh,
 }  // namespace fa
 }  // namespace xm
 
+XM_DEFINE_SEED_EPOCH_SLOT(attention_fused)
+
 using namespace xm;
 using namespace xm::fa;
 

@@ -219,6 +219,8 @@ static int grid_for(int64_t rows) {
 }  // namespace ga
 }  // namespace xm
 
+XM_DEFINE_SEED_EPOCH_SLOT(attention_general)
+
 using namespace xm;
 
 extern "C" int xm_attn_general_supported(int64_t L, int64_t dh) {

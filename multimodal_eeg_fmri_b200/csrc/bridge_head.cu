@@ -84,6 +84,8 @@ cross2_kernel(const float* __restrict__ q, const float* __restrict__ kv, const f
 }  // namespace head
 }  // namespace xm
 
+XM_DEFINE_SEED_EPOCH_SLOT(bridge_head)
+
 using namespace xm;
 
 extern "C" {

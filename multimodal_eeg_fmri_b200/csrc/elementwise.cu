@@ -1091,6 +1091,8 @@ static int ew_grid(long long n) {
 
 }  // namespace xm
 
+XM_DEFINE_SEED_EPOCH_SLOT(elementwise)
+
 using namespace xm;
 
 extern "C" {

@@ -795,6 +795,8 @@ static int fill(Params& p, int64_t M, int64_t D, int64_t hidden, int act, float 
 }  // namespace ffn
 }  // namespace xm
 
+XM_DEFINE_SEED_EPOCH_SLOT(ffn_fused)
+
 using namespace xm;
 
 static long long* g_ffn_trace = nullptr;

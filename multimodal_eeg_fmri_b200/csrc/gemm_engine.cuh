@@ -152,7 +152,7 @@ XM_DEVICE float fast_exp2(float x) {
 }
 // 16-bit dropout lanes: one 64-bit hash per 4 consecutive columns of a row
 XM_DEVICE uint64_t hash_u64(uint64_t idx, uint64_t seed) {
-  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  uint64_t z = idx + epoch_seed(seed) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);

@@ -43,9 +43,20 @@ struct AdamArgs {
 
 __global__ void __launch_bounds__(kThreads)
 clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                  const double* __restrict__ partials, int nblk, AdamArgs a, float* __restrict__ norm_out) {
+                  const double* __restrict__ partials, int nblk, AdamArgs a, float* __restrict__ norm_out,
+                  const float* __restrict__ lr_dev, const long long* __restrict__ step_dev) {
   __shared__ double red[kThreads / 32];
-  __shared__ float s_coef;
+  __shared__ float s_coef, s_lr, s_c1, s_c2;
+  if (threadIdx.x == 32) {  // step count / learning rate from device memory (a captured step replays with fresh values)
+    s_lr = lr_dev != nullptr ? *lr_dev : a.lr;
+    s_c1 = a.bias_c1;
+    s_c2 = a.bias_c2_sqrt;
+    if (step_dev != nullptr) {
+      const double t = (double)*step_dev;
+      s_c1 = (float)(1.0 - pow((double)a.beta1, t));
+      s_c2 = (float)sqrt(1.0 - pow((double)a.beta2, t));
+    }
+  }
   double acc = 0.0;
   for (int i = threadIdx.x; i < nblk; i += kThreads) acc += partials[i];
   acc = warp_sum(acc);
@@ -62,7 +73,7 @@ clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
   }
   __syncthreads();
   const float coef = s_coef;
-  const float decay = 1.0f - a.lr * a.weight_decay, step = a.lr / a.bias_c1, inv_c2 = 1.0f / a.bias_c2_sqrt;
+  const float decay = 1.0f - s_lr * a.weight_decay, step = s_lr / s_c1, inv_c2 = 1.0f / s_c2;
   for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
     const float gi = g[i] * coef;
     const float mi = a.beta1 * m[i] + (1.0f - a.beta1) * gi;
@@ -127,8 +138,81 @@ extern "C" int xm_clip_adamw_f32(float* p, float* g, float* m, float* v, int64_t
   a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   int64_t blocks = (n + opt::kThreads - 1) / opt::kThreads;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  opt::clip_adamw_kernel<<<(int)blocks, opt::kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, partials, nblk, a, norm_out);
+  opt::clip_adamw_kernel<<<(int)blocks, opt::kThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, partials, nblk, a, norm_out,
+                                                                                  nullptr, nullptr);
   return check_launch();
+}
+
+extern "C" int xm_clip_adamw_dev_f32(float* p, float* g, float* m, float* v, int64_t n, const double* partials, int nblk,
+                                     float max_norm, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                                     const int64_t* step_dev, float* norm_out, void* stream) {
+  if (!p || !g || !m || !v || !partials || !lr_dev || !step_dev || n <= 0 || nblk <= 0) return XM_ERR_INVALID;
+  opt::AdamArgs a;
+  a.max_norm = max_norm; a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bias_c1 = 1.f; a.bias_c2_sqrt = 1.f;
+  int64_t blocks = (n + opt::kThreads - 1) / opt::kThreads;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  opt::clip_adamw_kernel<<<(int)blocks, opt::kThreads, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, partials, nblk, a, norm_out, lr_dev, reinterpret_cast<const long long*>(step_dev));
+  return check_launch();
+}
+
+// ---- seed epoch: one device counter, mirrored into the __constant__ slot of every translation unit that hashes ----
+extern "C" {
+void* xm_seed_epoch_slot_elementwise();
+void* xm_seed_epoch_slot_transformer();
+void* xm_seed_epoch_slot_bridge_head();
+void* xm_seed_epoch_slot_attention_general();
+void* xm_seed_epoch_slot_attention_fused();
+void* xm_seed_epoch_slot_ffn_fused();
+}
+
+namespace xm {
+namespace opt {
+constexpr int kEpochSlots = 6;
+struct EpochState {
+  unsigned long long* counter = nullptr;
+  void* slots[kEpochSlots] = {};
+  int device = -1;
+};
+static EpochState g_epoch;
+
+__global__ void seed_epoch_kernel(unsigned long long* counter, unsigned long long value, int add) {
+  *counter = add ? *counter + value : value;
+}
+
+static int epoch_ready() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return XM_ERR_LAUNCH;
+  if (g_epoch.counter != nullptr) return dev == g_epoch.device ? XM_OK : XM_ERR_INVALID;  // one GPU per process
+  void* (*const get[kEpochSlots])() = {xm_seed_epoch_slot_elementwise,        xm_seed_epoch_slot_transformer,
+                                       xm_seed_epoch_slot_bridge_head,        xm_seed_epoch_slot_attention_general,
+                                       xm_seed_epoch_slot_attention_fused,    xm_seed_epoch_slot_ffn_fused};
+  for (int i = 0; i < kEpochSlots; ++i)
+    if ((g_epoch.slots[i] = get[i]()) == nullptr) return XM_ERR_LAUNCH;
+  if (cudaMalloc(&g_epoch.counter, sizeof(unsigned long long)) != cudaSuccess) return XM_ERR_LAUNCH;
+  if (cudaMemset(g_epoch.counter, 0, sizeof(unsigned long long)) != cudaSuccess) return XM_ERR_LAUNCH;
+  g_epoch.device = dev;
+  return XM_OK;
+}
+
+static int epoch_update(unsigned long long value, int add, cudaStream_t st) {
+  if (g_epoch.counter == nullptr) return XM_ERR_INVALID;  // xm_seed_epoch_init first (it allocates: not capturable)
+  seed_epoch_kernel<<<1, 1, 0, st>>>(g_epoch.counter, value, add);
+  for (int i = 0; i < kEpochSlots; ++i)
+    if (cudaMemcpyAsync(g_epoch.slots[i], g_epoch.counter, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return XM_ERR_LAUNCH;
+  return check_launch();
+}
+}  // namespace opt
+}  // namespace xm
+
+extern "C" int xm_seed_epoch_init(void) { return opt::epoch_ready(); }
+extern "C" int xm_seed_epoch_advance(void* stream) { return opt::epoch_update(1ull, 1, (cudaStream_t)stream); }
+extern "C" int xm_seed_epoch_set(uint64_t value, void* stream) { return opt::epoch_update(value, 0, (cudaStream_t)stream); }
+extern "C" int xm_seed_epoch_get(uint64_t* value_out) {
+  if (!value_out || opt::g_epoch.counter == nullptr) return XM_ERR_INVALID;
+  return cudaMemcpy(value_out, opt::g_epoch.counter, sizeof(uint64_t), cudaMemcpyDeviceToHost) == cudaSuccess ? XM_OK : XM_ERR_LAUNCH;
 }
 
 extern "C" int xm_gather_flat_f32(const void* const* src, const int64_t* dst_off, const int64_t* numel, int n_tensors, float* dst,

@@ -258,6 +258,8 @@ static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<
 
 }  // namespace xm
 
+XM_DEFINE_SEED_EPOCH_SLOT(transformer)
+
 using namespace xm;
 
 extern "C" {

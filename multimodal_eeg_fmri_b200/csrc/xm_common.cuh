@@ -89,7 +89,22 @@ XM_DEVICE float gelu_erf_grad(float x) {
 // seed-keyed index; ~10 integer instructions -- the streaming kernels that apply dropout next to an erf
 // GELU are instruction-bound, a 64-bit mixer doubled their integer work).
 // keep  <=>  hash >= threshold, threshold = p * 2^32.
+//
+// Seed epoch (CUDA-graph replay): a captured launch carries its 64-bit seed as a frozen kernel argument, so every hash
+// folds in a per-translation-unit constant that xm_seed_epoch_advance / xm_seed_epoch_set refresh from ONE device
+// counter (a kernel node + 8-byte copy nodes inside the graph): replay k draws the masks of (seed, epoch k), forward
+// and backward alike.  The epoch is 0 unless those entry points are used, which leaves every seed as passed.
+static __constant__ unsigned long long xm_seed_epoch_c = 0ull;
+XM_DEVICE uint64_t epoch_seed(uint64_t seed) { return seed + xm_seed_epoch_c * 0xD1B54A32D192ED03ull; }
+// Defines this translation unit's accessor for the library-wide refresh (csrc/optimizer.cu).
+#define XM_DEFINE_SEED_EPOCH_SLOT(tu)                                                     \
+  extern "C" __attribute__((visibility("hidden"))) void* xm_seed_epoch_slot_##tu() {     \
+    void* p = nullptr;                                                                    \
+    return cudaGetSymbolAddress(&p, xm::xm_seed_epoch_c) == cudaSuccess ? p : nullptr;    \
+  }
+
 XM_DEVICE uint32_t hash_u32(uint64_t idx, uint64_t seed) {
+  seed = epoch_seed(seed);
   uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x9E3779B1u) ^ (uint32_t)seed;
   x *= 0x85EBCA6Bu;
   x ^= x >> 13;

@@ -8,7 +8,6 @@ stored; values that feed the next tensor-core contraction are rounded to tf32 wh
 """
 from __future__ import annotations
 
-import itertools
 import os
 from dataclasses import dataclass
 from typing import Optional
@@ -58,7 +57,7 @@ def set_parallel_context(ctx: ParallelContext) -> None:
     _CTX = ctx
 
 
-_seed_counter = itertools.count(1)
+_seed_counter = 0  # seeds drawn since manual_seed
 _base_seed = 0x5EED
 
 
@@ -66,11 +65,23 @@ def manual_seed(seed: int) -> None:
     """Re-seed the dropout mask stream (counter-based: mask = hash(seed, element index))."""
     global _seed_counter, _base_seed
     _base_seed = int(seed) & 0xFFFFFFFF
-    _seed_counter = itertools.count(1)
+    _seed_counter = 0
 
 
 def next_seed() -> int:
-    return ((_base_seed << 32) ^ (next(_seed_counter) * 0x9E3779B1) ^ (_CTX.rank << 20)) & 0x7FFFFFFFFFFFFFFF
+    global _seed_counter
+    _seed_counter += 1
+    return ((_base_seed << 32) ^ (_seed_counter * 0x9E3779B1) ^ (_CTX.rank << 20)) & 0x7FFFFFFFFFFFFFFF
+
+
+def seed_state():
+    """(base seed, seeds drawn): restore with set_seed_state to re-draw the same seeds."""
+    return _base_seed, _seed_counter
+
+
+def set_seed_state(state) -> None:
+    global _seed_counter, _base_seed
+    _base_seed, _seed_counter = int(state[0]), int(state[1])
 
 
 class _PeerReduce:

@@ -1104,3 +1104,44 @@ def clip_adamw_(p, g, m, v, step, lr, weight_decay, max_norm=1.0, betas=(0.9, 0.
     _call("xm_clip_adamw_f32", _p(p), _p(g), _p(m), _p(v), n, _p(part), nblk, float(max_norm), float(lr), float(betas[0]),
           float(betas[1]), float(eps), float(weight_decay), int(step), _p(norm), _stream())
     return norm
+
+
+def clip_adamw_dev_(p, g, m, v, step_dev, lr_dev, weight_decay, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8):
+    """clip_adamw_ with the 1-based step count (int64, 1 element) and the learning rate (float32, 1 element) read from
+    device memory: the form a CUDA-graph capture of the step needs (kernel arguments are frozen at capture)."""
+    _chk(p, g, m, v, lr_dev)
+    if step_dev.dtype != torch.int64 or not step_dev.is_cuda:
+        raise _lib.XmodalError("step_dev: 1-element int64 CUDA tensor expected")
+    n = p.numel()
+    nblk = _lib.lib().xm_sumsq_nblk(n)
+    part = torch.empty(nblk, device=p.device, dtype=torch.float64)
+    norm = torch.empty(1, device=p.device, dtype=torch.float32)
+    _w(2.0 * n, 4.0 * n)
+    _call("xm_sumsq_partials_f32", _p(g), n, _p(part), _stream())
+    _w(12.0 * n, 28.0 * n)
+    _call("xm_clip_adamw_dev_f32", _p(p), _p(g), _p(m), _p(v), n, _p(part), nblk, float(max_norm), _p(lr_dev), float(betas[0]),
+          float(betas[1]), float(eps), float(weight_decay), _p(step_dev), _p(norm), _stream())
+    return norm
+
+
+# -- seed epoch (include/xmodal_b200.h): device-resident counter folded into every dropout hash ----------------------
+def seed_epoch_init() -> None:
+    """Allocate the counter on the current device (not capturable; idempotent)."""
+    _lib.call("xm_seed_epoch_init")
+
+
+def seed_epoch_advance() -> None:
+    """epoch += 1 on the current stream (capturable: first node of a captured step)."""
+    _call("xm_seed_epoch_advance", _stream())
+
+
+def seed_epoch_set(value: int) -> None:
+    seed_epoch_init()
+    _call("xm_seed_epoch_set", int(value), _stream())
+
+
+def seed_epoch_get() -> int:
+    seed_epoch_init()
+    out = ctypes.c_uint64(0)
+    _lib.call("xm_seed_epoch_get", ctypes.byref(out))
+    return int(out.value)

@@ -155,6 +155,8 @@ class PairedTrainer:
             p.grad = None
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, (0.9, 0.999), 1e-8
         self.step_count = 0
+        self._step_dev = self._lr_dev = None  # set by use_device_state()
+        self._lr_on_device = None
         self.last_grad_norm = None  # pre-clip total norm of the last step (device scalar)
         self.ctx = XF.parallel_context()
         self._stage = {}
@@ -220,9 +222,38 @@ class PairedTrainer:
         if self.ctx.active:
             self._allreduce_gradients()
         self.step_count += 1
-        self.last_grad_norm = ops.clip_adamw_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count,
-                                              self.lr, self.weight_decay, self.grad_clip or 0.0, self.betas, self.eps)
+        if self._step_dev is None:
+            self.last_grad_norm = ops.clip_adamw_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
+                                                  self.step_count, self.lr, self.weight_decay, self.grad_clip or 0.0,
+                                                  self.betas, self.eps)
+        else:  # device-resident step count / learning rate (a captured step replays with the values left there)
+            if not torch.cuda.is_current_stream_capturing():
+                self._sync_lr()
+            self._step_dev.add_(1)
+            self.last_grad_norm = ops.clip_adamw_dev_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq,
+                                                      self._step_dev, self._lr_dev, self.weight_decay,
+                                                      self.grad_clip or 0.0, self.betas, self.eps)
         return loss.detach()
+
+    # -- device-resident optimizer scalars + CUDA-graph capture ----------------------------------------
+    def use_device_state(self) -> None:
+        """Move the AdamW step count and the learning rate into device memory (idempotent).  Eager steps and graph
+        replays then share them: `self.lr` may be changed between steps, `self.step_count` keeps counting both."""
+        if self._step_dev is None:
+            dev = self.flat_param.device
+            self._step_dev = torch.full((1,), self.step_count, device=dev, dtype=torch.int64)
+            self._lr_dev = torch.full((1,), float(self.lr), device=dev, dtype=torch.float32)
+            self._lr_on_device = float(self.lr)
+
+    def _sync_lr(self) -> None:
+        if self._lr_on_device != float(self.lr):
+            self._lr_dev.fill_(float(self.lr))
+            self._lr_on_device = float(self.lr)
+
+    def capture(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None,
+                warmup: int = 1) -> "GraphedStep":
+        """-> the step on inputs of these shapes as ONE CUDA-graph launch (see GraphedStep)."""
+        return GraphedStep(self, eeg, roi_series, conn, warmup)
 
     # -- end-to-end step from pinned host buffers --------------------------------------------
     def step_from_host(self, eeg_h: torch.Tensor, roi_h: torch.Tensor, conn_h: Optional[torch.Tensor] = None) -> float:
@@ -290,6 +321,95 @@ class PairedTrainer:
         done[-1].synchronize()
         losses.append(float(pinned[len(batches) - 1]))
         return losses
+
+
+class GraphedStep:
+    """One `PairedTrainer.step` -- window gather, both encoders, InfoNCE, backward, clip_grad_norm_, AdamW: every launch
+    of _test_bridge.py:775-788's recipe -- captured once in a CUDA graph and replayed as ONE launch.  The small
+    configurations are bound by the ~200 C-ABI calls the host issues per step (BASELINE config 3, batch 256: 6.2 ms
+    eager); a replay costs what the kernels cost.
+
+    What a capture freezes, and how each piece still changes per replay:
+      * inputs: static device buffers, refilled by `__call__` (device or pinned host tensors of the captured shapes);
+      * dropout: every seed is a frozen kernel argument; the graph's first node advances the library's device-resident
+        seed epoch, which every mask hash folds in (ops.seed_epoch_advance) -- fresh masks per replay, the same in the
+        forward and the backward of one replay;
+      * AdamW: step count and learning rate live in device memory (PairedTrainer.use_device_state): the count is
+        incremented by a node of the graph, `trainer.lr` is written before the replay when it changed;
+      * BatchNorm running statistics and num_batches_tracked are updated by captured device operations.
+    The warm-up step(s) the capture needs (lazy initialisation must not happen inside a capture) run on a copy of the
+    training state that is restored afterwards, so constructing a GraphedStep does not train.  Single process only: the
+    data-parallel exchanges pass per-call sequence numbers as kernel arguments."""
+
+    def __init__(self, trainer: "PairedTrainer", eeg: torch.Tensor, roi_series: torch.Tensor,
+                 conn: Optional[torch.Tensor] = None, warmup: int = 1):
+        if trainer.ctx.active:
+            raise ops._lib.XmodalError("GraphedStep: single-process steps only (the data-parallel step is not capturable)")
+        dev = trainer.flat_param.device
+        if dev.type != "cuda":
+            raise ops._lib.XmodalError("GraphedStep needs a CUDA device")
+        self.trainer = trainer
+        ops.seed_epoch_init()
+        trainer.use_device_state()
+        self._in = [torch.empty(t.shape, device=dev, dtype=t.dtype).copy_(t, non_blocking=True) if t is not None else None
+                    for t in (eeg, roi_series, conn)]
+        args = [t for t in self._in if t is not None]
+        cur = torch.cuda.current_stream(dev)
+        # -- warm-up on a snapshot of the training state
+        model = trainer.model
+        saved = {k: v.clone() for k, v in model.state_dict().items()}
+        moments = (trainer.exp_avg.clone(), trainer.exp_avg_sq.clone())
+        count, seeds = trainer.step_count, XF.seed_state()
+        epoch = ops.seed_epoch_get()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                trainer.step(*args)
+        cur.wait_stream(side)
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(saved[k])
+            trainer.exp_avg.copy_(moments[0])
+            trainer.exp_avg_sq.copy_(moments[1])
+            trainer._step_dev.fill_(count)
+        trainer.step_count = count
+        XF.set_seed_state(seeds)  # (the warm-up drew host seeds; replays of this graph start from the same ones)
+        ops.seed_epoch_set(epoch)
+        trainer._sync_lr()
+        # -- capture
+        for p in trainer.params:
+            p.grad = None
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        launches = ops.launch_count()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            ops.seed_epoch_advance()
+            self._loss = trainer.step(*args)
+        self.launches_captured = ops.launch_count() - launches  # C-ABI calls inside the graph
+        trainer.step_count = count  # the capture ran the host side of one step, not the device side
+
+    def __call__(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Refill the static inputs (asynchronous copies on the current stream), replay, return the loss (device scalar)."""
+        for dst, src in zip(self._in, (eeg, roi_series, conn)):
+            if (dst is None) != (src is None):
+                raise ValueError("GraphedStep: the captured step had a different set of inputs")
+            if dst is not None and src is not dst:
+                if src.shape != dst.shape:
+                    raise ValueError(f"GraphedStep: input of shape {tuple(src.shape)}, captured {tuple(dst.shape)}")
+                dst.copy_(src, non_blocking=True)
+        return self.replay()
+
+    def replay(self) -> torch.Tensor:
+        """One step on whatever the static inputs (`self.inputs`) hold."""
+        self.trainer._sync_lr()
+        self.graph.replay()
+        self.trainer.step_count += 1
+        return self._loss.clone()
+
+    @property
+    def inputs(self):
+        return self._in
 
 
 def train_bridge_epoch(model, loader, optimizer, criterion, device, grad_clip: float = 1.0) -> float:
