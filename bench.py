@@ -215,7 +215,7 @@ def _extras(dev, rank, world, barrier, hbm):
     from multimodal_eeg_fmri_b200 import eeg_data_utils as edu, ops, synthetic
     from multimodal_eeg_fmri_b200.modules import LabelSmoothingCrossEntropy, fMRIFusionNet
     from multimodal_eeg_fmri_b200.run_training_lite import ImprovedTriModalFusionNetLite
-    from multimodal_eeg_fmri_b200.training import PairedBridgeModel, PairedTrainer
+    from multimodal_eeg_fmri_b200.training import GraphedCallable, PairedBridgeModel, PairedTrainer
 
     out = {}
     # ---- config 5: band power of 128-channel 1 kHz recordings, win 1024 / hop 512, windows read in place
@@ -264,7 +264,8 @@ def _extras(dev, rank, world, barrier, hbm):
     # ---- config 1: run_training_lite step (tri-modal lite net, label-smoothing CE, AdamW 5e-5 / 0.01, clip 1.0), batch 32
     torch.manual_seed(42)
     m1 = ImprovedTriModalFusionNetLite(64, 64, 6048).to(dev).train()
-    crit, opt1 = LabelSmoothingCrossEntropy(0.1), torch.optim.AdamW(m1.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
+    crit = LabelSmoothingCrossEntropy(0.1)
+    opt1 = torch.optim.AdamW(m1.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
     erp, pw, cn = torch.randn(32, 64, 500, device=dev), torch.randn(32, 64, 500, device=dev), torch.randn(32, 6048, device=dev)
     y = torch.randint(0, 2, (32,), device=dev)
 
@@ -276,10 +277,12 @@ def _extras(dev, rank, world, barrier, hbm):
     ms1 = step_time(step1)
     out["config1_lite_b32"] = {"metric": "tri-modal lite train samples/sec", "value": round(32 / (ms1 * 1e-3), 1), "unit": UNIT,
                                "batch": 32, "ms_per_step": round(ms1, 3)}
+    # (not graph-captured: the reference's lite wrapper reads its fusion weights back to the host in every forward,
+    #  crossmodal_v4_enhancements.py:803-806, and so does this one)
     # ---- config 2: run_fmri_v11 step (fMRIFusionNet 400 / 40 000, weighted CE, AdamW 1e-4, clip 1.0), batch 64
     torch.manual_seed(42)
     m2 = fMRIFusionNet(400, 40000).to(dev).train()
-    opt2 = torch.optim.AdamW(m2.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+    opt2 = torch.optim.AdamW(m2.parameters(), lr=1e-4, weight_decay=1e-4, fused=True, capturable=True)
     act, conn2, y2 = torch.randn(64, 400, device=dev), torch.randn(64, 40000, device=dev), torch.randint(0, 2, (64,), device=dev)
 
     def step2():
@@ -290,6 +293,11 @@ def _extras(dev, rank, world, barrier, hbm):
     ms2 = step_time(step2)
     out["config2_fmri_b64"] = {"metric": "fMRI ROI encoder train samples/sec", "value": round(64 / (ms2 * 1e-3), 1), "unit": UNIT,
                                "batch": 64, "ms_per_step": round(ms2, 3)}
+    g2 = GraphedCallable(lambda *_: step2(), [act, conn2, y2], [m2], [opt2])
+    ms2g = step_time(g2.graph.replay)
+    out["config2_fmri_b64"]["graphed"] = {"value": round(64 / (ms2g * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms2g, 3),
+                                          "c_abi_calls_captured": g2.launches_captured}
+    del g2
     return out
 
 

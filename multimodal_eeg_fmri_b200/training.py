@@ -412,6 +412,61 @@ class GraphedStep:
         return self._in
 
 
+class GraphedCallable:
+    """Any training step built from this package's modules -- `fn(*static_inputs)` doing zero_grad -> forward -> backward
+    -> clip -> optimizer.step, e.g. the recipes of run_training_lite.py:478-489 / run_fmri_v11.py:430-450 -- captured in a
+    CUDA graph.  The graph's first node advances the seed epoch (fresh dropout masks per replay, see GraphedStep); the
+    torch optimizers must be built with `capturable=True` (their step counters then live on the device).  `fn` runs
+    `warmup` times before the capture; the state of `modules` and `optimizers` is restored afterwards (optimizer state the
+    warm-up created is zeroed in place).  `fn` must not read device values back (no .item() / .tolist()).  `fn` may
+    return a tensor (e.g. the loss): `__call__` returns a copy of it."""
+
+    def __init__(self, fn, static_inputs, modules=(), optimizers=(), warmup: int = 1):
+        import copy
+        self.fn, self.inputs = fn, list(static_inputs)
+        dev = self.inputs[0].device
+        ops.seed_epoch_init()
+        saved_m = [copy.deepcopy(m.state_dict()) for m in modules]
+        saved_o = [copy.deepcopy(o.state_dict()) for o in optimizers]
+        seeds, epoch = XF.seed_state(), ops.seed_epoch_get()
+        cur, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                fn(*self.inputs)
+        cur.wait_stream(side)
+        for m, sd in zip(modules, saved_m):
+            m.load_state_dict(sd)
+        for o, sd in zip(optimizers, saved_o):
+            if sd["state"]:
+                o.load_state_dict(sd)
+            else:  # state first created by the warm-up: keep the tensors (a capture must not allocate and re-zero them on
+                # every replay) and reset them to the zeros torch's Adam-family optimizers start from
+                for st in o.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+        XF.set_seed_state(seeds)
+        ops.seed_epoch_set(epoch)
+        for m in modules:
+            for p in m.parameters():
+                p.grad = None
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        launches = ops.launch_count()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            ops.seed_epoch_advance()
+            self._out = fn(*self.inputs)
+        self.launches_captured = ops.launch_count() - launches
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self._out.clone() if torch.is_tensor(self._out) else self._out
+
+
 def train_bridge_epoch(model, loader, optimizer, criterion, device, grad_clip: float = 1.0) -> float:
     """_test_bridge.py:775-788 -- supervised bridge epoch (CE on logits), same recipe and return value."""
     model.train()

@@ -158,3 +158,46 @@ def test_graphed_step_with_window_gather_and_host_inputs():
     g = tr.capture(rec, roi)
     losses = [float(g(rec, roi)) for _ in range(6)]
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
+
+
+def test_graphed_callable_replays_the_fmri_recipe():
+    """run_fmri_v11.py:430-450's step (CE, clip_grad_norm_, torch AdamW) through GraphedCallable: constructing it does not
+    train, replays equal eager steps at the same (host seeds, seed epoch), torch's capturable optimizer counts on the device."""
+    from multimodal_eeg_fmri_b200 import functional as XF, ops
+    from multimodal_eeg_fmri_b200.modules import fMRIFusionNet
+    from multimodal_eeg_fmri_b200.training import GraphedCallable
+    act, conn = torch.randn(64, 40, device="cuda"), torch.randn(64, 400, device="cuda")
+    y = torch.randint(0, 2, (64,), device="cuda")
+
+    def make():
+        torch.manual_seed(1)
+        m = fMRIFusionNet(40, 400).cuda().train()
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-4, capturable=True)
+
+        def step(a, c, t):
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(m(a, c), t)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+            return loss.detach()
+        return m, opt, step
+
+    ma, oa, step_a = make()
+    mb, ob, step_b = make()
+    before = {k: v.clone() for k, v in ma.state_dict().items()}
+    XF.manual_seed(5)
+    g = GraphedCallable(step_a, [act, conn, y], [ma], [oa])
+    for k, v in ma.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    base = XF.seed_state()[0]
+    lg = [float(g(act, conn, y)) for _ in range(3)]
+    le = []
+    for k in (1, 2, 3):
+        XF.set_seed_state((base, 0))
+        ops.seed_epoch_set(k)
+        le.append(float(step_b(act, conn, y)))
+    assert lg == le, (lg, le)
+    for (k, a), b in zip(ma.state_dict().items(), mb.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert lg[2] < lg[0]

@@ -15,7 +15,7 @@ try:
     print("roofline", {k: d["roofline"][k] for k in ("achieved", "peak", "frac", "share_of_step")})
     print("cpu_baseline", d.get("cpu_baseline"))
     print("torch_eager_gpu", d.get("torch_eager_gpu"))
-    print("extras", {k: (v.get("value"), v.get("ms_per_step")) for k, v in d.get("extras", {}).items()})
+    print("extras", {k: (v.get("value"), v.get("ms_per_step"), v.get("graphed")) for k, v in d.get("extras", {}).items()})
 except Exception as e:
     print("bench parse failed", e)
 PY
