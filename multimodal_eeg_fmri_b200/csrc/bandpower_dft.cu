@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/xmodal_b200.h"
 #include "gemm_engine.cuh"
@@ -290,6 +291,284 @@ bandpower_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Overlap kernel (hop == win / 2, win % 64 == 0: Welch-style half-overlapping windows, BASELINE config 5; v1 above
+// serves every other shape).  What the measurements of v1 and three intermediate variants say
+// (profiles/r2_bandpower_experiments.txt):
+//   * an MMA whose A operand comes from tensor memory costs 80 clk PER 64 COLUMNS of N (N-stacking the twiddles does
+//     not make it cheaper); an MMA with both operands in shared memory costs (A + B bytes) / ~105 B/clk, and that port is
+//     shared with the TMA writes and the transform warps' loads: v1 is MMA-bound (12 x 80 clk per 32-sample block),
+//     an all-shared-memory variant is port-bound (120 KB per block);
+//   * switching the accumulator between MMAs costs nothing measurable; the loads are not the limit (the producer waits on
+//     `empty` 60 % of the time).
+// So the way forward is fewer MMA-cycles and fewer shared-memory bytes PER WINDOW: a 32-sample block of a recording
+// belongs to TWO windows (second half of window w, first half of window w + 1), and here it is loaded, split and
+// multiplied ONCE for both:
+//      D[128 ch, 256] (+)= x_blk (raw fp32 tile in shared memory = hi by truncation) * [Thi(kb+H) ; Thi(kb) ; Tlo(kb+H) ; Tlo(kb)]^T
+//      L[128 ch, 128] (+)= lo_blk (tensor memory)                                     * [Thi(kb+H) ; Thi(kb)]^T
+// one N = 256 MMA (tensor-core math rate, 128 clk) and one N = 128 MMA (160 clk) per k8: 1152 clk per block for two
+// windows instead of 2 x 960, 128 KB of shared-memory traffic instead of 2 x 72 KB, and every sample crosses L2 -> SM once.
+// Columns: [0, 64) older window x Thi, [64, 128) newer window x Thi, [128, 192) older x Tlo, [192, 256) newer x Tlo.
+// The lo products go to an accumulator of their own (columns [320, 448)): they are 2^-11 of the sums, so their accumulation
+// error is irrelevant, and keeping them out of the main accumulator halves ITS accumulation steps -- the tensor core
+// truncates at every step, which is this path's error floor (measured max relative error against the fp64 oracle,
+// tools/bp_err.py: v1 4.7e-6; here 4.6e-6 with one drain per hop of 16 blocks, 2.5e-6 with XM_BP_CHUNK=8 at -3 % speed).
+// Four epilogue warps drain the accumulators at every chunk end (a hop, or `XM_BP_CHUNK` blocks) and keep the two live
+// windows' partial sums in registers (setmaxnreg: 232 registers for them, 64 / 112 for the other roles -- with one budget
+// for all, one of the four arrays lived in local memory); at a hop boundary the older window is finished (band sums ->
+// HBM) and the newer one becomes the older one.  A CTA walks an item = (recording, channel tile, run of <= 16 windows)
+// along the time axis; the first / last hop of an item computes one half-window that belongs to its neighbour and is
+// dropped (1/16 overhead).
+constexpr int kThreads2 = 3 * 128;  // warpgroup 0: TMA producer, MMA issuer (+ 2 idle warps); 1: transform; 2: epilogue
+constexpr int kStages2 = 4;
+constexpr int kStageBytes2 = 16384 + 4 * 8192;  // x | Thi(old) | Thi(new) | Tlo(old) | Tlo(new)
+constexpr int kSmem2 = kStages2 * kStageBytes2 + 1024;
+constexpr float kTruncComp = 1.0f + 0.7213f / 2048.0f;  // makes the tensor core's truncation of lo zero-mean
+
+struct Params2 {
+  int C, n_win, HB, chunk_len, chunks_per_seg, n_bands, ct, wpi, ipr;  // HB = blocks per hop; wpi = windows per item; ipr = items per recording
+  long long items;                                                      // n_rec * ct * ipr
+  const Tables* tab;
+  float* power;
+};
+
+struct Bars2 {
+  uint64_t full[kStages2], empty[kStages2];
+  uint64_t lo_ready[2], lo_free[2];
+  uint64_t acc_full, acc_free;
+};
+
+struct Item2 {
+  int r, ct, w0, nw;  // recording, channel tile, first window, windows in this item
+};
+XM_DEVICE Item2 decode_item2(const Params2& p, long long it) {
+  Item2 q;
+  const int piece = (int)(it % p.ipr);
+  const long long rc = it / p.ipr;
+  q.ct = (int)(rc % p.ct);
+  q.r = (int)(rc / p.ct);
+  q.w0 = piece * p.wpi;
+  q.nw = min(p.wpi, p.n_win - q.w0);
+  return q;
+}
+
+// TMEM: main accumulator columns [0, 256); lo operand buffers b = 0, 1 at 256 + 32 b; lo-product accumulator [320, 448)
+__global__ void __launch_bounds__(kThreads2, 1)
+bandpower_dft2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmThi,
+                      const __grid_constant__ CUtensorMap tmTlo, const Params2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Bars2 bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmThi);
+    ptx::prefetch_tensormap(&tmTlo);
+    for (int i = 0; i < kStages2; ++i) {
+      ptx::mbar_init(&bar.full[i], 1);
+      ptx::mbar_init(&bar.empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bar.lo_ready[i], 4);
+      ptx::mbar_init(&bar.lo_free[i], 1);
+    }
+    ptx::mbar_init(&bar.acc_full, 1);
+    ptx::mbar_init(&bar.acc_free, 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tOp = tmem + 256u, tLoAcc = tmem + 320u;
+
+  // Register budget per warpgroup (setmaxnreg): the epilogue warps hold the partial sums of two windows (128 registers)
+  // plus two 32-column loads; 168 registers for everybody spilled one of the four arrays to local memory.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+        const Item2 q = decode_item2(p, it);
+        const int nblk = (q.nw + 1) * p.HB;
+        const int b0 = q.w0 * p.HB;
+        for (int i = 0; i < nblk; ++i) {
+          const int kb = i % p.HB;  // k-block of the newer window; the older one is at kb + HB
+          ptx::mbar_wait(&bar.empty[s], ph ^ 1u);
+          uint8_t* st = smem + s * kStageBytes2;
+          ptx::mbar_arrive_expect_tx(&bar.full[s], kStageBytes2);
+          ptx::tma_load_3d(&tmX, &bar.full[s], st, (b0 + i) * 32, q.ct * 128, q.r);
+          ptx::tma_load_3d(&tmThi, &bar.full[s], st + 16384, (kb + p.HB) * 32, 0, 0);
+          ptx::tma_load_3d(&tmThi, &bar.full[s], st + 24576, kb * 32, 0, 0);
+          ptx::tma_load_3d(&tmTlo, &bar.full[s], st + 32768, (kb + p.HB) * 32, 0, 0);
+          ptx::tma_load_3d(&tmTlo, &bar.full[s], st + 40960, kb * 32, 0, 0);
+          if (++s == kStages2) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc256 = ptx::make_idesc_tf32(128, 256, 0, 0), idesc128 = ptx::make_idesc_tf32(128, 128, 0, 0);
+    const uint64_t dx0 = ptx::make_smem_desc(ptx::smem_u32(smem), 16, 1024, 2);
+    const uint64_t dt0 = ptx::make_smem_desc(ptx::smem_u32(smem) + 16384, 16, 1024, 2);
+    int s = 0;
+    uint32_t ph = 0, kbg = 0, cg = 0;  // cg = chunks started so far
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item2 q = decode_item2(p, it);
+      const int nblk = (q.nw + 1) * p.HB;
+      for (int i = 0; i < nblk; ++i, ++kbg) {
+        const int kb = i % p.HB;
+        const bool first = (kb % p.chunk_len) == 0;
+        const bool last = ((kb + 1) % p.chunk_len) == 0 || kb == p.HB - 1;
+        if (first) {  // the epilogue warps have drained the previous chunk
+          ptx::mbar_wait(&bar.acc_free, (cg & 1u) ^ 1u);
+          ptx::tc_fence_after_sync();
+          ++cg;
+        }
+        ptx::mbar_wait(&bar.full[s], ph);
+        const uint32_t lb = kbg & 1u;
+        ptx::mbar_wait(&bar.lo_ready[lb], (kbg >> 1) & 1u);  // lo of this block is in tensor memory
+        ptx::tc_fence_after_sync();
+        const uint64_t so = (uint64_t)((uint32_t)s * (uint32_t)(kStageBytes2 >> 4));
+        const uint64_t dt = dt0 + so, dx = dx0 + so;
+        const uint32_t tl = tOp + lb * 32u;
+        const uint32_t acc0 = first ? 0u : 1u;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8)  // x * [Thi(old) ; Thi(new) ; Tlo(old) ; Tlo(new)], A = the raw sample tile
+            ptx::mma_tf32_ss(tmem, dx + (uint64_t)(k8 * 2), dt + (uint64_t)(k8 * 2), idesc256, k8 == 0 ? acc0 : 1u);
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8)  // lo * [Thi(old) ; Thi(new)] into its own accumulator, one run per hop
+            mma_tf32_ts(tLoAcc, tl + (uint32_t)(k8 * 8), dt + (uint64_t)(k8 * 2), idesc128, (k8 == 0 && kb == 0) ? 0u : 1u);
+          ptx::mma_commit(&bar.empty[s]);
+          ptx::mma_commit(&bar.lo_free[lb]);
+          if (last) ptx::mma_commit(&bar.acc_full);
+        }
+        __syncwarp();
+        if (++s == kStages2) { s = 0; ph ^= 1u; }
+      }
+    }
+  }  // (warps 2, 3: idle)
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;" ::: "memory");
+    const int q4 = warp & 3;  // TMEM lane quadrant of this warp
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int row = q4 * 32 + lane;  // channel inside the tile
+    int s = 0;
+    uint32_t ph = 0, kbg = 0;
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item2 q = decode_item2(p, it);
+      const int nblk = (q.nw + 1) * p.HB;
+      for (int i = 0; i < nblk; ++i, ++kbg) {
+        const uint32_t lb = kbg & 1u;
+        ptx::mbar_wait(&bar.full[s], ph);
+        const uint8_t* xt = smem + s * kStageBytes2 + row * 128;
+        uint32_t rl[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 16-B chunk j of row `row` sits at chunk j ^ (row & 7) (SWIZZLE_128B)
+          const uint4 v = *reinterpret_cast<const uint4*>(xt + ((j ^ (row & 7)) << 4));
+          const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            rl[4 * j + e] = __float_as_uint((__uint_as_float(xs[e]) - __uint_as_float(xs[e] & 0xFFFFE000u)) * kTruncComp);
+        }
+        ptx::mbar_wait(&bar.lo_free[lb], ((kbg >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer have retired
+        ptx::tc_fence_after_sync();
+        ptx::tmem_st_32x32(tOp + lb * 32u + lane_base, rl);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar.lo_ready[lb]);
+        if (++s == kStages2) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    const int q4 = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const int row = q4 * 32 + lane;
+    uint32_t cg = 0;  // chunks drained so far
+    for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item2 q = decode_item2(p, it);
+      const int ch = q.ct * 128 + row;
+      float ore[32], oim[32], nre[32], nim[32];  // partial sums of the older / newer live window
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ore[j] = oim[j] = nre[j] = nim[j] = 0.f;
+      for (int seg = 0; seg <= q.nw; ++seg) {
+        for (int c = 0; c < p.chunks_per_seg; ++c, ++cg) {
+          ptx::mbar_wait(&bar.acc_full, cg & 1u);
+          ptx::tc_fence_after_sync();
+          uint32_t a[32], b[32];
+#define XM_BP_DRAIN(col_a, col_b, dst)                                   \
+  ptx::tmem_ld_32x32(tmem + (uint32_t)(col_a) + lane_base, a);           \
+  ptx::tmem_ld_32x32(tmem + (uint32_t)(col_b) + lane_base, b);           \
+  ptx::tmem_ld_wait();                                                   \
+  _Pragma("unroll") for (int j = 0; j < 32; ++j) dst[j] += __uint_as_float(a[j]) + __uint_as_float(b[j]);
+          XM_BP_DRAIN(0, 128, ore)
+          XM_BP_DRAIN(32, 160, oim)
+          XM_BP_DRAIN(64, 192, nre)
+          XM_BP_DRAIN(96, 224, nim)
+          if (c == p.chunks_per_seg - 1) {  // the hop's lo products
+            ptx::tmem_ld_32x32(tmem + 320u + lane_base, a);
+            ptx::tmem_ld_32x32(tmem + 352u + lane_base, b);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              ore[j] += __uint_as_float(a[j]);
+              oim[j] += __uint_as_float(b[j]);
+            }
+            ptx::tmem_ld_32x32(tmem + 384u + lane_base, a);
+            ptx::tmem_ld_32x32(tmem + 416u + lane_base, b);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              nre[j] += __uint_as_float(a[j]);
+              nim[j] += __uint_as_float(b[j]);
+            }
+          }
+#undef XM_BP_DRAIN
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bar.acc_free);
+        }
+        // hop boundary: the older window (w0 + seg - 1) is complete; the newer one becomes the older one
+        if (seg >= 1 && ch < p.C) {
+          const long long g = (long long)q.r * p.n_win + q.w0 + seg - 1;
+          float* out = p.power + (g * p.C + ch) * p.n_bands;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ore[j] = fmaf(ore[j], ore[j], oim[j] * oim[j]) * __ldg(&p.tab->scale[j]);  // (overwritten below)
+          for (int b2 = 0; b2 < p.n_bands; ++b2) {
+            const int lo = __ldg(&p.tab->band_lo[b2]), hi = __ldg(&p.tab->band_hi[b2]);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += (j >= lo && j < hi) ? ore[j] : 0.f;
+            out[b2] = sum;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          ore[j] = nre[j];
+          oim[j] = nim[j];
+          nre[j] = nim[j] = 0.f;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace bp
 }  // namespace xm
 
@@ -348,13 +627,48 @@ int xm_bandpower_dft_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_s
   if (rc == XM_OK) rc = encode_tmap(&mh, th, 32, 64, 0);
   if (rc == XM_OK) rc = encode_tmap(&ml, tl, 32, 64, 0);
   if (rc != XM_OK) return rc;
-  cudaError_t e = cudaFuncSetAttribute(bp::bandpower_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bp::kSmem);
+  // half-overlapping windows on 64-sample-aligned lengths: the overlap kernel (XM_BP_DFT_KERNEL=1 keeps v1 for A/B runs)
+  static const bool force_v1 = [] { const char* e = getenv("XM_BP_DFT_KERNEL"); return e != nullptr && e[0] == '1'; }();
+  const bool overlap = !force_v1 && win % 64 == 0 && hop * 2 == win && n_win >= 2;
+  cudaError_t e;
+  if (!overlap) {
+    const int ctas = (int)(p.items < kNumSMs ? p.items : kNumSMs);
+    e = cudaFuncSetAttribute(bp::bandpower_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bp::kSmem);
+    if (e == cudaSuccess) bp::bandpower_dft_kernel<<<ctas, bp::kThreads, bp::kSmem, st>>>(mx, mh, ml, p);
+  } else {
+    bp::Params2 q{};
+    q.C = (int)C;
+    q.n_win = (int)n_win;
+    q.HB = KB / 2;
+    static const int max_chunk = [] { const char* c = getenv("XM_BP_CHUNK"); const int v = c ? atoi(c) : 16; return v < 1 ? 1 : v; }();  // A/B knob
+    q.chunks_per_seg = (q.HB + max_chunk - 1) / max_chunk;
+    q.chunk_len = (q.HB + q.chunks_per_seg - 1) / q.chunks_per_seg;
+    q.chunks_per_seg = (q.HB + q.chunk_len - 1) / q.chunk_len;
+    q.n_bands = n_bands;
+    q.ct = p.ct;
+    // windows per item: every item pays one extra hop, and the items should fill the 148 CTAs' rounds evenly
+    long long best_cost = -1;
+    for (int w = 4; w <= 64; ++w) {
+      const int wpi = (int)(n_win < w ? n_win : w);
+      const long long ipr = (n_win + wpi - 1) / wpi, items = n_rec * p.ct * ipr;
+      const long long rounds = (items + kNumSMs - 1) / kNumSMs, cost = rounds * (wpi + 1);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        q.wpi = wpi;
+      }
+    }
+    q.ipr = (int)((n_win + q.wpi - 1) / q.wpi);
+    q.items = n_rec * q.ct * q.ipr;
+    q.tab = tab;
+    q.power = power;
+    const int ctas = (int)(q.items < kNumSMs ? q.items : kNumSMs);
+    e = cudaFuncSetAttribute(bp::bandpower_dft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bp::kSmem2);
+    if (e == cudaSuccess) bp::bandpower_dft2_kernel<<<ctas, bp::kThreads2, bp::kSmem2, st>>>(mx, mh, ml, q);
+  }
   if (e != cudaSuccess) {
     g_last_cuda_error = (int)e;
     return XM_ERR_LAUNCH;
   }
-  const int ctas = (int)(p.items < kNumSMs ? p.items : kNumSMs);
-  bp::bandpower_dft_kernel<<<ctas, bp::kThreads, bp::kSmem, st>>>(mx, mh, ml, p);
   return check_launch();
 }
 

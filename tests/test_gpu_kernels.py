@@ -296,6 +296,9 @@ def test_window_index_gather_bandpower(ops, R, C, n, win, hop, nfft, fs):
 @pytest.mark.parametrize("R,C,n,win,hop,nfft,fs", [
     (2, 128, 8192, 1024, 512, 1024, 1000.0), (1, 64, 4096, 1000, 500, 1024, 1000.0), (2, 130, 4096, 512, 256, 512, 500.0),
     (1, 96, 2048, 256, 128, 256, 250.0), (3, 8, 2000, 500, 248, 500, 500.0), (1, 128, 1024, 1024, 1024, 1024, 1000.0),
+    # half-overlapping windows (the overlap kernel): several items per recording (41 windows = 16 + 16 + 9), two windows, one
+    (1, 128, 1024 + 40 * 512, 1024, 512, 1024, 1000.0), (2, 32, 1536, 1024, 512, 1024, 1000.0), (2, 64, 1024, 1024, 512, 1024, 1000.0),
+    (3, 200, 128 + 16 * 64, 128, 64, 128, 250.0),
 ])
 def test_bandpower_tensor_core_dft(ops, R, C, n, win, hop, nfft, fs):
     """The DFT-as-GEMM band-power kernel (3-pass tf32 with the split samples in tensor memory) against the fp64
