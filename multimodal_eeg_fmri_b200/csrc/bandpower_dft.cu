@@ -311,7 +311,7 @@ bandpower_dft_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // Columns: [0, 64) older window x Thi, [64, 128) newer window x Thi, [128, 192) older x Tlo, [192, 256) newer x Tlo.
 // The lo products go to an accumulator of their own (columns [320, 448)): they are 2^-11 of the sums, so their accumulation
 // error is irrelevant, and keeping them out of the main accumulator halves ITS accumulation steps -- the tensor core
-// truncates at every step, which is this path's error floor (measured max relative error against the fp64 oracle,
+// truncates at every step, which is this path's error floor (measured max relative error against a float64 computation,
 // tools/bp_err.py: v1 4.7e-6; here 4.6e-6 with one drain per hop of 16 blocks, 2.5e-6 with XM_BP_CHUNK=8 at -3 % speed).
 // Four epilogue warps drain the accumulators at every chunk end (a hop, or `XM_BP_CHUNK` blocks) and keep the two live
 // windows' partial sums in registers (setmaxnreg: 232 registers for them, 64 / 112 for the other roles -- with one budget
