@@ -423,26 +423,21 @@ def run_ours(args):
     loss = float(loss_t)
 
     # ---- strong scaling (SURVEY.md section 8e as written): the GLOBAL batch stays 4096, rank r holds 4096 / N rows
-    strong = None
+    strong = strong_inputs = None
     if world > 1 and B % world == 0:
         Bs = B // world
         sh = [t.to(dev) for t in make_inputs(Bs, rank * Bs)]
         for _ in range(3):
             trainer.step(*sh)
         ms_s = _timed(lambda: trainer.step(*sh), args.steps, barrier, dev, world) / args.steps
+        strong_inputs = sh
         strong = {"global_batch": B, "per_gpu_batch": Bs, "ms_per_step": round(ms_s, 3), "value": round(B / (ms_s * 1e-3), 1),
                   "unit": UNIT, "scaling": "strong", "note": "same global batch as the 1-GPU line; in-GEMM peer reads for per-GPU batch <= 512"}
-        del sh
     peak_mem = torch.cuda.max_memory_allocated()
-    del devt
     torch.cuda.empty_cache()
 
     hbm, tc_burst, tc_sus, src = _peaks()
     extras = _extras(dev, rank, world, barrier, hbm) if not args.no_extras else {}
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     kernels = {}
     for name, (n, ms, fl, by) in sorted(timeline.items(), key=lambda kv: -kv[1][1]):
         kernels[name] = {"calls_per_step": n / tl_steps, "ms_per_step": round(ms / tl_steps, 4),
@@ -477,44 +472,90 @@ def run_ours(args):
                      "floor_ms_tf32_rate": round(floor_tf32, 3), "frac_of_bf16_floor": round(floor_bf16 / ms_step, 4),
                      "frac_of_tf32_floor": round(floor_tf32 / ms_step, 4),
                      "note": "SURVEY 8d work per step over the measured sustained tensor rate; the path computes in tf32 (half the bf16 rate)"}
+    def make_line(cpu=None, eager=None, graphed=None):
+      line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+              "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+              "data": "synthetic",
+              "config": {"workload": f"paired bridge training step (BASELINE config 4), per-GPU batch {B}, global batch {B * world}, "
+                                     f"{args.encoder} ERP encoder + fMRIFusionNet + bridge projections + symmetric InfoNCE (global negatives), "
+                                     "backward, grad all-reduce, clip 1.0, AdamW",
+                         **SHAPE, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                         "connectivity": ("derived on the device from the ROI series (per-sample corrcoef, xm_roi_corrcoef_f32)" if derive
+                                          else "precomputed per sample, shipped from the host"),
+                         "l2": f"inputs {h2d / 1e6:.0f} MB per step and >10 GB of activations per step, far larger than the 126 MB L2 (no flush needed)",
+                         "final_loss": round(loss, 5)},
+              "clocks": clocks.summary(),
+              "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                      "ms_per_step": round(ms_e2e / args.e2e_steps, 3), "steps": args.e2e_steps},
+              "gpu_launches": launches,
+              "roofline": roofline,
+              "step_roofline": step_roofline,
+              "peak_device_memory_gb": round(peak_mem / 2 ** 30, 2),
+              "branch_overlap": bool(overlap),
+              "instrumented_pass": {"ms_per_step": round(ms_serial, 3), "steps": tl_steps, "own_kernels_ms_per_step": round(ours_ms, 3),
+                                    "torch_ops_ms_per_step": round(ms_serial - ours_ms, 3),
+                                    "note": "branches serialised, CUDA events around every C-ABI call: source of `kernels` and `roofline`"},
+              "kernels": kernels}
+      if strong is not None:
+          line["strong_scaling"] = strong
+      if extras:
+          line["extras"] = extras
+      if eager is not None:
+          line["torch_eager_gpu"] = eager
+      if cpu is not None:
+          line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+      if graphed is not None:
+          line["graphed_step"] = graphed
+      return line
+
+    # ---- the same step as ONE CUDA-graph launch (PairedTrainer.capture; replays equal eager steps bit for bit, also data
+    # parallel: tests/test_gpu_graphed_step.py, tests/dp_graph_check.py).  `value` above stays the eager call; this block is
+    # measured last on every rank, under a watchdog: should a capture or replay ever hang, rank 0 still prints the line.
+    import threading
+
+    def on_timeout():
+        if rank == 0:
+            print(json.dumps(make_line(graphed={"error": "timed out (watchdog)"})), flush=True)
+        os._exit(0)
+
+    graphed = None
+    if not args.no_graph:
+        watchdog = threading.Timer(240.0, on_timeout)
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            g = trainer.capture(*devt)
+            for _ in range(3):
+                g.replay()
+            ms_g = _timed(g.replay, args.steps, barrier, dev, world) / args.steps
+            graphed = {"ms_per_step": round(ms_g, 3), "value": round(world * B / (ms_g * 1e-3), 1), "unit": UNIT, "scaling": "weak",
+                       "c_abi_calls_captured": g.launches_captured, "graph_launches_per_step": 1,
+                       "note": "device-resident inputs, same per-GPU batch as `value`"}
+            del g
+            if strong_inputs is not None:
+                gs = trainer.capture(*strong_inputs)
+                for _ in range(3):
+                    gs.replay()
+                ms_gs = _timed(gs.replay, args.steps, barrier, dev, world) / args.steps
+                graphed["strong_scaling"] = {"global_batch": B, "per_gpu_batch": B // world, "ms_per_step": round(ms_gs, 3),
+                                             "value": round(B / (ms_gs * 1e-3), 1), "unit": UNIT}
+                del gs
+        except Exception as exc:  # noqa: BLE001 - an extra: never costs the line
+            graphed = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        watchdog.cancel()
+    del devt, strong_inputs
+    torch.cuda.empty_cache()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     cpu = eager = None
     if world == 1 and not args.no_cpu:
         cpu = cpu_reference_run(args.cpu_steps, 1, _cpu_batch(args.cpu_batch), max_seconds=30.0, derive_conn=derive)
     if world == 1 and not args.no_eager:
         free = torch.cuda.mem_get_info(dev)[0]
         eager = _torch_eager_gpu(dev, B if free > 150e9 else B // 4, derive, barrier)
-    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
-            "data": "synthetic",
-            "config": {"workload": f"paired bridge training step (BASELINE config 4), per-GPU batch {B}, global batch {B * world}, "
-                                   f"{args.encoder} ERP encoder + fMRIFusionNet + bridge projections + symmetric InfoNCE (global negatives), "
-                                   "backward, grad all-reduce, clip 1.0, AdamW",
-                       **SHAPE, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "connectivity": ("derived on the device from the ROI series (per-sample corrcoef, xm_roi_corrcoef_f32)" if derive
-                                        else "precomputed per sample, shipped from the host"),
-                       "l2": f"inputs {h2d / 1e6:.0f} MB per step and >10 GB of activations per step, far larger than the 126 MB L2 (no flush needed)",
-                       "final_loss": round(loss, 5)},
-            "clocks": clocks.summary(),
-            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": round(ms_e2e / args.e2e_steps, 3), "steps": args.e2e_steps},
-            "gpu_launches": launches,
-            "roofline": roofline,
-            "step_roofline": step_roofline,
-            "peak_device_memory_gb": round(peak_mem / 2 ** 30, 2),
-            "branch_overlap": bool(overlap),
-            "instrumented_pass": {"ms_per_step": round(ms_serial, 3), "steps": tl_steps, "own_kernels_ms_per_step": round(ours_ms, 3),
-                                  "torch_ops_ms_per_step": round(ms_serial - ours_ms, 3),
-                                  "note": "branches serialised, CUDA events around every C-ABI call: source of `kernels` and `roofline`"},
-            "kernels": kernels}
-    if strong is not None:
-        line["strong_scaling"] = strong
-    if extras:
-        line["extras"] = extras
-    if eager is not None:
-        line["torch_eager_gpu"] = eager
-    if cpu is not None:
-        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(make_line(cpu, eager, graphed)), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -550,6 +591,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the torch_eager_gpu baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (1, 2, 3, 5)")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay block (`graphed_step`)")
     ap.add_argument("--conn", default="device", choices=["device", "host"],
                     help="connectivity features: derived on the device from the ROI series | precomputed, shipped from the host")
     args = ap.parse_args()

@@ -330,7 +330,8 @@ int xm_peer_gather_f32(const void* const* src_peers, int n_peers, int64_t elems_
  * all equal seq, and writes out[i] = sum over r of slot_data[r * row_stride + i] (rank order: identical on all ranks).
  * The caller rotates >= 2 slots per channel and increases seq by one per call of the channel (seq > 0; flags start
  * at 0); calls of one channel are issued in the same order on every rank.  A peer that never arrives poisons the
- * result with NaN after ~10 s instead of hanging the device. */
+ * result with NaN after ~10 s instead of hanging the device.  The number actually published is seq + (seed epoch << 32)
+ * (xm_seed_epoch_*): a call captured in a CUDA graph stays distinct from replay to replay; seq itself must be < 2^32. */
 int xm_peer_allreduce_f64(const double* x, double* out, int64_t n, const void* const* data_dst, const void* const* flag_dst,
                           int n_peers, const double* slot_data, const uint64_t* slot_flags, int64_t row_stride, uint64_t seq,
                           void* stream);
@@ -454,7 +455,7 @@ int xm_clip_adamw_dev_f32(float* p, float* g, float* m, float* v, int64_t n, con
  * folds a device-resident 64-bit epoch into every hash: masks = f(seed + epoch * odd constant, element).  The epoch is 0
  * (seeds used as passed) until these entry points change it.
  * xm_seed_epoch_init: allocates the counter on the current device (call once, outside stream capture).
- * xm_seed_epoch_advance: epoch += 1 on `stream` -- one kernel node + six 8-byte device-to-device copies, capturable:
+ * xm_seed_epoch_advance: epoch += 1 on `stream` -- one kernel node + seven 8-byte device-to-device copies, capturable:
  * placed first in a captured step, every replay draws fresh masks, identical in its forward and backward.
  * xm_seed_epoch_set / _get: set (on `stream`) / read back (synchronous) the epoch, for tests and eager replays. */
 int xm_seed_epoch_init(void);

@@ -165,11 +165,12 @@ void* xm_seed_epoch_slot_bridge_head();
 void* xm_seed_epoch_slot_attention_general();
 void* xm_seed_epoch_slot_attention_fused();
 void* xm_seed_epoch_slot_ffn_fused();
+void* xm_seed_epoch_slot_peer_exchange();
 }
 
 namespace xm {
 namespace opt {
-constexpr int kEpochSlots = 6;
+constexpr int kEpochSlots = 7;
 struct EpochState {
   unsigned long long* counter = nullptr;
   void* slots[kEpochSlots] = {};
@@ -187,7 +188,8 @@ static int epoch_ready() {
   if (g_epoch.counter != nullptr) return dev == g_epoch.device ? XM_OK : XM_ERR_INVALID;  // one GPU per process
   void* (*const get[kEpochSlots])() = {xm_seed_epoch_slot_elementwise,        xm_seed_epoch_slot_transformer,
                                        xm_seed_epoch_slot_bridge_head,        xm_seed_epoch_slot_attention_general,
-                                       xm_seed_epoch_slot_attention_fused,    xm_seed_epoch_slot_ffn_fused};
+                                       xm_seed_epoch_slot_attention_fused,    xm_seed_epoch_slot_ffn_fused,
+                                       xm_seed_epoch_slot_peer_exchange};
   for (int i = 0; i < kEpochSlots; ++i)
     if ((g_epoch.slots[i] = get[i]()) == nullptr) return XM_ERR_LAUNCH;
   if (cudaMalloc(&g_epoch.counter, sizeof(unsigned long long)) != cudaSuccess) return XM_ERR_LAUNCH;

@@ -39,6 +39,9 @@ peer_allreduce_kernel(const double* __restrict__ x, double* __restrict__ out, in
                       unsigned long long seq) {
   __shared__ int timed_out;
   if (threadIdx.x == 0) timed_out = 0;
+  // A captured launch replays with its frozen `seq`; the device-resident seed epoch (xm_seed_epoch_advance, one step per
+  // replay on every rank) keeps the published numbers distinct: replay k of the call publishes seq + k * 2^32.
+  seq += xm_seed_epoch_c << 32;
   for (int p = 0; p < world; ++p)
     for (int i = threadIdx.x; i < n; i += blockDim.x) pp.data_dst[p][i] = x[i];
   __threadfence_system();
@@ -65,6 +68,8 @@ peer_allreduce_kernel(const double* __restrict__ x, double* __restrict__ out, in
 
 }  // namespace peer
 }  // namespace xm
+
+XM_DEFINE_SEED_EPOCH_SLOT(peer_exchange)
 
 using namespace xm;
 

@@ -144,6 +144,12 @@ class _PeerReduce:
         return out.view_as(t)
 
 
+def peer_exchange_counts() -> dict:
+    """{channel: calls issued so far} of the SyncBN peer exchange (empty when it is not in use)."""
+    st = _PeerReduce._state
+    return dict(st["seq"]) if st is not None else {}
+
+
 def _allreduce_sum(t: torch.Tensor) -> torch.Tensor:
     if _CTX.peer_memory and t.is_cuda:
         out = _PeerReduce.reduce(t)

@@ -338,13 +338,16 @@ class GraphedStep:
         incremented by a node of the graph, `trainer.lr` is written before the replay when it changed;
       * BatchNorm running statistics and num_batches_tracked are updated by captured device operations.
     The warm-up step(s) the capture needs (lazy initialisation must not happen inside a capture) run on a copy of the
-    training state that is restored afterwards, so constructing a GraphedStep does not train.  Single process only: the
-    data-parallel exchanges pass per-call sequence numbers as kernel arguments."""
+    training state that is restored afterwards, so constructing a GraphedStep does not train.
+
+    Data parallel (one process per GPU, every rank captures and replays in lockstep): NCCL's collectives and the
+    symmetric-memory barrier are captured as they are; the SyncBN peer exchange publishes `seq + (seed epoch << 32)`, so a
+    captured call stays distinct from replay to replay (csrc/peer_exchange.cu).  Its slot rotation is frozen with the
+    capture: replays must follow each other without eager steps of the same trainer in between (checked), and a channel's
+    calls per step must not be 1 modulo the slot count (checked at capture; they are 6 and 10)."""
 
     def __init__(self, trainer: "PairedTrainer", eeg: torch.Tensor, roi_series: torch.Tensor,
                  conn: Optional[torch.Tensor] = None, warmup: int = 1):
-        if trainer.ctx.active:
-            raise ops._lib.XmodalError("GraphedStep: single-process steps only (the data-parallel step is not capturable)")
         dev = trainer.flat_param.device
         if dev.type != "cuda":
             raise ops._lib.XmodalError("GraphedStep needs a CUDA device")
@@ -355,13 +358,14 @@ class GraphedStep:
                     for t in (eeg, roi_series, conn)]
         args = [t for t in self._in if t is not None]
         cur = torch.cuda.current_stream(dev)
+        self._stream = torch.cuda.Stream(dev)  # warm-up AND capture run here (the peer exchange keys its channels by stream)
         # -- warm-up on a snapshot of the training state
         model = trainer.model
         saved = {k: v.clone() for k, v in model.state_dict().items()}
         moments = (trainer.exp_avg.clone(), trainer.exp_avg_sq.clone())
         count, seeds = trainer.step_count, XF.seed_state()
         epoch = ops.seed_epoch_get()
-        side = torch.cuda.Stream(dev)
+        side = self._stream
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(max(int(warmup), 1)):
@@ -383,11 +387,18 @@ class GraphedStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         launches = ops.launch_count()
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        before = XF.peer_exchange_counts()
+        with torch.cuda.graph(self.graph, stream=self._stream, capture_error_mode="thread_local"):
             ops.seed_epoch_advance()
             self._loss = trainer.step(*args)
         self.launches_captured = ops.launch_count() - launches  # C-ABI calls inside the graph
         trainer.step_count = count  # the capture ran the host side of one step, not the device side
+        self._peer_counts = XF.peer_exchange_counts()
+        for ch, n in self._peer_counts.items():
+            calls = n - before.get(ch, 0)
+            if calls % XF._PeerReduce.SLOTS == 1:
+                raise ops._lib.XmodalError(f"GraphedStep: {calls} peer exchanges per step on channel {ch}: a replay would reuse "
+                                           "the slot of its predecessor's last call")
 
     def __call__(self, eeg: torch.Tensor, roi_series: torch.Tensor, conn: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Refill the static inputs (asynchronous copies on the current stream), replay, return the loss (device scalar)."""
@@ -402,6 +413,9 @@ class GraphedStep:
 
     def replay(self) -> torch.Tensor:
         """One step on whatever the static inputs (`self.inputs`) hold."""
+        if XF.peer_exchange_counts() != self._peer_counts:
+            raise ops._lib.XmodalError("GraphedStep: eager data-parallel steps ran since the capture / the last replay; the "
+                                       "captured slot rotation of the peer exchange no longer lines up -- capture again")
         self.trainer._sync_lr()
         self.graph.replay()
         self.trainer.step_count += 1

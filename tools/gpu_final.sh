@@ -13,6 +13,7 @@ try:
     print("ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"], "loss", d["config"]["final_loss"])
     print("instrumented", d["instrumented_pass"], "clocks", d["clocks"], "launches", d["gpu_launches"])
     print("roofline", {k: d["roofline"][k] for k in ("achieved", "peak", "frac", "share_of_step")})
+    print("graphed_step", d.get("graphed_step"))
     print("cpu_baseline", d.get("cpu_baseline"))
     print("torch_eager_gpu", d.get("torch_eager_gpu"))
     print("extras", {k: (v.get("value"), v.get("ms_per_step"), v.get("graphed")) for k, v in d.get("extras", {}).items()})

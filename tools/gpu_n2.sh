@@ -11,6 +11,7 @@ try:
     d = json.loads([l for l in open("gpurun_out/n2_bench.json").read().strip().splitlines() if l.startswith("{")][-1])
     print("N=2 ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"], "loss", d["config"]["final_loss"])
     print("strong", d.get("strong_scaling"))
+    print("graphed", d.get("graphed_step"))
     print("extras", {k: v.get("value") for k, v in d.get("extras", {}).items()})
 except Exception as e:
     print("parse failed", e)
