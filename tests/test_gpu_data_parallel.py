@@ -25,3 +25,20 @@ def test_sharded_step_equals_global_batch_oracle_on_gpus():
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("dp_gpu_check")]
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert len(lines) >= 3 and all(ln.rstrip().endswith("OK") for ln in lines), "\n".join(lines)
+
+
+def test_graph_replay_of_the_sharded_step_equals_eager_steps_on_gpus():
+    """tests/dp_graph_check.py under torchrun: every rank captures its data-parallel step in a CUDA graph (peer exchanges,
+    symmetric-memory barrier, NCCL collectives inside) and three replays equal three eager steps of a twin trainer."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs on the node")
+    if os.environ.get("XM_TEST_DP_GRAPH", "1") == "0":
+        pytest.skip("disabled by XM_TEST_DP_GRAPH=0")
+    world = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29542", os.path.join(HERE, "dp_graph_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=os.path.dirname(HERE))
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("dp_graph_check")]
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert len(lines) >= 2 and all(ln.rstrip().endswith("OK") for ln in lines), "\n".join(lines)
