@@ -79,6 +79,51 @@ __global__ void window_gather_nwc_kernel(const float* __restrict__ rec, long lon
   }
 }
 
+// Vectorised channels-last gather: a CTA transposes a (32 channels x 128 samples) tile through shared memory -- 512-B
+// row segments in (one float4 per lane), whole 128-B channel segments out (float4 stores; the [hi | lo] split writes two
+// of them).  The scalar 32 x 32 kernel above moved 4 bytes per thread and instruction and ran at 3.1 TB/s.
+__global__ void __launch_bounds__(256)
+window_gather_nwc_v4_kernel(const float* __restrict__ rec, long long C, long long n_samples, long long n_win, long long win,
+                            long long hop, float* __restrict__ out, long long ld_out, int round_out) {
+  __shared__ float tile[32][129];  // row stride 129: bank = (channel + sample) mod 32 in both phases
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long g = blockIdx.x;
+  const long long r = g / n_win, w = g - r * n_win;
+  const long long t0 = blockIdx.y * 128ll, c0 = blockIdx.z * 32ll;
+  const float* src = rec + (r * C) * n_samples + w * hop + t0;
+#pragma unroll
+  for (int j = warp; j < 32; j += 8) {  // channel row j of the tile: 128 samples = 32 lanes x float4
+    const long long c = c0 + j, t = t0 + 4 * lane;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C && t < win) v = *reinterpret_cast<const float4*>(src + c * n_samples + 4 * lane);  // win % 4 == 0: all or nothing
+    tile[j][4 * lane + 0] = v.x;
+    tile[j][4 * lane + 1] = v.y;
+    tile[j][4 * lane + 2] = v.z;
+    tile[j][4 * lane + 3] = v.w;
+  }
+  __syncthreads();
+  const int cq = lane & 7, tq = lane >> 3;  // 8 lanes x float4 = the tile's 32 channels of one sample; 4 samples per warp pass
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tt = warp * 16 + i * 4 + tq;  // warp covers samples [16 warp, 16 warp + 16)
+    const long long t = t0 + tt, c = c0 + 4 * cq;
+    if (t < win && c < C) {  // C % 4 == 0: all or nothing
+      float4 v = make_float4(tile[4 * cq + 0][tt], tile[4 * cq + 1][tt], tile[4 * cq + 2][tt], tile[4 * cq + 3][tt]);
+      float* o = out + (g * win + t) * ld_out + c;
+      if (round_out == 2) {
+        const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+        *reinterpret_cast<float4*>(o) = hi;
+        *reinterpret_cast<float4*>(o + C) = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z),
+                                                        round_tf32(v.w - hi.w));
+      } else {
+        if (round_out) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+        *reinterpret_cast<float4*>(o) = v;
+      }
+    }
+  }
+}
+
+
 // Ping-pong Stockham passes: pass p gathers from one per-warp buffer (pass 0: from global,
 // applying the taper and the zero padding) and scatters to the other, so a pass with more than
 // 32 butterflies never overwrites a source another lane group still has to read.
@@ -303,6 +348,14 @@ int xm_window_gather_f32(const float* rec, int64_t n_rec, int64_t C, int64_t n_s
   if (channels_last) {
     if (ld_out < (round_tf32 == 2 ? 2 * C : C)) return XM_ERR_INVALID;
     if (G > 2147483647ll || ceil_div(win, 32) > 65535 || ceil_div(C, 32) > 65535) return XM_ERR_UNSUPPORTED;
+    const bool v4 = ((n_samples | win | C | ld_out) & 3) == 0 && (n_win == 1 || (hop & 3) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(rec) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (v4) {
+      dim3 grid4((unsigned)G, ceil_div(win, 128), ceil_div(C, 32));
+      window_gather_nwc_v4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(rec, C, n_samples, n_win, win, hop, out, ld_out,
+                                                                           round_tf32);
+      return check_launch();
+    }
     dim3 grid((unsigned)G, ceil_div(win, 32), ceil_div(C, 32));
     window_gather_nwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rec, C, n_samples, n_win, win, hop, out, ld_out,
                                                                      round_tf32);
