@@ -93,3 +93,18 @@ def test_aggregate_rejects_unknown_method():
     from multimodal_eeg_fmri_b200 import fmri_utils
     with pytest.raises(ValueError):
         fmri_utils.aggregate_roi_timeseries(torch.zeros(1, 2, 3), "median")
+
+
+def test_dropout_seed_stream_can_be_saved_and_restored():
+    """functional.seed_state / set_seed_state: the host seeds a CUDA-graph capture freezes can be re-drawn (the eager twin
+    of a replay, tests/test_gpu_graphed_step.py) and a warm-up step leaves the stream where it was."""
+    from multimodal_eeg_fmri_b200 import functional as XF
+    XF.manual_seed(1234)
+    first = [XF.next_seed() for _ in range(3)]
+    state = XF.seed_state()
+    later = [XF.next_seed() for _ in range(4)]
+    XF.set_seed_state(state)
+    assert [XF.next_seed() for _ in range(4)] == later
+    XF.manual_seed(1234)
+    assert [XF.next_seed() for _ in range(3)] == first
+    assert len(set(first + later)) == 7 and all(0 < s < 2 ** 63 for s in first + later)
