@@ -48,6 +48,62 @@ __global__ void roi_meanstd_kernel(const float* __restrict__ x, long long TR, lo
   out[b * 2 * ROI + ROI + r] = sqrtf(q / (float)TR);
 }
 
+// Vectorised variant (ROI % 4 == 0, 16-B aligned): one CTA per sample, thread (c, g) owns the float4 of ROIs 4c..4c+3 and
+// the TRs g, g + G, ...; the G partial sums per column meet in shared memory.  Both passes (mean, then the centred sum
+// of squares, as the reference's two-pass std) read 128-bit words; the second pass hits in L1 / L2.  The scalar kernel
+// above moved 4 bytes per thread and instruction with 72 of 128 threads of its second block idle at ROI = 200 (1.9 TB/s).
+constexpr int kRoiThreads = 256;
+__global__ void __launch_bounds__(kRoiThreads)
+roi_meanstd_v4_kernel(const float* __restrict__ x, int TR, int ROI4, int G, float* __restrict__ out) {
+  extern __shared__ float4 part[];  // [G][ROI4]
+  const int c = threadIdx.x % ROI4, g = threadIdx.x / ROI4;
+  const long long b = blockIdx.x;
+  const float4* base = reinterpret_cast<const float4*>(x) + b * (long long)TR * ROI4 + c;
+  const bool active = g < G;
+  auto clean = [](float4 v) {
+    return make_float4(v.x != v.x ? 0.f : v.x, v.y != v.y ? 0.f : v.y, v.z != v.z ? 0.f : v.z, v.w != v.w ? 0.f : v.w);
+  };
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+#pragma unroll 4
+    for (int t = g; t < TR; t += G) {
+      const float4 v = clean(base[(long long)t * ROI4]);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    part[g * ROI4 + c] = s;
+  }
+  __syncthreads();
+  float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < G; ++i) {  // every thread folds its column's partials in the same order
+    const float4 p = part[i * ROI4 + c];
+    mean.x += p.x; mean.y += p.y; mean.z += p.z; mean.w += p.w;
+  }
+  const float inv = 1.0f / (float)TR;
+  mean.x *= inv; mean.y *= inv; mean.z *= inv; mean.w *= inv;
+  __syncthreads();
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+#pragma unroll 4
+    for (int t = g; t < TR; t += G) {
+      const float4 v = clean(base[(long long)t * ROI4]);
+      const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+      q.x += dx * dx; q.y += dy * dy; q.z += dz * dz; q.w += dw * dw;
+    }
+    part[g * ROI4 + c] = q;
+  }
+  __syncthreads();
+  if (g == 0) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < G; ++i) {
+      const float4 p = part[i * ROI4 + c];
+      t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out + b * 8ll * ROI4);
+    o[c] = mean;
+    o[ROI4 + c] = make_float4(sqrtf(t.x * inv), sqrtf(t.y * inv), sqrtf(t.z * inv), sqrtf(t.w * inv));
+  }
+}
+
 // ------------------------------------------------------------------ per-item z-score
 // EEG_CODE/run_training_lite.py:48-51
 __global__ void zscore_kernel(const float* __restrict__ x, long long len, float eps, float* __restrict__ out) {
@@ -1099,6 +1155,15 @@ extern "C" {
 
 int xm_roi_meanstd_f32(const float* x, int64_t B, int64_t TR, int64_t ROI, float* out, void* stream) {
   if (!x || !out || B <= 0 || TR <= 0 || ROI <= 0 || B > 65535) return XM_ERR_INVALID;
+  if (ROI % 4 == 0 && ROI / 4 <= kRoiThreads && TR < (1 << 30) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int roi4 = (int)(ROI / 4);
+    int G = kRoiThreads / roi4;
+    if (G > TR) G = (int)TR;
+    roi_meanstd_v4_kernel<<<(unsigned)B, kRoiThreads, (size_t)G * roi4 * sizeof(float4), (cudaStream_t)stream>>>(x, (int)TR, roi4, G,
+                                                                                                                 out);
+    return check_launch();
+  }
   dim3 grid(ceil_div(ROI, 128), (unsigned)B);
   roi_meanstd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, TR, ROI, out);
   return check_launch();

@@ -432,6 +432,9 @@ def test_roi_meanstd_zscore_colsum(ops):
     x = torch.randn(64, 100, 200, device="cuda")
     x[0, 3, 5] = float("nan")
     assert_close_rel(ops.roi_meanstd(x), om.roi_meanstd(x.cpu().double()), FP32, "roi mean/std")
+    for shape in ((3, 7, 12), (2, 300, 1024), (2, 9, 1028), (5, 33, 203), (4, 1, 8)):  # float4 kernel edge cases, scalar fallback
+        xs = torch.randn(*shape, device="cuda") * 2 + 0.5
+        assert_close_rel(ops.roi_meanstd(xs), om.roi_meanstd(xs.cpu().double()), FP32, f"roi mean/std {shape}", atol=1e-6)
     x = torch.randn(16, 75, 40, device="cuda") * 3 + 1
     z = ops.zscore(x).cpu()
     for i in range(16):
