@@ -208,9 +208,32 @@ struct BnActArgs {
   uint64_t seed;
 };
 
-XM_DEVICE float drop_mul(const BnActArgs& a, long long idx) {
+// Dropout mask of the BatchNorm blocks: ONE hash per group of four consecutive elements (a float4 of channels), then an
+// LCG step per element (h' = h * 747796405 + 2891336453, the stream the fused attention / FFN kernels use): element
+// idx is kept iff state (idx & 3) + 1 of the stream seeded by hash_u32(idx >> 2, seed) is >= p * 2^32.  The streaming
+// kernels around GELU are instruction-issue bound and a full hash per element was a quarter of their instructions.
+XM_DEVICE uint32_t lcg_next(uint32_t h) { return h * 747796405u + 2891336453u; }
+XM_DEVICE float drop_mul(const BnActArgs& a, long long idx) {  // scalar kernels (any C)
   if (a.drop_thresh == 0u) return 1.0f;
-  return dropout_keep((uint64_t)idx, a.seed, a.drop_thresh) ? a.drop_scale : 0.0f;
+  uint32_t h = hash_u32((uint64_t)(idx >> 2), a.seed);
+  const int j = (int)(idx & 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i <= j) h = lcg_next(h);
+  return h >= a.drop_thresh ? a.drop_scale : 0.0f;
+}
+struct Mul4 {
+  float v[4];
+};
+XM_DEVICE Mul4 drop_mul4(const BnActArgs& a, long long idx0) {  // idx0 % 4 == 0: the four elements of one float4
+  Mul4 m;
+  uint32_t h = hash_u32((uint64_t)(idx0 >> 2), a.seed);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h = lcg_next(h);
+    m.v[j] = h >= a.drop_thresh ? a.drop_scale : 0.0f;
+  }
+  return m;
 }
 
 // forward value and dz for one channel of one output position.
@@ -915,17 +938,22 @@ __global__ void bn_act_fwd_v4_kernel(const BnActArgs a, long long R_out, float* 
       const long long b = (long long)((unsigned)ro / (unsigned)To), tp = ro - b * To;  // rows < 2^31 (host-checked)
       const long long r0 = b * a.T + 2 * tp;
       const F4 x0 = ld4(a.y + r0 * a.ldy + c0), x1 = ld4(a.y + (r0 + 1) * a.ldy + c0);
+      Mul4 m0, m1;  // m0: row r0 (drop before pool) or the pooled row (drop after pool); m1: row r0 + 1
+      if (a.drop_thresh) {
+        m0 = drop_mul4(a, (a.drop_before_pool ? r0 : ro) * a.C + c0);
+        if (a.drop_before_pool) m1 = drop_mul4(a, (r0 + 1) * a.C + c0);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float a0 = act_c<ACT>(x0.v[j] * k.sc[j] + k.sh[j], a.act);
         float a1 = act_c<ACT>(x1.v[j] * k.sc[j] + k.sh[j], a.act);
         if (a.drop_thresh) {
           if (a.drop_before_pool) {
-            a0 *= drop_mul(a, r0 * a.C + c0 + j);
-            a1 *= drop_mul(a, (r0 + 1) * a.C + c0 + j);
+            a0 *= m0.v[j];
+            a1 *= m1.v[j];
             o.v[j] = fmaxf(a0, a1);
           } else {
-            o.v[j] = fmaxf(a0, a1) * drop_mul(a, ro * a.C + c0 + j);
+            o.v[j] = fmaxf(a0, a1) * m0.v[j];
           }
         } else {
           o.v[j] = fmaxf(a0, a1);
@@ -933,10 +961,12 @@ __global__ void bn_act_fwd_v4_kernel(const BnActArgs a, long long R_out, float* 
       }
     } else {
       const F4 x0 = ld4(a.y + ro * a.ldy + c0);
+      Mul4 m0;
+      if (a.drop_thresh) m0 = drop_mul4(a, ro * a.C + c0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = act_c<ACT>(x0.v[j] * k.sc[j] + k.sh[j], a.act);
-        if (a.drop_thresh) v *= drop_mul(a, ro * a.C + c0 + j);
+        if (a.drop_thresh) v *= m0.v[j];
         o.v[j] = v;
       }
     }
@@ -970,6 +1000,11 @@ XM_DEVICE void bn_dz4(const BnActArgs& a, const ChanConst& k, const float* __res
     r0 = b * a.T + 2 * tp;
     x0 = ld4(a.y + r0 * a.ldy + c0);
     x1 = ld4(a.y + (r0 + 1) * a.ldy + c0);
+    Mul4 d0, d1;
+    if (a.drop_thresh) {
+      d0 = drop_mul4(a, (a.drop_before_pool ? r0 : ro) * a.C + c0);
+      if (a.drop_before_pool) d1 = drop_mul4(a, (r0 + 1) * a.C + c0);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float z0 = x0.v[j] * k.sc[j] + k.sh[j], z1 = x1.v[j] * k.sc[j] + k.sh[j];
@@ -977,12 +1012,12 @@ XM_DEVICE void bn_dz4(const BnActArgs& a, const ChanConst& k, const float* __res
       float m0 = 1.f, m1 = 1.f, gg = g.v[j];
       if (a.drop_thresh) {
         if (a.drop_before_pool) {
-          m0 = drop_mul(a, r0 * a.C + c0 + j);
-          m1 = drop_mul(a, (r0 + 1) * a.C + c0 + j);
+          m0 = d0.v[j];
+          m1 = d1.v[j];
           a0 *= m0;
           a1 *= m1;
         } else {
-          gg *= drop_mul(a, ro * a.C + c0 + j);
+          gg *= d0.v[j];
         }
       }
       const bool first = a0 >= a1;  // ties -> first element, as torch max_pool1d
@@ -992,10 +1027,12 @@ XM_DEVICE void bn_dz4(const BnActArgs& a, const ChanConst& k, const float* __res
   } else {
     r0 = ro;
     x0 = ld4(a.y + ro * a.ldy + c0);
+    Mul4 d0;
+    if (a.drop_thresh) d0 = drop_mul4(a, ro * a.C + c0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float gg = g.v[j];
-      if (a.drop_thresh) gg *= drop_mul(a, ro * a.C + c0 + j);
+      if (a.drop_thresh) gg *= d0.v[j];
       dz0.v[j] = gg * actg_c<ACT>(x0.v[j] * k.sc[j] + k.sh[j], a.act);
       dz1.v[j] = 0.f;
       x1.v[j] = 0.f;
