@@ -265,7 +265,7 @@ def _extras(dev, rank, world, barrier, hbm):
     torch.manual_seed(42)
     m1 = ImprovedTriModalFusionNetLite(64, 64, 6048).to(dev).train()
     crit = LabelSmoothingCrossEntropy(0.1)
-    opt1 = torch.optim.AdamW(m1.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
+    opt1 = torch.optim.AdamW(m1.parameters(), lr=5e-5, weight_decay=0.01, fused=True, capturable=True)
     erp, pw, cn = torch.randn(32, 64, 500, device=dev), torch.randn(32, 64, 500, device=dev), torch.randn(32, 6048, device=dev)
     y = torch.randint(0, 2, (32,), device=dev)
 
@@ -277,8 +277,13 @@ def _extras(dev, rank, world, barrier, hbm):
     ms1 = step_time(step1)
     out["config1_lite_b32"] = {"metric": "tri-modal lite train samples/sec", "value": round(32 / (ms1 * 1e-3), 1), "unit": UNIT,
                                "batch": 32, "ms_per_step": round(ms1, 3)}
-    # (not graph-captured: the reference's lite wrapper reads its fusion weights back to the host in every forward,
-    #  crossmodal_v4_enhancements.py:803-806, and so does this one)
+    # (capturable because the wrapper's fusion weights stay on the device until somebody reads them, modules.DeviceFloats;
+    #  the reference reads five scalars back in every forward, crossmodal_v4_enhancements.py:803-806)
+    g1 = GraphedCallable(lambda *_: step1(), [pw, erp, cn, y], [m1], [opt1])
+    ms1g = step_time(g1.graph.replay)
+    out["config1_lite_b32"]["graphed"] = {"value": round(32 / (ms1g * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms1g, 3),
+                                          "c_abi_calls_captured": g1.launches_captured}
+    del g1
     # ---- config 2: run_fmri_v11 step (fMRIFusionNet 400 / 40 000, weighted CE, AdamW 1e-4, clip 1.0), batch 64
     torch.manual_seed(42)
     m2 = fMRIFusionNet(400, 40000).to(dev).train()

@@ -271,10 +271,69 @@ class HybridFusionModule(nn.Module):
         fused = XF.linear_bn_act(comb, self.late_fusion[0], self.late_fusion[1], "gelu", p, tr)
         if return_weights:
             fw = torch.softmax(self.final_gate, dim=0)
-            # one device->host transfer instead of the reference's five .item() syncs (:803-806)
-            v = torch.stack([g[:, 0].mean() * fw[0], g[:, 1].mean() * fw[0], fw[1] * self.conn_boost]).tolist()
-            return fused, {"erp_weight": v[0], "pw_weight": v[1], "conn_weight": v[2]}
+            # The reference reads five scalars back with .item() in EVERY forward (:803-806).  Here the three weights stay on
+            # the device and are read (one transfer) when somebody looks at them: the training forward never waits for
+            # the GPU, and run_training_lite's wrapper -- which asks for the weights and drops them -- can be captured in
+            # a CUDA graph.
+            with torch.no_grad():
+                t = torch.stack([g[:, 0].mean() * fw[0], g[:, 1].mean() * fw[0], fw[1] * self.conn_boost])
+            return fused, DeviceFloats(("erp_weight", "pw_weight", "conn_weight"), t)
         return fused
+
+
+class DeviceFloats(dict):
+    """A dict of Python floats whose values live in a small device tensor and are read back on access (`w["erp_weight"]`,
+    `.items()`, `dict(w)`, `==`, `repr` ...), not when the dict is made.  Under a CUDA-graph replay the tensor is static
+    memory: the dict then shows the values of the latest replay; `dict(w)` takes a snapshot."""
+
+    def __init__(self, names, tensor):
+        super().__init__((n, None) for n in names)
+        self._names, self._tensor = tuple(names), tensor
+
+    def _read(self):
+        for n, v in zip(self._names, self._tensor.tolist()):
+            dict.__setitem__(self, n, float(v))
+
+    def __getitem__(self, key):
+        self._read()
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        self._read()
+        return dict.get(self, key, default)
+
+    def __iter__(self):  # (overridden so that dict(w) / {**w} go through keys() + __getitem__ instead of copying the storage)
+        return iter(self._names)
+
+    def keys(self):
+        return list(self._names)
+
+    def items(self):
+        self._read()
+        return dict.items(self)
+
+    def values(self):
+        self._read()
+        return dict.values(self)
+
+    def copy(self):
+        return dict(self.items())
+
+    def __eq__(self, other):
+        self._read()
+        return dict.__eq__(self, other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._read()
+        return dict.__repr__(self)
+
+    def __reduce__(self):  # pickles / deep-copies as the plain dict of floats it stands for
+        return (dict, (self.copy(),))
 
 
 class EnhancedTriModalFusionNetV4Lite(nn.Module):

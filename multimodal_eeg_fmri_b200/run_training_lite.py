@@ -43,7 +43,7 @@ class ImprovedTriModalFusionNetLite(nn.Module):
     def track_fusion_weights(self):
         w = self.get_fusion_weights()
         if w:
-            self.fusion_weight_history.append(w)
+            self.fusion_weight_history.append(dict(w))  # a snapshot: the live object reads its device tensor on access
 
 
 def collate_balanced(batch):

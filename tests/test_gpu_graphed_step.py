@@ -201,3 +201,47 @@ def test_graphed_callable_replays_the_fmri_recipe():
     for (k, a), b in zip(ma.state_dict().items(), mb.state_dict().values()):
         assert torch.equal(a, b), k
     assert all(math.isfinite(v) for v in lg) and len(set(lg)) == 3  # three different steps (parameters and masks move)
+
+
+def test_lite_wrapper_is_capturable_and_its_fusion_weights_follow_the_replays():
+    """run_training_lite.py:302-328's wrapper asks for the fusion weights in every forward; they stay on the device
+    (modules.DeviceFloats), so the step (run_training_lite.py:478-489) can be captured, and get_fusion_weights() read after a
+    replay equals what the eager twin reports after the same step."""
+    from multimodal_eeg_fmri_b200 import functional as XF, ops
+    from multimodal_eeg_fmri_b200.modules import LabelSmoothingCrossEntropy
+    from multimodal_eeg_fmri_b200.run_training_lite import ImprovedTriModalFusionNetLite
+    from multimodal_eeg_fmri_b200.training import GraphedCallable
+    erp, pw, cn = torch.randn(16, 8, 64, device="cuda"), torch.randn(16, 6, 64, device="cuda"), torch.randn(16, 40, device="cuda")
+    y = torch.randint(0, 2, (16,), device="cuda")
+    crit = LabelSmoothingCrossEntropy(0.1)
+
+    def make():
+        torch.manual_seed(2)
+        m = ImprovedTriModalFusionNetLite(6, 8, 40, fusion_dim=32).cuda().train()
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.01, capturable=True)
+
+        def step(p, e, c, t):
+            opt.zero_grad(set_to_none=True)
+            loss = crit(m(p, e, c), t)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+            return loss.detach()
+        return m, opt, step
+
+    ma, oa, step_a = make()
+    mb, ob, step_b = make()
+    XF.manual_seed(6)
+    g = GraphedCallable(step_a, [pw, erp, cn, y], [ma], [oa])
+    base = XF.seed_state()[0]
+    for k in (1, 2):
+        lg = float(g(pw, erp, cn, y))
+        wg = dict(ma.get_fusion_weights())
+        XF.set_seed_state((base, 0))
+        ops.seed_epoch_set(k)
+        le = float(step_b(pw, erp, cn, y))
+        we = dict(mb.get_fusion_weights())
+        ops.seed_epoch_set(k)
+        assert lg == le and wg == we and set(wg) == {"erp_weight", "pw_weight", "conn_weight"}, (k, lg, le, wg, we)
+    for (k, a), b in zip(ma.state_dict().items(), mb.state_dict().values()):
+        assert torch.equal(a, b), k
