@@ -108,3 +108,23 @@ def test_dropout_seed_stream_can_be_saved_and_restored():
     XF.manual_seed(1234)
     assert [XF.next_seed() for _ in range(3)] == first
     assert len(set(first + later)) == 7 and all(0 < s < 2 ** 63 for s in first + later)
+
+
+def test_device_floats_reads_on_access_and_snapshots():
+    """modules.DeviceFloats: the fusion-weight dict of the lite net (crossmodal_v4_enhancements.py:803-809 returns floats)
+    reads its tensor when looked at; dict(w) / copy / pickle give plain snapshots."""
+    import copy
+    import json
+    import pickle
+    from multimodal_eeg_fmri_b200.modules import DeviceFloats
+    t = torch.tensor([0.25, 0.5, 1.25])
+    w = DeviceFloats(("erp_weight", "pw_weight", "conn_weight"), t)
+    assert w["erp_weight"] == 0.25 and w.get("conn_weight") == 1.25 and w.get("missing", 7) == 7
+    assert list(w) == ["erp_weight", "pw_weight", "conn_weight"] and len(w) == 3 and "pw_weight" in w
+    snap = dict(w)
+    assert type(snap) is dict and snap == {"erp_weight": 0.25, "pw_weight": 0.5, "conn_weight": 1.25} and w == snap
+    t[0] = 0.75  # what a graph replay does to the static tensor
+    assert w["erp_weight"] == 0.75 and snap["erp_weight"] == 0.25 and w != snap
+    assert {**w}["erp_weight"] == 0.75 and w.copy() == dict(w.items())
+    assert type(copy.deepcopy(w)) is dict and pickle.loads(pickle.dumps(w)) == dict(w)
+    assert json.loads(json.dumps(dict(w))) == dict(w) and all(isinstance(v, float) for v in w.values())
