@@ -109,6 +109,10 @@ resid_ln_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dres
     const float mu = mean[row], rs = rstd[row];
     float xh[NV][4], dz[NV][4];
     float s1 = 0.f, s2 = 0.f;
+    float4 rv4[NV];  // the residual-stream gradient is needed only after the two reductions, but its load goes out with the others
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      rv4[i] = dres != nullptr ? *reinterpret_cast<const float4*>(dres + row * D + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 128 + lane * 4;
@@ -134,10 +138,7 @@ resid_ln_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dres
       float o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = rs * (dz[i][j] - s1 - xh[i][j] * s2);
-      if (dres != nullptr) {
-        const float4 rv = *reinterpret_cast<const float4*>(dres + row * D + c);
-        o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-      }
+      o[0] += rv4[i].x; o[1] += rv4[i].y; o[2] += rv4[i].z; o[3] += rv4[i].w;
       *reinterpret_cast<float4*>(dx + row * D + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (da != nullptr) {
         float t[4];
